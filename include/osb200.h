@@ -1,0 +1,123 @@
+/* libosb200 -- C ABI of the B200-native open-speech audio hot path.
+ *
+ * The reference (will-assistant/open-speech, pure Python) has NO FFI for this path: its
+ * boundary is a set of Python callables.  Each entry point below names
+ * the reference callable (file:line under /root/reference) whose arithmetic it replaces;
+ * open_speech_b200/*.py keeps the reference's Python signatures and binds these symbols
+ * with ctypes (INTEGRATION.md shows the stub a maintainer would add).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types.
+ *   - every function returns OSB_OK (0) or a negative OSB_ERR_*; osb_last_error() gives a
+ *     thread-local message.  No exception crosses the boundary.
+ *   - `*_dev` functions take DEVICE pointers and a cudaStream_t (as void*; NULL = legacy
+ *     default stream), are asynchronous, and allocate their temporaries stream-ordered.
+ *   - `*_host` functions take HOST pointers, stage through a per-thread pinned workspace,
+ *     run the same kernels on a per-thread stream and return after the result is in the
+ *     caller's buffer.  They are re-entrant and thread-safe (per-thread stream/workspace).
+ *   - there is no CPU implementation behind any of these: without a CUDA device every
+ *     call returns OSB_ERR_NO_DEVICE.
+ */
+#ifndef OSB200_H
+#define OSB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OSB_VERSION 100 /* 0.1.0 */
+
+#define OSB_OK 0
+#define OSB_ERR_INVALID_ARG -1 /* -> ValueError   */
+#define OSB_ERR_CUDA -2        /* -> RuntimeError */
+#define OSB_ERR_NO_DEVICE -3   /* -> RuntimeError */
+#define OSB_ERR_BUFFER -4      /* -> BufferError  */
+#define OSB_ERR_UNSUPPORTED -5 /* -> RuntimeError */
+
+/* sample formats on the wire (src/realtime/audio_buffer.py:47-58) */
+#define OSB_FMT_PCM16 0
+#define OSB_FMT_ULAW 1
+#define OSB_FMT_ALAW 2
+#define OSB_FMT_F32 3
+
+/* ---------------------------------------------------------------- runtime */
+int osb_version(void);
+int osb_device_count(void);
+int osb_init(int device); /* selects the device for the calling thread; uploads constant tables */
+const char* osb_last_error(void);
+/* counts kernel launches issued by this library in this process (bench.py "gpu_launches") */
+uint64_t osb_launch_count(void);
+
+/* ---------------------------------------------------------------- G.711 + linear resample
+ * replaces audioop.ulaw2lin/alaw2lin/lin2ulaw/lin2alaw and _resample_linear as called from
+ * decode_audio_to_pcm16 / encode_pcm16_to_format (src/realtime/audio_buffer.py:20-81).
+ * Bit-exact: integer codec; np.interp arithmetic reproduced in IEEE f64 without contraction. */
+int osb_g711_decode_dev(const uint8_t* d_in, int16_t* d_out, size_t n, int law, void* stream);
+int osb_g711_encode_dev(const int16_t* d_in, uint8_t* d_out, size_t n, int law, void* stream);
+/* `batch` independent chunks, each n_in samples -> n_out samples (n_out = int(n_in*to/from),
+ * computed by the caller exactly as the reference does).  in_fmt: PCM16|ULAW|ALAW (G.711
+ * expand fused in front), out_fmt: PCM16|ULAW|ALAW (G.711 compress fused behind).
+ * Strides are in elements of the respective buffer. */
+int osb_resample_linear_dev(const void* d_in, int in_fmt, void* d_out, int out_fmt, int64_t n_in, int64_t n_out,
+                            int64_t batch, int64_t in_stride, int64_t out_stride, void* stream);
+int osb_g711_decode_host(const uint8_t* in, int16_t* out, size_t n, int law);
+int osb_g711_encode_host(const int16_t* in, uint8_t* out, size_t n, int law);
+int osb_resample_linear_host(const void* in, int in_fmt, void* out, int out_fmt, int64_t n_in, int64_t n_out,
+                             int64_t batch, int64_t in_stride, int64_t out_stride);
+
+/* ---------------------------------------------------------------- polyphase resample
+ * replaces resample_pcm16 (src/streaming.py:55-91) = scipy.signal.resample_poly(x_f32, up, down,
+ * padtype="line") + clip + truncation.  up/down already divided by their gcd.  The FIR is designed
+ * inside the library exactly as scipy does (firwin(20*max+1, 1/max, kaiser 5.0) -> f32 -> *up).
+ * n_out = ceil(n_in*up/down).  Bit-exact w.r.t. scipy's f32 tap-by-tap accumulation. */
+int osb_resample_poly_taps(int up, int down, float* taps_out, int capacity, int* n_taps);
+int osb_resample_poly_dev(const int16_t* d_in, int16_t* d_out, int64_t n_in, int64_t batch, int64_t in_stride,
+                          int64_t out_stride, int up, int down, void* stream);
+int osb_resample_poly_host(const int16_t* in, int16_t* out, int64_t n_in, int64_t batch, int64_t in_stride,
+                           int64_t out_stride, int up, int down);
+
+/* ---------------------------------------------------------------- PCM edge + gain normalise
+ * replaces wav_bytes_to_float32_mono / float32_mono_to_wav_bytes / normalize_gain
+ * (src/audio/preprocessing.py:9-42) and float32_to_int16 (src/tts/pipeline.py:32-37). */
+int osb_pcm16_to_f32_dev(const int16_t* d_in, float* d_out, size_t n, int channels, void* stream);
+int osb_f32_to_pcm16_dev(const float* d_in, int16_t* d_out, size_t n, void* stream);
+/* pcm16 [batch][stride] -> normalize_gain(target_dbfs) -> requantised pcm16 (normalize=0: requantise only) */
+int osb_normalize_gain_pcm16_dev(const int16_t* d_in, int16_t* d_out, int64_t n, int64_t batch, int64_t stride,
+                                 int normalize, float target_dbfs, void* stream);
+/* f32 -> normalize_gain -> f32 (out_pcm16=0) or requantised pcm16 (out_pcm16=1) */
+int osb_normalize_gain_f32_dev(const float* d_in, void* d_out, int out_pcm16, int64_t n, int64_t batch, int64_t stride,
+                               int normalize, float target_dbfs, void* stream);
+int osb_pcm16_to_f32_host(const int16_t* in, float* out, size_t n, int channels);
+int osb_f32_to_pcm16_host(const float* in, int16_t* out, size_t n);
+int osb_normalize_gain_pcm16_host(const int16_t* in, int16_t* out, int64_t n, int normalize, float target_dbfs);
+int osb_normalize_gain_f32_host(const float* in, void* out, int out_pcm16, int64_t n, int normalize, float target_dbfs,
+                                int* unchanged);
+
+/* ---------------------------------------------------------------- Silero VAD scoring + segmenting
+ * replaces SileroVAD.__call__ / is_speech / get_speech_segments (src/vad/silero.py:63-177): the
+ * per-window onnxruntime session.run (:86, :149) and the integer segment state machine (:133-177).
+ * Windows are raw 512-sample frames with NO 64-sample context, remainders are dropped, and the
+ * LSTM state [2][128] persists across calls -- all as the reference does.
+ * weights_host: flat f32 blob in the order of open_speech_b200/vad/silero.py WEIGHT_LAYOUT. */
+int osb_vad_create(const float* weights_host, size_t n_floats, void** handle);
+int osb_vad_destroy(void* handle);
+/* batch streams, n samples each (floor(n/512) windows); d_state [batch][2][128] in/out;
+ * d_probs [batch][probs_stride] out (one probability per window). */
+int osb_vad_score_dev(void* handle, const void* d_audio, int fmt, int64_t n, int64_t batch, int64_t stride, float* d_state,
+                      float* d_probs, int64_t probs_stride, void* stream);
+/* integer state machine on per-window probabilities: d_segments [batch][max_seg][2] (start_ms,end_ms),
+ * d_counts [batch] (may exceed max_seg: then only the first max_seg were stored). */
+int osb_vad_segments_dev(const float* d_probs, int64_t probs_stride, int64_t n_win, int64_t batch, int64_t n_samples,
+                         float threshold, int min_speech_ms, int silence_ms, int32_t* d_segments, int32_t* d_counts, int max_seg,
+                         void* stream);
+int osb_vad_score_host(void* handle, const void* audio, int fmt, int64_t n, float* state, float* probs, float* max_prob);
+int osb_vad_segments_host(void* handle, const void* audio, int fmt, int64_t n, float* state, float threshold, int min_speech_ms,
+                          int silence_ms, int32_t* segments, int max_seg, int* n_seg);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OSB200_H */

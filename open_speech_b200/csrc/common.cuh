@@ -1,0 +1,143 @@
+// Shared helpers for libosb200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/osb200.h"
+
+#define OSB_NUM_SMS 148  // B200: 2 dies x 74 SMs; grids are sized in multiples of this
+
+namespace osb {
+
+// thread-local error text (osb_last_error)
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+int ensure_init();          // lazy osb_init(current device)
+int num_sms();              // queried once; 148 on B200
+void count_launch();        // osb_launch_count bookkeeping
+
+#define OSB_LAUNCH(kern, grid, block, smem, stream, ...)              \
+    do {                                                              \
+        kern<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);     \
+        osb::count_launch();                                          \
+    } while (0)
+
+#define OSB_CUDA(expr)                                                        \
+    do {                                                                      \
+        cudaError_t _e = (expr);                                              \
+        if (_e != cudaSuccess) return osb::cuda_fail(_e, #expr, __FILE__, __LINE__); \
+    } while (0)
+
+#define OSB_CHECK_LAUNCH() OSB_CUDA(cudaGetLastError())
+
+#define OSB_REQUIRE(cond, msg)                         \
+    do {                                               \
+        if (!(cond)) {                                 \
+            osb::set_error("invalid argument: %s", msg); \
+            return OSB_ERR_INVALID_ARG;                \
+        }                                              \
+    } while (0)
+
+// Stream-ordered scratch allocation (cudaMallocAsync on the caller's stream; the
+// default mempool keeps freed blocks cached, so steady-state calls do not hit the driver).
+struct Scratch {
+    cudaStream_t s;
+    void* ptrs[16];
+    int n = 0;
+    explicit Scratch(cudaStream_t st) : s(st) {}
+    ~Scratch() {
+        for (int i = 0; i < n; ++i) cudaFreeAsync(ptrs[i], s);
+    }
+    template <typename T>
+    cudaError_t alloc(T** p, size_t count) {
+        void* q = nullptr;
+        cudaError_t e = cudaMallocAsync(&q, count * sizeof(T) + 256, s);
+        if (e == cudaSuccess) {
+            ptrs[n++] = q;
+            *p = reinterpret_cast<T*>(q);
+        }
+        return e;
+    }
+};
+
+// Host-call workspace: per-thread stream + pinned staging + device buffers.  The
+// *_host entry points copy in, launch the *_dev path, copy out and synchronise.
+struct HostWs {
+    cudaStream_t stream = nullptr;
+    void* pin[2] = {nullptr, nullptr};
+    size_t pin_cap[2] = {0, 0};
+    void* dev[4] = {nullptr, nullptr, nullptr, nullptr};
+    size_t dev_cap[4] = {0, 0, 0, 0};
+    int device = -1;
+    int prepare();
+    int dev_buf(int slot, size_t bytes, void** out);
+    int pin_buf(int slot, size_t bytes, void** out);
+    int h2d(void* d, const void* h, size_t bytes);   // through pinned staging when it fits
+    int d2h(void* h, const void* d, size_t bytes);   // synchronises the stream
+    int sync();
+};
+HostWs& host_ws();
+
+static inline int grid_for(size_t work_items, int per_block, int max_waves = 8) {
+    size_t b = (work_items + per_block - 1) / per_block;
+    size_t cap = (size_t)OSB_NUM_SMS * max_waves;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+
+}  // namespace osb
+
+// ------------------------------------------------------------------ device helpers
+#ifdef __CUDACC__
+namespace osb {
+
+__device__ __forceinline__ uint4 ld_stream_u4(const void* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void st_stream_u4(void* p, const uint4& v) {
+    asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};"
+                 :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint2 ld_stream_u2(const void* p) {
+    uint2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+    return r;
+}
+
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ int warp_min_i(int v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ int warp_max_i(int v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// clip to [-1,1], *32767, truncate toward zero  (src/audio/preprocessing.py:24-25,
+// src/tts/pipeline.py:32-37).  NaN -> 0 like a saturating cvt; the reference never feeds NaN.
+__device__ __forceinline__ int quant_pcm16(float x) {
+    x = fminf(fmaxf(x, -1.0f), 1.0f);
+    return __float2int_rz(__fmul_rn(x, 32767.0f));
+}
+
+}  // namespace osb
+#endif

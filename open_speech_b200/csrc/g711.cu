@@ -1,0 +1,292 @@
+// G.711 mu-law / A-law <-> PCM16 and the realtime path's linear resampler.
+//
+// Replaces (reference file:line):
+//   audioop.ulaw2lin / alaw2lin / lin2ulaw / lin2alaw   src/realtime/audio_buffer.py:52,55,76,79
+//   _resample_linear (np.interp over linspace grids)    src/realtime/audio_buffer.py:20-34
+//
+// HBM-bound byte movers: 128-bit loads/stores, closed-form codec arithmetic (no table, so no
+// divergent constant-cache or shared-memory bank traffic), grid = multiple of 148 CTAs.
+// The interpolation is IEEE f64 with explicit _rn intrinsics so that nvcc cannot contract
+// mul+add into an FMA: numpy's arr_interp computes slope*(x-xp[i]) + fp[i] as two roundings.
+#include "common.cuh"
+
+namespace osb {
+
+__device__ __forceinline__ int ulaw2lin(uint32_t b) {
+    uint32_t u = ~b & 0xFFu;
+    int t = (int)(((u & 0x0Fu) << 3) + 0x84u);
+    t <<= (u & 0x70u) >> 4;
+    return (u & 0x80u) ? (0x84 - t) : (t - 0x84);
+}
+
+__device__ __forceinline__ int alaw2lin(uint32_t b) {
+    uint32_t a = (b ^ 0x55u) & 0xFFu;
+    int t = (int)((a & 0x0Fu) << 4);
+    int seg = (int)((a & 0x70u) >> 4);
+    t = (seg == 0) ? (t + 8) : ((seg == 1) ? (t + 0x108) : ((t + 0x108) << (seg - 1)));
+    return (a & 0x80u) ? t : -t;
+}
+
+// audioop.lin2ulaw(width=2): st_14linear2ulaw(sample >> 2)
+__device__ __forceinline__ uint32_t lin2ulaw(int s) {
+    int v = s >> 2;
+    uint32_t mask = 0xFFu;
+    if (v < 0) { v = -v; mask = 0x7Fu; }
+    v = min(v, 8159) + 0x21;
+    int seg = max(0, 26 - __clz(v));  // first i with v <= (0x40<<i)-1
+    if (seg >= 8) return 0x7Fu ^ mask;
+    uint32_t uval = (uint32_t)(seg << 4) | ((uint32_t)(v >> (seg + 1)) & 0xFu);
+    return uval ^ mask;
+}
+
+// audioop.lin2alaw(width=2): st_linear2alaw(sample >> 3)
+__device__ __forceinline__ uint32_t lin2alaw(int s) {
+    int v = s >> 3;
+    uint32_t mask = 0xD5u;
+    if (v < 0) { mask = 0x55u; v = -v - 1; }
+    int seg = (v == 0) ? 0 : max(0, 27 - __clz(v));  // first i with v <= (0x20<<i)-1
+    uint32_t aval = (uint32_t)(seg << 4) | ((uint32_t)((seg < 2) ? (v >> 1) : (v >> seg)) & 0xFu);
+    return aval ^ mask;
+}
+
+template <int LAW>
+__device__ __forceinline__ int expand(uint32_t b) { return LAW == OSB_FMT_ULAW ? ulaw2lin(b) : alaw2lin(b); }
+template <int LAW>
+__device__ __forceinline__ uint32_t compress(int s) { return LAW == OSB_FMT_ULAW ? lin2ulaw(s) : lin2alaw(s); }
+
+// ---------------------------------------------------------------- flat decode / encode
+template <int LAW>
+__global__ void __launch_bounds__(256) k_g711_decode(const uint8_t* __restrict__ in, int16_t* __restrict__ out, size_t n) {
+    size_t nvec = n / 16;
+    size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nthr = (size_t)gridDim.x * blockDim.x;
+    for (size_t v = tid; v < nvec; v += nthr) {
+        uint4 w = ld_stream_u4(in + v * 16);
+        uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+        uint32_t o[8];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            int s0 = expand<LAW>(ws[k] & 0xFF), s1 = expand<LAW>((ws[k] >> 8) & 0xFF);
+            int s2 = expand<LAW>((ws[k] >> 16) & 0xFF), s3 = expand<LAW>(ws[k] >> 24);
+            o[2 * k] = (uint32_t)(s0 & 0xFFFF) | ((uint32_t)s1 << 16);
+            o[2 * k + 1] = (uint32_t)(s2 & 0xFFFF) | ((uint32_t)s3 << 16);
+        }
+        st_stream_u4(out + v * 16, make_uint4(o[0], o[1], o[2], o[3]));
+        st_stream_u4(out + v * 16 + 8, make_uint4(o[4], o[5], o[6], o[7]));
+    }
+    for (size_t i = nvec * 16 + tid; i < n; i += nthr) out[i] = (int16_t)expand<LAW>(in[i]);
+}
+
+template <int LAW>
+__global__ void __launch_bounds__(256) k_g711_encode(const int16_t* __restrict__ in, uint8_t* __restrict__ out, size_t n) {
+    size_t nvec = n / 16;
+    size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nthr = (size_t)gridDim.x * blockDim.x;
+    for (size_t v = tid; v < nvec; v += nthr) {
+        uint4 a = ld_stream_u4(in + v * 16), b = ld_stream_u4(in + v * 16 + 8);
+        uint32_t ws[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            uint32_t w0 = ws[2 * k], w1 = ws[2 * k + 1];
+            o[k] = compress<LAW>((int)(int16_t)(w0 & 0xFFFF)) | (compress<LAW>((int)(int16_t)(w0 >> 16)) << 8) |
+                   (compress<LAW>((int)(int16_t)(w1 & 0xFFFF)) << 16) | (compress<LAW>((int)(int16_t)(w1 >> 16)) << 24);
+        }
+        st_stream_u4(out + v * 16, make_uint4(o[0], o[1], o[2], o[3]));
+    }
+    for (size_t i = nvec * 16 + tid; i < n; i += nthr) out[i] = (uint8_t)compress<LAW>((int)in[i]);
+}
+
+// ---------------------------------------------------------------- linear resample (np.interp)
+struct LinArgs {
+    const void* in;
+    void* out;
+    long long n_in, n_out, batch, in_stride, out_stride;
+    double step_o, step_n;  // 1/(n_in-1), 1/(n_out-1) formed in f64 on the host like np.linspace
+};
+
+template <int IN_FMT>
+__device__ __forceinline__ int load_in(const void* base, long long idx) {
+    if (IN_FMT == OSB_FMT_PCM16) return (int)__ldg(reinterpret_cast<const int16_t*>(base) + idx);
+    return expand<IN_FMT>((uint32_t)__ldg(reinterpret_cast<const uint8_t*>(base) + idx));
+}
+
+__device__ __forceinline__ double grid_pt(long long i, long long last, double step) {
+    return (i == last) ? 1.0 : __dmul_rn((double)i, step);  // np.linspace: arange*step, end forced
+}
+
+template <int IN_FMT>
+__device__ __forceinline__ int interp_one(const void* in, long long j, const LinArgs& a) {
+    const long long n = a.n_in, m = a.n_out;
+    if (n == 1) return load_in<IN_FMT>(in, 0);
+    const double xn = (m == 1) ? 0.0 : grid_pt(j, m - 1, a.step_n);
+    long long i = (long long)(xn * (double)(n - 1));
+    i = i < 0 ? 0 : (i > n - 1 ? n - 1 : i);
+    double xo = grid_pt(i, n - 1, a.step_o);
+#pragma unroll 1
+    for (int it = 0; it < 2; ++it) {  // candidate bucket is off by at most one
+        if (xo > xn) {
+            --i;
+            xo = grid_pt(i, n - 1, a.step_o);
+        } else if (i < n - 1) {
+            double xo1 = grid_pt(i + 1, n - 1, a.step_o);
+            if (xo1 <= xn) { ++i; xo = xo1; }
+        }
+    }
+    const int f0 = load_in<IN_FMT>(in, i);
+    if (i == n - 1 || xo == xn) return f0;
+    const int f1 = load_in<IN_FMT>(in, i + 1);
+    const double xo1 = grid_pt(i + 1, n - 1, a.step_o);
+    const double slope = __ddiv_rn((double)(f1 - f0), __dsub_rn(xo1, xo));
+    const double y = __dadd_rn(__dmul_rn(slope, __dsub_rn(xn, xo)), (double)f0);
+    return __double2int_rz(y);  // astype(int16): truncation toward zero (|y| <= 32768)
+}
+
+template <int IN_FMT, int OUT_FMT>
+__global__ void __launch_bounds__(256) k_resample_linear(LinArgs a, int vec_ok) {
+    const long long groups = (a.n_out + 7) / 8;
+    const long long total = groups * a.batch;
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nthr = (long long)gridDim.x * blockDim.x;
+    const int in_es = (IN_FMT == OSB_FMT_PCM16) ? 2 : 1;
+    for (long long g = tid; g < total; g += nthr) {
+        const long long c = g / groups, j0 = (g - c * groups) * 8;
+        const void* in = reinterpret_cast<const char*>(a.in) + c * a.in_stride * in_es;
+        int v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = (j0 + k < a.n_out) ? interp_one<IN_FMT>(in, j0 + k, a) : 0;
+        if (OUT_FMT == OSB_FMT_PCM16) {
+            int16_t* o = reinterpret_cast<int16_t*>(a.out) + c * a.out_stride + j0;
+            if (vec_ok && j0 + 8 <= a.n_out) {
+                uint4 w;
+                w.x = (uint32_t)(v[0] & 0xFFFF) | ((uint32_t)v[1] << 16);
+                w.y = (uint32_t)(v[2] & 0xFFFF) | ((uint32_t)v[3] << 16);
+                w.z = (uint32_t)(v[4] & 0xFFFF) | ((uint32_t)v[5] << 16);
+                w.w = (uint32_t)(v[6] & 0xFFFF) | ((uint32_t)v[7] << 16);
+                st_stream_u4(o, w);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    if (j0 + k < a.n_out) o[k] = (int16_t)v[k];
+            }
+        } else {
+            uint8_t* o = reinterpret_cast<uint8_t*>(a.out) + c * a.out_stride + j0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (j0 + k < a.n_out) o[k] = (uint8_t)compress<OUT_FMT>((int)(int16_t)v[k]);
+        }
+    }
+}
+
+template <int IN_FMT>
+static int launch_linear_out(const LinArgs& a, int out_fmt, int vec_ok, int grid, cudaStream_t st) {
+    switch (out_fmt) {
+        case OSB_FMT_PCM16: OSB_LAUNCH((k_resample_linear<IN_FMT, OSB_FMT_PCM16>), grid, 256, 0, st, a, vec_ok); break;
+        case OSB_FMT_ULAW: OSB_LAUNCH((k_resample_linear<IN_FMT, OSB_FMT_ULAW>), grid, 256, 0, st, a, vec_ok); break;
+        case OSB_FMT_ALAW: OSB_LAUNCH((k_resample_linear<IN_FMT, OSB_FMT_ALAW>), grid, 256, 0, st, a, vec_ok); break;
+        default: set_error("invalid argument: out_fmt %d", out_fmt); return OSB_ERR_INVALID_ARG;
+    }
+    OSB_CHECK_LAUNCH();
+    return OSB_OK;
+}
+
+}  // namespace osb
+
+using namespace osb;
+
+extern "C" {
+
+int osb_g711_decode_dev(const uint8_t* d_in, int16_t* d_out, size_t n, int law, void* stream) {
+    int rc = ensure_init();
+    if (rc) return rc;
+    OSB_REQUIRE(law == OSB_FMT_ULAW || law == OSB_FMT_ALAW, "law must be OSB_FMT_ULAW or OSB_FMT_ALAW");
+    if (n == 0) return OSB_OK;
+    OSB_REQUIRE(d_in && d_out, "null buffer");
+    OSB_REQUIRE(((uintptr_t)d_in & 15) == 0 && ((uintptr_t)d_out & 15) == 0, "buffers must be 16-byte aligned");
+    int grid = grid_for(n / 16 + 1, 256);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (law == OSB_FMT_ULAW) OSB_LAUNCH(k_g711_decode<OSB_FMT_ULAW>, grid, 256, 0, st, d_in, d_out, n);
+    else OSB_LAUNCH(k_g711_decode<OSB_FMT_ALAW>, grid, 256, 0, st, d_in, d_out, n);
+    OSB_CHECK_LAUNCH();
+    return OSB_OK;
+}
+
+int osb_g711_encode_dev(const int16_t* d_in, uint8_t* d_out, size_t n, int law, void* stream) {
+    int rc = ensure_init();
+    if (rc) return rc;
+    OSB_REQUIRE(law == OSB_FMT_ULAW || law == OSB_FMT_ALAW, "law must be OSB_FMT_ULAW or OSB_FMT_ALAW");
+    if (n == 0) return OSB_OK;
+    OSB_REQUIRE(d_in && d_out, "null buffer");
+    OSB_REQUIRE(((uintptr_t)d_in & 15) == 0 && ((uintptr_t)d_out & 15) == 0, "buffers must be 16-byte aligned");
+    int grid = grid_for(n / 16 + 1, 256);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (law == OSB_FMT_ULAW) OSB_LAUNCH(k_g711_encode<OSB_FMT_ULAW>, grid, 256, 0, st, d_in, d_out, n);
+    else OSB_LAUNCH(k_g711_encode<OSB_FMT_ALAW>, grid, 256, 0, st, d_in, d_out, n);
+    OSB_CHECK_LAUNCH();
+    return OSB_OK;
+}
+
+int osb_resample_linear_dev(const void* d_in, int in_fmt, void* d_out, int out_fmt, int64_t n_in, int64_t n_out,
+                            int64_t batch, int64_t in_stride, int64_t out_stride, void* stream) {
+    int rc = ensure_init();
+    if (rc) return rc;
+    OSB_REQUIRE(n_in >= 0 && n_out >= 0 && batch >= 0, "negative size");
+    if (n_in == 0 || n_out == 0 || batch == 0) return OSB_OK;
+    OSB_REQUIRE(d_in && d_out, "null buffer");
+    OSB_REQUIRE(in_stride >= n_in && out_stride >= n_out, "stride smaller than row");
+    LinArgs a;
+    a.in = d_in; a.out = d_out; a.n_in = n_in; a.n_out = n_out; a.batch = batch;
+    a.in_stride = in_stride; a.out_stride = out_stride;
+    a.step_o = n_in > 1 ? 1.0 / (double)(n_in - 1) : 0.0;
+    a.step_n = n_out > 1 ? 1.0 / (double)(n_out - 1) : 0.0;
+    int vec_ok = (out_fmt == OSB_FMT_PCM16) && (((uintptr_t)d_out & 15) == 0) && (out_stride % 8 == 0);
+    long long groups = (n_out + 7) / 8 * batch;
+    int grid = grid_for((size_t)groups, 256);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (in_fmt) {
+        case OSB_FMT_PCM16: return launch_linear_out<OSB_FMT_PCM16>(a, out_fmt, vec_ok, grid, st);
+        case OSB_FMT_ULAW: return launch_linear_out<OSB_FMT_ULAW>(a, out_fmt, vec_ok, grid, st);
+        case OSB_FMT_ALAW: return launch_linear_out<OSB_FMT_ALAW>(a, out_fmt, vec_ok, grid, st);
+    }
+    set_error("invalid argument: in_fmt %d", in_fmt);
+    return OSB_ERR_INVALID_ARG;
+}
+
+// ---------------------------------------------------------------- host-pointer wrappers
+int osb_g711_decode_host(const uint8_t* in, int16_t* out, size_t n, int law) {
+    HostWs& ws = host_ws();
+    int rc = ws.prepare();
+    if (rc) return rc;
+    if (n == 0) return OSB_OK;
+    void *di, *dout;
+    if ((rc = ws.dev_buf(0, n, &di)) || (rc = ws.dev_buf(1, n * 2, &dout))) return rc;
+    if ((rc = ws.h2d(di, in, n))) return rc;
+    if ((rc = osb_g711_decode_dev((const uint8_t*)di, (int16_t*)dout, n, law, ws.stream))) return rc;
+    return ws.d2h(out, dout, n * 2);
+}
+
+int osb_g711_encode_host(const int16_t* in, uint8_t* out, size_t n, int law) {
+    HostWs& ws = host_ws();
+    int rc = ws.prepare();
+    if (rc) return rc;
+    if (n == 0) return OSB_OK;
+    void *di, *dout;
+    if ((rc = ws.dev_buf(0, n * 2, &di)) || (rc = ws.dev_buf(1, n, &dout))) return rc;
+    if ((rc = ws.h2d(di, in, n * 2))) return rc;
+    if ((rc = osb_g711_encode_dev((const int16_t*)di, (uint8_t*)dout, n, law, ws.stream))) return rc;
+    return ws.d2h(out, dout, n);
+}
+
+int osb_resample_linear_host(const void* in, int in_fmt, void* out, int out_fmt, int64_t n_in, int64_t n_out,
+                             int64_t batch, int64_t in_stride, int64_t out_stride) {
+    HostWs& ws = host_ws();
+    int rc = ws.prepare();
+    if (rc) return rc;
+    if (n_in <= 0 || n_out <= 0 || batch <= 0) return OSB_OK;
+    size_t ies = in_fmt == OSB_FMT_PCM16 ? 2 : 1, oes = out_fmt == OSB_FMT_PCM16 ? 2 : 1;
+    size_t ib = (size_t)((batch - 1) * in_stride + n_in) * ies, ob = (size_t)((batch - 1) * out_stride + n_out) * oes;
+    void *di, *dout;
+    if ((rc = ws.dev_buf(0, ib, &di)) || (rc = ws.dev_buf(1, ob, &dout))) return rc;
+    if ((rc = ws.h2d(di, in, ib))) return rc;
+    if ((rc = osb_resample_linear_dev(di, in_fmt, dout, out_fmt, n_in, n_out, batch, in_stride, out_stride, ws.stream))) return rc;
+    return ws.d2h(out, dout, ob);
+}
+
+}  // extern "C"

@@ -1,0 +1,178 @@
+// libosb200 runtime: device selection, error text, per-thread host workspace.
+#include <atomic>
+#include <cstdarg>
+#include <mutex>
+
+#include "common.cuh"
+
+namespace osb {
+
+static thread_local char t_err[512] = "";
+static std::atomic<uint64_t> g_launches{0};
+static std::atomic<int> g_sms{0};
+static thread_local int t_device = -1;
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(t_err, sizeof(t_err), fmt, ap);
+    va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+    set_error("CUDA error %d (%s) in %s at %s:%d", (int)e, cudaGetErrorString(e), what, file, line);
+    cudaGetLastError();  // clear sticky-less errors so later calls report their own
+    if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) return OSB_ERR_NO_DEVICE;
+    return OSB_ERR_CUDA;
+}
+
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+int num_sms() {
+    int v = g_sms.load();
+    return v > 0 ? v : OSB_NUM_SMS;
+}
+
+int ensure_init() {
+    if (t_device >= 0) return OSB_OK;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice", __FILE__, __LINE__);
+    return osb_init(dev);
+}
+
+int HostWs::prepare() {
+    int rc = ensure_init();
+    if (rc) return rc;
+    if (device != t_device) {  // first use on this thread, or the thread switched device
+        if (stream) {
+            cudaStreamDestroy(stream);
+            for (auto& p : pin) { if (p) cudaFreeHost(p); p = nullptr; }
+            for (auto& d : dev) { if (d) cudaFree(d); d = nullptr; }
+            pin_cap[0] = pin_cap[1] = 0;
+            dev_cap[0] = dev_cap[1] = dev_cap[2] = dev_cap[3] = 0;
+        }
+        OSB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        device = t_device;
+    }
+    return OSB_OK;
+}
+
+static size_t round_up_cap(size_t bytes) {
+    size_t c = 1 << 16;
+    while (c < bytes) c <<= 1;
+    return c;
+}
+
+int HostWs::dev_buf(int slot, size_t bytes, void** out) {
+    if (bytes > dev_cap[slot]) {
+        if (dev[slot]) { OSB_CUDA(cudaStreamSynchronize(stream)); OSB_CUDA(cudaFree(dev[slot])); dev[slot] = nullptr; dev_cap[slot] = 0; }
+        size_t c = round_up_cap(bytes);
+        OSB_CUDA(cudaMalloc(&dev[slot], c));
+        dev_cap[slot] = c;
+    }
+    *out = dev[slot];
+    return OSB_OK;
+}
+
+int HostWs::pin_buf(int slot, size_t bytes, void** out) {
+    if (bytes > pin_cap[slot]) {
+        if (pin[slot]) { OSB_CUDA(cudaStreamSynchronize(stream)); OSB_CUDA(cudaFreeHost(pin[slot])); pin[slot] = nullptr; pin_cap[slot] = 0; }
+        size_t c = round_up_cap(bytes);
+        OSB_CUDA(cudaMallocHost(&pin[slot], c));
+        pin_cap[slot] = c;
+    }
+    *out = pin[slot];
+    return OSB_OK;
+}
+
+static const size_t kPinLimit = (size_t)256 << 20;  // above this, copy straight from the caller's pages
+
+int HostWs::h2d(void* d, const void* h, size_t bytes) {
+    if (bytes == 0) return OSB_OK;
+    if (bytes <= kPinLimit) {
+        void* p;
+        int rc = pin_buf(0, bytes, &p);
+        if (rc) return rc;
+        memcpy(p, h, bytes);
+        OSB_CUDA(cudaMemcpyAsync(d, p, bytes, cudaMemcpyHostToDevice, stream));
+    } else {
+        OSB_CUDA(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, stream));
+    }
+    return OSB_OK;
+}
+
+int HostWs::d2h(void* h, const void* d, size_t bytes) {
+    if (bytes == 0) return sync();
+    if (bytes <= kPinLimit) {
+        void* p;
+        int rc = pin_buf(1, bytes, &p);
+        if (rc) return rc;
+        OSB_CUDA(cudaMemcpyAsync(p, d, bytes, cudaMemcpyDeviceToHost, stream));
+        OSB_CUDA(cudaStreamSynchronize(stream));
+        memcpy(h, p, bytes);
+    } else {
+        OSB_CUDA(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, stream));
+        OSB_CUDA(cudaStreamSynchronize(stream));
+    }
+    return OSB_OK;
+}
+
+int HostWs::sync() {
+    OSB_CUDA(cudaStreamSynchronize(stream));
+    return OSB_OK;
+}
+
+HostWs& host_ws() {
+    static thread_local HostWs ws;
+    return ws;
+}
+
+}  // namespace osb
+
+extern "C" {
+
+int osb_version(void) { return OSB_VERSION; }
+
+int osb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int osb_init(int device) {
+    int n = osb_device_count();
+    if (n <= 0) {
+        osb::set_error("no CUDA device visible: libosb200 has no CPU path");
+        return OSB_ERR_NO_DEVICE;
+    }
+    if (device < 0 || device >= n) {
+        osb::set_error("invalid argument: device %d out of range (0..%d)", device, n - 1);
+        return OSB_ERR_INVALID_ARG;
+    }
+    OSB_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    OSB_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        osb::set_error("device %d is sm_%d%d; libosb200 is built for sm_100a (B200) only", device, prop.major, prop.minor);
+        return OSB_ERR_UNSUPPORTED;
+    }
+    osb::g_sms.store(prop.multiProcessorCount);
+    // keep stream-ordered scratch cached in the pool instead of returning it to the driver
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        uint64_t thr = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    osb::t_device = device;
+    return OSB_OK;
+}
+
+const char* osb_last_error(void) { return osb::t_err; }
+
+uint64_t osb_launch_count(void) { return osb::g_launches.load(); }
+
+}  // extern "C"

@@ -1,0 +1,530 @@
+// Silero-VAD-shaped frame scoring and speech segmenting.
+//
+// Replaces (reference file:line):
+//   SileroVAD.__call__ / is_speech / get_speech_segments   src/vad/silero.py:63-177
+//   (the per-window onnxruntime session.run at :86 and :149, and the integer segmenter :133-177)
+//
+// Structure (the reference feeds raw 512-sample windows, no 64-sample context):
+//   front  (stateless, batched over every window of every stream; GEMM-shaped):
+//          right-reflect-pad 64 -> 3 frames x 256 -> Hann-DFT conv (258x256) -> |.| ->
+//          4x Conv1d(k=3)+ReLU -> W_ih.x + b_ih + b_hh          => gate pre-activations [W][512]
+//   recur  (sequential over windows, one CTA per stream): gates += W_hh.h ; LSTM cell ; head
+//   segment(integer state machine, one warp per stream): bit-exact with silero.py:133-177
+#include <mutex>
+#include <vector>
+
+#include "common.cuh"
+
+namespace osb {
+
+constexpr int kWin = 512, kHid = 128, kGates = 512;
+constexpr int kMagC = 132;            // 129 magnitude channels padded to a multiple of 4 floats
+constexpr int kK1 = 400;              // enc1 GEMM K: 3*132 = 396 padded to a multiple of 16
+
+// flat host weight blob layout (must match vad/silero.py WEIGHT_LAYOUT)
+constexpr size_t oBasis = 0, nBasis = 258 * 256;
+constexpr size_t oE1w = oBasis + nBasis, nE1w = 128 * 129 * 3, oE1b = oE1w + nE1w;
+constexpr size_t oE2w = oE1b + 128, nE2w = 64 * 128 * 3, oE2b = oE2w + nE2w;
+constexpr size_t oE3w = oE2b + 64, nE3w = 64 * 64 * 3, oE3b = oE3w + nE3w;
+constexpr size_t oE4w = oE3b + 64, nE4w = 128 * 64 * 3, oE4b = oE4w + nE4w;
+constexpr size_t oWih = oE4b + 128, nW = 512 * 128, oWhh = oWih + nW;
+constexpr size_t oBih = oWhh + nW, oBhh = oBih + 512, oDw = oBhh + 512, oDb = oDw + 128;
+constexpr size_t kBlobFloats = oDb + 1;
+
+struct VadModel {
+    int device;
+    // GEMM "B" matrices, row-major [N][K] with K padded as the kernels expect
+    float *basis;   // [258][256], rows interleaved re0,im0,re1,im1,... so |.| pairs are adjacent columns
+    float *e1w, *e1b;  // [128][400]  (k-major: col = k*132 + ic)
+    float *e2w, *e2b;  // [64][384]   (col = k*128 + ic)
+    float *e3w, *e3b;  // [64][192]   (col = k*64 + ic)
+    float *e4w, *e4b;  // [128][192]
+    float *wih, *bsum; // [512][128], b_ih + b_hh
+    float *whh;        // [512][128]
+    float *dw;         // [128]
+    float db;
+};
+
+// ------------------------------------------------------------------ batched front GEMM
+// C[r][n] = act( sum_k A(r,k) * B[n][k] + bias[n] ),   A rows addressed through a descriptor
+struct GemmDesc {
+    const void* A;
+    long long a_outer;  // elements between consecutive "outer" groups of rows
+    int a_icount;       // rows per outer group
+    int a_istride;      // elements between rows inside a group
+    const float* B;
+    const float* bias;
+    float* C;
+    long long c_outer;
+    int c_icount, c_istride, c_offset;
+    int M, N, K, relu;
+    // audio A-mode only: rows are (stream, window, frame); frames read the stream's samples
+    long long audio_stride;  // samples between streams
+    int wins_per_stream;     // windows of this chunk per stream
+    long long win0;          // first window of the chunk
+};
+
+constexpr int BM = 128, BN = 64, BK = 16;
+
+template <int AMODE>
+__device__ __forceinline__ void load_a8(const GemmDesc& d, int r, int k0, float v[8]) {
+    if (r >= d.M) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = 0.f;
+        return;
+    }
+    if (AMODE == 0) {
+        const float* p = reinterpret_cast<const float*>(d.A) + (long long)(r / d.a_icount) * d.a_outer + (long long)(r % d.a_icount) * d.a_istride + k0;
+        float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+        // r = (stream*wins + win)*3 + frame ; sample s = 128*frame + k in the 576-sample padded window
+        const int f = r % 3, wq = r / 3;
+        const int sidx = wq / d.wins_per_stream;
+        const long long win = d.win0 + (wq - sidx * d.wins_per_stream);
+        const long long base = (long long)sidx * d.audio_stride + win * kWin;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            int s = 128 * f + k0 + i;
+            s = s < kWin ? s : (2 * kWin - 2 - s);  // right reflect pad (no edge repeat)
+            if (AMODE == 1) v[i] = __fdiv_rn((float)reinterpret_cast<const int16_t*>(d.A)[base + s], 32768.0f);
+            else v[i] = reinterpret_cast<const float*>(d.A)[base + s];
+        }
+    }
+}
+
+template <int AMODE, int EPI>  // EPI 0: bias(+relu) ; 1: magnitude of adjacent (re,im) column pairs
+__global__ void __launch_bounds__(256) k_vad_gemm(GemmDesc d) {
+    __shared__ __align__(16) float As[2][BK][BM + 4];
+    __shared__ __align__(16) float Bs[2][BK][BN + 4];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    const int a_row = tid & 127, a_k = (tid >> 7) * 8;
+    const int b_n = tid & 63, b_k = (tid >> 6) * 4;
+    float acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    float av[8];
+    float4 bv;
+    auto gload = [&](int kt) {
+        load_a8<AMODE>(d, m0 + a_row, kt * BK + a_k, av);
+        const int n = n0 + b_n;
+        bv = (n < d.N) ? *reinterpret_cast<const float4*>(d.B + (long long)n * d.K + kt * BK + b_k) : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    auto sstore = [&](int buf) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) As[buf][a_k + i][a_row] = av[i];
+        Bs[buf][b_k + 0][b_n] = bv.x; Bs[buf][b_k + 1][b_n] = bv.y; Bs[buf][b_k + 2][b_n] = bv.z; Bs[buf][b_k + 3][b_n] = bv.w;
+    };
+    const int KT = d.K / BK;
+    gload(0);
+    sstore(0);
+    __syncthreads();
+    for (int kt = 0; kt < KT; ++kt) {
+        const int buf = kt & 1;
+        if (kt + 1 < KT) gload(kt + 1);
+#pragma unroll
+        for (int k = 0; k < BK; ++k) {
+            const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 8]);
+            const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 8 + 4]);
+            const float4 b = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
+            const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+        }
+        if (kt + 1 < KT) {
+            sstore(buf ^ 1);
+            __syncthreads();
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int r = m0 + ty * 8 + i;
+        if (r >= d.M) continue;
+        float* crow = d.C + (long long)(r / d.c_icount) * d.c_outer + (long long)(r % d.c_icount) * d.c_istride + d.c_offset;
+        const int n = n0 + tx * 4;
+        if (EPI == 1) {
+            // columns (n, n+1) = (re, im) of bin n/2
+            if (n < d.N) crow[n >> 1] = sqrtf(acc[i][0] * acc[i][0] + acc[i][1] * acc[i][1]);
+            if (n + 2 < d.N) crow[(n >> 1) + 1] = sqrtf(acc[i][2] * acc[i][2] + acc[i][3] * acc[i][3]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (n + j < d.N) {
+                    float v = acc[i][j] + (d.bias ? d.bias[n + j] : 0.f);
+                    crow[n + j] = d.relu ? fmaxf(v, 0.f) : v;
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------ recurrence + head
+// one CTA (512 threads, thread = one gate row) per stream; W_hh row: 96 weights in registers,
+// 32 in shared memory (the register file holds exactly 64 K floats = all of W_hh, so part of it
+// must live elsewhere); h broadcast from shared memory.
+constexpr int kRegW = 96, kSmW = kHid - kRegW;
+
+__device__ __forceinline__ float sigmoidf_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+__global__ void __launch_bounds__(512, 1) k_vad_recur(const float* __restrict__ pre, long long pre_stream_stride, int n_steps,
+                                                      const float* __restrict__ whh, const float* __restrict__ dw, float db,
+                                                      float* __restrict__ state, float* __restrict__ probs, long long probs_stride,
+                                                      long long win0) {
+    extern __shared__ __align__(16) float sm[];
+    float4* w_sm = reinterpret_cast<float4*>(sm);                 // [kSmW/4][512] float4
+    float* h_sm = sm + kSmW * kGates;                             // [128]
+    float* g_sm = h_sm + kHid;                                    // [512]
+    float* dw_sm = g_sm + kGates;                                 // [128]
+    const int row = threadIdx.x, b = blockIdx.x;
+    float w[kRegW];
+#pragma unroll
+    for (int k = 0; k < kRegW; ++k) w[k] = whh[row * kHid + k];
+#pragma unroll
+    for (int q = 0; q < kSmW / 4; ++q)
+        w_sm[q * kGates + row] = *reinterpret_cast<const float4*>(whh + row * kHid + kRegW + q * 4);
+    float c = 0.f;
+    float* st = state + (long long)b * 2 * kHid;
+    if (row < kHid) {
+        h_sm[row] = st[row];
+        c = st[kHid + row];
+        dw_sm[row] = dw[row];
+    }
+    const float* p = pre + (long long)b * pre_stream_stride + row;
+    float* pr = probs + (long long)b * probs_stride + win0;
+    float pre_v = n_steps > 0 ? p[0] : 0.f;
+    __syncthreads();
+    for (int t = 0; t < n_steps; ++t) {
+        const float pre_next = (t + 1 < n_steps) ? p[(long long)(t + 1) * kGates] : 0.f;  // prefetch
+        float a0 = pre_v, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+        for (int k = 0; k < kRegW; k += 4) {
+            const float4 h4 = *reinterpret_cast<const float4*>(h_sm + k);
+            a0 = fmaf(w[k], h4.x, a0); a1 = fmaf(w[k + 1], h4.y, a1); a2 = fmaf(w[k + 2], h4.z, a2); a3 = fmaf(w[k + 3], h4.w, a3);
+        }
+#pragma unroll
+        for (int q = 0; q < kSmW / 4; ++q) {
+            const float4 w4 = w_sm[q * kGates + row];
+            const float4 h4 = *reinterpret_cast<const float4*>(h_sm + kRegW + q * 4);
+            a0 = fmaf(w4.x, h4.x, a0); a1 = fmaf(w4.y, h4.y, a1); a2 = fmaf(w4.z, h4.z, a2); a3 = fmaf(w4.w, h4.w, a3);
+        }
+        g_sm[row] = (a0 + a1) + (a2 + a3);
+        __syncthreads();
+        if (row < kHid) {
+            const float gi = g_sm[row], gf = g_sm[kHid + row], gg = g_sm[2 * kHid + row], go = g_sm[3 * kHid + row];
+            c = sigmoidf_acc(gf) * c + sigmoidf_acc(gi) * tanhf(gg);
+            const float h = sigmoidf_acc(go) * tanhf(c);
+            h_sm[row] = h;
+            // head: relu(h) . w_dec -> sigmoid ; reduce over the 4 warps through g_sm (free after the sync below)
+            float part = warp_sum(fmaxf(h, 0.f) * dw_sm[row]);
+            if ((row & 31) == 0) dw_sm[kHid + (row >> 5)] = part;
+        }
+        __syncthreads();
+        if (row == 0) {
+            const float logit = ((dw_sm[kHid] + dw_sm[kHid + 1]) + (dw_sm[kHid + 2] + dw_sm[kHid + 3])) + db;
+            pr[t] = sigmoidf_acc(logit);
+        }
+        pre_v = pre_next;
+    }
+    if (row < kHid) {
+        st[row] = h_sm[row];
+        st[kHid + row] = c;
+    }
+}
+
+// ------------------------------------------------------------------ segmenter (bit-exact integer machine)
+// one warp per stream: 32 probabilities per coalesced load -> ballot -> lane 0 walks the bits.
+__global__ void __launch_bounds__(32) k_vad_segment(const float* __restrict__ probs, long long probs_stride, long long n_win,
+                                                    long long n_samples, float thr, int min_speech_windows, int silence_windows,
+                                                    int* __restrict__ segs, int* __restrict__ counts, int max_seg) {
+    const int b = blockIdx.x, lane = threadIdx.x;
+    const float* p = probs + (long long)b * probs_stride;
+    int* out = segs + (long long)b * max_seg * 2;
+    bool in_speech = false;
+    int speech_start = 0, silence_count = 0, speech_windows = 0, nseg = 0;
+    for (long long base = 0; base < n_win; base += 32) {
+        const long long k = base + lane;
+        const bool sp = (k < n_win) && (p[k] >= thr);
+        const unsigned mask = __ballot_sync(0xffffffffu, sp);
+        if (lane == 0) {
+            const int lim = (int)((n_win - base) < 32 ? (n_win - base) : 32);
+            for (int i = 0; i < lim; ++i) {
+                const int cur_ms = (int)(((base + i) * kWin * 1000) / 16000);
+                if ((mask >> i) & 1u) {
+                    silence_count = 0;
+                    if (!in_speech) { in_speech = true; speech_start = cur_ms; speech_windows = 0; }
+                    ++speech_windows;
+                } else if (in_speech) {
+                    if (++silence_count >= silence_windows) {
+                        if (speech_windows >= min_speech_windows) {
+                            if (nseg < max_seg) { out[2 * nseg] = speech_start; out[2 * nseg + 1] = cur_ms; }
+                            ++nseg;
+                        }
+                        in_speech = false; silence_count = 0; speech_windows = 0;
+                    }
+                }
+            }
+        }
+    }
+    if (lane == 0) {
+        if (in_speech && speech_windows >= min_speech_windows) {
+            if (nseg < max_seg) { out[2 * nseg] = speech_start; out[2 * nseg + 1] = (int)((n_samples * 1000) / 16000); }
+            ++nseg;
+        }
+        counts[b] = nseg;
+    }
+}
+
+// ------------------------------------------------------------------ host orchestration
+static int upload(float** dst, const std::vector<float>& v) {
+    OSB_CUDA(cudaMalloc(dst, v.size() * sizeof(float)));
+    OSB_CUDA(cudaMemcpy(*dst, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice));
+    return OSB_OK;
+}
+
+// conv weight [oc][ic][3] -> GEMM B [oc][Kpad], col = k*icp + ic
+static std::vector<float> relay_conv(const float* w, int oc, int ic, int icp, int kpad) {
+    std::vector<float> o((size_t)oc * kpad, 0.f);
+    for (int a = 0; a < oc; ++a)
+        for (int c = 0; c < ic; ++c)
+            for (int k = 0; k < 3; ++k) o[(size_t)a * kpad + k * icp + c] = w[((size_t)a * ic + c) * 3 + k];
+    return o;
+}
+
+template <int AMODE, int EPI>
+static int launch_gemm(const GemmDesc& d, cudaStream_t st) {
+    dim3 grid((d.M + BM - 1) / BM, (d.N + BN - 1) / BN);
+    OSB_LAUNCH((k_vad_gemm<AMODE, EPI>), grid, 256, 0, st, d);
+    OSB_CHECK_LAUNCH();
+    return OSB_OK;
+}
+
+static int vad_score(VadModel* m, const void* d_audio, int fmt, int64_t n, int64_t batch, int64_t stride, float* d_state,
+                     float* d_probs, int64_t probs_stride, cudaStream_t st) {
+    const long long n_win = n / kWin;
+    if (n_win == 0 || batch == 0) return OSB_OK;
+    // chunk the window axis so the activations of a chunk stay around the size of L2
+    long long T = (96ll << 20) / (batch * 9728ll);  // ~9.5 KB of activations per window
+    if (T < 32) T = 32;
+    if (T > n_win) T = n_win;
+    const long long W = batch * T;  // windows per chunk
+    Scratch scr(st);
+    float *mag, *h1, *h2, *h3, *h4, *pre;
+    OSB_CUDA(scr.alloc(&mag, (size_t)W * 5 * kMagC + 64));
+    OSB_CUDA(scr.alloc(&h1, (size_t)W * 5 * 128 + 64));
+    OSB_CUDA(scr.alloc(&h2, (size_t)W * 4 * 64 + 64));
+    OSB_CUDA(scr.alloc(&h3, (size_t)W * 3 * 64 + 64));
+    OSB_CUDA(scr.alloc(&h4, (size_t)W * 128 + 64));
+    OSB_CUDA(scr.alloc(&pre, (size_t)W * kGates + 64));
+    // zero once: the padding rows/channels are never written by the GEMMs
+    OSB_CUDA(cudaMemsetAsync(mag, 0, ((size_t)W * 5 * kMagC + 64) * 4, st));
+    OSB_CUDA(cudaMemsetAsync(h1, 0, ((size_t)W * 5 * 128 + 64) * 4, st));
+    OSB_CUDA(cudaMemsetAsync(h2, 0, ((size_t)W * 4 * 64 + 64) * 4, st));
+    OSB_CUDA(cudaMemsetAsync(h3, 0, ((size_t)W * 3 * 64 + 64) * 4, st));
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    const int recur_smem = (kSmW * kGates + kHid + kGates + 2 * kHid) * (int)sizeof(float);
+    std::call_once(once, [&] { attr_err = cudaFuncSetAttribute(k_vad_recur, cudaFuncAttributeMaxDynamicSharedMemorySize, recur_smem); });
+    OSB_CUDA(attr_err);
+    int rc;
+    for (long long w0 = 0; w0 < n_win; w0 += T) {
+        const int t = (int)((n_win - w0) < T ? (n_win - w0) : T);
+        const int Wc = (int)(batch * t);
+        GemmDesc d{};
+        // L0: DFT conv + magnitude -> mag[w][1+f][0..128]
+        d.A = d_audio; d.audio_stride = stride; d.wins_per_stream = t; d.win0 = w0;
+        d.B = m->basis; d.bias = nullptr; d.C = mag; d.c_outer = 5 * kMagC; d.c_icount = 3; d.c_istride = kMagC; d.c_offset = kMagC;
+        d.M = Wc * 3; d.N = 258; d.K = 256; d.relu = 0;
+        rc = (fmt == OSB_FMT_PCM16) ? launch_gemm<1, 1>(d, st) : launch_gemm<2, 1>(d, st);
+        if (rc) return rc;
+        // L1: enc1 129->128, k3 s1 p1, 3 positions
+        d = GemmDesc{};
+        d.A = mag; d.a_outer = 5 * kMagC; d.a_icount = 3; d.a_istride = kMagC;
+        d.B = m->e1w; d.bias = m->e1b; d.C = h1; d.c_outer = 5 * 128; d.c_icount = 3; d.c_istride = 128; d.c_offset = 128;
+        d.M = Wc * 3; d.N = 128; d.K = kK1; d.relu = 1;
+        if ((rc = launch_gemm<0, 0>(d, st))) return rc;
+        // L2: enc2 128->64, k3 s2 p1, 2 positions
+        d = GemmDesc{};
+        d.A = h1; d.a_outer = 5 * 128; d.a_icount = 2; d.a_istride = 2 * 128;
+        d.B = m->e2w; d.bias = m->e2b; d.C = h2; d.c_outer = 4 * 64; d.c_icount = 2; d.c_istride = 64; d.c_offset = 64;
+        d.M = Wc * 2; d.N = 64; d.K = 384; d.relu = 1;
+        if ((rc = launch_gemm<0, 0>(d, st))) return rc;
+        // L3: enc3 64->64, k3 s2 p1, 1 position
+        d = GemmDesc{};
+        d.A = h2; d.a_outer = 4 * 64; d.a_icount = 1; d.a_istride = 0;
+        d.B = m->e3w; d.bias = m->e3b; d.C = h3; d.c_outer = 3 * 64; d.c_icount = 1; d.c_istride = 0; d.c_offset = 64;
+        d.M = Wc; d.N = 64; d.K = 192; d.relu = 1;
+        if ((rc = launch_gemm<0, 0>(d, st))) return rc;
+        // L4: enc4 64->128, k3 s1 p1, 1 position
+        d = GemmDesc{};
+        d.A = h3; d.a_outer = 3 * 64; d.a_icount = 1; d.a_istride = 0;
+        d.B = m->e4w; d.bias = m->e4b; d.C = h4; d.c_outer = 128; d.c_icount = 1; d.c_istride = 0; d.c_offset = 0;
+        d.M = Wc; d.N = 128; d.K = 192; d.relu = 1;
+        if ((rc = launch_gemm<0, 0>(d, st))) return rc;
+        // L5: W_ih.x + (b_ih + b_hh) -> gate pre-activations
+        d = GemmDesc{};
+        d.A = h4; d.a_outer = 128; d.a_icount = 1; d.a_istride = 0;
+        d.B = m->wih; d.bias = m->bsum; d.C = pre; d.c_outer = kGates; d.c_icount = 1; d.c_istride = 0; d.c_offset = 0;
+        d.M = Wc; d.N = kGates; d.K = 128; d.relu = 0;
+        if ((rc = launch_gemm<0, 0>(d, st))) return rc;
+        // recurrence over the chunk's t windows, one CTA per stream
+        OSB_LAUNCH(k_vad_recur, (unsigned)batch, 512, recur_smem, st, pre, (long long)t * kGates, t, m->whh, m->dw, m->db,
+                   d_state, d_probs, (long long)probs_stride, w0);
+        OSB_CHECK_LAUNCH();
+    }
+    return OSB_OK;
+}
+
+static int vad_segments(const float* d_probs, int64_t probs_stride, int64_t n_win, int64_t batch, int64_t n_samples, float thr,
+                        int min_speech_ms, int silence_ms, int32_t* d_segs, int32_t* d_counts, int max_seg, cudaStream_t st) {
+    const int window_ms = kWin * 1000 / 16000;
+    int silence_windows = silence_ms / window_ms;
+    if (silence_windows < 1) silence_windows = 1;
+    int min_speech_windows = min_speech_ms / window_ms;
+    if (min_speech_windows < 1) min_speech_windows = 1;
+    OSB_LAUNCH(k_vad_segment, (unsigned)batch, 32, 0, st, d_probs, (long long)probs_stride, (long long)n_win, (long long)n_samples, thr,
+               min_speech_windows, silence_windows, d_segs, d_counts, max_seg);
+    OSB_CHECK_LAUNCH();
+    return OSB_OK;
+}
+
+}  // namespace osb
+
+using namespace osb;
+
+extern "C" {
+
+int osb_vad_create(const float* weights_host, size_t n_floats, void** handle) {
+    int rc = ensure_init();
+    if (rc) return rc;
+    OSB_REQUIRE(weights_host && handle, "null argument");
+    if (n_floats != kBlobFloats) {
+        set_error("invalid argument: VAD weight blob has %zu floats, expected %zu", n_floats, (size_t)kBlobFloats);
+        return OSB_ERR_INVALID_ARG;
+    }
+    const float* w = weights_host;
+    VadModel* m = new VadModel();
+    OSB_CUDA(cudaGetDevice(&m->device));
+    std::vector<float> basis((size_t)258 * 256);
+    for (int k = 0; k < 129; ++k)
+        for (int n = 0; n < 256; ++n) {
+            basis[(size_t)(2 * k) * 256 + n] = w[oBasis + (size_t)k * 256 + n];
+            basis[(size_t)(2 * k + 1) * 256 + n] = w[oBasis + (size_t)(129 + k) * 256 + n];
+        }
+    std::vector<float> bsum(512);
+    for (int i = 0; i < 512; ++i) bsum[i] = w[oBih + i] + w[oBhh + i];
+    auto vec = [&](size_t off, size_t n) { return std::vector<float>(w + off, w + off + n); };
+    if ((rc = upload(&m->basis, basis)) || (rc = upload(&m->e1w, relay_conv(w + oE1w, 128, 129, kMagC, kK1))) ||
+        (rc = upload(&m->e1b, vec(oE1b, 128))) || (rc = upload(&m->e2w, relay_conv(w + oE2w, 64, 128, 128, 384))) ||
+        (rc = upload(&m->e2b, vec(oE2b, 64))) || (rc = upload(&m->e3w, relay_conv(w + oE3w, 64, 64, 64, 192))) ||
+        (rc = upload(&m->e3b, vec(oE3b, 64))) || (rc = upload(&m->e4w, relay_conv(w + oE4w, 128, 64, 64, 192))) ||
+        (rc = upload(&m->e4b, vec(oE4b, 128))) || (rc = upload(&m->wih, vec(oWih, nW))) || (rc = upload(&m->bsum, bsum)) ||
+        (rc = upload(&m->whh, vec(oWhh, nW))) || (rc = upload(&m->dw, vec(oDw, 128)))) {
+        delete m;
+        return rc;
+    }
+    m->db = w[oDb];
+    *handle = m;
+    return OSB_OK;
+}
+
+int osb_vad_destroy(void* handle) {
+    if (!handle) return OSB_OK;
+    VadModel* m = reinterpret_cast<VadModel*>(handle);
+    float* ptrs[] = {m->basis, m->e1w, m->e1b, m->e2w, m->e2b, m->e3w, m->e3b, m->e4w, m->e4b, m->wih, m->bsum, m->whh, m->dw};
+    for (float* p : ptrs) cudaFree(p);
+    delete m;
+    return OSB_OK;
+}
+
+int osb_vad_score_dev(void* handle, const void* d_audio, int fmt, int64_t n, int64_t batch, int64_t stride, float* d_state,
+                      float* d_probs, int64_t probs_stride, void* stream) {
+    int rc = ensure_init();
+    if (rc) return rc;
+    OSB_REQUIRE(handle, "null VAD handle");
+    OSB_REQUIRE(fmt == OSB_FMT_PCM16 || fmt == OSB_FMT_F32, "fmt must be OSB_FMT_PCM16 or OSB_FMT_F32");
+    OSB_REQUIRE(n >= 0 && batch >= 0 && stride >= n, "bad sizes");
+    if (n / kWin == 0 || batch == 0) return OSB_OK;
+    OSB_REQUIRE(d_audio && d_state && d_probs && probs_stride >= n / kWin, "bad buffers");
+    return vad_score(reinterpret_cast<VadModel*>(handle), d_audio, fmt, n, batch, stride, d_state, d_probs, probs_stride, (cudaStream_t)stream);
+}
+
+int osb_vad_segments_dev(const float* d_probs, int64_t probs_stride, int64_t n_win, int64_t batch, int64_t n_samples,
+                         float threshold, int min_speech_ms, int silence_ms, int32_t* d_segments, int32_t* d_counts, int max_seg,
+                         void* stream) {
+    int rc = ensure_init();
+    if (rc) return rc;
+    OSB_REQUIRE(batch >= 0 && n_win >= 0 && max_seg >= 0, "bad sizes");
+    if (batch == 0) return OSB_OK;
+    OSB_REQUIRE(d_counts && (d_probs || n_win == 0) && (d_segments || max_seg == 0), "null buffer");
+    return vad_segments(d_probs, probs_stride, n_win, batch, n_samples, threshold, min_speech_ms, silence_ms, d_segments, d_counts, max_seg,
+                        (cudaStream_t)stream);
+}
+
+int osb_vad_score_host(void* handle, const void* audio, int fmt, int64_t n, float* state, float* probs, float* max_prob) {
+    HostWs& ws = host_ws();
+    int rc = ws.prepare();
+    if (rc) return rc;
+    OSB_REQUIRE(handle && state, "null argument");
+    OSB_REQUIRE(fmt == OSB_FMT_PCM16 || fmt == OSB_FMT_F32, "fmt must be OSB_FMT_PCM16 or OSB_FMT_F32");
+    if (max_prob) *max_prob = 0.f;
+    const long long n_win = n / kWin;
+    if (n_win <= 0) return OSB_OK;
+    const size_t es = fmt == OSB_FMT_PCM16 ? 2 : 4;
+    void *da, *dst, *dp;
+    if ((rc = ws.dev_buf(0, (size_t)n * es, &da)) || (rc = ws.dev_buf(1, 2 * kHid * 4, &dst)) || (rc = ws.dev_buf(2, (size_t)n_win * 4, &dp))) return rc;
+    if ((rc = ws.h2d(da, audio, (size_t)n_win * kWin * es))) return rc;
+    OSB_CUDA(cudaMemcpyAsync(dst, state, 2 * kHid * 4, cudaMemcpyHostToDevice, ws.stream));
+    if ((rc = vad_score(reinterpret_cast<VadModel*>(handle), da, fmt, n, 1, n, (float*)dst, (float*)dp, n_win, ws.stream))) return rc;
+    OSB_CUDA(cudaMemcpyAsync(state, dst, 2 * kHid * 4, cudaMemcpyDeviceToHost, ws.stream));
+    std::vector<float> tmp;
+    float* out = probs;
+    if (!out) { tmp.resize((size_t)n_win); out = tmp.data(); }
+    if ((rc = ws.d2h(out, dp, (size_t)n_win * 4))) return rc;
+    if (max_prob) {
+        float mx = 0.f;
+        for (long long i = 0; i < n_win; ++i) if (out[i] > mx) mx = out[i];
+        *max_prob = mx;
+    }
+    return OSB_OK;
+}
+
+int osb_vad_segments_host(void* handle, const void* audio, int fmt, int64_t n, float* state, float threshold, int min_speech_ms,
+                          int silence_ms, int32_t* segments, int max_seg, int* n_seg) {
+    HostWs& ws = host_ws();
+    int rc = ws.prepare();
+    if (rc) return rc;
+    OSB_REQUIRE(handle && state && n_seg && (segments || max_seg == 0), "null argument");
+    OSB_REQUIRE(fmt == OSB_FMT_PCM16 || fmt == OSB_FMT_F32, "fmt must be OSB_FMT_PCM16 or OSB_FMT_F32");
+    *n_seg = 0;
+    if (n <= 0) return OSB_OK;
+    const long long n_win = n / kWin;
+    const size_t es = fmt == OSB_FMT_PCM16 ? 2 : 4;
+    void *da, *dst, *dp, *dsg;
+    if ((rc = ws.dev_buf(0, (size_t)n * es + 16, &da)) || (rc = ws.dev_buf(1, 2 * kHid * 4, &dst)) ||
+        (rc = ws.dev_buf(2, (size_t)(n_win + 1) * 4, &dp)) || (rc = ws.dev_buf(3, ((size_t)max_seg * 2 + 4) * 4, &dsg))) return rc;
+    if ((rc = ws.h2d(da, audio, (size_t)n_win * kWin * es))) return rc;
+    OSB_CUDA(cudaMemcpyAsync(dst, state, 2 * kHid * 4, cudaMemcpyHostToDevice, ws.stream));
+    if ((rc = vad_score(reinterpret_cast<VadModel*>(handle), da, fmt, n, 1, n, (float*)dst, (float*)dp, n_win > 0 ? n_win : 1, ws.stream))) return rc;
+    int32_t* d_counts = reinterpret_cast<int32_t*>(dsg) + (size_t)max_seg * 2;
+    if ((rc = vad_segments((const float*)dp, n_win > 0 ? n_win : 1, n_win, 1, n, threshold, min_speech_ms, silence_ms, (int32_t*)dsg, d_counts, max_seg, ws.stream))) return rc;
+    OSB_CUDA(cudaMemcpyAsync(state, dst, 2 * kHid * 4, cudaMemcpyDeviceToHost, ws.stream));
+    std::vector<int32_t> buf((size_t)max_seg * 2 + 1);
+    if ((rc = ws.d2h(buf.data(), dsg, ((size_t)max_seg * 2 + 1) * 4))) return rc;
+    int cnt = buf[(size_t)max_seg * 2];
+    if (cnt > max_seg) {
+        set_error("segment buffer too small: %d segments, capacity %d", cnt, max_seg);
+        return OSB_ERR_BUFFER;
+    }
+    memcpy(segments, buf.data(), (size_t)cnt * 2 * 4);
+    *n_seg = cnt;
+    return OSB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,230 @@
+"""Drop-in for src/vad/silero.py (reference lines 38-209), GPU-backed.
+
+``SileroVAD(session, threshold)`` keeps the reference's attributes (.session, .sample_rate,
+.threshold, ._state[2,1,128]) and methods.  ``session`` is a :class:`VadSession` (weights
+resident on the GPU, shared between per-stream SileroVAD objects like the reference shares
+one ONNX session).  Any other object with the ORT ``run(None, {...})`` contract (the mocks of
+the reference's tests) is driven window by window exactly like the reference does.
+"""
+from __future__ import annotations
+
+import asyncio
+import ctypes
+import logging
+from dataclasses import dataclass
+
+import numpy as np
+
+from .. import _native as N
+
+logger = logging.getLogger(__name__)
+
+VAD_SAMPLE_RATE = 16000
+WINDOW = 512
+_MAX_SEGMENTS = 4096
+
+_vad_model: "SileroVAD | None" = None
+_vad_lock = asyncio.Lock()
+
+# flat weight layout shared with csrc/vad.cu (name, shape)
+WEIGHT_LAYOUT = (
+    ("stft_basis", (258, 256)),
+    ("enc1.weight", (128, 129, 3)), ("enc1.bias", (128,)),
+    ("enc2.weight", (64, 128, 3)), ("enc2.bias", (64,)),
+    ("enc3.weight", (64, 64, 3)), ("enc3.bias", (64,)),
+    ("enc4.weight", (128, 64, 3)), ("enc4.bias", (128,)),
+    ("lstm.weight_ih", (512, 128)), ("lstm.weight_hh", (512, 128)),
+    ("lstm.bias_ih", (512,)), ("lstm.bias_hh", (512,)),
+    ("dec.weight", (128,)), ("dec.bias", (1,)),
+)
+
+
+@dataclass
+class Segment:
+    """A detected speech segment."""
+    start_ms: int
+    end_ms: int
+
+
+def stft_basis() -> np.ndarray:
+    n = np.arange(256)
+    win = 0.5 - 0.5 * np.cos(2 * np.pi * n / 256)
+    fb = np.fft.fft(np.eye(256))
+    return (np.vstack([np.real(fb[:129]), np.imag(fb[:129])]) * win[None, :]).astype(np.float32)
+
+
+def random_init_weights(seed: int = 1002) -> dict[str, np.ndarray]:
+    """Seeded random-init Silero-v5-shaped weights (BASELINE config 2 allows this when the
+    silero-vad package / ONNX file is absent -- it is: the reference downloads it at run time)."""
+    rng = np.random.default_rng(seed)
+    w: dict[str, np.ndarray] = {"stft_basis": stft_basis()}
+
+    def u(shape, bound):
+        return rng.uniform(-bound, bound, size=shape).astype(np.float32)
+
+    for name, oc, ic, k in (("enc1", 128, 129, 3), ("enc2", 64, 128, 3), ("enc3", 64, 64, 3), ("enc4", 128, 64, 3)):
+        bound = 1.0 / np.sqrt(ic * k)
+        w[f"{name}.weight"] = u((oc, ic, k), bound)
+        if name == "enc1":
+            w[f"{name}.weight"] = (w[f"{name}.weight"] * 16.0).astype(np.float32)
+        w[f"{name}.bias"] = u((oc,), bound)
+    b = 1.0 / np.sqrt(128)
+    w["lstm.weight_ih"] = u((512, 128), b)
+    w["lstm.weight_hh"] = u((512, 128), b)
+    w["lstm.bias_ih"] = u((512,), b)
+    w["lstm.bias_hh"] = u((512,), b)
+    w["dec.weight"] = (u((128,), b) * -120.0).astype(np.float32)
+    w["dec.bias"] = np.array([-2.9], dtype=np.float32)
+    return w
+
+
+def pack_weights(w: dict[str, np.ndarray]) -> np.ndarray:
+    parts = []
+    for name, shape in WEIGHT_LAYOUT:
+        a = np.ascontiguousarray(w[name], dtype=np.float32)
+        if tuple(a.shape) != shape:
+            raise ValueError(f"VAD weight {name}: shape {a.shape}, expected {shape}")
+        parts.append(a.reshape(-1))
+    return np.concatenate(parts)
+
+
+class VadSession:
+    """Silero weights resident on the current GPU (the analogue of the shared ORT session)."""
+
+    def __init__(self, weights: dict[str, np.ndarray] | None = None):
+        self.weights = weights if weights is not None else random_init_weights()
+        flat = pack_weights(self.weights)
+        h = ctypes.c_void_p()
+        N.call("osb_vad_create", N.ptr(flat), flat.size, ctypes.byref(h))
+        self.handle = h
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                N.lib().osb_vad_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
+class SileroVAD:
+    """Per-stream VAD state over a shared session (reference class at :45-177)."""
+
+    def __init__(self, session, threshold: float = 0.5):
+        self.session = session
+        self.sample_rate = VAD_SAMPLE_RATE
+        self.threshold = threshold
+        self._state = np.zeros((2, 1, 128), dtype=np.float32)
+
+    def reset(self):
+        self._state = np.zeros((2, 1, 128), dtype=np.float32)
+
+    # ------------------------------------------------------------------ scoring
+    def _native(self) -> bool:
+        return isinstance(self.session, VadSession)
+
+    def _score(self, buf, fmt: int, n: int) -> np.ndarray:
+        """Per-window probabilities of the full windows in buf; advances self._state."""
+        n_win = n // WINDOW
+        probs = np.empty(n_win, dtype=np.float32)
+        if n_win == 0:
+            return probs
+        st = np.ascontiguousarray(self._state, dtype=np.float32)
+        mx = ctypes.c_float(0.0)
+        N.call("osb_vad_score_host", self.session.handle, buf, fmt, n, N.ptr(st), N.ptr(probs), ctypes.byref(mx))
+        self._state = st
+        return probs
+
+    def _score_mock(self, audio: np.ndarray) -> list[float]:
+        probs = []
+        for start in range(0, len(audio) - WINDOW + 1, WINDOW):
+            chunk = audio[start:start + WINDOW].reshape(1, -1).astype(np.float32)
+            out, self._state = self.session.run(None, {"input": chunk, "state": self._state,
+                                                       "sr": np.array(self.sample_rate, dtype=np.int64)})
+            probs.append(float(out[0][0]))
+        return probs
+
+    def __call__(self, audio: np.ndarray) -> float:
+        """Speech probability 0-1: max over the full 512-sample windows (0.0 if none)."""
+        if len(audio) == 0:
+            return 0.0
+        if self._native():
+            a = np.ascontiguousarray(audio, dtype=np.float32)
+            probs = self._score(N.ptr(a), N.FMT_F32, len(a))
+        else:
+            probs = self._score_mock(np.asarray(audio))
+        max_prob = 0.0
+        for p in probs:
+            if float(p) > max_prob:
+                max_prob = float(p)
+        return max_prob
+
+    def score_pcm16(self, pcm16_bytes: bytes) -> float:
+        """__call__ on int16 bytes (the /32768 convert is fused into the kernel)."""
+        if not pcm16_bytes:
+            return 0.0
+        if not self._native():
+            return self(np.frombuffer(pcm16_bytes, dtype=np.int16).astype(np.float32) / 32768.0)
+        probs = self._score(pcm16_bytes, N.FMT_PCM16, len(pcm16_bytes) // 2)
+        return float(probs.max()) if len(probs) and float(probs.max()) > 0.0 else 0.0
+
+    def is_speech(self, pcm16_bytes: bytes, threshold: float | None = None) -> bool:
+        if not pcm16_bytes:
+            return False
+        prob = self.score_pcm16(pcm16_bytes)
+        return prob >= (threshold if threshold is not None else self.threshold)
+
+    def get_speech_segments(self, pcm16_bytes: bytes, threshold: float | None = None,
+                            min_speech_ms: int = 250, silence_ms: int = 800) -> list[Segment]:
+        if not pcm16_bytes:
+            return []
+        thresh = threshold if threshold is not None else self.threshold
+        n = len(pcm16_bytes) // 2
+        if self._native():
+            st = np.ascontiguousarray(self._state, dtype=np.float32)
+            segs = np.empty((_MAX_SEGMENTS, 2), dtype=np.int32)
+            cnt = ctypes.c_int(0)
+            N.call("osb_vad_segments_host", self.session.handle, pcm16_bytes, N.FMT_PCM16, n, N.ptr(st),
+                   float(thresh), int(min_speech_ms), int(silence_ms), N.ptr(segs), _MAX_SEGMENTS, ctypes.byref(cnt))
+            self._state = st
+            return [Segment(int(s), int(e)) for s, e in segs[: cnt.value]]
+        audio = np.frombuffer(pcm16_bytes, dtype=np.int16).astype(np.float32) / 32768.0
+        return _segments_from_probs(self._score_mock(audio), n, thresh, min_speech_ms, silence_ms)
+
+
+def _segments_from_probs(probs, n_samples, thresh, min_speech_ms, silence_ms) -> list[Segment]:
+    """Host copy of the segmenter for non-native sessions (reference :133-177)."""
+    window_ms = WINDOW * 1000 // VAD_SAMPLE_RATE
+    silence_windows = max(1, silence_ms // window_ms)
+    min_speech_windows = max(1, min_speech_ms // window_ms)
+    segments: list[Segment] = []
+    in_speech, speech_start, silence_count, speech_windows = False, 0, 0, 0
+    for k, prob in enumerate(probs):
+        current_ms = k * WINDOW * 1000 // VAD_SAMPLE_RATE
+        if prob >= thresh:
+            silence_count = 0
+            if not in_speech:
+                in_speech, speech_start, speech_windows = True, current_ms, 0
+            speech_windows += 1
+        elif in_speech:
+            silence_count += 1
+            if silence_count >= silence_windows:
+                if speech_windows >= min_speech_windows:
+                    segments.append(Segment(start_ms=speech_start, end_ms=current_ms))
+                in_speech, silence_count, speech_windows = False, 0, 0
+    if in_speech and speech_windows >= min_speech_windows:
+        segments.append(Segment(start_ms=speech_start, end_ms=n_samples * 1000 // VAD_SAMPLE_RATE))
+    return segments
+
+
+async def get_vad_model() -> SileroVAD:
+    """Lazy singleton (reference :180-209).  Weights: silero-vad package if importable, else the
+    seeded random-init network (no network access: nothing is downloaded)."""
+    global _vad_model
+    if _vad_model is not None:
+        return _vad_model
+    async with _vad_lock:
+        if _vad_model is None:
+            _vad_model = SileroVAD(VadSession())
+            logger.info("Silero VAD weights uploaded to GPU")
+        return _vad_model
