@@ -1,0 +1,166 @@
+// In-register small FFTs (forward, e^{-2 pi i nk/N}) used by the STFT kernels.
+// __host__ __device__ so the index arithmetic can be checked on the CPU (tests/host/fft_check.cu)
+// without a GPU.  All loops are fully unrolled with compile-time indices: arrays stay in registers
+// and the twiddle constants become immediates.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace osb {
+
+#define OSB_HD __host__ __device__ __forceinline__
+
+struct cpx {
+    float x, y;
+};
+OSB_HD cpx cmul(cpx a, cpx b) { return cpx{a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x}; }
+OSB_HD cpx cadd(cpx a, cpx b) { return cpx{a.x + b.x, a.y + b.y}; }
+OSB_HD cpx csub(cpx a, cpx b) { return cpx{a.x - b.x, a.y - b.y}; }
+OSB_HD cpx cmul_negi(cpx a) { return cpx{a.y, -a.x}; }  // a * (-i)
+OSB_HD cpx cconj(cpx a) { return cpx{a.x, -a.y}; }
+
+// cos/sin(2 pi k / 32), k = 0..15
+#define OSB_C32 { 1.0000000000e+00f, 9.8078528040e-01f, 9.2387953251e-01f, 8.3146961230e-01f, 7.0710678119e-01f, 5.5557023302e-01f, 3.8268343237e-01f, 1.9509032202e-01f, 6.1232339957e-17f, -1.9509032202e-01f, -3.8268343237e-01f, -5.5557023302e-01f, -7.0710678119e-01f, -8.3146961230e-01f, -9.2387953251e-01f, -9.8078528040e-01f }
+#define OSB_S32 { 0.0000000000e+00f, 1.9509032202e-01f, 3.8268343237e-01f, 5.5557023302e-01f, 7.0710678119e-01f, 8.3146961230e-01f, 9.2387953251e-01f, 9.8078528040e-01f, 1.0000000000e+00f, 9.8078528040e-01f, 9.2387953251e-01f, 8.3146961230e-01f, 7.0710678119e-01f, 5.5557023302e-01f, 3.8268343237e-01f, 1.9509032202e-01f }
+// cos/sin(2 pi k / 25), k = 0..24
+#define OSB_C25 { 1.0000000000e+00f, 9.6858316113e-01f, 8.7630668004e-01f, 7.2896862742e-01f, 5.3582679498e-01f, 3.0901699437e-01f, 6.2790519529e-02f, -1.8738131459e-01f, -4.2577929157e-01f, -6.3742398975e-01f, -8.0901699437e-01f, -9.2977648589e-01f, -9.9211470131e-01f, -9.9211470131e-01f, -9.2977648589e-01f, -8.0901699437e-01f, -6.3742398975e-01f, -4.2577929157e-01f, -1.8738131459e-01f, 6.2790519529e-02f, 3.0901699437e-01f, 5.3582679498e-01f, 7.2896862742e-01f, 8.7630668004e-01f, 9.6858316113e-01f }
+#define OSB_S25 { 0.0000000000e+00f, 2.4868988716e-01f, 4.8175367410e-01f, 6.8454710593e-01f, 8.4432792550e-01f, 9.5105651630e-01f, 9.9802672843e-01f, 9.8228725073e-01f, 9.0482705247e-01f, 7.7051324278e-01f, 5.8778525229e-01f, 3.6812455268e-01f, 1.2533323356e-01f, -1.2533323356e-01f, -3.6812455268e-01f, -5.8778525229e-01f, -7.7051324278e-01f, -9.0482705247e-01f, -9.8228725073e-01f, -9.9802672843e-01f, -9.5105651630e-01f, -8.4432792550e-01f, -6.8454710593e-01f, -4.8175367410e-01f, -2.4868988716e-01f }
+
+template <int N>
+OSB_HD constexpr int bitrev(int i) {
+    int r = 0;
+    for (int b = 1; b < N; b <<= 1) {
+        r = (r << 1) | (i & 1);
+        i >>= 1;
+    }
+    return r;
+}
+
+// forward FFT, N in {2,4,8,16,32}, natural order in -> natural order out.  INV: conjugate twiddles.
+template <int N, bool INV = false>
+OSB_HD void fft_pow2(cpx (&v)[N]) {
+    constexpr float c32[16] = OSB_C32;
+    constexpr float s32[16] = OSB_S32;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        const int j = bitrev<N>(i);
+        if (j > i) {
+            cpx t = v[i];
+            v[i] = v[j];
+            v[j] = t;
+        }
+    }
+#pragma unroll
+    for (int len = 2; len <= N; len <<= 1) {
+        const int half = len >> 1;
+        const int step = 32 / len;
+#pragma unroll
+        for (int b = 0; b < N; b += len) {
+#pragma unroll
+            for (int j = 0; j < half; ++j) {
+                const float wc = c32[j * step], ws = INV ? s32[j * step] : -s32[j * step];
+                const cpx a = v[b + j], q = v[b + j + half];
+                const cpx t = cpx{q.x * wc - q.y * ws, q.x * ws + q.y * wc};
+                v[b + j] = cadd(a, t);
+                v[b + j + half] = csub(a, t);
+            }
+        }
+    }
+}
+
+// 5-point DFT (Winograd form), forward
+OSB_HD void dft5(cpx& a0, cpx& a1, cpx& a2, cpx& a3, cpx& a4) {
+    const float c2 = 0.559016994374947f, s1 = 0.951056516295154f, s2 = 0.587785252292473f;
+    const cpx t1 = cadd(a1, a4), t2 = cadd(a2, a3), t3 = csub(a1, a4), t4 = csub(a2, a3);
+    const cpx t5 = cadd(t1, t2);
+    const cpx b0 = cadd(a0, t5);
+    const cpx m1 = cpx{a0.x - 0.25f * t5.x, a0.y - 0.25f * t5.y};
+    const cpx m2 = cpx{c2 * (t1.x - t2.x), c2 * (t1.y - t2.y)};
+    const cpx r1 = cadd(m1, m2), r2 = csub(m1, m2);
+    const cpx u1 = cpx{s1 * t3.x + s2 * t4.x, s1 * t3.y + s2 * t4.y};
+    const cpx u2 = cpx{s2 * t3.x - s1 * t4.x, s2 * t3.y - s1 * t4.y};
+    const cpx n1 = cmul_negi(u1), n2 = cmul_negi(u2);
+    a0 = b0;
+    a1 = cadd(r1, n1);
+    a4 = csub(r1, n1);
+    a2 = cadd(r2, n2);
+    a3 = csub(r2, n2);
+}
+
+// 25-point DFT, forward, natural in -> natural out (in place)
+OSB_HD void dft25(cpx (&v)[25]) {
+    constexpr float c25[25] = OSB_C25;
+    constexpr float s25[25] = OSB_S25;
+    // n = 5a + b ; k = c + 5d.  stage 1: DFT over a for each b -> T[b][c] stored at v[5c + b]
+#pragma unroll
+    for (int b = 0; b < 5; ++b) dft5(v[b], v[5 + b], v[10 + b], v[15 + b], v[20 + b]);
+    // twiddle W25^(b*c)
+#pragma unroll
+    for (int c = 1; c < 5; ++c)
+#pragma unroll
+        for (int b = 1; b < 5; ++b) {
+            const cpx w = cpx{c25[b * c], -s25[b * c]};
+            v[5 * c + b] = cmul(v[5 * c + b], w);
+        }
+    // stage 2: DFT over b for each c -> Y[c + 5d] at v[5c + d]
+#pragma unroll
+    for (int c = 0; c < 5; ++c) dft5(v[5 * c], v[5 * c + 1], v[5 * c + 2], v[5 * c + 3], v[5 * c + 4]);
+    // transpose (c,d) -> k = c + 5d
+    cpx o[25];
+#pragma unroll
+    for (int c = 0; c < 5; ++c)
+#pragma unroll
+        for (int d = 0; d < 5; ++d) o[c + 5 * d] = v[5 * c + d];
+#pragma unroll
+    for (int i = 0; i < 25; ++i) v[i] = o[i];
+}
+
+// ---------------------------------------------------------------- 400-point complex FFT (25 x 16 four-step)
+// Two real 400-sample frames A,B are packed as z = w*(A + iB).  n = 16*n1 + n2, k = k1 + 25*k2:
+//   step1(n2): 25-point DFT over n1, times W400^(n2*k1)      -> Y[k1][n2]
+//   step2(k1): 16-point FFT over n2                          -> Z[k1 + 25*k2] stored at [k1][k2]
+// Y/Z live in two float planes [25][17] (row padded to 17 so step-2 rows hit distinct banks).
+constexpr int kF400Stride = 17, kF400Plane = 25 * 17;
+
+OSB_HD void fft400_step1(const float* xa, const float* xb, const float* win, const float* twc, const float* tws, int n2,
+                         float* Yre, float* Yim) {
+    cpx v[25];
+#pragma unroll
+    for (int n1 = 0; n1 < 25; ++n1) {
+        const int idx = 16 * n1 + n2;
+        const float w = win[idx];
+        v[n1] = cpx{xa[idx] * w, xb[idx] * w};
+    }
+    dft25(v);
+#pragma unroll
+    for (int k1 = 0; k1 < 25; ++k1) {
+        const int t = n2 * k1;  // < 400
+        const cpx y = cmul(v[k1], cpx{twc[t], -tws[t]});
+        Yre[k1 * kF400Stride + n2] = y.x;
+        Yim[k1 * kF400Stride + n2] = y.y;
+    }
+}
+
+OSB_HD void fft400_step2(int k1, float* Yre, float* Yim) {
+    cpx v[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = cpx{Yre[k1 * kF400Stride + i], Yim[k1 * kF400Stride + i]};
+    fft_pow2<16>(v);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        Yre[k1 * kF400Stride + i] = v[i].x;
+        Yim[k1 * kF400Stride + i] = v[i].y;
+    }
+}
+
+OSB_HD int fft400_addr(int k) { return (k % 25) * kF400Stride + (k / 25); }
+
+// power spectra of the two packed real frames at bin k (0..200):  X_A = (Z[k]+conj Z[N-k])/2, X_B = (Z[k]-conj Z[N-k])/(2i)
+OSB_HD void fft400_pair_power(const float* Zre, const float* Zim, int k, float* pa, float* pb) {
+    const int a0 = fft400_addr(k), a1 = fft400_addr(k == 0 ? 0 : 400 - k);
+    const float zr = Zre[a0], zi = Zim[a0], yr = Zre[a1], yi = Zim[a1];
+    const float ar = zr + yr, ai = zi - yi, br = zi + yi, bi = yr - zr;
+    *pa = 0.25f * (ar * ar + ai * ai);
+    *pb = 0.25f * (br * br + bi * bi);
+}
+
+}  // namespace osb

@@ -37,7 +37,8 @@ def test_g711_encode_all_65536(gpu, golden):
         assert np.array_equal(out, golden[key])
     # ragged tail (n % 16 != 0)
     out = np.empty(1003, np.uint8)
-    gpu.call("osb_g711_encode_host", gpu.ptr(all16[30000:31003].copy()), gpu.ptr(out), 1003, gpu.FMT_ULAW)
+    part = all16[30000:31003].copy()  # keep a reference: gpu.ptr() is a bare address
+    gpu.call("osb_g711_encode_host", gpu.ptr(part), gpu.ptr(out), 1003, gpu.FMT_ULAW)
     assert np.array_equal(out, golden["codec_lin2ulaw_all"][30000:31003])
 
 
