@@ -117,6 +117,18 @@ int osb_vad_score_host(void* handle, const void* audio, int fmt, int64_t n, floa
 int osb_vad_segments_host(void* handle, const void* audio, int fmt, int64_t n, float* state, float threshold, int min_speech_ms,
                           int silence_ms, int32_t* segments, int max_seg, int* n_seg);
 
+/* ---------------------------------------------------------------- Whisper log-mel front-end
+ * replaces faster_whisper.FeatureExtractor.__call__(waveform, padding=160) (third-party; call site
+ * src/backends/faster_whisper.py:245, model ctor :40-45).  n_mels = 80 | 128.  Output is
+ * f32 [batch][n_mels][osb_logmel_frames(n)], frames contiguous.  fuse_normalize=1 (pcm16 input only)
+ * applies normalize_gain + int16 requantisation (src/audio/preprocessing.py:35-42, :23-25) while the
+ * samples are staged, i.e. the result equals FeatureExtractor(preprocess_stt_audio(clip)). */
+int osb_logmel_frames(int64_t n_samples);
+int osb_mel_filters(int n_mels, float* out, size_t capacity); /* f32 [n_mels][201], host buffer */
+int osb_logmel_dev(const void* d_audio, int fmt, int64_t n, int64_t batch, int64_t stride, int n_mels, float* d_out,
+                   int fuse_normalize, float target_dbfs, void* stream);
+int osb_logmel_host(const void* audio, int fmt, int64_t n, int n_mels, float* out, int fuse_normalize, float target_dbfs);
+
 #ifdef __cplusplus
 }
 #endif

@@ -80,6 +80,11 @@ struct HostWs {
 };
 HostWs& host_ws();
 
+// cross-file launchers (gain.cu)
+int launch_sumsq_pcm16(const int16_t* d_in, long long n, long long batch, long long stride, unsigned long long* d_sumsq, cudaStream_t st);
+int launch_normalize_f32(const float* d_in, void* d_out, int out_pcm16, long long n, long long batch, long long stride, int normalize,
+                         float target_dbfs, cudaStream_t st);
+
 static inline int grid_for(size_t work_items, int per_block, int max_waves = 8) {
     size_t b = (work_items + per_block - 1) / per_block;
     size_t cap = (size_t)OSB_NUM_SMS * max_waves;
@@ -138,6 +143,23 @@ __device__ __forceinline__ int quant_pcm16(float x) {
     x = fminf(fmaxf(x, -1.0f), 1.0f);
     return __float2int_rz(__fmul_rn(x, 32767.0f));
 }
+
+// gain exactly as normalize_gain forms it, in f32:  rms -> 20*log10 -> target - cur -> /20 -> 10**x
+// returns 1.0 and *silent=true when rms <= 1e-8 (the reference returns its input unchanged).
+__device__ __forceinline__ float gain_from_meansq(double mean_sq, float target_dbfs, bool* silent) {
+    float rms = __fsqrt_rn((float)mean_sq);
+    if (rms <= 1e-8f) { *silent = true; return 1.0f; }
+    *silent = false;
+    float cur = __fmul_rn(20.0f, log10f(rms));
+    float gdb = __fsub_rn(target_dbfs, cur);
+    return powf(10.0f, __fdiv_rn(gdb, 20.0f));
+}
+
+__device__ __forceinline__ float apply_gain(float x, float gain, bool silent) {
+    if (silent) return x;  // unchanged, NOT clipped (preprocessing.py:37-38)
+    return fminf(fmaxf(__fmul_rn(x, gain), -1.0f), 1.0f);
+}
+
 
 }  // namespace osb
 #endif

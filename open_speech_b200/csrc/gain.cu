@@ -113,22 +113,6 @@ __global__ void __launch_bounds__(256) k_sumsq_f32(const float* __restrict__ in,
     }
 }
 
-// gain exactly as normalize_gain forms it, in f32:  rms -> 20*log10 -> target - cur -> /20 -> 10**x
-// returns 1.0 and *silent=true when rms <= 1e-8 (the reference returns its input unchanged).
-__device__ __forceinline__ float gain_from_meansq(double mean_sq, float target_dbfs, bool* silent) {
-    float rms = __fsqrt_rn((float)mean_sq);
-    if (rms <= 1e-8f) { *silent = true; return 1.0f; }
-    *silent = false;
-    float cur = __fmul_rn(20.0f, log10f(rms));
-    float gdb = __fsub_rn(target_dbfs, cur);
-    return powf(10.0f, __fdiv_rn(gdb, 20.0f));
-}
-
-__device__ __forceinline__ float apply_gain(float x, float gain, bool silent) {
-    if (silent) return x;  // unchanged, NOT clipped (preprocessing.py:37-38)
-    return fminf(fmaxf(__fmul_rn(x, gain), -1.0f), 1.0f);
-}
-
 __global__ void __launch_bounds__(256) k_gain_requant_pcm16(const int16_t* __restrict__ in, int16_t* __restrict__ out,
                                                             long long n, long long stride, const unsigned long long* __restrict__ sumsq,
                                                             int normalize, float target_dbfs) {
@@ -182,6 +166,14 @@ static inline dim3 clip_grid(long long n, long long batch, int per_thread) {
     if (per_clip > want) per_clip = want;
     if (per_clip < 1) per_clip = 1;
     return dim3((unsigned)per_clip, (unsigned)batch);
+}
+
+int launch_sumsq_pcm16(const int16_t* d_in, long long n, long long batch, long long stride, unsigned long long* d_sumsq,
+                       cudaStream_t st) {
+    OSB_CUDA(cudaMemsetAsync(d_sumsq, 0, sizeof(unsigned long long) * batch, st));
+    OSB_LAUNCH(k_sumsq_pcm16, clip_grid(n, batch, 8), 256, 0, st, d_in, n, stride, d_sumsq);
+    OSB_CHECK_LAUNCH();
+    return OSB_OK;
 }
 
 }  // namespace osb
@@ -330,3 +322,10 @@ int osb_normalize_gain_f32_host(const float* in, void* out, int out_pcm16, int64
 }
 
 }  // extern "C"
+
+namespace osb {
+int launch_normalize_f32(const float* d_in, void* d_out, int out_pcm16, long long n, long long batch, long long stride, int normalize,
+                         float target_dbfs, cudaStream_t st) {
+    return ::normalize_gain_f32_impl(d_in, d_out, out_pcm16, n, batch, stride, normalize, target_dbfs, nullptr, st);
+}
+}  // namespace osb

@@ -1,0 +1,304 @@
+// Whisper-style log-mel front-end (n_fft 400, hop 160, 80/128 Slaney mel bins).
+//
+// Replaces the arithmetic of faster_whisper.FeatureExtractor.__call__(waveform, padding=160)
+// (third-party, pinned faster-whisper==1.2.1 in requirements.lock:7; call site
+// src/backends/faster_whisper.py:245; algorithm restated in SURVEY.md App. A.4 / oracle/stt.py):
+//   pad 160 zeros | reflect-pad 200 | frames 400/160 * periodic Hann | rfft | |.|^2, drop last frame |
+//   mel[n_mels,201] @ P | log10(max(.,1e-10)) | max(., global_max-8) | (.+4)/4
+// and, fused in front of it for the batch STT path, normalize_gain + int16 requantisation
+// (src/audio/preprocessing.py:35-42, :23-25): the reference hands faster-whisper a re-quantised WAV.
+//
+// Design (why not a DFT-GEMM): the direct 400x402 DFT as a GEMM costs 37 MFLOP per audio-second
+// (x3 for split-precision operands) and sits above the tensor ridge; a 25x16 four-step FFT that
+// packs two real frames into one complex transform costs ~1.2 MFLOP per audio-second on the FP32
+// pipe and keeps the stage closer to its HBM bound.  One CTA = 32 consecutive
+// frames of one clip: samples are staged once in shared memory (5,360 samples serve 32 overlapping
+// frames), the spectra never leave the SM, and only [n_mels x 32] floats are written, 128 B per row.
+#include <cmath>
+#include <map>
+#include <mutex>
+#include <vector>
+
+#include "common.cuh"
+#include "fft.cuh"
+
+namespace osb {
+
+constexpr int kNfft = 400, kHop = 160, kBins = 201, kPad = 160;
+constexpr int MF = 32;                             // frames per CTA
+constexpr int kXs = kHop * (MF - 1) + kNfft;       // 5360 staged samples
+constexpr int kPStride = MF + 1;                   // power tile [201][33]
+
+struct MelTables {
+    int n_mels = 0;
+    std::vector<float> dense;   // [n_mels][201] f32 (what FeatureExtractor.mel_filters holds)
+    float* d_consts = nullptr;  // win[400], twc[400], tws[400]
+    int* d_start = nullptr;     // [n_mels] first non-zero bin
+    int* d_len = nullptr;       // [n_mels]
+    int* d_off = nullptr;       // [n_mels] offset into d_w
+    float* d_w = nullptr;
+};
+
+// faster_whisper.FeatureExtractor.get_mel_filters(16000, 400, n_mels): Slaney scale + area norm
+static void build_mel(int n_mels, std::vector<float>& dense) {
+    const int sr = 16000;
+    const double val = 1.0 / (kNfft * (1.0 / sr));
+    std::vector<double> fft(kBins), mels(n_mels + 2), freqs(n_mels + 2);
+    for (int k = 0; k < kBins; ++k) fft[k] = k * val;
+    const double max_mel = 45.245640471924965, step = max_mel / (n_mels + 1);
+    for (int i = 0; i < n_mels + 2; ++i) mels[i] = i * step;
+    mels[n_mels + 1] = max_mel;
+    const double f_sp = 200.0 / 3, min_log_hz = 1000.0, min_log_mel = min_log_hz / f_sp, logstep = std::log(6.4) / 27.0;
+    for (int i = 0; i < n_mels + 2; ++i)
+        freqs[i] = mels[i] >= min_log_mel ? min_log_hz * std::exp(logstep * (mels[i] - min_log_mel)) : f_sp * mels[i];
+    dense.assign((size_t)n_mels * kBins, 0.f);
+    for (int m = 0; m < n_mels; ++m) {
+        const double fd0 = freqs[m + 1] - freqs[m], fd1 = freqs[m + 2] - freqs[m + 1];
+        const double enorm = 2.0 / (freqs[m + 2] - freqs[m]);
+        for (int k = 0; k < kBins; ++k) {
+            const double lower = -(freqs[m] - fft[k]) / fd0, upper = (freqs[m + 2] - fft[k]) / fd1;
+            double w = lower < upper ? lower : upper;
+            if (w < 0) w = 0;
+            dense[(size_t)m * kBins + k] = (float)(w * enorm);
+        }
+    }
+}
+
+static std::mutex g_mel_mu;
+static std::map<long long, MelTables> g_mel;
+
+static int get_mel(int n_mels, bool need_device, const MelTables** out) {
+    int dev = 0;
+    if (need_device) OSB_CUDA(cudaGetDevice(&dev));
+    const long long key = ((long long)(need_device ? dev + 1 : 0) << 32) | (unsigned)n_mels;
+    std::lock_guard<std::mutex> lk(g_mel_mu);
+    auto it = g_mel.find(key);
+    if (it == g_mel.end()) {
+        MelTables t;
+        t.n_mels = n_mels;
+        build_mel(n_mels, t.dense);
+        if (need_device) {
+            std::vector<float> consts(1200);
+            const double pi = 3.14159265358979323846;
+            for (int i = 0; i < 400; ++i) {
+                consts[i] = (float)(0.5 - 0.5 * std::cos(2.0 * pi * i / 400.0));  // np.hanning(401)[:-1] -> f32
+                consts[400 + i] = (float)std::cos(2.0 * pi * i / 400.0);
+                consts[800 + i] = (float)std::sin(2.0 * pi * i / 400.0);
+            }
+            std::vector<int> start(n_mels), len(n_mels), off(n_mels);
+            std::vector<float> w;
+            for (int m = 0; m < n_mels; ++m) {
+                int a = -1, b = -1;
+                for (int k = 0; k < kBins; ++k)
+                    if (t.dense[(size_t)m * kBins + k] != 0.f) { if (a < 0) a = k; b = k; }
+                start[m] = a < 0 ? 0 : a;
+                len[m] = a < 0 ? 0 : b - a + 1;
+                off[m] = (int)w.size();
+                for (int k = 0; k < len[m]; ++k) w.push_back(t.dense[(size_t)m * kBins + start[m] + k]);
+            }
+            w.push_back(0.f);
+            OSB_CUDA(cudaMalloc(&t.d_consts, consts.size() * 4));
+            OSB_CUDA(cudaMemcpy(t.d_consts, consts.data(), consts.size() * 4, cudaMemcpyHostToDevice));
+            OSB_CUDA(cudaMalloc(&t.d_start, n_mels * 4)); OSB_CUDA(cudaMemcpy(t.d_start, start.data(), n_mels * 4, cudaMemcpyHostToDevice));
+            OSB_CUDA(cudaMalloc(&t.d_len, n_mels * 4)); OSB_CUDA(cudaMemcpy(t.d_len, len.data(), n_mels * 4, cudaMemcpyHostToDevice));
+            OSB_CUDA(cudaMalloc(&t.d_off, n_mels * 4)); OSB_CUDA(cudaMemcpy(t.d_off, off.data(), n_mels * 4, cudaMemcpyHostToDevice));
+            OSB_CUDA(cudaMalloc(&t.d_w, w.size() * 4)); OSB_CUDA(cudaMemcpy(t.d_w, w.data(), w.size() * 4, cudaMemcpyHostToDevice));
+        }
+        it = g_mel.emplace(key, std::move(t)).first;
+    }
+    *out = &it->second;
+    return OSB_OK;
+}
+
+struct MelArgs {
+    const void* audio;
+    long long n, stride;
+    int fmt, n_frames, n_mels;
+    float* out;                            // [batch][n_mels][n_frames] raw log10 values
+    unsigned int* gmax;                    // [batch] bits of (max log10 + 10) >= 0
+    const unsigned long long* sumsq;       // fused normalise (pcm16 only), else null
+    float target_dbfs;
+    const float* consts;
+    const int *mel_start, *mel_len, *mel_off;
+    const float* mel_w;
+};
+
+__global__ void __launch_bounds__(256, 2) k_logmel(MelArgs a) {
+    extern __shared__ __align__(16) float sm[];
+    float* xs = sm;                       // [kXs]
+    float* win = xs + kXs;                // [400]
+    float* twc = win + 400;               // [400]
+    float* tws = twc + 400;               // [400]
+    float* Y = tws + 400;                 // [16][2][425]
+    float* P = Y + 16 * 2 * kF400Plane;   // [201][33]
+    const int tid = threadIdx.x, b = blockIdx.y, t0 = blockIdx.x * MF;
+
+    for (int i = tid; i < 1200; i += 256) win[i] = a.consts[i];
+    {
+        // stage the tile's samples: reflect pad 200 around [x, 160 zeros]; fused normalise + requantise
+        bool silent = true;
+        float gain = 1.0f;
+        if (a.sumsq) gain = gain_from_meansq((double)a.sumsq[b] / 1073741824.0 / (double)a.n, a.target_dbfs, &silent);
+        const long long L = a.n + kPad;
+        const long long p0 = (long long)kHop * t0 - kNfft / 2;
+        for (int i = tid; i < kXs; i += 256) {
+            long long p = p0 + i;
+            while (p < 0 || p >= L) p = p < 0 ? -p : 2 * (L - 1) - p;
+            float v = 0.f;
+            if (p < a.n) {
+                if (a.fmt == OSB_FMT_PCM16) {
+                    const float x = __fdiv_rn((float)reinterpret_cast<const int16_t*>(a.audio)[(long long)b * a.stride + p], 32768.0f);
+                    v = a.sumsq ? __fdiv_rn((float)quant_pcm16(apply_gain(x, gain, silent)), 32768.0f) : x;
+                } else {
+                    v = reinterpret_cast<const float*>(a.audio)[(long long)b * a.stride + p];
+                }
+            }
+            xs[i] = v;
+        }
+    }
+    __syncthreads();
+    {   // four-step FFT, step 1: 16 frame pairs x 16 residues = 256 tasks
+        const int q = tid >> 4, n2 = tid & 15;
+        fft400_step1(xs + (2 * q) * kHop, xs + (2 * q + 1) * kHop, win, twc, tws, n2, Y + q * 2 * kF400Plane, Y + q * 2 * kF400Plane + kF400Plane);
+    }
+    __syncthreads();
+    for (int task = tid; task < 16 * 25; task += 256) {  // step 2: 16 pairs x 25 rows
+        const int q = task / 25, k1 = task - q * 25;
+        fft400_step2(k1, Y + q * 2 * kF400Plane, Y + q * 2 * kF400Plane + kF400Plane);
+    }
+    __syncthreads();
+    for (int task = tid; task < 16 * kBins; task += 256) {  // power of both frames of each pair
+        const int q = task / kBins, k = task - q * kBins;
+        float pa, pb;
+        fft400_pair_power(Y + q * 2 * kF400Plane, Y + q * 2 * kF400Plane + kF400Plane, k, &pa, &pb);
+        P[k * kPStride + 2 * q] = pa;
+        P[k * kPStride + 2 * q + 1] = pb;
+    }
+    __syncthreads();
+    // sparse mel contraction (each triangle touches a few bins) + log10; lanes = consecutive frames
+    const int f = tid & 31;
+    const bool live = (t0 + f) < a.n_frames;
+    float vmax = -10.0f;
+    float* outb = a.out + (long long)b * a.n_mels * a.n_frames + t0 + f;
+    for (int m = tid >> 5; m < a.n_mels; m += 8) {
+        const int s = __ldg(a.mel_start + m), len = __ldg(a.mel_len + m);
+        const float* w = a.mel_w + __ldg(a.mel_off + m);
+        float acc = 0.f;
+        for (int i = 0; i < len; ++i) acc = fmaf(__ldg(w + i), P[(s + i) * kPStride + f], acc);
+        const float v = log10f(fmaxf(acc, 1e-10f));
+        if (live) {
+            outb[(long long)m * a.n_frames] = v;
+            vmax = fmaxf(vmax, v);
+        }
+    }
+    vmax = warp_max(vmax);
+    if ((tid & 31) == 0) atomicMax(a.gmax + b, __float_as_uint(vmax + 10.0f));
+}
+
+// log_spec = maximum(log_spec, log_spec.max() - 8.0); (log_spec + 4.0) / 4.0
+__global__ void __launch_bounds__(256) k_logmel_finalize(float* __restrict__ out, long long per_clip, const unsigned int* __restrict__ gmax) {
+    const float thr = (__uint_as_float(gmax[blockIdx.y]) - 10.0f) - 8.0f;
+    float* o = out + (long long)blockIdx.y * per_clip;
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nthr = (long long)gridDim.x * blockDim.x;
+    const bool aligned = (((uintptr_t)o) & 15) == 0;
+    const long long nvec = aligned ? per_clip / 4 : 0;
+    for (long long v = tid; v < nvec; v += nthr) {
+        float4 x = reinterpret_cast<float4*>(o)[v];
+        x.x = __fdiv_rn(__fadd_rn(fmaxf(x.x, thr), 4.0f), 4.0f);
+        x.y = __fdiv_rn(__fadd_rn(fmaxf(x.y, thr), 4.0f), 4.0f);
+        x.z = __fdiv_rn(__fadd_rn(fmaxf(x.z, thr), 4.0f), 4.0f);
+        x.w = __fdiv_rn(__fadd_rn(fmaxf(x.w, thr), 4.0f), 4.0f);
+        reinterpret_cast<float4*>(o)[v] = x;
+    }
+    for (long long i = nvec * 4 + tid; i < per_clip; i += nthr) o[i] = __fdiv_rn(__fadd_rn(fmaxf(o[i], thr), 4.0f), 4.0f);
+}
+
+constexpr int kLogmelSmem = (kXs + 1200 + 16 * 2 * kF400Plane + kBins * kPStride) * (int)sizeof(float);
+
+int launch_logmel(const void* d_audio, int fmt, long long n, long long batch, long long stride, int n_mels, float* d_out,
+                  const unsigned long long* d_sumsq, float target_dbfs, cudaStream_t st) {
+    const MelTables* t;
+    int rc = get_mel(n_mels, true, &t);
+    if (rc) return rc;
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, [&] { attr_err = cudaFuncSetAttribute(k_logmel, cudaFuncAttributeMaxDynamicSharedMemorySize, kLogmelSmem); });
+    OSB_CUDA(attr_err);
+    const int n_frames = (int)((n + kPad) / kHop);
+    Scratch scr(st);
+    unsigned int* gmax;
+    OSB_CUDA(scr.alloc(&gmax, (size_t)batch));
+    OSB_CUDA(cudaMemsetAsync(gmax, 0, sizeof(unsigned int) * batch, st));
+    MelArgs a;
+    a.audio = d_audio; a.n = n; a.stride = stride; a.fmt = fmt; a.n_frames = n_frames; a.n_mels = n_mels;
+    a.out = d_out; a.gmax = gmax; a.sumsq = d_sumsq; a.target_dbfs = target_dbfs;
+    a.consts = t->d_consts; a.mel_start = t->d_start; a.mel_len = t->d_len; a.mel_off = t->d_off; a.mel_w = t->d_w;
+    dim3 grid((n_frames + MF - 1) / MF, (unsigned)batch);
+    OSB_LAUNCH(k_logmel, grid, 256, kLogmelSmem, st, a);
+    OSB_CHECK_LAUNCH();
+    const long long per_clip = (long long)n_mels * n_frames;
+    long long fb = (per_clip / 4 + 255) / 256;
+    long long want = ((long long)OSB_NUM_SMS * 8 + batch - 1) / batch;
+    if (fb > want) fb = want;
+    if (fb < 1) fb = 1;
+    OSB_LAUNCH(k_logmel_finalize, dim3((unsigned)fb, (unsigned)batch), 256, 0, st, d_out, per_clip, gmax);
+    OSB_CHECK_LAUNCH();
+    return OSB_OK;
+}
+
+}  // namespace osb
+
+using namespace osb;
+
+extern "C" {
+
+int osb_logmel_frames(int64_t n_samples) { return n_samples < 0 ? 0 : (int)((n_samples + kPad) / kHop); }
+
+int osb_mel_filters(int n_mels, float* out, size_t capacity) {
+    OSB_REQUIRE(n_mels == 80 || n_mels == 128, "n_mels must be 80 or 128");
+    OSB_REQUIRE(out && capacity >= (size_t)n_mels * kBins, "mel filter buffer too small");
+    const MelTables* t;
+    int rc = get_mel(n_mels, false, &t);
+    if (rc) return rc;
+    memcpy(out, t->dense.data(), sizeof(float) * n_mels * kBins);
+    return OSB_OK;
+}
+
+int osb_logmel_dev(const void* d_audio, int fmt, int64_t n, int64_t batch, int64_t stride, int n_mels, float* d_out,
+                   int fuse_normalize, float target_dbfs, void* stream) {
+    int rc = ensure_init();
+    if (rc) return rc;
+    OSB_REQUIRE(fmt == OSB_FMT_PCM16 || fmt == OSB_FMT_F32, "fmt must be OSB_FMT_PCM16 or OSB_FMT_F32");
+    OSB_REQUIRE(n_mels == 80 || n_mels == 128, "n_mels must be 80 or 128");
+    OSB_REQUIRE(n >= 0 && batch >= 0 && stride >= n, "bad sizes");
+    OSB_REQUIRE(!fuse_normalize || fmt == OSB_FMT_PCM16, "fused normalise needs pcm16 input");
+    OSB_REQUIRE(batch <= 65535, "batch too large (<= 65535)");
+    if (batch == 0) return OSB_OK;
+    OSB_REQUIRE(n + kPad > kNfft / 2, "clip too short for reflect padding (needs n + 160 > 200)");
+    OSB_REQUIRE(d_audio && d_out, "null buffer");
+    cudaStream_t st = (cudaStream_t)stream;
+    Scratch scr(st);
+    unsigned long long* sumsq = nullptr;
+    if (fuse_normalize) {
+        OSB_CUDA(scr.alloc(&sumsq, (size_t)batch));
+        if ((rc = launch_sumsq_pcm16((const int16_t*)d_audio, n, batch, stride, sumsq, st))) return rc;
+    }
+    return launch_logmel(d_audio, fmt, n, batch, stride, n_mels, d_out, sumsq, target_dbfs, st);
+}
+
+int osb_logmel_host(const void* audio, int fmt, int64_t n, int n_mels, float* out, int fuse_normalize, float target_dbfs) {
+    HostWs& ws = host_ws();
+    int rc = ws.prepare();
+    if (rc) return rc;
+    OSB_REQUIRE(fmt == OSB_FMT_PCM16 || fmt == OSB_FMT_F32, "fmt must be OSB_FMT_PCM16 or OSB_FMT_F32");
+    OSB_REQUIRE(n >= 0 && out, "bad arguments");
+    const size_t es = fmt == OSB_FMT_PCM16 ? 2 : 4;
+    const size_t ob = (size_t)n_mels * osb_logmel_frames(n) * 4;
+    void *da, *dout;
+    if ((rc = ws.dev_buf(0, (size_t)n * es + 16, &da)) || (rc = ws.dev_buf(1, ob + 16, &dout))) return rc;
+    if ((rc = ws.h2d(da, audio, (size_t)n * es))) return rc;
+    if ((rc = osb_logmel_dev(da, fmt, n, 1, n, n_mels, (float*)dout, fuse_normalize, target_dbfs, ws.stream))) return rc;
+    return ws.d2h(out, dout, ob);
+}
+
+}  // extern "C"
