@@ -129,6 +129,27 @@ int osb_logmel_dev(const void* d_audio, int fmt, int64_t n, int64_t batch, int64
                    int fuse_normalize, float target_dbfs, void* stream);
 int osb_logmel_host(const void* audio, int fmt, int64_t n, int n_mels, float* out, int fuse_normalize, float target_dbfs);
 
+/* ---------------------------------------------------------------- spectral-gating noise reduction
+ * replaces reduce_noise (src/audio/preprocessing.py:45-50) = noisereduce.reduce_noise(y, sr) with all
+ * defaults (non-stationary gate; STFT 1024/256; 600,000-sample chunks with 30,000 samples of context).
+ * Output f32 [batch][stride] (first n of each row). */
+int osb_spectral_gate_dev(const void* d_audio, int fmt, int64_t n, int64_t batch, int64_t stride, int sample_rate, float* d_out,
+                          void* stream);
+int osb_spectral_gate_host(const void* audio, int fmt, float* out, int64_t n, int sample_rate);
+
+/* ---------------------------------------------------------------- composed STT paths
+ * osb_preprocess_stt_host = preprocess_stt_audio (src/audio/preprocessing.py:53-63) after header parsing:
+ * interleaved int16 (n values, `channels` channels) -> mono f32 -> [reduce_noise] -> [normalize_gain] ->
+ * requantised int16 (n / channels values).
+ * osb_stt_frontend_*: BASELINE configs 1 / 4 -- the same chain followed by the log-mel front-end that
+ * faster-whisper applies to the WAV it is handed: pcm16 [batch][stride] -> f32 [batch][n_mels][frames]. */
+int osb_preprocess_stt_host(const int16_t* in, int64_t n, int channels, int sample_rate, int noise_reduce, int normalize,
+                            float target_dbfs, int16_t* out);
+int osb_stt_frontend_dev(const int16_t* d_pcm, int64_t n, int64_t batch, int64_t stride, int sample_rate, int noise_reduce,
+                         int normalize, int n_mels, float* d_mel, void* stream);
+int osb_stt_frontend_host(const int16_t* pcm, int64_t n, int64_t batch, int64_t stride, int sample_rate, int noise_reduce,
+                          int normalize, int n_mels, float* mel);
+
 #ifdef __cplusplus
 }
 #endif

@@ -80,7 +80,11 @@ struct HostWs {
 };
 HostWs& host_ws();
 
-// cross-file launchers (gain.cu)
+// cross-file launchers (logmel.cu, spectral_gate.cu, gain.cu)
+int launch_logmel(const void* d_audio, int fmt, long long n, long long batch, long long stride, int n_mels, float* d_out,
+                  const unsigned long long* d_sumsq, float target_dbfs, cudaStream_t st);
+int launch_spectral_gate(const void* d_audio, int fmt, long long n, long long batch, long long stride, int sr, float* d_out,
+                         cudaStream_t st);
 int launch_sumsq_pcm16(const int16_t* d_in, long long n, long long batch, long long stride, unsigned long long* d_sumsq, cudaStream_t st);
 int launch_normalize_f32(const float* d_in, void* d_out, int out_pcm16, long long n, long long batch, long long stride, int normalize,
                          float target_dbfs, cudaStream_t st);

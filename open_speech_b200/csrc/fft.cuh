@@ -26,43 +26,49 @@ OSB_HD cpx cconj(cpx a) { return cpx{a.x, -a.y}; }
 #define OSB_S25 { 0.0000000000e+00f, 2.4868988716e-01f, 4.8175367410e-01f, 6.8454710593e-01f, 8.4432792550e-01f, 9.5105651630e-01f, 9.9802672843e-01f, 9.8228725073e-01f, 9.0482705247e-01f, 7.7051324278e-01f, 5.8778525229e-01f, 3.6812455268e-01f, 1.2533323356e-01f, -1.2533323356e-01f, -3.6812455268e-01f, -5.8778525229e-01f, -7.7051324278e-01f, -9.0482705247e-01f, -9.8228725073e-01f, -9.9802672843e-01f, -9.5105651630e-01f, -8.4432792550e-01f, -6.8454710593e-01f, -4.8175367410e-01f, -2.4868988716e-01f }
 
 template <int N>
+struct Log2 {
+    static constexpr int value = 1 + Log2<N / 2>::value;
+};
+template <>
+struct Log2<1> {
+    static constexpr int value = 0;
+};
+
+template <int N>
 OSB_HD constexpr int bitrev(int i) {
     int r = 0;
-    for (int b = 1; b < N; b <<= 1) {
-        r = (r << 1) | (i & 1);
-        i >>= 1;
-    }
+    for (int b = 0; b < Log2<N>::value; ++b) r |= ((i >> b) & 1) << (Log2<N>::value - 1 - b);
     return r;
 }
 
 // forward FFT, N in {2,4,8,16,32}, natural order in -> natural order out.  INV: conjugate twiddles.
+// Every loop has a compile-time trip count so that v[] stays in registers.
 template <int N, bool INV = false>
 OSB_HD void fft_pow2(cpx (&v)[N]) {
     constexpr float c32[16] = OSB_C32;
     constexpr float s32[16] = OSB_S32;
 #pragma unroll
     for (int i = 0; i < N; ++i) {
+        constexpr int dummy = 0;
+        (void)dummy;
         const int j = bitrev<N>(i);
         if (j > i) {
-            cpx t = v[i];
+            const cpx t = v[i];
             v[i] = v[j];
             v[j] = t;
         }
     }
 #pragma unroll
-    for (int len = 2; len <= N; len <<= 1) {
-        const int half = len >> 1;
-        const int step = 32 / len;
+    for (int s = 1; s <= Log2<N>::value; ++s) {
+        const int len = 1 << s, half = len >> 1, step = 32 >> s;
 #pragma unroll
-        for (int b = 0; b < N; b += len) {
-#pragma unroll
-            for (int j = 0; j < half; ++j) {
-                const float wc = c32[j * step], ws = INV ? s32[j * step] : -s32[j * step];
-                const cpx a = v[b + j], q = v[b + j + half];
-                const cpx t = cpx{q.x * wc - q.y * ws, q.x * ws + q.y * wc};
-                v[b + j] = cadd(a, t);
-                v[b + j + half] = csub(a, t);
-            }
+        for (int g = 0; g < N / 2; ++g) {
+            const int blk = g / half, j = g - blk * half, b = blk * len;
+            const float wc = c32[j * step], ws = INV ? s32[j * step] : -s32[j * step];
+            const cpx a = v[b + j], q = v[b + j + half];
+            const cpx t = cpx{q.x * wc - q.y * ws, q.x * ws + q.y * wc};
+            v[b + j] = cadd(a, t);
+            v[b + j + half] = csub(a, t);
         }
     }
 }

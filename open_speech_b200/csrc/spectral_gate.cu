@@ -1,0 +1,454 @@
+// Non-stationary spectral-gating noise reduction.
+//
+// Replaces noisereduce.reduce_noise(y=audio, sr=sr) with every default, as called by reduce_noise
+// (reference src/audio/preprocessing.py:45-50; third-party noisereduce>=3.0, pyproject.toml:38; algorithm
+// restated in SURVEY.md App. A.5 / oracle/stt.py spectral_gate):
+//   chunks of 600,000 samples with 30,000 samples of context (zeros beyond the clip) |
+//   scipy.signal.stft(nperseg 1024, hop 256, periodic Hann, boundary zeros, spectrum scaling) |
+//   A=|S| ; A_s = filtfilt([b],[1,b-1],A) along time ; M = sigmoid(((A-A_s)/A_s - 2)*10) |
+//   M = conv2d_same(M, tri(33) x tri(7) / sum) ; istft(S*M) ; keep the centre.
+// The reference runs this in float64; here the FFTs run in float32 (relative error ~1e-6, far inside the
+// 1e-4 budget) and the one-pole recurrences keep a float64 state.
+//
+// Kernels: k_nr_stft (two real frames per complex 32x32 four-step FFT, samples staged once per 16 frames)
+//          k_nr_iir_fwd / k_nr_iir_bwd_mask (one thread per (chunk, bin), sequential in time, coalesced over bins)
+//          k_nr_smooth (separable 33x7 stencil in shared memory)
+//          k_nr_istft (32 frames -> 29 hop blocks per CTA, overlap-add in shared memory, one store per sample)
+#include <cmath>
+#include <map>
+#include <mutex>
+#include <vector>
+
+#include "common.cuh"
+#include "fft.cuh"
+
+namespace osb {
+
+constexpr int NF = 1024, NH = 256, NB = 513;       // n_fft, hop, one-sided bins
+constexpr long long kChunk = 600000, kCtx = 30000;
+constexpr int kYs = 33, kYPlane = 32 * 33;          // four-step planes [32][33]
+
+struct NrGeom {
+    long long n;       // samples per clip
+    long long stride;  // samples between clips
+    int n_chunks;
+    long long Lc;      // padded chunk length
+    int F;             // frames per chunk
+    int batch;
+    int fmt;
+};
+
+struct NrTables {
+    float* d = nullptr;  // win[1024], cos[1024], sin[1024], ola_scale[256]
+};
+static std::mutex g_nr_mu;
+static std::map<int, NrTables> g_nr;
+
+static int get_nr_tables(const float** out) {
+    int dev = 0;
+    OSB_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(g_nr_mu);
+    auto it = g_nr.find(dev);
+    if (it == g_nr.end()) {
+        std::vector<float> h(3 * NF + NH);
+        std::vector<double> w(NF);
+        const double pi = 3.14159265358979323846;
+        for (int i = 0; i < NF; ++i) {
+            w[i] = 0.5 - 0.5 * std::cos(2.0 * pi * i / NF);  // get_window('hann', 1024) (periodic)
+            h[i] = (float)w[i];
+            h[NF + i] = (float)std::cos(2.0 * pi * i / NF);
+            h[2 * NF + i] = (float)std::sin(2.0 * pi * i / NF);
+        }
+        for (int r = 0; r < NH; ++r) {
+            // istft: x *= win.sum() (=512); x /= sum_t win^2 ; our inverse FFT is unnormalised (x 1/1024)
+            const double norm = w[r] * w[r] + w[r + 256] * w[r + 256] + w[r + 512] * w[r + 512] + w[r + 768] * w[r + 768];
+            h[3 * NF + r] = (float)(512.0 / 1024.0 / norm);
+        }
+        NrTables t;
+        OSB_CUDA(cudaMalloc(&t.d, h.size() * 4));
+        OSB_CUDA(cudaMemcpy(t.d, h.data(), h.size() * 4, cudaMemcpyHostToDevice));
+        it = g_nr.emplace(dev, t).first;
+    }
+    *out = it->second.d;
+    return OSB_OK;
+}
+
+__device__ __forceinline__ float nr_sample(const void* audio, const NrGeom& g, int clip, int chunk, long long p) {
+    // p: chunk coordinate; zeros outside the chunk (stft boundary) and outside the clip (chunk context)
+    if (p < 0 || p >= g.Lc) return 0.f;
+    const long long i = (long long)chunk * kChunk - kCtx + p;
+    if (i < 0 || i >= g.n) return 0.f;
+    if (g.fmt == OSB_FMT_PCM16) return __fdiv_rn((float)reinterpret_cast<const int16_t*>(audio)[(long long)clip * g.stride + i], 32768.0f);
+    return reinterpret_cast<const float*>(audio)[(long long)clip * g.stride + i];
+}
+
+// ---------------------------------------------------------------- forward STFT
+// grid (ceil(F/16), n_chunks, batch), 256 threads.  S[((clip*n_chunks+chunk)*F + t)*513 + f]
+constexpr int kStftFrames = 16, kStftXs = NH * (kStftFrames - 1) + NF;  // 4864
+
+__global__ void __launch_bounds__(256, 2) k_nr_stft(const void* __restrict__ audio, NrGeom g, const float* __restrict__ tabs,
+                                                    float2* __restrict__ S) {
+    extern __shared__ __align__(16) float sm[];
+    float* xs = sm;                 // [4864]
+    float* win = xs + kStftXs;      // [1024]
+    float* twc = win + NF;          // [1024]
+    float* tws = twc + NF;          // [1024]
+    float* Y = tws + NF;            // [8][2][32*33]
+    const int tid = threadIdx.x, t0 = blockIdx.x * kStftFrames, chunk = blockIdx.y, clip = blockIdx.z;
+    for (int i = tid; i < 3 * NF; i += 256) win[i] = tabs[i];
+    const long long p0 = (long long)NH * t0 - NF / 2;
+    for (int i = tid; i < kStftXs; i += 256) xs[i] = nr_sample(audio, g, clip, chunk, p0 + i);
+    __syncthreads();
+    {   // step 1: 8 frame pairs x 32 residues.  n = 32*n1 + n2
+        const int q = tid >> 5, n2 = tid & 31;
+        const float* xa = xs + (2 * q) * NH;
+        const float* xb = xa + NH;
+        cpx v[32];
+#pragma unroll
+        for (int n1 = 0; n1 < 32; ++n1) {
+            const int idx = 32 * n1 + n2;
+            const float w = win[idx];
+            v[n1] = cpx{xa[idx] * w, xb[idx] * w};
+        }
+        fft_pow2<32>(v);
+        float* yr = Y + q * 2 * kYPlane;
+        float* yi = yr + kYPlane;
+#pragma unroll
+        for (int k1 = 0; k1 < 32; ++k1) {
+            const int tw = n2 * k1;  // < 1024
+            const cpx y = cmul(v[k1], cpx{twc[tw], -tws[tw]});
+            yr[k1 * kYs + n2] = y.x;
+            yi[k1 * kYs + n2] = y.y;
+        }
+    }
+    __syncthreads();
+    {   // step 2: 32-point FFT over n2 for each (pair, k1): Z[k1 + 32*k2] stored at [k1][k2]
+        const int q = tid >> 5, k1 = tid & 31;
+        float* yr = Y + q * 2 * kYPlane;
+        float* yi = yr + kYPlane;
+        cpx v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = cpx{yr[k1 * kYs + i], yi[k1 * kYs + i]};
+        fft_pow2<32>(v);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            yr[k1 * kYs + i] = v[i].x;
+            yi[k1 * kYs + i] = v[i].y;
+        }
+    }
+    __syncthreads();
+    // split the packed transform into the two one-sided spectra, apply the spectrum scaling 1/sum(win) = 1/512
+    const float sc = 0.5f / 512.0f;
+    const long long row0 = ((long long)clip * g.n_chunks + chunk) * g.F;
+    for (int task = tid; task < 8 * NB; task += 256) {
+        const int q = task / NB, f = task - q * NB;
+        const int ta = t0 + 2 * q;
+        if (ta >= g.F) continue;
+        const float* yr = Y + q * 2 * kYPlane;
+        const float* yi = yr + kYPlane;
+        const int m = (NF - f) & (NF - 1);
+        const int a0 = (f & 31) * kYs + (f >> 5), a1 = (m & 31) * kYs + (m >> 5);
+        const float zr = yr[a0], zi = yi[a0], wr = yr[a1], wi = yi[a1];
+        // X_a = (Z[f] + conj Z[N-f])/2 ; X_b = (Z[f] - conj Z[N-f])/(2i)
+        S[(row0 + ta) * NB + f] = make_float2((zr + wr) * sc, (zi - wi) * sc);
+        if (ta + 1 < g.F) S[(row0 + ta + 1) * NB + f] = make_float2((zi + wi) * sc, (wr - zr) * sc);
+    }
+}
+
+// ---------------------------------------------------------------- time smoothing (filtfilt) + sigmoid mask
+__global__ void __launch_bounds__(128) k_nr_iir_fwd(const float2* __restrict__ S, float* __restrict__ Afwd, int F, long long n_rows,
+                                                    double b) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_rows * NB) return;
+    const long long cc = idx / NB;
+    const int f = (int)(idx - cc * NB);
+    const float2* s = S + cc * F * NB + f;
+    float* o = Afwd + cc * F * NB + f;
+    const double a1 = 1.0 - b;
+    double y = 0.0;
+#pragma unroll 8
+    for (int t = 0; t < F; ++t) {
+        const float2 v = s[(long long)t * NB];
+        const double a = (double)sqrtf(v.x * v.x + v.y * v.y);
+        y = (t == 0) ? a : fma(a1, y, b * a);  // lfilter_zi start: y[-1] = x[0]
+        o[(long long)t * NB] = (float)y;
+    }
+}
+
+__global__ void __launch_bounds__(128) k_nr_iir_bwd_mask(const float2* __restrict__ S, const float* __restrict__ Afwd,
+                                                         float* __restrict__ M, int F, long long n_rows, double b) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_rows * NB) return;
+    const long long cc = idx / NB;
+    const int f = (int)(idx - cc * NB);
+    const float2* s = S + cc * F * NB + f;
+    const float* af = Afwd + cc * F * NB + f;
+    float* m = M + cc * F * NB + f;
+    const double a1 = 1.0 - b;
+    double y = 0.0;
+#pragma unroll 8
+    for (int t = F - 1; t >= 0; --t) {
+        const double x = (double)af[(long long)t * NB];
+        y = (t == F - 1) ? x : fma(a1, y, b * x);
+        const float2 v = s[(long long)t * NB];
+        const float a = sqrtf(v.x * v.x + v.y * v.y);
+        const float as = (float)y;
+        const float rel = (a - as) / as;  // 0/0 -> NaN on all-zero input, like the reference
+        m[(long long)t * NB] = 1.0f / (1.0f + expf(-(rel - 2.0f) * 10.0f));
+    }
+}
+
+// ---------------------------------------------------------------- 2-D mask smoothing (fftconvolve 'same')
+// tile: 32 frames x 64 bins; grid (ceil(513/64), ceil(F/32), n_rows)
+struct NrSmooth {
+    float vf[64];  // up to 2*nf+1 <= 63 taps
+    float vt[16];  // up to 2*nt+1 <= 15 taps
+    int nf, nt;
+};
+
+__global__ void __launch_bounds__(256) k_nr_smooth(const float* __restrict__ M, float* __restrict__ Msm, int F, NrSmooth p) {
+    __shared__ float tile[46][64 + 64];  // (32 + 2*nt<=14) rows x (64 + 2*nf<=62) cols
+    __shared__ float rowc[46][64];
+    const int f0 = blockIdx.x * 64, t0 = blockIdx.y * 32;
+    const long long base = (long long)blockIdx.z * F * NB;
+    const int rows = 32 + 2 * p.nt, cols = 64 + 2 * p.nf;
+    for (int i = threadIdx.x; i < rows * cols; i += 256) {
+        const int r = i / cols, c = i - r * cols;
+        const int t = t0 + r - p.nt, f = f0 + c - p.nf;
+        tile[r][c] = (t >= 0 && t < F && f >= 0 && f < NB) ? M[base + (long long)t * NB + f] : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < rows * 64; i += 256) {
+        const int r = i >> 6, c = i & 63;
+        float acc = 0.f;
+        for (int k = 0; k <= 2 * p.nf; ++k) acc = fmaf(p.vf[k], tile[r][c + k], acc);
+        rowc[r][c] = acc;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 32 * 64; i += 256) {
+        const int r = i >> 6, c = i & 63;
+        const int t = t0 + r, f = f0 + c;
+        if (t >= F || f >= NB) continue;
+        float acc = 0.f;
+        for (int k = 0; k <= 2 * p.nt; ++k) acc = fmaf(p.vt[k], rowc[r + k][c], acc);
+        Msm[base + (long long)t * NB + f] = acc;
+    }
+}
+
+// ---------------------------------------------------------------- inverse STFT + overlap-add
+// grid (tiles, n_chunks, batch): tile = 29 hop blocks [j0, j0+29) <- frames [j0-1, j0+30]
+constexpr int kOlaBlocks = 29, kOlaOut = kOlaBlocks * NH;  // 7424 samples
+
+__global__ void __launch_bounds__(256, 2) k_nr_istft(const float2* __restrict__ S, const float* __restrict__ Msm, NrGeom g,
+                                                     const float* __restrict__ tabs, int j_first, float* __restrict__ out) {
+    extern __shared__ __align__(16) float sm[];
+    float* win = sm;               // [1024]
+    float* twc = win + NF;
+    float* tws = twc + NF;
+    float* osc = tws + NF;         // [256] overlap-add scale
+    float* Y = osc + NH;           // [8][2][32*33]
+    float* acc = Y + 8 * 2 * kYPlane;  // [7424]
+    const int tid = threadIdx.x, chunk = blockIdx.y, clip = blockIdx.z;
+    const int j0 = j_first + blockIdx.x * kOlaBlocks;
+    for (int i = tid; i < 3 * NF + NH; i += 256) win[i] = tabs[i];
+    for (int i = tid; i < kOlaOut; i += 256) acc[i] = 0.f;
+    const long long row0 = ((long long)clip * g.n_chunks + chunk) * g.F;
+    __syncthreads();
+    for (int pass = 0; pass < 2; ++pass) {
+        const int tp0 = j0 - 1 + pass * 16;
+        {   // step 1 of the inverse (conjugate twiddles), reading Z'[k], k = 32*a + b, straight from S*Msm:
+            // Z'[k] = Sa[k] + i Sb[k] (k <= 512), conj(Sa[N-k]) + i conj(Sb[N-k]) (k > 512)
+            const int q = tid >> 5, bb = tid & 31;
+            const int ta = tp0 + 2 * q, tb = ta + 1;
+            const bool va = ta >= 0 && ta < g.F, vb = tb >= 0 && tb < g.F;
+            cpx v[32];
+#pragma unroll
+            for (int a = 0; a < 32; ++a) {
+                const int k = 32 * a + bb;
+                const int f = k <= 512 ? k : NF - k;
+                const float sgn = k <= 512 ? 1.f : -1.f;
+                float ar = 0.f, ai = 0.f, br = 0.f, bi = 0.f;
+                if (va) {
+                    const float2 s = S[(row0 + ta) * NB + f];
+                    const float m = Msm[(row0 + ta) * NB + f];
+                    ar = s.x * m; ai = s.y * m * sgn;
+                }
+                if (vb) {
+                    const float2 s = S[(row0 + tb) * NB + f];
+                    const float m = Msm[(row0 + tb) * NB + f];
+                    br = s.x * m; bi = s.y * m * sgn;
+                }
+                if (f == 0 || f == 512) { ai = 0.f; bi = 0.f; }  // irfft ignores the imaginary part of DC / Nyquist
+                v[a] = cpx{ar - bi, ai + br};
+            }
+            fft_pow2<32, true>(v);
+            float* yr = Y + q * 2 * kYPlane;
+            float* yi = yr + kYPlane;
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+                const int tw = bb * c;
+                const cpx y = cmul(v[c], cpx{twc[tw], tws[tw]});
+                yr[c * kYs + bb] = y.x;
+                yi[c * kYs + bb] = y.y;
+            }
+        }
+        __syncthreads();
+        {
+            const int q = tid >> 5, c = tid & 31;
+            float* yr = Y + q * 2 * kYPlane;
+            float* yi = yr + kYPlane;
+            cpx v[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = cpx{yr[c * kYs + i], yi[c * kYs + i]};
+            fft_pow2<32, true>(v);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {  // z[n = c + 32 d] at [c][d]
+                yr[c * kYs + i] = v[i].x;
+                yi[c * kYs + i] = v[i].y;
+            }
+        }
+        __syncthreads();
+        // overlap-add the 16 frames of this pass: output sample u (hop block j0 + u/256) <- frames j-1 .. j+2
+        for (int u = tid; u < kOlaOut; u += 256) {
+            const int j = j0 + (u >> 8), r = u & 255;
+            float s = 0.f;
+#pragma unroll
+            for (int d = -1; d <= 2; ++d) {
+                const int t = j + d, lt = t - tp0;
+                if (lt < 0 || lt >= 16) continue;
+                const int n = r + 512 - 256 * d;  // position inside frame t: e - 256 t, e = 256 j + r + 512
+                const float* pl = Y + (lt >> 1) * 2 * kYPlane + (lt & 1) * kYPlane;
+                s = fmaf(pl[(n & 31) * kYs + (n >> 5)], win[n], s);
+            }
+            acc[u] += s;
+        }
+        __syncthreads();
+    }
+    // store the kept centre [kCtx, kCtx + keep) of the chunk
+    const long long keep = (g.n_chunks == 1) ? g.n : ((g.n - (long long)chunk * kChunk) < kChunk ? (g.n - (long long)chunk * kChunk) : kChunk);
+    for (int u = tid; u < kOlaOut; u += 256) {
+        const long long p = (long long)NH * j0 + u;
+        const long long rel = p - kCtx;
+        if (rel < 0 || rel >= keep) continue;
+        out[(long long)clip * g.stride + (long long)chunk * kChunk + rel] = acc[u] * osc[u & 255];
+    }
+}
+
+constexpr int kStftSmem = (kStftXs + 3 * NF + 8 * 2 * kYPlane) * (int)sizeof(float);
+constexpr int kIstftSmem = (3 * NF + NH + 8 * 2 * kYPlane + kOlaOut) * (int)sizeof(float);
+
+static std::vector<double> tri_filter(int n) {
+    // concat(linspace(0,1,n+1,endpoint=False), linspace(1,0,n+2))[1:-1]
+    std::vector<double> v;
+    for (int i = 0; i < n + 1; ++i) v.push_back((double)i / (n + 1));
+    for (int i = 0; i < n + 2; ++i) v.push_back(1.0 - (double)i / (n + 1));
+    return std::vector<double>(v.begin() + 1, v.end() - 1);
+}
+
+int launch_spectral_gate(const void* d_audio, int fmt, long long n, long long batch, long long stride, int sr, float* d_out,
+                         cudaStream_t st) {
+    const float* tabs;
+    int rc = get_nr_tables(&tabs);
+    if (rc) return rc;
+    static std::once_flag once;
+    static cudaError_t e1 = cudaSuccess, e2 = cudaSuccess;
+    std::call_once(once, [&] {
+        e1 = cudaFuncSetAttribute(k_nr_stft, cudaFuncAttributeMaxDynamicSharedMemorySize, kStftSmem);
+        e2 = cudaFuncSetAttribute(k_nr_istft, cudaFuncAttributeMaxDynamicSharedMemorySize, kIstftSmem);
+    });
+    OSB_CUDA(e1);
+    OSB_CUDA(e2);
+    // noisereduce parameters (defaults)
+    const double t_frames = 2.0 * sr / (double)NH;
+    const double b = (std::sqrt(1.0 + 4.0 * t_frames * t_frames) - 1.0) / (2.0 * t_frames * t_frames);
+    const int nf = (int)(500.0 / (sr / (NF / 2.0)));
+    const int nt = (int)(50.0 / (((double)NH / sr) * 1000.0));
+    if (nf < 1 || nt < 1 || nf > 31 || nt > 7) {
+        set_error("unsupported: sample rate %d gives mask smoothing %dx%d outside the supported 1..31 x 1..7", sr, nf, nt);
+        return OSB_ERR_UNSUPPORTED;
+    }
+    NrSmooth sp{};
+    sp.nf = nf; sp.nt = nt;
+    {
+        std::vector<double> vf = tri_filter(nf), vt = tri_filter(nt);
+        double sf = 0, stt = 0;
+        for (double x : vf) sf += x;
+        for (double x : vt) stt += x;
+        for (size_t i = 0; i < vf.size(); ++i) sp.vf[i] = (float)(vf[i] / sf);
+        for (size_t i = 0; i < vt.size(); ++i) sp.vt[i] = (float)(vt[i] / stt);
+    }
+    NrGeom g;
+    g.n = n; g.stride = stride; g.fmt = fmt;
+    g.n_chunks = n > kChunk ? (int)((n - 1) / kChunk + 1) : 1;
+    g.Lc = n > kChunk ? kChunk + 2 * kCtx : n + 2 * kCtx;
+    g.F = (int)(g.Lc / NH) + 1;
+    const long long keep_max = n > kChunk ? kChunk : n;
+    const int j_first = (int)(kCtx / NH);
+    const int j_last = (int)((kCtx + keep_max - 1) / NH);
+    const int tiles = (j_last - j_first + 1 + kOlaBlocks - 1) / kOlaBlocks;
+    // scratch per clip: S (8 B) + Afwd + M + Msm (4 B each) per (frame, bin); process the batch in groups of <= ~24 GB
+    const long long per_clip = (long long)g.n_chunks * g.F * NB;
+    long long group = (24ll << 30) / (per_clip * 20);
+    if (group < 1) group = 1;
+    if (group > batch) group = batch;
+    Scratch scr(st);
+    float2* S;
+    float *Afwd, *M, *Msm;
+    OSB_CUDA(scr.alloc(&S, (size_t)(group * per_clip)));
+    OSB_CUDA(scr.alloc(&Afwd, (size_t)(group * per_clip)));
+    OSB_CUDA(scr.alloc(&M, (size_t)(group * per_clip)));
+    Msm = Afwd;  // Afwd is dead once the mask exists
+    for (long long c0 = 0; c0 < batch; c0 += group) {
+        const int gb = (int)((batch - c0) < group ? (batch - c0) : group);
+        g.batch = gb;
+        const char* in = reinterpret_cast<const char*>(d_audio) + c0 * stride * (fmt == OSB_FMT_PCM16 ? 2 : 4);
+        float* outp = d_out + c0 * stride;
+        const long long n_rows = (long long)gb * g.n_chunks;
+        OSB_LAUNCH(k_nr_stft, dim3((g.F + kStftFrames - 1) / kStftFrames, g.n_chunks, gb), 256, kStftSmem, st, (const void*)in, g, tabs, S);
+        OSB_CHECK_LAUNCH();
+        const unsigned gi = (unsigned)((n_rows * NB + 127) / 128);
+        OSB_LAUNCH(k_nr_iir_fwd, gi, 128, 0, st, S, Afwd, g.F, n_rows, b);
+        OSB_CHECK_LAUNCH();
+        OSB_LAUNCH(k_nr_iir_bwd_mask, gi, 128, 0, st, S, Afwd, M, g.F, n_rows, b);
+        OSB_CHECK_LAUNCH();
+        OSB_LAUNCH(k_nr_smooth, dim3((NB + 63) / 64, (g.F + 31) / 32, (unsigned)n_rows), 256, 0, st, M, Msm, g.F, sp);
+        OSB_CHECK_LAUNCH();
+        OSB_LAUNCH(k_nr_istft, dim3(tiles, g.n_chunks, gb), 256, kIstftSmem, st, S, Msm, g, tabs, j_first, outp);
+        OSB_CHECK_LAUNCH();
+    }
+    return OSB_OK;
+}
+
+}  // namespace osb
+
+using namespace osb;
+
+extern "C" {
+
+int osb_spectral_gate_dev(const void* d_audio, int fmt, int64_t n, int64_t batch, int64_t stride, int sample_rate, float* d_out,
+                          void* stream) {
+    int rc = ensure_init();
+    if (rc) return rc;
+    OSB_REQUIRE(fmt == OSB_FMT_PCM16 || fmt == OSB_FMT_F32, "fmt must be OSB_FMT_PCM16 or OSB_FMT_F32");
+    OSB_REQUIRE(n >= 0 && batch >= 0 && stride >= n && sample_rate > 0, "bad sizes");
+    if (n == 0 || batch == 0) return OSB_OK;
+    OSB_REQUIRE(d_audio && d_out, "null buffer");
+    OSB_REQUIRE(batch <= 65535, "batch too large (<= 65535)");
+    return launch_spectral_gate(d_audio, fmt, n, batch, stride, sample_rate, d_out, (cudaStream_t)stream);
+}
+
+int osb_spectral_gate_host(const void* audio, int fmt, float* out, int64_t n, int sample_rate) {
+    HostWs& ws = host_ws();
+    int rc = ws.prepare();
+    if (rc) return rc;
+    OSB_REQUIRE(fmt == OSB_FMT_PCM16 || fmt == OSB_FMT_F32, "fmt must be OSB_FMT_PCM16 or OSB_FMT_F32");
+    if (n <= 0) return OSB_OK;
+    const size_t es = fmt == OSB_FMT_PCM16 ? 2 : 4;
+    void *da, *dout;
+    if ((rc = ws.dev_buf(0, (size_t)n * es, &da)) || (rc = ws.dev_buf(1, (size_t)n * 4, &dout))) return rc;
+    if ((rc = ws.h2d(da, audio, (size_t)n * es))) return rc;
+    if ((rc = osb_spectral_gate_dev(da, fmt, n, 1, n, sample_rate, (float*)dout, ws.stream))) return rc;
+    return ws.d2h(out, dout, (size_t)n * 4);
+}
+
+}  // extern "C"
