@@ -1,0 +1,325 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native open-speech audio hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload stt_batch|c1|vad|realtime|tts] [--impl reference]
+
+Default workload = BASELINE.json configs[3], the configuration the metric's target is quoted on:
+batch STT front-end, 256 x 60 s 16 kHz pcm16 clips per GPU -> spectral-gating noise reduction -> RMS normalise
+-> int16 requantise -> Whisper large-v3 128-bin log-mel.  One "step" = one pass over the batch.
+
+  value   audio-seconds per second, inputs already resident in HBM (CUDA events, max over ranks)
+  e2e     same metric through the C-ABI host entry point: pinned HOST buffers in, HOST features out,
+          H2D and D2H inside the timed region
+  roofline / cpu_baseline / clocks: see DESIGN.md "Measurement"
+
+--impl reference times the reference's CPU implementation of the same chain (the numpy/scipy oracle port: the
+reference is pure Python around numpy/scipy/noisereduce/faster-whisper, three of which cannot be installed) on
+all host cores, on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "audio-seconds/sec"
+UNIT = "audio-s/s"
+SR = 16000
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, copy bandwidth)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ----------------------------------------------------------------------------- workloads
+WORKLOADS = {
+    # name: (description, clips per GPU, seconds per clip, noise_reduce, normalize, n_mels)
+    "stt_batch": ("BASELINE configs[3]: batch STT front-end, 256x60 s clips/GPU: spectral-gate denoise + normalise + 128-bin log-mel", 256, 60.0, True, True, 128),
+    "c1": ("BASELINE configs[0] as a batch: 256x30 s clips/GPU: normalise + 128-bin log-mel (no denoise)", 256, 30.0, False, True, 128),
+}
+
+# SURVEY.md 8(d) algorithmic bytes per audio-second (compulsory input + output, no intermediates)
+ALG_BYTES_PER_AUDIO_S = {"stt_batch": 83200.0, "c1": 83200.0}
+# denoise stage on its own: pcm16 in (2 B/sample) + f32 out (4 B/sample)
+DENOISE_BYTES_PER_AUDIO_S = 6.0 * SR
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.idx)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)), "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------- CPU baseline (oracle port)
+def _cpu_one(args):
+    import warnings
+
+    warnings.filterwarnings("ignore")
+    from oracle import stt
+
+    pcm, noise_reduce, normalize, n_mels = args
+    t = time.perf_counter()
+    stt.stt_frontend(pcm, noise_reduce=noise_reduce, normalize=normalize, n_mels=n_mels)
+    return time.perf_counter() - t
+
+
+def cpu_baseline(workload: str, cores: int, n_clips: int, seconds: float) -> dict:
+    """Oracle port of the reference chain on `cores` host processes, bounded sample of the same workload."""
+    from open_speech_b200 import synth
+
+    _, _, _, nr, norm, n_mels = WORKLOADS[workload]
+    clips = synth.clip_batch_pcm16(n_clips, seconds, seed=synth.SEED_C4, distinct=min(n_clips, 8))
+    jobs = [(clips[i], nr, norm, n_mels) for i in range(n_clips)]
+    if cores <= 1:
+        _cpu_one((clips[0][: SR * 2], nr, norm, n_mels))  # warm-up (imports, FFT plans)
+        t0 = time.perf_counter()
+        for j in jobs:
+            _cpu_one(j)
+        dt = time.perf_counter() - t0
+    else:
+        import multiprocessing as mp
+
+        with mp.get_context("fork").Pool(cores) as pool:
+            pool.map(_cpu_one, [(clips[0][: SR * 2], nr, norm, n_mels)] * cores)  # warm every worker
+            t0 = time.perf_counter()
+            pool.map(_cpu_one, jobs, chunksize=1)
+            dt = time.perf_counter() - t0
+    return {"value": n_clips * seconds / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{n_clips} x {seconds:g} s clips of the same synthetic workload, numpy/scipy oracle port "
+                      f"(noisereduce + faster-whisper FeatureExtractor restated; the reference itself is numpy/scipy), {dt:.2f} s of wall time"}
+
+
+def run_reference(args) -> None:
+    """--impl reference: the reference's CPU path (oracle port) on all host cores; rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    desc, clips_per_gpu, seconds, nr, norm, n_mels = WORKLOADS[args.workload]
+    cores = os.cpu_count() or 1
+    n_clips = max(cores, 8)
+    sample_s = 60.0 if seconds >= 60.0 else seconds
+    vals = []
+    base = None
+    for i in range(args.warmup + args.steps):
+        base = cpu_baseline(args.workload, cores, n_clips, sample_s)
+        if i >= args.warmup:
+            vals.append(base["value"])
+    v = float(np.mean(vals))
+    base["value"] = v
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1000.0 * n_clips * sample_s / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64/f32",
+            "data": "synthetic", "config": {"workload": desc, "clips_per_step": n_clips, "seconds_per_clip": sample_s, "host_cores": cores,
+                                            "note": "bounded sample of the GPU arm's workload; CPU throughput does not depend on the batch size"},
+            "cpu_baseline": base, "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def run_gpu(args) -> None:
+    import torch
+    import torch.distributed as dist
+
+    from open_speech_b200 import _native as N
+    from open_speech_b200 import synth
+    from open_speech_b200.batch import SttFrontEnd
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    N.require_gpu()
+    N.check(N.lib().osb_init(local))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    desc, clips, seconds, nr, norm, n_mels = WORKLOADS[args.workload]
+    clips = args.clips or clips
+    n = int(seconds * SR)
+    fe = SttFrontEnd(n_mels=n_mels, sample_rate=SR, noise_reduce=nr, normalize=norm)
+    nf = fe.frames(n)
+
+    # synthetic input of the config's shape, generated on the host, pinned; each rank its own shard (weak scaling)
+    host_np = synth.clip_batch_pcm16(clips, seconds, seed=synth.SEED_C4 + 1000 * rank, extra_noise_rms=0.01 if nr else 0.0, distinct=8)
+    pcm_host = torch.from_numpy(host_np).pin_memory()
+    pcm_dev = torch.empty_like(pcm_host, device="cuda")
+    pcm_dev.copy_(pcm_host)
+    mel_dev = torch.empty((clips, n_mels, nf), dtype=torch.float32, device="cuda")
+    mel_host = torch.empty((clips, n_mels, nf), dtype=torch.float32).pin_memory()
+    audio_s_per_step = clips * seconds
+    h2d_bytes, d2h_bytes = pcm_host.numel() * 2, mel_host.numel() * 4
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ev0.record()
+        for _ in range(steps):
+            fn()
+        ev1.record()
+        torch.cuda.synchronize()
+        ms = ev0.elapsed_time(ev1)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        barrier()
+        return ms
+
+    # ---- warm-up (also sizes the stream-ordered scratch pool)
+    for _ in range(max(args.warmup, 3)):
+        fe(pcm_dev, mel_dev)
+    torch.cuda.synchronize()
+
+    # ---- resident-input throughput, per-kernel events on the launching stream, clocks sampled during the region
+    sampler = ClockSampler(local)
+    launches0 = N.lib().osb_launch_count()
+    N.check(N.lib().osb_profile_enable(1))
+    if rank == 0:
+        sampler.start()
+    ms_total = timed(lambda: fe(pcm_dev, mel_dev), args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    buf = ctypes.create_string_buffer(1 << 16)
+    N.check(N.lib().osb_profile_report(buf, len(buf)))
+    N.check(N.lib().osb_profile_enable(0))
+    kern = json.loads(buf.value.decode())
+    launches = int(N.lib().osb_launch_count() - launches0)
+    ms_step = ms_total / args.steps
+    value = world * audio_s_per_step / (ms_step / 1000.0)
+
+    # ---- end to end: pinned host clips in, host features out, copies inside the timed region
+    for _ in range(2):
+        fe.run_host(pcm_host, pcm_dev, mel_dev, mel_host)
+    torch.cuda.synchronize()
+    e2e_steps = max(1, min(args.steps, 5))
+    ms_e2e = timed(lambda: fe.run_host(pcm_host, pcm_dev, mel_dev, mel_host), e2e_steps) / e2e_steps
+    e2e_value = world * audio_s_per_step / (ms_e2e / 1000.0)
+    checksum = float(mel_host[0, :, :16].double().sum())  # the D2H result is really read
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (CUDA-event time per launch from the timed region)
+    peak, peak_src = load_peaks()
+    dom = max(kern.items(), key=lambda kv: kv[1]["ms"])
+    dom_name, dom_ms = dom[0], dom[1]["ms"] / max(1, dom[1]["launches"])
+    stage_bytes = DENOISE_BYTES_PER_AUDIO_S if dom_name.startswith("k_nr_") else ALG_BYTES_PER_AUDIO_S[args.workload]
+    dom_alg = stage_bytes * audio_s_per_step  # one launch covers the whole per-GPU batch
+    achieved = dom_alg / (dom_ms / 1000.0) / 1e9
+    chain_alg = ALG_BYTES_PER_AUDIO_S[args.workload] * audio_s_per_step
+    chain_gbs = chain_alg / (ms_step / 1000.0) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get(args.workload, {}).get(dom_name)
+    roofline = {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "peak_source": peak_src, "ms_per_launch": dom_ms, "algorithmic_bytes_per_launch": dom_alg,
+                "share_of_step": dom[1]["ms"] / ms_total,
+                "chain": {"algorithmic_bytes_per_step": chain_alg, "achieved": chain_gbs, "frac": chain_gbs / peak},
+                "kernels_ms_per_step": {k: v["ms"] / args.steps for k, v in sorted(kern.items(), key=lambda kv: -kv[1]["ms"])}}
+
+    # ---- CPU baseline beside it (bounded sample, single thread = the reference's execution model)
+    cpu = None
+    if not args.no_cpu:
+        cpu = cpu_baseline(args.workload, 1, 2, min(seconds, 30.0))
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": desc, "clips_per_gpu": clips, "seconds_per_clip": seconds, "sample_rate": SR, "n_mels": n_mels,
+                       "noise_reduce": nr, "normalize": norm, "global_clips": clips * world, "parallelism": f"clip-sharded x{world}, no collective",
+                       "l2": f"inputs larger than L2 ({h2d_bytes / 1e6:.0f} MB of pcm16 per GPU per step vs 126 MB)"},
+            "clocks": clocks, "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+                                      "ms_per_step": ms_e2e, "checksum": checksum},
+            "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="stt_batch", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--clips", type=int, default=0, help="clips per GPU (default: the config's 256)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus > 1 and world == 1:
+        # convenience: re-launch under torchrun, one rank per GPU
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
+               "--master-port", "29517", os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -50,6 +50,10 @@ int osb_init(int device); /* selects the device for the calling thread; uploads 
 const char* osb_last_error(void);
 /* counts kernel launches issued by this library in this process (bench.py "gpu_launches") */
 uint64_t osb_launch_count(void);
+/* optional per-kernel timing: CUDA event pairs around every launch, on the launching stream.
+ * osb_profile_report synchronises the device and writes {"kernel": {"ms": total, "launches": n}, ...}. */
+int osb_profile_enable(int on);
+int osb_profile_report(char* buf, size_t capacity);
 
 /* ---------------------------------------------------------------- G.711 + linear resample
  * replaces audioop.ulaw2lin/alaw2lin/lin2ulaw/lin2alaw and _resample_linear as called from

@@ -1,0 +1,119 @@
+"""Batched, device-resident entry points (what bench.py and the multi-GPU driver call).
+
+PyTorch is only plumbing here: it owns device/pinned memory and the CUDA stream; every kernel is
+launched through libosb200's ``*_dev`` C entry points on ``torch.cuda.current_stream()``.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _native as N
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+class SttFrontEnd:
+    """pcm16 clips -> [spectral gate] -> [normalise] -> requantise -> log-mel (BASELINE configs 1 / 4).
+
+    The device-side equivalent of ``FeatureExtractor(decode(preprocess_stt_audio(wav)))`` for a batch of
+    equal-length clips: input int16 [B, n] (device), output float32 [B, n_mels, (n+160)//160] (device).
+    """
+
+    def __init__(self, n_mels: int = 128, sample_rate: int = 16000, noise_reduce: bool = False, normalize: bool = True):
+        N.require_gpu()
+        self.n_mels, self.sample_rate = n_mels, sample_rate
+        self.noise_reduce, self.normalize = bool(noise_reduce), bool(normalize)
+
+    def frames(self, n: int) -> int:
+        return N.lib().osb_logmel_frames(n)
+
+    def __call__(self, pcm: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+        if pcm.dtype != torch.int16 or not pcm.is_cuda or pcm.dim() != 2 or not pcm.is_contiguous():
+            raise ValueError("pcm must be a contiguous CUDA int16 tensor [batch, samples]")
+        b, n = pcm.shape
+        if out is None:
+            out = torch.empty((b, self.n_mels, self.frames(n)), dtype=torch.float32, device=pcm.device)
+        N.call("osb_stt_frontend_dev", pcm.data_ptr(), n, b, n, self.sample_rate, int(self.noise_reduce), int(self.normalize),
+               self.n_mels, out.data_ptr(), _stream())
+        return out
+
+    def run_host(self, pcm_host: torch.Tensor, pcm_dev: torch.Tensor, mel_dev: torch.Tensor, mel_host: torch.Tensor) -> torch.Tensor:
+        """End-to-end step with HOST buffers (pinned): H2D of the clips, kernels, D2H of the features."""
+        pcm_dev.copy_(pcm_host, non_blocking=True)
+        self(pcm_dev, mel_dev)
+        mel_host.copy_(mel_dev, non_blocking=True)
+        return mel_host
+
+
+class VadBatch:
+    """Silero-shaped VAD over a batch of equal-length streams resident on the device (BASELINE config 2)."""
+
+    def __init__(self, session=None, threshold: float = 0.5, min_speech_ms: int = 250, silence_ms: int = 800, max_segments: int = 4096):
+        from .vad.silero import VadSession
+
+        N.require_gpu()
+        self.session = session if session is not None else VadSession()
+        self.threshold, self.min_speech_ms, self.silence_ms, self.max_segments = threshold, min_speech_ms, silence_ms, max_segments
+
+    def score(self, pcm: torch.Tensor, state: torch.Tensor | None = None):
+        b, n = pcm.shape
+        n_win = n // 512
+        if state is None:
+            state = torch.zeros((b, 2, 128), dtype=torch.float32, device=pcm.device)
+        probs = torch.empty((b, max(n_win, 1)), dtype=torch.float32, device=pcm.device)
+        fmt = N.FMT_PCM16 if pcm.dtype == torch.int16 else N.FMT_F32
+        N.call("osb_vad_score_dev", self.session.handle, pcm.data_ptr(), fmt, n, b, n, state.data_ptr(), probs.data_ptr(), max(n_win, 1), _stream())
+        return probs[:, :n_win], state
+
+    def segments(self, probs: torch.Tensor, n_samples: int):
+        b, n_win = probs.shape
+        segs = torch.empty((b, self.max_segments, 2), dtype=torch.int32, device=probs.device)
+        counts = torch.zeros((b,), dtype=torch.int32, device=probs.device)
+        N.call("osb_vad_segments_dev", probs.data_ptr(), probs.stride(0), n_win, b, n_samples, float(self.threshold), self.min_speech_ms,
+               self.silence_ms, segs.data_ptr(), counts.data_ptr(), self.max_segments, _stream())
+        return segs, counts
+
+    def __call__(self, pcm: torch.Tensor):
+        probs, state = self.score(pcm)
+        segs, counts = self.segments(probs, pcm.shape[1])
+        return probs, segs, counts
+
+
+class RealtimeTick:
+    """One 20 ms tick of BASELINE config 3: S streams x 160 G.711 bytes -> 320 pcm16 @16 kHz each, one launch."""
+
+    def __init__(self, n_streams: int, chunk: int = 160, fmt: str = "g711_ulaw", from_rate: int = 8000, to_rate: int = 16000):
+        N.require_gpu()
+        self.n_streams, self.chunk = n_streams, chunk
+        self.fmt = {"g711_ulaw": N.FMT_ULAW, "g711_alaw": N.FMT_ALAW, "pcm16": N.FMT_PCM16}[fmt]
+        self.n_out = int(chunk * (to_rate / from_rate))
+
+    def __call__(self, tick: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+        if out is None:
+            out = torch.empty((self.n_streams, self.n_out), dtype=torch.int16, device=tick.device)
+        N.call("osb_resample_linear_dev", tick.data_ptr(), self.fmt, out.data_ptr(), N.FMT_PCM16, self.chunk, self.n_out, self.n_streams,
+               self.chunk, self.n_out, _stream())
+        return out
+
+
+def shard_units(n_units: int, world: int, rank: int) -> range:
+    """Static sharding of independent clips / streams / utterances: contiguous, balanced to +-1 unit.
+    No exchange step exists on this path, so there is no collective."""
+    base, rem = divmod(n_units, world)
+    start = rank * base + min(rank, rem)
+    return range(start, start + base + (1 if rank < rem else 0))
+
+
+def shard_by_length(lengths, world: int) -> list[list[int]]:
+    """Length-balanced static sharding (longest-processing-time-first greedy) for ragged units."""
+    order = sorted(range(len(lengths)), key=lambda i: -int(lengths[i]))
+    bins = [[] for _ in range(world)]
+    load = [0] * world
+    for i in order:
+        k = min(range(world), key=lambda j: load[j])
+        bins[k].append(i)
+        load[k] += int(lengths[i])
+    return [sorted(b) for b in bins]

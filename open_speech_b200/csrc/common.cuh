@@ -17,10 +17,16 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 int ensure_init();          // lazy osb_init(current device)
 int num_sms();              // queried once; 148 on B200
 void count_launch();        // osb_launch_count bookkeeping
+bool prof_on();             // osb_profile_enable: per-kernel CUDA-event timing on the launching stream
+void prof_begin(const char* name, cudaStream_t st);
+void prof_end(cudaStream_t st);
 
 #define OSB_LAUNCH(kern, grid, block, smem, stream, ...)              \
     do {                                                              \
+        const bool _p = osb::prof_on();                               \
+        if (_p) osb::prof_begin(#kern, (stream));                     \
         kern<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);     \
+        if (_p) osb::prof_end((stream));                              \
         osb::count_launch();                                          \
     } while (0)
 

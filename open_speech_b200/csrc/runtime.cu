@@ -1,7 +1,10 @@
 // libosb200 runtime: device selection, error text, per-thread host workspace.
 #include <atomic>
 #include <cstdarg>
+#include <map>
 #include <mutex>
+#include <string>
+#include <vector>
 
 #include "common.cuh"
 
@@ -27,6 +30,42 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
 }
 
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+// ---- optional per-kernel timing (bench.py roofline): event pairs recorded on the launching stream
+struct ProfRec { std::string name; cudaEvent_t a, b; };
+static std::atomic<bool> g_prof{false};
+static std::mutex g_prof_mu;
+static std::vector<ProfRec> g_prof_recs;
+static std::map<std::string, std::pair<double, long long>> g_prof_acc;  // name -> (ms, launches)
+static thread_local cudaEvent_t t_prof_a = nullptr;
+static thread_local const char* t_prof_name = nullptr;
+
+bool prof_on() { return g_prof.load(std::memory_order_relaxed); }
+void prof_begin(const char* name, cudaStream_t st) {
+    cudaEventCreate(&t_prof_a);
+    cudaEventRecord(t_prof_a, st);
+    t_prof_name = name;
+}
+void prof_end(cudaStream_t st) {
+    cudaEvent_t b;
+    cudaEventCreate(&b);
+    cudaEventRecord(b, st);
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof_recs.push_back(ProfRec{t_prof_name ? t_prof_name : "?", t_prof_a, b});
+}
+static void prof_drain() {  // caller holds g_prof_mu and has synchronised the device
+    for (auto& r : g_prof_recs) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+            auto& e = g_prof_acc[r.name];
+            e.first += ms;
+            e.second += 1;
+        }
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+    }
+    g_prof_recs.clear();
+}
 
 int num_sms() {
     int v = g_sms.load();
@@ -88,9 +127,18 @@ int HostWs::pin_buf(int slot, size_t bytes, void** out) {
 
 static const size_t kPinLimit = (size_t)256 << 20;  // above this, copy straight from the caller's pages
 
+static bool is_pinned(const void* h) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, h) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeHost;
+}
+
 int HostWs::h2d(void* d, const void* h, size_t bytes) {
     if (bytes == 0) return OSB_OK;
-    if (bytes <= kPinLimit) {
+    if (bytes <= kPinLimit && !is_pinned(h)) {
         void* p;
         int rc = pin_buf(0, bytes, &p);
         if (rc) return rc;
@@ -104,7 +152,7 @@ int HostWs::h2d(void* d, const void* h, size_t bytes) {
 
 int HostWs::d2h(void* h, const void* d, size_t bytes) {
     if (bytes == 0) return sync();
-    if (bytes <= kPinLimit) {
+    if (bytes <= kPinLimit && !is_pinned(h)) {
         void* p;
         int rc = pin_buf(1, bytes, &p);
         if (rc) return rc;
@@ -174,5 +222,32 @@ int osb_init(int device) {
 const char* osb_last_error(void) { return osb::t_err; }
 
 uint64_t osb_launch_count(void) { return osb::g_launches.load(); }
+
+int osb_profile_enable(int on) {
+    std::lock_guard<std::mutex> lk(osb::g_prof_mu);
+    if (on) osb::g_prof_acc.clear();
+    osb::g_prof.store(on != 0);
+    return OSB_OK;
+}
+
+int osb_profile_report(char* buf, size_t capacity) {
+    OSB_REQUIRE(buf && capacity > 2, "report buffer too small");
+    OSB_CUDA(cudaDeviceSynchronize());
+    std::lock_guard<std::mutex> lk(osb::g_prof_mu);
+    osb::prof_drain();
+    std::string out = "{";
+    bool first = true;
+    for (auto& kv : osb::g_prof_acc) {
+        char tmp[256];
+        snprintf(tmp, sizeof(tmp), "%s\"%s\": {\"ms\": %.6f, \"launches\": %lld}", first ? "" : ", ", kv.first.c_str(), kv.second.first,
+                 kv.second.second);
+        out += tmp;
+        first = false;
+    }
+    out += "}";
+    OSB_REQUIRE(out.size() + 1 <= capacity, "report buffer too small");
+    memcpy(buf, out.c_str(), out.size() + 1);
+    return OSB_OK;
+}
 
 }  // extern "C"
