@@ -154,6 +154,34 @@ int osb_stt_frontend_dev(const int16_t* d_pcm, int64_t n, int64_t batch, int64_t
 int osb_stt_frontend_host(const int16_t* pcm, int64_t n, int64_t batch, int64_t stride, int sample_rate, int noise_reduce,
                           int normalize, int n_mels, float* mel);
 
+/* ---------------------------------------------------------------- TTS post-processing, effects, voice blend
+ * Ragged batches: utterance b = flat[d_offsets[b] : d_offsets[b] + d_lens[b]] (int64 arrays on the device).
+ * osb_tts_post = process_tts_chunks after concatenation: trim_silence (|x| > threshold, first..last) then
+ *   normalize_output (peak -> `peak`, clip) (src/audio/postprocessing.py:8-40); output b starts at d_offsets[b],
+ *   its new length goes to d_out_lens[b].
+ * osb_fx_chain = apply_chain (src/effects/chain.py:15-32): ordered effects, float32 until the first float64
+ *   effect, float64 afterwards, cast to float32 at the end (out_pcm16=1 additionally applies float32_to_int16,
+ *   src/tts/pipeline.py:32-37).  fx_p0/fx_p1: NORMALIZE target_lufs,- | REVERB room_ms,mix | PITCH semitones,-.
+ * osb_voice_blend = KokoroBackend._blend_voices (src/tts/backends/kokoro.py:289-308): result += w_k * pack_k in
+ *   float32, in component order; d_idx [batch][kmax] (-1 terminates), d_weights [batch][kmax]. */
+#define OSB_FX_NORMALIZE 1
+#define OSB_FX_REVERB 2
+#define OSB_FX_PODCAST_EQ 3
+#define OSB_FX_ROBOT 4
+#define OSB_FX_PITCH 5
+int osb_tts_post_dev(const float* d_in, const int64_t* d_offsets, const int64_t* d_lens, int64_t batch, int64_t max_len, int trim,
+                     int normalize, float threshold, float peak, float* d_out, int64_t* d_out_lens, void* stream);
+int osb_fx_chain_dev(const float* d_in, const int64_t* d_offsets, const int64_t* d_lens, int64_t batch, int64_t max_len,
+                     int64_t total, int sample_rate, const int* fx_types, const double* fx_p0, const double* fx_p1, int n_fx,
+                     void* d_out, int out_pcm16, void* stream);
+int osb_voice_blend_dev(const float* d_packs, int64_t pack_elems, const int32_t* d_idx, const float* d_weights, int kmax, int64_t batch,
+                        float* d_out, void* stream);
+int osb_podcast_eq_coeffs(int sample_rate, double* out12); /* b_hp[3], a_hp[3], b_pk[3], a_pk[3] (host) */
+int osb_tts_post_host(const float* in, int64_t n, int trim, int normalize, float threshold, float peak, float* out, int64_t* out_len);
+int osb_fx_chain_host(const float* in, int64_t n, int sample_rate, const int* fx_types, const double* fx_p0, const double* fx_p1, int n_fx,
+                      void* out, int out_pcm16);
+int osb_voice_blend_host(const float* const* packs, const float* weights, int k, int64_t pack_elems, float* out);
+
 #ifdef __cplusplus
 }
 #endif

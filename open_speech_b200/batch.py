@@ -99,6 +99,50 @@ class RealtimeTick:
         return out
 
 
+class TtsPost:
+    """Ragged batch of float32 utterances: trim + peak-normalise -> effects chain -> int16 (BASELINE config 5)."""
+
+    def __init__(self, sample_rate: int = 24000, effects=None, trim: bool = True, normalize: bool = True):
+        from .effects.chain import encode_effects
+
+        N.require_gpu()
+        self.sample_rate, self.trim, self.normalize = sample_rate, trim, normalize
+        self.fx_types, self.fx_p0, self.fx_p1 = encode_effects(effects)
+
+    def __call__(self, flat: torch.Tensor, offsets: torch.Tensor, lens: torch.Tensor, max_len: int,
+                 out_pcm: torch.Tensor | None = None):
+        """flat f32 [total] (device), offsets/lens int64 [B] (device) -> (int16 [total], new lens int64 [B])."""
+        b, total = offsets.numel(), flat.numel()
+        post = torch.empty_like(flat)
+        new_lens = torch.empty_like(lens)
+        N.call("osb_tts_post_dev", flat.data_ptr(), offsets.data_ptr(), lens.data_ptr(), b, int(max_len), int(self.trim), int(self.normalize),
+               0.01, 0.95, post.data_ptr(), new_lens.data_ptr(), _stream())
+        if out_pcm is None:
+            out_pcm = torch.empty(total, dtype=torch.int16, device=flat.device)
+        N.call("osb_fx_chain_dev", post.data_ptr(), offsets.data_ptr(), new_lens.data_ptr(), b, int(max_len), total, self.sample_rate,
+               N.ptr(self.fx_types), N.ptr(self.fx_p0), N.ptr(self.fx_p1), len(self.fx_types), out_pcm.data_ptr(), 1, _stream())
+        return out_pcm, new_lens
+
+    @staticmethod
+    def pack(utts: list[np.ndarray]):
+        """list of f32 arrays -> (flat f32, offsets int64, lens int64); starts aligned to 4 samples."""
+        lens = np.array([len(u) for u in utts], dtype=np.int64)
+        padded = (lens + 3) // 4 * 4
+        offsets = np.concatenate([[0], np.cumsum(padded)[:-1]]).astype(np.int64)
+        flat = np.zeros(int(padded.sum()), dtype=np.float32)
+        for o, u in zip(offsets, utts):
+            flat[o:o + len(u)] = u
+        return flat, offsets, lens
+
+    def run_numpy(self, utts: list[np.ndarray]):
+        """Convenience: list of f32 arrays in, list of int16 arrays out (one H2D, one D2H for the whole batch)."""
+        flat, offsets, lens = self.pack(utts)
+        pcm, new_lens = self(torch.from_numpy(flat).cuda(), torch.from_numpy(offsets).cuda(), torch.from_numpy(lens).cuda(), int(lens.max()))
+        torch.cuda.synchronize()
+        pcm, new_lens = pcm.cpu().numpy(), new_lens.cpu().numpy()
+        return [pcm[o:o + n] for o, n in zip(offsets, new_lens)], new_lens.tolist()
+
+
 def shard_units(n_units: int, world: int, rank: int) -> range:
     """Static sharding of independent clips / streams / utterances: contiguous, balanced to +-1 unit.
     No exchange step exists on this path, so there is no collective."""

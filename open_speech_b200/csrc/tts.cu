@@ -1,0 +1,723 @@
+// TTS output post-processing, the effects chain, Kokoro voice-pack blending.
+//
+// Replaces (reference file:line):
+//   trim_silence / normalize_output / process_tts_chunks   src/audio/postprocessing.py:8-40
+//   apply_chain: _normalize, _reverb, _podcast_eq, _robot  src/effects/chain.py:15-74
+//   KokoroBackend._blend_voices                            src/tts/backends/kokoro.py:289-308
+//
+// Ragged batches: utterance b lives at [offsets[b], offsets[b] + len[b]) of a flat buffer.
+// Numerics follow the reference's dtype flow: float32 until the first float64-producing effect
+// (reverb / podcast_eq / robot), float64 afterwards, one cast to float32 at the end (chain.py:32).
+// The recurrences (exponential-IR reverb, two biquads) are linear: each CTA runs its own stretch of
+// samples from a state that is exact to f64 round-off (direct FIR sum for the reverb; a 4096-sample
+// zero-state warm-up for the biquads, whose poles decay below 1e-26 over that span), so all CTAs
+// are independent and the time axis is parallel.
+#include <cmath>
+#include <vector>
+
+#include "common.cuh"
+
+namespace osb {
+
+struct Ragged {
+    const long long* offsets;  // [B]   start of utterance b in the flat buffer
+    const long long* lens;     // [B]   current length of utterance b
+};
+
+// ---------------------------------------------------------------- trim + peak normalise
+struct TtsStats {
+    int first, last;      // first / last index with |x| > threshold (first = INT_MAX when none)
+    unsigned int maxbits; // bits of max |x| (non-negative float -> ordered as uint)
+    int pad;
+};
+
+__global__ void __launch_bounds__(256) k_tts_stats(const float* __restrict__ x, Ragged rg, float thr, TtsStats* __restrict__ st) {
+    const int b = blockIdx.y;
+    const long long n = rg.lens[b];
+    const float* p = x + rg.offsets[b];
+    int first = 0x7fffffff, last = -1;
+    float mx = 0.f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float a = fabsf(p[i]);
+        mx = fmaxf(mx, a);
+        if (a > thr) {
+            first = min(first, (int)i);
+            last = max(last, (int)i);
+        }
+    }
+    first = warp_min_i(first);
+    last = warp_max_i(last);
+    mx = warp_max(mx);
+    if ((threadIdx.x & 31) == 0) {
+        if (last >= 0) {
+            atomicMin(&st[b].first, first);
+            atomicMax(&st[b].last, last);
+        }
+        atomicMax(&st[b].maxbits, __float_as_uint(mx));
+    }
+}
+
+__global__ void k_tts_stats_init(TtsStats* st, int batch) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < batch) st[i] = TtsStats{0x7fffffff, -1, 0u, 0};
+}
+
+__global__ void __launch_bounds__(256) k_tts_apply(const float* __restrict__ x, Ragged rg, const TtsStats* __restrict__ st, int trim,
+                                                   int normalize, float peak, float* __restrict__ y, long long* __restrict__ out_len) {
+    const int b = blockIdx.y;
+    const long long n = rg.lens[b];
+    const TtsStats s = st[b];
+    long long start = 0, m = n;
+    if (trim && n > 0 && s.last >= 0) {  // nothing above the threshold -> returned unchanged (postprocessing.py:12-13)
+        start = s.first;
+        m = (long long)s.last - s.first + 1;
+    }
+    const float mx = __uint_as_float(s.maxbits);
+    const bool scale_on = normalize && m > 0 && mx > 1e-8f;  // float(max) <= 1e-8 -> unchanged (:21-22)
+    const float scale = scale_on ? (float)((double)peak / (double)mx) : 1.0f;
+    const float* p = x + rg.offsets[b] + start;
+    float* q = y + rg.offsets[b];
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (long long)gridDim.x * blockDim.x) {
+        const float v = p[i];
+        q[i] = scale_on ? fminf(fmaxf(__fmul_rn(v, scale), -1.0f), 1.0f) : v;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) out_len[b] = m;
+}
+
+// ---------------------------------------------------------------- effects: normalise (RMS), robot, cast
+template <typename T>
+__global__ void __launch_bounds__(256) k_fx_sumsq(const T* __restrict__ x, Ragged rg, double* __restrict__ sumsq) {
+    const int b = blockIdx.y;
+    const long long n = rg.lens[b];
+    const T* p = x + rg.offsets[b];
+    double acc = 0.0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const T v = p[i];
+        acc += (sizeof(T) == 4) ? (double)__fmul_rn((float)v, (float)v) : (double)v * (double)v;
+    }
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&sumsq[b], acc);
+}
+
+// samples * (target_rms / rms); rms < 1e-8 -> unchanged; f32 input stays f32 (np.float32 scalar arithmetic)
+template <typename T>
+__global__ void __launch_bounds__(256) k_fx_scale(const T* __restrict__ x, Ragged rg, const double* __restrict__ sumsq, double target_rms,
+                                                  T* __restrict__ y) {
+    const int b = blockIdx.y;
+    const long long n = rg.lens[b];
+    if (n == 0) return;
+    const T* p = x + rg.offsets[b];
+    T* q = y + rg.offsets[b];
+    bool on;
+    T scale;
+    if (sizeof(T) == 4) {
+        const float rms = __fsqrt_rn((float)(sumsq[b] / (double)n));
+        on = !(rms < 1e-8f);
+        scale = (T)((float)target_rms / rms);  // python float / np.float32 -> np.float32
+    } else {
+        const double rms = sqrt(sumsq[b] / (double)n);
+        on = !(rms < 1e-8);
+        scale = (T)(target_rms / rms);
+    }
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        q[i] = on ? (T)(p[i] * scale) : p[i];
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_fx_robot(const T* __restrict__ x, Ragged rg, double sr, double* __restrict__ y) {
+    const int b = blockIdx.y;
+    const long long n = rg.lens[b];
+    const T* p = x + rg.offsets[b];
+    double* q = y + rg.offsets[b];
+    const double w = 2.0 * 3.141592653589793 * 100.0;  // 2*np.pi*100
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        q[i] = (double)p[i] * sin(__dmul_rn(w, __ddiv_rn((double)i, sr)));
+}
+
+// final astype(float32) (f64 -> f32) or f32 copy; optionally clip/x32767/truncate to int16 (float32_to_int16)
+template <typename T, bool PCM16>
+__global__ void __launch_bounds__(256) k_fx_finish(const T* __restrict__ x, Ragged rg, void* __restrict__ y) {
+    const int b = blockIdx.y;
+    const long long n = rg.lens[b];
+    const T* p = x + rg.offsets[b];
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float v = (float)p[i];
+        if (PCM16) reinterpret_cast<int16_t*>(y)[rg.offsets[b] + i] = (int16_t)quant_pcm16(v);
+        else reinterpret_cast<float*>(y)[rg.offsets[b] + i] = v;
+    }
+}
+
+// ---------------------------------------------------------------- reverb: exp-decay FIR as a one-pole recurrence
+// wet[n] = sum_{k<L} ir[k] x[n-k], ir[k] = c r^k  =>  wet[n] = r wet[n-1] + c (x[n] - r^L x[n-L])
+// out = (1-mix) x + mix wet.  CTA = 8192 samples; wet[n0-1] comes from the direct FIR sum with the exact
+// host-computed taps, so CTAs are independent.
+constexpr int kRvT = 32, kRvBlock = 256 * kRvT;  // 8192 samples per CTA
+constexpr int kSegStride = kRvT + 1;             // padded per-thread segment (bank-conflict free for f64)
+
+struct ReverbArgs {
+    Ragged rg;
+    const double* ir;  // [L] host-computed exp(-linspace(0,6,L))/sum
+    int L;
+    double r, c, rL, rT, mix;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_fx_reverb(const T* __restrict__ x, ReverbArgs a, double* __restrict__ y) {
+    extern __shared__ __align__(16) double smd[];
+    double* u = smd;                 // [256][33]
+    __shared__ double red[8];
+    __shared__ double wsum[8];
+    const int b = blockIdx.y, tid = threadIdx.x;
+    const long long n = a.rg.lens[b];
+    const long long n0 = (long long)blockIdx.x * kRvBlock;
+    if (n0 >= n) return;
+    const T* p = x + a.rg.offsets[b];
+    // stage u[i] = c (x[n0+i] - r^L x[n0+i-L])
+    for (int i = tid; i < kRvBlock; i += 256) {
+        const long long g = n0 + i;
+        const double xv = g < n ? (double)p[g] : 0.0;
+        const double xd = (g - a.L >= 0 && g - a.L < n) ? (double)p[g - a.L] : 0.0;
+        u[(i / kRvT) * kSegStride + (i % kRvT)] = a.c * (xv - a.rL * xd);
+    }
+    // carry-in wet[n0-1] = sum_k ir[k] x[n0-1-k]
+    double part = 0.0;
+    if (n0 > 0)
+        for (int k = tid; k < a.L; k += 256) {
+            const long long g = n0 - 1 - k;
+            if (g >= 0) part = fma(a.ir[k], (double)p[g], part);
+        }
+    part = warp_sum(part);
+    if ((tid & 31) == 0) red[tid >> 5] = part;
+    __syncthreads();
+    const double carry0 = ((red[0] + red[1]) + (red[2] + red[3])) + ((red[4] + red[5]) + (red[6] + red[7]));
+    // phase A: zero-state end value of each thread's 32-sample segment
+    double* seg = u + tid * kSegStride;
+    double e = 0.0;
+#pragma unroll
+    for (int i = 0; i < kRvT; ++i) e = fma(a.r, e, seg[i]);
+    // inclusive warp scan with factor rT^(2^k)
+    double f = a.rT, v = e;
+    const int lane = tid & 31, wid = tid >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double up = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v = fma(f, up, v);
+        f *= f;
+    }
+    if (lane == 31) wsum[wid] = v;
+    __syncthreads();
+    // f == rT^32 now; carry into this warp = state after the previous warps, starting from carry0
+    double cw = carry0;
+    for (int w = 0; w < wid; ++w) cw = fma(f, cw, wsum[w]);
+    // state at the start of this thread's segment: rT^lane * cw + (exclusive prefix)
+    double ex = __shfl_up_sync(0xffffffffu, v, 1);
+    if (lane == 0) ex = 0.0;
+    double pw = 1.0, bb = a.rT;
+    for (int l = lane; l > 0; l >>= 1) {
+        if (l & 1) pw *= bb;
+        bb *= bb;
+    }
+    double s = fma(pw, cw, ex);
+    // phase C: real run, outputs written back in place
+#pragma unroll
+    for (int i = 0; i < kRvT; ++i) {
+        s = fma(a.r, s, seg[i]);
+        seg[i] = s;
+    }
+    __syncthreads();
+    double* q = y + a.rg.offsets[b];
+    for (int i = tid; i < kRvBlock; i += 256) {
+        const long long g = n0 + i;
+        if (g < n) {
+            // (1 - mix) * samples is a float32 product while samples is still float32 (NEP 50 weak scalar)
+            const double dry = (sizeof(T) == 4) ? (double)__fmul_rn((float)(1.0 - a.mix), (float)p[g]) : (1.0 - a.mix) * (double)p[g];
+            q[g] = dry + a.mix * u[(i / kRvT) * kSegStride + (i % kRvT)];
+        }
+    }
+}
+
+// ---------------------------------------------------------------- podcast EQ: two DF2T biquads, 4-state linear system
+constexpr int kEqWarm = 4096, kEqOut = 4096;
+
+struct EqArgs {
+    Ragged rg;
+    double b1[3], a1[3], b2[3], a2[3];
+    double P[5][16];  // Phi_T^(2^k), k = 0..4 (row-major 4x4), T = 32 samples
+    double Q[16];     // Phi_T^32
+};
+
+struct St4 {
+    double z[4];
+};
+
+__device__ __forceinline__ St4 mat4(const double* m, const St4& s) {
+    St4 o;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o.z[i] = ((m[4 * i] * s.z[0] + m[4 * i + 1] * s.z[1]) + (m[4 * i + 2] * s.z[2] + m[4 * i + 3] * s.z[3]));
+    return o;
+}
+
+__device__ __forceinline__ double eq_step(const EqArgs& a, St4& s, double x) {
+    // scipy lfilter, direct form II transposed, a[0] = 1
+    const double y1 = a.b1[0] * x + s.z[0];
+    s.z[0] = a.b1[1] * x - a.a1[1] * y1 + s.z[1];
+    s.z[1] = a.b1[2] * x - a.a1[2] * y1;
+    const double y2 = a.b2[0] * y1 + s.z[2];
+    s.z[2] = a.b2[1] * y1 - a.a2[1] * y2 + s.z[3];
+    s.z[3] = a.b2[2] * y1 - a.a2[2] * y2;
+    return y2;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_fx_eq(const T* __restrict__ x, EqArgs a, double* __restrict__ y) {
+    extern __shared__ __align__(16) double smd[];
+    double* u = smd;  // [256][33]
+    __shared__ St4 wsum[8];
+    const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const long long n = a.rg.lens[b];
+    const long long n0 = (long long)blockIdx.x * kEqOut;
+    if (n0 >= n) return;
+    const T* p = x + a.rg.offsets[b];
+    const long long base = n0 - kEqWarm;
+    for (int i = tid; i < kEqWarm + kEqOut; i += 256) {
+        const long long g = base + i;
+        u[(i / 32) * kSegStride + (i % 32)] = (g >= 0 && g < n) ? (double)p[g] : 0.0;
+    }
+    __syncthreads();
+    double* seg = u + tid * kSegStride;
+    St4 e{{0, 0, 0, 0}};
+#pragma unroll 4
+    for (int i = 0; i < 32; ++i) eq_step(a, e, seg[i]);
+    // inclusive warp scan over segments: v_j = Phi^(2^k) v_{j-2^k} + v_j
+    St4 v = e;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        St4 up;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) up.z[i] = __shfl_up_sync(0xffffffffu, v.z[i], 1 << k);
+        if (lane >= (1 << k)) {
+            const St4 t = mat4(a.P[k], up);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) v.z[i] += t.z[i];
+        }
+    }
+    if (lane == 31) wsum[wid] = v;
+    __syncthreads();
+    St4 cw{{0, 0, 0, 0}};  // the block starts from rest, kEqWarm samples before its first output
+    for (int w = 0; w < wid; ++w) {
+        const St4 t = mat4(a.Q, cw);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) cw.z[i] = t.z[i] + wsum[w].z[i];
+    }
+    // fold the warp carry into lane 0 and rescan: v'_j = true end state of segment j
+    St4 e2 = e;
+    if (lane == 0) {
+        const St4 t = mat4(a.P[0], cw);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) e2.z[i] += t.z[i];
+    }
+    v = e2;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        St4 up;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) up.z[i] = __shfl_up_sync(0xffffffffu, v.z[i], 1 << k);
+        if (lane >= (1 << k)) {
+            const St4 t = mat4(a.P[k], up);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) v.z[i] += t.z[i];
+        }
+    }
+    St4 s;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const double pv = __shfl_up_sync(0xffffffffu, v.z[i], 1);
+        s.z[i] = lane == 0 ? cw.z[i] : pv;
+    }
+#pragma unroll 4
+    for (int i = 0; i < 32; ++i) seg[i] = eq_step(a, s, seg[i]);
+    __syncthreads();
+    double* q = y + a.rg.offsets[b];
+    for (int i = kEqWarm + tid; i < kEqWarm + kEqOut; i += 256) {
+        const long long g = base + i;
+        if (g < n) q[g] = u[(i / 32) * kSegStride + (i % 32)];
+    }
+}
+
+// ---------------------------------------------------------------- voice blend
+// out[b] = sum_k w[b][k] * pack[idx[b][k]]  accumulated in order in f32 (torch: result += w * t)
+__global__ void __launch_bounds__(256) k_voice_blend(const float* __restrict__ packs, long long n, const int* __restrict__ idx,
+                                                     const float* __restrict__ w, int kmax, float* __restrict__ out) {
+    const int b = blockIdx.y;
+    const long long nvec = n / 4;
+    for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (long long)gridDim.x * blockDim.x) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int k = 0; k < kmax; ++k) {
+            const int id = idx[b * kmax + k];
+            if (id < 0) break;
+            const float wk = w[b * kmax + k];
+            const float4 t = reinterpret_cast<const float4*>(packs + (long long)id * n)[v];
+            acc.x = __fadd_rn(acc.x, __fmul_rn(wk, t.x)); acc.y = __fadd_rn(acc.y, __fmul_rn(wk, t.y));
+            acc.z = __fadd_rn(acc.z, __fmul_rn(wk, t.z)); acc.w = __fadd_rn(acc.w, __fmul_rn(wk, t.w));
+        }
+        reinterpret_cast<float4*>(out + (long long)b * n)[v] = acc;
+    }
+    if (blockIdx.x == 0)
+        for (long long i = nvec * 4 + threadIdx.x; i < n; i += blockDim.x) {
+            float acc = 0.f;
+            for (int k = 0; k < kmax; ++k) {
+                const int id = idx[b * kmax + k];
+                if (id < 0) break;
+                acc = __fadd_rn(acc, __fmul_rn(w[b * kmax + k], packs[(long long)id * n + i]));
+            }
+            out[(long long)b * n + i] = acc;
+        }
+}
+
+// ---------------------------------------------------------------- host side
+static dim3 ragged_grid(long long max_len, long long batch, int per_thread = 4) {
+    long long per = (max_len / per_thread + 255) / 256;
+    long long want = ((long long)OSB_NUM_SMS * 8 + batch - 1) / batch;
+    if (per > want) per = want;
+    if (per < 1) per = 1;
+    return dim3((unsigned)per, (unsigned)batch);
+}
+
+// simulate the 4-state cascade to get Phi_T (T samples, zero input) -- plain host doubles
+static void eq_transition(const EqArgs& a, int T, double* phi /*16*/) {
+    for (int col = 0; col < 4; ++col) {
+        double z[4] = {0, 0, 0, 0};
+        z[col] = 1.0;
+        for (int t = 0; t < T; ++t) {
+            const double y1 = z[0];
+            z[0] = -a.a1[1] * y1 + z[1];
+            z[1] = -a.a1[2] * y1;
+            const double y2 = a.b2[0] * y1 + z[2];
+            z[2] = a.b2[1] * y1 - a.a2[1] * y2 + z[3];
+            z[3] = a.b2[2] * y1 - a.a2[2] * y2;
+        }
+        for (int r = 0; r < 4; ++r) phi[4 * r + col] = z[r];
+    }
+}
+
+static void matmul4(const double* A, const double* B, double* C) {
+    double t[16];
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) {
+            double s = 0;
+            for (int k = 0; k < 4; ++k) s += A[4 * i + k] * B[4 * k + j];
+            t[4 * i + j] = s;
+        }
+    memcpy(C, t, sizeof(t));
+}
+
+// scipy.signal.butter(2, 80/nyq, 'high') and iirpeak(3000/nyq, Q=2), restated (bilinear transform forms)
+static void podcast_eq_coeffs(double sr, EqArgs& a) {
+    const double pi = 3.14159265358979323846;
+    {   // 2nd-order Butterworth high-pass: analog prototype s^2 + sqrt(2) s + 1, pre-warped, bilinear (fs = 2)
+        const double wn = 80.0 / (sr / 2.0);
+        const double warped = 4.0 * std::tan(pi * wn / 2.0);  // 2*fs*tan(pi*wn/fs), fs = 2
+        // lp2hp of the prototype poles p = exp(+-j 3pi/4): poles warped/p ; zeros at 0 (double) ; gain 1
+        const double pr = warped * std::cos(3.0 * pi / 4.0), pim = warped * std::sin(3.0 * pi / 4.0);  // warped/p = warped*conj(p)/|p|^2
+        const double fs2 = 4.0;
+        // bilinear: z = (fs2 + s)/(fs2 - s)
+        const double dr = fs2 - pr, di = -pim;                 // fs2 - p
+        const double nr = fs2 + pr, ni = pim;                  // fs2 + p
+        const double den = dr * dr + di * di;
+        const double zr = (nr * dr + ni * di) / den, zi = (ni * dr - nr * di) / den;  // pole in z
+        // gain: k * prod(fs2 - z)/prod(fs2 - p) with z = 0 (double): fs2^2 / |fs2 - p|^2
+        const double k = (fs2 * fs2) / den;
+        a.b1[0] = k; a.b1[1] = -2.0 * k; a.b1[2] = k;         // zeros at z = +1 (double)
+        a.a1[0] = 1.0; a.a1[1] = -2.0 * zr; a.a1[2] = zr * zr + zi * zi;
+    }
+    {   // iirpeak(w0, Q): scipy _design_notch_peak_filter
+        const double w0n = 3000.0 / (sr / 2.0);
+        const double bw = (w0n / 2.0) * pi;        // bw = w0/Q with Q = 2, then *pi
+        const double w0 = w0n * pi;
+        const double gb = 1.0 / std::sqrt(2.0);
+        const double beta = (gb / std::sqrt(1.0 - gb * gb)) * std::tan(bw / 2.0);
+        const double gain = 1.0 / (1.0 + beta);
+        a.b2[0] = (1.0 - gain); a.b2[1] = 0.0; a.b2[2] = -(1.0 - gain);
+        a.a2[0] = 1.0; a.a2[1] = -2.0 * gain * std::cos(w0); a.a2[2] = (2.0 * gain - 1.0);
+    }
+}
+
+struct FxState {
+    cudaStream_t st;
+    Ragged rg;
+    long long batch, max_len, total;
+    void* cur;       // current data
+    bool f64;
+    float* f32_tmp;  // scratch buffers (total elements each)
+    double* d_a;
+    double* d_b;
+};
+
+static int fx_normalize(FxState& s, double target_lufs, Scratch& scr) {
+    double* sumsq;
+    OSB_CUDA(scr.alloc(&sumsq, (size_t)s.batch));
+    OSB_CUDA(cudaMemsetAsync(sumsq, 0, sizeof(double) * s.batch, s.st));
+    const dim3 g = ragged_grid(s.max_len, s.batch);
+    const double target_rms = std::pow(10.0, target_lufs / 20.0);
+    if (!s.f64) {
+        OSB_LAUNCH(k_fx_sumsq<float>, g, 256, 0, s.st, (const float*)s.cur, s.rg, sumsq);
+        OSB_CHECK_LAUNCH();
+        OSB_LAUNCH(k_fx_scale<float>, g, 256, 0, s.st, (const float*)s.cur, s.rg, sumsq, target_rms, s.f32_tmp);
+        OSB_CHECK_LAUNCH();
+        s.cur = s.f32_tmp;
+    } else {
+        double* dst = (s.cur == s.d_a) ? s.d_b : s.d_a;
+        OSB_LAUNCH(k_fx_sumsq<double>, g, 256, 0, s.st, (const double*)s.cur, s.rg, sumsq);
+        OSB_CHECK_LAUNCH();
+        OSB_LAUNCH(k_fx_scale<double>, g, 256, 0, s.st, (const double*)s.cur, s.rg, sumsq, target_rms, dst);
+        OSB_CHECK_LAUNCH();
+        s.cur = dst;
+    }
+    return OSB_OK;
+}
+
+static int fx_reverb(FxState& s, int sample_rate, int room_ms, double mix, Scratch& scr) {
+    int L = (int)((long long)sample_rate * room_ms / 1000);
+    if (L < 1) L = 1;
+    std::vector<double> ir(L);
+    double sum = 0.0;
+    for (int k = 0; k < L; ++k) {
+        // np.linspace(0, 6, L)[k] = k * (6/(L-1)), last = 6
+        const double t = (L == 1) ? 0.0 : (k == L - 1 ? 6.0 : k * (6.0 / (L - 1)));
+        ir[k] = std::exp(-t);
+    }
+    // ir /= ir.sum()  (numpy pairwise sum; the Kahan sum below agrees to the last ulp or two of ~L terms)
+    double c = 0.0;
+    for (int k = 0; k < L; ++k) { const double yk = ir[k] - c, t = sum + yk; c = (t - sum) - yk; sum = t; }
+    for (int k = 0; k < L; ++k) ir[k] /= sum;
+    double* d_ir;
+    OSB_CUDA(scr.alloc(&d_ir, (size_t)L));
+    OSB_CUDA(cudaMemcpyAsync(d_ir, ir.data(), sizeof(double) * L, cudaMemcpyHostToDevice, s.st));
+    OSB_CUDA(cudaStreamSynchronize(s.st));  // ir is a stack vector: the copy must finish before it goes away
+    ReverbArgs a;
+    a.rg = s.rg; a.ir = d_ir; a.L = L; a.mix = mix;
+    a.r = (L == 1) ? 0.0 : std::exp(-6.0 / (L - 1));
+    a.c = ir[0];
+    a.rL = (L == 1) ? 0.0 : std::exp(-6.0 * L / (L - 1));
+    a.rT = std::pow(a.r, (double)kRvT);
+    double* dst = (s.cur == s.d_a) ? s.d_b : s.d_a;
+    const dim3 g((unsigned)((s.max_len + kRvBlock - 1) / kRvBlock), (unsigned)s.batch);
+    const int smem = 256 * kSegStride * (int)sizeof(double);
+    static bool attr_done = false;
+    if (!attr_done) {
+        OSB_CUDA(cudaFuncSetAttribute(k_fx_reverb<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        OSB_CUDA(cudaFuncSetAttribute(k_fx_reverb<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        OSB_CUDA(cudaFuncSetAttribute(k_fx_eq<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        OSB_CUDA(cudaFuncSetAttribute(k_fx_eq<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_done = true;
+    }
+    if (!s.f64) OSB_LAUNCH(k_fx_reverb<float>, g, 256, smem, s.st, (const float*)s.cur, a, dst);
+    else OSB_LAUNCH(k_fx_reverb<double>, g, 256, smem, s.st, (const double*)s.cur, a, dst);
+    OSB_CHECK_LAUNCH();
+    s.cur = dst;
+    s.f64 = true;
+    return OSB_OK;
+}
+
+static int fx_eq(FxState& s, int sample_rate) {
+    EqArgs a;
+    a.rg = s.rg;
+    podcast_eq_coeffs((double)sample_rate, a);
+    // warm-up must outlast the slowest pole: |p|^kEqWarm < 1e-17
+    const double rad = std::sqrt(std::fmax(a.a1[2], a.a2[2]));
+    if (!(rad < 1.0) || kEqWarm * std::log(rad) > std::log(1e-17)) {
+        set_error("unsupported: podcast_eq at %d Hz needs a warm-up longer than %d samples", sample_rate, kEqWarm);
+        return OSB_ERR_UNSUPPORTED;
+    }
+    eq_transition(a, 32, a.P[0]);
+    for (int k = 1; k < 5; ++k) matmul4(a.P[k - 1], a.P[k - 1], a.P[k]);
+    matmul4(a.P[4], a.P[4], a.Q);
+    double* dst = (s.cur == s.d_a) ? s.d_b : s.d_a;
+    const dim3 g((unsigned)((s.max_len + kEqOut - 1) / kEqOut), (unsigned)s.batch);
+    const int smem = 256 * kSegStride * (int)sizeof(double);
+    static bool attr_done = false;
+    if (!attr_done) {
+        OSB_CUDA(cudaFuncSetAttribute(k_fx_eq<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        OSB_CUDA(cudaFuncSetAttribute(k_fx_eq<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_done = true;
+    }
+    if (!s.f64) OSB_LAUNCH(k_fx_eq<float>, g, 256, smem, s.st, (const float*)s.cur, a, dst);
+    else OSB_LAUNCH(k_fx_eq<double>, g, 256, smem, s.st, (const double*)s.cur, a, dst);
+    OSB_CHECK_LAUNCH();
+    s.cur = dst;
+    s.f64 = true;
+    return OSB_OK;
+}
+
+static int fx_robot(FxState& s, int sample_rate) {
+    double* dst = (s.cur == s.d_a) ? s.d_b : s.d_a;
+    const dim3 g = ragged_grid(s.max_len, s.batch);
+    if (!s.f64) OSB_LAUNCH(k_fx_robot<float>, g, 256, 0, s.st, (const float*)s.cur, s.rg, (double)sample_rate, dst);
+    else OSB_LAUNCH(k_fx_robot<double>, g, 256, 0, s.st, (const double*)s.cur, s.rg, (double)sample_rate, dst);
+    OSB_CHECK_LAUNCH();
+    s.cur = dst;
+    s.f64 = true;
+    return OSB_OK;
+}
+
+}  // namespace osb
+
+using namespace osb;
+
+extern "C" {
+
+int osb_tts_post_dev(const float* d_in, const int64_t* d_offsets, const int64_t* d_lens, int64_t batch, int64_t max_len, int trim,
+                     int normalize, float threshold, float peak, float* d_out, int64_t* d_out_lens, void* stream) {
+    int rc = ensure_init();
+    if (rc) return rc;
+    OSB_REQUIRE(batch >= 0 && max_len >= 0, "bad sizes");
+    if (batch == 0) return OSB_OK;
+    OSB_REQUIRE(batch <= 65535, "batch too large (<= 65535)");
+    OSB_REQUIRE(d_in && d_offsets && d_lens && d_out && d_out_lens, "null buffer");
+    cudaStream_t st = (cudaStream_t)stream;
+    Scratch scr(st);
+    TtsStats* stats;
+    OSB_CUDA(scr.alloc(&stats, (size_t)batch));
+    Ragged rg{(const long long*)d_offsets, (const long long*)d_lens};
+    OSB_LAUNCH(k_tts_stats_init, (unsigned)((batch + 255) / 256), 256, 0, st, stats, (int)batch);
+    OSB_CHECK_LAUNCH();
+    const dim3 g = ragged_grid(max_len > 0 ? max_len : 1, batch);
+    OSB_LAUNCH(k_tts_stats, g, 256, 0, st, d_in, rg, threshold, stats);
+    OSB_CHECK_LAUNCH();
+    OSB_LAUNCH(k_tts_apply, g, 256, 0, st, d_in, rg, stats, trim, normalize, peak, d_out, (long long*)d_out_lens);
+    OSB_CHECK_LAUNCH();
+    return OSB_OK;
+}
+
+int osb_fx_chain_dev(const float* d_in, const int64_t* d_offsets, const int64_t* d_lens, int64_t batch, int64_t max_len,
+                     int64_t total, int sample_rate, const int* fx_types, const double* fx_p0, const double* fx_p1, int n_fx,
+                     void* d_out, int out_pcm16, void* stream) {
+    int rc = ensure_init();
+    if (rc) return rc;
+    OSB_REQUIRE(batch >= 0 && max_len >= 0 && total >= 0 && n_fx >= 0 && sample_rate > 0, "bad sizes");
+    if (batch == 0 || total == 0) return OSB_OK;
+    OSB_REQUIRE(batch <= 65535, "batch too large (<= 65535)");
+    OSB_REQUIRE(d_in && d_offsets && d_lens && d_out && (n_fx == 0 || (fx_types && fx_p0 && fx_p1)), "null buffer");
+    cudaStream_t st = (cudaStream_t)stream;
+    Scratch scr(st);
+    FxState s;
+    s.st = st; s.rg = Ragged{(const long long*)d_offsets, (const long long*)d_lens};
+    s.batch = batch; s.max_len = max_len > 0 ? max_len : 1; s.total = total;
+    s.cur = (void*)d_in; s.f64 = false;
+    OSB_CUDA(scr.alloc(&s.f32_tmp, (size_t)total));
+    OSB_CUDA(scr.alloc(&s.d_a, (size_t)total));
+    OSB_CUDA(scr.alloc(&s.d_b, (size_t)total));
+    for (int i = 0; i < n_fx; ++i) {
+        switch (fx_types[i]) {
+            case OSB_FX_NORMALIZE: rc = fx_normalize(s, fx_p0[i], scr); break;
+            case OSB_FX_REVERB: rc = fx_reverb(s, sample_rate, (int)fx_p0[i], fx_p1[i], scr); break;
+            case OSB_FX_PODCAST_EQ: rc = fx_eq(s, sample_rate); break;
+            case OSB_FX_ROBOT: rc = fx_robot(s, sample_rate); break;
+            case OSB_FX_PITCH:
+                if (fx_p0[i] == 0.0) { rc = OSB_OK; break; }  // identity (chain.py:46-47)
+                set_error("unsupported: pitch shift (librosa phase vocoder + soxr) is not implemented (SURVEY.md 8(f) row 2)");
+                rc = OSB_ERR_UNSUPPORTED;
+                break;
+            default: rc = OSB_OK; break;  // unknown effect types are skipped silently (chain.py:18-31)
+        }
+        if (rc) return rc;
+    }
+    const dim3 g = ragged_grid(s.max_len, batch);
+    if (s.f64) {
+        if (out_pcm16) OSB_LAUNCH((k_fx_finish<double, true>), g, 256, 0, st, (const double*)s.cur, s.rg, d_out);
+        else OSB_LAUNCH((k_fx_finish<double, false>), g, 256, 0, st, (const double*)s.cur, s.rg, d_out);
+    } else {
+        if (out_pcm16) OSB_LAUNCH((k_fx_finish<float, true>), g, 256, 0, st, (const float*)s.cur, s.rg, d_out);
+        else OSB_LAUNCH((k_fx_finish<float, false>), g, 256, 0, st, (const float*)s.cur, s.rg, d_out);
+    }
+    OSB_CHECK_LAUNCH();
+    return OSB_OK;
+}
+
+int osb_voice_blend_dev(const float* d_packs, int64_t pack_elems, const int32_t* d_idx, const float* d_weights, int kmax, int64_t batch,
+                        float* d_out, void* stream) {
+    int rc = ensure_init();
+    if (rc) return rc;
+    OSB_REQUIRE(pack_elems >= 0 && kmax >= 1 && batch >= 0, "bad sizes");
+    if (batch == 0 || pack_elems == 0) return OSB_OK;
+    OSB_REQUIRE(batch <= 65535, "batch too large (<= 65535)");
+    OSB_REQUIRE(d_packs && d_idx && d_weights && d_out, "null buffer");
+    OSB_REQUIRE(((uintptr_t)d_packs & 15) == 0 && ((uintptr_t)d_out & 15) == 0 && pack_elems % 4 == 0, "packs must be 16-byte aligned, length % 4 == 0");
+    long long per = (pack_elems / 4 + 255) / 256;
+    if (per > 64) per = 64;
+    OSB_LAUNCH(k_voice_blend, dim3((unsigned)per, (unsigned)batch), 256, 0, (cudaStream_t)stream, d_packs, (long long)pack_elems, d_idx,
+               d_weights, kmax, d_out);
+    OSB_CHECK_LAUNCH();
+    return OSB_OK;
+}
+
+int osb_podcast_eq_coeffs(int sample_rate, double* out12) {
+    OSB_REQUIRE(sample_rate > 0 && out12, "bad arguments");
+    EqArgs a;
+    podcast_eq_coeffs((double)sample_rate, a);
+    for (int i = 0; i < 3; ++i) { out12[i] = a.b1[i]; out12[3 + i] = a.a1[i]; out12[6 + i] = a.b2[i]; out12[9 + i] = a.a2[i]; }
+    return OSB_OK;
+}
+
+// ---------------------------------------------------------------- host-pointer wrappers (one utterance / one blend)
+int osb_tts_post_host(const float* in, int64_t n, int trim, int normalize, float threshold, float peak, float* out, int64_t* out_len) {
+    HostWs& ws = host_ws();
+    int rc = ws.prepare();
+    if (rc) return rc;
+    OSB_REQUIRE(out_len, "null out_len");
+    *out_len = n > 0 ? n : 0;
+    if (n <= 0) return OSB_OK;
+    void *di, *dout, *dmeta;
+    if ((rc = ws.dev_buf(0, (size_t)n * 4, &di)) || (rc = ws.dev_buf(1, (size_t)n * 4, &dout)) || (rc = ws.dev_buf(2, 64, &dmeta))) return rc;
+    if ((rc = ws.h2d(di, in, (size_t)n * 4))) return rc;
+    long long meta[3] = {0, n, 0};
+    OSB_CUDA(cudaMemcpyAsync(dmeta, meta, sizeof(meta), cudaMemcpyHostToDevice, ws.stream));
+    long long* dm = (long long*)dmeta;
+    if ((rc = osb_tts_post_dev((const float*)di, (const int64_t*)dm, (const int64_t*)(dm + 1), 1, n, trim, normalize, threshold, peak, (float*)dout,
+                               (int64_t*)(dm + 2), ws.stream))) return rc;
+    long long m = 0;
+    OSB_CUDA(cudaMemcpyAsync(&m, dm + 2, sizeof(long long), cudaMemcpyDeviceToHost, ws.stream));
+    if ((rc = ws.sync())) return rc;
+    *out_len = m;
+    return ws.d2h(out, dout, (size_t)m * 4);
+}
+
+int osb_fx_chain_host(const float* in, int64_t n, int sample_rate, const int* fx_types, const double* fx_p0, const double* fx_p1, int n_fx,
+                      void* out, int out_pcm16) {
+    HostWs& ws = host_ws();
+    int rc = ws.prepare();
+    if (rc) return rc;
+    if (n <= 0) return OSB_OK;
+    void *di, *dout, *dmeta;
+    if ((rc = ws.dev_buf(0, (size_t)n * 4, &di)) || (rc = ws.dev_buf(1, (size_t)n * 4, &dout)) || (rc = ws.dev_buf(2, 64, &dmeta))) return rc;
+    if ((rc = ws.h2d(di, in, (size_t)n * 4))) return rc;
+    long long meta[2] = {0, n};
+    OSB_CUDA(cudaMemcpyAsync(dmeta, meta, sizeof(meta), cudaMemcpyHostToDevice, ws.stream));
+    long long* dm = (long long*)dmeta;
+    if ((rc = osb_fx_chain_dev((const float*)di, (const int64_t*)dm, (const int64_t*)(dm + 1), 1, n, n, sample_rate, fx_types, fx_p0, fx_p1, n_fx,
+                               dout, out_pcm16, ws.stream))) return rc;
+    return ws.d2h(out, dout, (size_t)n * (out_pcm16 ? 2 : 4));
+}
+
+int osb_voice_blend_host(const float* const* packs, const float* weights, int k, int64_t pack_elems, float* out) {
+    HostWs& ws = host_ws();
+    int rc = ws.prepare();
+    if (rc) return rc;
+    OSB_REQUIRE(k >= 1 && k <= 64 && packs && weights && out && pack_elems >= 0, "bad arguments");
+    if (pack_elems == 0) return OSB_OK;
+    const long long padded = (pack_elems + 3) / 4 * 4;
+    void *dp, *dout, *dmeta;
+    if ((rc = ws.dev_buf(0, (size_t)k * padded * 4, &dp)) || (rc = ws.dev_buf(1, (size_t)padded * 4, &dout)) || (rc = ws.dev_buf(2, 1024, &dmeta))) return rc;
+    OSB_CUDA(cudaMemsetAsync(dp, 0, (size_t)k * padded * 4, ws.stream));
+    for (int i = 0; i < k; ++i)
+        OSB_CUDA(cudaMemcpyAsync((float*)dp + (size_t)i * padded, packs[i], (size_t)pack_elems * 4, cudaMemcpyHostToDevice, ws.stream));
+    int idx[64];
+    for (int i = 0; i < k; ++i) idx[i] = i;
+    OSB_CUDA(cudaMemcpyAsync(dmeta, idx, sizeof(int) * k, cudaMemcpyHostToDevice, ws.stream));
+    OSB_CUDA(cudaMemcpyAsync((char*)dmeta + 512, weights, sizeof(float) * k, cudaMemcpyHostToDevice, ws.stream));
+    OSB_CUDA(cudaStreamSynchronize(ws.stream));
+    if ((rc = osb_voice_blend_dev((const float*)dp, padded, (const int32_t*)dmeta, (const float*)((char*)dmeta + 512), k, 1, (float*)dout, ws.stream))) return rc;
+    return ws.d2h(out, dout, (size_t)pack_elems * 4);
+}
+
+}  // extern "C"

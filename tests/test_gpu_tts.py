@@ -1,0 +1,130 @@
+"""GPU parity: TTS post-processing, effects chain, voice blend (BASELINE config 5 chain)."""
+import numpy as np
+import pytest
+
+from oracle import tts as otts
+
+pytestmark = pytest.mark.gpu
+FX = [{"type": "normalize", "target_lufs": -16}, {"type": "reverb", "room": "medium"}, {"type": "podcast_eq"}, {"type": "robot"}]
+
+
+def _rel(got, ref):
+    return float(np.abs(got.astype(np.float64) - ref.astype(np.float64)).max() / max(1e-12, float(np.abs(ref).max())))
+
+
+def test_postprocessing_golden(gpu, golden):
+    from open_speech_b200.audio import postprocessing as post
+
+    utt = golden["tts_in"]
+    chunks = [utt[:9000], utt[9000:20000], utt[20000:]]
+    out = list(post.process_tts_chunks(iter(chunks), trim=True, normalize=True))
+    assert len(out) == 1 and out[0].dtype == np.float32
+    assert np.array_equal(out[0], golden["tts_post_out"])  # pure elementwise f32: bit-exact
+    assert np.array_equal(post.trim_silence(utt), golden["tts_trim_only"])
+    assert np.array_equal(post.normalize_output(utt), golden["tts_norm_only"])
+    assert list(post.process_tts_chunks(iter(()))) == []
+
+
+def test_postprocessing_reference_behaviour(gpu):
+    """tests/test_audio_processing.py:39-78 of the reference."""
+    from open_speech_b200.audio import postprocessing as post
+
+    x = np.concatenate([np.zeros(100), np.ones(200) * 0.5, np.zeros(100)]).astype(np.float32)
+    assert len(post.trim_silence(x, threshold=0.1)) == 200
+    z = np.zeros(100, dtype=np.float32)
+    assert post.trim_silence(z) is z
+    y = post.normalize_output(np.array([0.1, -0.2, 0.4], dtype=np.float32), peak=0.9)
+    assert abs(float(np.max(np.abs(y))) - 0.9) < 1e-3
+    out = list(post.process_tts_chunks(iter([np.ones(5, np.float32), np.ones(5, np.float32)]), trim=False, normalize=False))
+    assert len(out) == 1 and len(out[0]) == 10
+    x = np.concatenate([np.zeros(5), np.ones(5) * 0.2, np.zeros(5)]).astype(np.float32)
+    o = list(post.process_tts_chunks(iter([x]), trim=True, normalize=True))[0]
+    assert len(o) == 5 and float(np.max(np.abs(o))) > 0.9
+    assert np.allclose(post.normalize_output(np.zeros(10, np.float32)), 0)
+    e = np.zeros(0, np.float32)
+    assert post.trim_silence(e) is e and post.normalize_output(e) is e
+
+
+@pytest.mark.parametrize("key,fx", [
+    ("fx_chain_out", FX),
+    ("fx_normalize", [{"type": "normalize", "target_lufs": -20}]),
+    ("fx_reverb_small", [{"type": "reverb", "room": "small"}]),
+    ("fx_reverb_medium", [{"type": "reverb", "room": "medium"}]),
+    ("fx_reverb_large", [{"type": "reverb", "room": "large"}]),
+    ("fx_podcast_eq", [{"type": "podcast_eq"}]),
+    ("fx_robot", [{"type": "robot"}]),
+    ("fx_robot_then_norm", [{"type": "robot"}, {"type": "normalize", "target_lufs": -18}]),
+])
+def test_effects_golden(gpu, golden, key, fx):
+    """Vectors produced by the reference's own src/effects/chain.py.  Tolerance 1e-4 of the peak (north_star)."""
+    from open_speech_b200.effects.chain import apply_chain
+
+    got = apply_chain(golden["tts_post_out"], 24000, fx)
+    ref = golden[key]
+    assert got.dtype == np.float32 and got.shape == ref.shape
+    assert _rel(got, ref) <= 1e-4, _rel(got, ref)
+
+
+def test_effects_long_utterance_vs_oracle(gpu):
+    """12 s utterance: many CTAs per utterance -> exercises the carry-in of the blocked recurrences."""
+    from open_speech_b200 import synth
+    from open_speech_b200.effects.chain import _reverb, apply_chain
+
+    x = synth.tts_utterance(12.0, seed=3)
+    for fx in (FX, [{"type": "reverb", "room": "large", "mix": 0.7}], [{"type": "podcast_eq"}, {"type": "reverb", "room": "small"}]):
+        got, ref = apply_chain(x, 24000, fx), otts.apply_chain(x, 24000, fx)
+        assert _rel(got, ref) <= 1e-5, (fx, _rel(got, ref))
+    # reference behaviours (tests/test_effects_chain.py)
+    s = np.ones(1000, dtype=np.float32) * 0.95
+    assert np.max(np.abs(apply_chain(s, 24000, [{"type": "normalize", "target_lufs": -20}]))) < 0.95
+    r = np.random.default_rng(0).standard_normal(1000).astype(np.float32) * 0.1
+    assert np.allclose(apply_chain(r, 24000, []), r) and np.allclose(apply_chain(r, 24000, [{"type": "unknown"}]), r)
+    assert np.array_equal(apply_chain(r, 24000, [{"type": "pitch", "semitones": 0}]), r)
+    with pytest.raises(RuntimeError):
+        apply_chain(r, 24000, [{"type": "pitch", "semitones": 4}])
+    imp = np.zeros(24000, np.float32)
+    imp[0] = 1.0
+    assert np.sum(np.abs(_reverb(imp, 24000, room="medium", mix=0.5)[1:])) > 0
+
+
+def test_voice_blend_golden_bit_exact(gpu, golden):
+    import torch
+    from open_speech_b200.tts.blend import blend_voice_arrays, blend_voices
+    from open_speech_b200.tts.voices import parse_voice_spec
+
+    packs = [golden[f"blend_pack{i}"] for i in range(3)]
+    for name, spec, k in (("a2b1", "a(2)+b(1)", 2), ("ab", "a+b", 2), ("a3b2c1", "a(3)+b(2)+c(1)", 3)):
+        s = parse_voice_spec(spec)
+        out = blend_voice_arrays(packs[:k], s.normalized_weights())
+        assert out.shape == packs[0].shape and np.array_equal(out, golden[f"blend_{name}"]), name
+
+    class P:  # the reference's own test (tests/test_tts_kokoro.py:128-147): 50/50 of 3.0 and 6.0 = 4.5
+        def __init__(self):
+            self.calls = []
+
+        def load_voice(self, vid):
+            self.calls.append(vid)
+            return torch.ones(10) * (3.0 if len(self.calls) == 1 else 6.0)
+
+    p = P()
+    r = blend_voices(p, parse_voice_spec("af_bella+af_sky"))
+    assert isinstance(r, torch.Tensor) and torch.allclose(r, torch.ones(10) * 4.5) and p.calls == ["af_bella", "af_sky"]
+    assert parse_voice_spec("alloy").primary_id == "af_heart"
+    assert parse_voice_spec("a(2)+b(1)").normalized_weights() == [2 / 3, 1 / 3]
+    with pytest.raises(ValueError):
+        parse_voice_spec("a(+b")
+
+
+def test_tts_batch_config5_chain(gpu):
+    """Ragged batch through the device entry points == per-utterance oracle chain (trim+norm -> effects -> int16)."""
+    from open_speech_b200 import synth
+    from open_speech_b200.batch import TtsPost
+
+    utts = synth.tts_batch(12, seed=synth.SEED_C5, distinct=12, min_s=0.5, max_s=3.0)
+    pcm, lens = TtsPost(sample_rate=24000, effects=FX).run_numpy(utts)
+    for i, u in enumerate(utts):
+        ref = otts.tts_chain([u], FX)
+        got = pcm[i]
+        assert len(got) == len(ref) == lens[i]
+        d = np.abs(got.astype(np.int32) - ref.astype(np.int32))
+        assert d.max() <= 3, (i, int(d.max()))  # 1e-4 of full scale
