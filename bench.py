@@ -299,12 +299,190 @@ def run_gpu(args) -> None:
         dist.destroy_process_group()
 
 
+
+# ----------------------------------------------------------------------------- other BASELINE configs (single GPU)
+def _gpu_setup():
+    import torch
+
+    from open_speech_b200 import _native as N
+
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    N.require_gpu()
+    N.check(N.lib().osb_init(local))
+    return torch, N
+
+
+def _time_ms(torch, fn, steps, warmup=3):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def _profile(N, fn, steps):
+    N.check(N.lib().osb_profile_enable(1))
+    for _ in range(steps):
+        fn()
+    buf = ctypes.create_string_buffer(1 << 16)
+    N.check(N.lib().osb_profile_report(buf, len(buf)))
+    N.check(N.lib().osb_profile_enable(0))
+    return {k: v["ms"] / steps for k, v in json.loads(buf.value.decode()).items()}
+
+
+def run_vad(args):
+    """BASELINE configs[1]: Silero-shaped VAD scoring + segmenting; (i) one 1 h stream, (ii) 256 streams x 10 min."""
+    torch, N = _gpu_setup()
+    from open_speech_b200 import synth
+    from open_speech_b200.batch import VadBatch
+
+    peak, src = load_peaks()
+    vb = VadBatch()
+    one = torch.from_numpy(np.tile(synth.clip_pcm16(600.0, seed=synth.SEED_C2), 6)[None, :]).cuda()      # 1 h = 57.6 M samples
+    ms_one = _time_ms(torch, lambda: vb(one), max(1, args.steps // 3), warmup=1)
+    streams = args.clips or 256
+    many = torch.from_numpy(np.tile(synth.clip_pcm16(600.0, seed=synth.SEED_C2 + 1)[None, :], (streams, 1))).cuda()
+    ms_many = _time_ms(torch, lambda: vb(many), max(1, args.steps // 3), warmup=1)
+    kern = _profile(N, lambda: vb(many), 1)
+    audio_s = streams * 600.0
+    v = audio_s / (ms_many / 1e3)
+    alg = 32125.0 * audio_s
+    line = {"metric": METRIC, "value": v, "unit": UNIT, "n_gpus": 1, "steps": max(1, args.steps // 3), "warmup": 1, "ms_per_step": ms_many,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"BASELINE configs[1]: Silero-shaped VAD 512-sample scoring + segmenting, {streams} streams x 600 s (seeded random-init weights)",
+                       "single_stream_1h": {"ms": ms_one, "x_realtime": 3600.0 / (ms_one / 1e3), "windows": 112500}},
+            "roofline": {"bound": "hbm", "achieved": alg / (ms_many / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": alg / (ms_many / 1e3) / 1e9 / peak, "traffic": None, "peak_source": src,
+                         "note": "compute + serial-latency bound by arithmetic (SURVEY 8(d)); HBM fraction reported for completeness",
+                         "kernels_ms_per_step": dict(sorted(kern.items(), key=lambda kv: -kv[1]))}}
+    print(json.dumps(line), flush=True)
+
+
+def run_realtime(args):
+    """BASELINE configs[2]: 1024 concurrent G.711 mu-law 8 kHz streams, 20 ms chunks -> pcm16 -> 16 kHz (+VAD): p50/p99 chunk latency.
+
+    Reference-exact semantics: a 320-sample chunk holds no full 512-sample VAD window, so the reference's VAD returns
+    0.0 without running; variant B feeds 40 ms chunks (640 samples = 1 window) so that the VAD runs.
+    """
+    torch, N = _gpu_setup()
+    from open_speech_b200 import synth
+    from open_speech_b200.batch import RealtimeTick, VadBatch
+
+    S, ticks = args.clips or 1024, 1000
+    data = synth.ulaw_streams(S, 64)                     # [64, S, 160], cycled
+    host_in = torch.from_numpy(data).pin_memory()
+    host_out = torch.empty((S, 320), dtype=torch.int16).pin_memory()
+    dev_in = torch.empty((S, 160), dtype=torch.uint8, device="cuda")
+    dev_out = torch.empty((S, 320), dtype=torch.int16, device="cuda")
+    tick = RealtimeTick(S)
+
+    def one(i):
+        dev_in.copy_(host_in[i % 64], non_blocking=True)
+        tick(dev_in, dev_out)
+        host_out.copy_(dev_out, non_blocking=True)
+        torch.cuda.synchronize()
+
+    for i in range(20):
+        one(i)
+    lat = []
+    for i in range(ticks):
+        t0 = time.perf_counter()
+        one(i)
+        lat.append((time.perf_counter() - t0) * 1e3)
+    lat = np.array(lat)
+    # variant B: 40 ms chunks with the VAD (state carried per stream on the device)
+    vb = VadBatch()
+    dev_in2 = torch.empty((S, 320), dtype=torch.uint8, device="cuda")
+    dev_pcm2 = torch.empty((S, 640), dtype=torch.int16, device="cuda")
+    tick2 = RealtimeTick(S, chunk=320)
+    state = torch.zeros((S, 2, 128), dtype=torch.float32, device="cuda")
+    host_in2 = torch.from_numpy(np.ascontiguousarray(data.reshape(32, 2, S, 160).transpose(0, 2, 1, 3).reshape(32, S, 320))).pin_memory()
+    host_prob = torch.empty((S, 1), dtype=torch.float32).pin_memory()
+
+    def two(i):
+        nonlocal state
+        dev_in2.copy_(host_in2[i % 32], non_blocking=True)
+        tick2(dev_in2, dev_pcm2)
+        probs, state = vb.score(dev_pcm2, state)
+        host_prob.copy_(probs, non_blocking=True)
+        torch.cuda.synchronize()
+
+    for i in range(10):
+        two(i)
+    lat2 = []
+    for i in range(300):
+        t0 = time.perf_counter()
+        two(i)
+        lat2.append((time.perf_counter() - t0) * 1e3)
+    lat2 = np.array(lat2)
+    ms_dev = _time_ms(torch, lambda: tick(dev_in, dev_out), 200)
+    peak, src = load_peaks()
+    alg = 800.0 * S
+    v = S * 0.020 / (np.median(lat) / 1e3)
+    line = {"metric": METRIC, "value": v, "unit": UNIT, "n_gpus": 1, "steps": ticks, "warmup": 20, "ms_per_step": float(np.median(lat)),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/f64", "data": "synthetic",
+            "config": {"workload": f"BASELINE configs[2]: {S} G.711 mu-law 8 kHz streams, 20 ms chunks -> pcm16 16 kHz (host bytes in -> host bytes out per tick)",
+                       "latency_ms": {"p50": float(np.percentile(lat, 50)), "p99": float(np.percentile(lat, 99)), "max": float(lat.max())},
+                       "variant_B_40ms_with_vad_latency_ms": {"p50": float(np.percentile(lat2, 50)), "p99": float(np.percentile(lat2, 99))},
+                       "vad_semantics": "A: reference-exact (320 samples < 512 -> VAD scores nothing, prob 0.0); B: 40 ms chunks, 1 window scored"},
+            "roofline": {"bound": "hbm", "achieved": alg / (ms_dev / 1e3) / 1e9, "peak": peak, "unit": "GB/s", "frac": alg / (ms_dev / 1e3) / 1e9 / peak,
+                         "traffic": None, "peak_source": src, "ms_per_launch": ms_dev,
+                         "note": "a tick is 0.8 MB: launch-latency bound, latency is the headline (SURVEY 8(d))"}}
+    print(json.dumps(line), flush=True)
+
+
+def run_tts(args):
+    """BASELINE configs[4]: 4096 Kokoro-shaped 24 kHz utterances: trim + peak normalise + effects chain + int16, and voice blends."""
+    torch, N = _gpu_setup()
+    from open_speech_b200 import synth
+    from open_speech_b200.batch import TtsPost
+
+    B = args.clips or 4096
+    fx = [{"type": "normalize", "target_lufs": -16}, {"type": "reverb", "room": "medium"}, {"type": "podcast_eq"}, {"type": "robot"}]
+    utts = synth.tts_batch(B, seed=synth.SEED_C5, distinct=32)
+    post = TtsPost(24000, fx)
+    flat, offsets, lens = post.pack(utts)
+    audio_s = float(lens.sum()) / 24000.0
+    d_flat, d_off, d_len = torch.from_numpy(flat).cuda(), torch.from_numpy(offsets).cuda(), torch.from_numpy(lens).cuda()
+    out = torch.empty(flat.size, dtype=torch.int16, device="cuda")
+    mx = int(lens.max())
+    ms = _time_ms(torch, lambda: post(d_flat, d_off, d_len, mx, out), args.steps)
+    kern = _profile(N, lambda: post(d_flat, d_off, d_len, mx, out), 2)
+    # voice blends: B blends of 2-3 packs out of 3
+    packs = torch.from_numpy(np.stack([p.reshape(-1) for p in synth.voice_packs(3)])).cuda()
+    n = packs.shape[1]
+    idx = torch.tensor([[0, 1, -1], [0, 1, -1], [0, 1, 2]] * (B // 3 + 1), dtype=torch.int32)[:B].contiguous().cuda()
+    w = torch.tensor([[2 / 3, 1 / 3, 0], [0.5, 0.5, 0], [0.5, 1 / 3, 1 / 6]] * (B // 3 + 1), dtype=torch.float32)[:B].contiguous().cuda()
+    bout = torch.empty((B, n), dtype=torch.float32, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    ms_blend = _time_ms(torch, lambda: N.call("osb_voice_blend_dev", packs.data_ptr(), n, idx.data_ptr(), w.data_ptr(), 3, B, bout.data_ptr(), st), args.steps)
+    peak, src = load_peaks()
+    alg = 192000.0 * audio_s
+    blend_bytes = float((idx >= 0).sum().item() + B) * n * 4
+    line = {"metric": METRIC, "value": audio_s / (ms / 1e3), "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": 3, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32/f64", "data": "synthetic",
+            "config": {"workload": f"BASELINE configs[4]: {B} Kokoro-shaped 24 kHz utterances ({audio_s:.0f} audio-s): trim + peak normalise + "
+                                   "[normalize, reverb medium, podcast_eq, robot] + int16; plus voice-style blends",
+                       "voice_blend": {"blends_per_s": B / (ms_blend / 1e3), "GBps": blend_bytes / (ms_blend / 1e3) / 1e9, "frac_of_hbm": blend_bytes / (ms_blend / 1e3) / 1e9 / peak}},
+            "roofline": {"bound": "hbm", "achieved": alg / (ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s", "frac": alg / (ms / 1e3) / 1e9 / peak,
+                         "traffic": None, "peak_source": src, "kernels_ms_per_step": dict(sorted(kern.items(), key=lambda kv: -kv[1]))}}
+    print(json.dumps(line), flush=True)
+
+
+EXTRA = {"vad": run_vad, "realtime": run_realtime, "tts": run_tts}
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--workload", default="stt_batch", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="stt_batch", choices=sorted(WORKLOADS) + ["vad", "realtime", "tts"])
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--clips", type=int, default=0, help="clips per GPU (default: the config's 256)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
@@ -318,6 +496,9 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
                "--master-port", "29517", os.path.abspath(__file__)] + sys.argv[1:]
         sys.exit(subprocess.call(cmd))
+    if args.workload in EXTRA:
+        EXTRA[args.workload](args)
+        return
     run_gpu(args)
 
 
