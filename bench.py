@@ -249,11 +249,25 @@ def run_gpu(args) -> None:
     value = world * audio_s_per_step / (ms_step / 1000.0)
 
     # ---- end to end: pinned host clips in, host features out, copies inside the timed region
+    # (osb_stt_frontend_host: pinned host pointers; H2D / kernels / D2H pipelined over 4 clip groups inside the library)
+    del pcm_dev, mel_dev
+    torch.cuda.empty_cache()
+
+    def e2e_step():
+        N.call("osb_stt_frontend_host", pcm_host.data_ptr(), n, clips, n, SR, int(nr), int(norm), n_mels, mel_host.data_ptr())
+
     for _ in range(2):
-        fe.run_host(pcm_host, pcm_dev, mel_dev, mel_host)
-    torch.cuda.synchronize()
+        e2e_step()
     e2e_steps = max(1, min(args.steps, 5))
-    ms_e2e = timed(lambda: fe.run_host(pcm_host, pcm_dev, mel_dev, mel_host), e2e_steps) / e2e_steps
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()  # synchronous: returns when the features are in host memory
+    ms_e2e = (time.perf_counter() - t0) * 1e3 / e2e_steps
+    if world > 1:
+        t = torch.tensor([ms_e2e], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_e2e = float(t.item())
     e2e_value = world * audio_s_per_step / (ms_e2e / 1000.0)
     checksum = float(mel_host[0, :, :16].double().sum())  # the D2H result is really read
 

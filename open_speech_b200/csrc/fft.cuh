@@ -64,9 +64,17 @@ OSB_HD void fft_pow2(cpx (&v)[N]) {
 #pragma unroll
         for (int g = 0; g < N / 2; ++g) {
             const int blk = g / half, j = g - blk * half, b = blk * len;
-            const float wc = c32[j * step], ws = INV ? s32[j * step] : -s32[j * step];
+            const int ti = j * step;  // compile-time after unrolling: trivial twiddles cost no multiplies
             const cpx a = v[b + j], q = v[b + j + half];
-            const cpx t = cpx{q.x * wc - q.y * ws, q.x * ws + q.y * wc};
+            cpx t;
+            if (ti == 0) {
+                t = q;
+            } else if (ti == 8) {  // -i (forward) / +i (inverse)
+                t = INV ? cpx{-q.y, q.x} : cpx{q.y, -q.x};
+            } else {
+                const float wc = c32[ti], ws = INV ? s32[ti] : -s32[ti];
+                t = cpx{q.x * wc - q.y * ws, q.x * ws + q.y * wc};
+            }
             v[b + j] = cadd(a, t);
             v[b + j + half] = csub(a, t);
         }

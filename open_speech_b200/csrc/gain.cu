@@ -23,8 +23,8 @@ __global__ void __launch_bounds__(256) k_pcm16_to_f32(const int16_t* __restrict_
         float f[8];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            f[2 * k] = __fdiv_rn((float)(int16_t)(ws[k] & 0xFFFF), 32768.0f);
-            f[2 * k + 1] = __fdiv_rn((float)(int16_t)(ws[k] >> 16), 32768.0f);
+            f[2 * k] = ((float)(int16_t)(ws[k] & 0xFFFF) * 3.0517578125e-05f);
+            f[2 * k + 1] = ((float)(int16_t)(ws[k] >> 16) * 3.0517578125e-05f);
         }
         st_stream_u4(out + v * 8, make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3])));
         st_stream_u4(out + v * 8 + 4, make_uint4(__float_as_uint(f[4]), __float_as_uint(f[5]), __float_as_uint(f[6]), __float_as_uint(f[7])));
@@ -38,7 +38,7 @@ __global__ void __launch_bounds__(256) k_pcm16_to_f32_mc(const int16_t* __restri
     size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nthr = (size_t)gridDim.x * blockDim.x;
     for (size_t i = tid; i < frames; i += nthr) {
         float acc = 0.0f;
-        for (int c = 0; c < ch; ++c) acc = __fadd_rn(acc, __fdiv_rn((float)in[i * ch + c], 32768.0f));
+        for (int c = 0; c < ch; ++c) acc = __fadd_rn(acc, ((float)in[i * ch + c] * 3.0517578125e-05f));
         out[i] = __fdiv_rn(acc, (float)ch);
     }
 }
@@ -129,14 +129,14 @@ __global__ void __launch_bounds__(256) k_gain_requant_pcm16(const int16_t* __res
         uint32_t ws[4] = {w.x, w.y, w.z, w.w}, o[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            float a = __fdiv_rn((float)(int16_t)(ws[k] & 0xFFFF), 32768.0f), b = __fdiv_rn((float)(int16_t)(ws[k] >> 16), 32768.0f);
+            float a = ((float)(int16_t)(ws[k] & 0xFFFF) * 3.0517578125e-05f), b = ((float)(int16_t)(ws[k] >> 16) * 3.0517578125e-05f);
             int qa = quant_pcm16(apply_gain(a, gain, silent)), qb = quant_pcm16(apply_gain(b, gain, silent));
             o[k] = (uint32_t)(qa & 0xFFFF) | ((uint32_t)qb << 16);
         }
         st_stream_u4(y + v * 8, make_uint4(o[0], o[1], o[2], o[3]));
     }
     for (long long i = nvec * 8 + tid; i < n; i += nthr)
-        y[i] = (int16_t)quant_pcm16(apply_gain(__fdiv_rn((float)x[i], 32768.0f), gain, silent));
+        y[i] = (int16_t)quant_pcm16(apply_gain(((float)x[i] * 3.0517578125e-05f), gain, silent));
 }
 
 template <bool OUT_PCM16>

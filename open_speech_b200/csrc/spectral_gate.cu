@@ -78,7 +78,7 @@ __device__ __forceinline__ float nr_sample(const void* audio, const NrGeom& g, i
     if (p < 0 || p >= g.Lc) return 0.f;
     const long long i = (long long)chunk * kChunk - kCtx + p;
     if (i < 0 || i >= g.n) return 0.f;
-    if (g.fmt == OSB_FMT_PCM16) return __fdiv_rn((float)reinterpret_cast<const int16_t*>(audio)[(long long)clip * g.stride + i], 32768.0f);
+    if (g.fmt == OSB_FMT_PCM16) return ((float)reinterpret_cast<const int16_t*>(audio)[(long long)clip * g.stride + i] * 3.0517578125e-05f);
     return reinterpret_cast<const float*>(audio)[(long long)clip * g.stride + i];
 }
 
@@ -87,7 +87,7 @@ __device__ __forceinline__ float nr_sample(const void* audio, const NrGeom& g, i
 constexpr int kStftFrames = 16, kStftXs = NH * (kStftFrames - 1) + NF;  // 4864
 
 __global__ void __launch_bounds__(256, 2) k_nr_stft(const void* __restrict__ audio, NrGeom g, const float* __restrict__ tabs,
-                                                    float2* __restrict__ S) {
+                                                    float2* __restrict__ S, float* __restrict__ A) {
     extern __shared__ __align__(16) float sm[];
     float* xs = sm;                 // [4864]
     float* win = xs + kStftXs;      // [1024]
@@ -150,88 +150,123 @@ __global__ void __launch_bounds__(256, 2) k_nr_stft(const void* __restrict__ aud
         const int a0 = (f & 31) * kYs + (f >> 5), a1 = (m & 31) * kYs + (m >> 5);
         const float zr = yr[a0], zi = yi[a0], wr = yr[a1], wi = yi[a1];
         // X_a = (Z[f] + conj Z[N-f])/2 ; X_b = (Z[f] - conj Z[N-f])/(2i)
-        S[(row0 + ta) * NB + f] = make_float2((zr + wr) * sc, (zi - wi) * sc);
-        if (ta + 1 < g.F) S[(row0 + ta + 1) * NB + f] = make_float2((zi + wi) * sc, (wr - zr) * sc);
+        const float ar = (zr + wr) * sc, ai = (zi - wi) * sc, br = (zi + wi) * sc, bi = (wr - zr) * sc;
+        S[(row0 + ta) * NB + f] = make_float2(ar, ai);
+        A[(row0 + ta) * NB + f] = sqrtf(ar * ar + ai * ai);
+        if (ta + 1 < g.F) {
+            S[(row0 + ta + 1) * NB + f] = make_float2(br, bi);
+            A[(row0 + ta + 1) * NB + f] = sqrtf(br * br + bi * bi);
+        }
     }
 }
 
 // ---------------------------------------------------------------- time smoothing (filtfilt) + sigmoid mask
-__global__ void __launch_bounds__(128) k_nr_iir_fwd(const float2* __restrict__ S, float* __restrict__ Afwd, int F, long long n_rows,
-                                                    double b) {
+// one thread per (chunk, bin), sequential over frames, coalesced across bins; f64 state.
+__global__ void __launch_bounds__(128) k_nr_iir_fwd(const float* __restrict__ A, float* __restrict__ Afwd, int F, long long n_rows, double b) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= n_rows * NB) return;
     const long long cc = idx / NB;
     const int f = (int)(idx - cc * NB);
-    const float2* s = S + cc * F * NB + f;
+    const float* s = A + cc * F * NB + f;
     float* o = Afwd + cc * F * NB + f;
     const double a1 = 1.0 - b;
-    double y = 0.0;
-#pragma unroll 8
+    double y = (double)s[0];  // lfilter_zi start: y[-1] = x[0]
+#pragma unroll 16
     for (int t = 0; t < F; ++t) {
-        const float2 v = s[(long long)t * NB];
-        const double a = (double)sqrtf(v.x * v.x + v.y * v.y);
-        y = (t == 0) ? a : fma(a1, y, b * a);  // lfilter_zi start: y[-1] = x[0]
+        y = fma(a1, y, b * (double)s[(long long)t * NB]);
         o[(long long)t * NB] = (float)y;
     }
 }
 
-__global__ void __launch_bounds__(128) k_nr_iir_bwd_mask(const float2* __restrict__ S, const float* __restrict__ Afwd,
-                                                         float* __restrict__ M, int F, long long n_rows, double b) {
+// M may alias A (in place): thread (chunk, bin) reads A[t][f] before it writes M[t][f]; no __restrict__ on those two
+__global__ void __launch_bounds__(128) k_nr_iir_bwd_mask(const float* A, const float* __restrict__ Afwd, float* M, int F, long long n_rows,
+                                                         double b) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= n_rows * NB) return;
     const long long cc = idx / NB;
     const int f = (int)(idx - cc * NB);
-    const float2* s = S + cc * F * NB + f;
+    const float* s = A + cc * F * NB + f;
     const float* af = Afwd + cc * F * NB + f;
     float* m = M + cc * F * NB + f;
     const double a1 = 1.0 - b;
-    double y = 0.0;
-#pragma unroll 8
+    double y = (double)af[(long long)(F - 1) * NB];
+#pragma unroll 16
     for (int t = F - 1; t >= 0; --t) {
-        const double x = (double)af[(long long)t * NB];
-        y = (t == F - 1) ? x : fma(a1, y, b * x);
-        const float2 v = s[(long long)t * NB];
-        const float a = sqrtf(v.x * v.x + v.y * v.y);
+        y = fma(a1, y, b * (double)af[(long long)t * NB]);
+        const float a = s[(long long)t * NB];
         const float as = (float)y;
         const float rel = (a - as) / as;  // 0/0 -> NaN on all-zero input, like the reference
-        m[(long long)t * NB] = 1.0f / (1.0f + expf(-(rel - 2.0f) * 10.0f));
+        m[(long long)t * NB] = 1.0f / (1.0f + __expf(-(rel - 2.0f) * 10.0f));
     }
 }
 
 // ---------------------------------------------------------------- 2-D mask smoothing (fftconvolve 'same')
-// tile: 32 frames x 64 bins; grid (ceil(513/64), ceil(F/32), n_rows)
+// CTA = 32 frames x all 513 bins.  Time taps first, straight from global memory with a sliding register
+// window (coalesced over bins), result into shared memory; then the 2*nf+1 frequency taps with 4 outputs per
+// thread (for nf = 16: 9 LDS.128 feed 132 FMA).  grid (ceil(F/32), n_rows)
+constexpr int kSmT = 32, kSmPad = 32, kSmW = 584;  // row: 32 zeros | 513 bins | zeros up to 584 floats (16 B aligned)
+constexpr int kNtMax = 9, kNfMax = 32;
 struct NrSmooth {
-    float vf[64];  // up to 2*nf+1 <= 63 taps
-    float vt[16];  // up to 2*nt+1 <= 15 taps
-    int nf, nt;
+    float vf[2 * kNfMax + 1];  // centred: tap k multiplies M[f - NFT + k]; zero-padded when nf < NFT
+    float vt[2 * kNtMax + 1];
+    int nt;
 };
 
-__global__ void __launch_bounds__(256) k_nr_smooth(const float* __restrict__ M, float* __restrict__ Msm, int F, NrSmooth p) {
-    __shared__ float tile[46][64 + 64];  // (32 + 2*nt<=14) rows x (64 + 2*nf<=62) cols
-    __shared__ float rowc[46][64];
-    const int f0 = blockIdx.x * 64, t0 = blockIdx.y * 32;
-    const long long base = (long long)blockIdx.z * F * NB;
-    const int rows = 32 + 2 * p.nt, cols = 64 + 2 * p.nf;
-    for (int i = threadIdx.x; i < rows * cols; i += 256) {
-        const int r = i / cols, c = i - r * cols;
-        const int t = t0 + r - p.nt, f = f0 + c - p.nf;
-        tile[r][c] = (t >= 0 && t < F && f >= 0 && f < NB) ? M[base + (long long)t * NB + f] : 0.f;
+template <int NFT>
+__global__ void __launch_bounds__(256, 2) k_nr_smooth(const float* __restrict__ M, float* __restrict__ Msm, int F, NrSmooth p) {
+    extern __shared__ __align__(16) float tile[];  // [kSmT][kSmW]
+    const int t0 = blockIdx.x * kSmT, tid = threadIdx.x;
+    const long long base = (long long)blockIdx.y * F * NB;
+    for (int i = tid; i < kSmT * kSmW; i += 256) tile[i] = 0.f;
+    __syncthreads();
+    const int ntap = 2 * p.nt + 1;
+    for (int f = tid; f < NB; f += 256) {
+        float w[2 * kNtMax + 1];
+#pragma unroll
+        for (int k = 0; k < 2 * kNtMax + 1; ++k) {
+            const int t = t0 - p.nt + k;
+            w[k] = (k < ntap - 1 && t >= 0 && t < F) ? M[base + (long long)t * NB + f] : 0.f;
+        }
+        for (int r = 0; r < kSmT; ++r) {
+            const int t = t0 + r + p.nt;  // newest frame entering the window
+            const float nv = (t >= 0 && t < F) ? M[base + (long long)t * NB + f] : 0.f;
+            float acc = 0.f;
+#pragma unroll
+            for (int k = 0; k < 2 * kNtMax + 1; ++k) {
+                const float x = (k == ntap - 1) ? nv : w[k];
+                if (k < ntap) acc = fmaf(p.vt[k], x, acc);
+            }
+            tile[r * kSmW + kSmPad + f] = acc;
+#pragma unroll
+            for (int k = 0; k < 2 * kNtMax; ++k) w[k] = (k == ntap - 2) ? nv : w[k + 1];
+        }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < rows * 64; i += 256) {
-        const int r = i >> 6, c = i & 63;
-        float acc = 0.f;
-        for (int k = 0; k <= 2 * p.nf; ++k) acc = fmaf(p.vf[k], tile[r][c + k], acc);
-        rowc[r][c] = acc;
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < 32 * 64; i += 256) {
-        const int r = i >> 6, c = i & 63;
-        const int t = t0 + r, f = f0 + c;
-        if (t >= F || f >= NB) continue;
-        float acc = 0.f;
-        for (int k = 0; k <= 2 * p.nt; ++k) acc = fmaf(p.vt[k], rowc[r + k][c], acc);
-        Msm[base + (long long)t * NB + f] = acc;
+    constexpr int NFA = (NFT + 3) / 4 * 4;      // aligned left reach
+    constexpr int NV = (4 + 2 * NFA) / 4;       // float4 loads per thread
+    const int groups = (NB + 3) / 4;            // 129 groups of 4 bins
+    for (int task = tid; task < kSmT * groups; task += 256) {
+        const int r = task / groups, gq = task - r * groups;
+        if (t0 + r >= F) continue;
+        const float* row = tile + r * kSmW + kSmPad + 4 * gq - NFA;
+        float x[4 * NV];
+#pragma unroll
+        for (int q = 0; q < NV; ++q) {
+            const float4 v4 = *reinterpret_cast<const float4*>(row + 4 * q);
+            x[4 * q] = v4.x; x[4 * q + 1] = v4.y; x[4 * q + 2] = v4.z; x[4 * q + 3] = v4.w;
+        }
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+        for (int k = 0; k < 2 * NFT + 1; ++k) {
+            const float c = p.vf[k];
+            a0 = fmaf(c, x[NFA - NFT + k], a0);
+            a1 = fmaf(c, x[NFA - NFT + k + 1], a1);
+            a2 = fmaf(c, x[NFA - NFT + k + 2], a2);
+            a3 = fmaf(c, x[NFA - NFT + k + 3], a3);
+        }
+        float* o = Msm + base + (long long)(t0 + r) * NB + 4 * gq;
+        o[0] = a0;
+        if (4 * gq + 1 < NB) { o[1] = a1; o[2] = a2; o[3] = a3; }
     }
 }
 
@@ -335,6 +370,7 @@ __global__ void __launch_bounds__(256, 2) k_nr_istft(const float2* __restrict__ 
 }
 
 constexpr int kStftSmem = (kStftXs + 3 * NF + 8 * 2 * kYPlane) * (int)sizeof(float);
+constexpr int kSmoothSmem = kSmT * kSmW * (int)sizeof(float);
 constexpr int kIstftSmem = (3 * NF + NH + 8 * 2 * kYPlane + kOlaOut) * (int)sizeof(float);
 
 static std::vector<double> tri_filter(int n) {
@@ -355,6 +391,8 @@ int launch_spectral_gate(const void* d_audio, int fmt, long long n, long long ba
     std::call_once(once, [&] {
         e1 = cudaFuncSetAttribute(k_nr_stft, cudaFuncAttributeMaxDynamicSharedMemorySize, kStftSmem);
         e2 = cudaFuncSetAttribute(k_nr_istft, cudaFuncAttributeMaxDynamicSharedMemorySize, kIstftSmem);
+        if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(k_nr_smooth<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmoothSmem);
+        if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(k_nr_smooth<kNfMax>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmoothSmem);
     });
     OSB_CUDA(e1);
     OSB_CUDA(e2);
@@ -363,18 +401,19 @@ int launch_spectral_gate(const void* d_audio, int fmt, long long n, long long ba
     const double b = (std::sqrt(1.0 + 4.0 * t_frames * t_frames) - 1.0) / (2.0 * t_frames * t_frames);
     const int nf = (int)(500.0 / (sr / (NF / 2.0)));
     const int nt = (int)(50.0 / (((double)NH / sr) * 1000.0));
-    if (nf < 1 || nt < 1 || nf > 31 || nt > 7) {
-        set_error("unsupported: sample rate %d gives mask smoothing %dx%d outside the supported 1..31 x 1..7", sr, nf, nt);
+    if (nf < 1 || nt < 1 || nf > kNfMax || nt > kNtMax) {
+        set_error("unsupported: sample rate %d gives mask smoothing %dx%d outside the supported 1..%d x 1..%d", sr, nf, nt, kNfMax, kNtMax);
         return OSB_ERR_UNSUPPORTED;
     }
+    const int nft = (nf == 16) ? 16 : kNfMax;  // compile-time tap reach of the kernel instance
     NrSmooth sp{};
-    sp.nf = nf; sp.nt = nt;
+    sp.nt = nt;
     {
         std::vector<double> vf = tri_filter(nf), vt = tri_filter(nt);
         double sf = 0, stt = 0;
         for (double x : vf) sf += x;
         for (double x : vt) stt += x;
-        for (size_t i = 0; i < vf.size(); ++i) sp.vf[i] = (float)(vf[i] / sf);
+        for (size_t i = 0; i < vf.size(); ++i) sp.vf[(nft - nf) + i] = (float)(vf[i] / sf);
         for (size_t i = 0; i < vt.size(); ++i) sp.vt[i] = (float)(vt[i] / stt);
     }
     NrGeom g;
@@ -386,17 +425,18 @@ int launch_spectral_gate(const void* d_audio, int fmt, long long n, long long ba
     const int j_first = (int)(kCtx / NH);
     const int j_last = (int)((kCtx + keep_max - 1) / NH);
     const int tiles = (j_last - j_first + 1 + kOlaBlocks - 1) / kOlaBlocks;
-    // scratch per clip: S (8 B) + Afwd + M + Msm (4 B each) per (frame, bin); process the batch in groups of <= ~24 GB
+    // scratch per clip: S (8 B) + A/M (4 B) + Afwd/Msm (4 B) per (frame, bin); process the batch in groups of <= ~24 GB
     const long long per_clip = (long long)g.n_chunks * g.F * NB;
-    long long group = (24ll << 30) / (per_clip * 20);
+    long long group = (24ll << 30) / (per_clip * 16);
     if (group < 1) group = 1;
     if (group > batch) group = batch;
     Scratch scr(st);
     float2* S;
-    float *Afwd, *M, *Msm;
+    float *A, *Afwd, *M, *Msm;
     OSB_CUDA(scr.alloc(&S, (size_t)(group * per_clip)));
+    OSB_CUDA(scr.alloc(&A, (size_t)(group * per_clip)));
     OSB_CUDA(scr.alloc(&Afwd, (size_t)(group * per_clip)));
-    OSB_CUDA(scr.alloc(&M, (size_t)(group * per_clip)));
+    M = A;       // the mask overwrites |S| in place (same thread reads A[t][f] then writes M[t][f])
     Msm = Afwd;  // Afwd is dead once the mask exists
     for (long long c0 = 0; c0 < batch; c0 += group) {
         const int gb = (int)((batch - c0) < group ? (batch - c0) : group);
@@ -404,14 +444,15 @@ int launch_spectral_gate(const void* d_audio, int fmt, long long n, long long ba
         const char* in = reinterpret_cast<const char*>(d_audio) + c0 * stride * (fmt == OSB_FMT_PCM16 ? 2 : 4);
         float* outp = d_out + c0 * stride;
         const long long n_rows = (long long)gb * g.n_chunks;
-        OSB_LAUNCH(k_nr_stft, dim3((g.F + kStftFrames - 1) / kStftFrames, g.n_chunks, gb), 256, kStftSmem, st, (const void*)in, g, tabs, S);
+        OSB_LAUNCH(k_nr_stft, dim3((g.F + kStftFrames - 1) / kStftFrames, g.n_chunks, gb), 256, kStftSmem, st, (const void*)in, g, tabs, S, A);
         OSB_CHECK_LAUNCH();
         const unsigned gi = (unsigned)((n_rows * NB + 127) / 128);
-        OSB_LAUNCH(k_nr_iir_fwd, gi, 128, 0, st, S, Afwd, g.F, n_rows, b);
+        OSB_LAUNCH(k_nr_iir_fwd, gi, 128, 0, st, A, Afwd, g.F, n_rows, b);
         OSB_CHECK_LAUNCH();
-        OSB_LAUNCH(k_nr_iir_bwd_mask, gi, 128, 0, st, S, Afwd, M, g.F, n_rows, b);
+        OSB_LAUNCH(k_nr_iir_bwd_mask, gi, 128, 0, st, A, Afwd, M, g.F, n_rows, b);
         OSB_CHECK_LAUNCH();
-        OSB_LAUNCH(k_nr_smooth, dim3((NB + 63) / 64, (g.F + 31) / 32, (unsigned)n_rows), 256, 0, st, M, Msm, g.F, sp);
+        if (nft == 16) OSB_LAUNCH(k_nr_smooth<16>, dim3((g.F + kSmT - 1) / kSmT, (unsigned)n_rows), 256, kSmoothSmem, st, M, Msm, g.F, sp);
+        else OSB_LAUNCH(k_nr_smooth<kNfMax>, dim3((g.F + kSmT - 1) / kSmT, (unsigned)n_rows), 256, kSmoothSmem, st, M, Msm, g.F, sp);
         OSB_CHECK_LAUNCH();
         OSB_LAUNCH(k_nr_istft, dim3(tiles, g.n_chunks, gb), 256, kIstftSmem, st, S, Msm, g, tabs, j_first, outp);
         OSB_CHECK_LAUNCH();

@@ -46,19 +46,57 @@ int osb_stt_frontend_dev(const int16_t* d_pcm, int64_t n, int64_t batch, int64_t
     return stt_frontend(d_pcm, n, batch, stride, sample_rate, noise_reduce, normalize, n_mels, d_mel, (cudaStream_t)stream);
 }
 
+// Host-buffer entry: the batch is cut into groups; H2D of group g+1, the kernels of group g and D2H of group g-1
+// run concurrently on three streams (two copy engines + SMs), so the step costs ~max(copy, compute), not their sum.
 int osb_stt_frontend_host(const int16_t* pcm, int64_t n, int64_t batch, int64_t stride, int sample_rate, int noise_reduce,
                           int normalize, int n_mels, float* mel) {
     HostWs& ws = host_ws();
     int rc = ws.prepare();
     if (rc) return rc;
     OSB_REQUIRE(n > 0 && batch > 0 && stride >= n && pcm && mel, "bad arguments");
-    const size_t ib = (size_t)((batch - 1) * stride + n) * 2;
-    const size_t ob = (size_t)batch * n_mels * osb_logmel_frames(n) * 4;
+    OSB_REQUIRE(n_mels == 80 || n_mels == 128, "n_mels must be 80 or 128");
+    const size_t per_mel = (size_t)n_mels * osb_logmel_frames(n);
     void *di, *dout;
-    if ((rc = ws.dev_buf(0, (size_t)batch * stride * 2, &di)) || (rc = ws.dev_buf(1, ob, &dout))) return rc;
-    if ((rc = ws.h2d(di, pcm, ib))) return rc;
-    if ((rc = osb_stt_frontend_dev((const int16_t*)di, n, batch, stride, sample_rate, noise_reduce, normalize, n_mels, (float*)dout, ws.stream))) return rc;
-    return ws.d2h(mel, dout, ob);
+    if ((rc = ws.dev_buf(0, (size_t)batch * stride * 2, &di)) || (rc = ws.dev_buf(1, (size_t)batch * per_mel * 4, &dout))) return rc;
+    static thread_local cudaStream_t s_in = nullptr, s_out = nullptr;
+    static thread_local int s_dev = -1;
+    if (s_dev != ws.device) {
+        if (s_in) { cudaStreamDestroy(s_in); cudaStreamDestroy(s_out); }
+        OSB_CUDA(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
+        OSB_CUDA(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
+        s_dev = ws.device;
+    }
+    const int groups = batch >= 16 ? 4 : 1;
+    cudaEvent_t ev_in[4], ev_done[4];
+    for (int g = 0; g < groups; ++g) {
+        OSB_CUDA(cudaEventCreateWithFlags(&ev_in[g], cudaEventDisableTiming));
+        OSB_CUDA(cudaEventCreateWithFlags(&ev_done[g], cudaEventDisableTiming));
+    }
+    rc = OSB_OK;
+    for (int g = 0; g < groups && rc == OSB_OK; ++g) {
+        const int64_t c0 = batch * g / groups, c1 = batch * (g + 1) / groups, nb = c1 - c0;
+        const int16_t* hin = pcm + c0 * stride;
+        int16_t* din = (int16_t*)di + c0 * stride;
+        float* dmel = (float*)dout + c0 * per_mel;
+        const size_t ib = (size_t)((nb - 1) * stride + n) * 2;
+        cudaError_t e = cudaMemcpyAsync(din, hin, ib, cudaMemcpyHostToDevice, s_in);
+        if (e == cudaSuccess) e = cudaEventRecord(ev_in[g], s_in);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(ws.stream, ev_in[g], 0);
+        if (e != cudaSuccess) { rc = cuda_fail(e, "h2d group", __FILE__, __LINE__); break; }
+        rc = osb_stt_frontend_dev(din, n, nb, stride, sample_rate, noise_reduce, normalize, n_mels, dmel, ws.stream);
+        if (rc) break;
+        e = cudaEventRecord(ev_done[g], ws.stream);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(s_out, ev_done[g], 0);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(mel + c0 * per_mel, dmel, (size_t)nb * per_mel * 4, cudaMemcpyDeviceToHost, s_out);
+        if (e != cudaSuccess) { rc = cuda_fail(e, "d2h group", __FILE__, __LINE__); break; }
+    }
+    cudaError_t e1 = cudaStreamSynchronize(s_in), e2 = cudaStreamSynchronize(ws.stream), e3 = cudaStreamSynchronize(s_out);
+    for (int g = 0; g < groups; ++g) { cudaEventDestroy(ev_in[g]); cudaEventDestroy(ev_done[g]); }
+    if (rc) return rc;
+    OSB_CUDA(e1);
+    OSB_CUDA(e2);
+    OSB_CUDA(e3);
+    return OSB_OK;
 }
 
 int osb_preprocess_stt_host(const int16_t* in, int64_t n, int channels, int sample_rate, int noise_reduce, int normalize,

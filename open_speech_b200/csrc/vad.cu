@@ -87,7 +87,7 @@ __device__ __forceinline__ void load_a8(const GemmDesc& d, int r, int k0, float 
         for (int i = 0; i < 8; ++i) {
             int s = 128 * f + k0 + i;
             s = s < kWin ? s : (2 * kWin - 2 - s);  // right reflect pad (no edge repeat)
-            if (AMODE == 1) v[i] = __fdiv_rn((float)reinterpret_cast<const int16_t*>(d.A)[base + s], 32768.0f);
+            if (AMODE == 1) v[i] = ((float)reinterpret_cast<const int16_t*>(d.A)[base + s] * 3.0517578125e-05f);
             else v[i] = reinterpret_cast<const float*>(d.A)[base + s];
         }
     }
