@@ -97,7 +97,35 @@ __global__ void __launch_bounds__(256, 2) k_nr_stft(const void* __restrict__ aud
     const int tid = threadIdx.x, t0 = blockIdx.x * kStftFrames, chunk = blockIdx.y, clip = blockIdx.z;
     for (int i = tid; i < 3 * NF; i += 256) win[i] = tabs[i];
     const long long p0 = (long long)NH * t0 - NF / 2;
-    for (int i = tid; i < kStftXs; i += 256) xs[i] = nr_sample(audio, g, clip, chunk, p0 + i);
+    {
+        const long long i0 = (long long)chunk * kChunk - kCtx + p0;  // clip index of the first staged sample (multiple of 8)
+        const int16_t* src = reinterpret_cast<const int16_t*>(audio) + (long long)clip * g.stride + i0;
+        const bool interior = g.fmt == OSB_FMT_PCM16 && p0 >= 0 && p0 + kStftXs <= g.Lc && i0 >= 0 && i0 + kStftXs <= g.n &&
+                              (((uintptr_t)src) & 15) == 0;
+        if (interior) {
+            uint4 v[3];
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+                if (tid + 256 * r < kStftXs / 8) v[r] = ld_stream_u4(src + 8 * (tid + 256 * r));
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                const int i8 = tid + 256 * r;
+                if (i8 < kStftXs / 8) {
+                    const uint32_t w[4] = {v[r].x, v[r].y, v[r].z, v[r].w};
+                    float o[8];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        o[2 * k] = (float)(int16_t)(w[k] & 0xFFFF) * 3.0517578125e-05f;
+                        o[2 * k + 1] = (float)(int16_t)(w[k] >> 16) * 3.0517578125e-05f;
+                    }
+                    *reinterpret_cast<float4*>(xs + 8 * i8) = make_float4(o[0], o[1], o[2], o[3]);
+                    *reinterpret_cast<float4*>(xs + 8 * i8 + 4) = make_float4(o[4], o[5], o[6], o[7]);
+                }
+            }
+        } else {
+            for (int i = tid; i < kStftXs; i += 256) xs[i] = nr_sample(audio, g, clip, chunk, p0 + i);
+        }
+    }
     __syncthreads();
     {   // step 1: 8 frame pairs x 32 residues.  n = 32*n1 + n2
         const int q = tid >> 5, n2 = tid & 31;
@@ -140,22 +168,28 @@ __global__ void __launch_bounds__(256, 2) k_nr_stft(const void* __restrict__ aud
     // split the packed transform into the two one-sided spectra, apply the spectrum scaling 1/sum(win) = 1/512
     const float sc = 0.5f / 512.0f;
     const long long row0 = ((long long)clip * g.n_chunks + chunk) * g.F;
-    for (int task = tid; task < 8 * NB; task += 256) {
-        const int q = task / NB, f = task - q * NB;
+    {
+        const int q = tid >> 5, lane = tid & 31;  // warp q owns frame pair q
         const int ta = t0 + 2 * q;
-        if (ta >= g.F) continue;
-        const float* yr = Y + q * 2 * kYPlane;
-        const float* yi = yr + kYPlane;
-        const int m = (NF - f) & (NF - 1);
-        const int a0 = (f & 31) * kYs + (f >> 5), a1 = (m & 31) * kYs + (m >> 5);
-        const float zr = yr[a0], zi = yi[a0], wr = yr[a1], wi = yi[a1];
-        // X_a = (Z[f] + conj Z[N-f])/2 ; X_b = (Z[f] - conj Z[N-f])/(2i)
-        const float ar = (zr + wr) * sc, ai = (zi - wi) * sc, br = (zi + wi) * sc, bi = (wr - zr) * sc;
-        S[(row0 + ta) * NB + f] = make_float2(ar, ai);
-        A[(row0 + ta) * NB + f] = sqrtf(ar * ar + ai * ai);
-        if (ta + 1 < g.F) {
-            S[(row0 + ta + 1) * NB + f] = make_float2(br, bi);
-            A[(row0 + ta + 1) * NB + f] = sqrtf(br * br + bi * bi);
+        if (ta < g.F) {
+            const float* yr = Y + q * 2 * kYPlane;
+            const float* yi = yr + kYPlane;
+            const bool has_b = ta + 1 < g.F;
+            float2* Sa = S + (row0 + ta) * NB;
+            float* Aa = A + (row0 + ta) * NB;
+            for (int f = lane; f < NB; f += 32) {
+                const int m = (NF - f) & (NF - 1);
+                const int a0 = (f & 31) * kYs + (f >> 5), a1 = (m & 31) * kYs + (m >> 5);
+                const float zr = yr[a0], zi = yi[a0], wr = yr[a1], wi = yi[a1];
+                // X_a = (Z[f] + conj Z[N-f])/2 ; X_b = (Z[f] - conj Z[N-f])/(2i)
+                const float ar = (zr + wr) * sc, ai = (zi - wi) * sc, br = (zi + wi) * sc, bi = (wr - zr) * sc;
+                Sa[f] = make_float2(ar, ai);
+                Aa[f] = sqrtf(ar * ar + ai * ai);
+                if (has_b) {
+                    Sa[NB + f] = make_float2(br, bi);
+                    Aa[NB + f] = sqrtf(br * br + bi * bi);
+                }
+            }
         }
     }
 }
@@ -212,33 +246,31 @@ struct NrSmooth {
     int nt;
 };
 
-template <int NFT>
+template <int NFT, int NTT>
 __global__ void __launch_bounds__(256, 2) k_nr_smooth(const float* __restrict__ M, float* __restrict__ Msm, int F, NrSmooth p) {
     extern __shared__ __align__(16) float tile[];  // [kSmT][kSmW]
     const int t0 = blockIdx.x * kSmT, tid = threadIdx.x;
     const long long base = (long long)blockIdx.y * F * NB;
     for (int i = tid; i < kSmT * kSmW; i += 256) tile[i] = 0.f;
     __syncthreads();
-    const int ntap = 2 * p.nt + 1;
+    constexpr int ntap = 2 * NTT + 1;  // vt is centred and zero-padded to this reach
     for (int f = tid; f < NB; f += 256) {
-        float w[2 * kNtMax + 1];
+        float w[ntap];
 #pragma unroll
-        for (int k = 0; k < 2 * kNtMax + 1; ++k) {
-            const int t = t0 - p.nt + k;
-            w[k] = (k < ntap - 1 && t >= 0 && t < F) ? M[base + (long long)t * NB + f] : 0.f;
+        for (int k = 0; k < ntap - 1; ++k) {
+            const int t = t0 - NTT + k;
+            w[k] = (t >= 0 && t < F) ? M[base + (long long)t * NB + f] : 0.f;
         }
+#pragma unroll 4
         for (int r = 0; r < kSmT; ++r) {
-            const int t = t0 + r + p.nt;  // newest frame entering the window
-            const float nv = (t >= 0 && t < F) ? M[base + (long long)t * NB + f] : 0.f;
+            const int t = t0 + r + NTT;  // newest frame entering the window
+            w[ntap - 1] = (t < F) ? M[base + (long long)t * NB + f] : 0.f;
             float acc = 0.f;
 #pragma unroll
-            for (int k = 0; k < 2 * kNtMax + 1; ++k) {
-                const float x = (k == ntap - 1) ? nv : w[k];
-                if (k < ntap) acc = fmaf(p.vt[k], x, acc);
-            }
+            for (int k = 0; k < ntap; ++k) acc = fmaf(p.vt[k], w[k], acc);
             tile[r * kSmW + kSmPad + f] = acc;
 #pragma unroll
-            for (int k = 0; k < 2 * kNtMax; ++k) w[k] = (k == ntap - 2) ? nv : w[k + 1];
+            for (int k = 0; k < ntap - 1; ++k) w[k] = w[k + 1];
         }
     }
     __syncthreads();
@@ -343,19 +375,17 @@ __global__ void __launch_bounds__(256, 2) k_nr_istft(const float2* __restrict__ 
             }
         }
         __syncthreads();
-        // overlap-add the 16 frames of this pass: output sample u (hop block j0 + u/256) <- frames j-1 .. j+2
-        for (int u = tid; u < kOlaOut; u += 256) {
-            const int j = j0 + (u >> 8), r = u & 255;
-            float s = 0.f;
+        // overlap-add the 16 frames of this pass.  Sample n of frame t lands on u = 256 (t - j0) + n - 512, and with
+        // n = tid + 256 j every thread only ever touches u == tid (mod 256): no conflicts, no barrier between frames.
+#pragma unroll 4
+        for (int lt = 0; lt < 16; ++lt) {
+            const float* pl = Y + (lt >> 1) * 2 * kYPlane + (lt & 1) * kYPlane;
+            const int ub = 256 * (tp0 + lt - j0 - 2) + tid;
 #pragma unroll
-            for (int d = -1; d <= 2; ++d) {
-                const int t = j + d, lt = t - tp0;
-                if (lt < 0 || lt >= 16) continue;
-                const int n = r + 512 - 256 * d;  // position inside frame t: e - 256 t, e = 256 j + r + 512
-                const float* pl = Y + (lt >> 1) * 2 * kYPlane + (lt & 1) * kYPlane;
-                s = fmaf(pl[(n & 31) * kYs + (n >> 5)], win[n], s);
+            for (int j = 0; j < 4; ++j) {
+                const int u = ub + 256 * j, n = tid + 256 * j;
+                if (u >= 0 && u < kOlaOut) acc[u] = fmaf(pl[(n & 31) * kYs + (n >> 5)], win[n], acc[u]);
             }
-            acc[u] += s;
         }
         __syncthreads();
     }
@@ -391,8 +421,8 @@ int launch_spectral_gate(const void* d_audio, int fmt, long long n, long long ba
     std::call_once(once, [&] {
         e1 = cudaFuncSetAttribute(k_nr_stft, cudaFuncAttributeMaxDynamicSharedMemorySize, kStftSmem);
         e2 = cudaFuncSetAttribute(k_nr_istft, cudaFuncAttributeMaxDynamicSharedMemorySize, kIstftSmem);
-        if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(k_nr_smooth<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmoothSmem);
-        if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(k_nr_smooth<kNfMax>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmoothSmem);
+        if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(k_nr_smooth<16, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmoothSmem);
+        if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(k_nr_smooth<kNfMax, kNtMax>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmoothSmem);
     });
     OSB_CUDA(e1);
     OSB_CUDA(e2);
@@ -405,7 +435,7 @@ int launch_spectral_gate(const void* d_audio, int fmt, long long n, long long ba
         set_error("unsupported: sample rate %d gives mask smoothing %dx%d outside the supported 1..%d x 1..%d", sr, nf, nt, kNfMax, kNtMax);
         return OSB_ERR_UNSUPPORTED;
     }
-    const int nft = (nf == 16) ? 16 : kNfMax;  // compile-time tap reach of the kernel instance
+    const int nft = (nf == 16 && nt == 3) ? 16 : kNfMax;  // compile-time tap reach of the kernel instance
     NrSmooth sp{};
     sp.nt = nt;
     {
@@ -414,7 +444,8 @@ int launch_spectral_gate(const void* d_audio, int fmt, long long n, long long ba
         for (double x : vf) sf += x;
         for (double x : vt) stt += x;
         for (size_t i = 0; i < vf.size(); ++i) sp.vf[(nft - nf) + i] = (float)(vf[i] / sf);
-        for (size_t i = 0; i < vt.size(); ++i) sp.vt[i] = (float)(vt[i] / stt);
+        const int ntt = (nt == 3) ? 3 : kNtMax;
+        for (size_t i = 0; i < vt.size(); ++i) sp.vt[(ntt - nt) + i] = (float)(vt[i] / stt);
     }
     NrGeom g;
     g.n = n; g.stride = stride; g.fmt = fmt;
@@ -451,8 +482,8 @@ int launch_spectral_gate(const void* d_audio, int fmt, long long n, long long ba
         OSB_CHECK_LAUNCH();
         OSB_LAUNCH(k_nr_iir_bwd_mask, gi, 128, 0, st, A, Afwd, M, g.F, n_rows, b);
         OSB_CHECK_LAUNCH();
-        if (nft == 16) OSB_LAUNCH(k_nr_smooth<16>, dim3((g.F + kSmT - 1) / kSmT, (unsigned)n_rows), 256, kSmoothSmem, st, M, Msm, g.F, sp);
-        else OSB_LAUNCH(k_nr_smooth<kNfMax>, dim3((g.F + kSmT - 1) / kSmT, (unsigned)n_rows), 256, kSmoothSmem, st, M, Msm, g.F, sp);
+        if (nft == 16 && nt == 3) OSB_LAUNCH((k_nr_smooth<16, 3>), dim3((g.F + kSmT - 1) / kSmT, (unsigned)n_rows), 256, kSmoothSmem, st, M, Msm, g.F, sp);
+        else OSB_LAUNCH((k_nr_smooth<kNfMax, kNtMax>), dim3((g.F + kSmT - 1) / kSmT, (unsigned)n_rows), 256, kSmoothSmem, st, M, Msm, g.F, sp);
         OSB_CHECK_LAUNCH();
         OSB_LAUNCH(k_nr_istft, dim3(tiles, g.n_chunks, gb), 256, kIstftSmem, st, S, Msm, g, tabs, j_first, outp);
         OSB_CHECK_LAUNCH();
