@@ -128,121 +128,158 @@ __device__ __forceinline__ float mel_sample(const MelArgs& a, int s16, float gai
     return a.sumsq ? (float)quant_pcm16(apply_gain(x, gain, silent)) * 3.0517578125e-05f : x;
 }
 
-__global__ void __launch_bounds__(256, 2) k_logmel(MelArgs a) {
+// Persistent kernel: grid = 2 CTAs per SM, each CTA walks tiles (32 frames of one clip) round-robin.  The raw
+// int16 samples of the NEXT tile are fetched by the TMA unit (cp.async.bulk -> mbarrier) while the current tile is
+// transformed, so the HBM latency of the staging step is off the critical path.
+//   smem: [xs|P (aliased)] [win twc tws] [Y] [raw int16] ; P reuses the float sample buffer once step 1 is done.
+constexpr int kRawBytes = kXs * 2;                                   // 10,720 B (multiple of 16)
+constexpr int kXsP = (((kBins * kPStride > kXs) ? kBins * kPStride : kXs) + 3) / 4 * 4;  // 6,636 floats (keeps raw[] 16 B aligned)
+static_assert(((kXsP + 1200 + 16 * 2 * kF400Plane) * 4) % 16 == 0, "raw[] must be 16-byte aligned");
+
+__device__ __forceinline__ bool mel_tile_interior(const MelArgs& a, int b, int t0, const int16_t** src) {
+    const long long p0 = (long long)kHop * t0 - kNfft / 2;  // multiple of 8 samples
+    const int16_t* s = reinterpret_cast<const int16_t*>(a.audio) + (long long)b * a.stride + p0;
+    *src = s;
+    return a.fmt == OSB_FMT_PCM16 && p0 >= 0 && p0 + kXs <= a.n && (((uintptr_t)s) & 15) == 0;
+}
+
+__global__ void __launch_bounds__(256, 2) k_logmel(MelArgs a, int tiles_per_clip, int total_tiles) {
     extern __shared__ __align__(16) float sm[];
-    float* xs = sm;                       // [kXs]
-    float* win = xs + kXs;                // [400]
+    float* xs = sm;                       // [kXs] float samples (step 1)  |  P [201][33] (power, later phases)
+    float* P = sm;
+    float* win = sm + kXsP;               // [400]
     float* twc = win + 400;               // [400]
     float* tws = twc + 400;               // [400]
     float* Y = tws + 400;                 // [16][2][425]
-    float* P = Y + 16 * 2 * kF400Plane;   // [201][33]
+    int16_t* raw = reinterpret_cast<int16_t*>(Y + 16 * 2 * kF400Plane);  // [kXs] int16, TMA destination
     __shared__ unsigned short zaddr[402]; // four-step address of bin k and of its mirror 400-k
-    const int tid = threadIdx.x, b = blockIdx.y, t0 = blockIdx.x * MF;
+    __shared__ __align__(8) uint64_t bar;
+    const int tid = threadIdx.x;
 
     for (int i = tid; i < 1200; i += 256) win[i] = a.consts[i];
     for (int k = tid; k < kBins; k += 256) {
         zaddr[2 * k] = (unsigned short)fft400_addr(k);
         zaddr[2 * k + 1] = (unsigned short)fft400_addr(k == 0 ? 0 : 400 - k);
     }
-    {
-        // stage the tile's samples: reflect pad 200 around [x, 160 zeros]; fused normalise + requantise
-        bool silent = true;
-        float gain = 1.0f;
-        if (a.sumsq) gain = gain_from_meansq((double)a.sumsq[b] / 1073741824.0 / (double)a.n, a.target_dbfs, &silent);
-        const long long L = a.n + kPad;
-        const long long p0 = (long long)kHop * t0 - kNfft / 2;  // multiple of 8 samples
-        const bool interior = a.fmt == OSB_FMT_PCM16 && p0 >= 0 && p0 + kXs <= a.n &&
-                              (((uintptr_t)(reinterpret_cast<const int16_t*>(a.audio) + (long long)b * a.stride + p0)) & 15) == 0;
-        if (interior) {
-            const int16_t* src = reinterpret_cast<const int16_t*>(a.audio) + (long long)b * a.stride + p0;
-            uint4 v[3];
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        const int16_t* src;
+        const int tile = blockIdx.x;
+        if (tile < total_tiles && mel_tile_interior(a, tile / tiles_per_clip, (tile % tiles_per_clip) * MF, &src)) {
+            mbar_expect_tx(&bar, kRawBytes);
+            bulk_g2s(raw, src, kRawBytes, &bar);
+        }
+    }
+    __syncthreads();
+    uint32_t parity = 0;
+
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int b = tile / tiles_per_clip, t0 = (tile - b * tiles_per_clip) * MF;
+        {
+            // stage the tile's samples: reflect pad 200 around [x, 160 zeros]; fused normalise + requantise
+            bool silent = true;
+            float gain = 1.0f;
+            if (a.sumsq) gain = gain_from_meansq((double)a.sumsq[b] / 1073741824.0 / (double)a.n, a.target_dbfs, &silent);
+            const int16_t* src;
+            if (mel_tile_interior(a, b, t0, &src)) {
+                mbar_wait(&bar, parity);
+                parity ^= 1u;
 #pragma unroll
-            for (int r = 0; r < 3; ++r) {
-                const int i8 = tid + 256 * r;
-                if (i8 < kXs / 8) v[r] = ld_stream_u4(src + 8 * i8);
-            }
+                for (int r = 0; r < 3; ++r) {
+                    const int i8 = tid + 256 * r;
+                    if (i8 < kXs / 8) {
+                        const uint4 v = *reinterpret_cast<const uint4*>(raw + 8 * i8);
+                        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+                        float o[8];
 #pragma unroll
-            for (int r = 0; r < 3; ++r) {
-                const int i8 = tid + 256 * r;
-                if (i8 < kXs / 8) {
-                    const uint32_t w[4] = {v[r].x, v[r].y, v[r].z, v[r].w};
-                    float o[8];
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        o[2 * k] = mel_sample(a, (int)(int16_t)(w[k] & 0xFFFF), gain, silent);
-                        o[2 * k + 1] = mel_sample(a, (int)(int16_t)(w[k] >> 16), gain, silent);
+                        for (int k = 0; k < 4; ++k) {
+                            o[2 * k] = mel_sample(a, (int)(int16_t)(w[k] & 0xFFFF), gain, silent);
+                            o[2 * k + 1] = mel_sample(a, (int)(int16_t)(w[k] >> 16), gain, silent);
+                        }
+                        *reinterpret_cast<float4*>(xs + 8 * i8) = make_float4(o[0], o[1], o[2], o[3]);
+                        *reinterpret_cast<float4*>(xs + 8 * i8 + 4) = make_float4(o[4], o[5], o[6], o[7]);
                     }
-                    *reinterpret_cast<float4*>(xs + 8 * i8) = make_float4(o[0], o[1], o[2], o[3]);
-                    *reinterpret_cast<float4*>(xs + 8 * i8 + 4) = make_float4(o[4], o[5], o[6], o[7]);
                 }
-            }
-        } else {
-            for (int i = tid; i < kXs; i += 256) {
-                long long p = p0 + i;
-                while (p < 0 || p >= L) p = p < 0 ? -p : 2 * (L - 1) - p;
-                float v = 0.f;
-                if (p < a.n) {
-                    if (a.fmt == OSB_FMT_PCM16) v = mel_sample(a, (int)reinterpret_cast<const int16_t*>(a.audio)[(long long)b * a.stride + p], gain, silent);
-                    else v = reinterpret_cast<const float*>(a.audio)[(long long)b * a.stride + p];
+            } else {
+                const long long L = a.n + kPad;
+                const long long p0 = (long long)kHop * t0 - kNfft / 2;
+                for (int i = tid; i < kXs; i += 256) {
+                    long long p = p0 + i;
+                    while (p < 0 || p >= L) p = p < 0 ? -p : 2 * (L - 1) - p;
+                    float v = 0.f;
+                    if (p < a.n) {
+                        if (a.fmt == OSB_FMT_PCM16) v = mel_sample(a, (int)reinterpret_cast<const int16_t*>(a.audio)[(long long)b * a.stride + p], gain, silent);
+                        else v = reinterpret_cast<const float*>(a.audio)[(long long)b * a.stride + p];
+                    }
+                    xs[i] = v;
                 }
-                xs[i] = v;
             }
         }
-    }
-    __syncthreads();
-    {   // four-step FFT, step 1: 16 frame pairs x 16 residues = 256 tasks
-        const int q = tid >> 4, n2 = tid & 15;
-        fft400_step1(xs + (2 * q) * kHop, xs + (2 * q + 1) * kHop, win, twc, tws, n2, Y + q * 2 * kF400Plane, Y + q * 2 * kF400Plane + kF400Plane);
-    }
-    __syncthreads();
-    for (int task = tid; task < 16 * 25; task += 256) {  // step 2: 16 pairs x 25 rows
-        const int q = task / 25, k1 = task - q * 25;
-        fft400_step2(k1, Y + q * 2 * kF400Plane, Y + q * 2 * kF400Plane + kF400Plane);
-    }
-    __syncthreads();
-    {   // power of both frames of each pair: warp w takes pairs w and w+8, lanes stride over the 201 bins
-        const int lane = tid & 31;
+        __syncthreads();  // xs complete; raw[] has been consumed by every thread
+        if (tid == 0) {   // prefetch the next tile of this CTA while this one is transformed
+            const int nt = tile + gridDim.x;
+            const int16_t* src;
+            if (nt < total_tiles && mel_tile_interior(a, nt / tiles_per_clip, (nt % tiles_per_clip) * MF, &src)) {
+                fence_proxy_async();  // generic-proxy reads of raw[] above are ordered before the async-proxy write
+                mbar_expect_tx(&bar, kRawBytes);
+                bulk_g2s(raw, src, kRawBytes, &bar);
+            }
+        }
+        {   // four-step FFT, step 1: 16 frame pairs x 16 residues = 256 tasks
+            const int q = tid >> 4, n2 = tid & 15;
+            fft400_step1(xs + (2 * q) * kHop, xs + (2 * q + 1) * kHop, win, twc, tws, n2, Y + q * 2 * kF400Plane, Y + q * 2 * kF400Plane + kF400Plane);
+        }
+        __syncthreads();
+        for (int task = tid; task < 16 * 25; task += 256) {  // step 2: 16 pairs x 25 rows
+            const int q = task / 25, k1 = task - q * 25;
+            fft400_step2(k1, Y + q * 2 * kF400Plane, Y + q * 2 * kF400Plane + kF400Plane);
+        }
+        __syncthreads();
+        {   // power of both frames of each pair: warp w takes pairs w and w+8, lanes stride over the 201 bins
+            const int lane = tid & 31;
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int q = (tid >> 5) + 8 * h;
-            const float* zr_ = Y + q * 2 * kF400Plane;
-            const float* zi_ = zr_ + kF400Plane;
-            for (int k = lane; k < kBins; k += 32) {
-                const int a0 = zaddr[2 * k], a1 = zaddr[2 * k + 1];
-                const float zr = zr_[a0], zi = zi_[a0], yr = zr_[a1], yi = zi_[a1];
-                const float ar = zr + yr, ai = zi - yi, br = zi + yi, bi = yr - zr;
-                P[k * kPStride + 2 * q] = 0.25f * (ar * ar + ai * ai);
-                P[k * kPStride + 2 * q + 1] = 0.25f * (br * br + bi * bi);
+            for (int h = 0; h < 2; ++h) {
+                const int q = (tid >> 5) + 8 * h;
+                const float* zr_ = Y + q * 2 * kF400Plane;
+                const float* zi_ = zr_ + kF400Plane;
+                for (int k = lane; k < kBins; k += 32) {
+                    const int a0 = zaddr[2 * k], a1 = zaddr[2 * k + 1];
+                    const float zr = zr_[a0], zi = zi_[a0], yr = zr_[a1], yi = zi_[a1];
+                    const float ar = zr + yr, ai = zi - yi, br = zi + yi, bi = yr - zr;
+                    P[k * kPStride + 2 * q] = 0.25f * (ar * ar + ai * ai);
+                    P[k * kPStride + 2 * q + 1] = 0.25f * (br * br + bi * bi);
+                }
             }
         }
-    }
-    __syncthreads();
-    // sparse mel contraction (each triangle touches a few bins) + log10; lanes = consecutive frames
-    const int f = tid & 31;
-    const bool live = (t0 + f) < a.n_frames;
-    float vmax = -10.0f;
-    float* outb = a.out + (long long)b * a.n_mels * a.n_frames + t0 + f;
-    const float* Pf = P + f;
-    for (int m = tid >> 5; m < a.n_mels; m += 8) {
-        const int s = __ldg(a.mel_start + m), len = __ldg(a.mel_len + m);
-        const float* w = a.mel_w + __ldg(a.mel_off + m);
-        const float* pp = Pf + s * kPStride;
-        float acc0 = 0.f, acc1 = 0.f;
-        int i = 0;
-        for (; i + 1 < len; i += 2) {
-            acc0 = fmaf(__ldg(w + i), pp[i * kPStride], acc0);
-            acc1 = fmaf(__ldg(w + i + 1), pp[(i + 1) * kPStride], acc1);
+        __syncthreads();
+        // sparse mel contraction (each triangle touches a few bins) + log10; lanes = consecutive frames
+        const int f = tid & 31;
+        const bool live = (t0 + f) < a.n_frames;
+        float vmax = -10.0f;
+        float* outb = a.out + (long long)b * a.n_mels * a.n_frames + t0 + f;
+        const float* Pf = P + f;
+        for (int m = tid >> 5; m < a.n_mels; m += 8) {
+            const int s = __ldg(a.mel_start + m), len = __ldg(a.mel_len + m);
+            const float* w = a.mel_w + __ldg(a.mel_off + m);
+            const float* pp = Pf + s * kPStride;
+            float acc0 = 0.f, acc1 = 0.f;
+            int i = 0;
+            for (; i + 1 < len; i += 2) {
+                acc0 = fmaf(__ldg(w + i), pp[i * kPStride], acc0);
+                acc1 = fmaf(__ldg(w + i + 1), pp[(i + 1) * kPStride], acc1);
+            }
+            if (i < len) acc0 = fmaf(__ldg(w + i), pp[i * kPStride], acc0);
+            // log10 via the SFU log2: |error| < 3e-6 on log10, 1e-6 on the output (tolerance 1e-4)
+            const float v = __log2f(fmaxf(acc0 + acc1, 1e-10f)) * 0.30102999566398120f;
+            if (live) {
+                outb[(long long)m * a.n_frames] = v;
+                vmax = fmaxf(vmax, v);
+            }
         }
-        if (i < len) acc0 = fmaf(__ldg(w + i), pp[i * kPStride], acc0);
-        // log10 via the SFU log2: |error| < 3e-6 on log10, 1e-6 on the output (tolerance 1e-4)
-        const float v = __log2f(fmaxf(acc0 + acc1, 1e-10f)) * 0.30102999566398120f;
-        if (live) {
-            outb[(long long)m * a.n_frames] = v;
-            vmax = fmaxf(vmax, v);
-        }
+        vmax = warp_max(vmax);
+        if ((tid & 31) == 0) atomicMax(a.gmax + b, __float_as_uint(vmax + 10.0f));
+        __syncthreads();  // P (aliasing xs) is free again
     }
-    vmax = warp_max(vmax);
-    if ((tid & 31) == 0) atomicMax(a.gmax + b, __float_as_uint(vmax + 10.0f));
 }
 
 // log_spec = maximum(log_spec, log_spec.max() - 8.0); (log_spec + 4.0) / 4.0
@@ -263,7 +300,7 @@ __global__ void __launch_bounds__(256) k_logmel_finalize(float* __restrict__ out
     for (long long i = nvec * 4 + tid; i < per_clip; i += nthr) o[i] = __fdiv_rn(__fadd_rn(fmaxf(o[i], thr), 4.0f), 4.0f);
 }
 
-constexpr int kLogmelSmem = (kXs + 1200 + 16 * 2 * kF400Plane + kBins * kPStride) * (int)sizeof(float);
+constexpr int kLogmelSmem = (kXsP + 1200 + 16 * 2 * kF400Plane) * (int)sizeof(float) + kRawBytes;
 
 int launch_logmel(const void* d_audio, int fmt, long long n, long long batch, long long stride, int n_mels, float* d_out,
                   const unsigned long long* d_sumsq, float target_dbfs, cudaStream_t st) {
@@ -283,8 +320,16 @@ int launch_logmel(const void* d_audio, int fmt, long long n, long long batch, lo
     a.audio = d_audio; a.n = n; a.stride = stride; a.fmt = fmt; a.n_frames = n_frames; a.n_mels = n_mels;
     a.out = d_out; a.gmax = gmax; a.sumsq = d_sumsq; a.target_dbfs = target_dbfs;
     a.consts = t->d_consts; a.mel_start = t->d_start; a.mel_len = t->d_len; a.mel_off = t->d_off; a.mel_w = t->d_w;
-    dim3 grid((n_frames + MF - 1) / MF, (unsigned)batch);
-    OSB_LAUNCH(k_logmel, grid, 256, kLogmelSmem, st, a);
+    const int tiles_per_clip = (n_frames + MF - 1) / MF;
+    const long long total_tiles_ll = (long long)tiles_per_clip * batch;
+    if (total_tiles_ll > 0x7fffffffLL) {
+        set_error("invalid argument: too many log-mel tiles");
+        return OSB_ERR_INVALID_ARG;
+    }
+    const int total_tiles = (int)total_tiles_ll;
+    const int persistent = 2 * num_sms();  // 2 resident CTAs per SM (97 KB of shared memory each)
+    const int grid = total_tiles < persistent ? total_tiles : persistent;
+    OSB_LAUNCH(k_logmel, grid, 256, kLogmelSmem, st, a, tiles_per_clip, total_tiles);
     OSB_CHECK_LAUNCH();
     const long long per_clip = (long long)n_mels * n_frames;
     long long fb = (per_clip / 4 + 255) / 256;
