@@ -10,8 +10,11 @@
 //          4x Conv1d(k=3)+ReLU -> W_ih.x + b_ih + b_hh          => gate pre-activations [W][512]
 //   recur  (sequential over windows, one CTA per stream): gates += W_hh.h ; LSTM cell ; head
 //   segment(integer state machine, one warp per stream): bit-exact with silero.py:133-177
+#include <cstdlib>
 #include <mutex>
 #include <vector>
+
+#include <cuda_bf16.h>
 
 #include "common.cuh"
 
@@ -43,6 +46,10 @@ struct VadModel {
     float *whh;        // [512][128]
     float *dw;         // [128]
     float db;
+    // tcgen05 path: per layer, B as split-bf16 (hi, lo) tiles pre-arranged in the 128B-swizzled K-major
+    // shared-memory image, [n_tile][k_chunk][plane][NT*64]
+    struct Tc { uint16_t* img; int NT, n_tiles, k_chunks; } tc[6];
+    int use_tc;
 };
 
 // ------------------------------------------------------------------ batched front GEMM
@@ -163,6 +170,199 @@ __global__ void __launch_bounds__(256) k_vad_gemm(GemmDesc d) {
             }
         }
     }
+}
+
+
+// ------------------------------------------------------------------ tcgen05 front GEMM (split-bf16, FP32 accumulate in TMEM)
+// C[128 rows x N] per CTA.  A rows (f32 activations or pcm16 audio frames) are split by the CTA's threads into
+// bf16 hi + lo and written to shared memory in the canonical 128B-swizzled K-major layout; B (weights) arrives
+// pre-split and pre-swizzled through the TMA unit (cp.async.bulk).  Three MMAs per k-step (hi*hi, hi*lo, lo*hi)
+// give ~2^-16 relative operand precision, FP32 accumulation in tensor memory; the epilogue reads TMEM with
+// tcgen05.ld and fuses bias/ReLU (or the |re,im| magnitude of the DFT conv).
+constexpr int kTcM = 128, kTcKc = 64;                 // rows per CTA, K elements per chunk (one 128 B swizzle row of bf16)
+constexpr int kTcNTmax = 144;
+constexpr int kTcAPlane = kTcM * kTcKc * 2;           // 16 KB
+constexpr int kTcABuf = 2 * kTcAPlane;                // hi + lo
+constexpr int kTcBPlaneMax = kTcNTmax * kTcKc * 2;    // 18 KB
+constexpr int kTcBBuf = 2 * kTcBPlaneMax;
+constexpr int kTcNB = 4;                              // B ring depth
+constexpr int kTcSmem = 2 * kTcABuf + kTcNB * kTcBBuf + 1024;
+
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+    // start address (>>4) | LBO=1 (unused for swizzled K-major) | SBO = 1024 B (8 rows x 128 B) | version 1 | SWIZZLE_128B
+    const uint32_t lo = ((saddr >> 4) & 0x3FFFu) | (1u << 16);
+    const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+    return ((uint64_t)hi << 32) | lo;
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 :: "r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t& hi, uint32_t& lo) {
+    const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
+    const __nv_bfloat16 al = __float2bfloat16_rn(a - __bfloat162float(ah)), bl = __float2bfloat16_rn(b - __bfloat162float(bh));
+    hi = (uint32_t)__bfloat16_as_ushort(ah) | ((uint32_t)__bfloat16_as_ushort(bh) << 16);
+    lo = (uint32_t)__bfloat16_as_ushort(al) | ((uint32_t)__bfloat16_as_ushort(bl) << 16);
+}
+
+template <int AMODE, int EPI>
+__global__ void __launch_bounds__(256, 1) k_vad_gemm_tc(GemmDesc d, const uint16_t* __restrict__ Bimg, int NT, int n_tiles, int k_chunks) {
+    extern __shared__ uint8_t smraw[];
+    uint8_t* smb = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smraw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* Abuf = smb;                    // [2][hi|lo][128 x 128 B]
+    uint8_t* Bbuf = smb + 2 * kTcABuf;      // [4][hi|lo][NT x 128 B]
+    __shared__ __align__(8) uint64_t fullB[kTcNB], doneB[kTcNB], doneA[2], doneAll;
+    __shared__ uint32_t tmem_base_sm;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int m0 = blockIdx.x * kTcM;
+    const uint32_t b_plane = (uint32_t)NT * kTcKc * 2, b_tile = 2 * b_plane;
+
+    if (tid == 0) {
+        for (int i = 0; i < kTcNB; ++i) { mbar_init(&fullB[i], 1); mbar_init(&doneB[i], 1); }
+        mbar_init(&doneA[0], 1); mbar_init(&doneA[1], 1); mbar_init(&doneAll, 1);
+    }
+    if (warp == 0) {  // one full warp allocates all 512 TMEM columns (1 CTA per SM by construction: 209 KB of smem)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&tmem_base_sm)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_sm;
+    const int steps = k_chunks * n_tiles;
+    // instruction descriptor: D=f32, A=B=bf16, both K-major, N = NT, M = 128
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(kTcM >> 4) << 24);
+
+    auto issue_b_load = [&](int s) {  // step s = kc * n_tiles + nt ; image order is [nt][kc]
+        const int kc = s / n_tiles, nt = s - kc * n_tiles, b = s % kTcNB;
+        const uint16_t* src = Bimg + ((size_t)nt * k_chunks + kc) * (b_tile / 2);
+        mbar_expect_tx(&fullB[b], b_tile);
+        bulk_g2s(Bbuf + (size_t)b * kTcBBuf, src, b_plane, &fullB[b]);
+        bulk_g2s(Bbuf + (size_t)b * kTcBBuf + kTcBPlaneMax, src + b_plane / 2, b_plane, &fullB[b]);
+    };
+    if (tid == 0)
+        for (int s = 0; s < kTcNB - 1 && s < steps; ++s) issue_b_load(s);
+
+    const int arow = tid & 127, ahalf = tid >> 7;  // thread -> (row, 32-element half of the 64-wide chunk)
+    for (int kc = 0; kc < k_chunks; ++kc) {
+        const int ab = kc & 1;
+        if (kc >= 2) mbar_wait(&doneA[ab], (uint32_t)(((kc >> 1) - 1) & 1));  // MMAs of chunk kc-2 have drained this buffer
+        {   // stage A(kc): 32 elements per thread -> 4 x 16 B per plane at swizzled positions
+            float v[32];
+            const int r = m0 + arow, k0 = kc * kTcKc + 32 * ahalf;
+            if (r >= d.M) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = 0.f;
+            } else if (AMODE == 0) {
+                const float* p = reinterpret_cast<const float*>(d.A) + (long long)(r / d.a_icount) * d.a_outer + (long long)(r % d.a_icount) * d.a_istride + k0;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const float4 t = *reinterpret_cast<const float4*>(p + 4 * q);
+                    v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+                }
+            } else {
+                const int f = r % 3, wq = r / 3;
+                const int sidx = wq / d.wins_per_stream;
+                const long long win = d.win0 + (wq - sidx * d.wins_per_stream);
+                const long long base = (long long)sidx * d.audio_stride + win * kWin;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    int sidx2 = 128 * f + k0 + i;
+                    sidx2 = sidx2 < kWin ? sidx2 : (2 * kWin - 2 - sidx2);
+                    if (AMODE == 1) v[i] = (float)reinterpret_cast<const int16_t*>(d.A)[base + sidx2] * 3.0517578125e-05f;
+                    else v[i] = reinterpret_cast<const float*>(d.A)[base + sidx2];
+                }
+            }
+            uint8_t* hi_row = Abuf + (size_t)ab * kTcABuf + (arow >> 3) * 1024 + (arow & 7) * 128;
+            uint8_t* lo_row = hi_row + kTcAPlane;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                uint32_t h[4], l[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) split_bf16x2(v[8 * c + 2 * j], v[8 * c + 2 * j + 1], h[j], l[j]);
+                const int chunk = (4 * ahalf + c) ^ (arow & 7);
+                *reinterpret_cast<uint4*>(hi_row + chunk * 16) = make_uint4(h[0], h[1], h[2], h[3]);
+                *reinterpret_cast<uint4*>(lo_row + chunk * 16) = make_uint4(l[0], l[1], l[2], l[3]);
+            }
+        }
+        fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            const uint32_t a_hi = smem_u32(Abuf + (size_t)ab * kTcABuf), a_lo = a_hi + kTcAPlane;
+            for (int nt = 0; nt < n_tiles; ++nt) {
+                const int s = kc * n_tiles + nt, b = s % kTcNB;
+                mbar_wait(&fullB[b], (uint32_t)((s / kTcNB) & 1));
+                tc_fence_after();
+                const uint32_t b_hi = smem_u32(Bbuf + (size_t)b * kTcBBuf), b_lo = b_hi + kTcBPlaneMax;
+                const uint32_t dcol = tmem_base + (uint32_t)(nt * NT);
+#pragma unroll
+                for (int k = 0; k < kTcKc / 16; ++k) {
+                    const uint32_t ko = k * 32;  // 16 bf16 = 32 B along the swizzled row
+                    umma_bf16(dcol, umma_desc_sw128(a_hi + ko), umma_desc_sw128(b_hi + ko), idesc, (kc | k) ? 1u : 0u);
+                    umma_bf16(dcol, umma_desc_sw128(a_hi + ko), umma_desc_sw128(b_lo + ko), idesc, 1u);
+                    umma_bf16(dcol, umma_desc_sw128(a_lo + ko), umma_desc_sw128(b_hi + ko), idesc, 1u);
+                }
+                umma_commit(&doneB[b]);
+                if (nt == n_tiles - 1) umma_commit(&doneA[ab]);
+                // refill the ring: the buffer of step s-1 is free once its MMAs completed
+                const int sn = s + kTcNB - 1;
+                if (sn < steps) {
+                    if (s >= 1) mbar_wait(&doneB[(s - 1) % kTcNB], (uint32_t)(((s - 1) / kTcNB) & 1));
+                    issue_b_load(sn);
+                }
+            }
+            if (kc == k_chunks - 1) umma_commit(&doneAll);
+        }
+    }
+    // ---- epilogue: TMEM -> registers -> global
+    mbar_wait(&doneAll, 0);
+    tc_fence_after();
+    const int r = m0 + (warp & 3) * 32 + lane;
+    const bool row_ok = r < d.M;
+    float* crow = d.C;
+    if (row_ok) crow += (long long)(r / d.c_icount) * d.c_outer + (long long)(r % d.c_icount) * d.c_istride + d.c_offset;
+    const int ncb = (n_tiles * NT + 31) / 32;
+    for (int cb = warp >> 2; cb < ncb; cb += 2) {
+        uint32_t v[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(cb * 32);
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+                     "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                     : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                       "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                       "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                       "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                     : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (!row_ok) continue;
+        if (EPI == 1) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const int bin = cb * 16 + i;
+                const float re = __uint_as_float(v[2 * i]), im = __uint_as_float(v[2 * i + 1]);
+                if (2 * bin < d.N) crow[bin] = sqrtf(re * re + im * im);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const int n = cb * 32 + i;
+                if (n < d.N) {
+                    const float x = __uint_as_float(v[i]) + (d.bias ? __ldg(d.bias + n) : 0.f);
+                    crow[n] = d.relu ? fmaxf(x, 0.f) : x;
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(512));
 }
 
 // ------------------------------------------------------------------ recurrence + head
@@ -297,6 +497,56 @@ static std::vector<float> relay_conv(const float* w, int oc, int ic, int icp, in
     return o;
 }
 
+static uint16_t f2bf(float f) {  // round-to-nearest-even float -> bf16 bits
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);
+    u += 0x7fffu + ((u >> 16) & 1u);
+    return (uint16_t)(u >> 16);
+}
+static float bf2f(uint16_t h) {
+    uint32_t u = (uint32_t)h << 16;
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+}
+
+// B [N][Kp] f32 -> [n_tile][k_chunk][hi|lo][NT x 64] bf16 in the 128B-swizzled K-major shared-memory image
+static int build_tc_image(const std::vector<float>& B, int N, int Kp, int NT, VadModel::Tc* out) {
+    const int n_tiles = (N + NT - 1) / NT, k_chunks = (Kp + kTcKc - 1) / kTcKc;
+    const size_t plane = (size_t)NT * kTcKc, tile = 2 * plane;
+    std::vector<uint16_t> img((size_t)n_tiles * k_chunks * tile, 0);
+    for (int nt = 0; nt < n_tiles; ++nt)
+        for (int kc = 0; kc < k_chunks; ++kc) {
+            uint16_t* t = img.data() + ((size_t)nt * k_chunks + kc) * tile;
+            for (int r = 0; r < NT; ++r)
+                for (int e = 0; e < kTcKc; ++e) {
+                    const int n = nt * NT + r, k = kc * kTcKc + e;
+                    const float v = (n < N && k < Kp) ? B[(size_t)n * Kp + k] : 0.f;
+                    const uint16_t hi = f2bf(v), lo = f2bf(v - bf2f(hi));
+                    const size_t off = ((size_t)(r >> 3) * 1024 + (r & 7) * 128 + (((e >> 3) ^ (r & 7)) * 16) + (e & 7) * 2) / 2;
+                    t[off] = hi;
+                    t[plane + off] = lo;
+                }
+        }
+    OSB_CUDA(cudaMalloc(&out->img, img.size() * 2));
+    OSB_CUDA(cudaMemcpy(out->img, img.data(), img.size() * 2, cudaMemcpyHostToDevice));
+    out->NT = NT; out->n_tiles = n_tiles; out->k_chunks = k_chunks;
+    return OSB_OK;
+}
+
+template <int AMODE, int EPI>
+static int launch_gemm_tc(const GemmDesc& d, const VadModel::Tc& L, cudaStream_t st) {
+    static bool attr_done = false;
+    if (!attr_done) {
+        OSB_CUDA(cudaFuncSetAttribute(k_vad_gemm_tc<AMODE, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem));
+        attr_done = true;
+    }
+    OSB_LAUNCH((k_vad_gemm_tc<AMODE, EPI>), (d.M + kTcM - 1) / kTcM, 256, kTcSmem, st, d, (const uint16_t*)L.img, L.NT, L.n_tiles, L.k_chunks);
+    OSB_CHECK_LAUNCH();
+    return OSB_OK;
+}
+
 template <int AMODE, int EPI>
 static int launch_gemm(const GemmDesc& d, cudaStream_t st) {
     dim3 grid((d.M + BM - 1) / BM, (d.N + BN - 1) / BN);
@@ -316,14 +566,14 @@ static int vad_score(VadModel* m, const void* d_audio, int fmt, int64_t n, int64
     const long long W = batch * T;  // windows per chunk
     Scratch scr(st);
     float *mag, *h1, *h2, *h3, *h4, *pre;
-    OSB_CUDA(scr.alloc(&mag, (size_t)W * 5 * kMagC + 64));
+    OSB_CUDA(scr.alloc(&mag, (size_t)W * 5 * kMagC + 128));
     OSB_CUDA(scr.alloc(&h1, (size_t)W * 5 * 128 + 64));
     OSB_CUDA(scr.alloc(&h2, (size_t)W * 4 * 64 + 64));
     OSB_CUDA(scr.alloc(&h3, (size_t)W * 3 * 64 + 64));
     OSB_CUDA(scr.alloc(&h4, (size_t)W * 128 + 64));
     OSB_CUDA(scr.alloc(&pre, (size_t)W * kGates + 64));
     // zero once: the padding rows/channels are never written by the GEMMs
-    OSB_CUDA(cudaMemsetAsync(mag, 0, ((size_t)W * 5 * kMagC + 64) * 4, st));
+    OSB_CUDA(cudaMemsetAsync(mag, 0, ((size_t)W * 5 * kMagC + 128) * 4, st));
     OSB_CUDA(cudaMemsetAsync(h1, 0, ((size_t)W * 5 * 128 + 64) * 4, st));
     OSB_CUDA(cudaMemsetAsync(h2, 0, ((size_t)W * 4 * 64 + 64) * 4, st));
     OSB_CUDA(cudaMemsetAsync(h3, 0, ((size_t)W * 3 * 64 + 64) * 4, st));
@@ -341,38 +591,39 @@ static int vad_score(VadModel* m, const void* d_audio, int fmt, int64_t n, int64
         d.A = d_audio; d.audio_stride = stride; d.wins_per_stream = t; d.win0 = w0;
         d.B = m->basis; d.bias = nullptr; d.C = mag; d.c_outer = 5 * kMagC; d.c_icount = 3; d.c_istride = kMagC; d.c_offset = kMagC;
         d.M = Wc * 3; d.N = 258; d.K = 256; d.relu = 0;
-        rc = (fmt == OSB_FMT_PCM16) ? launch_gemm<1, 1>(d, st) : launch_gemm<2, 1>(d, st);
+        if (m->use_tc) rc = (fmt == OSB_FMT_PCM16) ? launch_gemm_tc<1, 1>(d, m->tc[0], st) : launch_gemm_tc<2, 1>(d, m->tc[0], st);
+        else rc = (fmt == OSB_FMT_PCM16) ? launch_gemm<1, 1>(d, st) : launch_gemm<2, 1>(d, st);
         if (rc) return rc;
         // L1: enc1 129->128, k3 s1 p1, 3 positions
         d = GemmDesc{};
         d.A = mag; d.a_outer = 5 * kMagC; d.a_icount = 3; d.a_istride = kMagC;
         d.B = m->e1w; d.bias = m->e1b; d.C = h1; d.c_outer = 5 * 128; d.c_icount = 3; d.c_istride = 128; d.c_offset = 128;
         d.M = Wc * 3; d.N = 128; d.K = kK1; d.relu = 1;
-        if ((rc = launch_gemm<0, 0>(d, st))) return rc;
+        if ((rc = m->use_tc ? launch_gemm_tc<0, 0>(d, m->tc[1], st) : launch_gemm<0, 0>(d, st))) return rc;
         // L2: enc2 128->64, k3 s2 p1, 2 positions
         d = GemmDesc{};
         d.A = h1; d.a_outer = 5 * 128; d.a_icount = 2; d.a_istride = 2 * 128;
         d.B = m->e2w; d.bias = m->e2b; d.C = h2; d.c_outer = 4 * 64; d.c_icount = 2; d.c_istride = 64; d.c_offset = 64;
         d.M = Wc * 2; d.N = 64; d.K = 384; d.relu = 1;
-        if ((rc = launch_gemm<0, 0>(d, st))) return rc;
+        if ((rc = m->use_tc ? launch_gemm_tc<0, 0>(d, m->tc[2], st) : launch_gemm<0, 0>(d, st))) return rc;
         // L3: enc3 64->64, k3 s2 p1, 1 position
         d = GemmDesc{};
         d.A = h2; d.a_outer = 4 * 64; d.a_icount = 1; d.a_istride = 0;
         d.B = m->e3w; d.bias = m->e3b; d.C = h3; d.c_outer = 3 * 64; d.c_icount = 1; d.c_istride = 0; d.c_offset = 64;
         d.M = Wc; d.N = 64; d.K = 192; d.relu = 1;
-        if ((rc = launch_gemm<0, 0>(d, st))) return rc;
+        if ((rc = m->use_tc ? launch_gemm_tc<0, 0>(d, m->tc[3], st) : launch_gemm<0, 0>(d, st))) return rc;
         // L4: enc4 64->128, k3 s1 p1, 1 position
         d = GemmDesc{};
         d.A = h3; d.a_outer = 3 * 64; d.a_icount = 1; d.a_istride = 0;
         d.B = m->e4w; d.bias = m->e4b; d.C = h4; d.c_outer = 128; d.c_icount = 1; d.c_istride = 0; d.c_offset = 0;
         d.M = Wc; d.N = 128; d.K = 192; d.relu = 1;
-        if ((rc = launch_gemm<0, 0>(d, st))) return rc;
+        if ((rc = m->use_tc ? launch_gemm_tc<0, 0>(d, m->tc[4], st) : launch_gemm<0, 0>(d, st))) return rc;
         // L5: W_ih.x + (b_ih + b_hh) -> gate pre-activations
         d = GemmDesc{};
         d.A = h4; d.a_outer = 128; d.a_icount = 1; d.a_istride = 0;
         d.B = m->wih; d.bias = m->bsum; d.C = pre; d.c_outer = kGates; d.c_icount = 1; d.c_istride = 0; d.c_offset = 0;
         d.M = Wc; d.N = kGates; d.K = 128; d.relu = 0;
-        if ((rc = launch_gemm<0, 0>(d, st))) return rc;
+        if ((rc = m->use_tc ? launch_gemm_tc<0, 0>(d, m->tc[5], st) : launch_gemm<0, 0>(d, st))) return rc;
         // recurrence over the chunk's t windows, one CTA per stream
         OSB_LAUNCH(k_vad_recur, (unsigned)batch, 512, recur_smem, st, pre, (long long)t * kGates, t, m->whh, m->dw, m->db,
                    d_state, d_probs, (long long)probs_stride, w0);
@@ -430,6 +681,19 @@ int osb_vad_create(const float* weights_host, size_t n_floats, void** handle) {
         return rc;
     }
     m->db = w[oDb];
+    {   // tcgen05 operand images
+        std::vector<float> e1 = relay_conv(w + oE1w, 128, 129, kMagC, 448);
+        if ((rc = build_tc_image(basis, 258, 256, 144, &m->tc[0])) || (rc = build_tc_image(e1, 128, 448, 128, &m->tc[1])) ||
+            (rc = build_tc_image(relay_conv(w + oE2w, 64, 128, 128, 384), 64, 384, 64, &m->tc[2])) ||
+            (rc = build_tc_image(relay_conv(w + oE3w, 64, 64, 64, 192), 64, 192, 64, &m->tc[3])) ||
+            (rc = build_tc_image(relay_conv(w + oE4w, 128, 64, 64, 192), 128, 192, 128, &m->tc[4])) ||
+            (rc = build_tc_image(vec(oWih, nW), 512, 128, 128, &m->tc[5]))) {
+            delete m;
+            return rc;
+        }
+    }
+    const char* env = getenv("OSB_VAD_GEMM");
+    m->use_tc = !(env && strcmp(env, "ffma") == 0);
     *handle = m;
     return OSB_OK;
 }
@@ -439,7 +703,14 @@ int osb_vad_destroy(void* handle) {
     VadModel* m = reinterpret_cast<VadModel*>(handle);
     float* ptrs[] = {m->basis, m->e1w, m->e1b, m->e2w, m->e2b, m->e3w, m->e3b, m->e4w, m->e4b, m->wih, m->bsum, m->whh, m->dw};
     for (float* p : ptrs) cudaFree(p);
+    for (auto& t : m->tc) cudaFree(t.img);
     delete m;
+    return OSB_OK;
+}
+
+int osb_vad_set_gemm(void* handle, int use_tcgen05) {
+    OSB_REQUIRE(handle, "null VAD handle");
+    reinterpret_cast<VadModel*>(handle)->use_tc = use_tcgen05 ? 1 : 0;
     return OSB_OK;
 }
 

@@ -118,3 +118,21 @@ def test_batched_streams_match_single(gpu, session):
     for i in range(5):
         ref, _ = net.score_stream(pcm[i].astype(np.float32) / 32768.0)
         assert np.abs(probs[i].cpu().numpy() - ref).max() <= PROB_TOL
+
+
+def test_tcgen05_front_matches_ffma_and_oracle(gpu, session):
+    """The tensor-core (tcgen05, split-bf16) front-end GEMM against the FP32 FFMA kernel and the oracle."""
+    from open_speech_b200.vad.silero import SileroVAD
+
+    pcm = _audio(20.0, 321)
+    ref, _ = ovad.SileroNet().score_stream(pcm.astype(np.float32) / 32768.0)
+    out = {}
+    try:
+        for mode in (1, 0):
+            gpu.call("osb_vad_set_gemm", session.handle, mode)
+            out[mode] = SileroVAD(session)._score(pcm.tobytes(), gpu.FMT_PCM16, len(pcm))
+    finally:
+        gpu.call("osb_vad_set_gemm", session.handle, 1)
+    assert np.abs(out[0] - ref).max() <= PROB_TOL
+    assert np.abs(out[1] - ref).max() <= PROB_TOL, float(np.abs(out[1] - ref).max())
+    assert np.abs(out[1] - out[0]).max() <= 2e-4, float(np.abs(out[1] - out[0]).max())
