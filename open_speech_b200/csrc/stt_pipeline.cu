@@ -1,5 +1,7 @@
 // Composed STT paths: preprocess_stt_audio (reference src/audio/preprocessing.py:53-63) and the batch
 // STT front-end of BASELINE configs 1 / 4 (preprocess -> WAV -> faster-whisper FeatureExtractor).
+#include <cstdlib>
+
 #include "common.cuh"
 
 using namespace osb;
@@ -66,15 +68,22 @@ int osb_stt_frontend_host(const int16_t* pcm, int64_t n, int64_t batch, int64_t 
         OSB_CUDA(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
         s_dev = ws.device;
     }
-    const int groups = batch >= 16 ? 4 : 1;
-    cudaEvent_t ev_in[4], ev_done[4];
+    // clip groups (default 4; OSB_STT_HOST_GROUPS=1..8 to tune): more groups = more copy/compute overlap but smaller launches
+    int64_t bounds[9] = {0};
+    int groups = batch >= 16 ? 4 : 1;
+    if (const char* e = getenv("OSB_STT_HOST_GROUPS")) {
+        const int g = atoi(e);
+        if (g >= 1 && g <= 8 && g <= batch) groups = g;
+    }
+    for (int g = 0; g <= groups; ++g) bounds[g] = batch * g / groups;
+    cudaEvent_t ev_in[8], ev_done[8];
     for (int g = 0; g < groups; ++g) {
         OSB_CUDA(cudaEventCreateWithFlags(&ev_in[g], cudaEventDisableTiming));
         OSB_CUDA(cudaEventCreateWithFlags(&ev_done[g], cudaEventDisableTiming));
     }
     rc = OSB_OK;
     for (int g = 0; g < groups && rc == OSB_OK; ++g) {
-        const int64_t c0 = batch * g / groups, c1 = batch * (g + 1) / groups, nb = c1 - c0;
+        const int64_t c0 = bounds[g], c1 = bounds[g + 1], nb = c1 - c0;
         const int16_t* hin = pcm + c0 * stride;
         int16_t* din = (int16_t*)di + c0 * stride;
         float* dmel = (float*)dout + c0 * per_mel;

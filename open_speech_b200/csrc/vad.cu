@@ -325,11 +325,11 @@ __global__ void __launch_bounds__(256, 1) k_vad_gemm_tc(GemmDesc d, const uint16
     // ---- epilogue: TMEM -> registers -> global
     mbar_wait(&doneAll, 0);
     tc_fence_after();
-    const int r = m0 + (warp & 3) * 32 + lane;
-    const bool row_ok = r < d.M;
-    float* crow = d.C;
-    if (row_ok) crow += (long long)(r / d.c_icount) * d.c_outer + (long long)(r % d.c_icount) * d.c_istride + d.c_offset;
     const int ncb = (n_tiles * NT + 31) / 32;
+    // each warp transposes its 32x32 block through shared memory (the operand buffers are free now) so that
+    // every global store instruction writes 128 contiguous bytes of one output row
+    float* tile = reinterpret_cast<float*>(smb) + warp * (32 * 33);
+    const int rbase = m0 + (warp & 3) * 32;
     for (int cb = warp >> 2; cb < ncb; cb += 2) {
         uint32_t v[32];
         const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(cb * 32);
@@ -341,24 +341,32 @@ __global__ void __launch_bounds__(256, 1) k_vad_gemm_tc(GemmDesc d, const uint16
                        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
                      : "r"(taddr));
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (!row_ok) continue;
         if (EPI == 1) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-                const int bin = cb * 16 + i;
                 const float re = __uint_as_float(v[2 * i]), im = __uint_as_float(v[2 * i + 1]);
-                if (2 * bin < d.N) crow[bin] = sqrtf(re * re + im * im);
+                tile[lane * 33 + i] = sqrtf(re * re + im * im);
             }
         } else {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                const int n = cb * 32 + i;
-                if (n < d.N) {
-                    const float x = __uint_as_float(v[i]) + (d.bias ? __ldg(d.bias + n) : 0.f);
-                    crow[n] = d.relu ? fmaxf(x, 0.f) : x;
-                }
+            for (int i = 0; i < 32; ++i) tile[lane * 33 + i] = __uint_as_float(v[i]);
+        }
+        __syncwarp();
+        const int ncols = (EPI == 1) ? 16 : 32;
+        const int n = cb * ncols + (lane % ncols);
+        const bool col_ok = (EPI == 1) ? (2 * n < d.N) : (n < d.N);
+        const float bias = (EPI == 0 && col_ok && d.bias) ? __ldg(d.bias + n) : 0.f;
+        // EPI 1: 16 columns per row -> a warp stores two rows per instruction
+        const int rows_per_it = 32 / ncols;
+        for (int rr = 0; rr < 32; rr += rows_per_it) {
+            const int rl = rr + lane / ncols, r = rbase + rl;
+            if (r < d.M && col_ok) {
+                float x = tile[rl * 33 + (lane % ncols)] + bias;
+                if (EPI == 0 && d.relu) x = fmaxf(x, 0.f);
+                d.C[(long long)(r / d.c_icount) * d.c_outer + (long long)(r % d.c_icount) * d.c_istride + d.c_offset + n] = x;
             }
         }
+        __syncwarp();
     }
     tc_fence_before();
     __syncthreads();
@@ -560,8 +568,9 @@ static int vad_score(VadModel* m, const void* d_audio, int fmt, int64_t n, int64
     const long long n_win = n / kWin;
     if (n_win == 0 || batch == 0) return OSB_OK;
     // chunk the window axis so the activations of a chunk stay around the size of L2
-    long long T = (96ll << 20) / (batch * 9728ll);  // ~9.5 KB of activations per window
-    if (T < 32) T = 32;
+    // windows per chunk ~ 148 SMs x 128 rows: the three GEMM shapes (3W, 2W, W rows) then fill 3 / 2 / 1 whole waves
+    long long T = ((long long)OSB_NUM_SMS * 128 + batch - 1) / batch;
+    if (T < 1) T = 1;
     if (T > n_win) T = n_win;
     const long long W = batch * T;  // windows per chunk
     Scratch scr(st);
