@@ -213,7 +213,7 @@ __device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t& hi, uin
 }
 
 template <int AMODE, int EPI>
-__global__ void __launch_bounds__(256, 1) k_vad_gemm_tc(GemmDesc d, const uint16_t* __restrict__ Bimg, int NT, int n_tiles, int k_chunks) {
+__global__ void __launch_bounds__(512, 1) k_vad_gemm_tc(GemmDesc d, const uint16_t* __restrict__ Bimg, int NT, int n_tiles, int k_chunks) {
     extern __shared__ uint8_t smraw[];
     uint8_t* smb = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smraw) + 1023) & ~(uintptr_t)1023);
     uint8_t* Abuf = smb;                    // [2][hi|lo][128 x 128 B]
@@ -250,20 +250,20 @@ __global__ void __launch_bounds__(256, 1) k_vad_gemm_tc(GemmDesc d, const uint16
     if (tid == 0)
         for (int s = 0; s < kTcNB - 1 && s < steps; ++s) issue_b_load(s);
 
-    const int arow = tid & 127, ahalf = tid >> 7;  // thread -> (row, 32-element half of the 64-wide chunk)
+    const int arow = tid & 127, aq = tid >> 7;  // thread -> (row, 16-element quarter of the 64-wide chunk)
     for (int kc = 0; kc < k_chunks; ++kc) {
         const int ab = kc & 1;
         if (kc >= 2) mbar_wait(&doneA[ab], (uint32_t)(((kc >> 1) - 1) & 1));  // MMAs of chunk kc-2 have drained this buffer
-        {   // stage A(kc): 32 elements per thread -> 4 x 16 B per plane at swizzled positions
-            float v[32];
-            const int r = m0 + arow, k0 = kc * kTcKc + 32 * ahalf;
+        {   // stage A(kc): 16 elements per thread -> 2 x 16 B per plane at swizzled positions
+            float v[16];
+            const int r = m0 + arow, k0 = kc * kTcKc + 16 * aq;
             if (r >= d.M) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] = 0.f;
+                for (int i = 0; i < 16; ++i) v[i] = 0.f;
             } else if (AMODE == 0) {
                 const float* p = reinterpret_cast<const float*>(d.A) + (long long)(r / d.a_icount) * d.a_outer + (long long)(r % d.a_icount) * d.a_istride + k0;
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
+                for (int q = 0; q < 4; ++q) {
                     const float4 t = *reinterpret_cast<const float4*>(p + 4 * q);
                     v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
                 }
@@ -272,22 +272,34 @@ __global__ void __launch_bounds__(256, 1) k_vad_gemm_tc(GemmDesc d, const uint16
                 const int sidx = wq / d.wins_per_stream;
                 const long long win = d.win0 + (wq - sidx * d.wins_per_stream);
                 const long long base = (long long)sidx * d.audio_stride + win * kWin;
+                const int s0 = 128 * f + k0;
+                const int16_t* p16 = reinterpret_cast<const int16_t*>(d.A) + base + s0;
+                if (AMODE == 1 && s0 + 16 <= kWin && (((uintptr_t)p16) & 15) == 0) {
+                    const uint4 w0 = *reinterpret_cast<const uint4*>(p16), w1 = *reinterpret_cast<const uint4*>(p16 + 8);
+                    const uint32_t ws[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    int sidx2 = 128 * f + k0 + i;
-                    sidx2 = sidx2 < kWin ? sidx2 : (2 * kWin - 2 - sidx2);
-                    if (AMODE == 1) v[i] = (float)reinterpret_cast<const int16_t*>(d.A)[base + sidx2] * 3.0517578125e-05f;
-                    else v[i] = reinterpret_cast<const float*>(d.A)[base + sidx2];
+                    for (int i = 0; i < 8; ++i) {
+                        v[2 * i] = (float)(int16_t)(ws[i] & 0xFFFF) * 3.0517578125e-05f;
+                        v[2 * i + 1] = (float)(int16_t)(ws[i] >> 16) * 3.0517578125e-05f;
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        int si = s0 + i;
+                        si = si < kWin ? si : (2 * kWin - 2 - si);
+                        if (AMODE == 1) v[i] = (float)reinterpret_cast<const int16_t*>(d.A)[base + si] * 3.0517578125e-05f;
+                        else v[i] = reinterpret_cast<const float*>(d.A)[base + si];
+                    }
                 }
             }
             uint8_t* hi_row = Abuf + (size_t)ab * kTcABuf + (arow >> 3) * 1024 + (arow & 7) * 128;
             uint8_t* lo_row = hi_row + kTcAPlane;
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
+            for (int c = 0; c < 2; ++c) {
                 uint32_t h[4], l[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) split_bf16x2(v[8 * c + 2 * j], v[8 * c + 2 * j + 1], h[j], l[j]);
-                const int chunk = (4 * ahalf + c) ^ (arow & 7);
+                const int chunk = (2 * aq + c) ^ (arow & 7);
                 *reinterpret_cast<uint4*>(hi_row + chunk * 16) = make_uint4(h[0], h[1], h[2], h[3]);
                 *reinterpret_cast<uint4*>(lo_row + chunk * 16) = make_uint4(l[0], l[1], l[2], l[3]);
             }
@@ -330,7 +342,7 @@ __global__ void __launch_bounds__(256, 1) k_vad_gemm_tc(GemmDesc d, const uint16
     // every global store instruction writes 128 contiguous bytes of one output row
     float* tile = reinterpret_cast<float*>(smb) + warp * (32 * 33);
     const int rbase = m0 + (warp & 3) * 32;
-    for (int cb = warp >> 2; cb < ncb; cb += 2) {
+    for (int cb = warp >> 2; cb < ncb; cb += 4) {
         uint32_t v[32];
         const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(cb * 32);
         asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
@@ -550,7 +562,7 @@ static int launch_gemm_tc(const GemmDesc& d, const VadModel::Tc& L, cudaStream_t
         OSB_CUDA(cudaFuncSetAttribute(k_vad_gemm_tc<AMODE, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem));
         attr_done = true;
     }
-    OSB_LAUNCH((k_vad_gemm_tc<AMODE, EPI>), (d.M + kTcM - 1) / kTcM, 256, kTcSmem, st, d, (const uint16_t*)L.img, L.NT, L.n_tiles, L.k_chunks);
+    OSB_LAUNCH((k_vad_gemm_tc<AMODE, EPI>), (d.M + kTcM - 1) / kTcM, 512, kTcSmem, st, d, (const uint16_t*)L.img, L.NT, L.n_tiles, L.k_chunks);
     OSB_CHECK_LAUNCH();
     return OSB_OK;
 }
