@@ -212,7 +212,10 @@ __global__ void __launch_bounds__(128) k_nr_iir_fwd(const float* __restrict__ A,
     }
 }
 
-// M may alias A (in place): thread (chunk, bin) reads A[t][f] before it writes M[t][f]; no __restrict__ on those two
+// M may alias A (in place): thread (chunk, bin) reads A[t][f] before it writes M[t][f].  Because of that alias the
+// compiler cannot hoist loads over stores, so the loop is software-pipelined by hand: 16 frames of A and Afwd are
+// loaded into registers, then the recurrence + mask for those frames is computed and stored.
+template <int U>
 __global__ void __launch_bounds__(128) k_nr_iir_bwd_mask(const float* A, const float* __restrict__ Afwd, float* M, int F, long long n_rows,
                                                          double b) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -224,13 +227,23 @@ __global__ void __launch_bounds__(128) k_nr_iir_bwd_mask(const float* A, const f
     float* m = M + cc * F * NB + f;
     const double a1 = 1.0 - b;
     double y = (double)af[(long long)(F - 1) * NB];
-#pragma unroll 16
-    for (int t = F - 1; t >= 0; --t) {
-        y = fma(a1, y, b * (double)af[(long long)t * NB]);
-        const float a = s[(long long)t * NB];
-        const float as = (float)y;
-        const float rel = (a - as) / as;  // 0/0 -> NaN on all-zero input, like the reference
-        m[(long long)t * NB] = 1.0f / (1.0f + __expf(-(rel - 2.0f) * 10.0f));
+    for (int t1 = F - 1; t1 >= 0; t1 -= U) {
+        float xa[U], xf[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int t = t1 - u;
+            xa[u] = t >= 0 ? s[(long long)t * NB] : 0.f;
+            xf[u] = t >= 0 ? af[(long long)t * NB] : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int t = t1 - u;
+            if (t < 0) break;
+            y = fma(a1, y, b * (double)xf[u]);
+            const float as = (float)y;
+            const float rel = (xa[u] - as) / as;  // 0/0 -> NaN on all-zero input, like the reference
+            m[(long long)t * NB] = 1.0f / (1.0f + __expf(-(rel - 2.0f) * 10.0f));
+        }
     }
 }
 
@@ -480,7 +493,9 @@ int launch_spectral_gate(const void* d_audio, int fmt, long long n, long long ba
         const unsigned gi = (unsigned)((n_rows * NB + 127) / 128);
         OSB_LAUNCH(k_nr_iir_fwd, gi, 128, 0, st, A, Afwd, g.F, n_rows, b);
         OSB_CHECK_LAUNCH();
-        OSB_LAUNCH(k_nr_iir_bwd_mask, gi, 128, 0, st, A, Afwd, M, g.F, n_rows, b);
+        // few rows: deep register pipelining hides latency; many rows: occupancy does, and a shallower pipeline keeps it high
+        if (n_rows * NB < 160000) OSB_LAUNCH(k_nr_iir_bwd_mask<16>, gi, 128, 0, st, A, Afwd, M, g.F, n_rows, b);
+        else OSB_LAUNCH(k_nr_iir_bwd_mask<4>, gi, 128, 0, st, A, Afwd, M, g.F, n_rows, b);
         OSB_CHECK_LAUNCH();
         if (nft == 16 && nt == 3) OSB_LAUNCH((k_nr_smooth<16, 3>), dim3((g.F + kSmT - 1) / kSmT, (unsigned)n_rows), 256, kSmoothSmem, st, M, Msm, g.F, sp);
         else OSB_LAUNCH((k_nr_smooth<kNfMax, kNtMax>), dim3((g.F + kSmT - 1) / kSmT, (unsigned)n_rows), 256, kSmoothSmem, st, M, Msm, g.F, sp);
