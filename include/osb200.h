@@ -184,6 +184,18 @@ int osb_fx_chain_host(const float* in, int64_t n, int sample_rate, const int* fx
                       void* out, int out_pcm16);
 int osb_voice_blend_host(const float* const* packs, const float* weights, int k, int64_t pack_elems, float* out);
 
+/* ---------------------------------------------------------------- SURVEY 8(f) "next" rows (callers either side of the path)
+ * osb_resample_poly_f32: MultiTrackComposer._resample (src/composer.py:167-173) = resample_poly(f32, up, down) with the
+ *   default zero ('constant') edge; same filter design and accumulation order as osb_resample_poly, float32 in/out.
+ * osb_mix_tracks: MultiTrackComposer._mix_prepared (src/composer.py:175-189): offset-add in track order, clip to [-1,1].
+ * osb_interp_index_f32: wyoming _resample_to_16k (src/wyoming/tts_handler.py:37-44): np.interp on an index grid, f64, -> f32. */
+int osb_resample_poly_f32_dev(const float* d_in, float* d_out, int64_t n_in, int64_t batch, int64_t in_stride, int64_t out_stride, int up,
+                              int down, void* stream);
+int osb_resample_poly_f32_host(const float* in, float* out, int64_t n_in, int up, int down);
+int osb_mix_tracks_host(const float* flat, const int64_t* offsets, const int64_t* lens, const int64_t* starts, int n_tracks, int64_t flat_len,
+                        int64_t total, float* out);
+int osb_interp_index_f32_host(const float* in, int64_t n, float* out, int64_t m);
+
 #ifdef __cplusplus
 }
 #endif

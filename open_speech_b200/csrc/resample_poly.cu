@@ -108,37 +108,80 @@ static int get_filter(int up, int down, bool need_device, const PolyFilter** out
 }
 
 struct PolyArgs {
-    const int16_t* in;
-    int16_t* out;
+    const void* in;
+    void* out;
     const float* h_tf;
     long long n_in, n_out, batch, in_stride, out_stride;
     int up, down, per_phase, n_pre_remove;
 };
 
+// PCM16: int16 in/out, 'line' edge extension, clip + truncate (resample_pcm16, src/streaming.py:55-91)
+// F32  : float32 in/out, zero ('constant') extension, no clip  (MultiTrackComposer._resample, src/composer.py:167-173)
+template <bool PCM16>
 __global__ void __launch_bounds__(256) k_resample_poly(PolyArgs a) {
     const long long total = a.n_out * a.batch;
     const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nthr = (long long)gridDim.x * blockDim.x;
     for (long long g = tid; g < total; g += nthr) {
         const long long c = g / a.n_out, j = g - c * a.n_out;
-        const int16_t* x = a.in + c * a.in_stride;
+        const int16_t* xi16 = reinterpret_cast<const int16_t*>(a.in) + c * a.in_stride;
+        const float* xf = reinterpret_cast<const float*>(a.in) + c * a.in_stride;
         const long long yi = j + a.n_pre_remove;
         const long long t = yi * a.down;
         const long long x_idx = t / a.up;
         const int phase = (int)(t - x_idx * a.up);
         const float* h = a.h_tf + (size_t)phase * a.per_phase;
-        const float x0 = (float)__ldg(x), xl = (float)__ldg(x + a.n_in - 1);
-        const float slope = __fdiv_rn(__fsub_rn(xl, x0), (float)(a.n_in - 1));
+        float x0 = 0.f, xl = 0.f, slope = 0.f;
+        if (PCM16) {
+            x0 = (float)__ldg(xi16);
+            xl = (float)__ldg(xi16 + a.n_in - 1);
+            slope = __fdiv_rn(__fsub_rn(xl, x0), (float)(a.n_in - 1));
+        }
         float acc = 0.0f;
         long long xi = x_idx - a.per_phase + 1;
         for (int k = 0; k < a.per_phase; ++k, ++xi) {
             float xv;
-            if (xi < 0) xv = __fadd_rn(x0, __fmul_rn((float)xi, slope));
-            else if (xi >= a.n_in) xv = __fadd_rn(xl, __fmul_rn((float)(xi - a.n_in + 1), slope));
-            else xv = (float)__ldg(x + xi);
+            if (xi < 0) xv = PCM16 ? __fadd_rn(x0, __fmul_rn((float)xi, slope)) : 0.f;
+            else if (xi >= a.n_in) xv = PCM16 ? __fadd_rn(xl, __fmul_rn((float)(xi - a.n_in + 1), slope)) : 0.f;
+            else xv = PCM16 ? (float)__ldg(xi16 + xi) : __ldg(xf + xi);
             acc = __fadd_rn(acc, __fmul_rn(xv, __ldg(h + k)));
         }
-        acc = fminf(fmaxf(acc, -32768.0f), 32767.0f);
-        a.out[c * a.out_stride + j] = (int16_t)__float2int_rz(acc);
+        if (PCM16) {
+            acc = fminf(fmaxf(acc, -32768.0f), 32767.0f);
+            reinterpret_cast<int16_t*>(a.out)[c * a.out_stride + j] = (int16_t)__float2int_rz(acc);
+        } else {
+            reinterpret_cast<float*>(a.out)[c * a.out_stride + j] = acc;
+        }
+    }
+}
+
+// MultiTrackComposer._mix_prepared (src/composer.py:175-189): mixed[start_k + i] += track_k[i] in track order, then clip
+__global__ void __launch_bounds__(256) k_mix_tracks(const float* __restrict__ flat, const long long* __restrict__ offs,
+                                                    const long long* __restrict__ lens, const long long* __restrict__ starts, int n_tracks,
+                                                    long long total, float* __restrict__ out) {
+    for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < total; j += (long long)gridDim.x * blockDim.x) {
+        float acc = 0.f;
+        for (int k = 0; k < n_tracks; ++k) {
+            const long long i = j - starts[k];
+            if (i >= 0 && i < lens[k]) acc = __fadd_rn(acc, flat[offs[k] + i]);
+        }
+        out[j] = fminf(fmaxf(acc, -1.0f), 1.0f);
+    }
+}
+
+// _resample_to_16k (src/wyoming/tts_handler.py:37-44): np.interp(linspace(0, n-1, m), arange(n), audio) in f64 -> f32
+__global__ void __launch_bounds__(256) k_interp_index_f32(const float* __restrict__ x, long long n, long long m, double step, float* __restrict__ out) {
+    for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < m; j += (long long)gridDim.x * blockDim.x) {
+        const double pos = (j == m - 1 && m > 1) ? (double)(n - 1) : __dmul_rn((double)j, step);
+        long long i = (long long)pos;
+        if (i > n - 1) i = n - 1;
+        double y;
+        if (i >= n - 1 || (double)i == pos) y = (double)x[i];
+        else {
+            const double f0 = (double)x[i], f1 = (double)x[i + 1];
+            const double slope = __ddiv_rn(__dsub_rn(f1, f0), 1.0);
+            y = __dadd_rn(__dmul_rn(slope, __dsub_rn(pos, (double)i)), f0);
+        }
+        out[j] = (float)y;
     }
 }
 
@@ -188,9 +231,91 @@ int osb_resample_poly_dev(const int16_t* d_in, int16_t* d_out, int64_t n_in, int
     a.in = d_in; a.out = d_out; a.h_tf = f->d_h_tf;
     a.n_in = n_in; a.n_out = n_out; a.batch = batch; a.in_stride = in_stride; a.out_stride = out_stride;
     a.up = up; a.down = down; a.per_phase = f->per_phase; a.n_pre_remove = f->n_pre_remove;
-    OSB_LAUNCH(k_resample_poly, grid_for((size_t)(n_out * batch), 256), 256, 0, (cudaStream_t)stream, a);
+    OSB_LAUNCH(k_resample_poly<true>, grid_for((size_t)(n_out * batch), 256), 256, 0, (cudaStream_t)stream, a);
     OSB_CHECK_LAUNCH();
     return OSB_OK;
+}
+
+int osb_resample_poly_f32_dev(const float* d_in, float* d_out, int64_t n_in, int64_t batch, int64_t in_stride, int64_t out_stride, int up,
+                              int down, void* stream) {
+    int rc = ensure_init();
+    if (rc) return rc;
+    OSB_REQUIRE(up >= 1 && down >= 1 && !(up == 1 && down == 1), "up/down must be >= 1 and not both 1 (divide by the gcd first)");
+    OSB_REQUIRE(up < (1 << 20) && down < (1 << 20), "ratio too large");
+    OSB_REQUIRE(n_in >= 0 && batch >= 0, "negative size");
+    if (n_in == 0 || batch == 0) return OSB_OK;
+    const long long n_out = (n_in * up + down - 1) / down;
+    OSB_REQUIRE(d_in && d_out && in_stride >= n_in && out_stride >= n_out, "bad buffers/strides");
+    const PolyFilter* f;
+    if ((rc = get_filter(up, down, true, &f))) return rc;
+    long long len_h = (long long)f->n_pre_pad + f->n_taps, n_post = 0;
+    while (output_len(len_h + n_post, n_in, up, down) < n_out + f->n_pre_remove) ++n_post;
+    long long padded = len_h + n_post;
+    padded += (up - padded % up) % up;
+    if (padded / up > f->per_phase) {
+        set_error("unsupported: filter needs %lld taps per phase (> %d)", padded / up, f->per_phase);
+        return OSB_ERR_UNSUPPORTED;
+    }
+    PolyArgs a;
+    a.in = d_in; a.out = d_out; a.h_tf = f->d_h_tf;
+    a.n_in = n_in; a.n_out = n_out; a.batch = batch; a.in_stride = in_stride; a.out_stride = out_stride;
+    a.up = up; a.down = down; a.per_phase = f->per_phase; a.n_pre_remove = f->n_pre_remove;
+    OSB_LAUNCH(k_resample_poly<false>, grid_for((size_t)(n_out * batch), 256), 256, 0, (cudaStream_t)stream, a);
+    OSB_CHECK_LAUNCH();
+    return OSB_OK;
+}
+
+int osb_resample_poly_f32_host(const float* in, float* out, int64_t n_in, int up, int down) {
+    HostWs& ws = host_ws();
+    int rc = ws.prepare();
+    if (rc) return rc;
+    if (n_in <= 0) return OSB_OK;
+    OSB_REQUIRE(up >= 1 && down >= 1, "up/down must be >= 1");
+    const long long n_out = (n_in * up + down - 1) / down;
+    void *di, *dout;
+    if ((rc = ws.dev_buf(0, (size_t)n_in * 4, &di)) || (rc = ws.dev_buf(1, (size_t)n_out * 4, &dout))) return rc;
+    if ((rc = ws.h2d(di, in, (size_t)n_in * 4))) return rc;
+    if ((rc = osb_resample_poly_f32_dev((const float*)di, (float*)dout, n_in, 1, n_in, n_out, up, down, ws.stream))) return rc;
+    return ws.d2h(out, dout, (size_t)n_out * 4);
+}
+
+int osb_mix_tracks_host(const float* flat, const int64_t* offsets, const int64_t* lens, const int64_t* starts, int n_tracks, int64_t flat_len,
+                        int64_t total, float* out) {
+    HostWs& ws = host_ws();
+    int rc = ws.prepare();
+    if (rc) return rc;
+    OSB_REQUIRE(n_tracks >= 0 && total >= 0 && flat_len >= 0, "bad sizes");
+    if (total == 0) return OSB_OK;
+    OSB_REQUIRE(out && (n_tracks == 0 || (flat && offsets && lens && starts)), "null buffer");
+    void *df, *dout, *dm;
+    if ((rc = ws.dev_buf(0, (size_t)flat_len * 4 + 16, &df)) || (rc = ws.dev_buf(1, (size_t)total * 4, &dout)) ||
+        (rc = ws.dev_buf(2, (size_t)n_tracks * 24 + 64, &dm))) return rc;
+    if ((rc = ws.h2d(df, flat, (size_t)flat_len * 4))) return rc;
+    long long* m = (long long*)dm;
+    OSB_CUDA(cudaMemcpyAsync(m, offsets, (size_t)n_tracks * 8, cudaMemcpyHostToDevice, ws.stream));
+    OSB_CUDA(cudaMemcpyAsync(m + n_tracks, lens, (size_t)n_tracks * 8, cudaMemcpyHostToDevice, ws.stream));
+    OSB_CUDA(cudaMemcpyAsync(m + 2 * n_tracks, starts, (size_t)n_tracks * 8, cudaMemcpyHostToDevice, ws.stream));
+    OSB_CUDA(cudaStreamSynchronize(ws.stream));  // the three small arrays are caller stack/heap memory
+    OSB_LAUNCH(k_mix_tracks, grid_for((size_t)total, 256), 256, 0, ws.stream, (const float*)df, m, m + n_tracks, m + 2 * n_tracks, n_tracks,
+               (long long)total, (float*)dout);
+    OSB_CHECK_LAUNCH();
+    return ws.d2h(out, dout, (size_t)total * 4);
+}
+
+int osb_interp_index_f32_host(const float* in, int64_t n, float* out, int64_t m) {
+    HostWs& ws = host_ws();
+    int rc = ws.prepare();
+    if (rc) return rc;
+    OSB_REQUIRE(n >= 0 && m >= 0, "bad sizes");
+    if (m == 0) return OSB_OK;
+    OSB_REQUIRE(n >= 1 && in && out, "need at least one input sample");
+    void *di, *dout;
+    if ((rc = ws.dev_buf(0, (size_t)n * 4, &di)) || (rc = ws.dev_buf(1, (size_t)m * 4, &dout))) return rc;
+    if ((rc = ws.h2d(di, in, (size_t)n * 4))) return rc;
+    const double step = m > 1 ? (double)(n - 1) / (double)(m - 1) : 0.0;  // np.linspace: delta / div
+    OSB_LAUNCH(k_interp_index_f32, grid_for((size_t)m, 256), 256, 0, ws.stream, (const float*)di, (long long)n, (long long)m, step, (float*)dout);
+    OSB_CHECK_LAUNCH();
+    return ws.d2h(out, dout, (size_t)m * 4);
 }
 
 int osb_resample_poly_host(const int16_t* in, int16_t* out, int64_t n_in, int64_t batch, int64_t in_stride,

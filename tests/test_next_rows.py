@@ -1,0 +1,62 @@
+"""composer mix path and the Wyoming float resampler -- oracle pin (CPU) and GPU parity."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import next_rows as nx
+
+
+@pytest.fixture(scope="module")
+def gnext():
+    return dict(np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_vectors_next.npz")))
+
+
+def _tracks(g):
+    a, b = g["comp_in_24k"], g["comp_track_b"]
+    return [{"samples": a, "offset_s": 0.0}, {"samples": b, "offset_s": 0.25}, {"samples": a[:5000] * 2.0, "offset_s": 0.9}]
+
+
+def test_oracle_matches_reference_vectors(gnext):
+    a = gnext["comp_in_24k"]
+    for dst in (16000, 48000, 22050, 8000):
+        assert np.array_equal(nx.composer_resample(a, 24000, dst), gnext[f"comp_resample_24k_{dst}"])
+    assert np.array_equal(nx.mix_prepared(_tracks(gnext), 24000), gnext["comp_mix"])
+    assert np.array_equal(nx.resample_to_16k(a, 24000), gnext["wy_24k_to_16k"])
+    assert np.array_equal(nx.resample_to_16k(a[:7777], 22050), gnext["wy_22050_to_16k"])
+    assert np.array_equal(nx.resample_to_16k(a, 48000), gnext["wy_48k_to_16k"])
+
+
+@pytest.mark.gpu
+def test_composer_gpu_bit_exact(gpu, gnext):
+    from open_speech_b200 import composer
+
+    a = gnext["comp_in_24k"]
+    for dst in (16000, 48000, 22050, 8000):
+        got = composer.resample(a, 24000, dst)
+        assert got.dtype == np.float32 and np.array_equal(got, gnext[f"comp_resample_24k_{dst}"]), dst
+    assert composer.resample(a, 24000, 24000) is a
+    mixed = composer.mix_prepared(_tracks(gnext), 24000)
+    assert np.array_equal(mixed, gnext["comp_mix"])
+    assert np.array_equal(composer.float_to_int16(mixed), gnext["comp_int16"])
+    # the reference's own unit tests (tests/test_composer_unit.py:13-41)
+    pulse = np.zeros(100, dtype=np.float32)
+    pulse[0] = 1.0
+    m = composer.mix_prepared([{"samples": pulse, "offset_s": 0.1}], sample_rate=1000)
+    assert len(m) == 200 and m[100] == 1.0 and np.allclose(m[:100], 0.0)
+    t = np.arange(2400) / 24000
+    s = (0.2 * np.sin(2 * np.pi * 440 * t)).astype(np.float32)
+    m = composer.mix_prepared([{"samples": s, "offset_s": 0.0}, {"samples": s, "offset_s": 0.0}], 24000)
+    assert np.isclose(np.max(np.abs(m)), np.max(np.abs(s)) * 2, rtol=0.05)
+    assert len(composer.mix_prepared([], 24000)) == 0
+
+
+@pytest.mark.gpu
+def test_wyoming_resample_gpu_bit_exact(gpu, gnext):
+    from open_speech_b200.wyoming_audio import _resample_to_16k
+
+    a = gnext["comp_in_24k"]
+    assert np.array_equal(_resample_to_16k(a, 24000), gnext["wy_24k_to_16k"])
+    assert np.array_equal(_resample_to_16k(a[:7777], 22050), gnext["wy_22050_to_16k"])
+    assert np.array_equal(_resample_to_16k(a, 48000), gnext["wy_48k_to_16k"])
+    assert _resample_to_16k(a, 16000) is a
