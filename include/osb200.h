@@ -189,6 +189,11 @@ int osb_voice_blend_host(const float* const* packs, const float* weights, int k,
  *   default zero ('constant') edge; same filter design and accumulation order as osb_resample_poly, float32 in/out.
  * osb_mix_tracks: MultiTrackComposer._mix_prepared (src/composer.py:175-189): offset-add in track order, clip to [-1,1].
  * osb_interp_index_f32: wyoming _resample_to_16k (src/wyoming/tts_handler.py:37-44): np.interp on an index grid, f64, -> f32. */
+/* osb_vad_extract_speech: wyoming _extract_speech_segments (src/wyoming/stt_handler.py:43-115): [polyphase to 16 kHz] -> VAD score ->
+ *   segments -> gather of the speech spans at the ORIGINAL rate, all on the device; only the speech samples come back.
+ *   *out_n == 0 means "no usable segment": the caller returns the original audio, as the reference does. */
+int osb_vad_extract_speech_host(void* handle, const int16_t* pcm, int64_t n, int rate, float threshold, int min_speech_ms, int silence_ms,
+                                int16_t* out, int64_t* out_n, int* n_segments);
 int osb_resample_poly_f32_dev(const float* d_in, float* d_out, int64_t n_in, int64_t batch, int64_t in_stride, int64_t out_stride, int up,
                               int down, void* stream);
 int osb_resample_poly_f32_host(const float* in, float* out, int64_t n_in, int up, int down);

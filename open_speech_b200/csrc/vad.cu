@@ -501,6 +501,34 @@ __global__ void __launch_bounds__(32) k_vad_segment(const float* __restrict__ pr
     }
 }
 
+// ------------------------------------------------------------------ VAD-gated assembly
+// _extract_speech_segments (src/wyoming/stt_handler.py:43-115): keep [start_ms, end_ms) * (rate // 1000) of every segment,
+// at the ORIGINAL rate, concatenated.  plan: one thread turns the segment list into (src start, length, dst offset).
+__global__ void k_vad_gather_plan(const int* __restrict__ segs, const int* __restrict__ count, int max_seg, long long n_samples,
+                                  int samples_per_ms, long long* __restrict__ plan /* [max_seg][3] */, long long* __restrict__ total) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const int n = min(*count, max_seg);
+    long long off = 0;
+    for (int i = 0; i < n; ++i) {
+        const long long s = (long long)segs[2 * i] * samples_per_ms;
+        long long e = (long long)segs[2 * i + 1] * samples_per_ms;
+        if (e > n_samples) e = n_samples;
+        const long long len = (s < n_samples && e > s) ? e - s : 0;
+        plan[3 * i] = s; plan[3 * i + 1] = len; plan[3 * i + 2] = off;
+        off += len;
+    }
+    total[0] = off;
+    total[1] = n;
+}
+
+__global__ void __launch_bounds__(256) k_vad_gather(const int16_t* __restrict__ pcm, const long long* __restrict__ plan,
+                                                    const long long* __restrict__ total, int16_t* __restrict__ out) {
+    const int seg = blockIdx.y;
+    if (seg >= (int)total[1]) return;
+    const long long s = plan[3 * seg], len = plan[3 * seg + 1], off = plan[3 * seg + 2];
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (long long)gridDim.x * blockDim.x) out[off + i] = pcm[s + i];
+}
+
 // ------------------------------------------------------------------ host orchestration
 static int upload(float** dst, const std::vector<float>& v) {
     OSB_CUDA(cudaMalloc(dst, v.size() * sizeof(float)));
@@ -784,6 +812,62 @@ int osb_vad_score_host(void* handle, const void* audio, int fmt, int64_t n, floa
         for (long long i = 0; i < n_win; ++i) if (out[i] > mx) mx = out[i];
         *max_prob = mx;
     }
+    return OSB_OK;
+}
+
+int osb_vad_extract_speech_host(void* handle, const int16_t* pcm, int64_t n, int rate, float threshold, int min_speech_ms, int silence_ms,
+                                int16_t* out, int64_t* out_n, int* n_segments) {
+    HostWs& ws = host_ws();
+    int rc = ws.prepare();
+    if (rc) return rc;
+    OSB_REQUIRE(handle && pcm && out && out_n && rate >= 1000, "bad arguments");
+    *out_n = 0;
+    if (n_segments) *n_segments = 0;
+    if (n <= 0) return OSB_OK;
+    const int max_seg = 4096;
+    int up = 1, down = 1;
+    long long n16 = n;
+    if (rate != 16000) {
+        int a = 16000, b = rate;
+        while (b) { const int t = a % b; a = b; b = t; }
+        up = 16000 / a; down = rate / a;
+        n16 = (n * up + down - 1) / down;
+        OSB_REQUIRE(n >= 2, "need at least two samples to resample");
+    }
+    const long long n_win = n16 / kWin;
+    void *d_in, *d_16k, *d_misc, *d_out;
+    const size_t misc = 2 * kHid * 4 + (size_t)(n_win + 1) * 4 + (size_t)max_seg * 8 + 64 + (size_t)max_seg * 24 + 64;
+    if ((rc = ws.dev_buf(0, (size_t)n * 2 + 16, &d_in)) || (rc = ws.dev_buf(1, (size_t)n16 * 2 + 16, &d_16k)) ||
+        (rc = ws.dev_buf(2, misc, &d_misc)) || (rc = ws.dev_buf(3, (size_t)n * 2 + 16, &d_out))) return rc;
+    if ((rc = ws.h2d(d_in, pcm, (size_t)n * 2))) return rc;
+    const int16_t* a16 = (const int16_t*)d_in;
+    if (rate != 16000) {
+        if ((rc = osb_resample_poly_dev((const int16_t*)d_in, (int16_t*)d_16k, n, 1, n, n16, up, down, ws.stream))) return rc;
+        a16 = (const int16_t*)d_16k;
+    }
+    float* d_state = (float*)d_misc;
+    float* d_probs = d_state + 2 * kHid;
+    int32_t* d_segs = (int32_t*)(d_probs + n_win + 1);
+    int32_t* d_cnt = d_segs + (size_t)max_seg * 2;
+    long long* d_plan = (long long*)(((uintptr_t)(d_cnt + 4) + 15) & ~(uintptr_t)15);
+    long long* d_total = d_plan + (size_t)max_seg * 3;
+    OSB_CUDA(cudaMemsetAsync(d_state, 0, 2 * kHid * 4, ws.stream));  // a fresh SileroVAD per call (stt_handler.py:68-71)
+    if ((rc = vad_score(reinterpret_cast<VadModel*>(handle), a16, OSB_FMT_PCM16, n16, 1, n16, d_state, d_probs, n_win > 0 ? n_win : 1, ws.stream))) return rc;
+    if ((rc = vad_segments(d_probs, n_win > 0 ? n_win : 1, n_win, 1, n16, threshold, min_speech_ms, silence_ms, d_segs, d_cnt, max_seg, ws.stream))) return rc;
+    OSB_LAUNCH(k_vad_gather_plan, 1, 32, 0, ws.stream, d_segs, d_cnt, max_seg, (long long)n, rate / 1000, d_plan, d_total);
+    OSB_CHECK_LAUNCH();
+    long long tot[2] = {0, 0};
+    OSB_CUDA(cudaMemcpyAsync(tot, d_total, sizeof(tot), cudaMemcpyDeviceToHost, ws.stream));
+    if ((rc = ws.sync())) return rc;
+    if (n_segments) *n_segments = (int)tot[1];
+    if (tot[1] == 0 || tot[0] == 0) return OSB_OK;  // caller keeps the original audio (stt_handler.py:88-90, :112-115)
+    long long per = (n / (tot[1] > 0 ? tot[1] : 1) / 8 + 255) / 256;
+    if (per < 1) per = 1;
+    if (per > 64) per = 64;
+    OSB_LAUNCH(k_vad_gather, dim3((unsigned)per, (unsigned)tot[1]), 256, 0, ws.stream, (const int16_t*)d_in, d_plan, d_total, (int16_t*)d_out);
+    OSB_CHECK_LAUNCH();
+    if ((rc = ws.d2h(out, d_out, (size_t)tot[0] * 2))) return rc;
+    *out_n = tot[0];
     return OSB_OK;
 }
 

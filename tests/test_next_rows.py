@@ -60,3 +60,39 @@ def test_wyoming_resample_gpu_bit_exact(gpu, gnext):
     assert np.array_equal(_resample_to_16k(a[:7777], 22050), gnext["wy_22050_to_16k"])
     assert np.array_equal(_resample_to_16k(a, 48000), gnext["wy_48k_to_16k"])
     assert _resample_to_16k(a, 16000) is a
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("rate", [16000, 8000, 48000])
+def test_vad_gated_assembly(gpu, rate):
+    """wyoming _extract_speech_segments: resample -> VAD -> segments -> gather at the original rate (8(f) row 4)."""
+    from open_speech_b200 import synth
+    from open_speech_b200.vad.silero import SileroVAD, VadSession
+    from open_speech_b200.streaming import resample_pcm16
+    from open_speech_b200.wyoming_audio import _extract_speech_segments, _pcm_to_wav
+    from oracle import vad as ovad
+
+    sess = VadSession()
+    pcm = synth.clip_pcm16(20.0, rate, seed=500 + rate // 1000)
+    got = np.frombuffer(_extract_speech_segments(pcm.tobytes(), rate, 2, 1, session=sess), np.int16)
+    # the reference's procedure, with the GPU's own 16 kHz audio and segments: the gather must be bit-exact
+    p16 = pcm.tobytes() if rate == 16000 else resample_pcm16(pcm.tobytes(), rate, 16000)
+    segs = SileroVAD(sess).get_speech_segments(p16)
+    spm = rate // 1000
+    parts = [pcm[s.start_ms * spm: min(s.end_ms * spm, len(pcm))] for s in segs if s.start_ms * spm < len(pcm)]
+    want = np.concatenate(parts) if parts else pcm
+    assert len(segs) >= 2 and np.array_equal(got, want)
+    assert 0 < len(got) < len(pcm)
+    # end to end against the oracle network unless a probability sits within tolerance of the threshold
+    probs, _ = ovad.SileroNet().score_stream(np.frombuffer(p16, np.int16).astype(np.float32) / 32768.0)
+    if int((np.abs(probs - 0.5) <= 1e-3).sum()) == 0:
+        osegs = ovad.segments_from_probs(probs, len(p16) // 2)
+        assert [(s.start_ms, s.end_ms) for s in osegs] == [(s.start_ms, s.end_ms) for s in segs]
+    # pass-through cases of the reference
+    assert _extract_speech_segments(b"", rate, 2, 1, session=sess) == b""
+    assert _extract_speech_segments(pcm.tobytes(), rate, 1, 1, session=sess) == pcm.tobytes()
+    assert _extract_speech_segments(pcm.tobytes(), rate, 2, 1, session=None) == pcm.tobytes()
+    silent = np.zeros(rate * 2, np.int16).tobytes()
+    assert _extract_speech_segments(silent, rate, 2, 1, session=sess, threshold=0.99) == silent
+    w = _pcm_to_wav(pcm.tobytes(), rate, 2, 1)
+    assert w[:4] == b"RIFF" and len(w) == 44 + 2 * len(pcm) and int.from_bytes(w[24:28], "little") == rate
