@@ -184,10 +184,10 @@ __global__ void __launch_bounds__(256, 2) k_nr_stft(const void* __restrict__ aud
                 // X_a = (Z[f] + conj Z[N-f])/2 ; X_b = (Z[f] - conj Z[N-f])/(2i)
                 const float ar = (zr + wr) * sc, ai = (zi - wi) * sc, br = (zi + wi) * sc, bi = (wr - zr) * sc;
                 Sa[f] = make_float2(ar, ai);
-                Aa[f] = sqrtf(ar * ar + ai * ai);
+                Aa[f] = __fsqrt_rn(ar * ar + ai * ai);
                 if (has_b) {
                     Sa[NB + f] = make_float2(br, bi);
-                    Aa[NB + f] = sqrtf(br * br + bi * bi);
+                    Aa[NB + f] = __fsqrt_rn(br * br + bi * bi);
                 }
             }
         }
@@ -336,34 +336,39 @@ __global__ void __launch_bounds__(256, 2) k_nr_istft(const float2* __restrict__ 
     __syncthreads();
     for (int pass = 0; pass < 2; ++pass) {
         const int tp0 = j0 - 1 + pass * 16;
-        {   // step 1 of the inverse (conjugate twiddles), reading Z'[k], k = 32*a + b, straight from S*Msm:
-            // Z'[k] = Sa[k] + i Sb[k] (k <= 512), conj(Sa[N-k]) + i conj(Sb[N-k]) (k > 512)
-            const int q = tid >> 5, bb = tid & 31;
+        {   // stage Z'[k] = Xa[k] + i Xb[k] for the 8 frame pairs of this pass, k stored at [k>>5][k&31] (row stride 33):
+            // Xa/Xb are the masked one-sided spectra S*Msm extended by Hermitian symmetry; every S cell is read once, coalesced
+            const int q = tid >> 5, lane = tid & 31;  // warp q owns pair q
             const int ta = tp0 + 2 * q, tb = ta + 1;
             const bool va = ta >= 0 && ta < g.F, vb = tb >= 0 && tb < g.F;
-            cpx v[32];
-#pragma unroll
-            for (int a = 0; a < 32; ++a) {
-                const int k = 32 * a + bb;
-                const int f = k <= 512 ? k : NF - k;
-                const float sgn = k <= 512 ? 1.f : -1.f;
-                float ar = 0.f, ai = 0.f, br = 0.f, bi = 0.f;
-                if (va) {
-                    const float2 s = S[(row0 + ta) * NB + f];
-                    const float m = Msm[(row0 + ta) * NB + f];
-                    ar = s.x * m; ai = s.y * m * sgn;
-                }
-                if (vb) {
-                    const float2 s = S[(row0 + tb) * NB + f];
-                    const float m = Msm[(row0 + tb) * NB + f];
-                    br = s.x * m; bi = s.y * m * sgn;
-                }
-                if (f == 0 || f == 512) { ai = 0.f; bi = 0.f; }  // irfft ignores the imaginary part of DC / Nyquist
-                v[a] = cpx{ar - bi, ai + br};
-            }
-            fft_pow2<32, true>(v);
             float* yr = Y + q * 2 * kYPlane;
             float* yi = yr + kYPlane;
+            const float2* Sa = S + (row0 + ta) * NB;
+            const float* Ma = Msm + (row0 + ta) * NB;
+            for (int f = lane; f < NB; f += 32) {
+                float ar = 0.f, ai = 0.f, br = 0.f, bi = 0.f;
+                if (va) { const float2 sv = Sa[f]; const float m = Ma[f]; ar = sv.x * m; ai = sv.y * m; }
+                if (vb) { const float2 sv = Sa[NB + f]; const float m = Ma[NB + f]; br = sv.x * m; bi = sv.y * m; }
+                if (f == 0 || f == 512) { ai = 0.f; bi = 0.f; }  // irfft ignores the imaginary part of DC / Nyquist
+                const int k0 = (f >> 5) * kYs + (f & 31);
+                yr[k0] = ar - bi;
+                yi[k0] = ai + br;
+                if (f != 0 && f != 512) {  // mirror bin N-f: conj(Xa[f]) + i conj(Xb[f])
+                    const int km = NF - f, k1 = (km >> 5) * kYs + (km & 31);
+                    yr[k1] = ar + bi;
+                    yi[k1] = br - ai;
+                }
+            }
+        }
+        __syncthreads();
+        {   // step 1 of the inverse (conjugate twiddles), in place: thread (q, b) owns column b of pair q
+            const int q = tid >> 5, bb = tid & 31;
+            float* yr = Y + q * 2 * kYPlane;
+            float* yi = yr + kYPlane;
+            cpx v[32];
+#pragma unroll
+            for (int a = 0; a < 32; ++a) v[a] = cpx{yr[a * kYs + bb], yi[a * kYs + bb]};
+            fft_pow2<32, true>(v);
 #pragma unroll
             for (int c = 0; c < 32; ++c) {
                 const int tw = bb * c;
