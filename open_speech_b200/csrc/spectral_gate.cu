@@ -82,6 +82,12 @@ __device__ __forceinline__ float nr_sample(const void* audio, const NrGeom& g, i
     return reinterpret_cast<const float*>(audio)[(long long)clip * g.stride + i];
 }
 
+// |z| through the SFU reciprocal square root (2 ulp); |S| only feeds the smoothed-threshold mask
+__device__ __forceinline__ float fast_mag(float re, float im) {
+    const float p = fmaf(re, re, im * im);
+    return p > 0.f ? p * rsqrtf(p) : 0.f;
+}
+
 // ---------------------------------------------------------------- forward STFT
 // grid (ceil(F/16), n_chunks, batch), 256 threads.  S[((clip*n_chunks+chunk)*F + t)*513 + f]
 constexpr int kStftFrames = 16, kStftXs = NH * (kStftFrames - 1) + NF;  // 4864
@@ -184,10 +190,10 @@ __global__ void __launch_bounds__(256, 2) k_nr_stft(const void* __restrict__ aud
                 // X_a = (Z[f] + conj Z[N-f])/2 ; X_b = (Z[f] - conj Z[N-f])/(2i)
                 const float ar = (zr + wr) * sc, ai = (zi - wi) * sc, br = (zi + wi) * sc, bi = (wr - zr) * sc;
                 Sa[f] = make_float2(ar, ai);
-                Aa[f] = __fsqrt_rn(ar * ar + ai * ai);
+                Aa[f] = fast_mag(ar, ai);
                 if (has_b) {
                     Sa[NB + f] = make_float2(br, bi);
-                    Aa[NB + f] = __fsqrt_rn(br * br + bi * bi);
+                    Aa[NB + f] = fast_mag(br, bi);
                 }
             }
         }
@@ -274,7 +280,7 @@ __global__ void __launch_bounds__(256, 2) k_nr_smooth(const float* __restrict__ 
             const int t = t0 - NTT + k;
             w[k] = (t >= 0 && t < F) ? M[base + (long long)t * NB + f] : 0.f;
         }
-#pragma unroll 4
+#pragma unroll
         for (int r = 0; r < kSmT; ++r) {
             const int t = t0 + r + NTT;  // newest frame entering the window
             w[ntap - 1] = (t < F) ? M[base + (long long)t * NB + f] : 0.f;

@@ -121,3 +121,18 @@ def test_large_decode_roundtrip_property(gpu):
         assert np.array_equal(d1, d2)
         tab = codec.ulaw2lin_table() if law == gpu.FMT_ULAW else codec.alaw2lin_table()
         assert np.array_equal(d1, tab[b])
+
+
+def test_realtime_tick_cuda_graph(gpu):
+    """The captured-graph tick (H2D + kernel + D2H in one launch) gives the same bytes as the oracle."""
+    import torch
+    from open_speech_b200 import synth
+    from open_speech_b200.batch import RealtimeTickGraph
+
+    ticks = synth.ulaw_streams(256, 4)
+    rg = RealtimeTickGraph(256)
+    for t in range(4):
+        rg.host_in.copy_(torch.from_numpy(np.ascontiguousarray(ticks[t])))
+        out = rg.run().numpy()
+        for s in (0, 7, 255):
+            assert out[s].tobytes() == codec.decode_audio_to_pcm16(ticks[t, s].tobytes(), "g711_ulaw", 16000)
