@@ -130,7 +130,7 @@ OSB_HD void dft25(cpx (&v)[25]) {
 
 // ---------------------------------------------------------------- 400-point complex FFT (25 x 16 four-step)
 // Two real 400-sample frames A,B are packed as z = w*(A + iB).  n = 16*n1 + n2, k = k1 + 25*k2:
-//   step1(n2): 25-point DFT over n1, times W400^(n2*k1)      -> Y[k1][n2]
+//   step1(n2): 25-point DFT over n1, times W400^(n2*k1)      -> Y[k1][n2]   (twc/tws hold W400^(n2*k1) at [k1*16 + n2])
 //   step2(k1): 16-point FFT over n2                          -> Z[k1 + 25*k2] stored at [k1][k2]
 // Y/Z live in two float planes [25][17] (row padded to 17 so step-2 rows hit distinct banks).
 constexpr int kF400Stride = 17, kF400Plane = 25 * 17;
@@ -147,7 +147,7 @@ OSB_HD void fft400_step1(const float* xa, const float* xb, const float* win, con
     dft25(v);
 #pragma unroll
     for (int k1 = 0; k1 < 25; ++k1) {
-        const int t = n2 * k1;  // < 400
+        const int t = k1 * 16 + n2;  // table laid out [k1][n2]
         const cpx y = cmul(v[k1], cpx{twc[t], -tws[t]});
         Yre[k1 * kF400Stride + n2] = y.x;
         Yim[k1 * kF400Stride + n2] = y.y;

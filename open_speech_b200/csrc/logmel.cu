@@ -82,8 +82,10 @@ static int get_mel(int n_mels, bool need_device, const MelTables** out) {
             const double pi = 3.14159265358979323846;
             for (int i = 0; i < 400; ++i) {
                 consts[i] = (float)(0.5 - 0.5 * std::cos(2.0 * pi * i / 400.0));  // np.hanning(401)[:-1] -> f32
-                consts[400 + i] = (float)std::cos(2.0 * pi * i / 400.0);
-                consts[800 + i] = (float)std::sin(2.0 * pi * i / 400.0);
+                // four-step twiddles W400^(n2*k1) stored as [k1][n2] (25 x 16): conflict-free per-lane reads
+                const int k1 = i / 16, n2 = i % 16;
+                consts[400 + i] = (float)std::cos(2.0 * pi * (double)(n2 * k1) / 400.0);
+                consts[800 + i] = (float)std::sin(2.0 * pi * (double)(n2 * k1) / 400.0);
             }
             std::vector<int> start(n_mels), len(n_mels), off(n_mels);
             std::vector<float> w;

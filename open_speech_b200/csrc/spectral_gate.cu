@@ -56,8 +56,10 @@ static int get_nr_tables(const float** out) {
         for (int i = 0; i < NF; ++i) {
             w[i] = 0.5 - 0.5 * std::cos(2.0 * pi * i / NF);  // get_window('hann', 1024) (periodic)
             h[i] = (float)w[i];
-            h[NF + i] = (float)std::cos(2.0 * pi * i / NF);
-            h[2 * NF + i] = (float)std::sin(2.0 * pi * i / NF);
+            // four-step twiddles W1024^(n2*k1) stored as [k1][n2]: a warp (n2 = lane) reads 32 consecutive words
+            const int k1 = i >> 5, n2 = i & 31;
+            h[NF + i] = (float)std::cos(2.0 * pi * (double)(n2 * k1) / NF);
+            h[2 * NF + i] = (float)std::sin(2.0 * pi * (double)(n2 * k1) / NF);
         }
         for (int r = 0; r < NH; ++r) {
             // istft: x *= win.sum() (=512); x /= sum_t win^2 ; our inverse FFT is unnormalised (x 1/1024)
@@ -149,7 +151,7 @@ __global__ void __launch_bounds__(256, 2) k_nr_stft(const void* __restrict__ aud
         float* yi = yr + kYPlane;
 #pragma unroll
         for (int k1 = 0; k1 < 32; ++k1) {
-            const int tw = n2 * k1;  // < 1024
+            const int tw = k1 * 32 + n2;
             const cpx y = cmul(v[k1], cpx{twc[tw], -tws[tw]});
             yr[k1 * kYs + n2] = y.x;
             yi[k1 * kYs + n2] = y.y;
@@ -377,7 +379,7 @@ __global__ void __launch_bounds__(256, 2) k_nr_istft(const float2* __restrict__ 
             fft_pow2<32, true>(v);
 #pragma unroll
             for (int c = 0; c < 32; ++c) {
-                const int tw = bb * c;
+                const int tw = c * 32 + bb;
                 const cpx y = cmul(v[c], cpx{twc[tw], tws[tw]});
                 yr[c * kYs + bb] = y.x;
                 yi[c * kYs + bb] = y.y;

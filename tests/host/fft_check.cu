@@ -39,7 +39,7 @@ static int check400() {
     for (int i = 0; i < 400; ++i) {
         xa[i] = rand() / (float)RAND_MAX - 0.5f; xb[i] = rand() / (float)RAND_MAX - 0.5f;
         win[i] = (float)(0.5 - 0.5 * cos(2 * M_PI * i / 400));
-        twc[i] = (float)cos(2 * M_PI * i / 400); tws[i] = (float)sin(2 * M_PI * i / 400);
+        twc[i] = (float)cos(2 * M_PI * ((i % 16) * (i / 16)) / 400); tws[i] = (float)sin(2 * M_PI * ((i % 16) * (i / 16)) / 400);
     }
     for (int n2 = 0; n2 < 16; ++n2) fft400_step1(xa, xb, win, twc, tws, n2, Yre, Yim);
     for (int k1 = 0; k1 < 25; ++k1) fft400_step2(k1, Yre, Yim);
