@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(128) k_nr_iir_fwd(const float* __restrict__ A,
     float* o = Afwd + cc * F * NB + f;
     const double a1 = 1.0 - b;
     double y = (double)s[0];  // lfilter_zi start: y[-1] = x[0]
-#pragma unroll 16
+#pragma unroll 32
     for (int t = 0; t < F; ++t) {
         y = fma(a1, y, b * (double)s[(long long)t * NB]);
         o[(long long)t * NB] = (float)y;
@@ -508,7 +508,7 @@ int launch_spectral_gate(const void* d_audio, int fmt, long long n, long long ba
         OSB_CHECK_LAUNCH();
         // few rows: deep register pipelining hides latency; many rows: occupancy does, and a shallower pipeline keeps it high
         if (n_rows * NB < 160000) OSB_LAUNCH(k_nr_iir_bwd_mask<16>, gi, 128, 0, st, A, Afwd, M, g.F, n_rows, b);
-        else OSB_LAUNCH(k_nr_iir_bwd_mask<4>, gi, 128, 0, st, A, Afwd, M, g.F, n_rows, b);
+        else OSB_LAUNCH(k_nr_iir_bwd_mask<8>, gi, 128, 0, st, A, Afwd, M, g.F, n_rows, b);
         OSB_CHECK_LAUNCH();
         if (nft == 16 && nt == 3) OSB_LAUNCH((k_nr_smooth<16, 3>), dim3((g.F + kSmT - 1) / kSmT, (unsigned)n_rows), 256, kSmoothSmem, st, M, Msm, g.F, sp);
         else OSB_LAUNCH((k_nr_smooth<kNfMax, kNtMax>), dim3((g.F + kSmT - 1) / kSmT, (unsigned)n_rows), 256, kSmoothSmem, st, M, Msm, g.F, sp);
