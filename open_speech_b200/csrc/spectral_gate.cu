@@ -11,8 +11,10 @@
 // 1e-4 budget) and the one-pole recurrences keep a float64 state.
 //
 // Kernels: k_nr_stft (two real frames per complex 32x32 four-step FFT, samples staged once per 16 frames)
-//          k_nr_iir_fwd / k_nr_iir_bwd_mask (one thread per (chunk, bin), sequential in time, coalesced over bins)
-//          k_nr_smooth (separable 33x7 stencil in shared memory)
+//                     + per-tile aggregates of the time smoothing
+//          k_nr_carry (chains the aggregates into the filtfilt state entering every 16-frame tile)
+//          k_nr_mask (per 32-frame tile: forward/backward one-pole from the carried state, sigmoid mask, separable
+//                     33x7 smoothing; |S| read once, smoothed mask written once)
 //          k_nr_istft (32 frames -> 29 hop blocks per CTA, overlap-add in shared memory, one store per sample)
 #include <cmath>
 #include <map>
@@ -93,15 +95,17 @@ __device__ __forceinline__ float fast_mag(float re, float im) {
 // ---------------------------------------------------------------- forward STFT
 // grid (ceil(F/16), n_chunks, batch), 256 threads.  S[((clip*n_chunks+chunk)*F + t)*513 + f]
 constexpr int kStftFrames = 16, kStftXs = NH * (kStftFrames - 1) + NF;  // 4864
+constexpr int kStftLow = (kStftXs + 3 * NF) > kStftFrames * NB ? (kStftXs + 3 * NF) : kStftFrames * NB;  // 8208 floats
 
 __global__ void __launch_bounds__(256, 2) k_nr_stft(const void* __restrict__ audio, NrGeom g, const float* __restrict__ tabs,
-                                                    float2* __restrict__ S, float* __restrict__ A) {
+                                                    float2* __restrict__ S, float* __restrict__ A, float2* __restrict__ PR, double b) {
     extern __shared__ __align__(16) float sm[];
     float* xs = sm;                 // [4864]
     float* win = xs + kStftXs;      // [1024]
     float* twc = win + NF;          // [1024]
     float* tws = twc + NF;          // [1024]
-    float* Y = tws + NF;            // [8][2][32*33]
+    float* Amat = sm;               // [16][513] magnitudes of this tile; aliases xs/win/tw, which are dead after step 1
+    float* Y = sm + kStftLow;       // [8][2][32*33]
     const int tid = threadIdx.x, t0 = blockIdx.x * kStftFrames, chunk = blockIdx.y, clip = blockIdx.z;
     for (int i = tid; i < 3 * NF; i += 256) win[i] = tabs[i];
     const long long p0 = (long long)NH * t0 - NF / 2;
@@ -191,135 +195,287 @@ __global__ void __launch_bounds__(256, 2) k_nr_stft(const void* __restrict__ aud
                 const float zr = yr[a0], zi = yi[a0], wr = yr[a1], wi = yi[a1];
                 // X_a = (Z[f] + conj Z[N-f])/2 ; X_b = (Z[f] - conj Z[N-f])/(2i)
                 const float ar = (zr + wr) * sc, ai = (zi - wi) * sc, br = (zi + wi) * sc, bi = (wr - zr) * sc;
+                const float ma = fast_mag(ar, ai), mb = fast_mag(br, bi);
                 Sa[f] = make_float2(ar, ai);
-                Aa[f] = fast_mag(ar, ai);
+                Aa[f] = ma;
+                Amat[(2 * q) * NB + f] = ma;
                 if (has_b) {
                     Sa[NB + f] = make_float2(br, bi);
-                    Aa[NB + f] = fast_mag(br, bi);
+                    Aa[NB + f] = mb;
+                    Amat[(2 * q + 1) * NB + f] = mb;
                 }
             }
         }
     }
-}
-
-// ---------------------------------------------------------------- time smoothing (filtfilt) + sigmoid mask
-// one thread per (chunk, bin), sequential over frames, coalesced across bins; f64 state.
-__global__ void __launch_bounds__(128) k_nr_iir_fwd(const float* __restrict__ A, float* __restrict__ Afwd, int F, long long n_rows, double b) {
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= n_rows * NB) return;
-    const long long cc = idx / NB;
-    const int f = (int)(idx - cc * NB);
-    const float* s = A + cc * F * NB + f;
-    float* o = Afwd + cc * F * NB + f;
-    const double a1 = 1.0 - b;
-    double y = (double)s[0];  // lfilter_zi start: y[-1] = x[0]
-#pragma unroll 32
-    for (int t = 0; t < F; ++t) {
-        y = fma(a1, y, b * (double)s[(long long)t * NB]);
-        o[(long long)t * NB] = (float)y;
-    }
-}
-
-// M may alias A (in place): thread (chunk, bin) reads A[t][f] before it writes M[t][f].  Because of that alias the
-// compiler cannot hoist loads over stores, so the loop is software-pipelined by hand: 16 frames of A and Afwd are
-// loaded into registers, then the recurrence + mask for those frames is computed and stored.
-template <int U>
-__global__ void __launch_bounds__(128) k_nr_iir_bwd_mask(const float* A, const float* __restrict__ Afwd, float* M, int F, long long n_rows,
-                                                         double b) {
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= n_rows * NB) return;
-    const long long cc = idx / NB;
-    const int f = (int)(idx - cc * NB);
-    const float* s = A + cc * F * NB + f;
-    const float* af = Afwd + cc * F * NB + f;
-    float* m = M + cc * F * NB + f;
-    const double a1 = 1.0 - b;
-    double y = (double)af[(long long)(F - 1) * NB];
-    for (int t1 = F - 1; t1 >= 0; t1 -= U) {
-        float xa[U], xf[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int t = t1 - u;
-            xa[u] = t >= 0 ? s[(long long)t * NB] : 0.f;
-            xf[u] = t >= 0 ? af[(long long)t * NB] : 0.f;
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int t = t1 - u;
-            if (t < 0) break;
-            y = fma(a1, y, b * (double)xf[u]);
-            const float as = (float)y;
-            const float rel = (xa[u] - as) / as;  // 0/0 -> NaN on all-zero input, like the reference
-            m[(long long)t * NB] = 1.0f / (1.0f + __expf(-(rel - 2.0f) * 10.0f));
+    __syncthreads();
+    // tile aggregates of the time smoothing (see k_nr_carry): with lf[k] the one-pole response of this tile alone,
+    //   P = lf[last]                      (what the tile adds to the forward state)
+    //   R = sum_k b a^(k - first) lf[k]   (what the tile's own forward response adds to the backward state)
+    {
+        const int L = min(kStftFrames, g.F - t0);
+        const double a = 1.0 - b;
+        for (int f = tid; f < NB; f += 256) {
+            double lf = 0.0, R = 0.0, bpw = b;
+            for (int k = 0; k < L; ++k) {
+                lf = fma(a, lf, b * (double)Amat[k * NB + f]);
+                R = fma(bpw, lf, R);
+                bpw *= a;
+            }
+            PR[((row0 / g.F) * gridDim.x + blockIdx.x) * NB + f] = make_float2((float)lf, (float)R);
         }
     }
 }
 
-// ---------------------------------------------------------------- 2-D mask smoothing (fftconvolve 'same')
-// CTA = 32 frames x all 513 bins.  Time taps first, straight from global memory with a sliding register
-// window (coalesced over bins), result into shared memory; then the 2*nf+1 frequency taps with 4 outputs per
-// thread (for nf = 16: 9 LDS.128 feed 132 FMA).  grid (ceil(F/32), n_rows)
+// ---------------------------------------------------------------- time smoothing (filtfilt) + sigmoid mask + 2-D smoothing
+// filtfilt([b],[1,b-1], A, padtype=None) is a forward one-pole pass started at y[-1] = x[0] followed by a backward
+// one-pole pass over the forward output started at y[F] = fwd[F-1].  Both passes are linear, so the time axis is
+// tiled: k_nr_stft leaves per-tile aggregates (P, R), k_nr_carry chains them into the state entering every tile
+// (forward: Cf = fwd[first-1]; backward: Cb = bwd[last+1]), and k_nr_mask redoes the two recurrences inside a tile
+// from those states.  |S| is then read once and the smoothed mask written once, instead of three full passes.
+//
+//   fwd[k] = a^(k-first+1) Cf + lf[k]
+//   Cf'    = a^L Cf + P
+//   Cb'    = bwd[first] = a^L Cb + Cf b a (1 - a^2L)/(1 - a^2) + R
+// one thread per (row, bin); rows = (clip, chunk); coalesced across bins; f64 state.
+__global__ void __launch_bounds__(128) k_nr_carry(const float* __restrict__ A, const float2* __restrict__ PR, float* __restrict__ CF,
+                                                  float* __restrict__ CB, int F, int NT, long long n_rows, double b) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_rows * NB) return;
+    const long long row = idx / NB;
+    const int f = (int)(idx - row * NB);
+    const double a = 1.0 - b;
+    const int Ll = F - kStftFrames * (NT - 1);  // frames in the last tile
+    const double aL = pow(a, (double)kStftFrames), aLl = pow(a, (double)Ll);
+    const double gs = b * a / (1.0 - a * a);
+    const double GL = gs * (1.0 - aL * aL), GLl = gs * (1.0 - aLl * aLl);
+    const float2* pr = PR + row * NT * NB + f;
+    float* cfp = CF + row * NT * NB + f;
+    float* cbp = CB + row * NT * NB + f;
+    double cf = (double)A[row * F * NB + f];  // lfilter_zi start: y[-1] = x[0]
+#pragma unroll 8
+    for (int i = 0; i < NT - 1; ++i) {
+        cfp[(long long)i * NB] = (float)cf;
+        cf = fma(aL, cf, (double)pr[(long long)i * NB].x);
+    }
+    cfp[(long long)(NT - 1) * NB] = (float)cf;
+    const double cf_last = cf;
+    cf = fma(aLl, cf, (double)pr[(long long)(NT - 1) * NB].x);  // fwd[F-1]
+    double cb = cf;                                             // backward pass starts at y[F] = fwd[F-1]
+    cbp[(long long)(NT - 1) * NB] = (float)cb;
+    cb = fma(aLl, cb, fma(cf_last, GLl, (double)pr[(long long)(NT - 1) * NB].y));
+#pragma unroll 8
+    for (int i = NT - 2; i >= 0; --i) {
+        cbp[(long long)i * NB] = (float)cb;
+        cb = fma(aL, cb, fma((double)cfp[(long long)i * NB], GL, (double)pr[(long long)i * NB].y));
+    }
+}
+
+// 2-D mask smoothing = fftconvolve(M, outer(tri_f, tri_t)/sum, 'same'): separable, zero beyond the spectrogram.
+// CTA = 32 frames x all 513 bins.  Column phase (thread = bin): load |S| for the 32 frames + NTT halo frames each
+// side straight into registers (coalesced across bins), forward recurrence from Cf (halo frames before the tile by
+// running the recurrence backwards: fwd[k-1] = (fwd[k] - b x[k])/a, at most 9 steps), backward recurrence from Cb
+// (halo after the tile likewise), sigmoid mask, then the time taps from registers into shared memory.  Row phase:
+// the 2*nf+1 frequency taps with 4 outputs per thread (for nf = 16: 9 LDS.128 feed 132 FMA).  grid (ceil(F/32), n_rows)
 constexpr int kSmT = 32, kSmPad = 32, kSmW = 584;  // row: 32 zeros | 513 bins | zeros up to 584 floats (16 B aligned)
-constexpr int kNtMax = 9, kNfMax = 32;
+constexpr int kNtMax = 9, kNfMax = 32, kMaskThreads = 288;
 struct NrSmooth {
     float vf[2 * kNfMax + 1];  // centred: tap k multiplies M[f - NFT + k]; zero-padded when nf < NFT
     float vt[2 * kNtMax + 1];
     int nt;
 };
 
-template <int NFT, int NTT>
-__global__ void __launch_bounds__(256, 2) k_nr_smooth(const float* __restrict__ M, float* __restrict__ Msm, int F, NrSmooth p) {
+// sigmoid(((x - as)/as - 2) * 10) = 1 / (1 + 2^((3 - x/as) * 10 log2 e)); 0/0 -> NaN on all-zero input, like the reference
+__device__ __forceinline__ float nr_mask_value(float x, float as) {
+    const float q = __fdividef(x, as);
+    return __fdividef(1.0f, 1.0f + exp2f(fmaf(q, -14.426950408889634f, 43.28085122666890f)));
+}
+
+// BOX: tri(n) = box(n+1) * box(n+1) / (n+1), so both smoothing axes are two running sums instead of 2n+1 taps
+// (the tap tables are then only used for their normalisation).
+template <int NFT, int NTT, bool BOX>
+__global__ void __launch_bounds__(kMaskThreads, 2) k_nr_mask(const float* __restrict__ A, const float* __restrict__ CF,
+                                                             const float* __restrict__ CB, float* __restrict__ Msm, int F, int NT,
+                                                             NrSmooth p, double bd) {
     extern __shared__ __align__(16) float tile[];  // [kSmT][kSmW]
+    constexpr int R = kSmT + 2 * NTT, ntap = 2 * NTT + 1;
+    static_assert(kSmT % kStftFrames == 0, "mask tiles must start and end on carry boundaries");
     const int t0 = blockIdx.x * kSmT, tid = threadIdx.x;
-    const long long base = (long long)blockIdx.y * F * NB;
-    for (int i = tid; i < kSmT * kSmW; i += 256) tile[i] = 0.f;
-    __syncthreads();
-    constexpr int ntap = 2 * NTT + 1;  // vt is centred and zero-padded to this reach
-    for (int f = tid; f < NB; f += 256) {
-        float w[ntap];
+    const long long row = blockIdx.y, base = row * F * NB;
+    const int t1 = min(t0 + kSmT - 1, F - 1);  // last frame of the tile: a carry boundary or the last frame
+    // zero the row pads; the 513 bins of every row are written by the column phase
+    for (int i = tid; i < kSmT * (kSmW - NB); i += kMaskThreads) {
+        const int r = i / (kSmW - NB), c = i - r * (kSmW - NB);
+        tile[r * kSmW + (c < kSmPad ? c : c + NB)] = 0.f;
+    }
+    // inside a tile the recurrences run in f32: 38 steps from an f64-chained state lose ~1e-7 relative
+    const float b = (float)bd, a = (float)(1.0 - bd), ia = (float)(1.0 / (1.0 - bd));
+    for (int f = tid; f < NB; f += kMaskThreads) {
+        float x[R], w[R];  // |S| ; forward pass, later the mask.  Row r is frame t0 - NTT + r
 #pragma unroll
-        for (int k = 0; k < ntap - 1; ++k) {
-            const int t = t0 - NTT + k;
-            w[k] = (t >= 0 && t < F) ? M[base + (long long)t * NB + f] : 0.f;
+        for (int r = 0; r < R; ++r) {
+            const int t = t0 - NTT + r;
+            x[r] = (t >= 0 && t < F) ? A[base + (long long)t * NB + f] : 0.f;
         }
+        const float cf = CF[(row * NT + t0 / kStftFrames) * NB + f];  // fwd[t0 - 1]
+        const float cb = CB[(row * NT + t1 / kStftFrames) * NB + f];  // bwd[t1 + 1]
+        {   // forward pass over the tile and the halo after it
+            float y = cf;
 #pragma unroll
-        for (int r = 0; r < kSmT; ++r) {
-            const int t = t0 + r + NTT;  // newest frame entering the window
-            w[ntap - 1] = (t < F) ? M[base + (long long)t * NB + f] : 0.f;
-            float acc = 0.f;
+            for (int r = NTT; r < R; ++r) {
+                y = fmaf(a, y, b * x[r]);
+                w[r] = y;
+            }
+            // halo before the tile (t0 is 0 or >= 32 > NTT): fwd[t0-1] = cf, then backwards
+            y = cf;
 #pragma unroll
-            for (int k = 0; k < ntap; ++k) acc = fmaf(p.vt[k], w[k], acc);
-            tile[r * kSmW + kSmPad + f] = acc;
+            for (int r = NTT - 1; r >= 0; --r) {
+                w[r] = y;
+                y = (y - b * x[r]) * ia;
+            }
+        }
+        {
+            float z = cb;
+            // halo after the tile exists only for full tiles (t1 = t0 + 31): bwd[t1+1] = cb, then forwards in time
 #pragma unroll
-            for (int k = 0; k < ntap - 1; ++k) w[k] = w[k + 1];
+            for (int r = NTT + kSmT; r < R; ++r) {
+                const float as = z;
+                z = (z - b * w[r]) * ia;
+                w[r] = (t0 - NTT + r < F) ? nr_mask_value(x[r], as) : 0.f;
+            }
+            z = cb;
+#pragma unroll
+            for (int r = NTT + kSmT - 1; r >= 0; --r) {
+                const int t = t0 - NTT + r;
+                if (t <= t1) {  // frames past a short last tile do not exist
+                    z = fmaf(a, z, b * w[r]);
+                    w[r] = (t >= 0) ? nr_mask_value(x[r], z) : 0.f;
+                } else {
+                    w[r] = 0.f;
+                }
+            }
+        }
+        if constexpr (BOX) {
+            // box(NTT+1) twice, unnormalised: x[] is dead and takes the first running sum
+            float s = 0.f;
+#pragma unroll
+            for (int k = 0; k <= NTT; ++k) s += w[k];
+            x[0] = s;
+#pragma unroll
+            for (int r = 1; r < R - NTT; ++r) {
+                s += w[r + NTT] - w[r - 1];
+                x[r] = s;
+            }
+            s = 0.f;
+#pragma unroll
+            for (int k = 0; k <= NTT; ++k) s += x[k];
+            tile[kSmPad + f] = s;
+#pragma unroll
+            for (int r = 1; r < kSmT; ++r) {
+                s += x[r + NTT] - x[r - 1];
+                tile[r * kSmW + kSmPad + f] = s;
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < kSmT; ++r) {
+                float acc = 0.f;
+#pragma unroll
+                for (int k = 0; k < ntap; ++k) acc = fmaf(p.vt[k], w[r + k], acc);
+                tile[r * kSmW + kSmPad + f] = acc;
+            }
         }
     }
     __syncthreads();
-    constexpr int NFA = (NFT + 3) / 4 * 4;      // aligned left reach
-    constexpr int NV = (4 + 2 * NFA) / 4;       // float4 loads per thread
-    const int groups = (NB + 3) / 4;            // 129 groups of 4 bins
-    for (int task = tid; task < kSmT * groups; task += 256) {
-        const int r = task / groups, gq = task - r * groups;
-        if (t0 + r >= F) continue;
-        const float* row = tile + r * kSmW + kSmPad + 4 * gq - NFA;
-        float x[4 * NV];
+    if constexpr (BOX) {
+        // frequency axis: B1[f] = sum_{|j| <= H} T[f+j] for f in [-H, 513+H), held in registers and written back in
+        // place after a barrier; then out[f] = sum_{|j| <= H} B1[f+j].  8 outputs per thread and stage (sliding sum).
+        constexpr int H = NFT / 2, G1 = (NB + 2 * H + 7) / 8, G2 = (NB + 7) / 8;
+        static_assert(NFT % 2 == 0 && H % 4 == 0 && 2 * H <= kSmPad && NB + 2 * H + 8 <= kSmW - kSmPad, "pads cover the box reach");
+        constexpr int IT1 = (kSmT * G1 + kMaskThreads - 1) / kMaskThreads;
+        float keep[IT1][8];
 #pragma unroll
-        for (int q = 0; q < NV; ++q) {
-            const float4 v4 = *reinterpret_cast<const float4*>(row + 4 * q);
-            x[4 * q] = v4.x; x[4 * q + 1] = v4.y; x[4 * q + 2] = v4.z; x[4 * q + 3] = v4.w;
-        }
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        for (int it = 0; it < IT1; ++it) {
+            const int task = tid + it * kMaskThreads;
+            if (task < kSmT * G1) {
+                const int r = task / G1, gq = task - r * G1;
+                const float* in = tile + r * kSmW + kSmPad - 2 * H + 8 * gq;  // input index of output f0 - H, f0 = -H + 8 gq
+                float v[8 + 2 * H];
 #pragma unroll
-        for (int k = 0; k < 2 * NFT + 1; ++k) {
-            const float c = p.vf[k];
-            a0 = fmaf(c, x[NFA - NFT + k], a0);
-            a1 = fmaf(c, x[NFA - NFT + k + 1], a1);
-            a2 = fmaf(c, x[NFA - NFT + k + 2], a2);
-            a3 = fmaf(c, x[NFA - NFT + k + 3], a3);
+                for (int q = 0; q < (8 + 2 * H) / 4; ++q) {
+                    const float4 v4 = *reinterpret_cast<const float4*>(in + 4 * q);
+                    v[4 * q] = v4.x; v[4 * q + 1] = v4.y; v[4 * q + 2] = v4.z; v[4 * q + 3] = v4.w;
+                }
+                float s = 0.f;
+#pragma unroll
+                for (int k = 0; k <= 2 * H; ++k) s += v[k];
+                keep[it][0] = s;
+#pragma unroll
+                for (int o = 1; o < 8; ++o) {
+                    s += v[o + 2 * H] - v[o - 1];
+                    keep[it][o] = s;
+                }
+            }
         }
-        float* o = Msm + base + (long long)(t0 + r) * NB + 4 * gq;
-        o[0] = a0;
-        if (4 * gq + 1 < NB) { o[1] = a1; o[2] = a2; o[3] = a3; }
+        __syncthreads();
+#pragma unroll
+        for (int it = 0; it < IT1; ++it) {
+            const int task = tid + it * kMaskThreads;
+            if (task < kSmT * G1) {
+                const int r = task / G1, gq = task - r * G1;
+                float* o = tile + r * kSmW + kSmPad - H + 8 * gq;
+                *reinterpret_cast<float4*>(o) = make_float4(keep[it][0], keep[it][1], keep[it][2], keep[it][3]);
+                *reinterpret_cast<float4*>(o + 4) = make_float4(keep[it][4], keep[it][5], keep[it][6], keep[it][7]);
+            }
+        }
+        __syncthreads();
+        const float sc = p.vf[0] * p.vt[0];  // first taps: 1/(nf+1)^2 and 1/(nt+1)^2
+        for (int task = tid; task < kSmT * G2; task += kMaskThreads) {
+            const int r = task / G2, gq = task - r * G2;
+            if (t0 + r >= F) continue;
+            const float* in = tile + r * kSmW + kSmPad - H + 8 * gq;
+            float v[8 + 2 * H];
+#pragma unroll
+            for (int q = 0; q < (8 + 2 * H) / 4; ++q) {
+                const float4 v4 = *reinterpret_cast<const float4*>(in + 4 * q);
+                v[4 * q] = v4.x; v[4 * q + 1] = v4.y; v[4 * q + 2] = v4.z; v[4 * q + 3] = v4.w;
+            }
+            float s = 0.f;
+#pragma unroll
+            for (int k = 0; k <= 2 * H; ++k) s += v[k];
+            float* o = Msm + base + (long long)(t0 + r) * NB + 8 * gq;
+            o[0] = s * sc;
+#pragma unroll
+            for (int q = 1; q < 8; ++q) {
+                s += v[q + 2 * H] - v[q - 1];
+                if (8 * gq + q < NB) o[q] = s * sc;
+            }
+        }
+    } else {
+        constexpr int NFA = (NFT + 3) / 4 * 4;      // aligned left reach
+        constexpr int NV = (4 + 2 * NFA) / 4;       // float4 loads per thread
+        const int groups = (NB + 3) / 4;            // 129 groups of 4 bins
+        for (int task = tid; task < kSmT * groups; task += kMaskThreads) {
+            const int r = task / groups, gq = task - r * groups;
+            if (t0 + r >= F) continue;
+            const float* rowp = tile + r * kSmW + kSmPad + 4 * gq - NFA;
+            float xv[4 * NV];
+#pragma unroll
+            for (int q = 0; q < NV; ++q) {
+                const float4 v4 = *reinterpret_cast<const float4*>(rowp + 4 * q);
+                xv[4 * q] = v4.x; xv[4 * q + 1] = v4.y; xv[4 * q + 2] = v4.z; xv[4 * q + 3] = v4.w;
+            }
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+            for (int k = 0; k < 2 * NFT + 1; ++k) {
+                const float c = p.vf[k];
+                a0 = fmaf(c, xv[NFA - NFT + k], a0);
+                a1 = fmaf(c, xv[NFA - NFT + k + 1], a1);
+                a2 = fmaf(c, xv[NFA - NFT + k + 2], a2);
+                a3 = fmaf(c, xv[NFA - NFT + k + 3], a3);
+            }
+            float* o = Msm + base + (long long)(t0 + r) * NB + 4 * gq;
+            o[0] = a0;
+            if (4 * gq + 1 < NB) { o[1] = a1; o[2] = a2; o[3] = a3; }
+        }
     }
 }
 
@@ -425,7 +581,7 @@ __global__ void __launch_bounds__(256, 2) k_nr_istft(const float2* __restrict__ 
     }
 }
 
-constexpr int kStftSmem = (kStftXs + 3 * NF + 8 * 2 * kYPlane) * (int)sizeof(float);
+constexpr int kStftSmem = (kStftLow + 8 * 2 * kYPlane) * (int)sizeof(float);
 constexpr int kSmoothSmem = kSmT * kSmW * (int)sizeof(float);
 constexpr int kIstftSmem = (3 * NF + NH + 8 * 2 * kYPlane + kOlaOut) * (int)sizeof(float);
 
@@ -447,8 +603,8 @@ int launch_spectral_gate(const void* d_audio, int fmt, long long n, long long ba
     std::call_once(once, [&] {
         e1 = cudaFuncSetAttribute(k_nr_stft, cudaFuncAttributeMaxDynamicSharedMemorySize, kStftSmem);
         e2 = cudaFuncSetAttribute(k_nr_istft, cudaFuncAttributeMaxDynamicSharedMemorySize, kIstftSmem);
-        if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(k_nr_smooth<16, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmoothSmem);
-        if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(k_nr_smooth<kNfMax, kNtMax>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmoothSmem);
+        if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(k_nr_mask<16, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmoothSmem);
+        if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(k_nr_mask<kNfMax, kNtMax, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmoothSmem);
     });
     OSB_CUDA(e1);
     OSB_CUDA(e2);
@@ -482,36 +638,35 @@ int launch_spectral_gate(const void* d_audio, int fmt, long long n, long long ba
     const int j_first = (int)(kCtx / NH);
     const int j_last = (int)((kCtx + keep_max - 1) / NH);
     const int tiles = (j_last - j_first + 1 + kOlaBlocks - 1) / kOlaBlocks;
-    // scratch per clip: S (8 B) + A/M (4 B) + Afwd/Msm (4 B) per (frame, bin); process the batch in groups of <= ~24 GB
-    const long long per_clip = (long long)g.n_chunks * g.F * NB;
-    long long group = (24ll << 30) / (per_clip * 16);
+    // scratch per clip: S (8 B) + |S| (4 B) + smoothed mask (4 B) per (frame, bin) + 16 B of tile carries per 16 frames;
+    // process the batch in groups of <= ~24 GB
+    const int NT = (g.F + kStftFrames - 1) / kStftFrames;
+    const long long per_clip = (long long)g.n_chunks * g.F * NB, per_clip_t = (long long)g.n_chunks * NT * NB;
+    long long group = (24ll << 30) / (per_clip * 17);
     if (group < 1) group = 1;
     if (group > batch) group = batch;
     Scratch scr(st);
-    float2* S;
-    float *A, *Afwd, *M, *Msm;
+    float2 *S, *PR;
+    float *A, *Msm, *CF, *CB;
     OSB_CUDA(scr.alloc(&S, (size_t)(group * per_clip)));
     OSB_CUDA(scr.alloc(&A, (size_t)(group * per_clip)));
-    OSB_CUDA(scr.alloc(&Afwd, (size_t)(group * per_clip)));
-    M = A;       // the mask overwrites |S| in place (same thread reads A[t][f] then writes M[t][f])
-    Msm = Afwd;  // Afwd is dead once the mask exists
+    OSB_CUDA(scr.alloc(&Msm, (size_t)(group * per_clip)));
+    OSB_CUDA(scr.alloc(&PR, (size_t)(group * per_clip_t)));
+    OSB_CUDA(scr.alloc(&CF, (size_t)(group * per_clip_t)));
+    OSB_CUDA(scr.alloc(&CB, (size_t)(group * per_clip_t)));
     for (long long c0 = 0; c0 < batch; c0 += group) {
         const int gb = (int)((batch - c0) < group ? (batch - c0) : group);
         g.batch = gb;
         const char* in = reinterpret_cast<const char*>(d_audio) + c0 * stride * (fmt == OSB_FMT_PCM16 ? 2 : 4);
         float* outp = d_out + c0 * stride;
         const long long n_rows = (long long)gb * g.n_chunks;
-        OSB_LAUNCH(k_nr_stft, dim3((g.F + kStftFrames - 1) / kStftFrames, g.n_chunks, gb), 256, kStftSmem, st, (const void*)in, g, tabs, S, A);
+        OSB_LAUNCH(k_nr_stft, dim3(NT, g.n_chunks, gb), 256, kStftSmem, st, (const void*)in, g, tabs, S, A, PR, b);
         OSB_CHECK_LAUNCH();
-        const unsigned gi = (unsigned)((n_rows * NB + 127) / 128);
-        OSB_LAUNCH(k_nr_iir_fwd, gi, 128, 0, st, A, Afwd, g.F, n_rows, b);
+        OSB_LAUNCH(k_nr_carry, (unsigned)((n_rows * NB + 127) / 128), 128, 0, st, A, PR, CF, CB, g.F, NT, n_rows, b);
         OSB_CHECK_LAUNCH();
-        // few rows: deep register pipelining hides latency; many rows: occupancy does, and a shallower pipeline keeps it high
-        if (n_rows * NB < 160000) OSB_LAUNCH(k_nr_iir_bwd_mask<16>, gi, 128, 0, st, A, Afwd, M, g.F, n_rows, b);
-        else OSB_LAUNCH(k_nr_iir_bwd_mask<8>, gi, 128, 0, st, A, Afwd, M, g.F, n_rows, b);
-        OSB_CHECK_LAUNCH();
-        if (nft == 16 && nt == 3) OSB_LAUNCH((k_nr_smooth<16, 3>), dim3((g.F + kSmT - 1) / kSmT, (unsigned)n_rows), 256, kSmoothSmem, st, M, Msm, g.F, sp);
-        else OSB_LAUNCH((k_nr_smooth<kNfMax, kNtMax>), dim3((g.F + kSmT - 1) / kSmT, (unsigned)n_rows), 256, kSmoothSmem, st, M, Msm, g.F, sp);
+        const dim3 gm((g.F + kSmT - 1) / kSmT, (unsigned)n_rows);
+        if (nft == 16 && nt == 3) OSB_LAUNCH((k_nr_mask<16, 3, true>), gm, kMaskThreads, kSmoothSmem, st, A, CF, CB, Msm, g.F, NT, sp, b);
+        else OSB_LAUNCH((k_nr_mask<kNfMax, kNtMax, false>), gm, kMaskThreads, kSmoothSmem, st, A, CF, CB, Msm, g.F, NT, sp, b);
         OSB_CHECK_LAUNCH();
         OSB_LAUNCH(k_nr_istft, dim3(tiles, g.n_chunks, gb), 256, kIstftSmem, st, S, Msm, g, tabs, j_first, outp);
         OSB_CHECK_LAUNCH();

