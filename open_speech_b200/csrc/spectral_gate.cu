@@ -276,8 +276,15 @@ __global__ void __launch_bounds__(128) k_nr_carry(const float* __restrict__ A, c
 // running the recurrence backwards: fwd[k-1] = (fwd[k] - b x[k])/a, at most 9 steps), backward recurrence from Cb
 // (halo after the tile likewise), sigmoid mask, then the time taps from registers into shared memory.  Row phase:
 // the 2*nf+1 frequency taps with 4 outputs per thread (for nf = 16: 9 LDS.128 feed 132 FMA).  grid (ceil(F/32), n_rows)
-constexpr int kSmT = 32, kSmPad = 32, kSmW = 584;  // row: 32 zeros | 513 bins | zeros up to 584 floats (16 B aligned)
+constexpr int kSmT = 32, kSmPad = 32;
+constexpr int kSmWBox = 576, kSmWTap = 584;  // row: 32 zeros | 513 bins | zeros (box variant: whole 32-float blocks)
 constexpr int kNtMax = 9, kNfMax = 32, kMaskThreads = 288;
+// The box variant's frequency phase reads 16-byte chunks at a lane stride of 32 bytes.  Chunks are XOR-swizzled inside
+// each 64-byte group by the index of the 128-byte block they sit in, which makes those LDS.128 and the scalar row
+// accesses (lanes on consecutive bins, starting on a 16-float boundary) both bank-conflict free.
+__device__ __forceinline__ int nr_swz(int i) {  // logical float index inside a row -> physical
+    return i ^ (((i >> 5) & 3) << 2);
+}
 struct NrSmooth {
     float vf[2 * kNfMax + 1];  // centred: tap k multiplies M[f - NFT + k]; zero-padded when nf < NFT
     float vt[2 * kNtMax + 1];
@@ -296,16 +303,17 @@ template <int NFT, int NTT, bool BOX>
 __global__ void __launch_bounds__(kMaskThreads, 2) k_nr_mask(const float* __restrict__ A, const float* __restrict__ CF,
                                                              const float* __restrict__ CB, float* __restrict__ Msm, int F, int NT,
                                                              NrSmooth p, double bd) {
-    extern __shared__ __align__(16) float tile[];  // [kSmT][kSmW]
-    constexpr int R = kSmT + 2 * NTT, ntap = 2 * NTT + 1;
+    extern __shared__ __align__(16) float tile[];  // [kSmT][W]
+    constexpr int R = kSmT + 2 * NTT, ntap = 2 * NTT + 1, W = BOX ? kSmWBox : kSmWTap;
     static_assert(kSmT % kStftFrames == 0, "mask tiles must start and end on carry boundaries");
+    auto at = [](int r, int i) { return r * W + (BOX ? nr_swz(i) : i); };
     const int t0 = blockIdx.x * kSmT, tid = threadIdx.x;
     const long long row = blockIdx.y, base = row * F * NB;
     const int t1 = min(t0 + kSmT - 1, F - 1);  // last frame of the tile: a carry boundary or the last frame
     // zero the row pads; the 513 bins of every row are written by the column phase
-    for (int i = tid; i < kSmT * (kSmW - NB); i += kMaskThreads) {
-        const int r = i / (kSmW - NB), c = i - r * (kSmW - NB);
-        tile[r * kSmW + (c < kSmPad ? c : c + NB)] = 0.f;
+    for (int i = tid; i < kSmT * (W - NB); i += kMaskThreads) {
+        const int r = i / (W - NB), c = i - r * (W - NB);
+        tile[at(r, c < kSmPad ? c : c + NB)] = 0.f;
     }
     // inside a tile the recurrences run in f32: 38 steps from an f64-chained state lose ~1e-7 relative
     const float b = (float)bd, a = (float)(1.0 - bd), ia = (float)(1.0 / (1.0 - bd));
@@ -368,11 +376,11 @@ __global__ void __launch_bounds__(kMaskThreads, 2) k_nr_mask(const float* __rest
             s = 0.f;
 #pragma unroll
             for (int k = 0; k <= NTT; ++k) s += x[k];
-            tile[kSmPad + f] = s;
+            tile[at(0, kSmPad + f)] = s;
 #pragma unroll
             for (int r = 1; r < kSmT; ++r) {
                 s += x[r + NTT] - x[r - 1];
-                tile[r * kSmW + kSmPad + f] = s;
+                tile[at(r, kSmPad + f)] = s;
             }
         } else {
 #pragma unroll
@@ -380,73 +388,70 @@ __global__ void __launch_bounds__(kMaskThreads, 2) k_nr_mask(const float* __rest
                 float acc = 0.f;
 #pragma unroll
                 for (int k = 0; k < ntap; ++k) acc = fmaf(p.vt[k], w[r + k], acc);
-                tile[r * kSmW + kSmPad + f] = acc;
+                tile[at(r, kSmPad + f)] = acc;
             }
         }
     }
     __syncthreads();
     if constexpr (BOX) {
-        // frequency axis: B1[f] = sum_{|j| <= H} T[f+j] for f in [-H, 513+H), held in registers and written back in
-        // place after a barrier; then out[f] = sum_{|j| <= H} B1[f+j].  8 outputs per thread and stage (sliding sum).
-        constexpr int H = NFT / 2, G1 = (NB + 2 * H + 7) / 8, G2 = (NB + 7) / 8;
-        static_assert(NFT % 2 == 0 && H % 4 == 0 && 2 * H <= kSmPad && NB + 2 * H + 8 <= kSmW - kSmPad, "pads cover the box reach");
-        constexpr int IT1 = (kSmT * G1 + kMaskThreads - 1) / kMaskThreads;
-        float keep[IT1][8];
+        // frequency axis, one warp per row: lane l owns bins [8l, 8l+8) and [256+8l, 256+8l+8); box(2H+1) twice as
+        // running sums in registers (40 inputs -> 24 first sums -> 8 outputs), results written back in place once the
+        // whole warp has read, then the row leaves as one contiguous, coalesced store.
+        constexpr int H = NFT / 2, NV = 8 + 4 * H, N1 = 8 + 2 * H;
+        static_assert(NFT == 16 && 2 * H <= kSmPad && kSmPad % 16 == 0 && kSmPad + 512 + 2 * H + 8 <= W, "pads cover the box reach");
+        const int warp = tid >> 5, lane = tid & 31;
+        const float sc = p.vf[0] * p.vt[0];  // first taps: 1/(nf+1)^2 and 1/(nt+1)^2
+        for (int r = warp; r < kSmT; r += kMaskThreads / 32) {
+            if (t0 + r >= F) break;
+            float* rowp = tile + r * W;
+            float outv[2][8];
 #pragma unroll
-        for (int it = 0; it < IT1; ++it) {
-            const int task = tid + it * kMaskThreads;
-            if (task < kSmT * G1) {
-                const int r = task / G1, gq = task - r * G1;
-                const float* in = tile + r * kSmW + kSmPad - 2 * H + 8 * gq;  // input index of output f0 - H, f0 = -H + 8 gq
-                float v[8 + 2 * H];
+            for (int h = 0; h < 2; ++h) {
+                const int l0 = kSmPad + 8 * (lane + 32 * h) - 2 * H;  // logical index of the first input
+                float v[NV];
 #pragma unroll
-                for (int q = 0; q < (8 + 2 * H) / 4; ++q) {
-                    const float4 v4 = *reinterpret_cast<const float4*>(in + 4 * q);
+                for (int q = 0; q < NV / 4; ++q) {
+                    const float4 v4 = *reinterpret_cast<const float4*>(rowp + nr_swz(l0 + 4 * q));
                     v[4 * q] = v4.x; v[4 * q + 1] = v4.y; v[4 * q + 2] = v4.z; v[4 * q + 3] = v4.w;
                 }
+                float b1[N1];
                 float s = 0.f;
 #pragma unroll
                 for (int k = 0; k <= 2 * H; ++k) s += v[k];
-                keep[it][0] = s;
+                b1[0] = s;
+#pragma unroll
+                for (int j = 1; j < N1; ++j) {
+                    s += v[j + 2 * H] - v[j - 1];
+                    b1[j] = s;
+                }
+                s = 0.f;
+#pragma unroll
+                for (int k = 0; k <= 2 * H; ++k) s += b1[k];
+                outv[h][0] = s * sc;
 #pragma unroll
                 for (int o = 1; o < 8; ++o) {
-                    s += v[o + 2 * H] - v[o - 1];
-                    keep[it][o] = s;
+                    s += b1[o + 2 * H] - b1[o - 1];
+                    outv[h][o] = s * sc;
                 }
             }
-        }
-        __syncthreads();
+            // bin 512: 4H+1 triangle taps spread over the lanes (box * box = 2H+1 - |k - 2H|)
+            float e = (float)(2 * H + 1 - abs(lane - 2 * H)) * rowp[nr_swz(kSmPad + 512 - 2 * H + lane)];
+            if (lane == 0) e += rowp[nr_swz(kSmPad + 512 + 2 * H)];
+            e = warp_sum(e) * sc;
+            __syncwarp();
 #pragma unroll
-        for (int it = 0; it < IT1; ++it) {
-            const int task = tid + it * kMaskThreads;
-            if (task < kSmT * G1) {
-                const int r = task / G1, gq = task - r * G1;
-                float* o = tile + r * kSmW + kSmPad - H + 8 * gq;
-                *reinterpret_cast<float4*>(o) = make_float4(keep[it][0], keep[it][1], keep[it][2], keep[it][3]);
-                *reinterpret_cast<float4*>(o + 4) = make_float4(keep[it][4], keep[it][5], keep[it][6], keep[it][7]);
+            for (int h = 0; h < 2; ++h) {
+                const int l0 = kSmPad + 8 * (lane + 32 * h);
+                *reinterpret_cast<float4*>(rowp + nr_swz(l0)) = make_float4(outv[h][0], outv[h][1], outv[h][2], outv[h][3]);
+                *reinterpret_cast<float4*>(rowp + nr_swz(l0 + 4)) = make_float4(outv[h][4], outv[h][5], outv[h][6], outv[h][7]);
             }
-        }
-        __syncthreads();
-        const float sc = p.vf[0] * p.vt[0];  // first taps: 1/(nf+1)^2 and 1/(nt+1)^2
-        for (int task = tid; task < kSmT * G2; task += kMaskThreads) {
-            const int r = task / G2, gq = task - r * G2;
-            if (t0 + r >= F) continue;
-            const float* in = tile + r * kSmW + kSmPad - H + 8 * gq;
-            float v[8 + 2 * H];
+            if (lane == 0) rowp[nr_swz(kSmPad + 512)] = e;
+            __syncwarp();
+            float* o = Msm + base + (long long)(t0 + r) * NB;
 #pragma unroll
-            for (int q = 0; q < (8 + 2 * H) / 4; ++q) {
-                const float4 v4 = *reinterpret_cast<const float4*>(in + 4 * q);
-                v[4 * q] = v4.x; v[4 * q + 1] = v4.y; v[4 * q + 2] = v4.z; v[4 * q + 3] = v4.w;
-            }
-            float s = 0.f;
-#pragma unroll
-            for (int k = 0; k <= 2 * H; ++k) s += v[k];
-            float* o = Msm + base + (long long)(t0 + r) * NB + 8 * gq;
-            o[0] = s * sc;
-#pragma unroll
-            for (int q = 1; q < 8; ++q) {
-                s += v[q + 2 * H] - v[q - 1];
-                if (8 * gq + q < NB) o[q] = s * sc;
+            for (int i = 0; i < (NB + 31) / 32; ++i) {
+                const int f = lane + 32 * i;
+                if (f < NB) o[f] = rowp[nr_swz(kSmPad + f)];
             }
         }
     } else {
@@ -456,7 +461,7 @@ __global__ void __launch_bounds__(kMaskThreads, 2) k_nr_mask(const float* __rest
         for (int task = tid; task < kSmT * groups; task += kMaskThreads) {
             const int r = task / groups, gq = task - r * groups;
             if (t0 + r >= F) continue;
-            const float* rowp = tile + r * kSmW + kSmPad + 4 * gq - NFA;
+            const float* rowp = tile + r * W + kSmPad + 4 * gq - NFA;
             float xv[4 * NV];
 #pragma unroll
             for (int q = 0; q < NV; ++q) {
@@ -582,7 +587,7 @@ __global__ void __launch_bounds__(256, 2) k_nr_istft(const float2* __restrict__ 
 }
 
 constexpr int kStftSmem = (kStftLow + 8 * 2 * kYPlane) * (int)sizeof(float);
-constexpr int kSmoothSmem = kSmT * kSmW * (int)sizeof(float);
+constexpr int kSmoothSmem = kSmT * kSmWTap * (int)sizeof(float);
 constexpr int kIstftSmem = (3 * NF + NH + 8 * 2 * kYPlane + kOlaOut) * (int)sizeof(float);
 
 static std::vector<double> tri_filter(int n) {
