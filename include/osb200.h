@@ -164,6 +164,9 @@ int osb_stt_frontend_host(const int16_t* pcm, int64_t n, int64_t batch, int64_t 
  * osb_fx_chain = apply_chain (src/effects/chain.py:15-32): ordered effects, float32 until the first float64
  *   effect, float64 afterwards, cast to float32 at the end (out_pcm16=1 additionally applies float32_to_int16,
  *   src/tts/pipeline.py:32-37).  fx_p0/fx_p1: NORMALIZE target_lufs,- | REVERB room_ms,mix | PITCH semitones,-.
+ *   PITCH = _pitch_shift (src/effects/chain.py:44-48 -> librosa.effects.pitch_shift defaults): input cast to float32,
+ *   STFT 2048/512 -> phase vocoder at rate 2^(-semitones/12) -> ISTFT -> band-limited resampling back to the input
+ *   length; float32 result.  Parity unpinned (librosa/soxr absent): Kaiser-sinc resampler instead of soxr_hq.
  * osb_voice_blend = KokoroBackend._blend_voices (src/tts/backends/kokoro.py:289-308): result += w_k * pack_k in
  *   float32, in component order; d_idx [batch][kmax] (-1 terminates), d_weights [batch][kmax]. */
 #define OSB_FX_NORMALIZE 1

@@ -91,6 +91,8 @@ int launch_logmel(const void* d_audio, int fmt, long long n, long long batch, lo
                   const unsigned long long* d_sumsq, float target_dbfs, cudaStream_t st);
 int launch_spectral_gate(const void* d_audio, int fmt, long long n, long long batch, long long stride, int sr, float* d_out,
                          cudaStream_t st);
+int launch_pitch_shift(const void* d_in, bool in_f64, const long long* d_offsets, const long long* d_lens, long long batch, long long max_len,
+                       int sample_rate, double semitones, float* d_out, cudaStream_t st);
 int launch_sumsq_pcm16(const int16_t* d_in, long long n, long long batch, long long stride, unsigned long long* d_sumsq, cudaStream_t st);
 int launch_normalize_f32(const float* d_in, void* d_out, int out_pcm16, long long n, long long batch, long long stride, int normalize,
                          float target_dbfs, cudaStream_t st);

@@ -177,4 +177,45 @@ OSB_HD void fft400_pair_power(const float* Zre, const float* Zim, int k, float* 
     *pb = 0.25f * (br * br + bi * bi);
 }
 
+// ---------------------------------------------------------------- 1024-point complex FFT by one warp (32 x 32 four-step)
+// In place on two float planes [32][33].  Input x[n], n = 32*n1 + n2, sits at [n1*33 + n2]; the result Z[k],
+// k = k1 + 32*k2, is left at [k1*33 + k2] (use fft1024_out_addr).  twc/tws hold cos/sin(2 pi n2 k1 / 1024) at
+// [k1*32 + n2].  INV conjugates every twiddle (unnormalised inverse).  Lane l owns column l in step 1 and row l
+// in step 2, so the only cross-lane hand-over is the __syncwarp between the steps.
+constexpr int kF1024Stride = 33, kF1024Plane = 32 * 33;
+OSB_HD int fft1024_in_addr(int n) { return (n >> 5) * kF1024Stride + (n & 31); }
+OSB_HD int fft1024_out_addr(int k) { return (k & 31) * kF1024Stride + (k >> 5); }
+
+#ifdef __CUDACC__
+template <bool INV>
+__device__ __forceinline__ void fft1024_warp(float* yr, float* yi, const float* twc, const float* tws, int lane) {
+    {
+        cpx v[32];
+#pragma unroll
+        for (int n1 = 0; n1 < 32; ++n1) v[n1] = cpx{yr[n1 * kF1024Stride + lane], yi[n1 * kF1024Stride + lane]};
+        fft_pow2<32, INV>(v);
+#pragma unroll
+        for (int k1 = 0; k1 < 32; ++k1) {
+            const int tw = k1 * 32 + lane;
+            const cpx y = cmul(v[k1], cpx{twc[tw], INV ? tws[tw] : -tws[tw]});
+            yr[k1 * kF1024Stride + lane] = y.x;
+            yi[k1 * kF1024Stride + lane] = y.y;
+        }
+    }
+    __syncwarp();
+    {
+        cpx v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = cpx{yr[lane * kF1024Stride + i], yi[lane * kF1024Stride + i]};
+        fft_pow2<32, INV>(v);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            yr[lane * kF1024Stride + i] = v[i].x;
+            yi[lane * kF1024Stride + i] = v[i].y;
+        }
+    }
+    __syncwarp();
+}
+#endif
+
 }  // namespace osb

@@ -615,8 +615,10 @@ int osb_fx_chain_dev(const float* d_in, const int64_t* d_offsets, const int64_t*
             case OSB_FX_ROBOT: rc = fx_robot(s, sample_rate); break;
             case OSB_FX_PITCH:
                 if (fx_p0[i] == 0.0) { rc = OSB_OK; break; }  // identity (chain.py:46-47)
-                set_error("unsupported: pitch shift (librosa phase vocoder + soxr) is not implemented (SURVEY.md 8(f) row 2)");
-                rc = OSB_ERR_UNSUPPORTED;
+                // x.astype(float32) -> float32 result (chain.py:48); f32_tmp may be the input: every group is read before it is written
+                rc = launch_pitch_shift(s.cur, s.f64, s.rg.offsets, s.rg.lens, s.batch, s.max_len, sample_rate, fx_p0[i], s.f32_tmp, st);
+                s.cur = s.f32_tmp;
+                s.f64 = false;
                 break;
             default: rc = OSB_OK; break;  // unknown effect types are skipped silently (chain.py:18-31)
         }

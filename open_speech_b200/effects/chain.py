@@ -2,7 +2,8 @@
 
 Same effect dictionaries, same order semantics, unknown types skipped, result float32.  The whole chain is
 one C call: the samples cross PCIe once in each direction regardless of the number of effects.
-``pitch`` with a non-zero shift raises (librosa's phase vocoder is not implemented).
+``pitch`` follows librosa.effects.pitch_shift's stretch-then-resample (phase vocoder 2048/512 on the GPU); librosa and
+soxr are absent here, so that effect is parity-unpinned and uses a Kaiser-sinc resampler (csrc/pitch.cu).
 """
 from __future__ import annotations
 

@@ -80,11 +80,52 @@ def test_effects_long_utterance_vs_oracle(gpu):
     r = np.random.default_rng(0).standard_normal(1000).astype(np.float32) * 0.1
     assert np.allclose(apply_chain(r, 24000, []), r) and np.allclose(apply_chain(r, 24000, [{"type": "unknown"}]), r)
     assert np.array_equal(apply_chain(r, 24000, [{"type": "pitch", "semitones": 0}]), r)
-    with pytest.raises(RuntimeError):
-        apply_chain(r, 24000, [{"type": "pitch", "semitones": 4}])
+    # tests/test_effects_chain.py:14-18: the pitch effect keeps the length and changes the audio
+    tone = np.sin(2 * np.pi * 220 * np.arange(24000) / 24000).astype(np.float32)
+    shifted = apply_chain(tone, 24000, [{"type": "pitch", "semitones": 4}])
+    assert shifted.dtype == np.float32 and len(shifted) == len(tone) and not np.allclose(shifted, tone)
     imp = np.zeros(24000, np.float32)
     imp[0] = 1.0
     assert np.sum(np.abs(_reverb(imp, 24000, room="medium", mix=0.5)[1:])) > 0
+
+
+@pytest.mark.parametrize("semitones", [4, -3, 12, 0.5])
+def test_pitch_shift_vs_oracle(gpu, semitones):
+    """_pitch_shift (src/effects/chain.py:44-48).  PARITY UNPINNED (librosa + soxr absent): the oracle restates librosa's
+    stretch-then-resample with a Kaiser-sinc resampler.  The phase accumulator is float32 by librosa's design, so a
+    last-bit difference in an analysis phase can move the accumulated phase of a high bin by one float32 ulp of ~1e5 rad
+    (~0.01 rad); the bar is therefore an RMS one: 1e-3 of the signal RMS, and 1e-2 of the peak for the worst sample."""
+    from open_speech_b200 import synth
+    from open_speech_b200.effects.chain import _pitch_shift, apply_chain
+
+    x = synth.tts_utterance(3.0, seed=21)
+    got, ref = _pitch_shift(x, 24000, semitones), otts.pitch_shift(x, 24000, semitones)
+    assert got.dtype == np.float32 and got.shape == ref.shape == x.shape
+    rms = float(np.sqrt(np.mean(ref.astype(np.float64) ** 2)))
+    err = got.astype(np.float64) - ref
+    assert np.sqrt(np.mean(err**2)) <= 1e-3 * rms, (np.sqrt(np.mean(err**2)), rms)
+    assert np.abs(err).max() <= 1e-2 * np.abs(ref).max(), (np.abs(err).max(), np.abs(ref).max())
+    # the pitch really moves: dominant frequency of a tone scales by 2^(n/12)
+    tone = (0.5 * np.sin(2 * np.pi * 440 * np.arange(48000) / 24000)).astype(np.float32)
+    y = _pitch_shift(tone, 24000, semitones)
+    f = np.fft.rfftfreq(16384, 1 / 24000)[np.argmax(np.abs(np.fft.rfft(y[8000 : 8000 + 16384] * np.hanning(16384))))]
+    assert abs(f - 440 * 2 ** (semitones / 12)) <= 3.0, f
+    # inside a chain: float64 state is cast to float32 first, later effects continue from the float32 result
+    fx = [{"type": "podcast_eq"}, {"type": "pitch", "semitones": semitones}, {"type": "normalize", "target_lufs": -20}]
+    g2, r2 = apply_chain(x, 24000, fx), otts.apply_chain(x, 24000, fx)
+    assert np.sqrt(np.mean((g2.astype(np.float64) - r2) ** 2)) <= 1e-3 * np.sqrt(np.mean(r2.astype(np.float64) ** 2))
+
+
+def test_pitch_shift_edge_lengths(gpu):
+    """shorter than one hop / one frame, and exactly on frame boundaries."""
+    from open_speech_b200.effects.chain import _pitch_shift
+
+    rng = np.random.default_rng(5)
+    for n in (1, 100, 511, 512, 2047, 2048, 2049, 5000):
+        x = (0.3 * rng.standard_normal(n)).astype(np.float32)
+        got, ref = _pitch_shift(x, 24000, 3), otts.pitch_shift(x, 24000, 3)
+        assert got.shape == ref.shape
+        assert np.abs(got - ref).max() <= 1e-2 * max(np.abs(ref).max(), 1e-3), (n, np.abs(got - ref).max())
 
 
 def test_voice_blend_golden_bit_exact(gpu, golden):
