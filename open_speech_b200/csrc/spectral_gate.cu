@@ -86,6 +86,15 @@ __device__ __forceinline__ float nr_sample(const void* audio, const NrGeom& g, i
     return reinterpret_cast<const float*>(audio)[(long long)clip * g.stride + i];
 }
 
+// First frame of a chunk whose window lies wholly in the zeros past the end of the clip (the last chunk of a clip is
+// padded to full length): frames from there on are exactly zero, so nobody computes, stores or reads them.
+__device__ __forceinline__ int nr_tlim(const NrGeom& g, int chunk) {
+    long long p_hi = g.n - (long long)chunk * kChunk + kCtx;  // chunk coordinate of the end of the clip
+    if (p_hi > g.Lc) p_hi = g.Lc;
+    const long long t = (p_hi + NF / 2 + NH - 1) / NH;        // frame t covers [256 t - 512, 256 t + 512)
+    return t < g.F ? (int)t : g.F;
+}
+
 // |z| through the SFU reciprocal square root (2 ulp); |S| only feeds the smoothed-threshold mask
 __device__ __forceinline__ float fast_mag(float re, float im) {
     const float p = fmaf(re, re, im * im);
@@ -107,6 +116,10 @@ __global__ void __launch_bounds__(256, 2) k_nr_stft(const void* __restrict__ aud
     float* Amat = sm;               // [16][513] magnitudes of this tile; aliases xs/win/tw, which are dead after step 1
     float* Y = sm + kStftLow;       // [8][2][32*33]
     const int tid = threadIdx.x, t0 = blockIdx.x * kStftFrames, chunk = blockIdx.y, clip = blockIdx.z;
+    if (t0 >= nr_tlim(g, chunk)) {  // all-zero tile: only its (zero) aggregates exist
+        for (int f = tid; f < NB; f += 256) PR[(((long long)clip * g.n_chunks + chunk) * gridDim.x + blockIdx.x) * NB + f] = make_float2(0.f, 0.f);
+        return;
+    }
     for (int i = tid; i < 3 * NF; i += 256) win[i] = tabs[i];
     const long long p0 = (long long)NH * t0 - NF / 2;
     {
@@ -301,9 +314,11 @@ __device__ __forceinline__ float nr_mask_value(float x, float as) {
 // (the tap tables are then only used for their normalisation).
 template <int NFT, int NTT, bool BOX>
 __global__ void __launch_bounds__(kMaskThreads, 2) k_nr_mask(const float* __restrict__ A, const float* __restrict__ CF,
-                                                             const float* __restrict__ CB, float* __restrict__ Msm, int F, int NT,
+                                                             const float* __restrict__ CB, float* __restrict__ Msm, NrGeom g, int NT,
                                                              NrSmooth p, double bd) {
     extern __shared__ __align__(16) float tile[];  // [kSmT][W]
+    const int F = g.F, TL = nr_tlim(g, (int)(blockIdx.y % g.n_chunks));  // frames >= TL are zero and never stored
+    if ((int)blockIdx.x * kSmT >= TL) return;
     constexpr int R = kSmT + 2 * NTT, ntap = 2 * NTT + 1, W = BOX ? kSmWBox : kSmWTap;
     static_assert(kSmT % kStftFrames == 0, "mask tiles must start and end on carry boundaries");
     auto at = [](int r, int i) { return r * W + (BOX ? nr_swz(i) : i); };
@@ -322,7 +337,7 @@ __global__ void __launch_bounds__(kMaskThreads, 2) k_nr_mask(const float* __rest
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const int t = t0 - NTT + r;
-            x[r] = (t >= 0 && t < F) ? A[base + (long long)t * NB + f] : 0.f;
+            x[r] = (t >= 0 && t < TL) ? A[base + (long long)t * NB + f] : 0.f;
         }
         const float cf = CF[(row * NT + t0 / kStftFrames) * NB + f];  // fwd[t0 - 1]
         const float cb = CB[(row * NT + t1 / kStftFrames) * NB + f];  // bwd[t1 + 1]
@@ -402,7 +417,7 @@ __global__ void __launch_bounds__(kMaskThreads, 2) k_nr_mask(const float* __rest
         const int warp = tid >> 5, lane = tid & 31;
         const float sc = p.vf[0] * p.vt[0];  // first taps: 1/(nf+1)^2 and 1/(nt+1)^2
         for (int r = warp; r < kSmT; r += kMaskThreads / 32) {
-            if (t0 + r >= F) break;
+            if (t0 + r >= TL) break;
             float* rowp = tile + r * W;
             float outv[2][8];
 #pragma unroll
@@ -460,7 +475,7 @@ __global__ void __launch_bounds__(kMaskThreads, 2) k_nr_mask(const float* __rest
         const int groups = (NB + 3) / 4;            // 129 groups of 4 bins
         for (int task = tid; task < kSmT * groups; task += kMaskThreads) {
             const int r = task / groups, gq = task - r * groups;
-            if (t0 + r >= F) continue;
+            if (t0 + r >= TL) continue;
             const float* rowp = tile + r * W + kSmPad + 4 * gq - NFA;
             float xv[4 * NV];
 #pragma unroll
@@ -499,17 +514,21 @@ __global__ void __launch_bounds__(256, 2) k_nr_istft(const float2* __restrict__ 
     float* acc = Y + 8 * 2 * kYPlane;  // [7424]
     const int tid = threadIdx.x, chunk = blockIdx.y, clip = blockIdx.z;
     const int j0 = j_first + blockIdx.x * kOlaBlocks;
+    const long long keep = (g.n_chunks == 1) ? g.n : ((g.n - (long long)chunk * kChunk) < kChunk ? (g.n - (long long)chunk * kChunk) : kChunk);
+    if ((long long)NH * j0 >= kCtx + keep) return;  // tile past the kept centre of a short last chunk
+    const int TL = nr_tlim(g, chunk);
     for (int i = tid; i < 3 * NF + NH; i += 256) win[i] = tabs[i];
     for (int i = tid; i < kOlaOut; i += 256) acc[i] = 0.f;
     const long long row0 = ((long long)clip * g.n_chunks + chunk) * g.F;
     __syncthreads();
     for (int pass = 0; pass < 2; ++pass) {
         const int tp0 = j0 - 1 + pass * 16;
+        if (tp0 >= TL) break;  // only zero frames left
         {   // stage Z'[k] = Xa[k] + i Xb[k] for the 8 frame pairs of this pass, k stored at [k>>5][k&31] (row stride 33):
             // Xa/Xb are the masked one-sided spectra S*Msm extended by Hermitian symmetry; every S cell is read once, coalesced
             const int q = tid >> 5, lane = tid & 31;  // warp q owns pair q
             const int ta = tp0 + 2 * q, tb = ta + 1;
-            const bool va = ta >= 0 && ta < g.F, vb = tb >= 0 && tb < g.F;
+            const bool va = ta >= 0 && ta < TL, vb = tb >= 0 && tb < TL;
             float* yr = Y + q * 2 * kYPlane;
             float* yi = yr + kYPlane;
             const float2* Sa = S + (row0 + ta) * NB;
@@ -577,7 +596,6 @@ __global__ void __launch_bounds__(256, 2) k_nr_istft(const float2* __restrict__ 
         __syncthreads();
     }
     // store the kept centre [kCtx, kCtx + keep) of the chunk
-    const long long keep = (g.n_chunks == 1) ? g.n : ((g.n - (long long)chunk * kChunk) < kChunk ? (g.n - (long long)chunk * kChunk) : kChunk);
     for (int u = tid; u < kOlaOut; u += 256) {
         const long long p = (long long)NH * j0 + u;
         const long long rel = p - kCtx;
@@ -670,8 +688,8 @@ int launch_spectral_gate(const void* d_audio, int fmt, long long n, long long ba
         OSB_LAUNCH(k_nr_carry, (unsigned)((n_rows * NB + 127) / 128), 128, 0, st, A, PR, CF, CB, g.F, NT, n_rows, b);
         OSB_CHECK_LAUNCH();
         const dim3 gm((g.F + kSmT - 1) / kSmT, (unsigned)n_rows);
-        if (nft == 16 && nt == 3) OSB_LAUNCH((k_nr_mask<16, 3, true>), gm, kMaskThreads, kSmoothSmem, st, A, CF, CB, Msm, g.F, NT, sp, b);
-        else OSB_LAUNCH((k_nr_mask<kNfMax, kNtMax, false>), gm, kMaskThreads, kSmoothSmem, st, A, CF, CB, Msm, g.F, NT, sp, b);
+        if (nft == 16 && nt == 3) OSB_LAUNCH((k_nr_mask<16, 3, true>), gm, kMaskThreads, kSmoothSmem, st, A, CF, CB, Msm, g, NT, sp, b);
+        else OSB_LAUNCH((k_nr_mask<kNfMax, kNtMax, false>), gm, kMaskThreads, kSmoothSmem, st, A, CF, CB, Msm, g, NT, sp, b);
         OSB_CHECK_LAUNCH();
         OSB_LAUNCH(k_nr_istft, dim3(tiles, g.n_chunks, gb), 256, kIstftSmem, st, S, Msm, g, tabs, j_first, outp);
         OSB_CHECK_LAUNCH();
