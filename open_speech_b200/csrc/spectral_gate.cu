@@ -104,7 +104,6 @@ __device__ __forceinline__ float fast_mag(float re, float im) {
 // ---------------------------------------------------------------- forward STFT
 // grid (ceil(F/16), n_chunks, batch), 256 threads.  S[((clip*n_chunks+chunk)*F + t)*513 + f]
 constexpr int kStftFrames = 16, kStftXs = NH * (kStftFrames - 1) + NF;  // 4864
-constexpr int kStftLow = (kStftXs + 3 * NF) > kStftFrames * NB ? (kStftXs + 3 * NF) : kStftFrames * NB;  // 8208 floats
 
 __global__ void __launch_bounds__(256, 2) k_nr_stft(const void* __restrict__ audio, NrGeom g, const float* __restrict__ tabs,
                                                     float2* __restrict__ S, float* __restrict__ A, float2* __restrict__ PR, double b) {
@@ -113,8 +112,7 @@ __global__ void __launch_bounds__(256, 2) k_nr_stft(const void* __restrict__ aud
     float* win = xs + kStftXs;      // [1024]
     float* twc = win + NF;          // [1024]
     float* tws = twc + NF;          // [1024]
-    float* Amat = sm;               // [16][513] magnitudes of this tile; aliases xs/win/tw, which are dead after step 1
-    float* Y = sm + kStftLow;       // [8][2][32*33]
+    float* Y = tws + NF;            // [8][2][32*33]; at the end plane k holds the 513 magnitudes of frame t0 + k
     const int tid = threadIdx.x, t0 = blockIdx.x * kStftFrames, chunk = blockIdx.y, clip = blockIdx.z;
     if (t0 >= nr_tlim(g, chunk)) {  // all-zero tile: only its (zero) aggregates exist
         for (int f = tid; f < NB; f += 256) PR[(((long long)clip * g.n_chunks + chunk) * gridDim.x + blockIdx.x) * NB + f] = make_float2(0.f, 0.f);
@@ -152,71 +150,81 @@ __global__ void __launch_bounds__(256, 2) k_nr_stft(const void* __restrict__ aud
         }
     }
     __syncthreads();
-    {   // step 1: 8 frame pairs x 32 residues.  n = 32*n1 + n2
-        const int q = tid >> 5, n2 = tid & 31;
+    // From here to the aggregates every warp works on its own frame pair and its own two planes: warp-level barriers only,
+    // so the eight warps drift apart and overlap each other's shared-memory and arithmetic phases.
+    const int q = tid >> 5, lane = tid & 31;
+    float* yr = Y + q * 2 * kYPlane;
+    float* yi = yr + kYPlane;
+    {   // step 1: 32 residues of the pair.  n = 32*n1 + n2, n2 = lane
         const float* xa = xs + (2 * q) * NH;
         const float* xb = xa + NH;
         cpx v[32];
 #pragma unroll
         for (int n1 = 0; n1 < 32; ++n1) {
-            const int idx = 32 * n1 + n2;
+            const int idx = 32 * n1 + lane;
             const float w = win[idx];
             v[n1] = cpx{xa[idx] * w, xb[idx] * w};
         }
         fft_pow2<32>(v);
-        float* yr = Y + q * 2 * kYPlane;
-        float* yi = yr + kYPlane;
 #pragma unroll
         for (int k1 = 0; k1 < 32; ++k1) {
-            const int tw = k1 * 32 + n2;
+            const int tw = k1 * 32 + lane;
             const cpx y = cmul(v[k1], cpx{twc[tw], -tws[tw]});
-            yr[k1 * kYs + n2] = y.x;
-            yi[k1 * kYs + n2] = y.y;
+            yr[k1 * kYs + lane] = y.x;
+            yi[k1 * kYs + lane] = y.y;
         }
     }
-    __syncthreads();
-    {   // step 2: 32-point FFT over n2 for each (pair, k1): Z[k1 + 32*k2] stored at [k1][k2]
-        const int q = tid >> 5, k1 = tid & 31;
-        float* yr = Y + q * 2 * kYPlane;
-        float* yi = yr + kYPlane;
+    __syncwarp();
+    {   // step 2: 32-point FFT over n2 for each k1 = lane: Z[k1 + 32*k2] stored at [k1][k2]
         cpx v[32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = cpx{yr[k1 * kYs + i], yi[k1 * kYs + i]};
+        for (int i = 0; i < 32; ++i) v[i] = cpx{yr[lane * kYs + i], yi[lane * kYs + i]};
         fft_pow2<32>(v);
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-            yr[k1 * kYs + i] = v[i].x;
-            yi[k1 * kYs + i] = v[i].y;
+            yr[lane * kYs + i] = v[i].x;
+            yi[lane * kYs + i] = v[i].y;
         }
     }
-    __syncthreads();
+    __syncwarp();
     // split the packed transform into the two one-sided spectra, apply the spectrum scaling 1/sum(win) = 1/512
     const float sc = 0.5f / 512.0f;
     const long long row0 = ((long long)clip * g.n_chunks + chunk) * g.F;
     {
-        const int q = tid >> 5, lane = tid & 31;  // warp q owns frame pair q
         const int ta = t0 + 2 * q;
+        float ma[17], mb[17];
         if (ta < g.F) {
-            const float* yr = Y + q * 2 * kYPlane;
-            const float* yi = yr + kYPlane;
             const bool has_b = ta + 1 < g.F;
             float2* Sa = S + (row0 + ta) * NB;
             float* Aa = A + (row0 + ta) * NB;
-            for (int f = lane; f < NB; f += 32) {
-                const int m = (NF - f) & (NF - 1);
-                const int a0 = (f & 31) * kYs + (f >> 5), a1 = (m & 31) * kYs + (m >> 5);
-                const float zr = yr[a0], zi = yi[a0], wr = yr[a1], wi = yi[a1];
-                // X_a = (Z[f] + conj Z[N-f])/2 ; X_b = (Z[f] - conj Z[N-f])/(2i)
-                const float ar = (zr + wr) * sc, ai = (zi - wi) * sc, br = (zi + wi) * sc, bi = (wr - zr) * sc;
-                const float ma = fast_mag(ar, ai), mb = fast_mag(br, bi);
-                Sa[f] = make_float2(ar, ai);
-                Aa[f] = ma;
-                Amat[(2 * q) * NB + f] = ma;
-                if (has_b) {
-                    Sa[NB + f] = make_float2(br, bi);
-                    Aa[NB + f] = mb;
-                    Amat[(2 * q + 1) * NB + f] = mb;
+#pragma unroll
+            for (int i = 0; i < 17; ++i) {
+                const int f = lane + 32 * i;
+                ma[i] = 0.f; mb[i] = 0.f;
+                if (f < NB) {
+                    const int m = (NF - f) & (NF - 1);
+                    const int a0 = (f & 31) * kYs + (f >> 5), a1 = (m & 31) * kYs + (m >> 5);
+                    const float zr = yr[a0], zi = yi[a0], wr = yr[a1], wi = yi[a1];
+                    // X_a = (Z[f] + conj Z[N-f])/2 ; X_b = (Z[f] - conj Z[N-f])/(2i)
+                    const float ar = (zr + wr) * sc, ai = (zi - wi) * sc, br = (zi + wi) * sc, bi = (wr - zr) * sc;
+                    ma[i] = fast_mag(ar, ai);
+                    mb[i] = fast_mag(br, bi);
+                    Sa[f] = make_float2(ar, ai);
+                    Aa[f] = ma[i];
+                    if (has_b) {
+                        Sa[NB + f] = make_float2(br, bi);
+                        Aa[NB + f] = mb[i];
+                    }
                 }
+            }
+        }
+        __syncwarp();
+        // the magnitudes of the pair replace its planes: row 2q at yr[0..513), row 2q+1 at yi[0..513)
+        if (ta < g.F) {
+#pragma unroll
+            for (int i = 0; i < 17; ++i) {
+                const int f = lane + 32 * i;
+                if (f < NB) { yr[f] = ma[i]; yi[f] = mb[i]; }
             }
         }
     }
@@ -230,7 +238,7 @@ __global__ void __launch_bounds__(256, 2) k_nr_stft(const void* __restrict__ aud
         for (int f = tid; f < NB; f += 256) {
             double lf = 0.0, R = 0.0, bpw = b;
             for (int k = 0; k < L; ++k) {
-                lf = fma(a, lf, b * (double)Amat[k * NB + f]);
+                lf = fma(a, lf, b * (double)Y[k * kYPlane + f]);
                 R = fma(bpw, lf, R);
                 bpw *= a;
             }
@@ -521,76 +529,99 @@ __global__ void __launch_bounds__(256, 2) k_nr_istft(const float2* __restrict__ 
     for (int i = tid; i < kOlaOut; i += 256) acc[i] = 0.f;
     const long long row0 = ((long long)clip * g.n_chunks + chunk) * g.F;
     __syncthreads();
+    // Each warp owns one frame pair and its two planes through staging and both FFT steps (warp-level barriers only);
+    // the CTA only meets for the overlap-add.
+    const int q = tid >> 5, lane = tid & 31;
+    float* yr = Y + q * 2 * kYPlane;
+    float* yi = yr + kYPlane;
+    float wreg[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) wreg[j] = win[tid + 256 * j];
     for (int pass = 0; pass < 2; ++pass) {
         const int tp0 = j0 - 1 + pass * 16;
         if (tp0 >= TL) break;  // only zero frames left
-        {   // stage Z'[k] = Xa[k] + i Xb[k] for the 8 frame pairs of this pass, k stored at [k>>5][k&31] (row stride 33):
-            // Xa/Xb are the masked one-sided spectra S*Msm extended by Hermitian symmetry; every S cell is read once, coalesced
-            const int q = tid >> 5, lane = tid & 31;  // warp q owns pair q
+        {   // stage Z'[k] = Xa[k] + i Xb[k], k stored at [k>>5][k&31] (row stride 33): Xa/Xb are the masked one-sided
+            // spectra S*Msm extended by Hermitian symmetry; every S cell is read once, coalesced, four bins in flight
             const int ta = tp0 + 2 * q, tb = ta + 1;
             const bool va = ta >= 0 && ta < TL, vb = tb >= 0 && tb < TL;
-            float* yr = Y + q * 2 * kYPlane;
-            float* yi = yr + kYPlane;
             const float2* Sa = S + (row0 + ta) * NB;
             const float* Ma = Msm + (row0 + ta) * NB;
-            for (int f = lane; f < NB; f += 32) {
-                float ar = 0.f, ai = 0.f, br = 0.f, bi = 0.f;
-                if (va) { const float2 sv = Sa[f]; const float m = Ma[f]; ar = sv.x * m; ai = sv.y * m; }
-                if (vb) { const float2 sv = Sa[NB + f]; const float m = Ma[NB + f]; br = sv.x * m; bi = sv.y * m; }
-                if (f == 0 || f == 512) { ai = 0.f; bi = 0.f; }  // irfft ignores the imaginary part of DC / Nyquist
-                const int k0 = (f >> 5) * kYs + (f & 31);
-                yr[k0] = ar - bi;
-                yi[k0] = ai + br;
-                if (f != 0 && f != 512) {  // mirror bin N-f: conj(Xa[f]) + i conj(Xb[f])
-                    const int km = NF - f, k1 = (km >> 5) * kYs + (km & 31);
-                    yr[k1] = ar + bi;
-                    yi[k1] = br - ai;
+#pragma unroll
+            for (int ib = 0; ib < 16; ib += 4) {
+                float2 sa[4], sb[4];
+                float ma[4], mb[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int f = lane + 32 * (ib + u);
+                    sa[u] = va ? Sa[f] : make_float2(0.f, 0.f);
+                    ma[u] = va ? Ma[f] : 0.f;
+                    sb[u] = vb ? Sa[NB + f] : make_float2(0.f, 0.f);
+                    mb[u] = vb ? Ma[NB + f] : 0.f;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int f = lane + 32 * (ib + u);
+                    const float ar = sa[u].x * ma[u], br = sb[u].x * mb[u];
+                    float ai = sa[u].y * ma[u], bi = sb[u].y * mb[u];
+                    if (f == 0) { ai = 0.f; bi = 0.f; }  // irfft ignores the imaginary part of DC
+                    const int k0 = (ib + u) * kYs + lane;
+                    yr[k0] = ar - bi;
+                    yi[k0] = ai + br;
+                    if (f != 0) {  // mirror bin N-f: conj(Xa[f]) + i conj(Xb[f])
+                        const int km = NF - f, k1 = (km >> 5) * kYs + (km & 31);
+                        yr[k1] = ar + bi;
+                        yi[k1] = br - ai;
+                    }
                 }
             }
+            if (lane == 0) {  // Nyquist: real part only
+                const float ar = va ? Sa[512].x * Ma[512] : 0.f, br = vb ? Sa[NB + 512].x * Ma[NB + 512] : 0.f;
+                yr[16 * kYs] = ar;
+                yi[16 * kYs] = br;
+            }
         }
-        __syncthreads();
-        {   // step 1 of the inverse (conjugate twiddles), in place: thread (q, b) owns column b of pair q
-            const int q = tid >> 5, bb = tid & 31;
-            float* yr = Y + q * 2 * kYPlane;
-            float* yi = yr + kYPlane;
+        __syncwarp();
+        {   // step 1 of the inverse (conjugate twiddles), in place: lane owns column `lane` of the pair
             cpx v[32];
 #pragma unroll
-            for (int a = 0; a < 32; ++a) v[a] = cpx{yr[a * kYs + bb], yi[a * kYs + bb]};
+            for (int a = 0; a < 32; ++a) v[a] = cpx{yr[a * kYs + lane], yi[a * kYs + lane]};
             fft_pow2<32, true>(v);
 #pragma unroll
             for (int c = 0; c < 32; ++c) {
-                const int tw = c * 32 + bb;
+                const int tw = c * 32 + lane;
                 const cpx y = cmul(v[c], cpx{twc[tw], tws[tw]});
-                yr[c * kYs + bb] = y.x;
-                yi[c * kYs + bb] = y.y;
+                yr[c * kYs + lane] = y.x;
+                yi[c * kYs + lane] = y.y;
             }
         }
-        __syncthreads();
+        __syncwarp();
         {
-            const int q = tid >> 5, c = tid & 31;
-            float* yr = Y + q * 2 * kYPlane;
-            float* yi = yr + kYPlane;
             cpx v[32];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = cpx{yr[c * kYs + i], yi[c * kYs + i]};
+            for (int i = 0; i < 32; ++i) v[i] = cpx{yr[lane * kYs + i], yi[lane * kYs + i]};
             fft_pow2<32, true>(v);
 #pragma unroll
             for (int i = 0; i < 32; ++i) {  // z[n = c + 32 d] at [c][d]
-                yr[c * kYs + i] = v[i].x;
-                yi[c * kYs + i] = v[i].y;
+                yr[lane * kYs + i] = v[i].x;
+                yi[lane * kYs + i] = v[i].y;
             }
         }
         __syncthreads();
-        // overlap-add the 16 frames of this pass.  Sample n of frame t lands on u = 256 (t - j0) + n - 512, and with
-        // n = tid + 256 j every thread only ever touches u == tid (mod 256): no conflicts, no barrier between frames.
-#pragma unroll 4
-        for (int lt = 0; lt < 16; ++lt) {
-            const float* pl = Y + (lt >> 1) * 2 * kYPlane + (lt & 1) * kYPlane;
-            const int ub = 256 * (tp0 + lt - j0 - 2) + tid;
+        // overlap-add the 16 frames of this pass.  Sample n = tid + 256 j of frame lt lands on hop block
+        // m = lt + j + 16 pass - 3 at offset tid: each thread sums the (up to four) frames meeting in a block in
+        // registers and touches acc[256 m + tid] once.
+        {
+            const float* pb = Y + lane * kYs + q;  // element n = tid + 256 j of a plane sits at pb[8 j]
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int u = ub + 256 * j, n = tid + 256 * j;
-                if (u >= 0 && u < kOlaOut) acc[u] = fmaf(pl[(n & 31) * kYs + (n >> 5)], win[n], acc[u]);
+            for (int mm = 0; mm < 19; ++mm) {
+                float sacc = 0.f;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int lt = mm - j;
+                    if (lt >= 0 && lt < 16) sacc = fmaf(pb[lt * kYPlane + 8 * j], wreg[j], sacc);
+                }
+                const int m = mm + 16 * pass - 3;
+                if (m >= 0 && m < kOlaBlocks) acc[256 * m + tid] += sacc;
             }
         }
         __syncthreads();
@@ -604,7 +635,7 @@ __global__ void __launch_bounds__(256, 2) k_nr_istft(const float2* __restrict__ 
     }
 }
 
-constexpr int kStftSmem = (kStftLow + 8 * 2 * kYPlane) * (int)sizeof(float);
+constexpr int kStftSmem = (kStftXs + 3 * NF + 8 * 2 * kYPlane) * (int)sizeof(float);
 constexpr int kSmoothSmem = kSmT * kSmWTap * (int)sizeof(float);
 constexpr int kIstftSmem = (3 * NF + NH + 8 * 2 * kYPlane + kOlaOut) * (int)sizeof(float);
 
