@@ -68,9 +68,10 @@ int osb_stt_frontend_host(const int16_t* pcm, int64_t n, int64_t batch, int64_t 
         OSB_CUDA(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
         s_dev = ws.device;
     }
-    // clip groups (default 4; OSB_STT_HOST_GROUPS=1..8 to tune): more groups = more copy/compute overlap but smaller launches
+    // clip groups (default 8 for large batches; OSB_STT_HOST_GROUPS=1..8 to tune): more groups = shorter pipeline fill and
+    // drain around the PCIe-bound middle, but smaller launches
     int64_t bounds[9] = {0};
-    int groups = batch >= 16 ? 4 : 1;
+    int groups = batch >= 64 ? 8 : (batch >= 16 ? 4 : 1);
     if (const char* e = getenv("OSB_STT_HOST_GROUPS")) {
         const int g = atoi(e);
         if (g >= 1 && g <= 8 && g <= batch) groups = g;
