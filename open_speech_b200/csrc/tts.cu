@@ -15,6 +15,10 @@
 #include <cmath>
 #include <vector>
 
+#include <map>
+#include <mutex>
+#include <utility>
+
 #include "common.cuh"
 
 namespace osb {
@@ -147,6 +151,43 @@ __global__ void __launch_bounds__(256) k_fx_finish(const T* __restrict__ x, Ragg
     }
 }
 
+// ---------------------------------------------------------------- fusing the element-wise effects into their neighbours
+// A normalise that precedes reverb / podcast_eq on float32 data is not materialised: the recurrence kernel multiplies
+// by the per-utterance float32 gain while it loads (FxPre), which yields exactly the float32 values k_fx_scale would
+// have stored.  A robot effect and the final cast that follow a recurrence kernel are applied to the float64 value it
+// is about to store (FxPost): same arithmetic as k_fx_robot / k_fx_finish, one HBM round trip less each.
+struct FxPre {
+    const double* sumsq;  // per-utterance sum of squares (null: no deferred normalise)
+    double target_rms;
+};
+struct FxPost {
+    int robot;    // multiply by the 100 Hz carrier sin(2 pi 100 n / sr) in float64
+    int finish;   // 0: store float64 to the chain buffer; 1: astype(float32) -> out; 2: float32_to_int16 -> out
+    int period;   // carrier period in samples, sr / gcd(100, sr)
+    const double* carrier;  // [period] sin(2*pi*100*(k/sr)) evaluated like numpy for n = k (host table); for n = k + m*period
+                            // numpy's own value differs from it by the rounding of its growing argument (~1e-13)
+    void* out;
+};
+
+__device__ __forceinline__ float fx_pre_scale(const FxPre& pre, int b, long long n, bool* on) {
+    *on = false;
+    if (!pre.sumsq || n == 0) return 1.0f;
+    const float rms = __fsqrt_rn((float)(pre.sumsq[b] / (double)n));
+    *on = !(rms < 1e-8f);
+    return (float)pre.target_rms / rms;  // python float / np.float32 -> np.float32
+}
+template <typename T>
+__device__ __forceinline__ T fx_ld(const T* p, long long g, bool on, float scale) {
+    if (sizeof(T) == 4 && on) return (T)__fmul_rn((float)p[g], scale);
+    return p[g];
+}
+__device__ __forceinline__ void fx_st(const FxPost& post, double* q, long long off, long long g, double v) {
+    if (post.robot) v = v * post.carrier[(unsigned)g % (unsigned)post.period];  // utterances are shorter than 2^31 samples (checked by the caller)
+    if (post.finish == 0) q[g] = v;
+    else if (post.finish == 1) reinterpret_cast<float*>(post.out)[off + g] = (float)v;
+    else reinterpret_cast<int16_t*>(post.out)[off + g] = (int16_t)quant_pcm16((float)v);
+}
+
 // ---------------------------------------------------------------- reverb: exp-decay FIR as a one-pole recurrence
 // wet[n] = sum_{k<L} ir[k] x[n-k], ir[k] = c r^k  =>  wet[n] = r wet[n-1] + c (x[n] - r^L x[n-L])
 // out = (1-mix) x + mix wet.  CTA = 8192 samples; wet[n0-1] comes from the direct FIR sum with the exact
@@ -162,7 +203,7 @@ struct ReverbArgs {
 };
 
 template <typename T>
-__global__ void __launch_bounds__(256) k_fx_reverb(const T* __restrict__ x, ReverbArgs a, double* __restrict__ y) {
+__global__ void __launch_bounds__(256) k_fx_reverb(const T* __restrict__ x, ReverbArgs a, FxPre pre, FxPost post, double* __restrict__ y) {
     extern __shared__ __align__(16) double smd[];
     double* u = smd;                 // [256][33]
     __shared__ double red[8];
@@ -172,20 +213,48 @@ __global__ void __launch_bounds__(256) k_fx_reverb(const T* __restrict__ x, Reve
     const long long n0 = (long long)blockIdx.x * kRvBlock;
     if (n0 >= n) return;
     const T* p = x + a.rg.offsets[b];
-    // stage u[i] = c (x[n0+i] - r^L x[n0+i-L])
-    for (int i = tid; i < kRvBlock; i += 256) {
-        const long long g = n0 + i;
-        const double xv = g < n ? (double)p[g] : 0.0;
-        const double xd = (g - a.L >= 0 && g - a.L < n) ? (double)p[g - a.L] : 0.0;
-        u[(i / kRvT) * kSegStride + (i % kRvT)] = a.c * (xv - a.rL * xd);
-    }
-    // carry-in wet[n0-1] = sum_k ir[k] x[n0-1-k]
-    double part = 0.0;
-    if (n0 > 0)
-        for (int k = tid; k < a.L; k += 256) {
-            const long long g = n0 - 1 - k;
-            if (g >= 0) part = fma(a.ir[k], (double)p[g], part);
+    bool pon;
+    const float pscale = fx_pre_scale(pre, b, n, &pon);
+    // stage u[i] = c (x[n0+i] - r^L x[n0+i-L]); eight samples' loads in flight per thread
+#pragma unroll 1
+    for (int i0 = tid; i0 < kRvBlock; i0 += 256 * 8) {
+        T xv[8], xd[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const long long g = n0 + i0 + 256 * j;
+            xv[j] = g < n ? p[g] : (T)0;
+            xd[j] = (g - a.L >= 0 && g - a.L < n) ? p[g - a.L] : (T)0;
         }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int i = i0 + 256 * j;
+            const double v = (sizeof(T) == 4 && pon) ? (double)__fmul_rn((float)xv[j], pscale) : (double)xv[j];
+            const double d = (sizeof(T) == 4 && pon) ? (double)__fmul_rn((float)xd[j], pscale) : (double)xd[j];
+            u[(i / kRvT) * kSegStride + (i % kRvT)] = a.c * (v - a.rL * d);
+        }
+    }
+    // carry-in wet[n0-1] = sum_k ir[k] x[n0-1-k]; four taps' loads in flight per thread
+    double part = 0.0;
+    if (n0 > 0) {
+#pragma unroll 1
+        for (int k0 = tid; k0 < a.L; k0 += 256 * 4) {
+            T xv[4];
+            double iv[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int k = k0 + 256 * j;
+                const long long g = n0 - 1 - k;
+                const bool ok = k < a.L && g >= 0;
+                xv[j] = ok ? p[g] : (T)0;
+                iv[j] = ok ? a.ir[k] : 0.0;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const double v = (sizeof(T) == 4 && pon) ? (double)__fmul_rn((float)xv[j], pscale) : (double)xv[j];
+                part = fma(iv[j], v, part);
+            }
+        }
+    }
     part = warp_sum(part);
     if ((tid & 31) == 0) red[tid >> 5] = part;
     __syncthreads();
@@ -226,12 +295,24 @@ __global__ void __launch_bounds__(256) k_fx_reverb(const T* __restrict__ x, Reve
     }
     __syncthreads();
     double* q = y + a.rg.offsets[b];
-    for (int i = tid; i < kRvBlock; i += 256) {
-        const long long g = n0 + i;
-        if (g < n) {
-            // (1 - mix) * samples is a float32 product while samples is still float32 (NEP 50 weak scalar)
-            const double dry = (sizeof(T) == 4) ? (double)__fmul_rn((float)(1.0 - a.mix), (float)p[g]) : (1.0 - a.mix) * (double)p[g];
-            q[g] = dry + a.mix * u[(i / kRvT) * kSegStride + (i % kRvT)];
+#pragma unroll 1
+    for (int i0 = tid; i0 < kRvBlock; i0 += 256 * 8) {
+        T xv[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const long long g = n0 + i0 + 256 * j;
+            xv[j] = g < n ? p[g] : (T)0;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int i = i0 + 256 * j;
+            const long long g = n0 + i;
+            if (g < n) {
+                // (1 - mix) * samples is a float32 product while samples is still float32 (NEP 50 weak scalar)
+                const T xg = (sizeof(T) == 4 && pon) ? (T)__fmul_rn((float)xv[j], pscale) : xv[j];
+                const double dry = (sizeof(T) == 4) ? (double)__fmul_rn((float)(1.0 - a.mix), (float)xg) : (1.0 - a.mix) * (double)xg;
+                fx_st(post, q, a.rg.offsets[b], g, dry + a.mix * u[(i / kRvT) * kSegStride + (i % kRvT)]);
+            }
         }
     }
 }
@@ -269,7 +350,7 @@ __device__ __forceinline__ double eq_step(const EqArgs& a, St4& s, double x) {
 }
 
 template <typename T>
-__global__ void __launch_bounds__(256) k_fx_eq(const T* __restrict__ x, EqArgs a, double* __restrict__ y) {
+__global__ void __launch_bounds__(256) k_fx_eq(const T* __restrict__ x, EqArgs a, FxPre pre, FxPost post, double* __restrict__ y) {
     extern __shared__ __align__(16) double smd[];
     double* u = smd;  // [256][33]
     __shared__ St4 wsum[8];
@@ -279,9 +360,21 @@ __global__ void __launch_bounds__(256) k_fx_eq(const T* __restrict__ x, EqArgs a
     if (n0 >= n) return;
     const T* p = x + a.rg.offsets[b];
     const long long base = n0 - kEqWarm;
-    for (int i = tid; i < kEqWarm + kEqOut; i += 256) {
-        const long long g = base + i;
-        u[(i / 32) * kSegStride + (i % 32)] = (g >= 0 && g < n) ? (double)p[g] : 0.0;
+    bool pon;
+    const float pscale = fx_pre_scale(pre, b, n, &pon);
+#pragma unroll 1
+    for (int i0 = tid; i0 < kEqWarm + kEqOut; i0 += 256 * 8) {
+        T xv[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const long long g = base + i0 + 256 * j;
+            xv[j] = (g >= 0 && g < n) ? p[g] : (T)0;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int i = i0 + 256 * j;
+            u[(i / 32) * kSegStride + (i % 32)] = (sizeof(T) == 4 && pon) ? (double)__fmul_rn((float)xv[j], pscale) : (double)xv[j];
+        }
     }
     __syncthreads();
     double* seg = u + tid * kSegStride;
@@ -340,7 +433,7 @@ __global__ void __launch_bounds__(256) k_fx_eq(const T* __restrict__ x, EqArgs a
     double* q = y + a.rg.offsets[b];
     for (int i = kEqWarm + tid; i < kEqWarm + kEqOut; i += 256) {
         const long long g = base + i;
-        if (g < n) q[g] = u[(i / 32) * kSegStride + (i % 32)];
+        if (g < n) fx_st(post, q, a.rg.offsets[b], g, u[(i / 32) * kSegStride + (i % 32)]);
     }
 }
 
@@ -451,9 +544,43 @@ struct FxState {
     float* f32_tmp;  // scratch buffers (total elements each)
     double* d_a;
     double* d_b;
+    FxPre pre{nullptr, 0.0};          // deferred float32 normalise, consumed by the next recurrence kernel
+    FxPost post{0, 0, 1, nullptr, nullptr};  // robot / final cast riding on the next recurrence kernel
+    bool finished = false;            // the final cast already happened inside a kernel
 };
 
-static int fx_normalize(FxState& s, double target_lufs, Scratch& scr) {
+// one period of the robot carrier, cached per (device, sample rate)
+static int robot_carrier(int sample_rate, const double** d_tab, int* period) {
+    static std::mutex mu;
+    static std::map<std::pair<int, int>, double*> cache;
+    int dev = 0;
+    OSB_CUDA(cudaGetDevice(&dev));
+    int a = 100, bb = sample_rate;
+    while (bb) { const int t = a % bb; a = bb; bb = t; }
+    *period = sample_rate / a;
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find({dev, sample_rate});
+    if (it == cache.end()) {
+        std::vector<double> h(*period);
+        const double w = 2 * 3.141592653589793 * 100;  // 2 * np.pi * 100
+        for (int k = 0; k < *period; ++k) h[k] = std::sin(w * ((double)k / (double)sample_rate));
+        double* d = nullptr;
+        OSB_CUDA(cudaMalloc(&d, h.size() * sizeof(double)));
+        OSB_CUDA(cudaMemcpy(d, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice));
+        it = cache.emplace(std::make_pair(dev, sample_rate), d).first;
+    }
+    *d_tab = it->second;
+    return OSB_OK;
+}
+
+static void fx_after_recurrence(FxState& s, double* dst) {
+    if (s.post.finish) s.finished = true;
+    else { s.cur = dst; s.f64 = true; }
+    s.pre = FxPre{nullptr, 0.0};
+    s.post = FxPost{0, 0, 1, nullptr, nullptr};
+}
+
+static int fx_normalize(FxState& s, double target_lufs, Scratch& scr, bool defer) {
     double* sumsq;
     OSB_CUDA(scr.alloc(&sumsq, (size_t)s.batch));
     OSB_CUDA(cudaMemsetAsync(sumsq, 0, sizeof(double) * s.batch, s.st));
@@ -462,6 +589,10 @@ static int fx_normalize(FxState& s, double target_lufs, Scratch& scr) {
     if (!s.f64) {
         OSB_LAUNCH(k_fx_sumsq<float>, g, 256, 0, s.st, (const float*)s.cur, s.rg, sumsq);
         OSB_CHECK_LAUNCH();
+        if (defer) {  // the next effect is a recurrence kernel: it applies the gain while loading
+            s.pre = FxPre{sumsq, target_rms};
+            return OSB_OK;
+        }
         OSB_LAUNCH(k_fx_scale<float>, g, 256, 0, s.st, (const float*)s.cur, s.rg, sumsq, target_rms, s.f32_tmp);
         OSB_CHECK_LAUNCH();
         s.cur = s.f32_tmp;
@@ -511,11 +642,10 @@ static int fx_reverb(FxState& s, int sample_rate, int room_ms, double mix, Scrat
         OSB_CUDA(cudaFuncSetAttribute(k_fx_eq<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_done = true;
     }
-    if (!s.f64) OSB_LAUNCH(k_fx_reverb<float>, g, 256, smem, s.st, (const float*)s.cur, a, dst);
-    else OSB_LAUNCH(k_fx_reverb<double>, g, 256, smem, s.st, (const double*)s.cur, a, dst);
+    if (!s.f64) OSB_LAUNCH(k_fx_reverb<float>, g, 256, smem, s.st, (const float*)s.cur, a, s.pre, s.post, dst);
+    else OSB_LAUNCH(k_fx_reverb<double>, g, 256, smem, s.st, (const double*)s.cur, a, s.pre, s.post, dst);
     OSB_CHECK_LAUNCH();
-    s.cur = dst;
-    s.f64 = true;
+    fx_after_recurrence(s, dst);
     return OSB_OK;
 }
 
@@ -541,11 +671,10 @@ static int fx_eq(FxState& s, int sample_rate) {
         OSB_CUDA(cudaFuncSetAttribute(k_fx_eq<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_done = true;
     }
-    if (!s.f64) OSB_LAUNCH(k_fx_eq<float>, g, 256, smem, s.st, (const float*)s.cur, a, dst);
-    else OSB_LAUNCH(k_fx_eq<double>, g, 256, smem, s.st, (const double*)s.cur, a, dst);
+    if (!s.f64) OSB_LAUNCH(k_fx_eq<float>, g, 256, smem, s.st, (const float*)s.cur, a, s.pre, s.post, dst);
+    else OSB_LAUNCH(k_fx_eq<double>, g, 256, smem, s.st, (const double*)s.cur, a, s.pre, s.post, dst);
     OSB_CHECK_LAUNCH();
-    s.cur = dst;
-    s.f64 = true;
+    fx_after_recurrence(s, dst);
     return OSB_OK;
 }
 
@@ -594,7 +723,7 @@ int osb_fx_chain_dev(const float* d_in, const int64_t* d_offsets, const int64_t*
                      void* d_out, int out_pcm16, void* stream) {
     int rc = ensure_init();
     if (rc) return rc;
-    OSB_REQUIRE(batch >= 0 && max_len >= 0 && total >= 0 && n_fx >= 0 && sample_rate > 0, "bad sizes");
+    OSB_REQUIRE(batch >= 0 && max_len >= 0 && max_len < (1ll << 31) && total >= 0 && n_fx >= 0 && sample_rate > 0, "bad sizes");
     if (batch == 0 || total == 0) return OSB_OK;
     OSB_REQUIRE(batch <= 65535, "batch too large (<= 65535)");
     OSB_REQUIRE(d_in && d_offsets && d_lens && d_out && (n_fx == 0 || (fx_types && fx_p0 && fx_p1)), "null buffer");
@@ -607,23 +736,42 @@ int osb_fx_chain_dev(const float* d_in, const int64_t* d_offsets, const int64_t*
     OSB_CUDA(scr.alloc(&s.f32_tmp, (size_t)total));
     OSB_CUDA(scr.alloc(&s.d_a, (size_t)total));
     OSB_CUDA(scr.alloc(&s.d_b, (size_t)total));
+    // effective chain: unknown types and zero pitch shifts are no-ops (chain.py:18-31, :46-47)
+    int idx[64], m = 0;
     for (int i = 0; i < n_fx; ++i) {
+        const int t = fx_types[i];
+        const bool live = t == OSB_FX_NORMALIZE || t == OSB_FX_REVERB || t == OSB_FX_PODCAST_EQ || t == OSB_FX_ROBOT ||
+                          (t == OSB_FX_PITCH && fx_p0[i] != 0.0);
+        if (!live) continue;
+        OSB_REQUIRE(m < 64, "more than 64 effects");
+        idx[m++] = i;
+    }
+    auto is_rec = [&](int k) { return k < m && (fx_types[idx[k]] == OSB_FX_REVERB || fx_types[idx[k]] == OSB_FX_PODCAST_EQ); };
+    for (int k = 0; k < m; ++k) {
+        const int i = idx[k];
+        if (is_rec(k)) {  // let a following robot and the final cast ride on this kernel's store
+            if (k + 1 < m && fx_types[idx[k + 1]] == OSB_FX_ROBOT) {
+                if ((rc = robot_carrier(sample_rate, &s.post.carrier, &s.post.period))) return rc;
+                s.post.robot = 1;
+            }
+            if (k + 1 + s.post.robot == m) { s.post.finish = out_pcm16 ? 2 : 1; s.post.out = d_out; }
+        }
         switch (fx_types[i]) {
-            case OSB_FX_NORMALIZE: rc = fx_normalize(s, fx_p0[i], scr); break;
-            case OSB_FX_REVERB: rc = fx_reverb(s, sample_rate, (int)fx_p0[i], fx_p1[i], scr); break;
-            case OSB_FX_PODCAST_EQ: rc = fx_eq(s, sample_rate); break;
+            case OSB_FX_NORMALIZE: rc = fx_normalize(s, fx_p0[i], scr, !s.f64 && is_rec(k + 1)); break;
+            case OSB_FX_REVERB: { const int rob = s.post.robot; rc = fx_reverb(s, sample_rate, (int)fx_p0[i], fx_p1[i], scr); k += rob; break; }
+            case OSB_FX_PODCAST_EQ: { const int rob = s.post.robot; rc = fx_eq(s, sample_rate); k += rob; break; }
             case OSB_FX_ROBOT: rc = fx_robot(s, sample_rate); break;
             case OSB_FX_PITCH:
-                if (fx_p0[i] == 0.0) { rc = OSB_OK; break; }  // identity (chain.py:46-47)
                 // x.astype(float32) -> float32 result (chain.py:48); f32_tmp may be the input: every group is read before it is written
                 rc = launch_pitch_shift(s.cur, s.f64, s.rg.offsets, s.rg.lens, s.batch, s.max_len, sample_rate, fx_p0[i], s.f32_tmp, st);
                 s.cur = s.f32_tmp;
                 s.f64 = false;
                 break;
-            default: rc = OSB_OK; break;  // unknown effect types are skipped silently (chain.py:18-31)
+            default: rc = OSB_OK; break;
         }
         if (rc) return rc;
     }
+    if (s.finished) return OSB_OK;
     const dim3 g = ragged_grid(s.max_len, batch);
     if (s.f64) {
         if (out_pcm16) OSB_LAUNCH((k_fx_finish<double, true>), g, 256, 0, st, (const double*)s.cur, s.rg, d_out);
