@@ -318,11 +318,12 @@ __global__ void __launch_bounds__(256) k_fx_reverb(const T* __restrict__ x, Reve
 }
 
 // ---------------------------------------------------------------- podcast EQ: two DF2T biquads, 4-state linear system
-constexpr int kEqWarm = 4096, kEqOut = 4096;
+constexpr int kEqBlock = 8192, kEqWarmMax = 6144;  // samples per CTA (warm-up + outputs); the warm-up is sized per sample rate
 
 struct EqArgs {
     Ragged rg;
     double b1[3], a1[3], b2[3], a2[3];
+    int warm;         // warm-up samples (multiple of 32): |slowest pole|^warm < 1e-17
     double P[5][16];  // Phi_T^(2^k), k = 0..4 (row-major 4x4), T = 32 samples
     double Q[16];     // Phi_T^32
 };
@@ -356,6 +357,7 @@ __global__ void __launch_bounds__(256) k_fx_eq(const T* __restrict__ x, EqArgs a
     __shared__ St4 wsum[8];
     const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const long long n = a.rg.lens[b];
+    const int kEqWarm = a.warm, kEqOut = kEqBlock - a.warm;
     const long long n0 = (long long)blockIdx.x * kEqOut;
     if (n0 >= n) return;
     const T* p = x + a.rg.offsets[b];
@@ -653,12 +655,15 @@ static int fx_eq(FxState& s, int sample_rate) {
     EqArgs a;
     a.rg = s.rg;
     podcast_eq_coeffs((double)sample_rate, a);
-    // warm-up must outlast the slowest pole: |p|^kEqWarm < 1e-17
+    // warm-up must outlast the slowest pole: |p|^warm < 1e-17
     const double rad = std::sqrt(std::fmax(a.a1[2], a.a2[2]));
-    if (!(rad < 1.0) || kEqWarm * std::log(rad) > std::log(1e-17)) {
-        set_error("unsupported: podcast_eq at %d Hz needs a warm-up longer than %d samples", sample_rate, kEqWarm);
+    const double need = rad < 1.0 ? std::log(1e-17) / std::log(rad) : 1e30;
+    if (!(need <= kEqWarmMax)) {
+        set_error("unsupported: podcast_eq at %d Hz needs a warm-up longer than %d samples", sample_rate, kEqWarmMax);
         return OSB_ERR_UNSUPPORTED;
     }
+    a.warm = ((int)std::ceil(need) + 31) / 32 * 32;
+    const int kEqOut = kEqBlock - a.warm;
     eq_transition(a, 32, a.P[0]);
     for (int k = 1; k < 5; ++k) matmul4(a.P[k - 1], a.P[k - 1], a.P[k]);
     matmul4(a.P[4], a.P[4], a.Q);
