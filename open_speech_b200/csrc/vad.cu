@@ -44,6 +44,7 @@ struct VadModel {
     float *e4w, *e4b;  // [128][192]
     float *wih, *bsum; // [512][128], b_ih + b_hh
     float *whh;        // [512][128]
+    float *whh_perm;   // the same weights in the per-thread block order of k_vad_recur
     float *dw;         // [128]
     float db;
     // tcgen05 path: per layer, B as split-bf16 (hi, lo) tiles pre-arranged in the 128B-swizzled K-major
@@ -386,75 +387,134 @@ __global__ void __launch_bounds__(512, 1) k_vad_gemm_tc(GemmDesc d, const uint16
 }
 
 // ------------------------------------------------------------------ recurrence + head
-// one CTA (512 threads, thread = one gate row) per stream; W_hh row: 96 weights in registers,
-// 32 in shared memory (the register file holds exactly 64 K floats = all of W_hh, so part of it
-// must live elsewhere); h broadcast from shared memory.
-constexpr int kRegW = 96, kSmW = kHid - kRegW;
-
+// One CTA of 512 threads walks S streams in lock step; W_hh (64 K floats) stays in the CTA's registers (+ a slice in
+// shared memory: the register file is exactly 64 K words), so a step costs one pass over the weights for S streams.
+//
+// The hidden vector has to reach every FMA from shared memory, and the shared-memory pipe - not the FMA pipe - bounds
+// the step.  So a thread does not own one 128-long row (32 h loads per stream) but a 4-row x 32-column block (8 h
+// loads per stream): lane l of warp w holds W[32w + 4(l>>2) + i][32(l&3) + k], i < 4, k < 32, the four lanes of a
+// group combine their partial sums with two shuffle rounds, and each lane ends up with one finished gate row.
+// The matvec issues as packed FFMA2.  S is chosen so that the grid is at most one wave (148 CTAs).
 __device__ __forceinline__ float sigmoidf_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
+// cell non-linearities on the SFU (ex2 + rcp): absolute error ~1e-7, three decimal orders inside the 1e-3 probability
+// budget, and they sit on the serial chain of every step
+__device__ __forceinline__ float sigmoidf_fast(float x) { return __frcp_rn(1.0f + __expf(-x)); }
+__device__ __forceinline__ float tanhf_fast(float x) {
+    const float t = __expf(-2.0f * fabsf(x));
+    return copysignf((1.0f - t) * __frcp_rn(1.0f + t), x);
+}
 
+constexpr int kHq = 36;  // floats between the four 32-float quarters of h in shared memory: the quarters sit in different banks
+template <int S>
+struct RecurCfg {
+    static constexpr int RKG = S == 1 ? 6 : (S == 2 ? 5 : 3);  // of the 8 four-column groups of a thread's block, those kept in registers
+    static constexpr int SKG = 8 - RKG;
+    static constexpr int smem = (SKG * 4 * 4 * kGates + S * (4 * kHq + kGates) + kHid + 4 * S) * (int)sizeof(float);
+};
+__host__ __device__ inline int recur_own_row(int tid) {  // the gate row a thread holds after the shuffle reduction
+    const int q = tid & 3;
+    return (tid >> 5) * 32 + ((tid & 31) >> 2) * 4 + ((q & 1) << 1 | (q >> 1));
+}
+
+// whh_perm: float4 chunk c = i*8 + kg of thread tid at [(c*512 + tid)*4], i = row of the block, kg = column group
+template <int S>
 __global__ void __launch_bounds__(512, 1) k_vad_recur(const float* __restrict__ pre, long long pre_stream_stride, int n_steps,
-                                                      const float* __restrict__ whh, const float* __restrict__ dw, float db,
+                                                      const float4* __restrict__ whh_perm, const float* __restrict__ dw, float db,
                                                       float* __restrict__ state, float* __restrict__ probs, long long probs_stride,
-                                                      long long win0) {
+                                                      long long win0, int batch) {
+    constexpr int RKG = RecurCfg<S>::RKG, SKG = RecurCfg<S>::SKG;
     extern __shared__ __align__(16) float sm[];
-    float4* w_sm = reinterpret_cast<float4*>(sm);                 // [kSmW/4][512] float4
-    float* h_sm = sm + kSmW * kGates;                             // [128]
-    float* g_sm = h_sm + kHid;                                    // [512]
-    float* dw_sm = g_sm + kGates;                                 // [128]
-    const int row = threadIdx.x, b = blockIdx.x;
-    float w[kRegW];
+    float4* w_sm = reinterpret_cast<float4*>(sm);                 // [4][SKG][512] float4
+    float* h_sm = sm + SKG * 4 * 4 * kGates;                      // [S][4 quarters x 36]
+    float* g_sm = h_sm + S * 4 * kHq;                             // [S][512]
+    float* dw_sm = g_sm + S * kGates;                             // [128]
+    float* part_sm = dw_sm + kHid;                                // [S][4]
+    const int tid = threadIdx.x, q = tid & 3, b0 = blockIdx.x * S;
+    const int ns = min(S, batch - b0);                            // live streams of this CTA
+    const int own = recur_own_row(tid);
+    float4 w[4][RKG];
 #pragma unroll
-    for (int k = 0; k < kRegW; ++k) w[k] = whh[row * kHid + k];
+    for (int i = 0; i < 4; ++i) {
 #pragma unroll
-    for (int q = 0; q < kSmW / 4; ++q)
-        w_sm[q * kGates + row] = *reinterpret_cast<const float4*>(whh + row * kHid + kRegW + q * 4);
-    float c = 0.f;
-    float* st = state + (long long)b * 2 * kHid;
-    if (row < kHid) {
-        h_sm[row] = st[row];
-        c = st[kHid + row];
-        dw_sm[row] = dw[row];
+        for (int kg = 0; kg < RKG; ++kg) w[i][kg] = whh_perm[(i * 8 + kg) * kGates + tid];
+#pragma unroll
+        for (int kg = RKG; kg < 8; ++kg) w_sm[(i * SKG + kg - RKG) * kGates + tid] = whh_perm[(i * 8 + kg) * kGates + tid];
     }
-    const float* p = pre + (long long)b * pre_stream_stride + row;
-    float* pr = probs + (long long)b * probs_stride + win0;
-    float pre_v = n_steps > 0 ? p[0] : 0.f;
+    // cell threads: thread (cs, cu) owns unit cu of stream cs
+    const int cs = tid >> 7, cu = tid & (kHid - 1);
+    const bool cell = cs < ns;
+    const int hpos = cs * 4 * kHq + (cu >> 5) * kHq + (cu & 31);
+    float c = 0.f;
+    float* st = state + (long long)(b0 + (cell ? cs : 0)) * 2 * kHid;
+    if (tid < S * kHid) h_sm[hpos] = cell ? st[cu] : 0.f;
+    if (cell) c = st[kHid + cu];
+    if (tid < kHid) dw_sm[tid] = dw[tid];
+    const float* p[S];
+    float pre_v[S];
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+        p[s] = pre + (long long)(b0 + (s < ns ? s : 0)) * pre_stream_stride + own;
+        pre_v[s] = n_steps > 0 ? p[s][0] : 0.f;
+    }
+    float* pr = probs + (long long)(b0 + (cell ? cs : 0)) * probs_stride + win0;
     __syncthreads();
     for (int t = 0; t < n_steps; ++t) {
-        const float pre_next = (t + 1 < n_steps) ? p[(long long)(t + 1) * kGates] : 0.f;  // prefetch
-        float a0 = pre_v, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        float pre_next[S];
+        float2 a[4][S];
 #pragma unroll
-        for (int k = 0; k < kRegW; k += 4) {
-            const float4 h4 = *reinterpret_cast<const float4*>(h_sm + k);
-            a0 = fmaf(w[k], h4.x, a0); a1 = fmaf(w[k + 1], h4.y, a1); a2 = fmaf(w[k + 2], h4.z, a2); a3 = fmaf(w[k + 3], h4.w, a3);
+        for (int s = 0; s < S; ++s) {
+            pre_next[s] = (t + 1 < n_steps) ? p[s][(long long)(t + 1) * kGates] : 0.f;  // prefetch
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i][s] = make_float2(0.f, 0.f);
         }
 #pragma unroll
-        for (int q = 0; q < kSmW / 4; ++q) {
-            const float4 w4 = w_sm[q * kGates + row];
-            const float4 h4 = *reinterpret_cast<const float4*>(h_sm + kRegW + q * 4);
-            a0 = fmaf(w4.x, h4.x, a0); a1 = fmaf(w4.y, h4.y, a1); a2 = fmaf(w4.z, h4.z, a2); a3 = fmaf(w4.w, h4.w, a3);
+        for (int kg = 0; kg < 8; ++kg) {
+            float4 h4[S];
+#pragma unroll
+            for (int s = 0; s < S; ++s) h4[s] = *reinterpret_cast<const float4*>(h_sm + s * 4 * kHq + q * kHq + 4 * kg);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float4 w4 = kg < RKG ? w[i][kg < RKG ? kg : 0] : w_sm[(i * SKG + (kg < RKG ? 0 : kg - RKG)) * kGates + tid];
+#pragma unroll
+                for (int s = 0; s < S; ++s) {
+                    a[i][s] = __ffma2_rn(make_float2(w4.x, w4.y), make_float2(h4[s].x, h4[s].y), a[i][s]);
+                    a[i][s] = __ffma2_rn(make_float2(w4.z, w4.w), make_float2(h4[s].z, h4[s].w), a[i][s]);
+                }
+            }
         }
-        g_sm[row] = (a0 + a1) + (a2 + a3);
+        // combine the four column quarters of a row group: two shuffle rounds, one finished row per lane
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            const float p0 = a[0][s].x + a[0][s].y, p1 = a[1][s].x + a[1][s].y, p2 = a[2][s].x + a[2][s].y, p3 = a[3][s].x + a[3][s].y;
+            const bool hi = q & 1;
+            const float v0 = (hi ? p2 : p0) + __shfl_xor_sync(0xffffffffu, hi ? p0 : p2, 1);
+            const float v1 = (hi ? p3 : p1) + __shfl_xor_sync(0xffffffffu, hi ? p1 : p3, 1);
+            const bool hi2 = q & 2;
+            const float r = (hi2 ? v1 : v0) + __shfl_xor_sync(0xffffffffu, hi2 ? v0 : v1, 2);
+            g_sm[s * kGates + own] = r + pre_v[s];
+        }
         __syncthreads();
-        if (row < kHid) {
-            const float gi = g_sm[row], gf = g_sm[kHid + row], gg = g_sm[2 * kHid + row], go = g_sm[3 * kHid + row];
-            c = sigmoidf_acc(gf) * c + sigmoidf_acc(gi) * tanhf(gg);
-            const float h = sigmoidf_acc(go) * tanhf(c);
-            h_sm[row] = h;
-            // head: relu(h) . w_dec -> sigmoid ; reduce over the 4 warps through g_sm (free after the sync below)
-            float part = warp_sum(fmaxf(h, 0.f) * dw_sm[row]);
-            if ((row & 31) == 0) dw_sm[kHid + (row >> 5)] = part;
+        if (tid < S * kHid) {
+            const float* g = g_sm + cs * kGates;
+            const float gi = g[cu], gf = g[kHid + cu], gg = g[2 * kHid + cu], go = g[3 * kHid + cu];
+            c = sigmoidf_fast(gf) * c + sigmoidf_fast(gi) * tanhf_fast(gg);
+            const float h = sigmoidf_fast(go) * tanhf_fast(c);
+            h_sm[hpos] = h;
+            // head: relu(h) . w_dec -> sigmoid ; one partial per warp, four warps per stream
+            const float part = warp_sum(fmaxf(h, 0.f) * dw_sm[cu]);
+            if ((tid & 31) == 0) part_sm[cs * 4 + (cu >> 5)] = part;
         }
         __syncthreads();
-        if (row == 0) {
-            const float logit = ((dw_sm[kHid] + dw_sm[kHid + 1]) + (dw_sm[kHid + 2] + dw_sm[kHid + 3])) + db;
-            pr[t] = sigmoidf_acc(logit);
+        if (cell && cu == 0) {
+            const float* ps = part_sm + cs * 4;
+            pr[t] = sigmoidf_acc(((ps[0] + ps[1]) + (ps[2] + ps[3])) + db);
         }
-        pre_v = pre_next;
+#pragma unroll
+        for (int s = 0; s < S; ++s) pre_v[s] = pre_next[s];
     }
-    if (row < kHid) {
-        st[row] = h_sm[row];
-        st[kHid + row] = c;
+    if (cell) {
+        st[cu] = h_sm[hpos];
+        st[kHid + cu] = c;
     }
 }
 
@@ -628,9 +688,14 @@ static int vad_score(VadModel* m, const void* d_audio, int fmt, int64_t n, int64
     OSB_CUDA(cudaMemsetAsync(h3, 0, ((size_t)W * 3 * 64 + 64) * 4, st));
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
-    const int recur_smem = (kSmW * kGates + kHid + kGates + 2 * kHid) * (int)sizeof(float);
-    std::call_once(once, [&] { attr_err = cudaFuncSetAttribute(k_vad_recur, cudaFuncAttributeMaxDynamicSharedMemorySize, recur_smem); });
+    std::call_once(once, [&] {
+        attr_err = cudaFuncSetAttribute(k_vad_recur<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, RecurCfg<1>::smem);
+        if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(k_vad_recur<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, RecurCfg<2>::smem);
+        if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(k_vad_recur<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, RecurCfg<4>::smem);
+    });
     OSB_CUDA(attr_err);
+    // streams per recurrence CTA: as few as keep the grid within one wave of SMs
+    const int rs = batch <= OSB_NUM_SMS ? 1 : (batch <= 2 * OSB_NUM_SMS ? 2 : 4);
     int rc;
     for (long long w0 = 0; w0 < n_win; w0 += T) {
         const int t = (int)((n_win - w0) < T ? (n_win - w0) : T);
@@ -674,8 +739,13 @@ static int vad_score(VadModel* m, const void* d_audio, int fmt, int64_t n, int64
         d.M = Wc; d.N = kGates; d.K = 128; d.relu = 0;
         if ((rc = m->use_tc ? launch_gemm_tc<0, 0>(d, m->tc[5], st) : launch_gemm<0, 0>(d, st))) return rc;
         // recurrence over the chunk's t windows, one CTA per stream
-        OSB_LAUNCH(k_vad_recur, (unsigned)batch, 512, recur_smem, st, pre, (long long)t * kGates, t, m->whh, m->dw, m->db,
-                   d_state, d_probs, (long long)probs_stride, w0);
+        const unsigned rg = (unsigned)((batch + rs - 1) / rs);
+        if (rs == 1) OSB_LAUNCH(k_vad_recur<1>, rg, 512, RecurCfg<1>::smem, st, pre, (long long)t * kGates, t, (const float4*)m->whh_perm, m->dw, m->db,
+                                d_state, d_probs, (long long)probs_stride, w0, (int)batch);
+        else if (rs == 2) OSB_LAUNCH(k_vad_recur<2>, rg, 512, RecurCfg<2>::smem, st, pre, (long long)t * kGates, t, (const float4*)m->whh_perm, m->dw, m->db,
+                                     d_state, d_probs, (long long)probs_stride, w0, (int)batch);
+        else OSB_LAUNCH(k_vad_recur<4>, rg, 512, RecurCfg<4>::smem, st, pre, (long long)t * kGates, t, (const float4*)m->whh_perm, m->dw, m->db,
+                        d_state, d_probs, (long long)probs_stride, w0, (int)batch);
         OSB_CHECK_LAUNCH();
     }
     return OSB_OK;
@@ -729,6 +799,19 @@ int osb_vad_create(const float* weights_host, size_t n_floats, void** handle) {
         delete m;
         return rc;
     }
+    {   // W_hh in the block order of the recurrence kernel: chunk (i, kg) of thread tid = W[row_i][32 q + 4 kg .. +3]
+        std::vector<float> perm(nW);
+        for (int tid = 0; tid < 512; ++tid)
+            for (int i = 0; i < 4; ++i)
+                for (int kg = 0; kg < 8; ++kg) {
+                    const int row = (tid >> 5) * 32 + ((tid & 31) >> 2) * 4 + i, col = 32 * (tid & 3) + 4 * kg;
+                    for (int e = 0; e < 4; ++e) perm[((size_t)(i * 8 + kg) * 512 + tid) * 4 + e] = w[oWhh + (size_t)row * 128 + col + e];
+                }
+        if ((rc = upload(&m->whh_perm, perm))) {
+            delete m;
+            return rc;
+        }
+    }
     m->db = w[oDb];
     {   // tcgen05 operand images
         std::vector<float> e1 = relay_conv(w + oE1w, 128, 129, kMagC, 448);
@@ -750,7 +833,7 @@ int osb_vad_create(const float* weights_host, size_t n_floats, void** handle) {
 int osb_vad_destroy(void* handle) {
     if (!handle) return OSB_OK;
     VadModel* m = reinterpret_cast<VadModel*>(handle);
-    float* ptrs[] = {m->basis, m->e1w, m->e1b, m->e2w, m->e2b, m->e3w, m->e3b, m->e4w, m->e4b, m->wih, m->bsum, m->whh, m->dw};
+    float* ptrs[] = {m->basis, m->e1w, m->e1b, m->e2w, m->e2b, m->e3w, m->e3b, m->e4w, m->e4b, m->wih, m->bsum, m->whh, m->whh_perm, m->dw};
     for (float* p : ptrs) cudaFree(p);
     for (auto& t : m->tc) cudaFree(t.img);
     delete m;
