@@ -213,13 +213,21 @@ __device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t& hi, uin
     lo = (uint32_t)__bfloat16_as_ushort(al) | ((uint32_t)__bfloat16_as_ushort(bl) << 16);
 }
 
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+
+// Warp roles: warps 0-15 (512 threads) stage A and run the epilogue; warp 16 (one elected lane) owns the tensor core:
+// it waits for a staged A chunk and the matching B tiles, issues the MMAs and refills the B ring.  Staging of chunk
+// k+1 therefore overlaps the MMAs of chunk k; the hand-over in both directions is by mbarrier (fullA / doneA).
+constexpr int kTcThreads = 544;
 template <int AMODE, int EPI>
-__global__ void __launch_bounds__(512, 1) k_vad_gemm_tc(GemmDesc d, const uint16_t* __restrict__ Bimg, int NT, int n_tiles, int k_chunks) {
+__global__ void __launch_bounds__(kTcThreads, 1) k_vad_gemm_tc(GemmDesc d, const uint16_t* __restrict__ Bimg, int NT, int n_tiles, int k_chunks) {
     extern __shared__ uint8_t smraw[];
     uint8_t* smb = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smraw) + 1023) & ~(uintptr_t)1023);
     uint8_t* Abuf = smb;                    // [2][hi|lo][128 x 128 B]
     uint8_t* Bbuf = smb + 2 * kTcABuf;      // [4][hi|lo][NT x 128 B]
-    __shared__ __align__(8) uint64_t fullB[kTcNB], doneB[kTcNB], doneA[2], doneAll;
+    __shared__ __align__(8) uint64_t fullB[kTcNB], doneB[kTcNB], fullA[2], doneA[2], doneAll;
     __shared__ uint32_t tmem_base_sm;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int m0 = blockIdx.x * kTcM;
@@ -228,6 +236,7 @@ __global__ void __launch_bounds__(512, 1) k_vad_gemm_tc(GemmDesc d, const uint16
     if (tid == 0) {
         for (int i = 0; i < kTcNB; ++i) { mbar_init(&fullB[i], 1); mbar_init(&doneB[i], 1); }
         mbar_init(&doneA[0], 1); mbar_init(&doneA[1], 1); mbar_init(&doneAll, 1);
+        mbar_init(&fullA[0], 512); mbar_init(&fullA[1], 512);
     }
     if (warp == 0) {  // one full warp allocates all 512 TMEM columns (1 CTA per SM by construction: 209 KB of smem)
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&tmem_base_sm)), "r"(512));
@@ -248,21 +257,23 @@ __global__ void __launch_bounds__(512, 1) k_vad_gemm_tc(GemmDesc d, const uint16
         bulk_g2s(Bbuf + (size_t)b * kTcBBuf, src, b_plane, &fullB[b]);
         bulk_g2s(Bbuf + (size_t)b * kTcBBuf + kTcBPlaneMax, src + b_plane / 2, b_plane, &fullB[b]);
     };
-    if (tid == 0)
+    if (tid == 512)
         for (int s = 0; s < kTcNB - 1 && s < steps; ++s) issue_b_load(s);
 
-    const int arow = tid & 127, aq = tid >> 7;  // thread -> (row, 16-element quarter of the 64-wide chunk)
-    for (int kc = 0; kc < k_chunks; ++kc) {
-        const int ab = kc & 1;
-        if (kc >= 2) mbar_wait(&doneA[ab], (uint32_t)(((kc >> 1) - 1) & 1));  // MMAs of chunk kc-2 have drained this buffer
-        {   // stage A(kc): 16 elements per thread -> 2 x 16 B per plane at swizzled positions
-            float v[16];
+    const int arow = tid & 127, aq = (tid >> 7) & 3;  // thread -> (row, 16-element quarter of the 64-wide chunk)
+    const float* a_row = nullptr;  // AMODE 0: start of this thread's activation row (the same for every chunk)
+    if (AMODE == 0 && warp < 16 && m0 + arow < d.M) {
+        const int r = m0 + arow;
+        a_row = reinterpret_cast<const float*>(d.A) + (long long)(r / d.a_icount) * d.a_outer + (long long)(r % d.a_icount) * d.a_istride;
+    }
+    // A(kc) -> registers: 16 elements per thread
+    auto load_A = [&](int kc, float (&v)[16]) {
             const int r = m0 + arow, k0 = kc * kTcKc + 16 * aq;
             if (r >= d.M) {
 #pragma unroll
                 for (int i = 0; i < 16; ++i) v[i] = 0.f;
             } else if (AMODE == 0) {
-                const float* p = reinterpret_cast<const float*>(d.A) + (long long)(r / d.a_icount) * d.a_outer + (long long)(r % d.a_icount) * d.a_istride + k0;
+                const float* p = a_row + k0;
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     const float4 t = *reinterpret_cast<const float4*>(p + 4 * q);
@@ -293,6 +304,10 @@ __global__ void __launch_bounds__(512, 1) k_vad_gemm_tc(GemmDesc d, const uint16
                     }
                 }
             }
+    };
+    // registers -> split bf16 hi/lo -> 2 x 16 B per plane at swizzled positions of buffer kc & 1
+    auto store_A = [&](int kc, const float (&v)[16]) {
+        const int ab = kc & 1;
             uint8_t* hi_row = Abuf + (size_t)ab * kTcABuf + (arow >> 3) * 1024 + (arow & 7) * 128;
             uint8_t* lo_row = hi_row + kTcAPlane;
 #pragma unroll
@@ -304,10 +319,28 @@ __global__ void __launch_bounds__(512, 1) k_vad_gemm_tc(GemmDesc d, const uint16
                 *reinterpret_cast<uint4*>(hi_row + chunk * 16) = make_uint4(h[0], h[1], h[2], h[3]);
                 *reinterpret_cast<uint4*>(lo_row + chunk * 16) = make_uint4(l[0], l[1], l[2], l[3]);
             }
-        }
+    };
+    // the loads of chunk kc+1 are in flight while chunk kc waits for its buffer, is split and stored
+    auto stage = [&](int kc, float (&cur)[16], float (&nxt)[16]) {
+        const int ab = kc & 1;
+        if (kc + 1 < k_chunks) load_A(kc + 1, nxt);
+        if (kc >= 2) mbar_wait(&doneA[ab], (uint32_t)(((kc >> 1) - 1) & 1));  // MMAs of chunk kc-2 have drained this buffer
+        store_A(kc, cur);
         fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
-        __syncthreads();
-        if (tid == 0) {
+        mbar_arrive(&fullA[ab]);
+    };
+    if (warp < 16) {
+        float va[16], vb[16];
+        load_A(0, va);
+        for (int kc = 0; kc < k_chunks; kc += 2) {
+            stage(kc, va, vb);
+            if (kc + 1 < k_chunks) stage(kc + 1, vb, va);
+        }
+    }
+    for (int kc = 0; kc < k_chunks; ++kc) {
+        const int ab = kc & 1;
+        if (tid == 512) {
+            mbar_wait(&fullA[ab], (uint32_t)((kc >> 1) & 1));
             tc_fence_after();
             const uint32_t a_hi = smem_u32(Abuf + (size_t)ab * kTcABuf), a_lo = a_hi + kTcAPlane;
             for (int nt = 0; nt < n_tiles; ++nt) {
@@ -335,51 +368,65 @@ __global__ void __launch_bounds__(512, 1) k_vad_gemm_tc(GemmDesc d, const uint16
             if (kc == k_chunks - 1) umma_commit(&doneAll);
         }
     }
-    // ---- epilogue: TMEM -> registers -> global
-    mbar_wait(&doneAll, 0);
-    tc_fence_after();
-    const int ncb = (n_tiles * NT + 31) / 32;
-    // each warp transposes its 32x32 block through shared memory (the operand buffers are free now) so that
-    // every global store instruction writes 128 contiguous bytes of one output row
-    float* tile = reinterpret_cast<float*>(smb) + warp * (32 * 33);
-    const int rbase = m0 + (warp & 3) * 32;
-    for (int cb = warp >> 2; cb < ncb; cb += 4) {
-        uint32_t v[32];
-        const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(cb * 32);
-        asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
-                     "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-                     : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                       "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-                       "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-                       "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                     : "r"(taddr));
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (EPI == 1) {
+    // ---- epilogue: TMEM -> registers -> global.  tcgen05.ld hands lane i of a warp 32 consecutive columns of row
+    // (warp & 3) * 32 + i, so every lane owns a 128-byte run of its own output row and stores it as float4s
+    // (16 B per lane and instruction; the eight instructions of a block complete the lines in L2).
+    if (warp < 16) {
+        mbar_wait(&doneAll, 0);
+        tc_fence_after();
+        const int ncb = (n_tiles * NT + 31) / 32;
+        const int r = m0 + (warp & 3) * 32 + lane;
+        float* crow = nullptr;  // start of this lane's output row
+        if (r < d.M) crow = d.C + (long long)(r / d.c_icount) * d.c_outer + (long long)(r % d.c_icount) * d.c_istride + d.c_offset;
+        for (int cb = warp >> 2; cb < ncb; cb += 4) {
+            uint32_t v[32];
+            const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(cb * 32);
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+                         "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                         : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                           "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                           "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                           "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                         : "r"(taddr));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (!crow) continue;
+            if (EPI == 1) {  // |re, im| of adjacent columns: 16 magnitudes, d.N / 2 of them exist in total
+                const int n0 = cb * 16, nmag = d.N / 2;
+                float mg[16];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const float re = __uint_as_float(v[2 * i]), im = __uint_as_float(v[2 * i + 1]);
-                tile[lane * 33 + i] = sqrtf(re * re + im * im);
-            }
-        } else {
+                for (int i = 0; i < 16; ++i) {
+                    const float re = __uint_as_float(v[2 * i]), im = __uint_as_float(v[2 * i + 1]);
+                    mg[i] = sqrtf(re * re + im * im);
+                }
 #pragma unroll
-            for (int i = 0; i < 32; ++i) tile[lane * 33 + i] = __uint_as_float(v[i]);
-        }
-        __syncwarp();
-        const int ncols = (EPI == 1) ? 16 : 32;
-        const int n = cb * ncols + (lane % ncols);
-        const bool col_ok = (EPI == 1) ? (2 * n < d.N) : (n < d.N);
-        const float bias = (EPI == 0 && col_ok && d.bias) ? __ldg(d.bias + n) : 0.f;
-        // EPI 1: 16 columns per row -> a warp stores two rows per instruction
-        const int rows_per_it = 32 / ncols;
-        for (int rr = 0; rr < 32; rr += rows_per_it) {
-            const int rl = rr + lane / ncols, r = rbase + rl;
-            if (r < d.M && col_ok) {
-                float x = tile[rl * 33 + (lane % ncols)] + bias;
-                if (EPI == 0 && d.relu) x = fmaxf(x, 0.f);
-                d.C[(long long)(r / d.c_icount) * d.c_outer + (long long)(r % d.c_icount) * d.c_istride + d.c_offset + n] = x;
+                for (int j = 0; j < 4; ++j) {
+                    const int n = n0 + 4 * j;
+                    if (n + 3 < nmag) *reinterpret_cast<float4*>(crow + n) = make_float4(mg[4 * j], mg[4 * j + 1], mg[4 * j + 2], mg[4 * j + 3]);
+                    else
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            if (n + e < nmag) crow[n + e] = mg[4 * j + e];
+                }
+            } else {
+                const int n0 = cb * 32;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int n = n0 + 4 * j;
+                    if (n >= d.N) break;
+                    float x[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        x[e] = __uint_as_float(v[4 * j + e]) + ((d.bias && n + e < d.N) ? __ldg(d.bias + n + e) : 0.f);
+                        if (d.relu) x[e] = fmaxf(x[e], 0.f);
+                    }
+                    if (n + 3 < d.N) *reinterpret_cast<float4*>(crow + n) = make_float4(x[0], x[1], x[2], x[3]);
+                    else
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            if (n + e < d.N) crow[n + e] = x[e];
+                }
             }
         }
-        __syncwarp();
     }
     tc_fence_before();
     __syncthreads();
@@ -650,7 +697,7 @@ static int launch_gemm_tc(const GemmDesc& d, const VadModel::Tc& L, cudaStream_t
         OSB_CUDA(cudaFuncSetAttribute(k_vad_gemm_tc<AMODE, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem));
         attr_done = true;
     }
-    OSB_LAUNCH((k_vad_gemm_tc<AMODE, EPI>), (d.M + kTcM - 1) / kTcM, 512, kTcSmem, st, d, (const uint16_t*)L.img, L.NT, L.n_tiles, L.k_chunks);
+    OSB_LAUNCH((k_vad_gemm_tc<AMODE, EPI>), (d.M + kTcM - 1) / kTcM, kTcThreads, kTcSmem, st, d, (const uint16_t*)L.img, L.NT, L.n_tiles, L.k_chunks);
     OSB_CHECK_LAUNCH();
     return OSB_OK;
 }
