@@ -88,9 +88,11 @@ HostWs& host_ws();
 
 // cross-file launchers (logmel.cu, spectral_gate.cu, gain.cu)
 int launch_logmel(const void* d_audio, int fmt, long long n, long long batch, long long stride, int n_mels, float* d_out,
-                  const unsigned long long* d_sumsq, float target_dbfs, cudaStream_t st);
+                  const unsigned long long* d_sumsq, float target_dbfs, cudaStream_t st, const double* d_sumsq_f = nullptr,
+                  int requant = 0);
+// d_sumsq (optional, zeroed by the caller): per-clip sum of squares of the float32 output, for a following normalize_gain
 int launch_spectral_gate(const void* d_audio, int fmt, long long n, long long batch, long long stride, int sr, float* d_out,
-                         cudaStream_t st);
+                         cudaStream_t st, double* d_sumsq = nullptr);
 int launch_pitch_shift(const void* d_in, bool in_f64, const long long* d_offsets, const long long* d_lens, long long batch, long long max_len,
                        int sample_rate, double semitones, float* d_out, cudaStream_t st);
 int launch_sumsq_pcm16(const int16_t* d_in, long long n, long long batch, long long stride, unsigned long long* d_sumsq, cudaStream_t st);

@@ -118,33 +118,39 @@ struct MelArgs {
     int fmt, n_frames, n_mels;
     float* out;                            // [batch][n_mels][n_frames] raw log10 values
     unsigned int* gmax;                    // [batch] bits of (max log10 + 10) >= 0
-    const unsigned long long* sumsq;       // fused normalise (pcm16 only), else null
+    const unsigned long long* sumsq;       // fused normalise of pcm16 input: per-clip sum of squared int16 samples, else null
+    const double* sumsq_f;                 // fused normalise of float32 input: per-clip sum of squares, else null
+    int requant;                           // clip / x32767 / truncate / (/32768) while staging (the chain's WAV round trip)
     float target_dbfs;
     const float* consts;
     const int *mel_start, *mel_len, *mel_off;
     const float* mel_w;
 };
 
+__device__ __forceinline__ float mel_requant(const MelArgs& a, float x, float gain, bool silent) {
+    return a.requant ? (float)quant_pcm16(apply_gain(x, gain, silent)) * 3.0517578125e-05f : x;
+}
 __device__ __forceinline__ float mel_sample(const MelArgs& a, int s16, float gain, bool silent) {
-    const float x = (float)s16 * 3.0517578125e-05f;  // /32768, exact
-    return a.sumsq ? (float)quant_pcm16(apply_gain(x, gain, silent)) * 3.0517578125e-05f : x;
+    return mel_requant(a, (float)s16 * 3.0517578125e-05f, gain, silent);  // /32768, exact
 }
 
 // Persistent kernel: grid = 2 CTAs per SM, each CTA walks tiles (32 frames of one clip) round-robin.  The raw
 // int16 samples of the NEXT tile are fetched by the TMA unit (cp.async.bulk -> mbarrier) while the current tile is
 // transformed, so the HBM latency of the staging step is off the critical path.
 //   smem: [xs|P (aliased)] [win twc tws] [Y] [raw int16] ; P reuses the float sample buffer once step 1 is done.
-constexpr int kRawBytes = kXs * 2;                                   // 10,720 B (multiple of 16)
+constexpr int kRawBytes = kXs * 4;                                   // raw staging: 10,720 B of int16 or 21,440 B of float32
 constexpr int kXsP = (((kBins * kPStride > kXs) ? kBins * kPStride : kXs) + 3) / 4 * 4;  // 6,636 floats (keeps raw[] 16 B aligned)
 static_assert(((kXsP + 1200 + 16 * 2 * kF400Plane) * 4) % 16 == 0, "raw[] must be 16-byte aligned");
 
 __device__ __forceinline__ bool mel_tile_interior(const MelArgs& a, int b, int t0, const int16_t** src) {
     const long long p0 = (long long)kHop * t0 - kNfft / 2;  // multiple of 8 samples
     const int16_t* s = reinterpret_cast<const int16_t*>(a.audio) + (long long)b * a.stride + p0;
+    if (a.fmt != OSB_FMT_PCM16) s = reinterpret_cast<const int16_t*>(reinterpret_cast<const float*>(a.audio) + (long long)b * a.stride + p0);
     *src = s;
-    return a.fmt == OSB_FMT_PCM16 && p0 >= 0 && p0 + kXs <= a.n && (((uintptr_t)s) & 15) == 0;
+    return p0 >= 0 && p0 + kXs <= a.n && (((uintptr_t)s) & 15) == 0;
 }
 
+template <bool F32>  // input format fixed at compile time: raw staging size and the conversion loop
 __global__ void __launch_bounds__(256, 2) k_logmel(MelArgs a, int tiles_per_clip, int total_tiles) {
     extern __shared__ __align__(16) float sm[];
     float* xs = sm;                       // [kXs] float samples (step 1)  |  P [201][33] (power, later phases)
@@ -153,7 +159,8 @@ __global__ void __launch_bounds__(256, 2) k_logmel(MelArgs a, int tiles_per_clip
     float* twc = win + 400;               // [400]
     float* tws = twc + 400;               // [400]
     float* Y = tws + 400;                 // [16][2][425]
-    int16_t* raw = reinterpret_cast<int16_t*>(Y + 16 * 2 * kF400Plane);  // [kXs] int16, TMA destination
+    int16_t* raw = reinterpret_cast<int16_t*>(Y + 16 * 2 * kF400Plane);  // [kXs] int16 or float32, TMA destination
+    constexpr uint32_t raw_bytes = F32 ? kXs * 4 : kXs * 2;
     __shared__ unsigned short zaddr[402]; // four-step address of bin k and of its mirror 400-k
     __shared__ __align__(8) uint64_t bar;
     const int tid = threadIdx.x;
@@ -168,8 +175,8 @@ __global__ void __launch_bounds__(256, 2) k_logmel(MelArgs a, int tiles_per_clip
         const int16_t* src;
         const int tile = blockIdx.x;
         if (tile < total_tiles && mel_tile_interior(a, tile / tiles_per_clip, (tile % tiles_per_clip) * MF, &src)) {
-            mbar_expect_tx(&bar, kRawBytes);
-            bulk_g2s(raw, src, kRawBytes, &bar);
+            mbar_expect_tx(&bar, raw_bytes);
+            bulk_g2s(raw, src, raw_bytes, &bar);
         }
     }
     __syncthreads();
@@ -182,10 +189,19 @@ __global__ void __launch_bounds__(256, 2) k_logmel(MelArgs a, int tiles_per_clip
             bool silent = true;
             float gain = 1.0f;
             if (a.sumsq) gain = gain_from_meansq((double)a.sumsq[b] / 1073741824.0 / (double)a.n, a.target_dbfs, &silent);
+            else if (a.sumsq_f) gain = gain_from_meansq(a.sumsq_f[b] / (double)a.n, a.target_dbfs, &silent);
             const int16_t* src;
             if (mel_tile_interior(a, b, t0, &src)) {
                 mbar_wait(&bar, parity);
                 parity ^= 1u;
+                if (F32) {
+                    const float4* rf = reinterpret_cast<const float4*>(raw);
+                    for (int i4 = tid; i4 < kXs / 4; i4 += 256) {
+                        const float4 v = rf[i4];
+                        *reinterpret_cast<float4*>(xs + 4 * i4) = make_float4(mel_requant(a, v.x, gain, silent), mel_requant(a, v.y, gain, silent),
+                                                                              mel_requant(a, v.z, gain, silent), mel_requant(a, v.w, gain, silent));
+                    }
+                } else
 #pragma unroll
                 for (int r = 0; r < 3; ++r) {
                     const int i8 = tid + 256 * r;
@@ -211,7 +227,7 @@ __global__ void __launch_bounds__(256, 2) k_logmel(MelArgs a, int tiles_per_clip
                     float v = 0.f;
                     if (p < a.n) {
                         if (a.fmt == OSB_FMT_PCM16) v = mel_sample(a, (int)reinterpret_cast<const int16_t*>(a.audio)[(long long)b * a.stride + p], gain, silent);
-                        else v = reinterpret_cast<const float*>(a.audio)[(long long)b * a.stride + p];
+                        else v = mel_requant(a, reinterpret_cast<const float*>(a.audio)[(long long)b * a.stride + p], gain, silent);
                     }
                     xs[i] = v;
                 }
@@ -223,8 +239,8 @@ __global__ void __launch_bounds__(256, 2) k_logmel(MelArgs a, int tiles_per_clip
             const int16_t* src;
             if (nt < total_tiles && mel_tile_interior(a, nt / tiles_per_clip, (nt % tiles_per_clip) * MF, &src)) {
                 fence_proxy_async();  // generic-proxy reads of raw[] above are ordered before the async-proxy write
-                mbar_expect_tx(&bar, kRawBytes);
-                bulk_g2s(raw, src, kRawBytes, &bar);
+                mbar_expect_tx(&bar, raw_bytes);
+                bulk_g2s(raw, src, raw_bytes, &bar);
             }
         }
         {   // four-step FFT, step 1: 16 frame pairs x 16 residues = 256 tasks
@@ -302,16 +318,21 @@ __global__ void __launch_bounds__(256) k_logmel_finalize(float* __restrict__ out
     for (long long i = nvec * 4 + tid; i < per_clip; i += nthr) o[i] = __fdiv_rn(__fadd_rn(fmaxf(o[i], thr), 4.0f), 4.0f);
 }
 
-constexpr int kLogmelSmem = (kXsP + 1200 + 16 * 2 * kF400Plane) * (int)sizeof(float) + kRawBytes;
+constexpr int kLogmelSmemF32 = (kXsP + 1200 + 16 * 2 * kF400Plane) * (int)sizeof(float) + kRawBytes;
+constexpr int kLogmelSmemP16 = kLogmelSmemF32 - kRawBytes / 2;
 
+// d_sumsq (pcm16 input) / d_sumsq_f (float32 input): fuse normalize_gain in front; requant: the chain's int16 round trip
 int launch_logmel(const void* d_audio, int fmt, long long n, long long batch, long long stride, int n_mels, float* d_out,
-                  const unsigned long long* d_sumsq, float target_dbfs, cudaStream_t st) {
+                  const unsigned long long* d_sumsq, float target_dbfs, cudaStream_t st, const double* d_sumsq_f, int requant) {
     const MelTables* t;
     int rc = get_mel(n_mels, true, &t);
     if (rc) return rc;
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
-    std::call_once(once, [&] { attr_err = cudaFuncSetAttribute(k_logmel, cudaFuncAttributeMaxDynamicSharedMemorySize, kLogmelSmem); });
+    std::call_once(once, [&] {
+        attr_err = cudaFuncSetAttribute(k_logmel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLogmelSmemF32);
+        if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(k_logmel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLogmelSmemP16);
+    });
     OSB_CUDA(attr_err);
     const int n_frames = (int)((n + kPad) / kHop);
     Scratch scr(st);
@@ -321,6 +342,7 @@ int launch_logmel(const void* d_audio, int fmt, long long n, long long batch, lo
     MelArgs a;
     a.audio = d_audio; a.n = n; a.stride = stride; a.fmt = fmt; a.n_frames = n_frames; a.n_mels = n_mels;
     a.out = d_out; a.gmax = gmax; a.sumsq = d_sumsq; a.target_dbfs = target_dbfs;
+    a.sumsq_f = d_sumsq_f; a.requant = (d_sumsq || d_sumsq_f || requant) ? 1 : 0;
     a.consts = t->d_consts; a.mel_start = t->d_start; a.mel_len = t->d_len; a.mel_off = t->d_off; a.mel_w = t->d_w;
     const int tiles_per_clip = (n_frames + MF - 1) / MF;
     const long long total_tiles_ll = (long long)tiles_per_clip * batch;
@@ -331,7 +353,8 @@ int launch_logmel(const void* d_audio, int fmt, long long n, long long batch, lo
     const int total_tiles = (int)total_tiles_ll;
     const int persistent = 2 * num_sms();  // 2 resident CTAs per SM (97 KB of shared memory each)
     const int grid = total_tiles < persistent ? total_tiles : persistent;
-    OSB_LAUNCH(k_logmel, grid, 256, kLogmelSmem, st, a, tiles_per_clip, total_tiles);
+    if (fmt == OSB_FMT_PCM16) OSB_LAUNCH(k_logmel<false>, grid, 256, kLogmelSmemP16, st, a, tiles_per_clip, total_tiles);
+    else OSB_LAUNCH(k_logmel<true>, grid, 256, kLogmelSmemF32, st, a, tiles_per_clip, total_tiles);
     OSB_CHECK_LAUNCH();
     const long long per_clip = (long long)n_mels * n_frames;
     long long fb = (per_clip / 4 + 255) / 256;

@@ -512,7 +512,8 @@ __global__ void __launch_bounds__(kMaskThreads, 2) k_nr_mask(const float* __rest
 constexpr int kOlaBlocks = 29, kOlaOut = kOlaBlocks * NH;  // 7424 samples
 
 __global__ void __launch_bounds__(256, 2) k_nr_istft(const float2* __restrict__ S, const float* __restrict__ Msm, NrGeom g,
-                                                     const float* __restrict__ tabs, int j_first, float* __restrict__ out) {
+                                                     const float* __restrict__ tabs, int j_first, float* __restrict__ out,
+                                                     double* __restrict__ sumsq) {
     extern __shared__ __align__(16) float sm[];
     float* win = sm;               // [1024]
     float* twc = win + NF;
@@ -626,12 +627,20 @@ __global__ void __launch_bounds__(256, 2) k_nr_istft(const float2* __restrict__ 
         }
         __syncthreads();
     }
-    // store the kept centre [kCtx, kCtx + keep) of the chunk
+    // store the kept centre [kCtx, kCtx + keep) of the chunk; optionally add its energy to the clip's sum of squares
+    // (np.square in float32, summed wide: what normalize_gain needs next)
+    double ss = 0.0;
     for (int u = tid; u < kOlaOut; u += 256) {
         const long long p = (long long)NH * j0 + u;
         const long long rel = p - kCtx;
         if (rel < 0 || rel >= keep) continue;
-        out[(long long)clip * g.stride + (long long)chunk * kChunk + rel] = acc[u] * osc[u & 255];
+        const float v = acc[u] * osc[u & 255];
+        out[(long long)clip * g.stride + (long long)chunk * kChunk + rel] = v;
+        ss += (double)__fmul_rn(v, v);
+    }
+    if (sumsq) {
+        ss = warp_sum(ss);
+        if (lane == 0) atomicAdd(sumsq + clip, ss);
     }
 }
 
@@ -648,7 +657,7 @@ static std::vector<double> tri_filter(int n) {
 }
 
 int launch_spectral_gate(const void* d_audio, int fmt, long long n, long long batch, long long stride, int sr, float* d_out,
-                         cudaStream_t st) {
+                         cudaStream_t st, double* d_sumsq) {
     const float* tabs;
     int rc = get_nr_tables(&tabs);
     if (rc) return rc;
@@ -722,7 +731,8 @@ int launch_spectral_gate(const void* d_audio, int fmt, long long n, long long ba
         if (nft == 16 && nt == 3) OSB_LAUNCH((k_nr_mask<16, 3, true>), gm, kMaskThreads, kSmoothSmem, st, A, CF, CB, Msm, g, NT, sp, b);
         else OSB_LAUNCH((k_nr_mask<kNfMax, kNtMax, false>), gm, kMaskThreads, kSmoothSmem, st, A, CF, CB, Msm, g, NT, sp, b);
         OSB_CHECK_LAUNCH();
-        OSB_LAUNCH(k_nr_istft, dim3(tiles, g.n_chunks, gb), 256, kIstftSmem, st, S, Msm, g, tabs, j_first, outp);
+        OSB_LAUNCH(k_nr_istft, dim3(tiles, g.n_chunks, gb), 256, kIstftSmem, st, S, Msm, g, tabs, j_first, outp,
+                   d_sumsq ? d_sumsq + c0 : (double*)nullptr);
         OSB_CHECK_LAUNCH();
     }
     return OSB_OK;

@@ -24,13 +24,18 @@ static int stt_frontend(const int16_t* d_pcm, long long n, long long batch, long
         if ((rc = osb_normalize_gain_pcm16_dev(d_pcm, q, n, batch, stride, 0, -18.0f, st))) return rc;
         return launch_logmel(q, OSB_FMT_PCM16, n, batch, stride, n_mels, d_mel, nullptr, -18.0f, st);
     }
+    // denoise -> (normalise) -> int16 round trip -> log-mel: the inverse STFT leaves each clip's sum of squares, and the
+    // log-mel kernel applies the gain and the requantisation while it stages the float32 samples, so the normalised
+    // int16 clip is never written
     float* den;
-    int16_t* q;
+    double* sumsq = nullptr;
     OSB_CUDA(scr.alloc(&den, (size_t)(batch * stride)));
-    OSB_CUDA(scr.alloc(&q, (size_t)(batch * stride)));
-    if ((rc = launch_spectral_gate(d_pcm, OSB_FMT_PCM16, n, batch, stride, sr, den, st))) return rc;
-    if ((rc = launch_normalize_f32(den, q, 1, n, batch, stride, normalize, -18.0f, st))) return rc;
-    return launch_logmel(q, OSB_FMT_PCM16, n, batch, stride, n_mels, d_mel, nullptr, -18.0f, st);
+    if (normalize) {
+        OSB_CUDA(scr.alloc(&sumsq, (size_t)batch));
+        OSB_CUDA(cudaMemsetAsync(sumsq, 0, sizeof(double) * batch, st));
+    }
+    if ((rc = launch_spectral_gate(d_pcm, OSB_FMT_PCM16, n, batch, stride, sr, den, st, sumsq))) return rc;
+    return launch_logmel(den, OSB_FMT_F32, n, batch, stride, n_mels, d_mel, nullptr, -18.0f, st, sumsq, 1);
 }
 
 extern "C" {
