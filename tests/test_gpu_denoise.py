@@ -37,6 +37,47 @@ def test_spectral_gate_vs_oracle(gpu, seconds):
     assert float(np.mean(got**2)) < float(np.mean(a**2))
 
 
+@pytest.mark.parametrize("sr", [8000, 22050, 24000, 44100, 48000])
+def test_spectral_gate_other_sample_rates(gpu, sr):
+    """reduce_noise(y, sr) takes the WAV's own rate: the mask smoothing reach follows it (8 kHz: 32x1 bins, 48 kHz: 5x9),
+    which runs the generic tap kernel instead of the 16 kHz running-sum instance."""
+    from open_speech_b200.audio import preprocessing as pre
+
+    a = _noisy(3.0, 17).astype(np.float32) / 32768.0
+    got, ref = pre.reduce_noise(a, sr), stt.spectral_gate(a, sr)
+    assert got.shape == ref.shape
+    assert np.abs(got - ref).max() <= TOL * np.abs(ref).max(), (sr, np.abs(got - ref).max(), np.abs(ref).max())
+
+
+@pytest.mark.parametrize("n", [600001 + 255, 600000 + 4096 * 3 + 17, 1200000, 1200001])
+def test_spectral_gate_short_last_chunk(gpu, n):
+    """last chunk much shorter than 600,000 samples: most of its frames lie in the zero padding and are skipped."""
+    from open_speech_b200.audio import preprocessing as pre
+
+    base = _noisy(76.0, 23).astype(np.float32) / 32768.0
+    a = base[:n]
+    got, ref = pre.reduce_noise(a, 16000), stt.spectral_gate(a, 16000)
+    assert np.abs(got - ref).max() <= TOL * np.abs(ref).max(), n
+
+
+def test_spectral_gate_batch_matches_single(gpu):
+    """device batch entry: ragged-free batch of clips == clip-by-clip host calls (and the fused sum of squares feeds the
+    same gain as the stand-alone normalise)."""
+    import torch
+    from open_speech_b200 import synth
+
+    pcm = synth.clip_batch_pcm16(4, 7.0, seed=31, distinct=4)
+    n = pcm.shape[1]
+    x = torch.from_numpy(pcm).cuda()
+    out = torch.empty((4, n), dtype=torch.float32, device="cuda")
+    gpu.call("osb_spectral_gate_dev", x.data_ptr(), 0, n, 4, n, 16000, out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    for i in range(4):
+        one = np.empty(n, np.float32)
+        gpu.call("osb_spectral_gate_host", gpu.ptr(pcm[i]), 0, gpu.ptr(one), n, 16000)
+        assert np.array_equal(out[i].cpu().numpy(), one)
+
+
 def test_spectral_gate_chunk_boundary_exact_multiple(gpu):
     """n == 600,000 is the single-chunk limit; n == 600,001 switches to two chunks (oracle get_traces)."""
     from open_speech_b200.audio import preprocessing as pre
