@@ -120,6 +120,41 @@ def test_batched_streams_match_single(gpu, session):
         assert np.abs(probs[i].cpu().numpy() - ref).max() <= PROB_TOL
 
 
+@pytest.mark.parametrize("batch", [149, 297, 301])
+def test_many_streams_share_recurrence_ctas(gpu, session, batch):
+    """More than 148 streams: the recurrence kernel walks 2 (149..296) or 4 (> 296) streams per CTA in lock step, the
+    last CTA partly empty.  Every stream must equal the same audio scored alone (stream-to-CTA packing is invisible),
+    carried state included."""
+    import torch
+
+    base = [_audio(2.0, 400 + i) for i in range(7)]
+    pcm = np.stack([base[i % 7] for i in range(batch)])
+    n = pcm.shape[1]
+    n_win = n // 512
+    x = torch.from_numpy(pcm).cuda()
+    state = torch.zeros((batch, 2, 128), dtype=torch.float32, device="cuda")
+    probs = torch.empty((batch, n_win), dtype=torch.float32, device="cuda")
+    for half in range(2):  # two calls: the second starts from the state the first left
+        gpu.call("osb_vad_score_dev", session.handle, x.data_ptr(), gpu.FMT_PCM16, n, batch, n, state.data_ptr(), probs.data_ptr(), n_win,
+                 torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    got, st = probs.cpu().numpy(), state.cpu().numpy()
+    one_state = torch.zeros((7, 2, 128), dtype=torch.float32, device="cuda")
+    one_probs = torch.empty((7, n_win), dtype=torch.float32, device="cuda")
+    x7 = torch.from_numpy(np.stack(base)).cuda()
+    for half in range(2):
+        gpu.call("osb_vad_score_dev", session.handle, x7.data_ptr(), gpu.FMT_PCM16, n, 7, n, one_state.data_ptr(), one_probs.data_ptr(), n_win,
+                 torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    ref, ref_st = one_probs.cpu().numpy(), one_state.cpu().numpy()
+    for i in range(batch):
+        assert np.array_equal(got[i], ref[i % 7]) and np.array_equal(st[i], ref_st[i % 7]), i
+    net = ovad.SileroNet()
+    o1, s1 = net.score_stream(base[0].astype(np.float32) / 32768.0)
+    o2, _ = net.score_stream(base[0].astype(np.float32) / 32768.0, s1)
+    assert np.abs(got[0] - o2).max() <= PROB_TOL
+
+
 def test_tcgen05_front_matches_ffma_and_oracle(gpu, session):
     """The tensor-core (tcgen05, split-bf16) front-end GEMM against the FP32 FFMA kernel and the oracle."""
     from open_speech_b200.vad.silero import SileroVAD
