@@ -94,7 +94,7 @@ def test_pitch_shift_vs_oracle(gpu, semitones):
     """_pitch_shift (src/effects/chain.py:44-48).  PARITY UNPINNED (librosa + soxr absent): the oracle restates librosa's
     stretch-then-resample with a Kaiser-sinc resampler.  The phase accumulator is float32 by librosa's design, so a
     last-bit difference in an analysis phase can move the accumulated phase of a high bin by one float32 ulp of ~1e5 rad
-    (~0.01 rad); the bar is therefore an RMS one: 1e-3 of the signal RMS, and 1e-2 of the peak for the worst sample."""
+    (~0.01 rad); the bar is therefore an RMS one: 3e-4 of the signal RMS (measured ~3e-5), and 1e-2 of the peak for the worst sample."""
     from open_speech_b200 import synth
     from open_speech_b200.effects.chain import _pitch_shift, apply_chain
 
@@ -103,7 +103,7 @@ def test_pitch_shift_vs_oracle(gpu, semitones):
     assert got.dtype == np.float32 and got.shape == ref.shape == x.shape
     rms = float(np.sqrt(np.mean(ref.astype(np.float64) ** 2)))
     err = got.astype(np.float64) - ref
-    assert np.sqrt(np.mean(err**2)) <= 1e-3 * rms, (np.sqrt(np.mean(err**2)), rms)
+    assert np.sqrt(np.mean(err**2)) <= 3e-4 * rms, (np.sqrt(np.mean(err**2)), rms)
     assert np.abs(err).max() <= 1e-2 * np.abs(ref).max(), (np.abs(err).max(), np.abs(ref).max())
     # the pitch really moves: dominant frequency of a tone scales by 2^(n/12)
     tone = (0.5 * np.sin(2 * np.pi * 440 * np.arange(48000) / 24000)).astype(np.float32)
