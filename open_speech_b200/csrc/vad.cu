@@ -371,16 +371,26 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_vad_gemm_tc(GemmDesc d, const
             if (kc == k_chunks - 1) umma_commit(&doneAll);
         }
     }
-    // ---- epilogue: TMEM -> registers -> global.  tcgen05.ld hands lane i of a warp 32 consecutive columns of row
-    // (warp & 3) * 32 + i, so every lane owns a 128-byte run of its own output row and stores it as float4s
-    // (16 B per lane and instruction; the eight instructions of a block complete the lines in L2).
+    // ---- epilogue: TMEM -> registers -> shared -> global.  tcgen05.ld hands lane i of a warp 32 consecutive columns of
+    // row (warp & 3) * 32 + i.  Bias / ReLU (or the |re,im| magnitude) happen in registers, the 32 x 32 block is
+    // transposed through shared memory (the operand buffers are free now) and leaves as float4s with eight lanes on
+    // one output row: every store instruction writes four complete 128-byte row segments.
     if (warp < 16) {
         mbar_wait(&doneAll, 0);
         tc_fence_after();
         const int ncb = (n_tiles * NT + 31) / 32;
-        const int r = m0 + (warp & 3) * 32 + lane;
-        float* crow = nullptr;  // start of this lane's output row
-        if (r < d.M) crow = d.C + (long long)(r / d.c_icount) * d.c_outer + (long long)(r % d.c_icount) * d.c_istride + d.c_offset;
+        constexpr int kTs = 36;  // padded row of the transpose tile (floats): 16-byte aligned, conflict-free float4 rows
+        float* tile = reinterpret_cast<float*>(smb) + warp * (32 * kTs);
+        const int rbase = m0 + (warp & 3) * 32;
+        // this lane's four output rows in the store phase: row = rbase + 4 * j + (lane >> 3), columns 4 * (lane & 7) .. +3
+        float* crow[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int r = rbase + 4 * j + (lane >> 3);
+            crow[j] = r < d.M ? d.C + (long long)(r / d.c_icount) * d.c_outer + (long long)(r % d.c_icount) * d.c_istride + d.c_offset : nullptr;
+        }
+        const int ncols = (EPI == 1) ? 16 : 32;           // output columns per block
+        const int nvalid = (EPI == 1) ? d.N / 2 : d.N;    // output columns that exist
         for (int cb = warp >> 2; cb < ncb; cb += 4) {
             uint32_t v[32];
             const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(cb * 32);
@@ -392,43 +402,48 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_vad_gemm_tc(GemmDesc d, const
                            "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
                          : "r"(taddr));
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (!crow) continue;
-            if (EPI == 1) {  // |re, im| of adjacent columns: 16 magnitudes, d.N / 2 of them exist in total
-                const int n0 = cb * 16, nmag = d.N / 2;
-                float mg[16];
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const float re = __uint_as_float(v[2 * i]), im = __uint_as_float(v[2 * i + 1]);
-                    mg[i] = sqrtf(re * re + im * im);
-                }
+            const int n0 = cb * ncols;
+            if (EPI == 1) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const int n = n0 + 4 * j;
-                    if (n + 3 < nmag) *reinterpret_cast<float4*>(crow + n) = make_float4(mg[4 * j], mg[4 * j + 1], mg[4 * j + 2], mg[4 * j + 3]);
-                    else
+                    float mg[4];
 #pragma unroll
-                        for (int e = 0; e < 4; ++e)
-                            if (n + e < nmag) crow[n + e] = mg[4 * j + e];
+                    for (int e = 0; e < 4; ++e) {
+                        const float re = __uint_as_float(v[8 * j + 2 * e]), im = __uint_as_float(v[8 * j + 2 * e + 1]);
+                        mg[e] = sqrtf(re * re + im * im);
+                    }
+                    *reinterpret_cast<float4*>(tile + lane * kTs + 4 * j) = make_float4(mg[0], mg[1], mg[2], mg[3]);
                 }
             } else {
-                const int n0 = cb * 32;
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    const int n = n0 + 4 * j;
-                    if (n >= d.N) break;
                     float x[4];
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
-                        x[e] = __uint_as_float(v[4 * j + e]) + ((d.bias && n + e < d.N) ? __ldg(d.bias + n + e) : 0.f);
+                        const int n = n0 + 4 * j + e;
+                        x[e] = __uint_as_float(v[4 * j + e]) + ((d.bias && n < d.N) ? __ldg(d.bias + n) : 0.f);
                         if (d.relu) x[e] = fmaxf(x[e], 0.f);
                     }
-                    if (n + 3 < d.N) *reinterpret_cast<float4*>(crow + n) = make_float4(x[0], x[1], x[2], x[3]);
-                    else
-#pragma unroll
-                        for (int e = 0; e < 4; ++e)
-                            if (n + e < d.N) crow[n + e] = x[e];
+                    *reinterpret_cast<float4*>(tile + lane * kTs + 4 * j) = make_float4(x[0], x[1], x[2], x[3]);
                 }
             }
+            __syncwarp();
+            const int c4 = 4 * (lane & 7);
+            if (c4 < ncols) {
+                const int n = n0 + c4;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (!crow[j] || n >= nvalid) continue;
+                    const float4 t = *reinterpret_cast<const float4*>(tile + (4 * j + (lane >> 3)) * kTs + c4);
+                    if (n + 3 < nvalid) *reinterpret_cast<float4*>(crow[j] + n) = t;
+                    else {
+                        crow[j][n] = t.x;
+                        if (n + 1 < nvalid) crow[j][n + 1] = t.y;
+                        if (n + 2 < nvalid) crow[j][n + 2] = t.z;
+                    }
+                }
+            }
+            __syncwarp();
         }
     }
     tc_fence_before();
