@@ -324,6 +324,7 @@ struct EqArgs {
     Ragged rg;
     double b1[3], a1[3], b2[3], a2[3];
     int warm;         // warm-up samples (multiple of 32): |slowest pole|^warm < 1e-17
+    double K[4][32];  // K[r][i]: state r at the end of a 32-sample segment for a unit impulse at its sample i (zero state before)
     double P[5][16];  // Phi_T^(2^k), k = 0..4 (row-major 4x4), T = 32 samples
     double Q[16];     // Phi_T^32
 };
@@ -380,9 +381,15 @@ __global__ void __launch_bounds__(256) k_fx_eq(const T* __restrict__ x, EqArgs a
     }
     __syncthreads();
     double* seg = u + tid * kSegStride;
+    // zero-state end state of the segment = four 32-tap dot products with the impulse-to-state table (the system is
+    // linear): four independent FMA chains instead of 32 dependent filter steps
     St4 e{{0, 0, 0, 0}};
-#pragma unroll 4
-    for (int i = 0; i < 32; ++i) eq_step(a, e, seg[i]);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+        const double xv = seg[i];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) e.z[r] = fma(a.K[r][i], xv, e.z[r]);
+    }
     // inclusive warp scan over segments: v_j = Phi^(2^k) v_{j-2^k} + v_j
     St4 v = e;
 #pragma unroll
@@ -665,6 +672,19 @@ static int fx_eq(FxState& s, int sample_rate) {
     a.warm = ((int)std::ceil(need) + 31) / 32 * 32;
     const int kEqOut = kEqBlock - a.warm;
     eq_transition(a, 32, a.P[0]);
+    for (int i = 0; i < 32; ++i) {  // impulse at sample i of a segment, then zeros to its end
+        double z[4] = {0, 0, 0, 0};
+        for (int t = i; t < 32; ++t) {
+            const double x = t == i ? 1.0 : 0.0;
+            const double y1 = a.b1[0] * x + z[0];
+            z[0] = a.b1[1] * x - a.a1[1] * y1 + z[1];
+            z[1] = a.b1[2] * x - a.a1[2] * y1;
+            const double y2 = a.b2[0] * y1 + z[2];
+            z[2] = a.b2[1] * y1 - a.a2[1] * y2 + z[3];
+            z[3] = a.b2[2] * y1 - a.a2[2] * y2;
+        }
+        for (int r = 0; r < 4; ++r) a.K[r][i] = z[r];
+    }
     for (int k = 1; k < 5; ++k) matmul4(a.P[k - 1], a.P[k - 1], a.P[k]);
     matmul4(a.P[4], a.P[4], a.Q);
     double* dst = (s.cur == s.d_a) ? s.d_b : s.d_a;
