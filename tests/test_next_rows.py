@@ -96,3 +96,23 @@ def test_vad_gated_assembly(gpu, rate):
     assert _extract_speech_segments(silent, rate, 2, 1, session=sess, threshold=0.99) == silent
     w = _pcm_to_wav(pcm.tobytes(), rate, 2, 1)
     assert w[:4] == b"RIFF" and len(w) == 44 + 2 * len(pcm) and int.from_bytes(w[24:28], "little") == rate
+
+
+@pytest.mark.gpu
+def test_conversation_render_turns(gpu):
+    """src/conversation.py:96-158, audio half: effects per turn, 500 ms gaps between turns, durations, per-turn WAVs."""
+    from open_speech_b200 import synth
+    from open_speech_b200.conversation import SILENCE_MS, render_turns
+    from oracle import tts as otts
+
+    turns = [synth.tts_utterance(1.2, seed=70), synth.tts_utterance(0.7, seed=71), synth.tts_utterance(0.9, seed=72)]
+    fx = [[{"type": "podcast_eq"}], None, [{"type": "normalize", "target_lufs": -18}, {"type": "robot"}]]
+    out = render_turns(turns, fx, 24000)
+    gap = np.zeros(int(24000 * SILENCE_MS / 1000), np.float32)
+    ref_parts = [otts.apply_chain(t, 24000, f) if f else t for t, f in zip(turns, fx)]
+    ref = np.concatenate([ref_parts[0], gap, ref_parts[1], gap, ref_parts[2]])
+    assert out["merged"].dtype == np.float32 and out["merged"].shape == ref.shape
+    assert np.abs(out["merged"] - ref).max() <= 1e-5 * np.abs(ref).max()
+    assert out["duration_ms"] == int(1000 * len(ref) / 24000) and out["turn_duration_ms"] == [int(1000 * len(p) / 24000) for p in ref_parts]
+    assert out["turn_wavs"][1] == otts.encode_wav(turns[1], 24000) and len(out["turn_wavs"][0]) == 44 + 2 * len(turns[0])
+    assert render_turns([], None, 24000)["merged"].shape == (0,)
