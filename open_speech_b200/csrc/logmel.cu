@@ -27,16 +27,17 @@ namespace osb {
 constexpr int kNfft = 400, kHop = 160, kBins = 201, kPad = 160;
 constexpr int MF = 32;                             // frames per CTA
 constexpr int kXs = kHop * (MF - 1) + kNfft;       // 5360 staged samples
-constexpr int kPStride = MF + 1;                   // power tile [201][33]
+constexpr int kPStride = MF + 1;                   // power tile [204][33]: 201 bins + 3 rows the zero-padded mel taps may touch
+constexpr int kPRows = kBins + 3;
+constexpr int kMelWMax = 768;                      // padded mel taps staged in shared memory (128 mels: 512, 80 mels: 480)
 
 struct MelTables {
     int n_mels = 0;
     std::vector<float> dense;   // [n_mels][201] f32 (what FeatureExtractor.mel_filters holds)
     float* d_consts = nullptr;  // win[400], twc[400], tws[400]
-    int* d_start = nullptr;     // [n_mels] first non-zero bin
-    int* d_len = nullptr;       // [n_mels]
-    int* d_off = nullptr;       // [n_mels] offset into d_w
-    float* d_w = nullptr;
+    int* d_meta = nullptr;      // [n_mels] first non-zero bin | padded tap count << 8 | offset into d_w << 16
+    float* d_w = nullptr;       // taps of every filter, each zero-padded to a multiple of 4 (kMelWMax floats in total at most)
+    int n_w = 0;
 };
 
 // faster_whisper.FeatureExtractor.get_mel_filters(16000, 400, n_mels): Slaney scale + area norm
@@ -87,23 +88,24 @@ static int get_mel(int n_mels, bool need_device, const MelTables** out) {
                 consts[400 + i] = (float)std::cos(2.0 * pi * (double)(n2 * k1) / 400.0);
                 consts[800 + i] = (float)std::sin(2.0 * pi * (double)(n2 * k1) / 400.0);
             }
-            std::vector<int> start(n_mels), len(n_mels), off(n_mels);
+            std::vector<int> meta(n_mels);
             std::vector<float> w;
             for (int m = 0; m < n_mels; ++m) {
                 int a = -1, b = -1;
                 for (int k = 0; k < kBins; ++k)
                     if (t.dense[(size_t)m * kBins + k] != 0.f) { if (a < 0) a = k; b = k; }
-                start[m] = a < 0 ? 0 : a;
-                len[m] = a < 0 ? 0 : b - a + 1;
-                off[m] = (int)w.size();
-                for (int k = 0; k < len[m]; ++k) w.push_back(t.dense[(size_t)m * kBins + start[m] + k]);
+                const int start = a < 0 ? 0 : a, len = a < 0 ? 0 : b - a + 1, len4 = (len + 3) / 4 * 4;
+                meta[m] = start | (len4 << 8) | ((int)w.size() << 16);
+                for (int k = 0; k < len4; ++k) w.push_back(k < len ? t.dense[(size_t)m * kBins + start + k] : 0.f);
             }
-            w.push_back(0.f);
+            if ((int)w.size() > kMelWMax) {
+                set_error("internal: mel filterbank has %d padded taps (> %d)", (int)w.size(), kMelWMax);
+                return OSB_ERR_UNSUPPORTED;
+            }
+            t.n_w = (int)w.size();
             OSB_CUDA(cudaMalloc(&t.d_consts, consts.size() * 4));
             OSB_CUDA(cudaMemcpy(t.d_consts, consts.data(), consts.size() * 4, cudaMemcpyHostToDevice));
-            OSB_CUDA(cudaMalloc(&t.d_start, n_mels * 4)); OSB_CUDA(cudaMemcpy(t.d_start, start.data(), n_mels * 4, cudaMemcpyHostToDevice));
-            OSB_CUDA(cudaMalloc(&t.d_len, n_mels * 4)); OSB_CUDA(cudaMemcpy(t.d_len, len.data(), n_mels * 4, cudaMemcpyHostToDevice));
-            OSB_CUDA(cudaMalloc(&t.d_off, n_mels * 4)); OSB_CUDA(cudaMemcpy(t.d_off, off.data(), n_mels * 4, cudaMemcpyHostToDevice));
+            OSB_CUDA(cudaMalloc(&t.d_meta, n_mels * 4)); OSB_CUDA(cudaMemcpy(t.d_meta, meta.data(), n_mels * 4, cudaMemcpyHostToDevice));
             OSB_CUDA(cudaMalloc(&t.d_w, w.size() * 4)); OSB_CUDA(cudaMemcpy(t.d_w, w.data(), w.size() * 4, cudaMemcpyHostToDevice));
         }
         it = g_mel.emplace(key, std::move(t)).first;
@@ -123,8 +125,9 @@ struct MelArgs {
     int requant;                           // clip / x32767 / truncate / (/32768) while staging (the chain's WAV round trip)
     float target_dbfs;
     const float* consts;
-    const int *mel_start, *mel_len, *mel_off;
+    const int* mel_meta;
     const float* mel_w;
+    int n_w;
 };
 
 __device__ __forceinline__ float mel_requant(const MelArgs& a, float x, float gain, bool silent) {
@@ -139,7 +142,7 @@ __device__ __forceinline__ float mel_sample(const MelArgs& a, int s16, float gai
 // transformed, so the HBM latency of the staging step is off the critical path.
 //   smem: [xs|P (aliased)] [win twc tws] [Y] [raw int16] ; P reuses the float sample buffer once step 1 is done.
 constexpr int kRawBytes = kXs * 4;                                   // raw staging: 10,720 B of int16 or 21,440 B of float32
-constexpr int kXsP = (((kBins * kPStride > kXs) ? kBins * kPStride : kXs) + 3) / 4 * 4;  // 6,636 floats (keeps raw[] 16 B aligned)
+constexpr int kXsP = (((kPRows * kPStride > kXs) ? kPRows * kPStride : kXs) + 3) / 4 * 4;  // 6,732 floats (keeps raw[] 16 B aligned)
 static_assert(((kXsP + 1200 + 16 * 2 * kF400Plane) * 4) % 16 == 0, "raw[] must be 16-byte aligned");
 
 __device__ __forceinline__ bool mel_tile_interior(const MelArgs& a, int b, int t0, const int16_t** src) {
@@ -161,15 +164,14 @@ __global__ void __launch_bounds__(256, 2) k_logmel(MelArgs a, int tiles_per_clip
     float* Y = tws + 400;                 // [16][2][425]
     int16_t* raw = reinterpret_cast<int16_t*>(Y + 16 * 2 * kF400Plane);  // [kXs] int16 or float32, TMA destination
     constexpr uint32_t raw_bytes = F32 ? kXs * 4 : kXs * 2;
-    __shared__ unsigned short zaddr[402]; // four-step address of bin k and of its mirror 400-k
+    __shared__ int mel_meta[128];
+    __shared__ __align__(16) float mel_wsm[kMelWMax];
     __shared__ __align__(8) uint64_t bar;
     const int tid = threadIdx.x;
 
     for (int i = tid; i < 1200; i += 256) win[i] = a.consts[i];
-    for (int k = tid; k < kBins; k += 256) {
-        zaddr[2 * k] = (unsigned short)fft400_addr(k);
-        zaddr[2 * k + 1] = (unsigned short)fft400_addr(k == 0 ? 0 : 400 - k);
-    }
+    for (int m = tid; m < a.n_mels; m += 256) mel_meta[m] = a.mel_meta[m];
+    for (int i = tid; i < a.n_w; i += 256) mel_wsm[i] = a.mel_w[i];
     if (tid == 0) {
         mbar_init(&bar, 1);
         const int16_t* src;
@@ -248,45 +250,56 @@ __global__ void __launch_bounds__(256, 2) k_logmel(MelArgs a, int tiles_per_clip
             fft400_step1(xs + (2 * q) * kHop, xs + (2 * q + 1) * kHop, win, twc, tws, n2, Y + q * 2 * kF400Plane, Y + q * 2 * kF400Plane + kF400Plane);
         }
         __syncthreads();
-        for (int task = tid; task < 16 * 25; task += 256) {  // step 2: 16 pairs x 25 rows
-            const int q = task / 25, k1 = task - q * 25;
-            fft400_step2(k1, Y + q * 2 * kF400Plane, Y + q * 2 * kF400Plane + kF400Plane);
-        }
-        __syncthreads();
-        {   // power of both frames of each pair: warp w takes pairs w and w+8, lanes stride over the 201 bins
-            const int lane = tid & 31;
-#pragma unroll
+        {   // step 2 fused with the power spectrum, one warp per frame pair (two pairs per warp): lane k1 < 25 runs the
+            // 16-point FFT of row k1 and then holds Z[k1 + 25 k2], k2 = 0..15.  The mirror bin 400 - k sits in lane
+            // 25 - k1 at index 15 - k2 (lane 0: its own index 16 - k2), so the split of the two packed real frames is
+            // a pair of shuffles, and the power goes straight to P: no write-back of Z, no second pass.
+            const int lane = tid & 31, k1 = lane < 25 ? lane : 0, src = lane == 0 ? 0 : (lane < 25 ? 25 - lane : 0);
+#pragma unroll 1
             for (int h = 0; h < 2; ++h) {
                 const int q = (tid >> 5) + 8 * h;
-                const float* zr_ = Y + q * 2 * kF400Plane;
-                const float* zi_ = zr_ + kF400Plane;
-                for (int k = lane; k < kBins; k += 32) {
-                    const int a0 = zaddr[2 * k], a1 = zaddr[2 * k + 1];
-                    const float zr = zr_[a0], zi = zi_[a0], yr = zr_[a1], yi = zi_[a1];
-                    const float ar = zr + yr, ai = zi - yi, br = zi + yi, bi = yr - zr;
-                    P[k * kPStride + 2 * q] = 0.25f * (ar * ar + ai * ai);
-                    P[k * kPStride + 2 * q + 1] = 0.25f * (br * br + bi * bi);
+                const float* yr = Y + q * 2 * kF400Plane;
+                const float* yi = yr + kF400Plane;
+                cpx v[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = cpx{yr[k1 * kF400Stride + i], yi[k1 * kF400Stride + i]};
+                fft_pow2<16>(v);
+#pragma unroll
+                for (int k2 = 0; k2 <= 8; ++k2) {
+                    // general lanes: partner's Z[(25-k1) + 25 (15-k2)]; lane 0: own Z[25 (16-k2)] (k2 = 0: Z[0] itself)
+                    const float sr = __shfl_sync(0xffffffffu, v[k2 < 8 ? 15 - k2 : 15].x, src);
+                    const float si = __shfl_sync(0xffffffffu, v[k2 < 8 ? 15 - k2 : 15].y, src);
+                    const float mr = lane == 0 ? v[(16 - k2) & 15].x : sr, mi = lane == 0 ? v[(16 - k2) & 15].y : si;
+                    const int k = k1 + 25 * k2;
+                    if (lane < 25 && k < kBins) {
+                        const float zr = v[k2].x, zi = v[k2].y;
+                        const float ar = zr + mr, ai = zi - mi, br = zi + mi, bi = mr - zr;
+                        P[k * kPStride + 2 * q] = 0.25f * (ar * ar + ai * ai);
+                        P[k * kPStride + 2 * q + 1] = 0.25f * (br * br + bi * bi);
+                    }
                 }
             }
         }
         __syncthreads();
-        // sparse mel contraction (each triangle touches a few bins) + log10; lanes = consecutive frames
+        // sparse mel contraction (each triangle touches a few bins; taps zero-padded to fours) + log10; lanes = frames
         const int f = tid & 31;
         const bool live = (t0 + f) < a.n_frames;
         float vmax = -10.0f;
         float* outb = a.out + (long long)b * a.n_mels * a.n_frames + t0 + f;
         const float* Pf = P + f;
         for (int m = tid >> 5; m < a.n_mels; m += 8) {
-            const int s = __ldg(a.mel_start + m), len = __ldg(a.mel_len + m);
-            const float* w = a.mel_w + __ldg(a.mel_off + m);
-            const float* pp = Pf + s * kPStride;
+            const int meta = mel_meta[m];
+            const int len4 = (meta >> 8) & 255;
+            const float* w = mel_wsm + (meta >> 16);
+            const float* pp = Pf + (meta & 255) * kPStride;
             float acc0 = 0.f, acc1 = 0.f;
-            int i = 0;
-            for (; i + 1 < len; i += 2) {
-                acc0 = fmaf(__ldg(w + i), pp[i * kPStride], acc0);
-                acc1 = fmaf(__ldg(w + i + 1), pp[(i + 1) * kPStride], acc1);
+            for (int i = 0; i < len4; i += 4) {
+                const float4 w4 = *reinterpret_cast<const float4*>(w + i);
+                acc0 = fmaf(w4.x, pp[i * kPStride], acc0);
+                acc1 = fmaf(w4.y, pp[(i + 1) * kPStride], acc1);
+                acc0 = fmaf(w4.z, pp[(i + 2) * kPStride], acc0);
+                acc1 = fmaf(w4.w, pp[(i + 3) * kPStride], acc1);
             }
-            if (i < len) acc0 = fmaf(__ldg(w + i), pp[i * kPStride], acc0);
             // log10 via the SFU log2: |error| < 3e-6 on log10, 1e-6 on the output (tolerance 1e-4)
             const float v = __log2f(fmaxf(acc0 + acc1, 1e-10f)) * 0.30102999566398120f;
             if (live) {
@@ -343,7 +356,7 @@ int launch_logmel(const void* d_audio, int fmt, long long n, long long batch, lo
     a.audio = d_audio; a.n = n; a.stride = stride; a.fmt = fmt; a.n_frames = n_frames; a.n_mels = n_mels;
     a.out = d_out; a.gmax = gmax; a.sumsq = d_sumsq; a.target_dbfs = target_dbfs;
     a.sumsq_f = d_sumsq_f; a.requant = (d_sumsq || d_sumsq_f || requant) ? 1 : 0;
-    a.consts = t->d_consts; a.mel_start = t->d_start; a.mel_len = t->d_len; a.mel_off = t->d_off; a.mel_w = t->d_w;
+    a.consts = t->d_consts; a.mel_meta = t->d_meta; a.mel_w = t->d_w; a.n_w = t->n_w;
     const int tiles_per_clip = (n_frames + MF - 1) / MF;
     const long long total_tiles_ll = (long long)tiles_per_clip * batch;
     if (total_tiles_ll > 0x7fffffffLL) {
