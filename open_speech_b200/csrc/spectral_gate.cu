@@ -175,56 +175,41 @@ __global__ void __launch_bounds__(256, 2) k_nr_stft(const void* __restrict__ aud
         }
     }
     __syncwarp();
-    {   // step 2: 32-point FFT over n2 for each k1 = lane: Z[k1 + 32*k2] stored at [k1][k2]
+    const long long row0 = ((long long)clip * g.n_chunks + chunk) * g.F;
+    {   // step 2: 32-point FFT over n2 for row k1 = lane, fused with the split of the packed transform.  The lane ends up
+        // with Z[lane + 32 k2]; the mirror bin 1024 - k sits in lane 32 - lane at index 31 - k2 (lane 0: its own index
+        // 32 - k2), so X_a = (Z[k] + conj Z[N-k])/2 and X_b = (Z[k] - conj Z[N-k])/(2i) take two shuffles per bin and
+        // go straight to global memory: lanes are consecutive bins, every store is coalesced.  Z never returns to
+        // shared memory; the planes receive the magnitudes instead (row 2q at yr[0..513), row 2q+1 at yi[0..513)).
         cpx v[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = cpx{yr[lane * kYs + i], yi[lane * kYs + i]};
         fft_pow2<32>(v);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-            yr[lane * kYs + i] = v[i].x;
-            yi[lane * kYs + i] = v[i].y;
-        }
-    }
-    __syncwarp();
-    // split the packed transform into the two one-sided spectra, apply the spectrum scaling 1/sum(win) = 1/512
-    const float sc = 0.5f / 512.0f;
-    const long long row0 = ((long long)clip * g.n_chunks + chunk) * g.F;
-    {
+        __syncwarp();  // every lane has read its row
+        const float sc = 0.5f / 512.0f;  // spectrum scaling 1/sum(win) = 1/512, and the 1/2 of the split
+        const int src = (32 - lane) & 31;
         const int ta = t0 + 2 * q;
-        float ma[17], mb[17];
-        if (ta < g.F) {
-            const bool has_b = ta + 1 < g.F;
-            float2* Sa = S + (row0 + ta) * NB;
-            float* Aa = A + (row0 + ta) * NB;
+        const bool has_a = ta < g.F, has_b = ta + 1 < g.F;
+        float2* Sa = S + (row0 + ta) * NB;
+        float* Aa = A + (row0 + ta) * NB;
 #pragma unroll
-            for (int i = 0; i < 17; ++i) {
-                const int f = lane + 32 * i;
-                ma[i] = 0.f; mb[i] = 0.f;
-                if (f < NB) {
-                    const int m = (NF - f) & (NF - 1);
-                    const int a0 = (f & 31) * kYs + (f >> 5), a1 = (m & 31) * kYs + (m >> 5);
-                    const float zr = yr[a0], zi = yi[a0], wr = yr[a1], wi = yi[a1];
-                    // X_a = (Z[f] + conj Z[N-f])/2 ; X_b = (Z[f] - conj Z[N-f])/(2i)
-                    const float ar = (zr + wr) * sc, ai = (zi - wi) * sc, br = (zi + wi) * sc, bi = (wr - zr) * sc;
-                    ma[i] = fast_mag(ar, ai);
-                    mb[i] = fast_mag(br, bi);
-                    Sa[f] = make_float2(ar, ai);
-                    Aa[f] = ma[i];
-                    if (has_b) {
-                        Sa[NB + f] = make_float2(br, bi);
-                        Aa[NB + f] = mb[i];
-                    }
+        for (int k2 = 0; k2 <= 16; ++k2) {
+            const float sr = __shfl_sync(0xffffffffu, v[k2 < 16 ? 31 - k2 : 31].x, src);
+            const float si = __shfl_sync(0xffffffffu, v[k2 < 16 ? 31 - k2 : 31].y, src);
+            const float wr = lane == 0 ? v[(32 - k2) & 31].x : sr, wi = lane == 0 ? v[(32 - k2) & 31].y : si;
+            const int f = lane + 32 * k2;
+            if (has_a && f < NB) {
+                const float zr = v[k2 & 31].x, zi = v[k2 & 31].y;
+                const float ar = (zr + wr) * sc, ai = (zi - wi) * sc, br = (zi + wi) * sc, bi = (wr - zr) * sc;
+                const float ma = fast_mag(ar, ai), mb = fast_mag(br, bi);
+                Sa[f] = make_float2(ar, ai);
+                Aa[f] = ma;
+                yr[f] = ma;
+                yi[f] = mb;
+                if (has_b) {
+                    Sa[NB + f] = make_float2(br, bi);
+                    Aa[NB + f] = mb;
                 }
-            }
-        }
-        __syncwarp();
-        // the magnitudes of the pair replace its planes: row 2q at yr[0..513), row 2q+1 at yi[0..513)
-        if (ta < g.F) {
-#pragma unroll
-            for (int i = 0; i < 17; ++i) {
-                const int f = lane + 32 * i;
-                if (f < NB) { yr[f] = ma[i]; yi[f] = mb[i]; }
             }
         }
     }
@@ -541,12 +526,16 @@ __global__ void __launch_bounds__(256, 2) k_nr_istft(const float2* __restrict__ 
     for (int pass = 0; pass < 2; ++pass) {
         const int tp0 = j0 - 1 + pass * 16;
         if (tp0 >= TL) break;  // only zero frames left
-        {   // stage Z'[k] = Xa[k] + i Xb[k], k stored at [k>>5][k&31] (row stride 33): Xa/Xb are the masked one-sided
-            // spectra S*Msm extended by Hermitian symmetry; every S cell is read once, coalesced, four bins in flight
+        {   // step 1 of the inverse, fed straight from global memory.  The packed spectrum is Z'[k] = Xa[k] + i Xb[k] with
+            // Xa/Xb the masked one-sided spectra S*Msm extended by Hermitian symmetry.  Lane l needs column l:
+            // Z'[32 a + l], a = 0..31.  Bins 32 a + l <= 511 it loads itself (coalesced, every S cell read once); the
+            // upper half are mirrors conj(Xa[f]) + i conj(Xb[f]) of bins held by lane 32 - l (lane 0: by itself), which
+            // arrive by shuffle.  Nothing is staged in shared memory before the first butterfly.
             const int ta = tp0 + 2 * q, tb = ta + 1;
             const bool va = ta >= 0 && ta < TL, vb = tb >= 0 && tb < TL;
             const float2* Sa = S + (row0 + ta) * NB;
             const float* Ma = Msm + (row0 + ta) * NB;
+            cpx v[32], mir[16];
 #pragma unroll
             for (int ib = 0; ib < 16; ib += 4) {
                 float2 sa[4], sb[4];
@@ -561,31 +550,23 @@ __global__ void __launch_bounds__(256, 2) k_nr_istft(const float2* __restrict__ 
                 }
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    const int f = lane + 32 * (ib + u);
                     const float ar = sa[u].x * ma[u], br = sb[u].x * mb[u];
                     float ai = sa[u].y * ma[u], bi = sb[u].y * mb[u];
-                    if (f == 0) { ai = 0.f; bi = 0.f; }  // irfft ignores the imaginary part of DC
-                    const int k0 = (ib + u) * kYs + lane;
-                    yr[k0] = ar - bi;
-                    yi[k0] = ai + br;
-                    if (f != 0) {  // mirror bin N-f: conj(Xa[f]) + i conj(Xb[f])
-                        const int km = NF - f, k1 = (km >> 5) * kYs + (km & 31);
-                        yr[k1] = ar + bi;
-                        yi[k1] = br - ai;
-                    }
+                    if (ib + u == 0 && lane == 0) { ai = 0.f; bi = 0.f; }  // irfft ignores the imaginary part of DC
+                    v[ib + u] = cpx{ar - bi, ai + br};
+                    mir[ib + u] = cpx{ar + bi, br - ai};
                 }
             }
-            if (lane == 0) {  // Nyquist: real part only
-                const float ar = va ? Sa[512].x * Ma[512] : 0.f, br = vb ? Sa[NB + 512].x * Ma[NB + 512] : 0.f;
-                yr[16 * kYs] = ar;
-                yi[16 * kYs] = br;
-            }
-        }
-        __syncwarp();
-        {   // step 1 of the inverse (conjugate twiddles), in place: lane owns column `lane` of the pair
-            cpx v[32];
+            // Nyquist (lane 0 only): real parts
+            const float nyr = (lane == 0 && va) ? Sa[512].x * Ma[512] : 0.f, nyi = (lane == 0 && vb) ? Sa[NB + 512].x * Ma[NB + 512] : 0.f;
+            const int src = (32 - lane) & 31;
 #pragma unroll
-            for (int a = 0; a < 32; ++a) v[a] = cpx{yr[a * kYs + lane], yi[a * kYs + lane]};
+            for (int j = 0; j < 16; ++j) {
+                // k = 32 (16 + j) + lane  <-  bin 1024 - k = 32 (15 - j) + (32 - lane)   (lane 0: 32 (16 - j), j = 0: Nyquist)
+                const float sr = __shfl_sync(0xffffffffu, mir[15 - j].x, src), si = __shfl_sync(0xffffffffu, mir[15 - j].y, src);
+                if (lane == 0) v[16 + j] = j == 0 ? cpx{nyr, nyi} : mir[(16 - j) & 15];
+                else v[16 + j] = cpx{sr, si};
+            }
             fft_pow2<32, true>(v);
 #pragma unroll
             for (int c = 0; c < 32; ++c) {
