@@ -497,8 +497,9 @@ __global__ void __launch_bounds__(kMaskThreads, 2) k_nr_mask(const float* __rest
 constexpr int kOlaBlocks = 29, kOlaOut = kOlaBlocks * NH;  // 7424 samples
 
 __global__ void __launch_bounds__(256, 2) k_nr_istft(const float2* __restrict__ S, const float* __restrict__ Msm, NrGeom g,
-                                                     const float* __restrict__ tabs, int j_first, float* __restrict__ out,
+                                                     const float* __restrict__ tabs, int j_first, int tiles_per_chunk, float* __restrict__ out,
                                                      double* __restrict__ sumsq) {
+    // persistent: 2 CTAs per SM walk the (clip, chunk, tile) list, so the 13 KB of tables are fetched once per CTA
     extern __shared__ __align__(16) float sm[];
     float* win = sm;               // [1024]
     float* twc = win + NF;
@@ -506,23 +507,27 @@ __global__ void __launch_bounds__(256, 2) k_nr_istft(const float2* __restrict__ 
     float* osc = tws + NF;         // [256] overlap-add scale
     float* Y = osc + NH;           // [8][2][32*33]
     float* acc = Y + 8 * 2 * kYPlane;  // [7424]
-    const int tid = threadIdx.x, chunk = blockIdx.y, clip = blockIdx.z;
-    const int j0 = j_first + blockIdx.x * kOlaBlocks;
-    const long long keep = (g.n_chunks == 1) ? g.n : ((g.n - (long long)chunk * kChunk) < kChunk ? (g.n - (long long)chunk * kChunk) : kChunk);
-    if ((long long)NH * j0 >= kCtx + keep) return;  // tile past the kept centre of a short last chunk
-    const int TL = nr_tlim(g, chunk);
+    const int tid = threadIdx.x, q = tid >> 5, lane = tid & 31;
     for (int i = tid; i < 3 * NF + NH; i += 256) win[i] = tabs[i];
-    for (int i = tid; i < kOlaOut; i += 256) acc[i] = 0.f;
-    const long long row0 = ((long long)clip * g.n_chunks + chunk) * g.F;
     __syncthreads();
-    // Each warp owns one frame pair and its two planes through staging and both FFT steps (warp-level barriers only);
-    // the CTA only meets for the overlap-add.
-    const int q = tid >> 5, lane = tid & 31;
-    float* yr = Y + q * 2 * kYPlane;
-    float* yi = yr + kYPlane;
     float wreg[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) wreg[j] = win[tid + 256 * j];
+    float* yr = Y + q * 2 * kYPlane;
+    float* yi = yr + kYPlane;
+    const long long total_tiles = (long long)tiles_per_chunk * g.n_chunks * g.batch;
+    for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    const int clip = (int)(tile / ((long long)tiles_per_chunk * g.n_chunks));
+    const int rem = (int)(tile - (long long)clip * tiles_per_chunk * g.n_chunks);
+    const int chunk = rem / tiles_per_chunk;
+    const int j0 = j_first + (rem - chunk * tiles_per_chunk) * kOlaBlocks;
+    const long long keep = (g.n_chunks == 1) ? g.n : ((g.n - (long long)chunk * kChunk) < kChunk ? (g.n - (long long)chunk * kChunk) : kChunk);
+    if ((long long)NH * j0 >= kCtx + keep) continue;  // tile past the kept centre of a short last chunk
+    const int TL = nr_tlim(g, chunk);
+    for (int i = tid; i < kOlaOut; i += 256) acc[i] = 0.f;  // a thread only ever touches acc[u], u == tid (mod 256)
+    const long long row0 = ((long long)clip * g.n_chunks + chunk) * g.F;
+    // Each warp owns one frame pair and its two planes through both FFT steps (warp-level barriers only);
+    // the CTA only meets for the overlap-add.
     for (int pass = 0; pass < 2; ++pass) {
         const int tp0 = j0 - 1 + pass * 16;
         if (tp0 >= TL) break;  // only zero frames left
@@ -623,6 +628,7 @@ __global__ void __launch_bounds__(256, 2) k_nr_istft(const float2* __restrict__ 
         ss = warp_sum(ss);
         if (lane == 0) atomicAdd(sumsq + clip, ss);
     }
+    }  // tile loop
 }
 
 constexpr int kStftSmem = (kStftXs + 3 * NF + 8 * 2 * kYPlane) * (int)sizeof(float);
@@ -712,8 +718,12 @@ int launch_spectral_gate(const void* d_audio, int fmt, long long n, long long ba
         if (nft == 16 && nt == 3) OSB_LAUNCH((k_nr_mask<16, 3, true>), gm, kMaskThreads, kSmoothSmem, st, A, CF, CB, Msm, g, NT, sp, b);
         else OSB_LAUNCH((k_nr_mask<kNfMax, kNtMax, false>), gm, kMaskThreads, kSmoothSmem, st, A, CF, CB, Msm, g, NT, sp, b);
         OSB_CHECK_LAUNCH();
-        OSB_LAUNCH(k_nr_istft, dim3(tiles, g.n_chunks, gb), 256, kIstftSmem, st, S, Msm, g, tabs, j_first, outp,
-                   d_sumsq ? d_sumsq + c0 : (double*)nullptr);
+        {
+            const long long total_tiles = (long long)tiles * g.n_chunks * gb;
+            const long long persistent = 2ll * num_sms();  // 2 resident CTAs per SM (110 KB of shared memory each)
+            OSB_LAUNCH(k_nr_istft, (unsigned)(total_tiles < persistent ? total_tiles : persistent), 256, kIstftSmem, st, S, Msm, g, tabs, j_first,
+                       tiles, outp, d_sumsq ? d_sumsq + c0 : (double*)nullptr);
+        }
         OSB_CHECK_LAUNCH();
     }
     return OSB_OK;
