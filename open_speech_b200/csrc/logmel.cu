@@ -170,6 +170,9 @@ __global__ void __launch_bounds__(256, 2) k_logmel(MelArgs a, int tiles_per_clip
     const int tid = threadIdx.x;
 
     for (int i = tid; i < 1200; i += 256) win[i] = a.consts[i];
+    // rows 201..203 of P are only ever multiplied by the zero padding of the mel taps, but they must hold finite numbers:
+    // they lie beyond the staged samples, so they keep whatever the previous kernel on this SM left there
+    for (int i = tid; i < (kPRows - kBins) * kPStride; i += 256) P[kBins * kPStride + i] = 0.f;
     for (int m = tid; m < a.n_mels; m += 256) mel_meta[m] = a.mel_meta[m];
     for (int i = tid; i < a.n_w; i += 256) mel_wsm[i] = a.mel_w[i];
     if (tid == 0) {

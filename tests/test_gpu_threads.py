@@ -1,0 +1,57 @@
+"""Re-entrancy: the reference calls this path from the asyncio loop thread and from 4-worker thread pools at once
+(src/streaming.py:50-52, src/realtime/server.py:33-35, src/main.py:796-813; SURVEY.md 8(b) "Threading").  Every host
+entry uses a thread-local stream and workspace, and one VAD session (weights) is shared by per-stream SileroVAD states.
+Eight threads hammer different entry points concurrently; every result must equal the single-threaded one bit for bit."""
+import threading
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def test_concurrent_host_calls_are_independent(gpu):
+    from open_speech_b200 import synth
+    from open_speech_b200.audio import preprocessing as pre
+    from open_speech_b200.effects.chain import apply_chain
+    from open_speech_b200.features import B200FeatureExtractor
+    from open_speech_b200.realtime.audio_buffer import decode_audio_to_pcm16
+    from open_speech_b200.streaming import resample_pcm16
+    from open_speech_b200.vad.silero import SileroVAD, VadSession
+
+    session = VadSession()
+    clip = synth.clip_pcm16(6.0, seed=77, extra_noise_rms=0.01)
+    clip_f = clip.astype(np.float32) / 32768.0
+    ulaw = synth.ulaw_streams(1, 50)[0].reshape(-1).tobytes()
+    utt = synth.tts_utterance(2.0, seed=78)
+    fe = B200FeatureExtractor(feature_size=128)
+    fx = [{"type": "normalize"}, {"type": "reverb", "room": "medium"}, {"type": "podcast_eq"}, {"type": "robot"}]
+
+    jobs = {
+        "decode": lambda: decode_audio_to_pcm16(ulaw, "g711_ulaw", 16000),
+        "poly": lambda: resample_pcm16(clip.tobytes(), 16000, 8000),
+        "gate": lambda: pre.reduce_noise(clip_f, 16000).tobytes(),
+        "gain": lambda: pre.normalize_gain(clip_f).tobytes(),
+        "mel": lambda: fe(clip_f).tobytes(),
+        "vad": lambda: repr(SileroVAD(session).get_speech_segments(clip.tobytes())),
+        "fx": lambda: apply_chain(utt, 24000, fx).tobytes(),
+        "pitch": lambda: apply_chain(utt, 24000, [{"type": "pitch", "semitones": 3}]).tobytes(),
+    }
+    expected = {k: f() for k, f in jobs.items()}
+    errors, barrier = [], threading.Barrier(len(jobs))
+
+    def worker(name, fn):
+        try:
+            barrier.wait()
+            for _ in range(6):
+                if fn() != expected[name]:
+                    errors.append(name)
+        except Exception as e:  # noqa: BLE001
+            errors.append(f"{name}: {e!r}")
+
+    threads = [threading.Thread(target=worker, args=kv) for kv in jobs.items()]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
