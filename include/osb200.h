@@ -54,6 +54,9 @@ uint64_t osb_launch_count(void);
  * osb_profile_report synchronises the device and writes {"kernel": {"ms": total, "launches": n}, ...}. */
 int osb_profile_enable(int on);
 int osb_profile_report(char* buf, size_t capacity);
+/* test aid: fills the shared memory of every SM with NaN bit patterns and synchronises the device, so that a kernel
+ * relying on stale shared memory (instead of what it wrote itself) shows up as a mismatch in the next call */
+int osb_debug_poison_smem(void);
 
 /* ---------------------------------------------------------------- G.711 + linear resample
  * replaces audioop.ulaw2lin/alaw2lin/lin2ulaw/lin2alaw and _resample_linear as called from

@@ -223,6 +223,29 @@ const char* osb_last_error(void) { return osb::t_err; }
 
 uint64_t osb_launch_count(void) { return osb::g_launches.load(); }
 
+namespace osb {
+__global__ void __launch_bounds__(1024, 1) k_poison_smem(int words, unsigned int* sink) {
+    extern __shared__ unsigned int psm[];
+    for (int i = threadIdx.x; i < words; i += blockDim.x) psm[i] = 0x7FC00000u | (unsigned)(i & 0xFFFF);  // quiet NaNs
+    __syncthreads();
+    if (sink && psm[(threadIdx.x * 7919) % words] == 0u) *sink = 1;  // keeps the stores alive
+}
+}  // namespace osb
+
+int osb_debug_poison_smem(void) {
+    int rc = osb::ensure_init();
+    if (rc) return rc;
+    int dev = 0, max_smem = 0;
+    OSB_CUDA(cudaGetDevice(&dev));
+    OSB_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    OSB_CUDA(cudaFuncSetAttribute(osb::k_poison_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    OSB_CUDA(cudaDeviceSynchronize());
+    osb::k_poison_smem<<<4 * osb::num_sms(), 1024, max_smem>>>(max_smem / 4, nullptr);  // one CTA per SM at a time, four waves
+    OSB_CUDA(cudaGetLastError());
+    OSB_CUDA(cudaDeviceSynchronize());
+    return OSB_OK;
+}
+
 int osb_profile_enable(int on) {
     std::lock_guard<std::mutex> lk(osb::g_prof_mu);
     if (on) osb::g_prof_acc.clear();
