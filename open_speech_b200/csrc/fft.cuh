@@ -66,17 +66,21 @@ OSB_HD void fft_pow2(cpx (&v)[N]) {
             const int blk = g / half, j = g - blk * half, b = blk * len;
             const int ti = j * step;  // compile-time after unrolling: trivial twiddles cost no multiplies
             const cpx a = v[b + j], q = v[b + j + half];
-            cpx t;
             if (ti == 0) {
-                t = q;
+                v[b + j] = cadd(a, q);
+                v[b + j + half] = csub(a, q);
             } else if (ti == 8) {  // -i (forward) / +i (inverse)
-                t = INV ? cpx{-q.y, q.x} : cpx{q.y, -q.x};
+                const cpx t = INV ? cpx{-q.y, q.x} : cpx{q.y, -q.x};
+                v[b + j] = cadd(a, t);
+                v[b + j + half] = csub(a, t);
             } else {
+                // a + w q as two FMA chains, a - w q = 2a - (a + w q): six FMA-pipe instructions with immediate
+                // twiddles instead of a complex multiply and four additions
                 const float wc = c32[ti], ws = INV ? s32[ti] : -s32[ti];
-                t = cpx{q.x * wc - q.y * ws, q.x * ws + q.y * wc};
+                const cpx hi = cpx{fmaf(q.x, wc, fmaf(-q.y, ws, a.x)), fmaf(q.x, ws, fmaf(q.y, wc, a.y))};
+                v[b + j] = hi;
+                v[b + j + half] = cpx{fmaf(2.0f, a.x, -hi.x), fmaf(2.0f, a.y, -hi.y)};
             }
-            v[b + j] = cadd(a, t);
-            v[b + j + half] = csub(a, t);
         }
     }
 }
