@@ -271,6 +271,17 @@ def run_gpu(args) -> None:
     e2e_value = world * audio_s_per_step / (ms_e2e / 1000.0)
     checksum = float(mel_host[0, :, :16].double().sum())  # the D2H result is really read
 
+    # ---- one clip, host bytes in -> host features out (BASELINE configs[0] is literally a single clip): latency, not throughput
+    single = None
+    if rank == 0:
+        lat = []
+        for i in range(60):
+            t0 = time.perf_counter()
+            N.call("osb_stt_frontend_host", pcm_host.data_ptr(), n, 1, n, SR, int(nr), int(norm), n_mels, mel_host.data_ptr())
+            lat.append((time.perf_counter() - t0) * 1e3)
+        lat = sorted(lat[10:])
+        single = {"p50_ms": lat[len(lat) // 2], "p99_ms": lat[-1], "x_realtime_p50": seconds / (lat[len(lat) // 2] / 1e3)}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -307,7 +318,7 @@ def run_gpu(args) -> None:
                        "l2": f"inputs larger than L2 ({h2d_bytes / 1e6:.0f} MB of pcm16 per GPU per step vs 126 MB)"},
             "clocks": clocks, "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                                       "ms_per_step": ms_e2e, "checksum": checksum},
-            "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu}
+            "single_clip_latency": single, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

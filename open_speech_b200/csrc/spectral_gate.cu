@@ -105,36 +105,81 @@ __device__ __forceinline__ float fast_mag(float re, float im) {
 // grid (ceil(F/16), n_chunks, batch), 256 threads.  S[((clip*n_chunks+chunk)*F + t)*513 + f]
 constexpr int kStftFrames = 16, kStftXs = NH * (kStftFrames - 1) + NF;  // 4864
 
+// interior tile of pcm16 audio: its 4864 samples are one aligned run inside the clip and can be fetched by the TMA unit
+__device__ __forceinline__ bool nr_stft_interior(const void* audio, const NrGeom& g, int clip, int chunk, int t0, const int16_t** src) {
+    const long long p0 = (long long)NH * t0 - NF / 2;
+    const long long i0 = (long long)chunk * kChunk - kCtx + p0;  // clip index of the first staged sample (multiple of 8)
+    const int16_t* s = reinterpret_cast<const int16_t*>(audio) + (long long)clip * g.stride + i0;
+    *src = s;
+    return g.fmt == OSB_FMT_PCM16 && p0 >= 0 && p0 + kStftXs <= g.Lc && i0 >= 0 && i0 + kStftXs <= g.n && (((uintptr_t)s) & 15) == 0;
+}
+
+// Persistent: 2 CTAs per SM walk the (clip, chunk, tile) list; the window / twiddle tables are fetched once per CTA and
+// the raw int16 samples of the CTA's next tile arrive by cp.async.bulk (mbarrier) while the current tile is transformed.
 __global__ void __launch_bounds__(256, 2) k_nr_stft(const void* __restrict__ audio, NrGeom g, const float* __restrict__ tabs,
-                                                    float2* __restrict__ S, float* __restrict__ A, float2* __restrict__ PR, double b) {
+                                                    float2* __restrict__ S, float* __restrict__ A, float2* __restrict__ PR, double b, int NT) {
     extern __shared__ __align__(16) float sm[];
     float* xs = sm;                 // [4864]
     float* win = xs + kStftXs;      // [1024]
     float* twc = win + NF;          // [1024]
     float* tws = twc + NF;          // [1024]
     float* Y = tws + NF;            // [8][2][32*33]; at the end plane k holds the 513 magnitudes of frame t0 + k
-    const int tid = threadIdx.x, t0 = blockIdx.x * kStftFrames, chunk = blockIdx.y, clip = blockIdx.z;
-    if (t0 >= nr_tlim(g, chunk)) {  // all-zero tile: only its (zero) aggregates exist
-        for (int f = tid; f < NB; f += 256) PR[(((long long)clip * g.n_chunks + chunk) * gridDim.x + blockIdx.x) * NB + f] = make_float2(0.f, 0.f);
-        return;
-    }
+    int16_t* raw = reinterpret_cast<int16_t*>(Y + 8 * 2 * kYPlane);  // [4864] int16, TMA destination
+    __shared__ __align__(8) uint64_t bar;
+    const int tid = threadIdx.x;
+    const long long total_tiles = (long long)NT * g.n_chunks * g.batch;
+    // tile -> (clip, chunk, t0); wants_tma: the tile is transformed (not all-zero) and its samples are one aligned run
+    auto decode = [&](long long tile, int& clip, int& chunk, int& t0) {
+        clip = (int)(tile / ((long long)NT * g.n_chunks));
+        const int rem = (int)(tile - (long long)clip * NT * g.n_chunks);
+        chunk = rem / NT;
+        t0 = (rem - chunk * NT) * kStftFrames;
+    };
+    auto wants_tma = [&](long long tile, const int16_t** src) {
+        if (tile >= total_tiles) return false;
+        int clip, chunk, t0;
+        decode(tile, clip, chunk, t0);
+        return t0 < nr_tlim(g, chunk) && nr_stft_interior(audio, g, clip, chunk, t0, src);
+    };
     for (int i = tid; i < 3 * NF; i += 256) win[i] = tabs[i];
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        const int16_t* src;
+        if (wants_tma(blockIdx.x, &src)) {
+            mbar_expect_tx(&bar, kStftXs * 2);
+            bulk_g2s(raw, src, kStftXs * 2, &bar);
+        }
+    }
+    __syncthreads();
+    uint32_t parity = 0;
+    for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    int clip, chunk, t0;
+    decode(tile, clip, chunk, t0);
+    const int tx = t0 / kStftFrames;
+    if (t0 >= nr_tlim(g, chunk)) {  // all-zero tile: only its (zero) aggregates exist
+        for (int f = tid; f < NB; f += 256) PR[(((long long)clip * g.n_chunks + chunk) * NT + tx) * NB + f] = make_float2(0.f, 0.f);
+        if (tid == 0) {  // nothing was in flight for this tile; keep the prefetch chain going for the next one
+            const int16_t* src;
+            if (wants_tma(tile + gridDim.x, &src)) {
+                fence_proxy_async();
+                mbar_expect_tx(&bar, kStftXs * 2);
+                bulk_g2s(raw, src, kStftXs * 2, &bar);
+            }
+        }
+        continue;
+    }
     const long long p0 = (long long)NH * t0 - NF / 2;
     {
-        const long long i0 = (long long)chunk * kChunk - kCtx + p0;  // clip index of the first staged sample (multiple of 8)
-        const int16_t* src = reinterpret_cast<const int16_t*>(audio) + (long long)clip * g.stride + i0;
-        const bool interior = g.fmt == OSB_FMT_PCM16 && p0 >= 0 && p0 + kStftXs <= g.Lc && i0 >= 0 && i0 + kStftXs <= g.n &&
-                              (((uintptr_t)src) & 15) == 0;
-        if (interior) {
-            uint4 v[3];
-#pragma unroll
-            for (int r = 0; r < 3; ++r)
-                if (tid + 256 * r < kStftXs / 8) v[r] = ld_stream_u4(src + 8 * (tid + 256 * r));
+        const int16_t* src;
+        if (nr_stft_interior(audio, g, clip, chunk, t0, &src)) {
+            mbar_wait(&bar, parity);
+            parity ^= 1u;
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
                 const int i8 = tid + 256 * r;
                 if (i8 < kStftXs / 8) {
-                    const uint32_t w[4] = {v[r].x, v[r].y, v[r].z, v[r].w};
+                    const uint4 v = *reinterpret_cast<const uint4*>(raw + 8 * i8);
+                    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
                     float o[8];
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
@@ -149,7 +194,15 @@ __global__ void __launch_bounds__(256, 2) k_nr_stft(const void* __restrict__ aud
             for (int i = tid; i < kStftXs; i += 256) xs[i] = nr_sample(audio, g, clip, chunk, p0 + i);
         }
     }
-    __syncthreads();
+    __syncthreads();  // xs complete; raw[] has been consumed by every thread
+    if (tid == 0) {   // prefetch the next tile of this CTA while this one is transformed
+        const int16_t* src;
+        if (wants_tma(tile + gridDim.x, &src)) {
+            fence_proxy_async();  // generic-proxy reads of raw[] above are ordered before the async-proxy write
+            mbar_expect_tx(&bar, kStftXs * 2);
+            bulk_g2s(raw, src, kStftXs * 2, &bar);
+        }
+    }
     // From here to the aggregates every warp works on its own frame pair and its own two planes: warp-level barriers only,
     // so the eight warps drift apart and overlap each other's shared-memory and arithmetic phases.
     const int q = tid >> 5, lane = tid & 31;
@@ -227,9 +280,10 @@ __global__ void __launch_bounds__(256, 2) k_nr_stft(const void* __restrict__ aud
                 R = fma(bpw, lf, R);
                 bpw *= a;
             }
-            PR[((row0 / g.F) * gridDim.x + blockIdx.x) * NB + f] = make_float2((float)lf, (float)R);
+            PR[((row0 / g.F) * NT + tx) * NB + f] = make_float2((float)lf, (float)R);
         }
     }
+    }  // tile loop (the next tile's staging only writes xs; its step 1 follows a barrier, after these plane reads)
 }
 
 // ---------------------------------------------------------------- time smoothing (filtfilt) + sigmoid mask + 2-D smoothing
@@ -631,7 +685,7 @@ __global__ void __launch_bounds__(256, 2) k_nr_istft(const float2* __restrict__ 
     }  // tile loop
 }
 
-constexpr int kStftSmem = (kStftXs + 3 * NF + 8 * 2 * kYPlane) * (int)sizeof(float);
+constexpr int kStftSmem = (kStftXs + 3 * NF + 8 * 2 * kYPlane) * (int)sizeof(float) + kStftXs * 2;
 constexpr int kSmoothSmem = kSmT * kSmWTap * (int)sizeof(float);
 constexpr int kIstftSmem = (3 * NF + NH + 8 * 2 * kYPlane + kOlaOut) * (int)sizeof(float);
 
@@ -710,7 +764,12 @@ int launch_spectral_gate(const void* d_audio, int fmt, long long n, long long ba
         const char* in = reinterpret_cast<const char*>(d_audio) + c0 * stride * (fmt == OSB_FMT_PCM16 ? 2 : 4);
         float* outp = d_out + c0 * stride;
         const long long n_rows = (long long)gb * g.n_chunks;
-        OSB_LAUNCH(k_nr_stft, dim3(NT, g.n_chunks, gb), 256, kStftSmem, st, (const void*)in, g, tabs, S, A, PR, b);
+        {
+            const long long total_tiles = (long long)NT * g.n_chunks * gb;
+            const long long persistent = 2ll * num_sms();  // 2 resident CTAs per SM (109 KB of shared memory each)
+            OSB_LAUNCH(k_nr_stft, (unsigned)(total_tiles < persistent ? total_tiles : persistent), 256, kStftSmem, st, (const void*)in, g, tabs,
+                       S, A, PR, b, NT);
+        }
         OSB_CHECK_LAUNCH();
         OSB_LAUNCH(k_nr_carry, (unsigned)((n_rows * NB + 127) / 128), 128, 0, st, A, PR, CF, CB, g.F, NT, n_rows, b);
         OSB_CHECK_LAUNCH();
