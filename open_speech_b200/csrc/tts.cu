@@ -582,6 +582,51 @@ static int robot_carrier(int sample_rate, const double** d_tab, int* period) {
     return OSB_OK;
 }
 
+// dynamic shared memory opt-in of the recurrence kernels, once per process (the effect entry points are called from
+// several threads at once)
+static cudaError_t fx_smem_attrs(int smem) {
+    static std::once_flag once;
+    static cudaError_t err = cudaSuccess;
+    std::call_once(once, [&] {
+        err = cudaFuncSetAttribute(k_fx_reverb<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (err == cudaSuccess) err = cudaFuncSetAttribute(k_fx_reverb<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (err == cudaSuccess) err = cudaFuncSetAttribute(k_fx_eq<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (err == cudaSuccess) err = cudaFuncSetAttribute(k_fx_eq<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    });
+    return err;
+}
+
+// exponential impulse response exp(-linspace(0, 6, L)) / sum, cached on the device per (device, L): no upload and no
+// host synchronisation on the effect path after the first use
+static int reverb_ir(int L, const double** d_ir, double* c0) {
+    static std::mutex mu;
+    static std::map<std::pair<int, int>, std::pair<double*, double>> cache;
+    int dev = 0;
+    OSB_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find({dev, L});
+    if (it == cache.end()) {
+        std::vector<double> ir(L);
+        double sum = 0.0;
+        for (int k = 0; k < L; ++k) {
+            // np.linspace(0, 6, L)[k] = k * (6/(L-1)), last = 6
+            const double t = (L == 1) ? 0.0 : (k == L - 1 ? 6.0 : k * (6.0 / (L - 1)));
+            ir[k] = std::exp(-t);
+        }
+        // ir /= ir.sum()  (numpy pairwise sum; the Kahan sum below agrees to the last ulp or two of ~L terms)
+        double c = 0.0;
+        for (int k = 0; k < L; ++k) { const double yk = ir[k] - c, t = sum + yk; c = (t - sum) - yk; sum = t; }
+        for (int k = 0; k < L; ++k) ir[k] /= sum;
+        double* d = nullptr;
+        OSB_CUDA(cudaMalloc(&d, sizeof(double) * L));
+        OSB_CUDA(cudaMemcpy(d, ir.data(), sizeof(double) * L, cudaMemcpyHostToDevice));
+        it = cache.emplace(std::make_pair(dev, L), std::make_pair(d, ir[0])).first;
+    }
+    *d_ir = it->second.first;
+    *c0 = it->second.second;
+    return OSB_OK;
+}
+
 static void fx_after_recurrence(FxState& s, double* dst) {
     if (s.post.finish) s.finished = true;
     else { s.cur = dst; s.f64 = true; }
@@ -619,38 +664,20 @@ static int fx_normalize(FxState& s, double target_lufs, Scratch& scr, bool defer
 static int fx_reverb(FxState& s, int sample_rate, int room_ms, double mix, Scratch& scr) {
     int L = (int)((long long)sample_rate * room_ms / 1000);
     if (L < 1) L = 1;
-    std::vector<double> ir(L);
-    double sum = 0.0;
-    for (int k = 0; k < L; ++k) {
-        // np.linspace(0, 6, L)[k] = k * (6/(L-1)), last = 6
-        const double t = (L == 1) ? 0.0 : (k == L - 1 ? 6.0 : k * (6.0 / (L - 1)));
-        ir[k] = std::exp(-t);
-    }
-    // ir /= ir.sum()  (numpy pairwise sum; the Kahan sum below agrees to the last ulp or two of ~L terms)
-    double c = 0.0;
-    for (int k = 0; k < L; ++k) { const double yk = ir[k] - c, t = sum + yk; c = (t - sum) - yk; sum = t; }
-    for (int k = 0; k < L; ++k) ir[k] /= sum;
-    double* d_ir;
-    OSB_CUDA(scr.alloc(&d_ir, (size_t)L));
-    OSB_CUDA(cudaMemcpyAsync(d_ir, ir.data(), sizeof(double) * L, cudaMemcpyHostToDevice, s.st));
-    OSB_CUDA(cudaStreamSynchronize(s.st));  // ir is a stack vector: the copy must finish before it goes away
+    const double* d_ir;
+    double ir0;
+    int rc = reverb_ir(L, &d_ir, &ir0);
+    if (rc) return rc;
     ReverbArgs a;
     a.rg = s.rg; a.ir = d_ir; a.L = L; a.mix = mix;
     a.r = (L == 1) ? 0.0 : std::exp(-6.0 / (L - 1));
-    a.c = ir[0];
+    a.c = ir0;
     a.rL = (L == 1) ? 0.0 : std::exp(-6.0 * L / (L - 1));
     a.rT = std::pow(a.r, (double)kRvT);
     double* dst = (s.cur == s.d_a) ? s.d_b : s.d_a;
     const dim3 g((unsigned)((s.max_len + kRvBlock - 1) / kRvBlock), (unsigned)s.batch);
     const int smem = 256 * kSegStride * (int)sizeof(double);
-    static bool attr_done = false;
-    if (!attr_done) {
-        OSB_CUDA(cudaFuncSetAttribute(k_fx_reverb<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        OSB_CUDA(cudaFuncSetAttribute(k_fx_reverb<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        OSB_CUDA(cudaFuncSetAttribute(k_fx_eq<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        OSB_CUDA(cudaFuncSetAttribute(k_fx_eq<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_done = true;
-    }
+    OSB_CUDA(fx_smem_attrs(smem));
     if (!s.f64) OSB_LAUNCH(k_fx_reverb<float>, g, 256, smem, s.st, (const float*)s.cur, a, s.pre, s.post, dst);
     else OSB_LAUNCH(k_fx_reverb<double>, g, 256, smem, s.st, (const double*)s.cur, a, s.pre, s.post, dst);
     OSB_CHECK_LAUNCH();
@@ -690,12 +717,7 @@ static int fx_eq(FxState& s, int sample_rate) {
     double* dst = (s.cur == s.d_a) ? s.d_b : s.d_a;
     const dim3 g((unsigned)((s.max_len + kEqOut - 1) / kEqOut), (unsigned)s.batch);
     const int smem = 256 * kSegStride * (int)sizeof(double);
-    static bool attr_done = false;
-    if (!attr_done) {
-        OSB_CUDA(cudaFuncSetAttribute(k_fx_eq<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        OSB_CUDA(cudaFuncSetAttribute(k_fx_eq<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_done = true;
-    }
+    OSB_CUDA(fx_smem_attrs(smem));
     if (!s.f64) OSB_LAUNCH(k_fx_eq<float>, g, 256, smem, s.st, (const float*)s.cur, a, s.pre, s.post, dst);
     else OSB_LAUNCH(k_fx_eq<double>, g, 256, smem, s.st, (const double*)s.cur, a, s.pre, s.post, dst);
     OSB_CHECK_LAUNCH();
