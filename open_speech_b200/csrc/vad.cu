@@ -710,11 +710,10 @@ static int build_tc_image(const std::vector<float>& B, int N, int Kp, int NT, Va
 
 template <int AMODE, int EPI>
 static int launch_gemm_tc(const GemmDesc& d, const VadModel::Tc& L, cudaStream_t st) {
-    static bool attr_done = false;
-    if (!attr_done) {
-        OSB_CUDA(cudaFuncSetAttribute(k_vad_gemm_tc<AMODE, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem));
-        attr_done = true;
-    }
+    static std::once_flag once;  // per template instance; VAD sessions are scored from several threads
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, [&] { attr_err = cudaFuncSetAttribute(k_vad_gemm_tc<AMODE, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem); });
+    OSB_CUDA(attr_err);
     OSB_LAUNCH((k_vad_gemm_tc<AMODE, EPI>), (d.M + kTcM - 1) / kTcM, kTcThreads, kTcSmem, st, d, (const uint16_t*)L.img, L.NT, L.n_tiles, L.k_chunks);
     OSB_CHECK_LAUNCH();
     return OSB_OK;
