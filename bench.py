@@ -171,6 +171,28 @@ def run_reference(args) -> None:
     print(json.dumps(line), flush=True)
 
 
+def bind_to_gpu_numa_node(torch, local: int):
+    """Run this rank (and first-touch its pinned staging buffers) on the NUMA node its GPU hangs off: with several ranks
+    per box the host<->device copies of the e2e leg otherwise cross the socket interconnect.  Returns the node or None."""
+    try:
+        p = torch.cuda.get_device_properties(local)
+        bus = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
 # ----------------------------------------------------------------------------- GPU arm
 def run_gpu(args) -> None:
     import torch
@@ -184,6 +206,7 @@ def run_gpu(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa_node(torch, local) if world > 1 else None
     N.require_gpu()
     N.check(N.lib().osb_init(local))
     if world > 1:
@@ -314,7 +337,7 @@ def run_gpu(args) -> None:
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": desc, "clips_per_gpu": clips, "seconds_per_clip": seconds, "sample_rate": SR, "n_mels": n_mels,
-                       "noise_reduce": nr, "normalize": norm, "global_clips": clips * world, "parallelism": f"clip-sharded x{world}, no collective",
+                       "noise_reduce": nr, "normalize": norm, "global_clips": clips * world, "parallelism": f"clip-sharded x{world}, no collective", "numa_node_rank0": numa,
                        "l2": f"inputs larger than L2 ({h2d_bytes / 1e6:.0f} MB of pcm16 per GPU per step vs 126 MB)"},
             "clocks": clocks, "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                                       "ms_per_step": ms_e2e, "checksum": checksum},
