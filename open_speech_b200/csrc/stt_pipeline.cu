@@ -73,16 +73,17 @@ int osb_stt_frontend_host(const int16_t* pcm, int64_t n, int64_t batch, int64_t 
         OSB_CUDA(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
         s_dev = ws.device;
     }
-    // clip groups (default 8 for large batches; OSB_STT_HOST_GROUPS=1..8 to tune): more groups = shorter pipeline fill and
-    // drain around the PCIe-bound middle, but smaller launches
-    int64_t bounds[9] = {0};
-    int groups = batch >= 64 ? 8 : (batch >= 16 ? 4 : 1);
+    // clip groups (OSB_STT_HOST_GROUPS=1..32 to tune): the middle of the pipeline is PCIe-bound (the float32 features
+    // leaving), so more groups = shorter fill (first H2D + first kernels) and drain; measured on 256 x 60 s: 8 groups
+    // 17.0 ms, 16: 16.2 ms, 24: 16.0 ms per step
+    int64_t bounds[33] = {0};
+    int groups = batch >= 192 ? 24 : (batch >= 64 ? 8 : (batch >= 16 ? 4 : 1));
     if (const char* e = getenv("OSB_STT_HOST_GROUPS")) {
         const int g = atoi(e);
-        if (g >= 1 && g <= 8 && g <= batch) groups = g;
+        if (g >= 1 && g <= 32 && g <= batch) groups = g;
     }
     for (int g = 0; g <= groups; ++g) bounds[g] = batch * g / groups;
-    cudaEvent_t ev_in[8], ev_done[8];
+    cudaEvent_t ev_in[32], ev_done[32];
     for (int g = 0; g < groups; ++g) {
         OSB_CUDA(cudaEventCreateWithFlags(&ev_in[g], cudaEventDisableTiming));
         OSB_CUDA(cudaEventCreateWithFlags(&ev_done[g], cudaEventDisableTiming));
