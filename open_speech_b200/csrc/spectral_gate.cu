@@ -352,9 +352,21 @@ struct NrSmooth {
 };
 
 // sigmoid(((x - as)/as - 2) * 10) = 1 / (1 + 2^((3 - x/as) * 10 log2 e)); 0/0 -> NaN on all-zero input, like the reference
+// Bare SFU instructions (rcp.approx / ex2.approx, ~1 ulp): the library forms add range fix-ups that cost more than the
+// operations themselves, 38 times per column and tile; the mask only needs ~1e-6.
+__device__ __forceinline__ float nr_rcp(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float nr_ex2(float x) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 __device__ __forceinline__ float nr_mask_value(float x, float as) {
-    const float q = __fdividef(x, as);
-    return __fdividef(1.0f, 1.0f + exp2f(fmaf(q, -14.426950408889634f, 43.28085122666890f)));
+    const float q = x * nr_rcp(as);
+    return nr_rcp(1.0f + nr_ex2(fmaf(q, -14.426950408889634f, 43.28085122666890f)));
 }
 
 // BOX: tri(n) = box(n+1) * box(n+1) / (n+1), so both smoothing axes are two running sums instead of 2n+1 taps
