@@ -98,7 +98,9 @@ __device__ __forceinline__ int nr_tlim(const NrGeom& g, int chunk) {
 // |z| through the SFU reciprocal square root (2 ulp); |S| only feeds the smoothed-threshold mask
 __device__ __forceinline__ float fast_mag(float re, float im) {
     const float p = fmaf(re, re, im * im);
-    return p > 0.f ? p * rsqrtf(p) : 0.f;
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(p));  // bare MUFU.RSQ: no denormal fix-ups
+    return p > 1e-30f ? p * r : 0.f;                          // |S| < 1e-15 is zero for every purpose here
 }
 
 // ---------------------------------------------------------------- forward STFT
