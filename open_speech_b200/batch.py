@@ -115,12 +115,11 @@ class TtsPost:
         b, total = offsets.numel(), flat.numel()
         post = torch.empty_like(flat)
         new_lens = torch.empty_like(lens)
-        N.call("osb_tts_post_dev", flat.data_ptr(), offsets.data_ptr(), lens.data_ptr(), b, int(max_len), int(self.trim), int(self.normalize),
-               0.01, 0.95, post.data_ptr(), new_lens.data_ptr(), _stream())
         if out_pcm is None:
             out_pcm = torch.empty(total, dtype=torch.int16, device=flat.device)
-        N.call("osb_fx_chain_dev", post.data_ptr(), offsets.data_ptr(), new_lens.data_ptr(), b, int(max_len), total, self.sample_rate,
-               N.ptr(self.fx_types), N.ptr(self.fx_p0), N.ptr(self.fx_p1), len(self.fx_types), out_pcm.data_ptr(), 1, _stream())
+        N.call("osb_tts_post_fx_dev", flat.data_ptr(), offsets.data_ptr(), lens.data_ptr(), b, int(max_len), total, int(self.trim),
+               int(self.normalize), 0.01, 0.95, self.sample_rate, N.ptr(self.fx_types), N.ptr(self.fx_p0), N.ptr(self.fx_p1),
+               len(self.fx_types), post.data_ptr(), new_lens.data_ptr(), out_pcm.data_ptr(), 1, _stream())
         return out_pcm, new_lens
 
     @staticmethod

@@ -66,8 +66,11 @@ __global__ void k_tts_stats_init(TtsStats* st, int batch) {
     if (i < batch) st[i] = TtsStats{0x7fffffff, -1, 0u, 0};
 }
 
+// sumsq (optional): per-utterance sum of squares of the samples written (float32 squares summed wide, as k_fx_sumsq
+// does): an RMS normalise at the head of the effects chain then needs no pass of its own
 __global__ void __launch_bounds__(256) k_tts_apply(const float* __restrict__ x, Ragged rg, const TtsStats* __restrict__ st, int trim,
-                                                   int normalize, float peak, float* __restrict__ y, long long* __restrict__ out_len) {
+                                                   int normalize, float peak, float* __restrict__ y, long long* __restrict__ out_len,
+                                                   double* __restrict__ sumsq) {
     const int b = blockIdx.y;
     const long long n = rg.lens[b];
     const TtsStats s = st[b];
@@ -81,9 +84,16 @@ __global__ void __launch_bounds__(256) k_tts_apply(const float* __restrict__ x, 
     const float scale = scale_on ? (float)((double)peak / (double)mx) : 1.0f;
     const float* p = x + rg.offsets[b] + start;
     float* q = y + rg.offsets[b];
+    double acc = 0.0;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (long long)gridDim.x * blockDim.x) {
         const float v = p[i];
-        q[i] = scale_on ? fminf(fmaxf(__fmul_rn(v, scale), -1.0f), 1.0f) : v;
+        const float o = scale_on ? fminf(fmaxf(__fmul_rn(v, scale), -1.0f), 1.0f) : v;
+        q[i] = o;
+        acc += (double)__fmul_rn(o, o);
+    }
+    if (sumsq) {
+        acc = warp_sum(acc);
+        if ((threadIdx.x & 31) == 0) atomicAdd(&sumsq[b], acc);
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) out_len[b] = m;
 }
@@ -634,15 +644,21 @@ static void fx_after_recurrence(FxState& s, double* dst) {
     s.post = FxPost{0, 0, 1, nullptr, nullptr};
 }
 
-static int fx_normalize(FxState& s, double target_lufs, Scratch& scr, bool defer) {
+static int fx_normalize(FxState& s, double target_lufs, Scratch& scr, bool defer, const double* have_sumsq = nullptr) {
     double* sumsq;
-    OSB_CUDA(scr.alloc(&sumsq, (size_t)s.batch));
-    OSB_CUDA(cudaMemsetAsync(sumsq, 0, sizeof(double) * s.batch, s.st));
+    if (have_sumsq) {
+        sumsq = const_cast<double*>(have_sumsq);  // the producer of s.cur already summed its squares (float32 data)
+    } else {
+        OSB_CUDA(scr.alloc(&sumsq, (size_t)s.batch));
+        OSB_CUDA(cudaMemsetAsync(sumsq, 0, sizeof(double) * s.batch, s.st));
+    }
     const dim3 g = ragged_grid(s.max_len, s.batch);
     const double target_rms = std::pow(10.0, target_lufs / 20.0);
     if (!s.f64) {
-        OSB_LAUNCH(k_fx_sumsq<float>, g, 256, 0, s.st, (const float*)s.cur, s.rg, sumsq);
-        OSB_CHECK_LAUNCH();
+        if (!have_sumsq) {
+            OSB_LAUNCH(k_fx_sumsq<float>, g, 256, 0, s.st, (const float*)s.cur, s.rg, sumsq);
+            OSB_CHECK_LAUNCH();
+        }
         if (defer) {  // the next effect is a recurrence kernel: it applies the gain while loading
             s.pre = FxPre{sumsq, target_rms};
             return OSB_OK;
@@ -742,8 +758,8 @@ using namespace osb;
 
 extern "C" {
 
-int osb_tts_post_dev(const float* d_in, const int64_t* d_offsets, const int64_t* d_lens, int64_t batch, int64_t max_len, int trim,
-                     int normalize, float threshold, float peak, float* d_out, int64_t* d_out_lens, void* stream) {
+static int tts_post_impl(const float* d_in, const int64_t* d_offsets, const int64_t* d_lens, int64_t batch, int64_t max_len, int trim,
+                         int normalize, float threshold, float peak, float* d_out, int64_t* d_out_lens, double* d_sumsq, void* stream) {
     int rc = ensure_init();
     if (rc) return rc;
     OSB_REQUIRE(batch >= 0 && max_len >= 0, "bad sizes");
@@ -760,14 +776,20 @@ int osb_tts_post_dev(const float* d_in, const int64_t* d_offsets, const int64_t*
     const dim3 g = ragged_grid(max_len > 0 ? max_len : 1, batch);
     OSB_LAUNCH(k_tts_stats, g, 256, 0, st, d_in, rg, threshold, stats);
     OSB_CHECK_LAUNCH();
-    OSB_LAUNCH(k_tts_apply, g, 256, 0, st, d_in, rg, stats, trim, normalize, peak, d_out, (long long*)d_out_lens);
+    OSB_LAUNCH(k_tts_apply, g, 256, 0, st, d_in, rg, stats, trim, normalize, peak, d_out, (long long*)d_out_lens, d_sumsq);
     OSB_CHECK_LAUNCH();
     return OSB_OK;
 }
 
-int osb_fx_chain_dev(const float* d_in, const int64_t* d_offsets, const int64_t* d_lens, int64_t batch, int64_t max_len,
-                     int64_t total, int sample_rate, const int* fx_types, const double* fx_p0, const double* fx_p1, int n_fx,
-                     void* d_out, int out_pcm16, void* stream) {
+int osb_tts_post_dev(const float* d_in, const int64_t* d_offsets, const int64_t* d_lens, int64_t batch, int64_t max_len, int trim,
+                     int normalize, float threshold, float peak, float* d_out, int64_t* d_out_lens, void* stream) {
+    return tts_post_impl(d_in, d_offsets, d_lens, batch, max_len, trim, normalize, threshold, peak, d_out, d_out_lens, nullptr, stream);
+}
+
+// d_in_sumsq (optional): per-utterance sum of squares of d_in, used by a normalise that is the first effective effect
+static int fx_chain_impl(const float* d_in, const int64_t* d_offsets, const int64_t* d_lens, int64_t batch, int64_t max_len,
+                         int64_t total, int sample_rate, const int* fx_types, const double* fx_p0, const double* fx_p1, int n_fx,
+                         void* d_out, int out_pcm16, const double* d_in_sumsq, void* stream) {
     int rc = ensure_init();
     if (rc) return rc;
     OSB_REQUIRE(batch >= 0 && max_len >= 0 && max_len < (1ll << 31) && total >= 0 && n_fx >= 0 && sample_rate > 0, "bad sizes");
@@ -804,7 +826,7 @@ int osb_fx_chain_dev(const float* d_in, const int64_t* d_offsets, const int64_t*
             if (k + 1 + s.post.robot == m) { s.post.finish = out_pcm16 ? 2 : 1; s.post.out = d_out; }
         }
         switch (fx_types[i]) {
-            case OSB_FX_NORMALIZE: rc = fx_normalize(s, fx_p0[i], scr, !s.f64 && is_rec(k + 1)); break;
+            case OSB_FX_NORMALIZE: rc = fx_normalize(s, fx_p0[i], scr, !s.f64 && is_rec(k + 1), k == 0 ? d_in_sumsq : nullptr); break;
             case OSB_FX_REVERB: { const int rob = s.post.robot; rc = fx_reverb(s, sample_rate, (int)fx_p0[i], fx_p1[i], scr); k += rob; break; }
             case OSB_FX_PODCAST_EQ: { const int rob = s.post.robot; rc = fx_eq(s, sample_rate); k += rob; break; }
             case OSB_FX_ROBOT: rc = fx_robot(s, sample_rate); break;
@@ -829,6 +851,29 @@ int osb_fx_chain_dev(const float* d_in, const int64_t* d_offsets, const int64_t*
     }
     OSB_CHECK_LAUNCH();
     return OSB_OK;
+}
+
+int osb_fx_chain_dev(const float* d_in, const int64_t* d_offsets, const int64_t* d_lens, int64_t batch, int64_t max_len,
+                     int64_t total, int sample_rate, const int* fx_types, const double* fx_p0, const double* fx_p1, int n_fx,
+                     void* d_out, int out_pcm16, void* stream) {
+    return fx_chain_impl(d_in, d_offsets, d_lens, batch, max_len, total, sample_rate, fx_types, fx_p0, fx_p1, n_fx, d_out, out_pcm16, nullptr, stream);
+}
+
+int osb_tts_post_fx_dev(const float* d_in, const int64_t* d_offsets, const int64_t* d_lens, int64_t batch, int64_t max_len, int64_t total,
+                        int trim, int normalize, float threshold, float peak, int sample_rate, const int* fx_types, const double* fx_p0,
+                        const double* fx_p1, int n_fx, float* d_post, int64_t* d_out_lens, void* d_out, int out_pcm16, void* stream) {
+    int rc = ensure_init();
+    if (rc) return rc;
+    OSB_REQUIRE(batch >= 0 && total >= 0, "bad sizes");
+    if (batch == 0 || total == 0) return OSB_OK;
+    OSB_REQUIRE(d_post && d_out_lens, "null buffer");
+    cudaStream_t st = (cudaStream_t)stream;
+    Scratch scr(st);
+    double* sumsq;
+    OSB_CUDA(scr.alloc(&sumsq, (size_t)batch));
+    OSB_CUDA(cudaMemsetAsync(sumsq, 0, sizeof(double) * batch, st));
+    if ((rc = tts_post_impl(d_in, d_offsets, d_lens, batch, max_len, trim, normalize, threshold, peak, d_post, d_out_lens, sumsq, stream))) return rc;
+    return fx_chain_impl(d_post, d_offsets, d_out_lens, batch, max_len, total, sample_rate, fx_types, fx_p0, fx_p1, n_fx, d_out, out_pcm16, sumsq, stream);
 }
 
 int osb_voice_blend_dev(const float* d_packs, int64_t pack_elems, const int32_t* d_idx, const float* d_weights, int kmax, int64_t batch,
