@@ -457,8 +457,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_vad_gemm_tc(GemmDesc d, const
 //
 // The hidden vector has to reach every FMA from shared memory, and the shared-memory pipe - not the FMA pipe - bounds
 // the step.  So a thread does not own one 128-long row (32 h loads per stream) but a 4-row x 32-column block (8 h
-// loads per stream): lane l of warp w holds W[32w + 4(l>>2) + i][32(l&3) + k], i < 4, k < 32, the four lanes of a
-// group combine their partial sums with two shuffle rounds, and each lane ends up with one finished gate row.
+// loads per stream): lane l of warp w holds W[32w + 4(l&7) + i][32(l>>3) + k], i < 4, k < 32 (the 8 lanes of a
+// quarter-warp share one column quarter, so each 16-byte h load is a single address per quarter-warp), the four lanes
+// l, l^8, l^16, l^24 combine their partial sums with two shuffle rounds, and each lane ends up with one finished gate row.
 // The matvec issues as packed FFMA2.  S is chosen so that the grid is at most one wave (148 CTAs).
 __device__ __forceinline__ float sigmoidf_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
 // cell non-linearities on the SFU (ex2 + rcp): absolute error ~1e-7, three decimal orders inside the 1e-3 probability
@@ -477,8 +478,8 @@ struct RecurCfg {
     static constexpr int smem = (SKG * 4 * 4 * kGates + S * (4 * kHq + kGates) + kHid + 4 * S) * (int)sizeof(float);
 };
 __host__ __device__ inline int recur_own_row(int tid) {  // the gate row a thread holds after the shuffle reduction
-    const int q = tid & 3;
-    return (tid >> 5) * 32 + ((tid & 31) >> 2) * 4 + ((q & 1) << 1 | (q >> 1));
+    const int q = (tid & 31) >> 3;  // column quarter = quarter-warp: the 8 lanes of a quarter-warp load the same h chunk
+    return (tid >> 5) * 32 + (tid & 7) * 4 + ((q & 1) << 1 | (q >> 1));
 }
 
 // whh_perm: float4 chunk c = i*8 + kg of thread tid at [(c*512 + tid)*4], i = row of the block, kg = column group
@@ -494,7 +495,7 @@ __global__ void __launch_bounds__(512, 1) k_vad_recur(const float* __restrict__ 
     float* g_sm = h_sm + S * 4 * kHq;                             // [S][512]
     float* dw_sm = g_sm + S * kGates;                             // [128]
     float* part_sm = dw_sm + kHid;                                // [S][4]
-    const int tid = threadIdx.x, q = tid & 3, b0 = blockIdx.x * S;
+    const int tid = threadIdx.x, q = (tid & 31) >> 3, b0 = blockIdx.x * S;
     const int ns = min(S, batch - b0);                            // live streams of this CTA
     const int own = recur_own_row(tid);
     float4 w[4][RKG];
@@ -552,10 +553,10 @@ __global__ void __launch_bounds__(512, 1) k_vad_recur(const float* __restrict__ 
         for (int s = 0; s < S; ++s) {
             const float p0 = a[0][s].x + a[0][s].y, p1 = a[1][s].x + a[1][s].y, p2 = a[2][s].x + a[2][s].y, p3 = a[3][s].x + a[3][s].y;
             const bool hi = q & 1;
-            const float v0 = (hi ? p2 : p0) + __shfl_xor_sync(0xffffffffu, hi ? p0 : p2, 1);
-            const float v1 = (hi ? p3 : p1) + __shfl_xor_sync(0xffffffffu, hi ? p1 : p3, 1);
+            const float v0 = (hi ? p2 : p0) + __shfl_xor_sync(0xffffffffu, hi ? p0 : p2, 8);
+            const float v1 = (hi ? p3 : p1) + __shfl_xor_sync(0xffffffffu, hi ? p1 : p3, 8);
             const bool hi2 = q & 2;
-            const float r = (hi2 ? v1 : v0) + __shfl_xor_sync(0xffffffffu, hi2 ? v0 : v1, 2);
+            const float r = (hi2 ? v1 : v0) + __shfl_xor_sync(0xffffffffu, hi2 ? v0 : v1, 16);
             g_sm[s * kGates + own] = r + pre_v[s];
         }
         __syncthreads();
@@ -869,7 +870,7 @@ int osb_vad_create(const float* weights_host, size_t n_floats, void** handle) {
         for (int tid = 0; tid < 512; ++tid)
             for (int i = 0; i < 4; ++i)
                 for (int kg = 0; kg < 8; ++kg) {
-                    const int row = (tid >> 5) * 32 + ((tid & 31) >> 2) * 4 + i, col = 32 * (tid & 3) + 4 * kg;
+                    const int row = (tid >> 5) * 32 + (tid & 7) * 4 + i, col = 32 * ((tid & 31) >> 3) + 4 * kg;
                     for (int e = 0; e < 4; ++e) perm[((size_t)(i * 8 + kg) * 512 + tid) * 4 + e] = w[oWhh + (size_t)row * 128 + col + e];
                 }
         if ((rc = upload(&m->whh_perm, perm))) {
