@@ -17,6 +17,8 @@ length and "changed" only).  The time-stretch half is librosa's published algori
 (stft 2048/512 Hann centred, phase_vocoder, istft with window-sum-square normalisation); the resampling
 half substitutes a Kaiser-windowed sinc interpolator (the "kaiser_best" design librosa used before soxr:
 64 zero crossings, 512 table entries per crossing, roll-off 0.9476, beta 14.77) for soxr_hq.
+tests/test_oracle_pitch.py checks the restated pieces against torch.stft / torch.istft, torchaudio's phase_vocoder and
+torchaudio's Kaiser-sinc resampler (independent implementations that are installed).
 """
 from __future__ import annotations
 
