@@ -182,9 +182,11 @@ int osb_tts_post_dev(const float* d_in, const int64_t* d_offsets, const int64_t*
 int osb_fx_chain_dev(const float* d_in, const int64_t* d_offsets, const int64_t* d_lens, int64_t batch, int64_t max_len,
                      int64_t total, int sample_rate, const int* fx_types, const double* fx_p0, const double* fx_p1, int n_fx,
                      void* d_out, int out_pcm16, void* stream);
-/* process_tts_chunks + apply_chain (+ float32_to_int16) in one call (src/main.py:848-857 runs them back to back): d_post
- * receives the trimmed / peak-normalised float32 utterances (at d_offsets, lengths in d_out_lens), d_out the chain's
- * result.  The post-processing pass leaves each utterance's sum of squares for a normalise at the head of the chain. */
+/* process_tts_chunks + apply_chain (+ float32_to_int16) in one call (src/main.py:848-857 runs them back to back).
+ * d_out receives the chain's result at d_offsets, d_out_lens the post-trim lengths.  When the chain starts with
+ * ([normalize ->] reverb | podcast_eq) its first kernel trims, peak-normalises and clips while loading and the
+ * post-processed utterances are never written; otherwise they are materialised in d_post (scratch of `total` floats,
+ * may be NULL; contents unspecified on return) and that pass leaves the sum of squares for a leading normalize. */
 int osb_tts_post_fx_dev(const float* d_in, const int64_t* d_offsets, const int64_t* d_lens, int64_t batch, int64_t max_len, int64_t total,
                         int trim, int normalize, float threshold, float peak, int sample_rate, const int* fx_types, const double* fx_p0,
                         const double* fx_p1, int n_fx, float* d_post, int64_t* d_out_lens, void* d_out, int out_pcm16, void* stream);

@@ -113,13 +113,12 @@ class TtsPost:
                  out_pcm: torch.Tensor | None = None):
         """flat f32 [total] (device), offsets/lens int64 [B] (device) -> (int16 [total], new lens int64 [B])."""
         b, total = offsets.numel(), flat.numel()
-        post = torch.empty_like(flat)
         new_lens = torch.empty_like(lens)
         if out_pcm is None:
             out_pcm = torch.empty(total, dtype=torch.int16, device=flat.device)
         N.call("osb_tts_post_fx_dev", flat.data_ptr(), offsets.data_ptr(), lens.data_ptr(), b, int(max_len), total, int(self.trim),
                int(self.normalize), 0.01, 0.95, self.sample_rate, N.ptr(self.fx_types), N.ptr(self.fx_p0), N.ptr(self.fx_p1),
-               len(self.fx_types), post.data_ptr(), new_lens.data_ptr(), out_pcm.data_ptr(), 1, _stream())
+               len(self.fx_types), 0, new_lens.data_ptr(), out_pcm.data_ptr(), 1, _stream())  # 0: intermediate from the library's pool
         return out_pcm, new_lens
 
     @staticmethod

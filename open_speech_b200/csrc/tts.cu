@@ -98,6 +98,45 @@ __global__ void __launch_bounds__(256) k_tts_apply(const float* __restrict__ x, 
     if (blockIdx.x == 0 && threadIdx.x == 0) out_len[b] = m;
 }
 
+// trim_silence / normalize_output as a plan instead of a pass: where the kept span starts, how long it is and the
+// peak gain, so that the first kernel of the effects chain can read the untouched input (osb_tts_post_fx_dev)
+__global__ void k_tts_plan(Ragged rg, const TtsStats* __restrict__ st, int batch, int trim, int normalize, float peak,
+                           long long* __restrict__ offs2, long long* __restrict__ lens2, float* __restrict__ pscale, int* __restrict__ pon) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= batch) return;
+    const long long n = rg.lens[b];
+    const TtsStats s = st[b];
+    long long start = 0, m = n;
+    if (trim && n > 0 && s.last >= 0) {
+        start = s.first;
+        m = (long long)s.last - s.first + 1;
+    }
+    const float mx = __uint_as_float(s.maxbits);
+    const bool on = normalize && m > 0 && mx > 1e-8f;
+    offs2[b] = rg.offsets[b] + start;
+    lens2[b] = m;
+    pscale[b] = on ? (float)((double)peak / (double)mx) : 1.0f;
+    pon[b] = on ? 1 : 0;
+}
+
+// sum of squares of the post-processed utterance without materialising it (same arithmetic as k_tts_apply + k_fx_sumsq)
+__global__ void __launch_bounds__(256) k_fx_sumsq_post(const float* __restrict__ x, Ragged rg, const float* __restrict__ pscale,
+                                                       const int* __restrict__ pon, double* __restrict__ sumsq) {
+    const int b = blockIdx.y;
+    const long long n = rg.lens[b];
+    const float* p = x + rg.offsets[b];
+    const bool on = pon[b] != 0;
+    const float sc = pscale[b];
+    double acc = 0.0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float v = p[i];
+        const float o = on ? fminf(fmaxf(__fmul_rn(v, sc), -1.0f), 1.0f) : v;
+        acc += (double)__fmul_rn(o, o);
+    }
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&sumsq[b], acc);
+}
+
 // ---------------------------------------------------------------- effects: normalise (RMS), robot, cast
 template <typename T>
 __global__ void __launch_bounds__(256) k_fx_sumsq(const T* __restrict__ x, Ragged rg, double* __restrict__ sumsq) {
@@ -150,14 +189,15 @@ __global__ void __launch_bounds__(256) k_fx_robot(const T* __restrict__ x, Ragge
 
 // final astype(float32) (f64 -> f32) or f32 copy; optionally clip/x32767/truncate to int16 (float32_to_int16)
 template <typename T, bool PCM16>
-__global__ void __launch_bounds__(256) k_fx_finish(const T* __restrict__ x, Ragged rg, void* __restrict__ y) {
+__global__ void __launch_bounds__(256) k_fx_finish(const T* __restrict__ x, Ragged rg, void* __restrict__ y, const long long* __restrict__ out_offsets) {
     const int b = blockIdx.y;
     const long long n = rg.lens[b];
     const T* p = x + rg.offsets[b];
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const float v = (float)p[i];
-        if (PCM16) reinterpret_cast<int16_t*>(y)[rg.offsets[b] + i] = (int16_t)quant_pcm16(v);
-        else reinterpret_cast<float*>(y)[rg.offsets[b] + i] = v;
+        const long long o = (out_offsets ? out_offsets[b] : rg.offsets[b]) + i;
+        if (PCM16) reinterpret_cast<int16_t*>(y)[o] = (int16_t)quant_pcm16(v);
+        else reinterpret_cast<float*>(y)[o] = v;
     }
 }
 
@@ -169,6 +209,14 @@ __global__ void __launch_bounds__(256) k_fx_finish(const T* __restrict__ x, Ragg
 struct FxPre {
     const double* sumsq;  // per-utterance sum of squares (null: no deferred normalise)
     double target_rms;
+    // deferred normalize_output (src/audio/postprocessing.py:17-23) of the utterance: x -> clip(x * peak_scale, -1, 1) where
+    // peak_on; applied before the gain above.  Null: the input is already post-processed.
+    const float* peak_scale;
+    const int* peak_on;
+};
+struct PreOps {
+    bool peak_on, gain_on;
+    float peak_scale, gain;
 };
 struct FxPost {
     int robot;    // multiply by the 100 Hz carrier sin(2 pi 100 n / sr) in float64
@@ -177,19 +225,31 @@ struct FxPost {
     const double* carrier;  // [period] sin(2*pi*100*(k/sr)) evaluated like numpy for n = k (host table); for n = k + m*period
                             // numpy's own value differs from it by the rounding of its growing argument (~1e-13)
     void* out;
+    const long long* out_offsets;  // where utterance b starts in `out` (null: at the input offsets)
 };
 
-__device__ __forceinline__ float fx_pre_scale(const FxPre& pre, int b, long long n, bool* on) {
-    *on = false;
-    if (!pre.sumsq || n == 0) return 1.0f;
-    const float rms = __fsqrt_rn((float)(pre.sumsq[b] / (double)n));
-    *on = !(rms < 1e-8f);
-    return (float)pre.target_rms / rms;  // python float / np.float32 -> np.float32
+__device__ __forceinline__ PreOps fx_pre_ops(const FxPre& pre, int b, long long n) {
+    PreOps o{false, false, 1.0f, 1.0f};
+    if (pre.peak_on && pre.peak_on[b]) { o.peak_on = true; o.peak_scale = pre.peak_scale[b]; }
+    if (pre.sumsq && n > 0) {
+        const float rms = __fsqrt_rn((float)(pre.sumsq[b] / (double)n));
+        o.gain_on = !(rms < 1e-8f);
+        o.gain = (float)pre.target_rms / rms;  // python float / np.float32 -> np.float32
+    }
+    return o;
+}
+// the float32 value the materialising kernels (k_tts_apply, k_fx_scale) would have stored for this sample
+__device__ __forceinline__ float fx_pre(float x, const PreOps& o) {
+    if (o.peak_on) x = fminf(fmaxf(__fmul_rn(x, o.peak_scale), -1.0f), 1.0f);
+    if (o.gain_on) x = __fmul_rn(x, o.gain);
+    return x;
 }
 template <typename T>
-__device__ __forceinline__ T fx_ld(const T* p, long long g, bool on, float scale) {
-    if (sizeof(T) == 4 && on) return (T)__fmul_rn((float)p[g], scale);
-    return p[g];
+__device__ __forceinline__ double fx_pre_d(T x, const PreOps& o) {
+    return sizeof(T) == 4 ? (double)fx_pre((float)x, o) : (double)x;
+}
+__device__ __forceinline__ long long fx_out_off(const FxPost& post, const Ragged& rg, int b) {
+    return post.out_offsets ? post.out_offsets[b] : rg.offsets[b];
 }
 __device__ __forceinline__ void fx_st(const FxPost& post, double* q, long long off, long long g, double v) {
     if (post.robot) v = v * post.carrier[(unsigned)g % (unsigned)post.period];  // utterances are shorter than 2^31 samples (checked by the caller)
@@ -223,8 +283,7 @@ __global__ void __launch_bounds__(256) k_fx_reverb(const T* __restrict__ x, Reve
     const long long n0 = (long long)blockIdx.x * kRvBlock;
     if (n0 >= n) return;
     const T* p = x + a.rg.offsets[b];
-    bool pon;
-    const float pscale = fx_pre_scale(pre, b, n, &pon);
+    const PreOps po = fx_pre_ops(pre, b, n);
     // stage u[i] = c (x[n0+i] - r^L x[n0+i-L]); eight samples' loads in flight per thread
 #pragma unroll 1
     for (int i0 = tid; i0 < kRvBlock; i0 += 256 * 8) {
@@ -238,8 +297,8 @@ __global__ void __launch_bounds__(256) k_fx_reverb(const T* __restrict__ x, Reve
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int i = i0 + 256 * j;
-            const double v = (sizeof(T) == 4 && pon) ? (double)__fmul_rn((float)xv[j], pscale) : (double)xv[j];
-            const double d = (sizeof(T) == 4 && pon) ? (double)__fmul_rn((float)xd[j], pscale) : (double)xd[j];
+            // zeros beyond the utterance stay zeros (the pre-ops map 0 to 0)
+            const double v = fx_pre_d(xv[j], po), d = fx_pre_d(xd[j], po);
             u[(i / kRvT) * kSegStride + (i % kRvT)] = a.c * (v - a.rL * d);
         }
     }
@@ -260,8 +319,7 @@ __global__ void __launch_bounds__(256) k_fx_reverb(const T* __restrict__ x, Reve
             }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const double v = (sizeof(T) == 4 && pon) ? (double)__fmul_rn((float)xv[j], pscale) : (double)xv[j];
-                part = fma(iv[j], v, part);
+                part = fma(iv[j], fx_pre_d(xv[j], po), part);
             }
         }
     }
@@ -319,9 +377,9 @@ __global__ void __launch_bounds__(256) k_fx_reverb(const T* __restrict__ x, Reve
             const long long g = n0 + i;
             if (g < n) {
                 // (1 - mix) * samples is a float32 product while samples is still float32 (NEP 50 weak scalar)
-                const T xg = (sizeof(T) == 4 && pon) ? (T)__fmul_rn((float)xv[j], pscale) : xv[j];
-                const double dry = (sizeof(T) == 4) ? (double)__fmul_rn((float)(1.0 - a.mix), (float)xg) : (1.0 - a.mix) * (double)xg;
-                fx_st(post, q, a.rg.offsets[b], g, dry + a.mix * u[(i / kRvT) * kSegStride + (i % kRvT)]);
+                const double xg = fx_pre_d(xv[j], po);
+                const double dry = (sizeof(T) == 4) ? (double)__fmul_rn((float)(1.0 - a.mix), (float)xg) : (1.0 - a.mix) * xg;
+                fx_st(post, q, fx_out_off(post, a.rg, b), g, dry + a.mix * u[(i / kRvT) * kSegStride + (i % kRvT)]);
             }
         }
     }
@@ -373,8 +431,7 @@ __global__ void __launch_bounds__(256) k_fx_eq(const T* __restrict__ x, EqArgs a
     if (n0 >= n) return;
     const T* p = x + a.rg.offsets[b];
     const long long base = n0 - kEqWarm;
-    bool pon;
-    const float pscale = fx_pre_scale(pre, b, n, &pon);
+    const PreOps po = fx_pre_ops(pre, b, n);
 #pragma unroll 1
     for (int i0 = tid; i0 < kEqWarm + kEqOut; i0 += 256 * 8) {
         T xv[8];
@@ -386,7 +443,7 @@ __global__ void __launch_bounds__(256) k_fx_eq(const T* __restrict__ x, EqArgs a
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int i = i0 + 256 * j;
-            u[(i / 32) * kSegStride + (i % 32)] = (sizeof(T) == 4 && pon) ? (double)__fmul_rn((float)xv[j], pscale) : (double)xv[j];
+            u[(i / 32) * kSegStride + (i % 32)] = fx_pre_d(xv[j], po);
         }
     }
     __syncthreads();
@@ -452,7 +509,7 @@ __global__ void __launch_bounds__(256) k_fx_eq(const T* __restrict__ x, EqArgs a
     double* q = y + a.rg.offsets[b];
     for (int i = kEqWarm + tid; i < kEqWarm + kEqOut; i += 256) {
         const long long g = base + i;
-        if (g < n) fx_st(post, q, a.rg.offsets[b], g, u[(i / 32) * kSegStride + (i % 32)]);
+        if (g < n) fx_st(post, q, fx_out_off(post, a.rg, b), g, u[(i / 32) * kSegStride + (i % 32)]);
     }
 }
 
@@ -563,8 +620,9 @@ struct FxState {
     float* f32_tmp;  // scratch buffers (total elements each)
     double* d_a;
     double* d_b;
-    FxPre pre{nullptr, 0.0};          // deferred float32 normalise, consumed by the next recurrence kernel
-    FxPost post{0, 0, 1, nullptr, nullptr};  // robot / final cast riding on the next recurrence kernel
+    FxPre pre{nullptr, 0.0, nullptr, nullptr};  // deferred float32 normalise(s), consumed by the next recurrence kernel
+    FxPost post{0, 0, 1, nullptr, nullptr, nullptr};  // robot / final cast riding on the next recurrence kernel
+    const long long* out_offsets = nullptr;  // final placement of utterance b (null: its input offset)
     bool finished = false;            // the final cast already happened inside a kernel
 };
 
@@ -640,11 +698,35 @@ static int reverb_ir(int L, const double** d_ir, double* c0) {
 static void fx_after_recurrence(FxState& s, double* dst) {
     if (s.post.finish) s.finished = true;
     else { s.cur = dst; s.f64 = true; }
-    s.pre = FxPre{nullptr, 0.0};
-    s.post = FxPost{0, 0, 1, nullptr, nullptr};
+    s.pre = FxPre{nullptr, 0.0, nullptr, nullptr};
+    s.post = FxPost{0, 0, 1, nullptr, nullptr, nullptr};
 }
 
-static int fx_normalize(FxState& s, double target_lufs, Scratch& scr, bool defer, const double* have_sumsq = nullptr) {
+// trim / peak-normalise left to the first kernel of the chain (osb_tts_post_fx_dev)
+struct TtsPlan {
+    const long long* offs2;        // start of the kept span of utterance b in the untouched input
+    const long long* lens2;        // its length
+    const float* pscale;           // peak gain
+    const int* pon;                // ... applied (with clip) where non-zero
+    const long long* out_offsets;  // where the result of utterance b goes
+};
+
+// effective chain: unknown types and zero pitch shifts are no-ops (chain.py:18-31, :46-47); returns the count or -1
+static int fx_effective(const int* fx_types, const double* fx_p0, int n_fx, int (&idx)[64]) {
+    int m = 0;
+    for (int i = 0; i < n_fx; ++i) {
+        const int t = fx_types[i];
+        const bool live = t == OSB_FX_NORMALIZE || t == OSB_FX_REVERB || t == OSB_FX_PODCAST_EQ || t == OSB_FX_ROBOT ||
+                          (t == OSB_FX_PITCH && fx_p0[i] != 0.0);
+        if (!live) continue;
+        if (m >= 64) return -1;
+        idx[m++] = i;
+    }
+    return m;
+}
+
+static int fx_normalize(FxState& s, double target_lufs, Scratch& scr, bool defer, const double* have_sumsq = nullptr,
+                        const TtsPlan* plan = nullptr) {
     double* sumsq;
     if (have_sumsq) {
         sumsq = const_cast<double*>(have_sumsq);  // the producer of s.cur already summed its squares (float32 data)
@@ -656,11 +738,13 @@ static int fx_normalize(FxState& s, double target_lufs, Scratch& scr, bool defer
     const double target_rms = std::pow(10.0, target_lufs / 20.0);
     if (!s.f64) {
         if (!have_sumsq) {
-            OSB_LAUNCH(k_fx_sumsq<float>, g, 256, 0, s.st, (const float*)s.cur, s.rg, sumsq);
+            if (plan) OSB_LAUNCH(k_fx_sumsq_post, g, 256, 0, s.st, (const float*)s.cur, s.rg, plan->pscale, plan->pon, sumsq);
+            else OSB_LAUNCH(k_fx_sumsq<float>, g, 256, 0, s.st, (const float*)s.cur, s.rg, sumsq);
             OSB_CHECK_LAUNCH();
         }
         if (defer) {  // the next effect is a recurrence kernel: it applies the gain while loading
-            s.pre = FxPre{sumsq, target_rms};
+            s.pre.sumsq = sumsq;
+            s.pre.target_rms = target_rms;
             return OSB_OK;
         }
         OSB_LAUNCH(k_fx_scale<float>, g, 256, 0, s.st, (const float*)s.cur, s.rg, sumsq, target_rms, s.f32_tmp);
@@ -789,7 +873,7 @@ int osb_tts_post_dev(const float* d_in, const int64_t* d_offsets, const int64_t*
 // d_in_sumsq (optional): per-utterance sum of squares of d_in, used by a normalise that is the first effective effect
 static int fx_chain_impl(const float* d_in, const int64_t* d_offsets, const int64_t* d_lens, int64_t batch, int64_t max_len,
                          int64_t total, int sample_rate, const int* fx_types, const double* fx_p0, const double* fx_p1, int n_fx,
-                         void* d_out, int out_pcm16, const double* d_in_sumsq, void* stream) {
+                         void* d_out, int out_pcm16, const double* d_in_sumsq, void* stream, const TtsPlan* plan = nullptr) {
     int rc = ensure_init();
     if (rc) return rc;
     OSB_REQUIRE(batch >= 0 && max_len >= 0 && max_len < (1ll << 31) && total >= 0 && n_fx >= 0 && sample_rate > 0, "bad sizes");
@@ -802,19 +886,18 @@ static int fx_chain_impl(const float* d_in, const int64_t* d_offsets, const int6
     s.st = st; s.rg = Ragged{(const long long*)d_offsets, (const long long*)d_lens};
     s.batch = batch; s.max_len = max_len > 0 ? max_len : 1; s.total = total;
     s.cur = (void*)d_in; s.f64 = false;
+    if (plan) {  // the chain reads the untouched input: kept spans, peak gain applied by its first kernel
+        s.rg = Ragged{plan->offs2, plan->lens2};
+        s.pre.peak_scale = plan->pscale;
+        s.pre.peak_on = plan->pon;
+        s.out_offsets = plan->out_offsets;
+    }
     OSB_CUDA(scr.alloc(&s.f32_tmp, (size_t)total));
     OSB_CUDA(scr.alloc(&s.d_a, (size_t)total));
     OSB_CUDA(scr.alloc(&s.d_b, (size_t)total));
-    // effective chain: unknown types and zero pitch shifts are no-ops (chain.py:18-31, :46-47)
-    int idx[64], m = 0;
-    for (int i = 0; i < n_fx; ++i) {
-        const int t = fx_types[i];
-        const bool live = t == OSB_FX_NORMALIZE || t == OSB_FX_REVERB || t == OSB_FX_PODCAST_EQ || t == OSB_FX_ROBOT ||
-                          (t == OSB_FX_PITCH && fx_p0[i] != 0.0);
-        if (!live) continue;
-        OSB_REQUIRE(m < 64, "more than 64 effects");
-        idx[m++] = i;
-    }
+    int idx[64];
+    const int m = fx_effective(fx_types, fx_p0, n_fx, idx);
+    OSB_REQUIRE(m >= 0, "more than 64 effects");
     auto is_rec = [&](int k) { return k < m && (fx_types[idx[k]] == OSB_FX_REVERB || fx_types[idx[k]] == OSB_FX_PODCAST_EQ); };
     for (int k = 0; k < m; ++k) {
         const int i = idx[k];
@@ -823,10 +906,10 @@ static int fx_chain_impl(const float* d_in, const int64_t* d_offsets, const int6
                 if ((rc = robot_carrier(sample_rate, &s.post.carrier, &s.post.period))) return rc;
                 s.post.robot = 1;
             }
-            if (k + 1 + s.post.robot == m) { s.post.finish = out_pcm16 ? 2 : 1; s.post.out = d_out; }
+            if (k + 1 + s.post.robot == m) { s.post.finish = out_pcm16 ? 2 : 1; s.post.out = d_out; s.post.out_offsets = s.out_offsets; }
         }
         switch (fx_types[i]) {
-            case OSB_FX_NORMALIZE: rc = fx_normalize(s, fx_p0[i], scr, !s.f64 && is_rec(k + 1), k == 0 ? d_in_sumsq : nullptr); break;
+            case OSB_FX_NORMALIZE: rc = fx_normalize(s, fx_p0[i], scr, !s.f64 && is_rec(k + 1), k == 0 ? d_in_sumsq : nullptr, k == 0 ? plan : nullptr); break;
             case OSB_FX_REVERB: { const int rob = s.post.robot; rc = fx_reverb(s, sample_rate, (int)fx_p0[i], fx_p1[i], scr); k += rob; break; }
             case OSB_FX_PODCAST_EQ: { const int rob = s.post.robot; rc = fx_eq(s, sample_rate); k += rob; break; }
             case OSB_FX_ROBOT: rc = fx_robot(s, sample_rate); break;
@@ -843,11 +926,11 @@ static int fx_chain_impl(const float* d_in, const int64_t* d_offsets, const int6
     if (s.finished) return OSB_OK;
     const dim3 g = ragged_grid(s.max_len, batch);
     if (s.f64) {
-        if (out_pcm16) OSB_LAUNCH((k_fx_finish<double, true>), g, 256, 0, st, (const double*)s.cur, s.rg, d_out);
-        else OSB_LAUNCH((k_fx_finish<double, false>), g, 256, 0, st, (const double*)s.cur, s.rg, d_out);
+        if (out_pcm16) OSB_LAUNCH((k_fx_finish<double, true>), g, 256, 0, st, (const double*)s.cur, s.rg, d_out, s.out_offsets);
+        else OSB_LAUNCH((k_fx_finish<double, false>), g, 256, 0, st, (const double*)s.cur, s.rg, d_out, s.out_offsets);
     } else {
-        if (out_pcm16) OSB_LAUNCH((k_fx_finish<float, true>), g, 256, 0, st, (const float*)s.cur, s.rg, d_out);
-        else OSB_LAUNCH((k_fx_finish<float, false>), g, 256, 0, st, (const float*)s.cur, s.rg, d_out);
+        if (out_pcm16) OSB_LAUNCH((k_fx_finish<float, true>), g, 256, 0, st, (const float*)s.cur, s.rg, d_out, s.out_offsets);
+        else OSB_LAUNCH((k_fx_finish<float, false>), g, 256, 0, st, (const float*)s.cur, s.rg, d_out, s.out_offsets);
     }
     OSB_CHECK_LAUNCH();
     return OSB_OK;
@@ -864,14 +947,44 @@ int osb_tts_post_fx_dev(const float* d_in, const int64_t* d_offsets, const int64
                         const double* fx_p1, int n_fx, float* d_post, int64_t* d_out_lens, void* d_out, int out_pcm16, void* stream) {
     int rc = ensure_init();
     if (rc) return rc;
-    OSB_REQUIRE(batch >= 0 && total >= 0, "bad sizes");
+    OSB_REQUIRE(batch >= 0 && total >= 0 && max_len >= 0 && n_fx >= 0, "bad sizes");
     if (batch == 0 || total == 0) return OSB_OK;
-    OSB_REQUIRE(d_post && d_out_lens, "null buffer");
+    OSB_REQUIRE(batch <= 65535, "batch too large (<= 65535)");
+    OSB_REQUIRE(d_in && d_offsets && d_lens && d_out_lens && d_out && (n_fx == 0 || (fx_types && fx_p0 && fx_p1)), "null buffer");
     cudaStream_t st = (cudaStream_t)stream;
     Scratch scr(st);
+    int idx[64];
+    const int m = fx_effective(fx_types, fx_p0, n_fx, idx);
+    OSB_REQUIRE(m >= 0, "more than 64 effects");
+    auto is_rec = [&](int k) { return k < m && (fx_types[idx[k]] == OSB_FX_REVERB || fx_types[idx[k]] == OSB_FX_PODCAST_EQ); };
+    if (is_rec(0) || (m >= 2 && fx_types[idx[0]] == OSB_FX_NORMALIZE && is_rec(1))) {
+        // The chain starts ([normalise ->] reverb / podcast_eq) with a kernel that can trim, peak-normalise and clip while
+        // it loads: only the statistics pass touches the input before it; the post-processed utterances are never written.
+        TtsStats* stats;
+        long long* offs2;
+        float* pscale;
+        int* pon;
+        OSB_CUDA(scr.alloc(&stats, (size_t)batch));
+        OSB_CUDA(scr.alloc(&offs2, (size_t)batch));
+        OSB_CUDA(scr.alloc(&pscale, (size_t)batch));
+        OSB_CUDA(scr.alloc(&pon, (size_t)batch));
+        Ragged rg{(const long long*)d_offsets, (const long long*)d_lens};
+        OSB_LAUNCH(k_tts_stats_init, (unsigned)((batch + 255) / 256), 256, 0, st, stats, (int)batch);
+        OSB_CHECK_LAUNCH();
+        OSB_LAUNCH(k_tts_stats, ragged_grid(max_len > 0 ? max_len : 1, batch), 256, 0, st, d_in, rg, threshold, stats);
+        OSB_CHECK_LAUNCH();
+        OSB_LAUNCH(k_tts_plan, (unsigned)((batch + 255) / 256), 256, 0, st, rg, stats, (int)batch, trim, normalize, peak, offs2,
+                   (long long*)d_out_lens, pscale, pon);
+        OSB_CHECK_LAUNCH();
+        const TtsPlan plan{offs2, (const long long*)d_out_lens, pscale, pon, (const long long*)d_offsets};
+        return fx_chain_impl(d_in, d_offsets, d_out_lens, batch, max_len, total, sample_rate, fx_types, fx_p0, fx_p1, n_fx, d_out, out_pcm16,
+                             nullptr, stream, &plan);
+    }
+    // any other chain head: materialise the post-processed utterances (into d_post, or scratch), leaving each one's sum of squares
     double* sumsq;
     OSB_CUDA(scr.alloc(&sumsq, (size_t)batch));
     OSB_CUDA(cudaMemsetAsync(sumsq, 0, sizeof(double) * batch, st));
+    if (!d_post) OSB_CUDA(scr.alloc(&d_post, (size_t)total));
     if ((rc = tts_post_impl(d_in, d_offsets, d_lens, batch, max_len, trim, normalize, threshold, peak, d_post, d_out_lens, sumsq, stream))) return rc;
     return fx_chain_impl(d_post, d_offsets, d_out_lens, batch, max_len, total, sample_rate, fx_types, fx_p0, fx_p1, n_fx, d_out, out_pcm16, sumsq, stream);
 }

@@ -169,3 +169,47 @@ def test_tts_batch_config5_chain(gpu):
         assert len(got) == len(ref) == lens[i]
         d = np.abs(got.astype(np.int32) - ref.astype(np.int32))
         assert d.max() <= 3, (i, int(d.max()))  # 1e-4 of full scale
+
+
+@pytest.mark.parametrize("fx", [
+    [{"type": "reverb", "room": "small"}],                                              # recurrence first: trim / peak gain while loading
+    [{"type": "normalize", "target_lufs": -20}, {"type": "podcast_eq"}, {"type": "robot"}],  # normalise + recurrence: both gains deferred
+    [{"type": "podcast_eq"}, {"type": "pitch", "semitones": 2}],                         # deferred head, float32 producer later in the chain
+    [{"type": "robot"}, {"type": "reverb"}],                                             # other head: materialised post-processing
+    [{"type": "normalize"}],                                                             # materialised, sum of squares handed over
+    [],                                                                                  # no effects: post-processing + cast only
+])
+@pytest.mark.parametrize("trim,normalize", [(True, True), (False, True), (True, False)])
+def test_tts_post_fx_one_call_matches_two_calls(gpu, fx, trim, normalize):
+    """osb_tts_post_fx_dev == osb_tts_post_dev followed by osb_fx_chain_dev, for every chain head it special-cases,
+    including utterances that are silent (nothing above the trim threshold, peak below 1e-8)."""
+    import torch
+    from open_speech_b200 import synth
+    from open_speech_b200.batch import TtsPost
+    from open_speech_b200.effects.chain import encode_effects
+
+    utts = synth.tts_batch(6, seed=77, distinct=6, min_s=0.4, max_s=1.5)
+    utts.append(np.zeros(5000, np.float32))                      # silent: returned unchanged by both reference functions
+    utts.append((0.004 * np.ones(3000)).astype(np.float32))      # below the trim threshold everywhere, but normalisable
+    flat, offsets, lens = TtsPost.pack(utts)
+    d_flat, d_off, d_len = torch.from_numpy(flat).cuda(), torch.from_numpy(offsets).cuda(), torch.from_numpy(lens).cuda()
+    b, total, max_len = len(utts), flat.size, int(lens.max())
+    types, p0, p1 = encode_effects(fx)
+    stream = torch.cuda.current_stream().cuda_stream
+    post = torch.empty_like(d_flat)
+    lens_a, lens_b = torch.empty_like(d_len), torch.empty_like(d_len)
+    out_a = torch.zeros(total, dtype=torch.int16, device="cuda")
+    out_b = torch.zeros(total, dtype=torch.int16, device="cuda")
+    gpu.call("osb_tts_post_dev", d_flat.data_ptr(), d_off.data_ptr(), d_len.data_ptr(), b, max_len, int(trim), int(normalize), 0.01, 0.95,
+             post.data_ptr(), lens_a.data_ptr(), stream)
+    gpu.call("osb_fx_chain_dev", post.data_ptr(), d_off.data_ptr(), lens_a.data_ptr(), b, max_len, total, 24000, gpu.ptr(types), gpu.ptr(p0),
+             gpu.ptr(p1), len(types), out_a.data_ptr(), 1, stream)
+    gpu.call("osb_tts_post_fx_dev", d_flat.data_ptr(), d_off.data_ptr(), d_len.data_ptr(), b, max_len, total, int(trim), int(normalize),
+             0.01, 0.95, 24000, gpu.ptr(types), gpu.ptr(p0), gpu.ptr(p1), len(types), 0, lens_b.data_ptr(), out_b.data_ptr(), 1, stream)
+    torch.cuda.synchronize()
+    assert torch.equal(lens_a, lens_b)
+    a, c = out_a.cpu().numpy(), out_b.cpu().numpy()
+    for i in range(b):
+        o, n = int(offsets[i]), int(lens_a[i].item())
+        d = np.abs(a[o:o + n].astype(np.int32) - c[o:o + n].astype(np.int32))
+        assert d.max(initial=0) <= 1, (i, int(d.max()))  # the summation order of the RMS may move a gain by one ulp
