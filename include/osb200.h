@@ -215,6 +215,18 @@ int osb_mix_tracks_host(const float* flat, const int64_t* offsets, const int64_t
                         int64_t total, float* out);
 int osb_interp_index_f32_host(const float* in, int64_t n, float* out, int64_t m);
 
+/* Realtime TTS output framing: src/realtime/server.py:249-251 and :268-277.
+ * osb_f32_to_pcm16_rt: (x * 32767).clip(-32768, 32767).astype(int16) -- the realtime handler's own quantiser (clip AFTER the
+ *   multiply; differs from float32_to_int16 for x <= -1).  Bit-exact.
+ * osb_base64_encode: RFC 4648 text of n payload bytes, 4*ceil(n/3) characters with '=' padding, no terminator; the reference's
+ *   3000-byte deltas are consecutive 4000-character slices of it.  Bit-exact vs base64.b64encode.
+ * osb_realtime_tts_encode_host: float32 24 kHz -> PCM16 -> out_fmt (PCM16: as is; ULAW/ALAW: np.interp to 8 kHz + lin2ulaw/lin2alaw,
+ *   n_out = int(n * (8000 / 24000)) computed by the caller as the reference does) -> payload bytes and/or their base64 text
+ *   (either pointer may be null). */
+int osb_f32_to_pcm16_rt_dev(const float* d_in, int16_t* d_out, size_t n, void* stream);
+int osb_base64_encode_dev(const uint8_t* d_in, size_t n, char* d_out, void* stream);
+int osb_realtime_tts_encode_host(const float* audio, int64_t n, int out_fmt, int64_t n_out, uint8_t* payload, char* b64);
+
 #ifdef __cplusplus
 }
 #endif

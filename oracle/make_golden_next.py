@@ -53,6 +53,23 @@ def main() -> None:
     g["wy_24k_to_16k"] = f(a, 24000)
     g["wy_22050_to_16k"] = f(a[:7777], 22050)
     g["wy_48k_to_16k"] = f(a, 48000)
+    # realtime TTS output framing (src/realtime/server.py:238-277).  The handler's body is a closure inside a coroutine, so its
+    # three statements are replayed here around the REFERENCE's own encode_pcm16_to_format and the stdlib base64 it calls.
+    import base64
+
+    from src.realtime.audio_buffer import encode_pcm16_to_format
+
+    rt = np.concatenate([a * 1.7, np.array([1.0, -1.0, 1.5, -1.5, 0.99999, -0.99999, 3.0517578125e-05, -3.0517578125e-05, 0.0],
+                                           dtype=np.float32)]).astype(np.float32)
+    g["rt_in_24k"] = rt
+    for n_take, tag in ((len(rt), "full"), (4001, "odd"), (2, "tiny")):
+        for fmt in ("pcm16", "g711_ulaw", "g711_alaw"):
+            combined = np.concatenate([rt[:n_take // 2], rt[n_take // 2:n_take]])
+            pcm16 = (combined * 32767).clip(-32768, 32767).astype(np.int16).tobytes()
+            audio_data = encode_pcm16_to_format(pcm16, 24000, fmt)
+            deltas = [base64.b64encode(audio_data[i:i + 3000]).decode("ascii") for i in range(0, len(audio_data), 3000)]
+            g[f"rt_payload_{tag}_{fmt}"] = np.frombuffer(audio_data, dtype=np.uint8)
+            g[f"rt_deltas_{tag}_{fmt}"] = np.frombuffer("\n".join(deltas).encode("ascii"), dtype=np.uint8)
     np.savez_compressed(os.path.join(OUT, "reference_vectors_next.npz"), **g)
     print("wrote", len(g), "arrays")
 

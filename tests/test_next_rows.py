@@ -116,3 +116,52 @@ def test_conversation_render_turns(gpu):
     assert out["duration_ms"] == int(1000 * len(ref) / 24000) and out["turn_duration_ms"] == [int(1000 * len(p) / 24000) for p in ref_parts]
     assert out["turn_wavs"][1] == otts.encode_wav(turns[1], 24000) and len(out["turn_wavs"][0]) == 44 + 2 * len(turns[0])
     assert render_turns([], None, 24000)["merged"].shape == (0,)
+
+
+# ---------------------------------------------------------------- realtime TTS output framing (src/realtime/server.py:238-277)
+_RT_CASES = [(tag, fmt) for tag in ("full", "odd", "tiny") for fmt in ("pcm16", "g711_ulaw", "g711_alaw")]
+
+
+def _rt_chunks(g, tag):
+    rt = g["rt_in_24k"]
+    n = {"full": len(rt), "odd": 4001, "tiny": 2}[tag]
+    return [rt[:n // 2], rt[n // 2:n]]
+
+
+def test_oracle_realtime_framing_matches_reference_vectors(gnext):
+    for tag, fmt in _RT_CASES:
+        chunks = _rt_chunks(gnext, tag)
+        assert nx.realtime_response_payload(chunks, fmt) == gnext[f"rt_payload_{tag}_{fmt}"].tobytes(), (tag, fmt)
+        assert "\n".join(nx.realtime_deltas(chunks, fmt)) == gnext[f"rt_deltas_{tag}_{fmt}"].tobytes().decode("ascii"), (tag, fmt)
+    assert nx.realtime_response_payload([], "pcm16") == b"" and nx.realtime_deltas([], "g711_ulaw") == []
+
+
+@pytest.mark.gpu
+def test_realtime_framing_gpu_bit_exact(gpu, gnext):
+    import base64
+
+    from open_speech_b200.realtime import tts_out
+
+    for tag, fmt in _RT_CASES:
+        chunks = _rt_chunks(gnext, tag)
+        want_payload = gnext[f"rt_payload_{tag}_{fmt}"].tobytes()
+        want_deltas = gnext[f"rt_deltas_{tag}_{fmt}"].tobytes().decode("ascii")
+        assert tts_out.encode_response_audio(chunks, fmt) == want_payload, (tag, fmt)
+        got = tts_out.audio_deltas(chunks, fmt)
+        assert "\n".join(got) == want_deltas, (tag, fmt)
+        assert all(len(d) == 4000 for d in got[:-1]) and b"".join(base64.b64decode(d) for d in got) == want_payload
+    # list chunks go through np.array(dtype=float32) like the reference; nothing to send -> nothing sent
+    assert tts_out.audio_deltas([[0.5, -0.25, 1.0]], "pcm16") == nx.realtime_deltas([[0.5, -0.25, 1.0]], "pcm16")
+    assert tts_out.encode_response_audio([], "pcm16") == b"" and tts_out.audio_deltas([], "g711_alaw") == []
+    assert tts_out.audio_deltas([np.zeros(0, np.float32)], "pcm16") == []
+    assert tts_out.audio_deltas([np.zeros(2, np.float32)], "g711_ulaw") == []  # int(2 / 3) == 0 output samples
+    with pytest.raises(ValueError):
+        tts_out.audio_deltas([np.zeros(8, np.float32)], "opus")
+    # every payload length modulo 12 (vector groups, 3-byte tail, '=' padding) against the stdlib encoder
+    rng = np.random.default_rng(5)
+    for n in list(range(1, 40)) + [3000, 3001, 6007]:
+        x = (rng.random(n, dtype=np.float32) * 2.2 - 1.1).astype(np.float32)
+        assert "".join(tts_out.audio_deltas([x], "pcm16")) == "".join(nx.realtime_deltas([x], "pcm16")), n
+    big = (rng.random(1_000_003, dtype=np.float32) * 2.0 - 1.0).astype(np.float32)  # full-size response: a checksum of the text
+    for fmt in ("pcm16", "g711_ulaw"):
+        assert tts_out.audio_deltas([big], fmt) == nx.realtime_deltas([big], fmt), fmt
