@@ -89,6 +89,30 @@ def test_effects_long_utterance_vs_oracle(gpu):
     assert np.sum(np.abs(_reverb(imp, 24000, room="medium", mix=0.5)[1:])) > 0
 
 
+@pytest.mark.parametrize("fx", [
+    [{"type": "reverb", "room": "medium"}, {"type": "podcast_eq"}],                                 # float32 in, float64 out of the chain
+    [{"type": "normalize"}, {"type": "reverb", "room": "large", "mix": 0.6}, {"type": "podcast_eq"}, {"type": "robot"}],
+    [{"type": "robot"}, {"type": "reverb", "room": "small"}, {"type": "podcast_eq"}, {"type": "normalize"}],  # float64 into the fused kernel
+    [{"type": "reverb"}, {"type": "podcast_eq"}, {"type": "reverb"}, {"type": "podcast_eq"}],
+])
+def test_reverb_eq_one_kernel_matches_two_kernels_and_oracle(gpu, fx, monkeypatch):
+    """reverb directly followed by podcast_eq runs as one kernel (k_fx_reverb_eq): same result as the two-kernel path
+    (OSB_FX_UNFUSED=1) and as the oracle, on an utterance long enough for many CTAs and on short ones."""
+    from open_speech_b200 import synth
+    from open_speech_b200.effects.chain import apply_chain
+
+    for x in (synth.tts_utterance(12.0, seed=5), synth.tts_utterance(0.2, seed=6), np.full(7, 0.3, np.float32)):
+        monkeypatch.delenv("OSB_FX_UNFUSED", raising=False)
+        fused = apply_chain(x, 24000, fx)
+        monkeypatch.setenv("OSB_FX_UNFUSED", "1")
+        split = apply_chain(x, 24000, fx)
+        monkeypatch.delenv("OSB_FX_UNFUSED", raising=False)
+        ref = otts.apply_chain(x, 24000, fx)
+        assert fused.dtype == np.float32 and fused.shape == ref.shape
+        assert _rel(fused, split) <= 1e-6, (fx, _rel(fused, split))
+        assert _rel(fused, ref) <= 1e-5, (fx, _rel(fused, ref))
+
+
 @pytest.mark.parametrize("semitones", [4, -3, 12, 0.5])
 def test_pitch_shift_vs_oracle(gpu, semitones):
     """_pitch_shift (src/effects/chain.py:44-48).  PARITY UNPINNED (librosa + soxr absent): the oracle restates librosa's
