@@ -443,6 +443,7 @@ struct EqArgs {
     double K[4][32];  // K[r][i]: state r at the end of a 32-sample segment for a unit impulse at its sample i (zero state before)
     double P[5][16];  // Phi_T^(2^k), k = 0..4 (row-major 4x4), T = 32 samples
     double Q[16];     // Phi_T^32
+    double Qp[4][16]; // Q^(2^k), k = 0..3
 };
 
 struct St4 {
@@ -562,93 +563,129 @@ __global__ void __launch_bounds__(256) k_fx_eq(const T* __restrict__ x, EqArgs a
 }
 
 // ---------------------------------------------------------------- reverb -> podcast EQ in one kernel
-// The chain [.. reverb, podcast_eq ..] exchanges float64 samples between the two recurrences; here they stay in shared
-// memory.  CTA = kEqBlock consecutive samples (EQ warm-up + outputs).  The reverb runs over the whole block from its exact
-// FIR carry-in (so the warm-up stretch holds true reverb output), the block is mixed with the dry signal in place, then the
-// biquads run over it from rest as in k_fx_eq.  Same arithmetic per sample as k_fx_reverb followed by k_fx_eq.
+// The chain [.. reverb, podcast_eq ..] exchanges float64 samples between the two recurrences; here they never leave the
+// registers.  CTA = kEqBlock consecutive samples (EQ warm-up + outputs), 512 threads, thread = one 16-sample segment.
+// The reverb runs over the whole block from its exact FIR carry-in (so the warm-up stretch holds true reverb output), is
+// mixed with the dry signal, then the biquads run from rest as in k_fx_eq.  Same arithmetic per sample as k_fx_reverb
+// followed by k_fx_eq.
 //
-// The kernel is bound by instruction issue, not by the float64 pipe (ncu: fp64 23 %, issue 56 % on the first version), so
-// everything around the recurrences is kept short: an interior block (every sample it touches, delayed ones included, lies
-// inside the utterance) skips the bounds checks; float32 input stays in registers between staging and the dry/wet mix
-// (a thread stages and mixes the same 32 samples); shared-memory addresses are compile-time offsets from one base; the
-// warp carry of the biquad scan is folded in with a table of Phi^j (16 FMA per thread) instead of a second scan; the
-// robot carrier's phase advances incrementally instead of one modulo per sample.
+// ncu on the earlier versions of this kernel (segments in shared memory; then float64 staging): float64 pipe 25 %, issue
+// 50-56 %, LSU data pipe 58-67 %, 110-136 instructions per sample of which a quarter were float64 arithmetic -- bound by
+// everything around the recurrences.  Hence:
+//  * shared memory holds only the pre-processed input as float32 (one coalesced store per sample); the segment mapping
+//    reads it twice (the sample and its delayed copy x[n-L], which lies in the same block except for the first L samples)
+//    and, after the last biquad step, receives the finished float32 sample for the coalesced store;
+//  * INTERIOR blocks (every sample they touch, delayed ones included, lies inside the utterance) carry no bounds checks;
+//  * the robot carrier and the final cast are applied in the segment mapping (carrier phase advances by one per sample);
+//  * the warp carry of the biquad scan is folded in with a table of Phi^lane instead of a second scan, and segments that
+//    lie wholly in the warm-up skip the final biquad run (their outputs are discarded).
+constexpr int kRqT = 16, kRqThreads = kEqBlock / kRqT;  // 16-sample segments, 512 threads
+constexpr int kRqStride = kRqT + 1;                     // padded segment: conflict-free in both mappings
+constexpr int kRqJ = kEqBlock / kRqThreads;             // 16 coalesced rounds per block
+constexpr int kRqRow = (kRqThreads / kRqT) * kRqStride; // coalesced mapping: sample tid + 512 j sits kRqRow * j further on
 struct EqLanePow {
     const double* tab;  // [32][16]: Phi_T^j, j = 0..31 (row-major 4x4), device memory
 };
+__device__ __forceinline__ int rq_idx(int i) { return i + (i >> 4); }  // sample i of the block -> padded shared-memory index
+// The Phi^lane table and the robot carrier are read in the segment mapping, where neighbouring lanes are 16 entries apart:
+// from global memory that is 32 sectors per load instruction (the LSU data pipe was 79 % busy with exactly this), so both
+// are copied into padded shared memory once per block.  Carriers longer than kRqMaxPeriod stay in global memory.
+constexpr int kRqMaxPeriod = 1024;
+constexpr int kRqTabDoubles = 32 * kRqStride;
 
-template <typename T, bool INTERIOR>
-__device__ __forceinline__ void rveq_stage(const T* __restrict__ p, long long base, long long n, const ReverbArgs& ra, const PreOps& po,
-                                           double* __restrict__ ub, float (&xr)[32]) {
-    // ub = u + (tid/32)*33 + (tid%32): sample i = tid + 256 j sits at ub[264 j]
-#pragma unroll
-    for (int jb = 0; jb < 32; jb += 8) {
-        T xv[8], xd[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const long long g = base + 256 * (jb + j);  // base already includes tid
-            xv[j] = (INTERIOR || (g >= 0 && g < n)) ? p[g] : (T)0;
-            xd[j] = (INTERIOR || (g - ra.L >= 0 && g - ra.L < n)) ? p[g - ra.L] : (T)0;
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const double v = fx_pre_d(xv[j], po), d = fx_pre_d(xd[j], po);
-            if (sizeof(T) == 4) xr[jb + j] = (float)v;
-            ub[264 * (jb + j)] = ra.c * (v - ra.rL * d);
-        }
-    }
-}
+struct RqShared {
+    double red[16];
+    double rsum[16];
+    St4 wsum[16];
+};
 
-template <typename T>
-__global__ void __launch_bounds__(256, 3) k_fx_reverb_eq(const T* __restrict__ x, ReverbArgs ra, EqArgs a, EqLanePow lp, FxPre pre, FxPost post,
-                                                         double* __restrict__ y) {
-    extern __shared__ __align__(16) double smd[];
-    double* u = smd;  // [256][33]
-    __shared__ double red[8];
-    __shared__ double rsum[8];
-    __shared__ St4 wsum[8];
-    const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const long long n = a.rg.lens[b];
-    const int kEqWarm = a.warm, kEqOut = kEqBlock - a.warm;
-    const long long n0 = (long long)blockIdx.x * kEqOut;
-    if (n0 >= n) return;
-    const T* p = x + a.rg.offsets[b];
+template <typename T, bool INTERIOR, int FINISH>
+__device__ __forceinline__ void rveq_block(const T* __restrict__ p, const ReverbArgs& ra, const EqArgs& a, const EqLanePow& lp, const FxPre& pre,
+                                           const FxPost& post, double* __restrict__ y, double* smd, RqShared& sh, int b, long long n,
+                                           long long n0) {
+    T* xs = reinterpret_cast<T*>(smd);          // [512][17] pre-processed input
+    float* os = reinterpret_cast<float*>(smd);  // later: finished samples (FINISH != 0)
+    double* tabs = reinterpret_cast<double*>(xs + kRqThreads * kRqStride);  // [32][17] Phi^lane
+    double* cs = tabs + kRqTabDoubles;                                      // padded robot carrier
+    const bool cs_on = post.robot && post.period <= kRqMaxPeriod;
+    double* red = sh.red;
+    double* rsum = sh.rsum;
+    St4* wsum = sh.wsum;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int kEqWarm = a.warm;
     const long long base = n0 - kEqWarm;
     const PreOps po = fx_pre_ops(pre, b, n);
-    const bool interior = base - ra.L >= 0 && base + kEqBlock <= n;
-    double* ub = u + wid * kSegStride + lane;
-    float xr[32];
-    // ---- reverb input u[i] = c (x[base+i] - r^L x[base+i-L]); zeros outside the utterance
-    if (interior) rveq_stage<T, true>(p, base + tid, n, ra, po, ub, xr);
-    else rveq_stage<T, false>(p, base + tid, n, ra, po, ub, xr);
-    // carry-in wet[base-1] = sum_k ir[k] x[base-1-k]
+    const int cidx = (tid >> 4) * kRqStride + (tid & 15);
+    tabs[(tid >> 4) * kRqStride + (tid & 15)] = lp.tab[tid];
+    if (cs_on)
+        for (int k = tid; k < post.period; k += kRqThreads) cs[rq_idx(k)] = post.carrier[k];
+    // ---- pre-processed input, coalesced: zeros outside the utterance
+    {
+        const T* pt = p + base + tid;
+#pragma unroll
+        for (int jb = 0; jb < kRqJ; jb += 8) {
+            T xv[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const long long g = base + tid + kRqThreads * (jb + j);
+                xv[j] = (INTERIOR || (g >= 0 && g < n)) ? pt[kRqThreads * (jb + j)] : (T)0;
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) xs[cidx + kRqRow * (jb + j)] = sizeof(T) == 4 ? (T)fx_pre((float)xv[j], po) : xv[j];
+        }
+    }
+    // carry-in wet[base-1] = sum_k ir[k] x[base-1-k]: eight taps' loads in flight per thread
     double part = 0.0;
     if (base > 0) {
 #pragma unroll 1
-        for (int k0 = tid; k0 < ra.L; k0 += 256 * 4) {
-            T xv[4];
-            double iv[4];
+        for (int k0 = tid; k0 < ra.L; k0 += kRqThreads * 8) {
+            T xv[8];
+            double iv[8];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int k = k0 + 256 * j;
+            for (int j = 0; j < 8; ++j) {
+                const int k = k0 + kRqThreads * j;
                 const long long g = base - 1 - k;
-                const bool ok = k < ra.L && g >= 0;
+                const bool ok = k < ra.L && (INTERIOR || g >= 0);
                 xv[j] = ok ? p[g] : (T)0;
                 iv[j] = ok ? ra.ir[k] : 0.0;
             }
 #pragma unroll
-            for (int j = 0; j < 4; ++j) part = fma(iv[j], fx_pre_d(xv[j], po), part);
+            for (int j = 0; j < 8; ++j) part = fma(iv[j], fx_pre_d(xv[j], po), part);
         }
     }
     part = warp_sum(part);
     if (lane == 0) red[wid] = part;
     __syncthreads();
-    const double carry0 = ((red[0] + red[1]) + (red[2] + red[3])) + ((red[4] + red[5]) + (red[6] + red[7]));
-    double* seg = u + tid * kSegStride;
-    {
+    double carry0 = 0.0;
+#pragma unroll
+    for (int w = 0; w < 16; ++w) carry0 += red[w];
+    // ---- segment mapping: thread = samples [16 tid, 16 tid + 16) of the block, in registers from here on
+    const int i0 = kRqT * tid;
+    double uu[kRqT];
+    {   // reverb input u = c x[n] - c r^L x[n-L]
+        const double crl = ra.c * ra.rL;
+        if (i0 >= ra.L) {  // the delayed samples are in the block
+#pragma unroll
+            for (int i = 0; i < kRqT; ++i) uu[i] = fma(-crl, (double)xs[rq_idx(i0 + i - ra.L)], ra.c * (double)xs[tid * kRqStride + i]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < kRqT; ++i) {
+                const int il = i0 + i - ra.L;
+                double d;
+                if (il >= 0) {
+                    d = (double)xs[rq_idx(il)];
+                } else {
+                    const long long g = base + il;
+                    d = (INTERIOR || (g >= 0 && g < n)) ? fx_pre_d(p[(INTERIOR || g >= 0) ? g : 0], po) : 0.0;
+                }
+                uu[i] = fma(-crl, d, ra.c * (double)xs[tid * kRqStride + i]);
+            }
+        }
+    }
+    {   // reverb: zero-state end value, warp scan with factor rT^(2^k), carry across warps, real run, dry/wet mix
         double e = 0.0;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) e = fma(ra.r, e, seg[i]);
+        for (int i = 0; i < kRqT; ++i) e = fma(ra.r, e, uu[i]);
         double f = ra.rT, v = e;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -658,7 +695,7 @@ __global__ void __launch_bounds__(256, 3) k_fx_reverb_eq(const T* __restrict__ x
         }
         if (lane == 31) rsum[wid] = v;
         __syncthreads();
-        double cw = carry0;
+        double cw = carry0;  // f == rT^32
         for (int w = 0; w < wid; ++w) cw = fma(f, cw, rsum[w]);
         double ex = __shfl_up_sync(0xffffffffu, v, 1);
         if (lane == 0) ex = 0.0;
@@ -669,44 +706,26 @@ __global__ void __launch_bounds__(256, 3) k_fx_reverb_eq(const T* __restrict__ x
         }
         double s = fma(pw, cw, ex);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-            s = fma(ra.r, s, seg[i]);
-            seg[i] = s;
-        }
-    }
-    __syncthreads();
-    // ---- mix with the dry signal in place; the reverb tail past the utterance is cut (chain.py: [:len(x)])
-#pragma unroll
-    for (int jb = 0; jb < 32; jb += 8) {
-        double xg[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            if (sizeof(T) == 4) {
-                xg[j] = (double)xr[jb + j];
-            } else {  // float64 input is not kept in registers: reload (L1/L2 hit)
-                const long long g = base + tid + 256 * (jb + j);
-                xg[j] = (interior || (g >= 0 && g < n)) ? fx_pre_d(p[g], po) : 0.0;
+        for (int i = 0; i < kRqT; ++i) {
+            s = fma(ra.r, s, uu[i]);
+            const T xi = xs[tid * kRqStride + i];
+            // (1 - mix) * samples is a float32 product while samples is still float32 (NEP 50 weak scalar)
+            const double dry = (sizeof(T) == 4) ? (double)__fmul_rn((float)(1.0 - ra.mix), (float)xi) : (1.0 - ra.mix) * (double)xi;
+            uu[i] = fma(ra.mix, s, dry);
+            if (!INTERIOR) {  // the reverb tail past the utterance is cut (chain.py: [:len(x)])
+                const long long g = base + i0 + i;
+                if (g < 0 || g >= n) uu[i] = 0.0;
             }
         }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const long long g = base + tid + 256 * (jb + j);
-            double* q = ub + 264 * (jb + j);
-            // (1 - mix) * samples is a float32 product while samples is still float32 (NEP 50 weak scalar)
-            const double dry = (sizeof(T) == 4) ? (double)__fmul_rn((float)(1.0 - ra.mix), (float)xg[j]) : (1.0 - ra.mix) * xg[j];
-            *q = (interior || (g >= 0 && g < n)) ? dry + ra.mix * *q : 0.0;
-        }
     }
-    __syncthreads();
-    // ---- biquads from rest over the block
+    // ---- biquads from rest over the block: zero-state end state of the segment (impulse-to-state table), warp scan
     St4 e{{0, 0, 0, 0}};
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-        const double xv = seg[i];
+    for (int i = 0; i < kRqT; ++i) {
 #pragma unroll
-        for (int r = 0; r < 4; ++r) e.z[r] = fma(a.K[r][i], xv, e.z[r]);
+        for (int r = 0; r < 4; ++r) e.z[r] = fma(a.K[r][i], uu[i], e.z[r]);
     }
-    St4 v = e;  // inclusive warp scan over segments: v_j = Phi^(2^k) v_{j-2^k} + v_j
+    St4 v = e;  // v_j = Phi^(2^k) v_{j-2^k} + v_j
 #pragma unroll
     for (int k = 0; k < 5; ++k) {
         St4 up;
@@ -719,52 +738,108 @@ __global__ void __launch_bounds__(256, 3) k_fx_reverb_eq(const T* __restrict__ x
         }
     }
     if (lane == 31) wsum[wid] = v;
+    __syncthreads();  // also: every thread has read its xs[] values
+    if (i0 >= kEqWarm) {  // warm-up segments are done: their outputs are discarded (warp-uniform: the warm-up is a multiple of 512)
+        // state entering this warp's first segment: every warp scans the 16 warp totals itself (lane w holds warp w; four
+        // rounds with Q^(2^k)) instead of waiting for one thread to chain them; the block starts from rest
+        St4 cw;
+        {
+            St4 t = wsum[lane & 15];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                St4 up;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) up.z[i] = __shfl_up_sync(0xffffffffu, t.z[i], 1 << k);
+                if ((lane & 15) >= (1 << k)) {
+                    const St4 m = mat4(a.Qp[k], up);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) t.z[i] += m.z[i];
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const double c = __shfl_sync(0xffffffffu, t.z[i], (wid + 15) & 15);  // inclusive total of warps 0..wid-1
+                cw.z[i] = wid == 0 ? 0.0 : c;
+            }
+        }
+        St4 s;            // state entering this segment = zero-carry prefix of the previous lanes + Phi^lane (warp carry)
+        {
+            double m[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) m[i] = tabs[lane * kRqStride + i];
+            const St4 t = mat4(m, cw);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const double pv = __shfl_up_sync(0xffffffffu, v.z[i], 1);
+                s.z[i] = t.z[i] + (lane == 0 ? 0.0 : pv);
+            }
+        }
+        const long long g0 = base + i0;  // >= n0 >= 0
+        unsigned ph = post.robot ? (unsigned)((unsigned long long)g0 % (unsigned)post.period) : 0u;
+        double* q = y + a.rg.offsets[b] + g0;
+#pragma unroll
+        for (int i = 0; i < kRqT; ++i) {
+            double o = eq_step(a, s, uu[i]);
+            if (post.robot) {
+                o *= cs_on ? cs[rq_idx((int)ph)] : post.carrier[ph];
+                ph = ph + 1 == (unsigned)post.period ? 0u : ph + 1;
+            }
+            if (FINISH == 0) {
+                if (INTERIOR || g0 + i < n) q[i] = o;
+            } else {
+                os[tid * kRqStride + i] = (float)o;
+            }
+        }
+    }
+    if (FINISH == 0) return;
     __syncthreads();
-    St4 cw{{0, 0, 0, 0}};  // state entering this warp's first segment; the block starts from rest
-    for (int w = 0; w < wid; ++w) {
-        const St4 t = mat4(a.Q, cw);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) cw.z[i] = t.z[i] + wsum[w].z[i];
+    // ---- coalesced store of the finished float32 samples
+    const long long off = fx_out_off(post, a.rg, b) + n0 + tid;
+    const int jw = kEqWarm / kRqThreads;
+    const int jn = INTERIOR ? kRqJ : (int)min((long long)kRqJ, jw + (n - n0 - tid + kRqThreads - 1) / kRqThreads);
+    for (int j = jw; j < jn; ++j) {
+        const float o = os[cidx + kRqRow * j];
+        if (FINISH == 1) reinterpret_cast<float*>(post.out)[off + kRqThreads * (j - jw)] = o;
+        else reinterpret_cast<int16_t*>(post.out)[off + kRqThreads * (j - jw)] = (int16_t)quant_pcm16(o);
     }
-    // state entering segment `lane` = (zero-carry prefix of the previous lanes) + Phi^lane cw
-    St4 s;
-    {
-        double m[16];
-        const double2* mp = reinterpret_cast<const double2*>(lp.tab + 16 * lane);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const double2 t = __ldg(mp + i);
-            m[2 * i] = t.x;
-            m[2 * i + 1] = t.y;
-        }
-        const St4 t = mat4(m, cw);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const double pv = __shfl_up_sync(0xffffffffu, v.z[i], 1);
-            s.z[i] = t.z[i] + (lane == 0 ? 0.0 : pv);
-        }
+}
+
+// one block-uniform branch picks the body: blocks in the interior of an utterance run without a single bounds check
+template <typename T, int FINISH>
+__global__ void __launch_bounds__(kRqThreads, 2) k_fx_reverb_eq(const T* __restrict__ x, ReverbArgs ra, EqArgs a, EqLanePow lp, FxPre pre,
+                                                                FxPost post, double* __restrict__ y) {
+    extern __shared__ __align__(16) double smd[];
+    __shared__ RqShared sh;
+    const int b = blockIdx.y;
+    const long long n = a.rg.lens[b];
+    const long long n0 = (long long)blockIdx.x * (kEqBlock - a.warm);
+    if (n0 >= n) return;
+    const long long base = n0 - a.warm;
+    const T* p = x + a.rg.offsets[b];
+    if (base - ra.L >= 0 && base + kEqBlock <= n) rveq_block<T, true, FINISH>(p, ra, a, lp, pre, post, y, smd, sh, b, n, n0);
+    else rveq_block<T, false, FINISH>(p, ra, a, lp, pre, post, y, smd, sh, b, n, n0);
+}
+
+template <typename T>
+static int launch_reverb_eq(dim3 grid, cudaStream_t st, const T* x, const ReverbArgs& ra, const EqArgs& e, EqLanePow lp, const FxPre& pre,
+                            const FxPost& post, double* dst) {
+    const int smem_max = kRqThreads * kRqStride * (int)sizeof(T) + (kRqTabDoubles + kRqMaxPeriod + kRqMaxPeriod / 16 + 1) * (int)sizeof(double);
+    const int smem = kRqThreads * kRqStride * (int)sizeof(T) +
+                     (kRqTabDoubles + ((post.robot && post.period <= kRqMaxPeriod) ? post.period + post.period / 16 + 1 : 0)) * (int)sizeof(double);
+    static std::once_flag once;
+    static cudaError_t err = cudaSuccess;
+    std::call_once(once, [&] {
+        auto opt = [&](auto kern) { if (err == cudaSuccess) err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max); };
+        opt(k_fx_reverb_eq<T, 0>); opt(k_fx_reverb_eq<T, 1>); opt(k_fx_reverb_eq<T, 2>);
+    });
+    OSB_CUDA(err);
+    switch (post.finish) {
+        case 0: OSB_LAUNCH((k_fx_reverb_eq<T, 0>), grid, kRqThreads, smem, st, x, ra, e, lp, pre, post, dst); break;
+        case 1: OSB_LAUNCH((k_fx_reverb_eq<T, 1>), grid, kRqThreads, smem, st, x, ra, e, lp, pre, post, dst); break;
+        default: OSB_LAUNCH((k_fx_reverb_eq<T, 2>), grid, kRqThreads, smem, st, x, ra, e, lp, pre, post, dst); break;
     }
-#pragma unroll 4
-    for (int i = 0; i < 32; ++i) seg[i] = eq_step(a, s, seg[i]);
-    __syncthreads();
-    // ---- outputs: robot carrier phase advanced incrementally (fx_st takes one modulo per sample)
-    double* q = y + a.rg.offsets[b];
-    const long long off = fx_out_off(post, a.rg, b);
-    const unsigned period = (unsigned)post.period, step = 256u % period;
-    unsigned ph = post.robot ? (unsigned)((unsigned long long)(n0 + tid) % period) : 0u;
-    const int jw = kEqWarm >> 8;  // kEqWarm is a multiple of 256 (host)
-    for (int j = jw; j < 32; ++j) {
-        const long long g = n0 + tid + 256 * (j - jw);
-        if (g < n) {
-            double v2 = ub[264 * j];
-            if (post.robot) v2 = v2 * post.carrier[ph];
-            if (post.finish == 0) q[g] = v2;
-            else if (post.finish == 1) reinterpret_cast<float*>(post.out)[off + g] = (float)v2;
-            else reinterpret_cast<int16_t*>(post.out)[off + g] = (int16_t)quant_pcm16((float)v2);
-        }
-        ph += step;
-        if (ph >= period) ph -= period;
-    }
+    OSB_CHECK_LAUNCH();
+    return OSB_OK;
 }
 
 // ---------------------------------------------------------------- voice blend
@@ -914,8 +989,6 @@ static cudaError_t fx_smem_attrs(int smem) {
         if (err == cudaSuccess) err = cudaFuncSetAttribute(k_fx_reverb<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (err == cudaSuccess) err = cudaFuncSetAttribute(k_fx_eq<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (err == cudaSuccess) err = cudaFuncSetAttribute(k_fx_eq<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (err == cudaSuccess) err = cudaFuncSetAttribute(k_fx_reverb_eq<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (err == cudaSuccess) err = cudaFuncSetAttribute(k_fx_reverb_eq<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     });
     return err;
 }
@@ -1023,8 +1096,8 @@ static int fx_normalize(FxState& s, double target_lufs, Scratch& scr, bool defer
     return OSB_OK;
 }
 
-static int eq_prepare(int sample_rate, EqArgs& a, double eps = 1e-17, int align = 32);
-static int eq_lane_pow(int sample_rate, const EqArgs& a, const double** d_tab);
+static int eq_prepare(int sample_rate, EqArgs& a, double eps = 1e-17, int align = 32, int T = 32);
+static int eq_lane_pow(int sample_rate, int T, const EqArgs& a, const double** d_tab);
 
 // with_eq: the next effect is podcast_eq and runs in the same kernel (the float64 samples between them stay on chip)
 static int fx_reverb(FxState& s, int sample_rate, int room_ms, double mix, Scratch& scr, bool with_eq = false) {
@@ -1045,18 +1118,19 @@ static int fx_reverb(FxState& s, int sample_rate, int room_ms, double mix, Scrat
     OSB_CUDA(fx_smem_attrs(smem));
     if (with_eq) {
         // The chain's result is cast to float32 (chain.py:32): a start-up transient below 1e-11 of the state is invisible, and
-        // the shorter warm-up (1792 instead of 2656 samples at 24 kHz) is recomputed by every block.  Multiple of 256 samples:
-        // thread t then owns outputs t, t + 256, ...
+        // the shorter warm-up (2048 instead of 2656 samples at 24 kHz) is recomputed by every block.  Multiple of 512 samples:
+        // thread t then owns outputs t, t + 512, ...
         EqArgs e;
-        if ((rc = eq_prepare(sample_rate, e, 1e-11, 256))) return rc;
+        if ((rc = eq_prepare(sample_rate, e, 1e-11, kRqThreads, kRqT))) return rc;
         e.rg = s.rg;
         EqLanePow lp;
-        if ((rc = eq_lane_pow(sample_rate, e, &lp.tab))) return rc;
+        if ((rc = eq_lane_pow(sample_rate, kRqT, e, &lp.tab))) return rc;
+        a.rT = std::pow(a.r, (double)kRqT);
         const int kEqOut = kEqBlock - e.warm;
         const dim3 ge((unsigned)((s.max_len + kEqOut - 1) / kEqOut), (unsigned)s.batch);
-        if (!s.f64) OSB_LAUNCH(k_fx_reverb_eq<float>, ge, 256, smem, s.st, (const float*)s.cur, a, e, lp, s.pre, s.post, dst);
-        else OSB_LAUNCH(k_fx_reverb_eq<double>, ge, 256, smem, s.st, (const double*)s.cur, a, e, lp, s.pre, s.post, dst);
-        OSB_CHECK_LAUNCH();
+        if (!s.f64) rc = launch_reverb_eq<float>(ge, s.st, (const float*)s.cur, a, e, lp, s.pre, s.post, dst);
+        else rc = launch_reverb_eq<double>(ge, s.st, (const double*)s.cur, a, e, lp, s.pre, s.post, dst);
+        if (rc) return rc;
         fx_after_recurrence(s, dst);
         return OSB_OK;
     }
@@ -1068,14 +1142,14 @@ static int fx_reverb(FxState& s, int sample_rate, int room_ms, double mix, Scrat
     return OSB_OK;
 }
 
-// Phi_T^j for j = 0..31 (T = 32 samples), cached on the device per (device, sample rate)
-static int eq_lane_pow(int sample_rate, const EqArgs& a, const double** d_tab) {
+// Phi_T^j for j = 0..31 (T-sample segments; a.P[0] = Phi_T), cached on the device per (device, sample rate, T)
+static int eq_lane_pow(int sample_rate, int T, const EqArgs& a, const double** d_tab) {
     static std::mutex mu;
     static std::map<std::pair<int, int>, double*> cache;
     int dev = 0;
     OSB_CUDA(cudaGetDevice(&dev));
     std::lock_guard<std::mutex> lk(mu);
-    auto it = cache.find({dev, sample_rate});
+    auto it = cache.find({dev * 64 + T, sample_rate});
     if (it == cache.end()) {
         std::vector<double> h(32 * 16, 0.0);
         for (int i = 0; i < 4; ++i) h[4 * i + i] = 1.0;
@@ -1083,13 +1157,14 @@ static int eq_lane_pow(int sample_rate, const EqArgs& a, const double** d_tab) {
         double* d = nullptr;
         OSB_CUDA(cudaMalloc(&d, h.size() * sizeof(double)));
         OSB_CUDA(cudaMemcpy(d, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice));
-        it = cache.emplace(std::make_pair(dev, sample_rate), d).first;
+        it = cache.emplace(std::make_pair(dev * 64 + T, sample_rate), d).first;
     }
     *d_tab = it->second;
     return OSB_OK;
 }
 
-static int eq_prepare(int sample_rate, EqArgs& a, double eps, int align) {
+// T: samples per thread segment (K, P, Q are built for it; T <= 32)
+static int eq_prepare(int sample_rate, EqArgs& a, double eps, int align, int T) {
     podcast_eq_coeffs((double)sample_rate, a);
     // warm-up must outlast the slowest pole: |p|^warm < eps
     const double rad = std::sqrt(std::fmax(a.a1[2], a.a2[2]));
@@ -1099,10 +1174,12 @@ static int eq_prepare(int sample_rate, EqArgs& a, double eps, int align) {
         return OSB_ERR_UNSUPPORTED;
     }
     a.warm = ((int)std::ceil(need) + align - 1) / align * align;
-    eq_transition(a, 32, a.P[0]);
-    for (int i = 0; i < 32; ++i) {  // impulse at sample i of a segment, then zeros to its end
+    eq_transition(a, T, a.P[0]);
+    for (int r = 0; r < 4; ++r)
+        for (int i = 0; i < 32; ++i) a.K[r][i] = 0.0;
+    for (int i = 0; i < T; ++i) {  // impulse at sample i of a segment, then zeros to its end
         double z[4] = {0, 0, 0, 0};
-        for (int t = i; t < 32; ++t) {
+        for (int t = i; t < T; ++t) {
             const double x = t == i ? 1.0 : 0.0;
             const double y1 = a.b1[0] * x + z[0];
             z[0] = a.b1[1] * x - a.a1[1] * y1 + z[1];
@@ -1115,6 +1192,8 @@ static int eq_prepare(int sample_rate, EqArgs& a, double eps, int align) {
     }
     for (int k = 1; k < 5; ++k) matmul4(a.P[k - 1], a.P[k - 1], a.P[k]);
     matmul4(a.P[4], a.P[4], a.Q);
+    memcpy(a.Qp[0], a.Q, sizeof(a.Q));
+    for (int k = 1; k < 4; ++k) matmul4(a.Qp[k - 1], a.Qp[k - 1], a.Qp[k]);
     return OSB_OK;
 }
 
