@@ -206,7 +206,7 @@ def run_gpu(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
-    numa = bind_to_gpu_numa_node(torch, local) if world > 1 else None
+    numa = bind_to_gpu_numa_node(torch, local)  # also at N=1: a process started on the far socket pins its staging buffers there
     N.require_gpu()
     N.check(N.lib().osb_init(local))
     if world > 1:
