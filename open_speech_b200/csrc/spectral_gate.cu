@@ -304,7 +304,7 @@ __global__ void __launch_bounds__(256, 2) k_nr_stft(const void* __restrict__ aud
 //   Cf'    = a^L Cf + P
 //   Cb'    = bwd[first] = a^L Cb + Cf b a (1 - a^2L)/(1 - a^2) + R
 // one thread per (row, bin); rows = (clip, chunk); coalesced across bins; f64 state.
-__global__ void __launch_bounds__(128) k_nr_carry(const float* __restrict__ A, const float2* __restrict__ PR, float* __restrict__ CF,
+__global__ void __launch_bounds__(128, 14) k_nr_carry(const float* __restrict__ A, const float2* __restrict__ PR, float* __restrict__ CF,
                                                   float* __restrict__ CB, int F, int NT, long long n_rows, double b) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= n_rows * NB) return;
@@ -319,7 +319,7 @@ __global__ void __launch_bounds__(128) k_nr_carry(const float* __restrict__ A, c
     float* cfp = CF + row * NT * NB + f;
     float* cbp = CB + row * NT * NB + f;
     double cf = (double)A[row * F * NB + f];  // lfilter_zi start: y[-1] = x[0]
-#pragma unroll 8
+#pragma unroll 4
     for (int i = 0; i < NT - 1; ++i) {
         cfp[(long long)i * NB] = (float)cf;
         cf = fma(aL, cf, (double)pr[(long long)i * NB].x);
@@ -330,7 +330,7 @@ __global__ void __launch_bounds__(128) k_nr_carry(const float* __restrict__ A, c
     double cb = cf;                                             // backward pass starts at y[F] = fwd[F-1]
     cbp[(long long)(NT - 1) * NB] = (float)cb;
     cb = fma(aLl, cb, fma(cf_last, GLl, (double)pr[(long long)(NT - 1) * NB].y));
-#pragma unroll 8
+#pragma unroll 4
     for (int i = NT - 2; i >= 0; --i) {
         cbp[(long long)i * NB] = (float)cb;
         cb = fma(aL, cb, fma((double)cfp[(long long)i * NB], GL, (double)pr[(long long)i * NB].y));
