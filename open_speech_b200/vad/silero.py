@@ -78,6 +78,56 @@ def random_init_weights(seed: int = 1002) -> dict[str, np.ndarray]:
     return w
 
 
+# silero-vad v5 (16 kHz branch) state-dict names -> WEIGHT_LAYOUT names.  The packaged TorchScript model prefixes the 16 kHz
+# branch with "_model." (the 8 kHz one with "_model_8k."); the plain nn.Module export has no prefix.
+_SILERO_KEYS = {
+    "stft.forward_basis_buffer": "stft_basis",
+    "encoder.0.reparam_conv.weight": "enc1.weight", "encoder.0.reparam_conv.bias": "enc1.bias",
+    "encoder.1.reparam_conv.weight": "enc2.weight", "encoder.1.reparam_conv.bias": "enc2.bias",
+    "encoder.2.reparam_conv.weight": "enc3.weight", "encoder.2.reparam_conv.bias": "enc3.bias",
+    "encoder.3.reparam_conv.weight": "enc4.weight", "encoder.3.reparam_conv.bias": "enc4.bias",
+    "decoder.rnn.weight_ih": "lstm.weight_ih", "decoder.rnn.weight_hh": "lstm.weight_hh",
+    "decoder.rnn.bias_ih": "lstm.bias_ih", "decoder.rnn.bias_hh": "lstm.bias_hh",
+    "decoder.decoder.2.weight": "dec.weight", "decoder.decoder.2.bias": "dec.bias",
+}
+
+
+def weights_from_state_dict(sd) -> dict[str, np.ndarray]:
+    """Silero-v5-shaped state dict (torch tensors or arrays) -> the weight dict of :class:`VadSession`.
+
+    Accepts the key names of the silero-vad package's 16 kHz branch with or without the "_model." prefix; every tensor is
+    reshaped to the layout shape (the STFT basis is stored as [258, 1, 256], the 1x1 output conv as [1, 128, 1]) and the
+    element counts must match exactly, so a model of another architecture fails loudly instead of being mis-read."""
+    shapes = dict(WEIGHT_LAYOUT)
+    out: dict[str, np.ndarray] = {}
+    for key, val in sd.items():
+        k = key[len("_model."):] if key.startswith("_model.") else key
+        name = _SILERO_KEYS.get(k)
+        if name is None:
+            continue
+        a = val.detach().cpu().numpy() if hasattr(val, "detach") else np.asarray(val)
+        if a.size != int(np.prod(shapes[name])):
+            raise ValueError(f"VAD weight {key}: {a.shape} does not fit {name} {shapes[name]}")
+        out[name] = np.ascontiguousarray(a, dtype=np.float32).reshape(shapes[name])
+    missing = [n for n, _ in WEIGHT_LAYOUT if n not in out]
+    if missing:
+        raise ValueError(f"VAD state dict lacks {missing}")
+    return out
+
+
+def load_installed_silero_weights() -> dict[str, np.ndarray] | None:
+    """Weights of the installed ``silero_vad`` package (BASELINE config 2), or None when it is absent / has another layout.
+    Nothing is downloaded: the reference fetches its ONNX file at run time (vad/silero.py:28), this never does."""
+    try:
+        import silero_vad  # type: ignore
+
+        model = silero_vad.load_silero_vad(onnx=False)
+        return weights_from_state_dict(model.state_dict())
+    except Exception as e:  # ImportError, or a package version with a different architecture
+        logger.info("silero_vad weights not used (%s): seeded random-init network instead", e)
+        return None
+
+
 def pack_weights(w: dict[str, np.ndarray]) -> np.ndarray:
     parts = []
     for name, shape in WEIGHT_LAYOUT:
@@ -225,6 +275,6 @@ async def get_vad_model() -> SileroVAD:
         return _vad_model
     async with _vad_lock:
         if _vad_model is None:
-            _vad_model = SileroVAD(VadSession())
+            _vad_model = SileroVAD(VadSession(load_installed_silero_weights()))
             logger.info("Silero VAD weights uploaded to GPU")
         return _vad_model

@@ -131,3 +131,36 @@ def test_vad_wrapper_with_scripted_session_golden(golden_vad):
     v._state = np.ones((2, 1, 128), np.float32)
     v.reset()
     assert np.all(v._state == 0)
+
+
+def test_silero_state_dict_mapping():
+    """weights_from_state_dict: the silero-vad v5 key names (with and without the TorchScript "_model." prefix), the
+    stored shapes ([258,1,256] basis, [1,128,1] output conv), the 8 kHz branch ignored, wrong architectures rejected."""
+    import torch
+
+    from open_speech_b200.vad import silero as S
+
+    ref = S.random_init_weights(7)
+    inv = {v: k for k, v in S._SILERO_KEYS.items()}
+    sd = {}
+    for name, arr in ref.items():
+        t = torch.from_numpy(arr.copy())
+        if name == "stft_basis":
+            t = t.reshape(258, 1, 256)
+        if name == "dec.weight":
+            t = t.reshape(1, 128, 1)
+        sd["_model." + inv[name]] = t
+        sd["_model_8k." + inv[name]] = torch.zeros(3)  # the other branch must not be picked up
+    got = S.weights_from_state_dict(sd)
+    assert set(got) == set(ref) and all(np.array_equal(got[k], ref[k]) for k in ref)
+    assert np.array_equal(S.pack_weights(got), S.pack_weights(ref))
+    plain = {k[len("_model."):]: v for k, v in sd.items() if k.startswith("_model.")}
+    assert all(np.array_equal(S.weights_from_state_dict(plain)[k], ref[k]) for k in ref)
+    bad = dict(sd)
+    bad["_model.decoder.rnn.weight_hh"] = torch.zeros(256, 64)
+    with pytest.raises(ValueError):
+        S.weights_from_state_dict(bad)
+    del sd["_model.encoder.2.reparam_conv.bias"]
+    with pytest.raises(ValueError):
+        S.weights_from_state_dict(sd)
+    assert S.load_installed_silero_weights() is None  # the package is not installed here: random-init path (BASELINE config 2)
