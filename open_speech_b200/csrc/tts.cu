@@ -656,9 +656,13 @@ __device__ __forceinline__ void rveq_block(const T* __restrict__ p, const Reverb
     part = warp_sum(part);
     if (lane == 0) red[wid] = part;
     __syncthreads();
-    double carry0 = 0.0;
+    double carry0;
+    {
+        double r8[8];
 #pragma unroll
-    for (int w = 0; w < 16; ++w) carry0 += red[w];
+        for (int w = 0; w < 8; ++w) r8[w] = red[2 * w] + red[2 * w + 1];
+        carry0 = ((r8[0] + r8[1]) + (r8[2] + r8[3])) + ((r8[4] + r8[5]) + (r8[6] + r8[7]));
+    }
     // ---- segment mapping: thread = samples [16 tid, 16 tid + 16) of the block, in registers from here on
     const int i0 = kRqT * tid;
     double uu[kRqT];
@@ -695,8 +699,15 @@ __device__ __forceinline__ void rveq_block(const T* __restrict__ p, const Reverb
         }
         if (lane == 31) rsum[wid] = v;
         __syncthreads();
-        double cw = carry0;  // f == rT^32
-        for (int w = 0; w < wid; ++w) cw = fma(f, cw, rsum[w]);
+        double cw = carry0;  // f == rT^32; unrolled with the loads up front: the chain is 15 FMAs, not 15 load-FMA round trips
+        {
+            double rs[15];
+#pragma unroll
+            for (int w = 0; w < 15; ++w) rs[w] = rsum[w];
+#pragma unroll
+            for (int w = 0; w < 15; ++w)
+                if (w < wid) cw = fma(f, cw, rs[w]);
+        }
         double ex = __shfl_up_sync(0xffffffffu, v, 1);
         if (lane == 0) ex = 0.0;
         double pw = 1.0, bb = ra.rT;
@@ -774,15 +785,22 @@ __device__ __forceinline__ void rveq_block(const T* __restrict__ p, const Reverb
                 s.z[i] = t.z[i] + (lane == 0 ? 0.0 : pv);
             }
         }
-        const long long g0 = base + i0;  // >= n0 >= 0
+        const long long g0 = base + i0;  // >= n0 >= 0, and a multiple of 16 (block starts and the warm-up are)
         unsigned ph = post.robot ? (unsigned)((unsigned long long)g0 % (unsigned)post.period) : 0u;
+        // period % 16 == 0 (8, 16, 24, 48 kHz): the segment's 16 carrier values are one unbroken padded row
+        const bool row16 = cs_on && (post.period & 15) == 0;
+        const double* crow = cs + rq_idx((int)ph);
         double* q = y + a.rg.offsets[b] + g0;
 #pragma unroll
         for (int i = 0; i < kRqT; ++i) {
             double o = eq_step(a, s, uu[i]);
             if (post.robot) {
-                o *= cs_on ? cs[rq_idx((int)ph)] : post.carrier[ph];
-                ph = ph + 1 == (unsigned)post.period ? 0u : ph + 1;
+                if (row16) {
+                    o *= crow[i];
+                } else {
+                    o *= cs_on ? cs[rq_idx((int)ph)] : post.carrier[ph];
+                    ph = ph + 1 == (unsigned)post.period ? 0u : ph + 1;
+                }
             }
             if (FINISH == 0) {
                 if (INTERIOR || g0 + i < n) q[i] = o;
