@@ -1,7 +1,7 @@
 """Re-entrancy: the reference calls this path from the asyncio loop thread and from 4-worker thread pools at once
 (src/streaming.py:50-52, src/realtime/server.py:33-35, src/main.py:796-813; SURVEY.md 8(b) "Threading").  Every host
 entry uses a thread-local stream and workspace, and one VAD session (weights) is shared by per-stream SileroVAD states.
-Eight threads hammer different entry points concurrently; every result must equal the single-threaded one bit for bit."""
+Nine threads hammer different entry points concurrently; every result must equal the single-threaded one bit for bit."""
 import threading
 
 import numpy as np
@@ -16,6 +16,7 @@ def test_concurrent_host_calls_are_independent(gpu):
     from open_speech_b200.effects.chain import apply_chain
     from open_speech_b200.features import B200FeatureExtractor
     from open_speech_b200.realtime.audio_buffer import decode_audio_to_pcm16
+    from open_speech_b200.realtime.tts_out import audio_deltas
     from open_speech_b200.streaming import resample_pcm16
     from open_speech_b200.vad.silero import SileroVAD, VadSession
 
@@ -35,6 +36,7 @@ def test_concurrent_host_calls_are_independent(gpu):
         "mel": lambda: fe(clip_f).tobytes(),
         "vad": lambda: repr(SileroVAD(session).get_speech_segments(clip.tobytes())),
         "fx": lambda: apply_chain(utt, 24000, fx).tobytes(),
+        "deltas": lambda: "\n".join(audio_deltas([utt[:20000], utt[20000:]], "g711_ulaw")),
         "pitch": lambda: apply_chain(utt, 24000, [{"type": "pitch", "semitones": 3}]).tobytes(),
     }
     expected = {k: f() for k, f in jobs.items()}
