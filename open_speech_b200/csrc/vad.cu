@@ -464,10 +464,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_vad_gemm_tc(GemmDesc d, const
 __device__ __forceinline__ float sigmoidf_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
 // cell non-linearities on the SFU (ex2 + rcp): absolute error ~1e-7, three decimal orders inside the 1e-3 probability
 // budget, and they sit on the serial chain of every step
-__device__ __forceinline__ float sigmoidf_fast(float x) { return __frcp_rn(1.0f + __expf(-x)); }
+// sigmoid with explicit roundings (both recurrence kernels must round alike): t = exp(-|x|), r = 1/(1+t); sigmoid(|x|) = r, sigmoid(-|x|) = t r
+__device__ __forceinline__ float sigmoidf_det(float x) {
+    const float t = __expf(-fabsf(x));
+    const float r = __frcp_rn(__fadd_rn(1.0f, t));
+    return x >= 0.f ? r : __fmul_rn(t, r);
+}
 __device__ __forceinline__ float tanhf_fast(float x) {
     const float t = __expf(-2.0f * fabsf(x));
-    return copysignf((1.0f - t) * __frcp_rn(1.0f + t), x);
+    return copysignf(__fmul_rn(__fsub_rn(1.0f, t), __frcp_rn(__fadd_rn(1.0f, t))), x);
 }
 
 constexpr int kHq = 36;  // floats between the four 32-float quarters of h in shared memory: the quarters sit in different banks
@@ -475,12 +480,14 @@ template <int S>
 struct RecurCfg {
     static constexpr int RKG = S == 1 ? 6 : (S == 2 ? 5 : 3);  // of the 8 four-column groups of a thread's block, those kept in registers
     static constexpr int SKG = 8 - RKG;
-    static constexpr int smem = (SKG * 4 * 4 * kGates + S * (4 * kHq + kGates) + kHid + 4 * S) * (int)sizeof(float);
+    // W slice | h, double-buffered | per-warp partials of the head, double-buffered
+    static constexpr int smem = (SKG * 4 * 4 * kGates + 2 * S * 4 * kHq + 2 * S * 16) * (int)sizeof(float);
 };
-__host__ __device__ inline int recur_own_row(int tid) {  // the gate row a thread holds after the shuffle reduction
-    const int q = (tid & 31) >> 3;  // column quarter = quarter-warp: the 8 lanes of a quarter-warp load the same h chunk
-    return (tid >> 5) * 32 + (tid & 7) * 4 + ((q & 1) << 1 | (q >> 1));
-}
+// Rows are dealt so that ONE WARP owns all four gates of its eight units: warp-local row r = 4 j + gate is row
+// 128 gate + 8 warp + j of W_hh (PyTorch gate order i, f, g, o).  After the shuffle reduction the four lanes (j, q = 0..3)
+// hold the four gates of unit 8 warp + j, so the cell update is three more shuffles inside the warp: no gate exchange
+// through shared memory and ONE block barrier per step (h and the head partials are double-buffered) instead of two.
+__host__ __device__ inline int recur_row(int warp, int r) { return 128 * (r & 3) + 8 * warp + (r >> 2); }
 
 // whh_perm: float4 chunk c = i*8 + kg of thread tid at [(c*512 + tid)*4], i = row of the block, kg = column group
 template <int S>
@@ -491,13 +498,159 @@ __global__ void __launch_bounds__(512, 1) k_vad_recur(const float* __restrict__ 
     constexpr int RKG = RecurCfg<S>::RKG, SKG = RecurCfg<S>::SKG;
     extern __shared__ __align__(16) float sm[];
     float4* w_sm = reinterpret_cast<float4*>(sm);                 // [4][SKG][512] float4
+    float* h_sm = sm + SKG * 4 * 4 * kGates;                      // [2][S][4 quarters x 36]
+    float* part_sm = h_sm + 2 * S * 4 * kHq;                      // [2][S][16]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, q = lane >> 3, j = lane & 7, b0 = blockIdx.x * S;
+    const int ns = min(S, batch - b0);                            // live streams of this CTA
+    const int gate = ((q & 1) << 1) | (q >> 1);                   // the gate row this lane holds after the shuffle reduction
+    const int unit = 8 * warp + j;
+    const int own = 128 * gate + unit;                            // its row in W_hh / in the gate pre-activations
+    const int upos = (unit >> 5) * kHq + (unit & 31);
+    float4 w[4][RKG];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+#pragma unroll
+        for (int kg = 0; kg < RKG; ++kg) w[i][kg] = whh_perm[(i * 8 + kg) * kGates + tid];
+#pragma unroll
+        for (int kg = RKG; kg < 8; ++kg) w_sm[(i * SKG + kg - RKG) * kGates + tid] = whh_perm[(i * 8 + kg) * kGates + tid];
+    }
+    // the q == 0 lane of a unit carries its cell state and writes its h
+    float c[S];
+    const float dw_u = dw[unit];
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+        const float* st = state + (long long)(b0 + (s < ns ? s : 0)) * 2 * kHid;
+        c[s] = s < ns ? st[kHid + unit] : 0.f;
+        if (q == 0) h_sm[s * 4 * kHq + upos] = s < ns ? st[unit] : 0.f;
+    }
+    const float* p[S];
+    float pre_v[S];
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+        p[s] = pre + (long long)(b0 + (s < ns ? s : 0)) * pre_stream_stride + own;
+        pre_v[s] = n_steps > 0 ? p[s][0] : 0.f;
+    }
+    __syncthreads();
+    for (int t = 0; t < n_steps; ++t) {
+        const float* hr = h_sm + (t & 1) * (S * 4 * kHq);          // h of the previous step
+        float* hw = h_sm + ((t + 1) & 1) * (S * 4 * kHq);          // h of this step
+        float* pw = part_sm + (t & 1) * (S * 16);
+        float pre_next[S];
+        float2 a[4][S];
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            pre_next[s] = (t + 1 < n_steps) ? p[s][(long long)(t + 1) * kGates] : 0.f;  // prefetch
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i][s] = make_float2(0.f, 0.f);
+        }
+#pragma unroll
+        for (int kg = 0; kg < 8; ++kg) {
+            float4 h4[S];
+#pragma unroll
+            for (int s = 0; s < S; ++s) h4[s] = *reinterpret_cast<const float4*>(hr + s * 4 * kHq + q * kHq + 4 * kg);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float4 w4 = kg < RKG ? w[i][kg < RKG ? kg : 0] : w_sm[(i * SKG + (kg < RKG ? 0 : kg - RKG)) * kGates + tid];
+#pragma unroll
+                for (int s = 0; s < S; ++s) {
+                    a[i][s] = __ffma2_rn(make_float2(w4.x, w4.y), make_float2(h4[s].x, h4[s].y), a[i][s]);
+                    a[i][s] = __ffma2_rn(make_float2(w4.z, w4.w), make_float2(h4[s].z, h4[s].w), a[i][s]);
+                }
+            }
+        }
+        // Phase by phase over the S streams (independent chains interleave), no divergent region: every lane runs the cell
+        // arithmetic, only the unit's q == 0 lane holds meaningful state and stores.
+        float x[S], act[S], tt[S];
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            // combine the four column quarters of a row group: two shuffle rounds, one finished gate per lane
+            const float p0 = a[0][s].x + a[0][s].y, p1 = a[1][s].x + a[1][s].y, p2 = a[2][s].x + a[2][s].y, p3 = a[3][s].x + a[3][s].y;
+            const bool hi = q & 1;
+            const float v0 = (hi ? p2 : p0) + __shfl_xor_sync(0xffffffffu, hi ? p0 : p2, 8);
+            const float v1 = (hi ? p3 : p1) + __shfl_xor_sync(0xffffffffu, hi ? p1 : p3, 8);
+            const bool hi2 = q & 2;
+            x[s] = ((hi2 ? v1 : v0) + __shfl_xor_sync(0xffffffffu, hi2 ? v0 : v1, 16)) + pre_v[s];
+        }
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            // the lane's own gate: g -> tanh, i/f/o -> sigmoid, from one exponential and one reciprocal:
+            // t = exp(-k|x|), r = 1/(1+t):  sigmoid(|x|) = r, sigmoid(-|x|) = t r (k = 1),  tanh(|x|) = (1-t) r (k = 2)
+            const float ax = fabsf(x[s]);
+            const float t = __expf(gate == 2 ? -2.0f * ax : -ax);
+            const float r = __frcp_rn(__fadd_rn(1.0f, t));
+            // (explicit roundings: every S instantiation must round alike, the packing of streams into CTAs is invisible)
+            act[s] = gate == 2 ? copysignf(__fmul_rn(__fsub_rn(1.0f, t), r), x[s]) : (x[s] >= 0.f ? r : __fmul_rn(t, r));  // sigmoid(-|x|) = t r
+        }
+        float gg[S], gf[S], go[S];
+#pragma unroll
+        for (int s = 0; s < S; ++s) {  // the unit's q == 0 lane collects g, f, o
+            gg[s] = __shfl_sync(0xffffffffu, act[s], j + 8);
+            gf[s] = __shfl_sync(0xffffffffu, act[s], j + 16);
+            go[s] = __shfl_sync(0xffffffffu, act[s], j + 24);
+        }
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            c[s] = __fmaf_rn(gf[s], c[s], __fmul_rn(act[s], gg[s]));
+            const float h = __fmul_rn(go[s], tanhf_fast(c[s]));
+            if (q == 0) hw[s * 4 * kHq + upos] = h;
+            tt[s] = q == 0 ? __fmul_rn(fmaxf(h, 0.f), dw_u) : 0.f;  // head: relu(h) . w_dec
+        }
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) {
+#pragma unroll
+            for (int s = 0; s < S; ++s) tt[s] += __shfl_xor_sync(0xffffffffu, tt[s], o);
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int s = 0; s < S; ++s) pw[s * 16 + warp] = tt[s];
+        }
+        __syncthreads();
+        if (lane == 0 && warp < ns) {  // warp s finishes stream s: sixteen partials -> sigmoid (overlaps the next step)
+            const float* ps = pw + warp * 16;
+            float sum = 0.f;
+#pragma unroll
+            for (int k = 0; k < 16; k += 4) sum += (ps[k] + ps[k + 1]) + (ps[k + 2] + ps[k + 3]);
+            probs[(long long)(b0 + warp) * probs_stride + win0 + t] = sigmoidf_acc(sum + db);
+        }
+#pragma unroll
+        for (int s = 0; s < S; ++s) pre_v[s] = pre_next[s];
+    }
+    if (q == 0) {
+        const float* hf = h_sm + (n_steps & 1) * (S * 4 * kHq);
+#pragma unroll
+        for (int s = 0; s < S; ++s)
+            if (s < ns) {
+                float* st = state + (long long)(b0 + s) * 2 * kHid;
+                st[unit] = hf[s * 4 * kHq + upos];
+                st[kHid + unit] = c[s];
+            }
+    }
+}
+
+template <int S>
+struct RecurMbCfg {
+    static constexpr int RKG = S == 1 ? 6 : (S == 2 ? 5 : 3);  // of the 8 four-column groups of a thread's block, those kept in registers
+    static constexpr int SKG = 8 - RKG;
+    static constexpr int smem = (SKG * 4 * 4 * kGates + S * (4 * kHq + kGates) + kHid + 16 * S) * (int)sizeof(float);
+};
+// The same recurrence for S >= 2 streams per CTA: there the in-warp cell update of k_vad_recur costs more than it saves (every
+// lane repeats the cell arithmetic of its unit: measured 33.7 ms against 30.5 ms on 256 streams), so the gates go through shared
+// memory to 128 S cell threads and the step takes two barriers.  Same row dealing, same whh_perm, same arithmetic.
+template <int S>
+__global__ void __launch_bounds__(512, 1) k_vad_recur_mb(const float* __restrict__ pre, long long pre_stream_stride, int n_steps,
+                                                      const float4* __restrict__ whh_perm, const float* __restrict__ dw, float db,
+                                                      float* __restrict__ state, float* __restrict__ probs, long long probs_stride,
+                                                      long long win0, int batch) {
+    constexpr int RKG = RecurMbCfg<S>::RKG, SKG = RecurMbCfg<S>::SKG;
+    extern __shared__ __align__(16) float sm[];
+    float4* w_sm = reinterpret_cast<float4*>(sm);                 // [4][SKG][512] float4
     float* h_sm = sm + SKG * 4 * 4 * kGates;                      // [S][4 quarters x 36]
     float* g_sm = h_sm + S * 4 * kHq;                             // [S][512]
     float* dw_sm = g_sm + S * kGates;                             // [128]
-    float* part_sm = dw_sm + kHid;                                // [S][4]
+    float* part_sm = dw_sm + kHid;                                // [S][16]
     const int tid = threadIdx.x, q = (tid & 31) >> 3, b0 = blockIdx.x * S;
     const int ns = min(S, batch - b0);                            // live streams of this CTA
-    const int own = recur_own_row(tid);
+    const int own = 128 * (((q & 1) << 1) | (q >> 1)) + 8 * (tid >> 5) + (tid & 7);  // row dealing of recur_row()
     float4 w[4][RKG];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -561,19 +714,26 @@ __global__ void __launch_bounds__(512, 1) k_vad_recur(const float* __restrict__ 
         }
         __syncthreads();
         if (tid < S * kHid) {
+            // same arithmetic, same roundings and the same reduction tree as k_vad_recur: which kernel scored a stream is invisible
             const float* g = g_sm + cs * kGates;
-            const float gi = g[cu], gf = g[kHid + cu], gg = g[2 * kHid + cu], go = g[3 * kHid + cu];
-            c = sigmoidf_fast(gf) * c + sigmoidf_fast(gi) * tanhf_fast(gg);
-            const float h = sigmoidf_fast(go) * tanhf_fast(c);
+            const float ai = sigmoidf_det(g[cu]), af = sigmoidf_det(g[kHid + cu]), ag = tanhf_fast(g[2 * kHid + cu]), ao = sigmoidf_det(g[3 * kHid + cu]);
+            c = __fmaf_rn(af, c, __fmul_rn(ai, ag));
+            const float h = __fmul_rn(ao, tanhf_fast(c));
             h_sm[hpos] = h;
-            // head: relu(h) . w_dec -> sigmoid ; one partial per warp, four warps per stream
-            const float part = warp_sum(fmaxf(h, 0.f) * dw_sm[cu]);
-            if ((tid & 31) == 0) part_sm[cs * 4 + (cu >> 5)] = part;
+            // head: relu(h) . w_dec -> sigmoid ; one partial per eight units, sixteen per stream
+            float part = __fmul_rn(fmaxf(h, 0.f), dw_sm[cu]);
+            part += __shfl_xor_sync(0xffffffffu, part, 1);
+            part += __shfl_xor_sync(0xffffffffu, part, 2);
+            part += __shfl_xor_sync(0xffffffffu, part, 4);
+            if ((tid & 7) == 0) part_sm[cs * 16 + (cu >> 3)] = part;
         }
         __syncthreads();
         if (cell && cu == 0) {
-            const float* ps = part_sm + cs * 4;
-            pr[t] = sigmoidf_acc(((ps[0] + ps[1]) + (ps[2] + ps[3])) + db);
+            const float* ps = part_sm + cs * 16;
+            float sum = 0.f;
+#pragma unroll
+            for (int k = 0; k < 16; k += 4) sum += (ps[k] + ps[k + 1]) + (ps[k + 2] + ps[k + 3]);
+            pr[t] = sigmoidf_acc(sum + db);
         }
 #pragma unroll
         for (int s = 0; s < S; ++s) pre_v[s] = pre_next[s];
@@ -756,8 +916,8 @@ static int vad_score(VadModel* m, const void* d_audio, int fmt, int64_t n, int64
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(once, [&] {
         attr_err = cudaFuncSetAttribute(k_vad_recur<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, RecurCfg<1>::smem);
-        if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(k_vad_recur<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, RecurCfg<2>::smem);
-        if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(k_vad_recur<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, RecurCfg<4>::smem);
+        if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(k_vad_recur_mb<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, RecurMbCfg<2>::smem);
+        if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(k_vad_recur_mb<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, RecurMbCfg<4>::smem);
     });
     OSB_CUDA(attr_err);
     // streams per recurrence CTA: as few as keep the grid within one wave of SMs
@@ -808,9 +968,9 @@ static int vad_score(VadModel* m, const void* d_audio, int fmt, int64_t n, int64
         const unsigned rg = (unsigned)((batch + rs - 1) / rs);
         if (rs == 1) OSB_LAUNCH(k_vad_recur<1>, rg, 512, RecurCfg<1>::smem, st, pre, (long long)t * kGates, t, (const float4*)m->whh_perm, m->dw, m->db,
                                 d_state, d_probs, (long long)probs_stride, w0, (int)batch);
-        else if (rs == 2) OSB_LAUNCH(k_vad_recur<2>, rg, 512, RecurCfg<2>::smem, st, pre, (long long)t * kGates, t, (const float4*)m->whh_perm, m->dw, m->db,
+        else if (rs == 2) OSB_LAUNCH(k_vad_recur_mb<2>, rg, 512, RecurMbCfg<2>::smem, st, pre, (long long)t * kGates, t, (const float4*)m->whh_perm, m->dw, m->db,
                                      d_state, d_probs, (long long)probs_stride, w0, (int)batch);
-        else OSB_LAUNCH(k_vad_recur<4>, rg, 512, RecurCfg<4>::smem, st, pre, (long long)t * kGates, t, (const float4*)m->whh_perm, m->dw, m->db,
+        else OSB_LAUNCH(k_vad_recur_mb<4>, rg, 512, RecurMbCfg<4>::smem, st, pre, (long long)t * kGates, t, (const float4*)m->whh_perm, m->dw, m->db,
                         d_state, d_probs, (long long)probs_stride, w0, (int)batch);
         OSB_CHECK_LAUNCH();
     }
@@ -870,7 +1030,7 @@ int osb_vad_create(const float* weights_host, size_t n_floats, void** handle) {
         for (int tid = 0; tid < 512; ++tid)
             for (int i = 0; i < 4; ++i)
                 for (int kg = 0; kg < 8; ++kg) {
-                    const int row = (tid >> 5) * 32 + (tid & 7) * 4 + i, col = 32 * ((tid & 31) >> 3) + 4 * kg;
+                    const int row = recur_row(tid >> 5, (tid & 7) * 4 + i), col = 32 * ((tid & 31) >> 3) + 4 * kg;
                     for (int e = 0; e < 4; ++e) perm[((size_t)(i * 8 + kg) * 512 + tid) * 4 + e] = w[oWhh + (size_t)row * 128 + col + e];
                 }
         if ((rc = upload(&m->whh_perm, perm))) {
