@@ -480,8 +480,8 @@ template <int S>
 struct RecurCfg {
     static constexpr int RKG = S == 1 ? 6 : (S == 2 ? 5 : 3);  // of the 8 four-column groups of a thread's block, those kept in registers
     static constexpr int SKG = 8 - RKG;
-    // W slice | h, double-buffered | per-warp partials of the head, double-buffered
-    static constexpr int smem = (SKG * 4 * 4 * kGates + 2 * S * 4 * kHq + 2 * S * 16) * (int)sizeof(float);
+    // W slice | h, double-buffered | per-warp partials of the head: a ring of 64 steps (row of 16 padded to 17)
+    static constexpr int smem = (SKG * 4 * 4 * kGates + 2 * S * 4 * kHq + 64 * S * 17) * (int)sizeof(float);
 };
 // Rows are dealt so that ONE WARP owns all four gates of its eight units: warp-local row r = 4 j + gate is row
 // 128 gate + 8 warp + j of W_hh (PyTorch gate order i, f, g, o).  After the shuffle reduction the four lanes (j, q = 0..3)
@@ -499,7 +499,7 @@ __global__ void __launch_bounds__(512, 1) k_vad_recur(const float* __restrict__ 
     extern __shared__ __align__(16) float sm[];
     float4* w_sm = reinterpret_cast<float4*>(sm);                 // [4][SKG][512] float4
     float* h_sm = sm + SKG * 4 * 4 * kGates;                      // [2][S][4 quarters x 36]
-    float* part_sm = h_sm + 2 * S * 4 * kHq;                      // [2][S][16]
+    float* part_sm = h_sm + 2 * S * 4 * kHq;                      // [64 steps][S][17]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, q = lane >> 3, j = lane & 7, b0 = blockIdx.x * S;
     const int ns = min(S, batch - b0);                            // live streams of this CTA
     const int gate = ((q & 1) << 1) | (q >> 1);                   // the gate row this lane holds after the shuffle reduction
@@ -534,7 +534,7 @@ __global__ void __launch_bounds__(512, 1) k_vad_recur(const float* __restrict__ 
     for (int t = 0; t < n_steps; ++t) {
         const float* hr = h_sm + (t & 1) * (S * 4 * kHq);          // h of the previous step
         float* hw = h_sm + ((t + 1) & 1) * (S * 4 * kHq);          // h of this step
-        float* pw = part_sm + (t & 1) * (S * 16);
+        float* pw = part_sm + (t & 63) * (S * 17);
         float pre_next[S];
         float2 a[4][S];
 #pragma unroll
@@ -602,15 +602,21 @@ __global__ void __launch_bounds__(512, 1) k_vad_recur(const float* __restrict__ 
         }
         if (lane == 0) {
 #pragma unroll
-            for (int s = 0; s < S; ++s) pw[s * 16 + warp] = tt[s];
+            for (int s = 0; s < S; ++s) pw[s * 17 + warp] = tt[s];
         }
         __syncthreads();
-        if (lane == 0 && warp < ns) {  // warp s finishes stream s: sixteen partials -> sigmoid (overlaps the next step)
-            const float* ps = pw + warp * 16;
-            float sum = 0.f;
+        // The head's sigmoid is off the serial chain: every 32 steps warp s turns the last 32 rows of partials of stream s into
+        // 32 probabilities, one per lane, while the other half of the ring takes the next steps (one exp per lane per 32 steps
+        // instead of a dependent exp + divide in front of every step's barrier).
+        if ((t & 31) == 31 || t == n_steps - 1) {
+            const int tb = t & ~31;  // first step of the block
+            if (warp < ns && tb + lane <= t) {
+                const float* ps = part_sm + ((tb + lane) & 63) * (S * 17) + warp * 17;
+                float sum = 0.f;
 #pragma unroll
-            for (int k = 0; k < 16; k += 4) sum += (ps[k] + ps[k + 1]) + (ps[k + 2] + ps[k + 3]);
-            probs[(long long)(b0 + warp) * probs_stride + win0 + t] = sigmoidf_acc(sum + db);
+                for (int k = 0; k < 16; k += 4) sum += (ps[k] + ps[k + 1]) + (ps[k + 2] + ps[k + 3]);
+                probs[(long long)(b0 + warp) * probs_stride + win0 + tb + lane] = sigmoidf_acc(sum + db);
+            }
         }
 #pragma unroll
         for (int s = 0; s < S; ++s) pre_v[s] = pre_next[s];
@@ -631,7 +637,7 @@ template <int S>
 struct RecurMbCfg {
     static constexpr int RKG = S == 1 ? 6 : (S == 2 ? 5 : 3);  // of the 8 four-column groups of a thread's block, those kept in registers
     static constexpr int SKG = 8 - RKG;
-    static constexpr int smem = (SKG * 4 * 4 * kGates + S * (4 * kHq + kGates) + kHid + 16 * S) * (int)sizeof(float);
+    static constexpr int smem = (SKG * 4 * 4 * kGates + S * (4 * kHq + kGates) + kHid + 64 * S * 17) * (int)sizeof(float);
 };
 // The same recurrence for S >= 2 streams per CTA: there the in-warp cell update of k_vad_recur costs more than it saves (every
 // lane repeats the cell arithmetic of its unit: measured 33.7 ms against 30.5 ms on 256 streams), so the gates go through shared
@@ -647,7 +653,7 @@ __global__ void __launch_bounds__(512, 1) k_vad_recur_mb(const float* __restrict
     float* h_sm = sm + SKG * 4 * 4 * kGates;                      // [S][4 quarters x 36]
     float* g_sm = h_sm + S * 4 * kHq;                             // [S][512]
     float* dw_sm = g_sm + S * kGates;                             // [128]
-    float* part_sm = dw_sm + kHid;                                // [S][16]
+    float* part_sm = dw_sm + kHid;                                // [64 steps][S][17]: ring of head partials
     const int tid = threadIdx.x, q = (tid & 31) >> 3, b0 = blockIdx.x * S;
     const int ns = min(S, batch - b0);                            // live streams of this CTA
     const int own = 128 * (((q & 1) << 1) | (q >> 1)) + 8 * (tid >> 5) + (tid & 7);  // row dealing of recur_row()
@@ -725,15 +731,18 @@ __global__ void __launch_bounds__(512, 1) k_vad_recur_mb(const float* __restrict
             part += __shfl_xor_sync(0xffffffffu, part, 1);
             part += __shfl_xor_sync(0xffffffffu, part, 2);
             part += __shfl_xor_sync(0xffffffffu, part, 4);
-            if ((tid & 7) == 0) part_sm[cs * 16 + (cu >> 3)] = part;
+            if ((tid & 7) == 0) part_sm[(t & 63) * (S * 17) + cs * 17 + (cu >> 3)] = part;
         }
         __syncthreads();
-        if (cell && cu == 0) {
-            const float* ps = part_sm + cs * 16;
-            float sum = 0.f;
+        if (((t & 31) == 31 || t == n_steps - 1) && cell && cu < 32) {  // as in k_vad_recur: 32 probabilities per 32 steps, one per lane
+            const int tb = t & ~31;
+            if (tb + cu <= t) {
+                const float* ps = part_sm + ((tb + cu) & 63) * (S * 17) + cs * 17;
+                float sum = 0.f;
 #pragma unroll
-            for (int k = 0; k < 16; k += 4) sum += (ps[k] + ps[k + 1]) + (ps[k + 2] + ps[k + 3]);
-            pr[t] = sigmoidf_acc(sum + db);
+                for (int k = 0; k < 16; k += 4) sum += (ps[k] + ps[k + 1]) + (ps[k + 2] + ps[k + 3]);
+                pr[tb + cu] = sigmoidf_acc(sum + db);
+            }
         }
 #pragma unroll
         for (int s = 0; s < S; ++s) pre_v[s] = pre_next[s];
