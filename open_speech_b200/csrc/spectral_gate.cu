@@ -392,9 +392,12 @@ __global__ void __launch_bounds__(kMaskThreads, 2) k_nr_mask(const float* __rest
     const long long row = blockIdx.y, base = row * F * NB;
     const int t1 = min(t0 + kSmT - 1, F - 1);  // last frame of the tile: a carry boundary or the last frame
     // zero the row pads; the 513 bins of every row are written by the column phase
-    for (int i = tid; i < kSmT * (W - NB); i += kMaskThreads) {
-        const int r = i / (W - NB), c = i - r * (W - NB);
-        tile[at(r, c < kSmPad ? c : c + NB)] = 0.f;
+    // (one warp per row, a lane per pad entry: no division; W - NB - kSmPad <= 39 entries behind the bins)
+    for (int r = tid >> 5; r < kSmT; r += kMaskThreads / 32) {
+        const int l = tid & 31;
+        tile[at(r, l)] = 0.f;
+        if (kSmPad + NB + l < W) tile[at(r, kSmPad + NB + l)] = 0.f;
+        if (kSmPad + NB + 32 + l < W) tile[at(r, kSmPad + NB + 32 + l)] = 0.f;
     }
     // inside a tile the recurrences run in f32: 38 steps from an f64-chained state lose ~1e-7 relative
     const float b = (float)bd, a = (float)(1.0 - bd), ia = (float)(1.0 / (1.0 - bd));
