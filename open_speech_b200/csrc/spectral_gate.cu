@@ -123,8 +123,12 @@ __device__ __forceinline__ bool nr_stft_interior(const void* audio, const NrGeom
 
 // Persistent: 2 CTAs per SM walk the (clip, chunk, tile) list; the window / twiddle tables are fetched once per CTA and
 // the raw int16 samples of the CTA's next tile arrive by cp.async.bulk (mbarrier) while the current tile is transformed.
+struct NrAgg {
+    double bb[kStftFrames];  // b^2 a^k: weight of u[k] in the tile's backward aggregate R
+};
 __global__ void __launch_bounds__(256, 2) k_nr_stft(const void* __restrict__ audio, NrGeom g, const float* __restrict__ tabs,
-                                                    float2* __restrict__ S, float* __restrict__ A, float2* __restrict__ PR, double b, int NT) {
+                                                    float2* __restrict__ S, float* __restrict__ A, float2* __restrict__ PR, double b, int NT,
+                                                    NrAgg ag) {
     extern __shared__ __align__(16) float sm[];
     float* xs = sm;                 // [4864]
     float* win = xs + kStftXs;      // [1024]
@@ -281,11 +285,24 @@ __global__ void __launch_bounds__(256, 2) k_nr_stft(const void* __restrict__ aud
         const int L = min(kStftFrames, g.F - t0);
         const double a = 1.0 - b;
         for (int f = tid; f < NB; f += 256) {
-            double lf = 0.0, R = 0.0, bpw = b;
-            for (int k = 0; k < L; ++k) {
-                lf = fma(a, lf, b * (double)Y[k * kYPlane + f]);
-                R = fma(bpw, lf, R);
-                bpw *= a;
+            double lf = 0.0, R = 0.0;
+            if (L == kStftFrames) {
+                // full tile, unrolled, the gain b taken out of the recurrence: u[k] = a u[k-1] + y[k], lf = b u, and
+                // R = sum_k (b^2 a^k) u[k] with the weights as kernel constants: two FMAs per frame
+                double u = 0.0;
+#pragma unroll
+                for (int k = 0; k < kStftFrames; ++k) {
+                    u = fma(a, u, (double)Y[k * kYPlane + f]);
+                    R = fma(ag.bb[k], u, R);
+                }
+                lf = b * u;
+            } else {
+                double bpw = b;
+                for (int k = 0; k < L; ++k) {
+                    lf = fma(a, lf, b * (double)Y[k * kYPlane + f]);
+                    R = fma(bpw, lf, R);
+                    bpw *= a;
+                }
             }
             PR[((row0 / g.F) * NT + tx) * NB + f] = make_float2((float)lf, (float)R);
         }
@@ -601,6 +618,8 @@ __global__ void __launch_bounds__(256, 2) k_nr_istft(const float2* __restrict__ 
     for (int j = 0; j < 4; ++j) wreg[j] = win[tid + 256 * j];
     float* yr = Y + q * 2 * kYPlane;
     float* yi = yr + kYPlane;
+    const float oscv = osc[tid];
+    for (int i = tid; i < kOlaOut; i += 256) acc[i] = 0.f;
     const long long total_tiles = (long long)tiles_per_chunk * g.n_chunks * g.batch;
     for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
     const int clip = (int)(tile / ((long long)tiles_per_chunk * g.n_chunks));
@@ -610,7 +629,7 @@ __global__ void __launch_bounds__(256, 2) k_nr_istft(const float2* __restrict__ 
     const long long keep = (g.n_chunks == 1) ? g.n : ((g.n - (long long)chunk * kChunk) < kChunk ? (g.n - (long long)chunk * kChunk) : kChunk);
     if ((long long)NH * j0 >= kCtx + keep) continue;  // tile past the kept centre of a short last chunk
     const int TL = nr_tlim(g, chunk);
-    for (int i = tid; i < kOlaOut; i += 256) acc[i] = 0.f;  // a thread only ever touches acc[u], u == tid (mod 256)
+    // (acc is zero here: zeroed once before the tile loop, and every tile leaves it zeroed when it stores)
     const long long row0 = ((long long)clip * g.n_chunks + chunk) * g.F;
     // Each warp owns one frame pair and its two planes through both FFT steps (warp-level barriers only);
     // the CTA only meets for the overlap-add.
@@ -702,13 +721,21 @@ __global__ void __launch_bounds__(256, 2) k_nr_istft(const float2* __restrict__ 
     // store the kept centre [kCtx, kCtx + keep) of the chunk; optionally add its energy to the clip's sum of squares
     // (np.square in float32, summed wide: what normalize_gain needs next)
     double ss = 0.0;
-    for (int u = tid; u < kOlaOut; u += 256) {
-        const long long p = (long long)NH * j0 + u;
-        const long long rel = p - kCtx;
-        if (rel < 0 || rel >= keep) continue;
-        const float v = acc[u] * osc[u & 255];
-        out[(long long)clip * g.stride + (long long)chunk * kChunk + rel] = v;
-        ss += (double)__fmul_rn(v, v);
+    {
+        // a thread only ever touches acc[u], u == tid (mod 256): its overlap-add scale is one value, the range check one
+        // unsigned compare, and the accumulator is handed back zeroed for the next tile
+        const long long rel0 = (long long)NH * j0 - kCtx + tid;
+        float* ob = out + (long long)clip * g.stride + (long long)chunk * kChunk + rel0;
+#pragma unroll 1
+        for (int k = 0; k < kOlaBlocks; ++k) {
+            const float av = acc[256 * k + tid];
+            acc[256 * k + tid] = 0.f;
+            if ((unsigned long long)(rel0 + 256 * k) < (unsigned long long)keep) {
+                const float v = av * oscv;
+                ob[256 * k] = v;
+                ss += (double)__fmul_rn(v, v);
+            }
+        }
     }
     if (sumsq) {
         ss = warp_sum(ss);
@@ -799,8 +826,10 @@ int launch_spectral_gate(const void* d_audio, int fmt, long long n, long long ba
         {
             const long long total_tiles = (long long)NT * g.n_chunks * gb;
             const long long persistent = 2ll * num_sms();  // 2 resident CTAs per SM (109 KB of shared memory each)
+            NrAgg ag;
+            for (int k = 0; k < kStftFrames; ++k) ag.bb[k] = b * b * std::pow(1.0 - b, (double)k);
             OSB_LAUNCH(k_nr_stft, (unsigned)(total_tiles < persistent ? total_tiles : persistent), 256, kStftSmem, st, (const void*)in, g, tabs,
-                       S, A, PR, b, NT);
+                       S, A, PR, b, NT, ag);
         }
         OSB_CHECK_LAUNCH();
         OSB_LAUNCH(k_nr_carry, (unsigned)((n_rows * NB + 127) / 128), 128, 0, st, A, PR, CF, CB, g.F, NT, n_rows, b);
