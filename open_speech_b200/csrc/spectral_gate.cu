@@ -726,7 +726,7 @@ __global__ void __launch_bounds__(256, 2) k_nr_istft(const float2* __restrict__ 
         // unsigned compare, and the accumulator is handed back zeroed for the next tile
         const long long rel0 = (long long)NH * j0 - kCtx + tid;
         float* ob = out + (long long)clip * g.stride + (long long)chunk * kChunk + rel0;
-#pragma unroll 1
+#pragma unroll
         for (int k = 0; k < kOlaBlocks; ++k) {
             const float av = acc[256 * k + tid];
             acc[256 * k + tid] = 0.f;
