@@ -140,11 +140,14 @@ __global__ void __launch_bounds__(256, 2) k_nr_stft(const void* __restrict__ aud
     const int tid = threadIdx.x;
     const long long total_tiles = (long long)NT * g.n_chunks * g.batch;
     // tile -> (clip, chunk, t0); wants_tma: the tile is transformed (not all-zero) and its samples are one aligned run
+    // (32-bit: the host caps a group at 2^31 tiles; a 64-bit division here costs ~100 instructions, three times per tile)
+    const unsigned per_clip_tiles = (unsigned)NT * (unsigned)g.n_chunks;
     auto decode = [&](long long tile, int& clip, int& chunk, int& t0) {
-        clip = (int)(tile / ((long long)NT * g.n_chunks));
-        const int rem = (int)(tile - (long long)clip * NT * g.n_chunks);
-        chunk = rem / NT;
-        t0 = (rem - chunk * NT) * kStftFrames;
+        const unsigned tl = (unsigned)tile;
+        clip = (int)(tl / per_clip_tiles);
+        const unsigned rem = tl - (unsigned)clip * per_clip_tiles;
+        chunk = (int)(rem / (unsigned)NT);
+        t0 = (int)(rem - (unsigned)chunk * (unsigned)NT) * kStftFrames;
     };
     auto wants_tma = [&](long long tile, const int16_t** src) {
         if (tile >= total_tiles) return false;
@@ -622,8 +625,9 @@ __global__ void __launch_bounds__(256, 2) k_nr_istft(const float2* __restrict__ 
     for (int i = tid; i < kOlaOut; i += 256) acc[i] = 0.f;
     const long long total_tiles = (long long)tiles_per_chunk * g.n_chunks * g.batch;
     for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-    const int clip = (int)(tile / ((long long)tiles_per_chunk * g.n_chunks));
-    const int rem = (int)(tile - (long long)clip * tiles_per_chunk * g.n_chunks);
+    const unsigned per_clip_tiles = (unsigned)tiles_per_chunk * (unsigned)g.n_chunks;  // 32-bit decode (< 2^31 tiles per group)
+    const int clip = (int)((unsigned)tile / per_clip_tiles);
+    const int rem = (int)((unsigned)tile - (unsigned)clip * per_clip_tiles);
     const int chunk = rem / tiles_per_chunk;
     const int j0 = j_first + (rem - chunk * tiles_per_chunk) * kOlaBlocks;
     const long long keep = (g.n_chunks == 1) ? g.n : ((g.n - (long long)chunk * kChunk) < kChunk ? (g.n - (long long)chunk * kChunk) : kChunk);
