@@ -205,6 +205,7 @@ def run_gpu(args) -> None:
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    N.require_gpu()  # no device: RuntimeError here, there is nothing to fall back to
     torch.cuda.set_device(local)
     numa = bind_to_gpu_numa_node(torch, local)  # also at N=1: a process started on the far socket pins its staging buffers there
     N.require_gpu()
