@@ -159,6 +159,23 @@ int osb_stt_frontend_dev(const int16_t* d_pcm, int64_t n, int64_t batch, int64_t
 int osb_stt_frontend_host(const int16_t* pcm, int64_t n, int64_t batch, int64_t stride, int sample_rate, int noise_reduce,
                           int normalize, int n_mels, float* mel);
 
+/* osb_stt_full_*: the north_star chain as ONE call, no host hop between stages -- wire audio [batch][n_in] (PCM16 | ULAW | ALAW at
+ * from_rate) -> decode_audio_to_pcm16 / resample_pcm16 to 16 kHz -> { SileroVAD.get_speech_segments | preprocess_stt_audio -> log-mel }.
+ *   Reference chain: src/realtime/server.py:127-170 -> audio_buffer.py:37-58 -> :111-154 -> src/vad/silero.py:63-177, and
+ *   src/main.py:295-296 -> src/audio/preprocessing.py:53-63 -> src/backends/faster_whisper.py:245.  Both branches read the resampled pcm16.
+ *   linear_chunk = 0: whole-clip polyphase resample (resample_pcm16, as the Wyoming and streaming doors do);
+ *   linear_chunk = k: the realtime door, every k input samples are one append() and are resampled on their own with np.interp arithmetic
+ *   (k must divide n_in).  n16 = osb_stt_full_samples(n_in, from_rate, linear_chunk) samples per clip at 16 kHz.
+ *   Outputs (each may be NULL to skip): d_pcm16k [batch][n16]; d_probs [batch][n16/512] (fresh LSTM state per clip); d_segments
+ *   [batch][max_seg][2] + d_counts [batch]; d_mel [batch][n_mels][osb_logmel_frames(n16)].  vad = NULL skips the VAD branch. */
+int64_t osb_stt_full_samples(int64_t n_in, int from_rate, int linear_chunk);
+int osb_stt_full_dev(void* vad, const void* d_in, int in_fmt, int from_rate, int64_t n_in, int64_t batch, int64_t in_stride, int linear_chunk,
+                     int noise_reduce, int normalize, int n_mels, float vad_threshold, int min_speech_ms, int silence_ms, int16_t* d_pcm16k,
+                     float* d_probs, int32_t* d_segments, int32_t* d_counts, int max_seg, float* d_mel, void* stream);
+int osb_stt_full_host(void* vad, const void* in, int in_fmt, int from_rate, int64_t n_in, int64_t batch, int linear_chunk, int noise_reduce,
+                      int normalize, int n_mels, float vad_threshold, int min_speech_ms, int silence_ms, float* probs, int32_t* segments,
+                      int32_t* counts, int max_seg, float* mel);
+
 /* ---------------------------------------------------------------- TTS post-processing, effects, voice blend
  * Ragged batches: utterance b = flat[d_offsets[b] : d_offsets[b] + d_lens[b]] (int64 arrays on the device).
  * osb_tts_post = process_tts_chunks after concatenation: trim_silence (|x| > threshold, first..last) then
@@ -226,6 +243,57 @@ int osb_interp_index_f32_host(const float* in, int64_t n, float* out, int64_t m)
 int osb_f32_to_pcm16_rt_dev(const float* d_in, int16_t* d_out, size_t n, void* stream);
 int osb_base64_encode_dev(const uint8_t* d_in, size_t n, char* d_out, void* stream);
 int osb_realtime_tts_encode_host(const float* audio, int64_t n, int out_fmt, int64_t n_out, uint8_t* payload, char* b64);
+
+/* ---------------------------------------------------------------- batched realtime gates (device-resident per-stream state)
+ * osb_gate_tick_dev = for each of n_streams concurrent streams, one decode_audio_to_pcm16 (src/realtime/audio_buffer.py:37-58; poly=1:
+ *   audioop + resample_pcm16, src/streaming.py:55-91) followed by one InputAudioBuffer.append (src/realtime/audio_buffer.py:111-156):
+ *   the chunk is resampled into d_pcm [S][n_out] (n_out computed by the caller like the reference: int(n_in * (16000 / from_rate)) for
+ *   the linear path, ceil(n_in*up/down) for the polyphase path), appended to the stream's arena slice (d_arena [S][arena_stride], may be
+ *   NULL), scored (max over the chunk's full 512-sample windows, 0.0 when there is none; d_vad_state [S][2][128] carried), and the
+ *   integer start / stop machine advances.  gated=0 is `vad=None`: buffer and clock only.  d_prob_override [S] (may be NULL) replaces the
+ *   VAD's value for the chunk (scripted tests, external VADs).  Events of the tick: d_events [max_events][3] = (stream, OSB_EVT_*, ms) in
+ *   stream order, *d_event_count = how many there were.  OSB_EVT_FRAME_TOO_LARGE / OSB_EVT_BUFFER_FULL are the two BufferError cases
+ *   (:118-122) against arena_stride; the stream's state is then left as the reference leaves it.
+ *   d_work: osb_gate_work_bytes(n_streams) bytes, zeroed once by the caller, private to the gate.
+ * osb_gate_clear_dev = InputAudioBuffer.clear() / the clearing half of commit() (:106-109, :158-162) for the listed streams.
+ * osb_stream_tick_dev = StreamingSession._process_chunk (src/streaming.py:290-355) for n_streams sessions: polyphase resample of the
+ *   client-rate chunk, VAD, and the utterance machine including the state half of _transcribe_utterance / _finalize_utterance
+ *   (:357-360, :429-436, :493-498).  d_actions [S]: OSB_ACT_* bits telling the host what the reference would do next for that session. */
+typedef struct osb_gate_state {
+    int64_t total_samples, silence_samples, buffered_samples;
+    int32_t in_speech, speech_start_ms;
+} osb_gate_state;
+typedef struct osb_stream_state {
+    int64_t silence_samples, utterance_bytes;
+    int32_t speech_active, reserved;
+} osb_stream_state;
+#define OSB_EVT_SPEECH_STARTED 1
+#define OSB_EVT_SPEECH_STOPPED 2
+#define OSB_EVT_FRAME_TOO_LARGE 3
+#define OSB_EVT_BUFFER_FULL 4
+#define OSB_ACT_SPEECH_START 1     /* send {"type": "vad", "state": "speech_start"} */
+#define OSB_ACT_UTTERANCE_RESET 2  /* utterance_audio = bytearray(); agreement.reset() before appending */
+#define OSB_ACT_APPEND 4           /* utterance_audio.extend(chunk_16k) */
+#define OSB_ACT_TRANSCRIBE 8       /* _transcribe_utterance() runs (>= 3200 bytes) */
+#define OSB_ACT_FINALIZE 16        /* _finalize_utterance() transcribes and resets the utterance */
+#define OSB_ACT_SPEECH_END 32      /* send {"type": "vad", "state": "speech_end"} */
+int64_t osb_gate_work_bytes(int64_t n_streams);
+int osb_gate_tick_dev(void* vad, const void* d_in, int in_fmt, int64_t n_in, int from_rate, int poly, int64_t n_streams, int64_t in_stride,
+                      int16_t* d_pcm, int64_t n_out, osb_gate_state* d_state, float* d_vad_state, const float* d_prob_override, int gated,
+                      int16_t* d_arena, int64_t arena_stride, float threshold, int silence_duration_ms, int32_t* d_work, int32_t* d_events,
+                      int32_t* d_event_count, int max_events, void* stream);
+int osb_gate_clear_dev(osb_gate_state* d_state, const int32_t* d_stream_ids, int n, void* stream);
+int osb_stream_tick_dev(void* vad, const int16_t* d_in, int64_t n_in, int from_rate, int64_t n_streams, int64_t in_stride, int16_t* d_pcm,
+                        int64_t n_out, osb_stream_state* d_state, float* d_vad_state, const float* d_prob_override, int vad_enabled,
+                        float threshold, int64_t endpointing_samples, int64_t max_utterance_bytes, int32_t* d_actions, void* stream);
+/* per-stream host entries behind the drop-in classes (state lives in the caller's object, like the reference's):
+ * osb_gate_append_host = one InputAudioBuffer.append(pcm16 @16 kHz); event[0] = OSB_EVT_* or 0, event[1] = its ms.
+ * osb_stream_chunk_host = one StreamingSession._process_chunk(client-rate chunk); out16k receives resample_pcm16(chunk) (n_out samples). */
+int osb_gate_append_host(void* vad, const int16_t* pcm, int64_t n, osb_gate_state* state, float* vad_state, int gated, float threshold,
+                         int silence_duration_ms, int32_t* event);
+int osb_stream_chunk_host(void* vad, const int16_t* pcm, int64_t n_in, int from_rate, int16_t* out16k, int64_t n_out, osb_stream_state* state,
+                          float* vad_state, int vad_enabled, float threshold, int64_t endpointing_samples, int64_t max_utterance_bytes,
+                          int32_t* actions);
 
 #ifdef __cplusplus
 }

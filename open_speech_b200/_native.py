@@ -22,7 +22,7 @@ _CTYPES = {
     "int": ctypes.c_int, "float": ctypes.c_float, "double": ctypes.c_double, "size_t": ctypes.c_size_t,
     "int64_t": ctypes.c_int64, "uint64_t": ctypes.c_uint64, "int32_t": ctypes.c_int32, "void": None,
 }
-_DECL = re.compile(r"^\s*(const\s+char\s*\*|uint64_t|int|void)\s+(osb_\w+)\s*\(([^;{]*)\)\s*;", re.M | re.S)
+_DECL = re.compile(r"^\s*(const\s+char\s*\*|uint64_t|int64_t|int|void)\s+(osb_\w+)\s*\(([^;{]*)\)\s*;", re.M | re.S)
 
 
 def parse_header(path: str = HEADER) -> dict[str, tuple[object, list[object]]]:

@@ -14,7 +14,12 @@ def _post(audio: np.ndarray, trim: bool, normalize: bool, threshold: float, peak
     out = np.empty_like(a)
     m = ctypes.c_int64(0)
     N.call("osb_tts_post_host", N.ptr(a), a.size, int(trim), int(normalize), float(threshold), float(peak), N.ptr(out), ctypes.byref(m))
-    return out[: m.value]
+    out = out[: m.value]
+    # the kernels compute in float32; a float64 caller gets its dtype back like the reference's numpy expressions would give
+    # (values carry float32 precision: INTEGRATION.md, deviations)
+    if isinstance(audio, np.ndarray) and audio.dtype != np.float32 and np.issubdtype(audio.dtype, np.floating):
+        out = out.astype(audio.dtype)
+    return out
 
 
 def trim_silence(audio: np.ndarray, threshold: float = 0.01) -> np.ndarray:

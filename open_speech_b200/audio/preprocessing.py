@@ -63,7 +63,11 @@ def normalize_gain(audio: np.ndarray, target_dbfs: float = -18.0) -> np.ndarray:
     out = np.empty_like(a)
     unchanged = ctypes.c_int(0)
     N.call("osb_normalize_gain_f32_host", N.ptr(a), N.ptr(out), 0, a.size, 1, float(target_dbfs), ctypes.byref(unchanged))
-    return audio if unchanged.value else out
+    if unchanged.value:
+        return audio
+    if isinstance(audio, np.ndarray) and audio.dtype != np.float32 and np.issubdtype(audio.dtype, np.floating):
+        out = out.astype(audio.dtype)  # float32 arithmetic, the caller's dtype (deviations)
+    return out
 
 
 def reduce_noise(audio: np.ndarray, sample_rate: int) -> np.ndarray:

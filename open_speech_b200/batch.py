@@ -48,6 +48,66 @@ class SttFrontEnd:
         return mel_host
 
 
+class SttFull:
+    """The whole STT front-end as one device-resident call (north_star chain): wire audio [B, n_in] (pcm16 | G.711 at
+    ``from_rate``) -> 16 kHz -> { VAD probabilities + segments | [spectral gate] -> [normalise] -> requantise -> log-mel }.
+
+    ``linear_chunk`` = 0: whole-clip polyphase resample (resample_pcm16); k > 0: every k input samples are resampled on
+    their own with np.interp arithmetic, as the realtime door does per append.  Results stay on the device.
+    """
+
+    def __init__(self, session=None, fmt: str = "g711_ulaw", from_rate: int = 8000, linear_chunk: int = 0, n_mels: int = 128,
+                 noise_reduce: bool = True, normalize: bool = True, threshold: float = 0.5, min_speech_ms: int = 250, silence_ms: int = 800,
+                 keep_pcm: bool = False):
+        N.require_gpu()
+        self.session = session
+        self.fmt = {"g711_ulaw": N.FMT_ULAW, "g711_alaw": N.FMT_ALAW, "pcm16": N.FMT_PCM16}[fmt]
+        self.in_dtype = torch.int16 if self.fmt == N.FMT_PCM16 else torch.uint8
+        self.from_rate, self.linear_chunk, self.n_mels = from_rate, linear_chunk, n_mels
+        self.noise_reduce, self.normalize = bool(noise_reduce), bool(normalize)
+        self.threshold, self.min_speech_ms, self.silence_ms, self.keep_pcm = threshold, min_speech_ms, silence_ms, keep_pcm
+        self._bufs = {}
+
+    def samples_16k(self, n_in: int) -> int:
+        return int(N.lib().osb_stt_full_samples(n_in, self.from_rate, self.linear_chunk))
+
+    def buffers(self, batch: int, n_in: int, device) -> dict:
+        key = (batch, n_in, str(device))
+        if key not in self._bufs:
+            n16 = self.samples_16k(n_in)
+            n_win, max_seg = n16 // 512, n16 // 512 // 2 + 2
+            b = {"n16": n16, "n_win": n_win, "max_seg": max_seg,
+                 "mel": torch.empty((batch, self.n_mels, N.lib().osb_logmel_frames(n16)), dtype=torch.float32, device=device),
+                 "probs": torch.empty((batch, max(n_win, 1)), dtype=torch.float32, device=device),
+                 "segments": torch.empty((batch, max_seg, 2), dtype=torch.int32, device=device),
+                 "counts": torch.zeros((batch,), dtype=torch.int32, device=device),
+                 "pcm16k": torch.empty((batch, n16), dtype=torch.int16, device=device) if self.keep_pcm else None}
+            self._bufs[key] = b
+        return self._bufs[key]
+
+    def __call__(self, wire: torch.Tensor) -> dict:
+        if wire.dtype != self.in_dtype or not wire.is_cuda or wire.dim() != 2 or not wire.is_contiguous():
+            raise ValueError("wire must be a contiguous CUDA tensor [batch, samples] of the wire dtype")
+        batch, n_in = wire.shape
+        b = self.buffers(batch, n_in, wire.device)
+        vad = self.session.handle if self.session is not None else None
+        N.call("osb_stt_full_dev", vad, wire.data_ptr(), self.fmt, self.from_rate, n_in, batch, n_in, self.linear_chunk, int(self.noise_reduce),
+               int(self.normalize), self.n_mels, float(self.threshold), self.min_speech_ms, self.silence_ms,
+               b["pcm16k"].data_ptr() if b["pcm16k"] is not None else None, b["probs"].data_ptr() if vad else None,
+               b["segments"].data_ptr() if vad else None, b["counts"].data_ptr() if vad else None, b["max_seg"], b["mel"].data_ptr(), _stream())
+        return b
+
+    def run_host(self, wire_host, out: dict) -> dict:
+        """End to end with HOST buffers: numpy / pinned torch rows in, results into the caller's host arrays
+        (out: probs [B, n_win] f32, segments [B, max_seg, 2] i32, counts [B] i32, mel [B, n_mels, frames] f32)."""
+        batch, n_in = wire_host.shape
+        vad = self.session.handle if self.session is not None else None
+        N.call("osb_stt_full_host", vad, N.ptr(wire_host), self.fmt, self.from_rate, n_in, batch, self.linear_chunk, int(self.noise_reduce),
+               int(self.normalize), self.n_mels, float(self.threshold), self.min_speech_ms, self.silence_ms, N.ptr(out["probs"]) if vad else None,
+               N.ptr(out["segments"]) if vad else None, N.ptr(out["counts"]) if vad else None, int(out["segments"].shape[1]), N.ptr(out["mel"]))
+        return out
+
+
 class VadBatch:
     """Silero-shaped VAD over a batch of equal-length streams resident on the device (BASELINE config 2)."""
 

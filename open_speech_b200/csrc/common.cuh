@@ -1,6 +1,7 @@
 // Shared helpers for libosb200 (sm_100a only).
 #pragma once
 #include <cuda_runtime.h>
+#include <mutex>
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
@@ -50,7 +51,7 @@ void prof_end(cudaStream_t st);
 // default mempool keeps freed blocks cached, so steady-state calls do not hit the driver).
 struct Scratch {
     cudaStream_t s;
-    void* ptrs[16];
+    void* ptrs[24];
     int n = 0;
     explicit Scratch(cudaStream_t st) : s(st) {}
     ~Scratch() {
@@ -58,12 +59,31 @@ struct Scratch {
     }
     template <typename T>
     cudaError_t alloc(T** p, size_t count) {
+        if (n >= (int)(sizeof(ptrs) / sizeof(ptrs[0]))) return cudaErrorMemoryAllocation;
         void* q = nullptr;
         cudaError_t e = cudaMallocAsync(&q, count * sizeof(T) + 256, s);
         if (e == cudaSuccess) {
             ptrs[n++] = q;
             *p = reinterpret_cast<T*>(q);
         }
+        return e;
+    }
+};
+
+// Function attributes (dynamic shared memory opt-in) belong to the CONTEXT: a process that drives several devices has to set them once
+// per device, and a failure must not be remembered for ever.  Usage: static PerDeviceOnce once; OSB_CUDA(once.run([&] { return ...; }));
+struct PerDeviceOnce {
+    std::mutex mu;
+    unsigned long long done = 0;  // bit d: device d is set up (up to 64 devices per process)
+    template <typename F>
+    cudaError_t run(F&& f) {
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) return e;
+        std::lock_guard<std::mutex> lk(mu);
+        if (dev < 64 && ((done >> dev) & 1ull)) return cudaSuccess;
+        e = f();
+        if (e == cudaSuccess && dev < 64) done |= 1ull << dev;
         return e;
     }
 };
@@ -98,6 +118,12 @@ int launch_pitch_shift(const void* d_in, bool in_f64, const long long* d_offsets
 int launch_sumsq_pcm16(const int16_t* d_in, long long n, long long batch, long long stride, unsigned long long* d_sumsq, cudaStream_t st);
 int launch_normalize_f32(const float* d_in, void* d_out, int out_pcm16, long long n, long long batch, long long stride, int normalize,
                          float target_dbfs, cudaStream_t st);
+
+// vad.cu: batched scoring (state [batch][2][128] in/out) and the integer segmenter, for the composed paths
+int launch_vad_score(void* handle, const void* d_audio, int fmt, long long n, long long batch, long long stride, float* d_state,
+                     float* d_probs, long long probs_stride, cudaStream_t st);
+int launch_vad_segments(const float* d_probs, long long probs_stride, long long n_win, long long batch, long long n_samples, float thr,
+                        int min_speech_ms, int silence_ms, int32_t* d_segs, int32_t* d_counts, int max_seg, cudaStream_t st);
 
 static inline int grid_for(size_t work_items, int per_block, int max_waves = 8) {
     size_t b = (work_items + per_block - 1) / per_block;

@@ -356,13 +356,12 @@ int launch_logmel(const void* d_audio, int fmt, long long n, long long batch, lo
     const MelTables* t;
     int rc = get_mel(n_mels, true, &t);
     if (rc) return rc;
-    static std::once_flag once;
-    static cudaError_t attr_err = cudaSuccess;
-    std::call_once(once, [&] {
-        attr_err = cudaFuncSetAttribute(k_logmel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLogmelSmemF32);
-        if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(k_logmel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLogmelSmemP16);
-    });
-    OSB_CUDA(attr_err);
+    static PerDeviceOnce once;
+    OSB_CUDA(once.run([&] {
+        cudaError_t e = cudaFuncSetAttribute(k_logmel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLogmelSmemF32);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_logmel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLogmelSmemP16);
+        return e;
+    }));
     const int n_frames = (int)((n + kPad) / kHop);
     Scratch scr(st);
     unsigned int* gmax;

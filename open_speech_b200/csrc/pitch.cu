@@ -321,14 +321,13 @@ int launch_pitch_shift(const void* d_in, bool in_f64, const long long* d_offsets
     const float* tabs;
     int rc = get_ps_tables(&tabs);
     if (rc) return rc;
-    static std::once_flag once;
-    static cudaError_t e1 = cudaSuccess;
-    std::call_once(once, [&] {
-        e1 = cudaFuncSetAttribute(k_ps_stft<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPsSmemFft);
+    static PerDeviceOnce once;
+    OSB_CUDA(once.run([&] {
+        cudaError_t e1 = cudaFuncSetAttribute(k_ps_stft<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPsSmemFft);
         if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(k_ps_stft<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPsSmemFft);
         if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(k_ps_istft, cudaFuncAttributeMaxDynamicSharedMemorySize, kPsSmemIstft);
-    });
-    OSB_CUDA(e1);
+        return e1;
+    }));
     PsGeom g;
     g.rate = std::pow(2.0, -semitones / 12.0);
     g.ratio = (double)sample_rate / ((double)sample_rate / g.rate);

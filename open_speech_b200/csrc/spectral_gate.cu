@@ -765,16 +765,14 @@ int launch_spectral_gate(const void* d_audio, int fmt, long long n, long long ba
     const float* tabs;
     int rc = get_nr_tables(&tabs);
     if (rc) return rc;
-    static std::once_flag once;
-    static cudaError_t e1 = cudaSuccess, e2 = cudaSuccess;
-    std::call_once(once, [&] {
-        e1 = cudaFuncSetAttribute(k_nr_stft, cudaFuncAttributeMaxDynamicSharedMemorySize, kStftSmem);
-        e2 = cudaFuncSetAttribute(k_nr_istft, cudaFuncAttributeMaxDynamicSharedMemorySize, kIstftSmem);
+    static PerDeviceOnce once;
+    OSB_CUDA(once.run([&] {
+        cudaError_t e2 = cudaFuncSetAttribute(k_nr_stft, cudaFuncAttributeMaxDynamicSharedMemorySize, kStftSmem);
+        if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(k_nr_istft, cudaFuncAttributeMaxDynamicSharedMemorySize, kIstftSmem);
         if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(k_nr_mask<16, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmoothSmem);
         if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(k_nr_mask<kNfMax, kNtMax, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmoothSmem);
-    });
-    OSB_CUDA(e1);
-    OSB_CUDA(e2);
+        return e2;
+    }));
     // noisereduce parameters (defaults)
     const double t_frames = 2.0 * sr / (double)NH;
     const double b = (std::sqrt(1.0 + 4.0 * t_frames * t_frames) - 1.0) / (2.0 * t_frames * t_frames);

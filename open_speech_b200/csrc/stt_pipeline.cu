@@ -38,7 +38,202 @@ static int stt_frontend(const int16_t* d_pcm, long long n, long long batch, long
     return launch_logmel(den, OSB_FMT_F32, n, batch, stride, n_mels, d_mel, nullptr, -18.0f, st, sumsq, 1);
 }
 
+// ------------------------------------------------------------------ full STT front-end (north_star chain)
+// wire audio -> [G.711 expand] -> resample to 16 kHz -> { Silero score + segments | [spectral gate] -> [normalise] -> requantise -> log-mel }
+// The VAD reads the resampled pcm16 exactly as InputAudioBuffer.append / _extract_speech_segments hand it over (server.py:137-146,
+// stt_handler.py:75-86); the denoise -> log-mel branch reads the same samples as the committed WAV (server.py:186-199 -> main.py:295-296 ->
+// faster_whisper.py:245).  Neither branch depends on the other.
+static long long full_samples(long long n_in, int from_rate, int linear_chunk) {
+    if (from_rate == 16000) return n_in;
+    if (linear_chunk > 0) {
+        const long long per = (long long)((double)linear_chunk * (16000.0 / (double)from_rate));  // int(len * (to / from)), audio_buffer.py:28
+        return (n_in / linear_chunk) * per;
+    }
+    int a = 16000, b = from_rate;
+    while (b) { const int t = a % b; a = b; b = t; }
+    const long long up = 16000 / a, down = from_rate / a;
+    return (n_in * up + down - 1) / down;
+}
+
+static int stt_full(void* vad, const void* d_in, int in_fmt, int from_rate, long long n_in, long long batch, long long in_stride, int linear_chunk,
+                    int noise_reduce, int normalize, int n_mels, float thr, int min_speech_ms, int silence_ms, int16_t* d_pcm16k, float* d_probs,
+                    int32_t* d_segs, int32_t* d_counts, int max_seg, float* d_mel, cudaStream_t st) {
+    int rc;
+    Scratch scr(st);
+    const long long n16 = full_samples(n_in, from_rate, linear_chunk);
+    const int16_t* pcm = nullptr;
+    long long stride16 = n16;
+    if (from_rate == 16000 && in_fmt == OSB_FMT_PCM16 && !d_pcm16k) {
+        pcm = (const int16_t*)d_in;  // already what the branches read
+        stride16 = in_stride;
+    } else {
+        int16_t* out = d_pcm16k;
+        if (!out) OSB_CUDA(scr.alloc(&out, (size_t)(batch * n16) + 8));
+        if (from_rate == 16000) {
+            if (in_fmt == OSB_FMT_PCM16) OSB_CUDA(cudaMemcpy2DAsync(out, (size_t)n16 * 2, d_in, (size_t)in_stride * 2, (size_t)n_in * 2, (size_t)batch, cudaMemcpyDeviceToDevice, st));
+            else {
+                OSB_REQUIRE(in_stride == n_in, "G.711 rows must be dense");
+                if ((rc = osb_g711_decode_dev((const uint8_t*)d_in, out, (size_t)(batch * n_in), in_fmt, st))) return rc;
+            }
+        } else if (linear_chunk > 0) {
+            // the realtime door: every chunk is resampled on its own (decode_audio_to_pcm16 per append, server.py:137)
+            OSB_REQUIRE(n_in % linear_chunk == 0 && in_stride == n_in, "linear_chunk must divide n_in and rows must be dense");
+            const long long per = n16 / (n_in / linear_chunk);
+            if ((rc = osb_resample_linear_dev(d_in, in_fmt, out, OSB_FMT_PCM16, linear_chunk, per, batch * (n_in / linear_chunk), linear_chunk, per, st))) return rc;
+        } else {
+            int a = 16000, b = from_rate;
+            while (b) { const int t = a % b; a = b; b = t; }
+            const int16_t* lin = (const int16_t*)d_in;
+            long long lin_stride = in_stride;
+            if (in_fmt != OSB_FMT_PCM16) {
+                OSB_REQUIRE(in_stride == n_in, "G.711 rows must be dense");
+                int16_t* tmp;
+                OSB_CUDA(scr.alloc(&tmp, (size_t)(batch * n_in) + 8));
+                if ((rc = osb_g711_decode_dev((const uint8_t*)d_in, tmp, (size_t)(batch * n_in), in_fmt, st))) return rc;
+                lin = tmp;
+                lin_stride = n_in;
+            }
+            if ((rc = osb_resample_poly_dev(lin, out, n_in, batch, lin_stride, n16, 16000 / a, from_rate / a, st))) return rc;
+        }
+        pcm = out;
+    }
+    // VAD branch: a fresh state per recording (stt_handler.py:68-71 builds a new SileroVAD per call)
+    const long long n_win = n16 / 512;
+    if (vad && d_probs && n_win > 0) {
+        float* state;
+        OSB_CUDA(scr.alloc(&state, (size_t)(batch * 256)));
+        OSB_CUDA(cudaMemsetAsync(state, 0, sizeof(float) * batch * 256, st));
+        if ((rc = launch_vad_score(vad, pcm, OSB_FMT_PCM16, n16, batch, stride16, state, d_probs, n_win, st))) return rc;
+        if (d_counts && (rc = launch_vad_segments(d_probs, n_win, n_win, batch, n16, thr, min_speech_ms, silence_ms, d_segs, d_counts, max_seg, st))) return rc;
+    } else if (d_counts) {
+        OSB_CUDA(cudaMemsetAsync(d_counts, 0, sizeof(int32_t) * batch, st));
+    }
+    if (!d_mel) return OSB_OK;
+    return stt_frontend(pcm, n16, batch, stride16, 16000, noise_reduce, normalize, n_mels, d_mel, st);
+}
+
+// Host-buffer pipeline shared by the *_host batch entries: the batch is cut into groups; H2D of group g+1, the kernels of group g and
+// D2H of group g-1 run concurrently on three streams (two copy engines + SMs), so a step costs ~max(copy, compute), not their sum.
+struct GroupPipe {
+    HostWs& ws;
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    cudaEvent_t ev_in[32], ev_done[32];
+    int groups = 0;
+    int64_t bounds[33] = {0};
+    explicit GroupPipe(HostWs& w) : ws(w) {}
+    int open(int64_t batch) {
+        static thread_local cudaStream_t t_in = nullptr, t_out = nullptr;
+        static thread_local cudaEvent_t t_ev[64];
+        static thread_local int t_dev = -1;
+        if (t_dev != ws.device) {  // per-thread copy streams and events, created once per device instead of per call
+            if (t_in) {
+                cudaStreamDestroy(t_in);
+                cudaStreamDestroy(t_out);
+                for (auto& e : t_ev) cudaEventDestroy(e);
+            }
+            OSB_CUDA(cudaStreamCreateWithFlags(&t_in, cudaStreamNonBlocking));
+            OSB_CUDA(cudaStreamCreateWithFlags(&t_out, cudaStreamNonBlocking));
+            for (auto& e : t_ev) OSB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            t_dev = ws.device;
+        }
+        s_in = t_in; s_out = t_out;
+        for (int g = 0; g < 32; ++g) { ev_in[g] = t_ev[g]; ev_done[g] = t_ev[32 + g]; }
+        // clip groups (OSB_STT_HOST_GROUPS=1..32 to tune): the middle of the pipeline is PCIe-bound (the float32 features leaving), so
+        // more groups = shorter fill (first H2D + first kernels) and drain; measured on 256 x 60 s: 8 groups 17.0 ms, 16: 16.2, 24: 16.0
+        groups = batch >= 192 ? 24 : (batch >= 64 ? 8 : (batch >= 16 ? 4 : 1));
+        if (const char* e = getenv("OSB_STT_HOST_GROUPS")) {
+            const int g = atoi(e);
+            if (g >= 1 && g <= 32 && g <= batch) groups = g;
+        }
+        for (int g = 0; g <= groups; ++g) bounds[g] = batch * g / groups;
+        return OSB_OK;
+    }
+    int close(int rc) {
+        cudaError_t e1 = cudaStreamSynchronize(s_in), e2 = cudaStreamSynchronize(ws.stream), e3 = cudaStreamSynchronize(s_out);
+        if (rc) return rc;
+        OSB_CUDA(e1);
+        OSB_CUDA(e2);
+        OSB_CUDA(e3);
+        return OSB_OK;
+    }
+};
+
 extern "C" {
+
+int64_t osb_stt_full_samples(int64_t n_in, int from_rate, int linear_chunk) {
+    if (n_in < 0 || from_rate <= 0 || linear_chunk < 0) return -1;
+    return full_samples(n_in, from_rate, linear_chunk);
+}
+
+int osb_stt_full_dev(void* vad, const void* d_in, int in_fmt, int from_rate, int64_t n_in, int64_t batch, int64_t in_stride, int linear_chunk,
+                     int noise_reduce, int normalize, int n_mels, float vad_threshold, int min_speech_ms, int silence_ms, int16_t* d_pcm16k,
+                     float* d_probs, int32_t* d_segments, int32_t* d_counts, int max_seg, float* d_mel, void* stream) {
+    int rc = ensure_init();
+    if (rc) return rc;
+    OSB_REQUIRE(in_fmt == OSB_FMT_PCM16 || in_fmt == OSB_FMT_ULAW || in_fmt == OSB_FMT_ALAW, "in_fmt must be PCM16, ULAW or ALAW");
+    OSB_REQUIRE(n_mels == 80 || n_mels == 128, "n_mels must be 80 or 128");
+    OSB_REQUIRE(n_in >= 0 && batch >= 0 && in_stride >= n_in && from_rate >= 1000 && linear_chunk >= 0 && max_seg >= 0, "bad sizes");
+    OSB_REQUIRE(batch <= 65535, "batch too large (<= 65535)");
+    if (batch == 0) return OSB_OK;
+    OSB_REQUIRE(d_in, "null input");
+    OSB_REQUIRE(!d_counts || d_segments || max_seg == 0, "null segment buffer");
+    const long long n16 = full_samples(n_in, from_rate, linear_chunk);
+    OSB_REQUIRE(!d_mel || n16 + 160 > 200, "clip too short");
+    OSB_REQUIRE(from_rate == 16000 || linear_chunk > 0 || n_in >= 2, "need at least two samples to resample");
+    return stt_full(vad, d_in, in_fmt, from_rate, n_in, batch, in_stride, linear_chunk, noise_reduce, normalize, n_mels, vad_threshold,
+                    min_speech_ms, silence_ms, d_pcm16k, d_probs, d_segments, d_counts, max_seg, d_mel, (cudaStream_t)stream);
+}
+
+// host buffers in (dense rows), host results out; probs [batch][n16/512], segments [batch][max_seg][2], counts [batch], mel [batch][n_mels][frames]
+int osb_stt_full_host(void* vad, const void* in, int in_fmt, int from_rate, int64_t n_in, int64_t batch, int linear_chunk, int noise_reduce,
+                      int normalize, int n_mels, float vad_threshold, int min_speech_ms, int silence_ms, float* probs, int32_t* segments,
+                      int32_t* counts, int max_seg, float* mel) {
+    HostWs& ws = host_ws();
+    int rc = ws.prepare();
+    if (rc) return rc;
+    OSB_REQUIRE(n_in > 0 && batch > 0 && in && mel && max_seg >= 0, "bad arguments");
+    OSB_REQUIRE(n_mels == 80 || n_mels == 128, "n_mels must be 80 or 128");
+    OSB_REQUIRE(!vad || (probs && segments && counts), "null VAD result buffer");
+    const size_t es = in_fmt == OSB_FMT_PCM16 ? 2 : 1;
+    const long long n16 = full_samples(n_in, from_rate, linear_chunk), n_win = n16 / 512;
+    const size_t per_mel = (size_t)n_mels * osb_logmel_frames(n16);
+    const size_t per_vad = vad ? ((size_t)n_win * 4 + (size_t)max_seg * 8 + 4 + 15) / 16 * 16 : 0;  // probs | segments | count, per clip
+    void *di, *dmel, *dvad;
+    if ((rc = ws.dev_buf(0, (size_t)batch * n_in * es + 16, &di)) || (rc = ws.dev_buf(1, (size_t)batch * per_mel * 4, &dmel)) ||
+        (rc = ws.dev_buf(2, (size_t)batch * (per_vad ? per_vad : 16) + 16, &dvad))) return rc;
+    // VAD results of the whole batch, planar on the device: probs [batch][n_win] | segments [batch][max_seg][2] | counts [batch]
+    float* d_probs = (float*)dvad;
+    int32_t* d_segs = (int32_t*)(d_probs + (size_t)batch * n_win);
+    int32_t* d_cnt = d_segs + (size_t)batch * max_seg * 2;
+    GroupPipe gp(ws);
+    if ((rc = gp.open(batch))) return rc;
+    rc = OSB_OK;
+    for (int g = 0; g < gp.groups && rc == OSB_OK; ++g) {
+        const int64_t c0 = gp.bounds[g], nb = gp.bounds[g + 1] - c0;
+        uint8_t* din = (uint8_t*)di + (size_t)c0 * n_in * es;
+        float* dm = (float*)dmel + c0 * per_mel;
+        cudaError_t e = cudaMemcpyAsync(din, (const uint8_t*)in + (size_t)c0 * n_in * es, (size_t)nb * n_in * es, cudaMemcpyHostToDevice, gp.s_in);
+        if (e == cudaSuccess) e = cudaEventRecord(gp.ev_in[g], gp.s_in);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(ws.stream, gp.ev_in[g], 0);
+        if (e != cudaSuccess) { rc = cuda_fail(e, "h2d group", __FILE__, __LINE__); break; }
+        rc = osb_stt_full_dev(vad, din, in_fmt, from_rate, n_in, nb, n_in, linear_chunk, noise_reduce, normalize, n_mels, vad_threshold, min_speech_ms,
+                              silence_ms, nullptr, vad ? d_probs + c0 * n_win : nullptr, vad ? d_segs + c0 * max_seg * 2 : nullptr,
+                              vad ? d_cnt + c0 : nullptr, max_seg, dm, ws.stream);
+        if (rc) break;
+        e = cudaEventRecord(gp.ev_done[g], ws.stream);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(gp.s_out, gp.ev_done[g], 0);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(mel + c0 * per_mel, dm, (size_t)nb * per_mel * 4, cudaMemcpyDeviceToHost, gp.s_out);
+        if (e != cudaSuccess) { rc = cuda_fail(e, "d2h group", __FILE__, __LINE__); break; }
+    }
+    if (rc == OSB_OK && vad) {  // the VAD results are small: three copies for the whole batch behind the last group
+        cudaError_t e = cudaStreamWaitEvent(gp.s_out, gp.ev_done[gp.groups - 1], 0);
+        if (e == cudaSuccess && n_win > 0) e = cudaMemcpyAsync(probs, d_probs, (size_t)batch * n_win * 4, cudaMemcpyDeviceToHost, gp.s_out);
+        if (e == cudaSuccess && max_seg > 0) e = cudaMemcpyAsync(segments, d_segs, (size_t)batch * max_seg * 8, cudaMemcpyDeviceToHost, gp.s_out);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(counts, d_cnt, (size_t)batch * 4, cudaMemcpyDeviceToHost, gp.s_out);
+        if (e != cudaSuccess) rc = cuda_fail(e, "d2h vad", __FILE__, __LINE__);
+    }
+    return gp.close(rc);
+}
 
 int osb_stt_frontend_dev(const int16_t* d_pcm, int64_t n, int64_t batch, int64_t stride, int sample_rate, int noise_reduce,
                          int normalize, int n_mels, float* d_mel, void* stream) {
@@ -53,8 +248,6 @@ int osb_stt_frontend_dev(const int16_t* d_pcm, int64_t n, int64_t batch, int64_t
     return stt_frontend(d_pcm, n, batch, stride, sample_rate, noise_reduce, normalize, n_mels, d_mel, (cudaStream_t)stream);
 }
 
-// Host-buffer entry: the batch is cut into groups; H2D of group g+1, the kernels of group g and D2H of group g-1
-// run concurrently on three streams (two copy engines + SMs), so the step costs ~max(copy, compute), not their sum.
 int osb_stt_frontend_host(const int16_t* pcm, int64_t n, int64_t batch, int64_t stride, int sample_rate, int noise_reduce,
                           int normalize, int n_mels, float* mel) {
     HostWs& ws = host_ws();
@@ -65,54 +258,27 @@ int osb_stt_frontend_host(const int16_t* pcm, int64_t n, int64_t batch, int64_t 
     const size_t per_mel = (size_t)n_mels * osb_logmel_frames(n);
     void *di, *dout;
     if ((rc = ws.dev_buf(0, (size_t)batch * stride * 2, &di)) || (rc = ws.dev_buf(1, (size_t)batch * per_mel * 4, &dout))) return rc;
-    static thread_local cudaStream_t s_in = nullptr, s_out = nullptr;
-    static thread_local int s_dev = -1;
-    if (s_dev != ws.device) {
-        if (s_in) { cudaStreamDestroy(s_in); cudaStreamDestroy(s_out); }
-        OSB_CUDA(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
-        OSB_CUDA(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
-        s_dev = ws.device;
-    }
-    // clip groups (OSB_STT_HOST_GROUPS=1..32 to tune): the middle of the pipeline is PCIe-bound (the float32 features
-    // leaving), so more groups = shorter fill (first H2D + first kernels) and drain; measured on 256 x 60 s: 8 groups
-    // 17.0 ms, 16: 16.2 ms, 24: 16.0 ms per step
-    int64_t bounds[33] = {0};
-    int groups = batch >= 192 ? 24 : (batch >= 64 ? 8 : (batch >= 16 ? 4 : 1));
-    if (const char* e = getenv("OSB_STT_HOST_GROUPS")) {
-        const int g = atoi(e);
-        if (g >= 1 && g <= 32 && g <= batch) groups = g;
-    }
-    for (int g = 0; g <= groups; ++g) bounds[g] = batch * g / groups;
-    cudaEvent_t ev_in[32], ev_done[32];
-    for (int g = 0; g < groups; ++g) {
-        OSB_CUDA(cudaEventCreateWithFlags(&ev_in[g], cudaEventDisableTiming));
-        OSB_CUDA(cudaEventCreateWithFlags(&ev_done[g], cudaEventDisableTiming));
-    }
+    GroupPipe gp(ws);
+    if ((rc = gp.open(batch))) return rc;
     rc = OSB_OK;
-    for (int g = 0; g < groups && rc == OSB_OK; ++g) {
-        const int64_t c0 = bounds[g], c1 = bounds[g + 1], nb = c1 - c0;
+    for (int g = 0; g < gp.groups && rc == OSB_OK; ++g) {
+        const int64_t c0 = gp.bounds[g], nb = gp.bounds[g + 1] - c0;
         const int16_t* hin = pcm + c0 * stride;
         int16_t* din = (int16_t*)di + c0 * stride;
         float* dmel = (float*)dout + c0 * per_mel;
         const size_t ib = (size_t)((nb - 1) * stride + n) * 2;
-        cudaError_t e = cudaMemcpyAsync(din, hin, ib, cudaMemcpyHostToDevice, s_in);
-        if (e == cudaSuccess) e = cudaEventRecord(ev_in[g], s_in);
-        if (e == cudaSuccess) e = cudaStreamWaitEvent(ws.stream, ev_in[g], 0);
+        cudaError_t e = cudaMemcpyAsync(din, hin, ib, cudaMemcpyHostToDevice, gp.s_in);
+        if (e == cudaSuccess) e = cudaEventRecord(gp.ev_in[g], gp.s_in);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(ws.stream, gp.ev_in[g], 0);
         if (e != cudaSuccess) { rc = cuda_fail(e, "h2d group", __FILE__, __LINE__); break; }
         rc = osb_stt_frontend_dev(din, n, nb, stride, sample_rate, noise_reduce, normalize, n_mels, dmel, ws.stream);
         if (rc) break;
-        e = cudaEventRecord(ev_done[g], ws.stream);
-        if (e == cudaSuccess) e = cudaStreamWaitEvent(s_out, ev_done[g], 0);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(mel + c0 * per_mel, dmel, (size_t)nb * per_mel * 4, cudaMemcpyDeviceToHost, s_out);
+        e = cudaEventRecord(gp.ev_done[g], ws.stream);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(gp.s_out, gp.ev_done[g], 0);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(mel + c0 * per_mel, dmel, (size_t)nb * per_mel * 4, cudaMemcpyDeviceToHost, gp.s_out);
         if (e != cudaSuccess) { rc = cuda_fail(e, "d2h group", __FILE__, __LINE__); break; }
     }
-    cudaError_t e1 = cudaStreamSynchronize(s_in), e2 = cudaStreamSynchronize(ws.stream), e3 = cudaStreamSynchronize(s_out);
-    for (int g = 0; g < groups; ++g) { cudaEventDestroy(ev_in[g]); cudaEventDestroy(ev_done[g]); }
-    if (rc) return rc;
-    OSB_CUDA(e1);
-    OSB_CUDA(e2);
-    OSB_CUDA(e3);
-    return OSB_OK;
+    return gp.close(rc);
 }
 
 int osb_preprocess_stt_host(const int16_t* in, int64_t n, int channels, int sample_rate, int noise_reduce, int normalize,

@@ -844,13 +844,13 @@ static int launch_reverb_eq(dim3 grid, cudaStream_t st, const T* x, const Reverb
     const int smem_max = kRqThreads * kRqStride * (int)sizeof(T) + (kRqTabDoubles + kRqMaxPeriod + kRqMaxPeriod / 16 + 1) * (int)sizeof(double);
     const int smem = kRqThreads * kRqStride * (int)sizeof(T) +
                      (kRqTabDoubles + ((post.robot && post.period <= kRqMaxPeriod) ? post.period + post.period / 16 + 1 : 0)) * (int)sizeof(double);
-    static std::once_flag once;
-    static cudaError_t err = cudaSuccess;
-    std::call_once(once, [&] {
+    static PerDeviceOnce once;  // per T
+    OSB_CUDA(once.run([&] {
+        cudaError_t err = cudaSuccess;
         auto opt = [&](auto kern) { if (err == cudaSuccess) err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max); };
         opt(k_fx_reverb_eq<T, 0>); opt(k_fx_reverb_eq<T, 1>); opt(k_fx_reverb_eq<T, 2>);
-    });
-    OSB_CUDA(err);
+        return err;
+    }));
     switch (post.finish) {
         case 0: OSB_LAUNCH((k_fx_reverb_eq<T, 0>), grid, kRqThreads, smem, st, x, ra, e, lp, pre, post, dst); break;
         case 1: OSB_LAUNCH((k_fx_reverb_eq<T, 1>), grid, kRqThreads, smem, st, x, ra, e, lp, pre, post, dst); break;
@@ -1000,15 +1000,14 @@ static int robot_carrier(int sample_rate, const double** d_tab, int* period) {
 // dynamic shared memory opt-in of the recurrence kernels, once per process (the effect entry points are called from
 // several threads at once)
 static cudaError_t fx_smem_attrs(int smem) {
-    static std::once_flag once;
-    static cudaError_t err = cudaSuccess;
-    std::call_once(once, [&] {
-        err = cudaFuncSetAttribute(k_fx_reverb<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    static PerDeviceOnce once;
+    return once.run([&] {
+        cudaError_t err = cudaFuncSetAttribute(k_fx_reverb<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (err == cudaSuccess) err = cudaFuncSetAttribute(k_fx_reverb<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (err == cudaSuccess) err = cudaFuncSetAttribute(k_fx_eq<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (err == cudaSuccess) err = cudaFuncSetAttribute(k_fx_eq<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        return err;
     });
-    return err;
 }
 
 // exponential impulse response exp(-linspace(0, 6, L)) / sum, cached on the device per (device, L): no upload and no

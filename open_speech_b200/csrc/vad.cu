@@ -880,10 +880,8 @@ static int build_tc_image(const std::vector<float>& B, int N, int Kp, int NT, Va
 
 template <int AMODE, int EPI>
 static int launch_gemm_tc(const GemmDesc& d, const VadModel::Tc& L, cudaStream_t st) {
-    static std::once_flag once;  // per template instance; VAD sessions are scored from several threads
-    static cudaError_t attr_err = cudaSuccess;
-    std::call_once(once, [&] { attr_err = cudaFuncSetAttribute(k_vad_gemm_tc<AMODE, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem); });
-    OSB_CUDA(attr_err);
+    static PerDeviceOnce once;  // per template instance; VAD sessions are scored from several threads
+    OSB_CUDA(once.run([&] { return cudaFuncSetAttribute(k_vad_gemm_tc<AMODE, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem); }));
     OSB_LAUNCH((k_vad_gemm_tc<AMODE, EPI>), (d.M + kTcM - 1) / kTcM, kTcThreads, kTcSmem, st, d, (const uint16_t*)L.img, L.NT, L.n_tiles, L.k_chunks);
     OSB_CHECK_LAUNCH();
     return OSB_OK;
@@ -921,14 +919,13 @@ static int vad_score(VadModel* m, const void* d_audio, int fmt, int64_t n, int64
     OSB_CUDA(cudaMemsetAsync(h1, 0, ((size_t)W * 5 * 128 + 64) * 4, st));
     OSB_CUDA(cudaMemsetAsync(h2, 0, ((size_t)W * 4 * 64 + 64) * 4, st));
     OSB_CUDA(cudaMemsetAsync(h3, 0, ((size_t)W * 3 * 64 + 64) * 4, st));
-    static std::once_flag once;
-    static cudaError_t attr_err = cudaSuccess;
-    std::call_once(once, [&] {
-        attr_err = cudaFuncSetAttribute(k_vad_recur<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, RecurCfg<1>::smem);
-        if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(k_vad_recur_mb<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, RecurMbCfg<2>::smem);
-        if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(k_vad_recur_mb<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, RecurMbCfg<4>::smem);
-    });
-    OSB_CUDA(attr_err);
+    static PerDeviceOnce once;
+    OSB_CUDA(once.run([&] {
+        cudaError_t e = cudaFuncSetAttribute(k_vad_recur<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, RecurCfg<1>::smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_vad_recur_mb<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, RecurMbCfg<2>::smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_vad_recur_mb<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, RecurMbCfg<4>::smem);
+        return e;
+    }));
     // streams per recurrence CTA: as few as keep the grid within one wave of SMs
     const int rs = batch <= OSB_NUM_SMS ? 1 : (batch <= 2 * OSB_NUM_SMS ? 2 : 4);
     int rc;
@@ -997,6 +994,16 @@ static int vad_segments(const float* d_probs, int64_t probs_stride, int64_t n_wi
                min_speech_windows, silence_windows, d_segs, d_counts, max_seg);
     OSB_CHECK_LAUNCH();
     return OSB_OK;
+}
+
+int launch_vad_score(void* handle, const void* d_audio, int fmt, long long n, long long batch, long long stride, float* d_state,
+                     float* d_probs, long long probs_stride, cudaStream_t st) {
+    if (!handle) { set_error("invalid argument: null VAD handle"); return OSB_ERR_INVALID_ARG; }
+    return vad_score(reinterpret_cast<VadModel*>(handle), d_audio, fmt, n, batch, stride, d_state, d_probs, probs_stride, st);
+}
+int launch_vad_segments(const float* d_probs, long long probs_stride, long long n_win, long long batch, long long n_samples, float thr,
+                        int min_speech_ms, int silence_ms, int32_t* d_segs, int32_t* d_counts, int max_seg, cudaStream_t st) {
+    return vad_segments(d_probs, probs_stride, n_win, batch, n_samples, thr, min_speech_ms, silence_ms, d_segs, d_counts, max_seg, st);
 }
 
 }  // namespace osb
@@ -1142,7 +1149,6 @@ int osb_vad_extract_speech_host(void* handle, const int16_t* pcm, int64_t n, int
     *out_n = 0;
     if (n_segments) *n_segments = 0;
     if (n <= 0) return OSB_OK;
-    const int max_seg = 4096;
     int up = 1, down = 1;
     long long n16 = n;
     if (rate != 16000) {
@@ -1153,6 +1159,7 @@ int osb_vad_extract_speech_host(void* handle, const int16_t* pcm, int64_t n, int
         OSB_REQUIRE(n >= 2, "need at least two samples to resample");
     }
     const long long n_win = n16 / kWin;
+    const int max_seg = (int)(n_win / 2 + 2);  // a segment needs a speech window and a silence window: never more than this
     void *d_in, *d_16k, *d_misc, *d_out;
     const size_t misc = 2 * kHid * 4 + (size_t)(n_win + 1) * 4 + (size_t)max_seg * 8 + 64 + (size_t)max_seg * 24 + 64;
     if ((rc = ws.dev_buf(0, (size_t)n * 2 + 16, &d_in)) || (rc = ws.dev_buf(1, (size_t)n16 * 2 + 16, &d_16k)) ||

@@ -2,8 +2,8 @@
 
 Same names, argument meaning and error behaviour; the codec and the np.interp resampler run
 in libosb200 (osb_resample_linear_host: G.711 expand/compress fused with the f64 linear
-interpolation, bit-exact).  The speech start/stop gate stays host-side Python, exactly the
-reference's integer state machine (audio_buffer.py:125-156).
+interpolation, bit-exact).  The speech start/stop gate runs in libosb200 as well
+(csrc/realtime_gate.cu): InputAudioBuffer is a per-connection view of it.
 """
 from __future__ import annotations
 
@@ -13,7 +13,9 @@ from typing import Any
 import numpy as np
 
 from .. import _native as N
-from ..vad.silero import VAD_SAMPLE_RATE, SileroVAD
+from ..vad.silero import VAD_SAMPLE_RATE, SileroVAD, VadSession
+
+N_EVT_STARTED, N_EVT_STOPPED, N_EVT_FRAME_TOO_LARGE, N_EVT_BUFFER_FULL = 1, 2, 3, 4  # OSB_EVT_* (include/osb200.h)
 
 logger = logging.getLogger(__name__)
 
@@ -70,65 +72,77 @@ def encode_pcm16_to_format(pcm16_data: bytes, from_rate: int, fmt: str) -> bytes
     raise ValueError(f"Unsupported audio format: {fmt}")
 
 
+GATE_STATE = np.dtype([("total_samples", "<i8"), ("silence_samples", "<i8"), ("buffered_samples", "<i8"),
+                       ("in_speech", "<i4"), ("speech_start_ms", "<i4")])  # osb_gate_state (include/osb200.h)
+_EVENT = {N_EVT_STARTED: ("speech_started", "audio_start_ms"), N_EVT_STOPPED: ("speech_stopped", "audio_end_ms")}
+
+
 class InputAudioBuffer:
-    """Input audio buffer (PCM16 16 kHz mono) with optional VAD gating (reference :84-166)."""
+    """Per-connection view of the device gate (reference class: src/realtime/audio_buffer.py:84-166).
+
+    The object holds what the drop-in boundary has to hand back as host ``bytes`` (the committed audio goes to the
+    transcriber as a WAV) and one ``osb_gate_state`` record; every gated ``append`` is one ``osb_gate_append_host``
+    call: VAD scoring of the chunk and the start / stop machine run in libosb200, there is no host copy of that logic.
+    S concurrent connections are better served by :class:`open_speech_b200.realtime.gate.RealtimeGate`, which keeps
+    the same records, the LSTM states and the audio arena resident on the GPU and advances all of them per tick.
+    """
 
     def __init__(self, vad: SileroVAD | None = None, threshold: float = 0.5,
                  silence_duration_ms: int = 500, max_buffer_bytes: int = 50 * 1024 * 1024):
+        if vad is not None and not isinstance(getattr(vad, "session", None), VadSession):
+            raise TypeError("InputAudioBuffer needs an open_speech_b200 SileroVAD over a VadSession (GPU-resident weights); "
+                            "there is no host implementation of the gate")
         self._buffer = bytearray()
         self._vad = vad
         self._threshold = threshold
         self._silence_duration_ms = silence_duration_ms
-        self._in_speech = False
-        self._silence_samples = 0
-        self._speech_start_ms = 0
-        self._total_samples = 0
         self._max_buffer_bytes = max_buffer_bytes
+        self._gate = np.zeros(1, dtype=GATE_STATE)
+        self._event = np.zeros(2, dtype=np.int32)
 
+    # the reference's private counters, read-only views of the record
     @property
     def in_speech(self) -> bool:
-        return self._in_speech
+        return bool(self._gate["in_speech"][0])
+
+    _in_speech = in_speech
+
+    @property
+    def _silence_samples(self) -> int:
+        return int(self._gate["silence_samples"][0])
+
+    @property
+    def _total_samples(self) -> int:
+        return int(self._gate["total_samples"][0])
+
+    @property
+    def _speech_start_ms(self) -> int:
+        return int(self._gate["speech_start_ms"][0])
 
     def clear(self) -> None:
         self._buffer.clear()
-        self._silence_samples = 0
+        self._gate["silence_samples"] = 0
 
     def append(self, pcm16_16khz: bytes) -> list[dict[str, Any]]:
-        events: list[dict[str, Any]] = []
-        frame_size = len(pcm16_16khz)
-        if frame_size > self._max_buffer_bytes:
+        size = len(pcm16_16khz)
+        if size > self._max_buffer_bytes:
             self.clear()
             raise BufferError(f"Audio frame exceeds max buffer size ({self._max_buffer_bytes} bytes)")
-        if len(self._buffer) + frame_size > self._max_buffer_bytes:
+        if len(self._buffer) + size > self._max_buffer_bytes:
             raise BufferError(f"Input audio buffer exceeded max size ({self._max_buffer_bytes} bytes)")
-        self._buffer.extend(pcm16_16khz)
-
-        num_samples = frame_size // 2
-        current_ms = (self._total_samples * 1000) // VAD_SAMPLE_RATE
-        self._total_samples += num_samples
-        if self._vad is None or num_samples == 0:
-            return events
-
-        # the reference converts to float32/32768 and calls vad(audio); a SileroVAD from this
-        # package scores the int16 bytes on the GPU directly (same arithmetic, fused convert)
-        score = getattr(self._vad, "score_pcm16", None)
-        if score is not None:
-            prob = score(pcm16_16khz)
-        else:  # any callable with the reference's __call__(float32 ndarray) contract (e.g. a mock)
-            prob = self._vad(np.frombuffer(pcm16_16khz, dtype=np.int16).astype(np.float32) / 32768.0)
-        if prob >= self._threshold:
-            self._silence_samples = 0
-            if not self._in_speech:
-                self._in_speech = True
-                self._speech_start_ms = current_ms
-                events.append({"type": "speech_started", "audio_start_ms": current_ms})
-        elif self._in_speech:
-            self._silence_samples += num_samples
-            if (self._silence_samples * 1000) // VAD_SAMPLE_RATE >= self._silence_duration_ms:
-                self._in_speech = False
-                self._silence_samples = 0
-                events.append({"type": "speech_stopped", "audio_end_ms": current_ms})
-        return events
+        self._buffer += pcm16_16khz
+        n = size // 2
+        if self._vad is None or n == 0:
+            self._gate["total_samples"] += n  # no gate configured: the clock is all there is (reference :125-129)
+            return []
+        if size % 2:
+            raise ValueError("buffer size must be a multiple of element size")  # np.frombuffer(..., int16) in the reference (:133)
+        st = np.ascontiguousarray(self._vad._state, dtype=np.float32)
+        N.call("osb_gate_append_host", self._vad.session.handle, pcm16_16khz, n, N.ptr(self._gate), N.ptr(st), 1,
+               float(self._threshold), int(self._silence_duration_ms), N.ptr(self._event))
+        self._vad._state = st
+        kind = _EVENT.get(int(self._event[0]))
+        return [{"type": kind[0], kind[1]: int(self._event[1])}] if kind else []
 
     def commit(self) -> bytes:
         data = bytes(self._buffer)

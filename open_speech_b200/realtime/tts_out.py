@@ -25,9 +25,8 @@ def _collect(chunks: Iterable) -> np.ndarray | None:
     if not parts:
         return None
     combined = np.concatenate(parts)
-    if combined.dtype != np.float32:
-        raise ValueError(f"realtime TTS audio must be float32, got {combined.dtype}")
-    return np.ascontiguousarray(combined)
+    # the reference multiplies in the chunks' own dtype; backends deliver float32, anything else is cast (deviations)
+    return np.ascontiguousarray(combined, dtype=np.float32)
 
 
 def _encode(chunks: Iterable, output_format: str, want_payload: bool, want_text: bool) -> tuple[bytes, str]:

@@ -3,14 +3,15 @@
 ``SileroVAD(session, threshold)`` keeps the reference's attributes (.session, .sample_rate,
 .threshold, ._state[2,1,128]) and methods.  ``session`` is a :class:`VadSession` (weights
 resident on the GPU, shared between per-stream SileroVAD objects like the reference shares
-one ONNX session).  Any other object with the ORT ``run(None, {...})`` contract (the mocks of
-the reference's tests) is driven window by window exactly like the reference does.
+one ONNX session).  There is no host implementation: the window loop, the network and the
+segmenter all run in libosb200, and any other kind of session object is refused.
 """
 from __future__ import annotations
 
 import asyncio
 import ctypes
 import logging
+import os
 from dataclasses import dataclass
 
 import numpy as np
@@ -21,7 +22,7 @@ logger = logging.getLogger(__name__)
 
 VAD_SAMPLE_RATE = 16000
 WINDOW = 512
-_MAX_SEGMENTS = 4096
+ALLOW_RANDOM_INIT_ENV = "OSB_VAD_ALLOW_RANDOM_INIT"
 
 _vad_model: "SileroVAD | None" = None
 _vad_lock = asyncio.Lock()
@@ -124,7 +125,7 @@ def load_installed_silero_weights() -> dict[str, np.ndarray] | None:
         model = silero_vad.load_silero_vad(onnx=False)
         return weights_from_state_dict(model.state_dict())
     except Exception as e:  # ImportError, or a package version with a different architecture
-        logger.info("silero_vad weights not used (%s): seeded random-init network instead", e)
+        logger.warning("silero_vad weights not available (%s)", e)
         return None
 
 
@@ -161,6 +162,9 @@ class SileroVAD:
     """Per-stream VAD state over a shared session (reference class at :45-177)."""
 
     def __init__(self, session, threshold: float = 0.5):
+        if not isinstance(session, VadSession):
+            raise TypeError("SileroVAD needs a VadSession (weights resident on the GPU); open_speech_b200 has no host "
+                            f"implementation to drive a {type(session).__name__} with")
         self.session = session
         self.sample_rate = VAD_SAMPLE_RATE
         self.threshold = threshold
@@ -170,9 +174,6 @@ class SileroVAD:
         self._state = np.zeros((2, 1, 128), dtype=np.float32)
 
     # ------------------------------------------------------------------ scoring
-    def _native(self) -> bool:
-        return isinstance(self.session, VadSession)
-
     def _score(self, buf, fmt: int, n: int) -> np.ndarray:
         """Per-window probabilities of the full windows in buf; advances self._state."""
         n_win = n // WINDOW
@@ -185,24 +186,12 @@ class SileroVAD:
         self._state = st
         return probs
 
-    def _score_mock(self, audio: np.ndarray) -> list[float]:
-        probs = []
-        for start in range(0, len(audio) - WINDOW + 1, WINDOW):
-            chunk = audio[start:start + WINDOW].reshape(1, -1).astype(np.float32)
-            out, self._state = self.session.run(None, {"input": chunk, "state": self._state,
-                                                       "sr": np.array(self.sample_rate, dtype=np.int64)})
-            probs.append(float(out[0][0]))
-        return probs
-
     def __call__(self, audio: np.ndarray) -> float:
         """Speech probability 0-1: max over the full 512-sample windows (0.0 if none)."""
         if len(audio) == 0:
             return 0.0
-        if self._native():
-            a = np.ascontiguousarray(audio, dtype=np.float32)
-            probs = self._score(N.ptr(a), N.FMT_F32, len(a))
-        else:
-            probs = self._score_mock(np.asarray(audio))
+        a = np.ascontiguousarray(audio, dtype=np.float32)
+        probs = self._score(N.ptr(a), N.FMT_F32, len(a))
         max_prob = 0.0
         for p in probs:
             if float(p) > max_prob:
@@ -213,8 +202,6 @@ class SileroVAD:
         """__call__ on int16 bytes (the /32768 convert is fused into the kernel)."""
         if not pcm16_bytes:
             return 0.0
-        if not self._native():
-            return self(np.frombuffer(pcm16_bytes, dtype=np.int16).astype(np.float32) / 32768.0)
         probs = self._score(pcm16_bytes, N.FMT_PCM16, len(pcm16_bytes) // 2)
         return float(probs.max()) if len(probs) and float(probs.max()) > 0.0 else 0.0
 
@@ -230,51 +217,36 @@ class SileroVAD:
             return []
         thresh = threshold if threshold is not None else self.threshold
         n = len(pcm16_bytes) // 2
-        if self._native():
-            st = np.ascontiguousarray(self._state, dtype=np.float32)
-            segs = np.empty((_MAX_SEGMENTS, 2), dtype=np.int32)
-            cnt = ctypes.c_int(0)
-            N.call("osb_vad_segments_host", self.session.handle, pcm16_bytes, N.FMT_PCM16, n, N.ptr(st),
-                   float(thresh), int(min_speech_ms), int(silence_ms), N.ptr(segs), _MAX_SEGMENTS, ctypes.byref(cnt))
-            self._state = st
-            return [Segment(int(s), int(e)) for s, e in segs[: cnt.value]]
-        audio = np.frombuffer(pcm16_bytes, dtype=np.int16).astype(np.float32) / 32768.0
-        return _segments_from_probs(self._score_mock(audio), n, thresh, min_speech_ms, silence_ms)
-
-
-def _segments_from_probs(probs, n_samples, thresh, min_speech_ms, silence_ms) -> list[Segment]:
-    """Host copy of the segmenter for non-native sessions (reference :133-177)."""
-    window_ms = WINDOW * 1000 // VAD_SAMPLE_RATE
-    silence_windows = max(1, silence_ms // window_ms)
-    min_speech_windows = max(1, min_speech_ms // window_ms)
-    segments: list[Segment] = []
-    in_speech, speech_start, silence_count, speech_windows = False, 0, 0, 0
-    for k, prob in enumerate(probs):
-        current_ms = k * WINDOW * 1000 // VAD_SAMPLE_RATE
-        if prob >= thresh:
-            silence_count = 0
-            if not in_speech:
-                in_speech, speech_start, speech_windows = True, current_ms, 0
-            speech_windows += 1
-        elif in_speech:
-            silence_count += 1
-            if silence_count >= silence_windows:
-                if speech_windows >= min_speech_windows:
-                    segments.append(Segment(start_ms=speech_start, end_ms=current_ms))
-                in_speech, silence_count, speech_windows = False, 0, 0
-    if in_speech and speech_windows >= min_speech_windows:
-        segments.append(Segment(start_ms=speech_start, end_ms=n_samples * 1000 // VAD_SAMPLE_RATE))
-    return segments
+        if len(pcm16_bytes) % 2:
+            raise ValueError("buffer size must be a multiple of element size")  # np.frombuffer(..., int16) in the reference (:131)
+        st = np.ascontiguousarray(self._state, dtype=np.float32)
+        max_seg = n // WINDOW // 2 + 2  # a segment needs a speech window and a silence window: never more than this
+        segs = np.empty((max_seg, 2), dtype=np.int32)
+        cnt = ctypes.c_int(0)
+        N.call("osb_vad_segments_host", self.session.handle, pcm16_bytes, N.FMT_PCM16, n, N.ptr(st),
+               float(thresh), int(min_speech_ms), int(silence_ms), N.ptr(segs), max_seg, ctypes.byref(cnt))
+        self._state = st
+        return [Segment(int(s), int(e)) for s, e in segs[: cnt.value]]
 
 
 async def get_vad_model() -> SileroVAD:
-    """Lazy singleton (reference :180-209).  Weights: silero-vad package if importable, else the
-    seeded random-init network (no network access: nothing is downloaded)."""
+    """Lazy singleton (reference :180-209).  The weights come from the installed silero-vad package; nothing is downloaded.
+
+    Like the reference, which raises when its model cannot be fetched or loaded (:196-206; the realtime server then disables
+    server VAD, server.py:55-59), this raises when no real weights are available.  The seeded random-init network of
+    BASELINE configs[1] is for benchmarks and tests only: ``VadSession()`` builds it explicitly, or set
+    OSB_VAD_ALLOW_RANDOM_INIT=1 to let the server singleton use it."""
     global _vad_model
     if _vad_model is not None:
         return _vad_model
     async with _vad_lock:
         if _vad_model is None:
-            _vad_model = SileroVAD(VadSession(load_installed_silero_weights()))
+            weights = load_installed_silero_weights()
+            if weights is None:
+                if os.environ.get(ALLOW_RANDOM_INIT_ENV) != "1":
+                    raise RuntimeError("Silero VAD weights are not available (pip package `silero-vad` missing or of another layout); "
+                                       f"refusing to gate speech with a random network (set {ALLOW_RANDOM_INIT_ENV}=1 to allow it)")
+                logger.error("Silero VAD: using the seeded RANDOM-INIT network (%s=1); its events are meaningless", ALLOW_RANDOM_INIT_ENV)
+            _vad_model = SileroVAD(VadSession(weights))
             logger.info("Silero VAD weights uploaded to GPU")
         return _vad_model

