@@ -1,20 +1,25 @@
 #!/usr/bin/env python
-"""bench.py -- headline benchmark of the B200-native open-speech audio hot path.
+"""bench.py -- benchmark of the B200-native open-speech audio hot path.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload stt_batch|c1|vad|realtime|tts] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload stt_batch|stt_full|c1|vad|realtime|tts] [--impl reference] [--no-extra]
 
-Default workload = BASELINE.json configs[3], the configuration the metric's target is quoted on:
-batch STT front-end, 256 x 60 s 16 kHz pcm16 clips per GPU -> spectral-gating noise reduction -> RMS normalise
--> int16 requantise -> Whisper large-v3 128-bin log-mel.  One "step" = one pass over the batch.
+Default (headline) workload = BASELINE.json configs[3], the configuration the metric's target is quoted on: batch STT
+front-end, 256 x 60 s 16 kHz pcm16 clips per GPU -> spectral-gating noise reduction -> RMS normalise -> int16 requantise
+-> Whisper large-v3 128-bin log-mel.  One "step" = one pass over the batch.  The same JSON line carries, under
+"configs", compact results for the other BASELINE shapes (full STT front-end with decode + resample + VAD, configs[0] as
+a batch, configs[1] VAD over 256 x 1 h, configs[2] realtime ticks with events, configs[4] TTS post-processing), so that
+every named shape is timed by the driver at every N.  `--workload X` prints X's own full line instead.
 
-  value   audio-seconds per second, inputs already resident in HBM (CUDA events, max over ranks)
-  e2e     same metric through the C-ABI host entry point: pinned HOST buffers in, HOST features out,
-          H2D and D2H inside the timed region
-  roofline / cpu_baseline / clocks: see DESIGN.md "Measurement"
+  value     audio-seconds per second, inputs already resident in HBM (CUDA events, barrier both sides, max over ranks)
+  e2e       same metric through the C-ABI host entry point: pinned HOST buffers in, HOST results out, H2D and D2H inside
+            the timed region; copy_floor_ms = the same copy schedule with no kernels; pageable_ms = numpy (pageable) buffers
+  roofline  frac = the step's SURVEY 8(d) algorithmic bytes / step time / measured HBM peak; kernel_frac = the dominant
+            kernel's own input + output bytes / its CUDA-event time / the same peak
+  cpu_baseline / clocks: DESIGN.md "Measurement"
 
---impl reference times the reference's CPU implementation of the same chain (the numpy/scipy oracle port: the
-reference is pure Python around numpy/scipy/noisereduce/faster-whisper, three of which cannot be installed) on
-all host cores, on a bounded sample of the same workload.
+--impl reference times the reference's CPU implementation of the same chain (the numpy/scipy oracle port: the reference is
+pure Python around numpy/scipy/noisereduce/faster-whisper/onnxruntime, four of which cannot be installed here) on all host
+cores, on a bounded sample of the same workload.
 """
 from __future__ import annotations
 
@@ -35,6 +40,7 @@ import numpy as np  # noqa: E402
 METRIC = "audio-seconds/sec"
 UNIT = "audio-s/s"
 SR = 16000
+DISTINCT = 8  # distinct synthetic clips per rank, tiled to the batch (distinct addresses: the traffic is the full batch's)
 
 
 def load_peaks():
@@ -46,16 +52,46 @@ def load_peaks():
 
 
 # ----------------------------------------------------------------------------- workloads
-WORKLOADS = {
-    # name: (description, clips per GPU, seconds per clip, noise_reduce, normalize, n_mels)
-    "stt_batch": ("BASELINE configs[3]: batch STT front-end, 256x60 s clips/GPU: spectral-gate denoise + normalise + 128-bin log-mel", 256, 60.0, True, True, 128),
-    "c1": ("BASELINE configs[0] as a batch: 256x30 s clips/GPU: normalise + 128-bin log-mel (no denoise)", 256, 30.0, False, True, 128),
+STT = {
+    # name: description, clips per GPU, seconds per clip, noise_reduce, normalize, n_mels, full chain (decode + resample + VAD in front)
+    "stt_batch": ("BASELINE configs[3]: batch STT front-end, 256x60 s clips/GPU: spectral-gate denoise + normalise + 128-bin log-mel", 256, 60.0, True, True, 128, False),
+    "c1": ("BASELINE configs[0] as a batch: 256x30 s clips/GPU: normalise + 128-bin log-mel (no denoise)", 256, 30.0, False, True, 128, False),
+    "stt_full": ("north_star full STT front-end, 256x60 s recordings/GPU: G.711 mu-law 8 kHz -> pcm16 -> 16 kHz (np.interp per 20 ms chunk, the realtime door) "
+                 "-> Silero-shaped VAD scoring + segmenting -> spectral-gate denoise + normalise + 128-bin log-mel, one call", 256, 60.0, True, True, 128, True),
 }
+# SURVEY.md 8(d) algorithmic bytes per audio-second (compulsory input + output, no intermediates).
+#   stt_batch / c1: 32,000 (pcm16 in) + 51,200 (f32 [128][100] out)
+#   stt_full: 8,000 (mu-law in) + 51,200 (features) + 125 (31.25 probabilities) -- the survey has no row for the composed chain;
+#             same rule applied to its wire input and its outputs
+ALG_BYTES_PER_AUDIO_S = {"stt_batch": 83200.0, "c1": 83200.0, "stt_full": 59325.0}
+VAD_ALG_BYTES_PER_AUDIO_S = 32125.0
+TTS_ALG_BYTES_PER_AUDIO_S = 192000.0
 
-# SURVEY.md 8(d) algorithmic bytes per audio-second (compulsory input + output, no intermediates)
-ALG_BYTES_PER_AUDIO_S = {"stt_batch": 83200.0, "c1": 83200.0}
-# denoise stage on its own: pcm16 in (2 B/sample) + f32 out (4 B/sample)
-DENOISE_BYTES_PER_AUDIO_S = 6.0 * SR
+
+def kernel_io_bytes_per_audio_s(name: str, seconds: float, denoised_input: bool) -> float | None:
+    """The kernel's OWN compulsory input + output bytes per audio-second in the decomposition that ships:
+    what it would move if every byte crossed HBM exactly once.  Spectral-gate cells: 513 bins x the frames of noisereduce's
+    600,000-sample chunks with 30,000 samples of context either side, hop 256 (frames wholly past the clip end are skipped)."""
+    n = seconds * SR
+    chunks = max(1, int(np.ceil(n / 600000.0)))
+    frames = (n + 60000.0 * chunks) / 256.0 + chunks
+    cells = 513.0 * frames / seconds
+    table = {
+        "k_nr_stft": 2.0 * SR + 12.0 * cells,             # pcm16 in; spectrum (8 B) + magnitude (4 B) out
+        "k_nr_carry": 2.0 * cells / 16.0 * 8.0,           # per-16-frame tile aggregates in, filter states out (f64)
+        "k_nr_mask": 4.0 * cells + 4.0 * cells,           # magnitude in, smoothed mask out
+        "k_nr_istft": 12.0 * cells + 4.0 * SR,            # spectrum + mask in, float32 samples out
+        "k_logmel": (4.0 if denoised_input else 2.0) * SR + 51200.0,
+        "k_logmel_finalize": 2.0 * 51200.0,
+        "k_sumsq_pcm16": 2.0 * SR,
+        "k_resample_linear": 1.0 * SR / 2 + 2.0 * SR,     # mu-law 8 kHz in, pcm16 16 kHz out
+        "k_vad_front_fused": 2.0 * SR + 31.25 * 2048.0,   # pcm16 in, gate pre-activations [512] f32 per window out
+        "k_vad_recur": 31.25 * 2048.0 + 31.25 * 4.0,      # pre-activations in, probabilities out
+    }
+    for k, v in table.items():
+        if name.startswith(k):
+            return v
+    return None
 
 
 class ClockSampler:
@@ -107,6 +143,32 @@ class ClockSampler:
                 "reasons": sorted(reasons)}
 
 
+# ----------------------------------------------------------------------------- synthetic inputs
+def make_clips(workload: str, clips: int, seconds: float, rank: int, nr: bool):
+    """int16 [clips, n] @16 kHz for the batch chains (the full chain takes ulaw_clips)."""
+    from open_speech_b200 import synth
+
+    return synth.clip_batch_pcm16(clips, seconds, seed=synth.SEED_C4 + 1000 * rank, extra_noise_rms=0.01 if nr else 0.0, distinct=DISTINCT)
+
+
+def ulaw_clips(clips: int, seconds: float, rank: int) -> np.ndarray:
+    """mu-law 8 kHz recordings: speech-like 8 kHz pcm16 encoded ON THE GPU by the library's own lin2ulaw kernel
+    (bit-exact with audioop, tests/test_gpu_codec_resample.py) -- the bench's GPU arm never imports oracle/."""
+    import torch
+
+    from open_speech_b200 import _native as N
+    from open_speech_b200 import synth
+
+    n8 = int(seconds * 8000)
+    base = np.stack([synth.clip_pcm16(seconds, sr=8000, seed=synth.SEED_C4 + 1000 * rank + i, extra_noise_rms=0.01) for i in range(min(DISTINCT, clips))])
+    d = torch.from_numpy(base).cuda()
+    out = torch.empty(d.shape, dtype=torch.uint8, device="cuda")
+    N.call("osb_g711_encode_dev", d.data_ptr(), out.data_ptr(), d.numel(), N.FMT_ULAW, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    ul = out.cpu().numpy()
+    return np.ascontiguousarray(ul[np.arange(clips) % ul.shape[0]]).reshape(clips, n8)
+
+
 # ----------------------------------------------------------------------------- CPU baseline (oracle port)
 def _cpu_one(args):
     import warnings
@@ -114,9 +176,14 @@ def _cpu_one(args):
     warnings.filterwarnings("ignore")
     from oracle import stt
 
-    pcm, noise_reduce, normalize, n_mels = args
+    kind, data, nr, norm, n_mels = args
     t = time.perf_counter()
-    stt.stt_frontend(pcm, noise_reduce=noise_reduce, normalize=normalize, n_mels=n_mels)
+    if kind == "full":
+        from oracle import vad as ovad
+
+        stt.stt_full(data, "g711_ulaw", 8000, linear_chunk=160, noise_reduce=nr, normalize=norm, n_mels=n_mels, net=ovad.SileroNet())
+    else:
+        stt.stt_frontend(data, noise_reduce=nr, normalize=norm, n_mels=n_mels)
     return time.perf_counter() - t
 
 
@@ -124,11 +191,19 @@ def cpu_baseline(workload: str, cores: int, n_clips: int, seconds: float) -> dic
     """Oracle port of the reference chain on `cores` host processes, bounded sample of the same workload."""
     from open_speech_b200 import synth
 
-    _, _, _, nr, norm, n_mels = WORKLOADS[workload]
-    clips = synth.clip_batch_pcm16(n_clips, seconds, seed=synth.SEED_C4, distinct=min(n_clips, 8))
-    jobs = [(clips[i], nr, norm, n_mels) for i in range(n_clips)]
+    _, _, _, nr, norm, n_mels, full = STT[workload]
+    if full:
+        from oracle import codec
+
+        base = [codec.lin2ulaw(synth.clip_pcm16(seconds, sr=8000, seed=synth.SEED_C4 + i, extra_noise_rms=0.01).tobytes()) for i in range(min(n_clips, DISTINCT))]
+        jobs = [("full", base[i % len(base)], nr, norm, n_mels) for i in range(n_clips)]
+        warm = ("full", base[0][: 8000 * 2], nr, norm, n_mels)
+    else:
+        clips = synth.clip_batch_pcm16(n_clips, seconds, seed=synth.SEED_C4, distinct=min(n_clips, DISTINCT))
+        jobs = [("batch", clips[i], nr, norm, n_mels) for i in range(n_clips)]
+        warm = ("batch", clips[0][: SR * 2], nr, norm, n_mels)
     if cores <= 1:
-        _cpu_one((clips[0][: SR * 2], nr, norm, n_mels))  # warm-up (imports, FFT plans)
+        _cpu_one(warm)  # imports, FFT plans
         t0 = time.perf_counter()
         for j in jobs:
             _cpu_one(j)
@@ -137,13 +212,15 @@ def cpu_baseline(workload: str, cores: int, n_clips: int, seconds: float) -> dic
         import multiprocessing as mp
 
         with mp.get_context("fork").Pool(cores) as pool:
-            pool.map(_cpu_one, [(clips[0][: SR * 2], nr, norm, n_mels)] * cores)  # warm every worker
+            pool.map(_cpu_one, [warm] * cores)  # warm every worker
             t0 = time.perf_counter()
             pool.map(_cpu_one, jobs, chunksize=1)
             dt = time.perf_counter() - t0
+    what = ("audioop + np.interp + Silero-shaped network in numpy + noisereduce + faster-whisper FeatureExtractor restated" if full
+            else "noisereduce + faster-whisper FeatureExtractor restated")
     return {"value": n_clips * seconds / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{n_clips} x {seconds:g} s clips of the same synthetic workload, numpy/scipy oracle port "
-                      f"(noisereduce + faster-whisper FeatureExtractor restated; the reference itself is numpy/scipy), {dt:.2f} s of wall time"}
+            "sample": f"{n_clips} x {seconds:g} s clips of the same synthetic workload, numpy/scipy oracle port ({what}; the reference itself is "
+                      f"numpy/scipy around those packages), {dt:.2f} s of wall time"}
 
 
 def run_reference(args) -> None:
@@ -151,14 +228,15 @@ def run_reference(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    desc, clips_per_gpu, seconds, nr, norm, n_mels = WORKLOADS[args.workload]
+    wl = args.workload if args.workload in STT else "stt_batch"
+    desc, clips_per_gpu, seconds, nr, norm, n_mels, _full = STT[wl]
     cores = os.cpu_count() or 1
     n_clips = max(cores, 8)
     sample_s = 60.0 if seconds >= 60.0 else seconds
     vals = []
     base = None
     for i in range(args.warmup + args.steps):
-        base = cpu_baseline(args.workload, cores, n_clips, sample_s)
+        base = cpu_baseline(wl, cores, n_clips, sample_s)
         if i >= args.warmup:
             vals.append(base["value"])
     v = float(np.mean(vals))
@@ -166,391 +244,432 @@ def run_reference(args) -> None:
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1000.0 * n_clips * sample_s / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64/f32",
             "data": "synthetic", "config": {"workload": desc, "clips_per_step": n_clips, "seconds_per_clip": sample_s, "host_cores": cores,
-                                            "note": "bounded sample of the GPU arm's workload; CPU throughput does not depend on the batch size"},
+                                            "note": f"bounded sample ({n_clips} clips per step instead of {clips_per_gpu} per GPU) of the GPU arm's workload; the metric "
+                                                    "is per audio-second and CPU throughput does not depend on the batch size"},
             "cpu_baseline": base, "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
-def bind_to_gpu_numa_node(torch, local: int):
-    """Run this rank (and first-touch its pinned staging buffers) on the NUMA node its GPU hangs off: with several ranks
-    per box the host<->device copies of the e2e leg otherwise cross the socket interconnect.  Returns the node or None."""
+def bind_to_gpu_numa_node(torch, local: int) -> dict:
+    """Run this rank (and first-touch its pinned staging buffers) on the CPUs next to its GPU: with several ranks per box the
+    host<->device copies of the e2e leg otherwise cross the socket interconnect.  NVML's affinity first, sysfs second; the
+    outcome (or the reason nothing was bound) goes into the JSON line."""
+    allowed = os.sched_getaffinity(0)
+    info = {"method": None, "numa_node": None, "cpus_bound": None, "cpus_allowed": len(allowed)}
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        p = torch.cuda.get_device_properties(local)
+        h = None
+        try:
+            h = pynvml.nvmlDeviceGetHandleByPciBusId(f"{p.pci_domain_id:08x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0".encode())
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (max(allowed) // 64) + 1)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1} & allowed
+        try:
+            info["numa_node"] = int(pynvml.nvmlDeviceGetNumaNodeId(h))
+        except Exception:
+            pass
+        if cpus and len(cpus) < len(allowed):
+            os.sched_setaffinity(0, cpus)
+            info.update(method="nvml cpu affinity", cpus_bound=len(cpus))
+            return info
+        info["method"] = "nvml: the GPU's affinity covers every allowed CPU (single NUMA domain visible)"
+        return info
+    except Exception as e:
+        info["method"] = f"nvml unavailable ({type(e).__name__})"
     try:
         p = torch.cuda.get_device_properties(local)
         bus = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
         node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
         if node < 0:
-            return None
+            info["method"] += "; sysfs numa_node = -1 (the VM exposes no NUMA topology)"
+            return info
         cpus = set()
         for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
             a, _, b = part.partition("-")
             cpus.update(range(int(a), int(b or a) + 1))
-        cpus &= os.sched_getaffinity(0)
-        if not cpus:
-            return None
-        os.sched_setaffinity(0, cpus)
-        return node
-    except Exception:
-        return None
+        cpus &= allowed
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            info.update(method="sysfs numa_node", numa_node=node, cpus_bound=len(cpus))
+    except Exception as e:
+        info["method"] += f"; sysfs unavailable ({type(e).__name__})"
+    return info
 
 
-# ----------------------------------------------------------------------------- GPU arm
-def run_gpu(args) -> None:
-    import torch
-    import torch.distributed as dist
+# ----------------------------------------------------------------------------- GPU arm plumbing
+class Ctx:
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
 
-    from open_speech_b200 import _native as N
-    from open_speech_b200 import synth
-    from open_speech_b200.batch import SttFrontEnd
+        from open_speech_b200 import _native as N
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    N.require_gpu()  # no device: RuntimeError here, there is nothing to fall back to
-    torch.cuda.set_device(local)
-    numa = bind_to_gpu_numa_node(torch, local)  # also at N=1: a process started on the far socket pins its staging buffers there
-    N.require_gpu()
-    N.check(N.lib().osb_init(local))
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        self.torch, self.dist, self.N = torch, dist, N
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        N.require_gpu()  # no device: RuntimeError here, there is nothing to fall back to
+        torch.cuda.set_device(self.local)
+        self.numa = bind_to_gpu_numa_node(torch, self.local)
+        N.check(N.lib().osb_init(self.local))
+        if self.world > 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+        self.peak, self.peak_src = load_peaks()
 
-    desc, clips, seconds, nr, norm, n_mels = WORKLOADS[args.workload]
-    clips = args.clips or clips
-    n = int(seconds * SR)
-    fe = SttFrontEnd(n_mels=n_mels, sample_rate=SR, noise_reduce=nr, normalize=norm)
-    nf = fe.frames(n)
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
 
-    # synthetic input of the config's shape, generated on the host, pinned; each rank its own shard (weak scaling)
-    host_np = synth.clip_batch_pcm16(clips, seconds, seed=synth.SEED_C4 + 1000 * rank, extra_noise_rms=0.01 if nr else 0.0, distinct=8)
-    pcm_host = torch.from_numpy(host_np).pin_memory()
-    pcm_dev = torch.empty_like(pcm_host, device="cuda")
-    pcm_dev.copy_(pcm_host)
-    mel_dev = torch.empty((clips, n_mels, nf), dtype=torch.float32, device="cuda")
-    mel_host = torch.empty((clips, n_mels, nf), dtype=torch.float32).pin_memory()
-    audio_s_per_step = clips * seconds
-    h2d_bytes, d2h_bytes = pcm_host.numel() * 2, mel_host.numel() * 4
+    def max_over_ranks(self, x: float) -> float:
+        if self.world == 1:
+            return float(x)
+        t = self.torch.tensor([x], dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(fn, steps):
+    def timed(self, fn, steps: int, warmup: int = 3) -> float:
+        """ms per step: CUDA events on the current stream, barrier + synchronize both sides, max over ranks."""
+        torch = self.torch
+        for _ in range(warmup):
+            fn()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
+        self.barrier()
         ev0.record()
         for _ in range(steps):
             fn()
         ev1.record()
         torch.cuda.synchronize()
-        ms = ev0.elapsed_time(ev1)
-        if world > 1:
-            t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        barrier()
+        ms = self.max_over_ranks(ev0.elapsed_time(ev1) / steps)
+        self.barrier()
         return ms
 
-    # ---- warm-up (also sizes the stream-ordered scratch pool)
-    for _ in range(max(args.warmup, 3)):
-        fe(pcm_dev, mel_dev)
-    torch.cuda.synchronize()
+    def wall(self, fn, steps: int, warmup: int = 2) -> float:
+        """ms per step of a synchronous host-to-host call, max over ranks."""
+        for _ in range(warmup):
+            fn()
+        self.barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            fn()
+        ms = self.max_over_ranks((time.perf_counter() - t0) * 1e3 / steps)
+        self.barrier()
+        return ms
 
-    # ---- resident-input throughput, per-kernel events on the launching stream, clocks sampled during the region
-    sampler = ClockSampler(local)
-    launches0 = N.lib().osb_launch_count()
-    N.check(N.lib().osb_profile_enable(1))
-    if rank == 0:
-        sampler.start()
-    ms_total = timed(lambda: fe(pcm_dev, mel_dev), args.steps)
-    clocks = sampler.stop() if rank == 0 else None
-    buf = ctypes.create_string_buffer(1 << 16)
-    N.check(N.lib().osb_profile_report(buf, len(buf)))
-    N.check(N.lib().osb_profile_enable(0))
-    kern = json.loads(buf.value.decode())
-    launches = int(N.lib().osb_launch_count() - launches0)
-    ms_step = ms_total / args.steps
-    value = world * audio_s_per_step / (ms_step / 1000.0)
+    def profile(self, fn, steps: int) -> dict:
+        """per-kernel CUDA-event ms per step (library hook, events on the launching stream)."""
+        N = self.N
+        N.check(N.lib().osb_profile_enable(1))
+        for _ in range(steps):
+            fn()
+        buf = ctypes.create_string_buffer(1 << 16)
+        N.check(N.lib().osb_profile_report(buf, len(buf)))
+        N.check(N.lib().osb_profile_enable(0))
+        return {k: {"ms": v["ms"] / steps, "launches": v["launches"] / steps} for k, v in json.loads(buf.value.decode()).items()}
 
-    # ---- end to end: pinned host clips in, host features out, copies inside the timed region
-    # (osb_stt_frontend_host: pinned host pointers; H2D / kernels / D2H pipelined over 4 clip groups inside the library)
-    del pcm_dev, mel_dev
-    torch.cuda.empty_cache()
+    def close(self):
+        if self.world > 1:
+            self.dist.destroy_process_group()
 
-    def e2e_step():
-        N.call("osb_stt_frontend_host", pcm_host.data_ptr(), n, clips, n, SR, int(nr), int(norm), n_mels, mel_host.data_ptr())
 
-    for _ in range(2):
-        e2e_step()
-    e2e_steps = max(1, min(args.steps, 5))
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_step()  # synchronous: returns when the features are in host memory
-    ms_e2e = (time.perf_counter() - t0) * 1e3 / e2e_steps
-    if world > 1:
-        t = torch.tensor([ms_e2e], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_e2e = float(t.item())
-    e2e_value = world * audio_s_per_step / (ms_e2e / 1000.0)
-    checksum = float(mel_host[0, :, :16].double().sum())  # the D2H result is really read
+def _vad_session():
+    from open_speech_b200.vad.silero import VadSession
 
-    # ---- one clip, host bytes in -> host features out (BASELINE configs[0] is literally a single clip): latency, not throughput
-    single = None
-    if rank == 0:
-        lat = []
-        for i in range(60):
-            t0 = time.perf_counter()
-            N.call("osb_stt_frontend_host", pcm_host.data_ptr(), n, 1, n, SR, int(nr), int(norm), n_mels, mel_host.data_ptr())
-            lat.append((time.perf_counter() - t0) * 1e3)
-        lat = sorted(lat[10:])
-        single = {"p50_ms": lat[len(lat) // 2], "p99_ms": lat[-1], "x_realtime_p50": seconds / (lat[len(lat) // 2] / 1e3)}
+    return VadSession()  # seeded random-init weights (BASELINE configs[1] allows; silero-vad is not installed)
 
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
 
-    # ---- roofline of the dominant kernel (CUDA-event time per launch from the timed region)
-    peak, peak_src = load_peaks()
-    dom = max(kern.items(), key=lambda kv: kv[1]["ms"])
-    dom_name, dom_ms = dom[0], dom[1]["ms"] / max(1, dom[1]["launches"])
-    stage_bytes = DENOISE_BYTES_PER_AUDIO_S if dom_name.startswith("k_nr_") else ALG_BYTES_PER_AUDIO_S[args.workload]
-    dom_alg = stage_bytes * audio_s_per_step  # one launch covers the whole per-GPU batch
-    achieved = dom_alg / (dom_ms / 1000.0) / 1e9
-    chain_alg = ALG_BYTES_PER_AUDIO_S[args.workload] * audio_s_per_step
-    chain_gbs = chain_alg / (ms_step / 1000.0) / 1e9
+# ----------------------------------------------------------------------------- STT chains (stt_batch, c1, stt_full)
+def stt_setup(ctx: Ctx, workload: str, clips: int):
+    torch, N = ctx.torch, ctx.N
+    from open_speech_b200.batch import SttFrontEnd, SttFull
+
+    desc, dclips, seconds, nr, norm, n_mels, full = STT[workload]
+    clips = clips or dclips
+    if full:
+        host_np = ulaw_clips(clips, seconds, ctx.rank)
+        op = SttFull(_vad_session(), fmt="g711_ulaw", from_rate=8000, linear_chunk=160, n_mels=n_mels, noise_reduce=nr, normalize=norm)
+    else:
+        host_np = make_clips(workload, clips, seconds, ctx.rank, nr)
+        op = SttFrontEnd(n_mels=n_mels, sample_rate=SR, noise_reduce=nr, normalize=norm)
+    wire_host = torch.from_numpy(host_np).pin_memory()
+    wire_dev = wire_host.cuda()
+    n16 = int(seconds * SR)
+    nf = N.lib().osb_logmel_frames(n16)
+    if full:
+        run = lambda: op(wire_dev)  # noqa: E731
+    else:
+        mel_dev = torch.empty((clips, n_mels, nf), dtype=torch.float32, device="cuda")
+        run = lambda: op(wire_dev, mel_dev)  # noqa: E731
+    return dict(desc=desc, clips=clips, seconds=seconds, nr=nr, norm=norm, n_mels=n_mels, full=full, op=op, host_np=host_np, wire_host=wire_host,
+                wire_dev=wire_dev, run=run, n16=n16, nf=nf, audio_s=clips * seconds)
+
+
+def stt_e2e(ctx: Ctx, s: dict, steps: int, with_floor: bool):
+    """host buffers in -> host results out through the C ABI (copies inside the timed region)."""
+    torch, N = ctx.torch, ctx.N
+    clips, n_mels, nf, n16 = s["clips"], s["n_mels"], s["nf"], s["n16"]
+    mel_host = torch.empty((clips, n_mels, nf), dtype=torch.float32).pin_memory()
+    h2d = s["wire_host"].numel() * s["wire_host"].element_size()
+    d2h = mel_host.numel() * 4
+    if s["full"]:
+        n_win, max_seg = n16 // 512, n16 // 512 // 2 + 2
+        out = {"probs": torch.empty((clips, n_win), dtype=torch.float32).pin_memory(), "segments": torch.empty((clips, max_seg, 2), dtype=torch.int32).pin_memory(),
+               "counts": torch.empty((clips,), dtype=torch.int32).pin_memory(), "mel": mel_host}
+        d2h += sum(out[k].numel() * 4 for k in ("probs", "segments", "counts"))
+        step = lambda: s["op"].run_host(s["wire_host"], out)  # noqa: E731
+    else:
+        n = s["wire_host"].shape[1]
+        step = lambda: N.call("osb_stt_frontend_host", s["wire_host"].data_ptr(), n, clips, n, SR, int(s["nr"]), int(s["norm"]), n_mels, mel_host.data_ptr())  # noqa: E731
+    ms = ctx.wall(step, steps)
+    res = {"value": ctx.world * s["audio_s"] / (ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms,
+           "checksum": float(mel_host[0, :, :16].double().sum())}  # the D2H result is really read
+    if with_floor:
+        row_in = s["wire_host"].shape[1] * s["wire_host"].element_size()
+        floor = lambda: N.call("osb_copy_floor_host", s["wire_host"].data_ptr(), row_in, mel_host.data_ptr(), d2h // clips, clips)  # noqa: E731
+        fms = ctx.wall(floor, steps)
+        res["copy_floor_ms"] = fms
+        res["copy_floor_gbps"] = ctx.world * (h2d + d2h) / (fms / 1e3) / 1e9
+        res["over_floor"] = ms / fms
+        # the drop-in as a Python caller reaches it: numpy (pageable) arrays, same C entry
+        page_in = np.array(s["host_np"], copy=True)
+        page_mel = np.empty((clips, n_mels, nf), dtype=np.float32)
+        if s["full"]:
+            pout = {"probs": np.empty((clips, n16 // 512), np.float32), "segments": np.empty((clips, n16 // 512 // 2 + 2, 2), np.int32),
+                    "counts": np.empty(clips, np.int32), "mel": page_mel}
+            pstep = lambda: s["op"].run_host(page_in, pout)  # noqa: E731
+        else:
+            n = page_in.shape[1]
+            pstep = lambda: N.call("osb_stt_frontend_host", N.ptr(page_in), n, clips, n, SR, int(s["nr"]), int(s["norm"]), n_mels, N.ptr(page_mel))  # noqa: E731
+        res["pageable_ms"] = ctx.wall(pstep, max(1, steps // 2), warmup=1)
+    return res, step, mel_host
+
+
+def stt_roofline(ctx: Ctx, workload: str, s: dict, ms_step: float, kern: dict) -> dict:
+    dom_name, dom = max(kern.items(), key=lambda kv: kv[1]["ms"])
+    dom_ms = dom["ms"] / max(1.0, dom["launches"])
+    alg = ALG_BYTES_PER_AUDIO_S[workload] * s["audio_s"]
+    gbs = alg / (ms_step / 1e3) / 1e9
+    kio = kernel_io_bytes_per_audio_s(dom_name, s["seconds"], s["nr"])
+    kbytes = kio * s["audio_s"] / max(1.0, dom["launches"]) if kio else None
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
-        traffic = json.load(open(tp)).get(args.workload, {}).get(dom_name)
-    roofline = {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src, "ms_per_launch": dom_ms, "algorithmic_bytes_per_launch": dom_alg,
-                "share_of_step": dom[1]["ms"] / ms_total,
-                "chain": {"algorithmic_bytes_per_step": chain_alg, "achieved": chain_gbs, "frac": chain_gbs / peak},
-                "kernels_ms_per_step": {k: v["ms"] / args.steps for k, v in sorted(kern.items(), key=lambda kv: -kv[1]["ms"])}}
+        traffic = json.load(open(tp)).get(workload, {}).get(dom_name)
+    r = {"bound": "hbm", "achieved": gbs, "peak": ctx.peak, "unit": "GB/s", "frac": gbs / ctx.peak, "traffic": traffic, "peak_source": ctx.peak_src,
+         "algorithmic_bytes_per_step": alg, "what": "whole step: SURVEY 8(d) algorithmic bytes of the chain / step time",
+         "kernel": dom_name, "kernel_ms_per_launch": dom_ms, "kernel_share_of_step": dom["ms"] / ms_step,
+         "kernel_io_bytes_per_launch": kbytes,
+         "kernel_frac": (kbytes / (dom_ms / 1e3) / 1e9 / ctx.peak) if kbytes else None,
+         "kernels_ms_per_step": {k: round(v["ms"], 4) for k, v in sorted(kern.items(), key=lambda kv: -kv[1]["ms"])}}
+    return r
 
-    # ---- CPU baseline beside it (bounded sample, single thread = the reference's execution model)
+
+def bench_stt(ctx: Ctx, args, workload: str, extra: dict | None) -> None:
+    torch, N = ctx.torch, ctx.N
+    s = stt_setup(ctx, workload, args.clips)
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
+        s["run"]()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(ctx.local)
+    launches0 = N.lib().osb_launch_count()
+    if ctx.rank == 0:
+        sampler.start()
+    ms_step = ctx.timed(s["run"], args.steps, warmup=0)
+    clocks = sampler.stop() if ctx.rank == 0 else None
+    launches = int(N.lib().osb_launch_count() - launches0)
+    kern = ctx.profile(s["run"], 2)  # per-kernel event pairs outside the timed region (the events themselves cost launch slots)
+    value = ctx.world * s["audio_s"] / (ms_step / 1e3)
+    e2e, e2e_step, mel_host = stt_e2e(ctx, s, max(1, min(args.steps, 5)), with_floor=True)
+
+    single = None
+    if ctx.rank == 0 and not s["full"]:  # BASELINE configs[0] is literally a single clip: latency, not throughput
+        n = s["wire_host"].shape[1]
+        lat = []
+        for _ in range(60):
+            t0 = time.perf_counter()
+            N.call("osb_stt_frontend_host", s["wire_host"].data_ptr(), n, 1, n, SR, int(s["nr"]), int(s["norm"]), s["n_mels"], mel_host.data_ptr())
+            lat.append((time.perf_counter() - t0) * 1e3)
+        lat = sorted(lat[10:])
+        single = {"p50_ms": lat[len(lat) // 2], "p99_ms": lat[-1], "x_realtime_p50": s["seconds"] / (lat[len(lat) // 2] / 1e3)}
+    if ctx.rank != 0:
+        return
     cpu = None
-    if not args.no_cpu:
-        cpu = cpu_baseline(args.workload, 1, 24 if seconds >= 60 else 48, seconds)  # several seconds of single-thread CPU work
-
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+    if not args.no_cpu:  # bounded sample, single thread = the reference's execution model (it runs this path on the event-loop thread)
+        cpu = cpu_baseline(workload, 1, 8 if s["full"] else (24 if s["seconds"] >= 60 else 48), s["seconds"])
+    h2d_mb = s["wire_host"].numel() * s["wire_host"].element_size() / 1e6
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": ctx.world, "steps": args.steps, "warmup": warm,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": desc, "clips_per_gpu": clips, "seconds_per_clip": seconds, "sample_rate": SR, "n_mels": n_mels,
-                       "noise_reduce": nr, "normalize": norm, "global_clips": clips * world, "parallelism": f"clip-sharded x{world}, no collective", "numa_node_rank0": numa,
-                       "l2": f"inputs larger than L2 ({h2d_bytes / 1e6:.0f} MB of pcm16 per GPU per step vs 126 MB)"},
-            "clocks": clocks, "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
-                                      "ms_per_step": ms_e2e, "checksum": checksum},
-            "single_clip_latency": single, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu}
+            "config": {"workload": s["desc"], "clips_per_gpu": s["clips"], "seconds_per_clip": s["seconds"], "sample_rate": SR, "n_mels": s["n_mels"],
+                       "noise_reduce": s["nr"], "normalize": s["norm"], "global_clips": s["clips"] * ctx.world,
+                       "parallelism": f"clip-sharded x{ctx.world}, no collective", "host_binding_rank0": ctx.numa,
+                       "clips": f"{DISTINCT} distinct seeded synthetic clips per rank, tiled to {s['clips']} (distinct addresses, full traffic)",
+                       "l2": f"inputs + outputs larger than L2 ({h2d_mb:.0f} MB in, {s['clips'] * s['n_mels'] * s['nf'] * 4 / 1e6:.0f} MB out per GPU per step vs 126 MB)"},
+            "clocks": clocks, "e2e": e2e, "single_clip_latency": single, "gpu_launches": launches,
+            "roofline": stt_roofline(ctx, workload, s, ms_step, kern), "cpu_baseline": cpu}
+    if extra is not None:
+        line["configs"] = extra
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
 
 
-
-# ----------------------------------------------------------------------------- other BASELINE configs (single GPU)
-def _gpu_setup():
-    import torch
-
-    from open_speech_b200 import _native as N
-
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    N.require_gpu()
-    N.check(N.lib().osb_init(local))
-    return torch, N
-
-
-def _time_ms(torch, fn, steps, warmup=3):
-    for _ in range(warmup):
-        fn()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(steps):
-        fn()
-    e1.record()
-    torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / steps
+def compact_stt(ctx: Ctx, workload: str, steps: int) -> dict:
+    s = stt_setup(ctx, workload, 0)
+    ms = ctx.timed(s["run"], steps)
+    kern = ctx.profile(s["run"], 1)
+    e2e, _, _ = stt_e2e(ctx, s, 3, with_floor=False)
+    alg = ALG_BYTES_PER_AUDIO_S[workload] * s["audio_s"]
+    top = sorted(kern.items(), key=lambda kv: -kv[1]["ms"])[:8]
+    return {"workload": s["desc"], "value": ctx.world * s["audio_s"] / (ms / 1e3), "unit": UNIT, "ms_per_step": ms, "steps": steps,
+            "e2e_value": e2e["value"], "e2e_ms_per_step": e2e["ms_per_step"], "h2d_bytes_per_step": e2e["h2d_bytes_per_step"],
+            "d2h_bytes_per_step": e2e["d2h_bytes_per_step"], "roofline_frac": alg / (ms / 1e3) / 1e9 / ctx.peak,
+            "kernels_ms_per_step": {k: round(v["ms"], 4) for k, v in top}}
 
 
-def _profile(N, fn, steps):
-    N.check(N.lib().osb_profile_enable(1))
-    for _ in range(steps):
-        fn()
-    buf = ctypes.create_string_buffer(1 << 16)
-    N.check(N.lib().osb_profile_report(buf, len(buf)))
-    N.check(N.lib().osb_profile_enable(0))
-    return {k: v["ms"] / steps for k, v in json.loads(buf.value.decode()).items()}
-
-
-def run_vad(args):
-    """BASELINE configs[1]: Silero-shaped VAD scoring + segmenting; (i) one 1 h stream, (ii) 256 streams x 10 min."""
-    torch, N = _gpu_setup()
+# ----------------------------------------------------------------------------- BASELINE configs[1]: VAD
+def vad_run(ctx: Ctx, streams: int, seconds: float, steps: int) -> dict:
+    """Silero-shaped VAD scoring + segmenting: (i) `streams` independent streams of `seconds` each, (ii) one 1 h stream."""
+    torch = ctx.torch
     from open_speech_b200 import synth
     from open_speech_b200.batch import VadBatch
 
-    peak, src = load_peaks()
-    vb = VadBatch()
-    one = torch.from_numpy(np.tile(synth.clip_pcm16(600.0, seed=synth.SEED_C2), 6)[None, :]).cuda()      # 1 h = 57.6 M samples
-    ms_one = _time_ms(torch, lambda: vb(one), max(1, args.steps // 3), warmup=1)
-    streams = args.clips or 256
-    many = torch.from_numpy(np.tile(synth.clip_pcm16(600.0, seed=synth.SEED_C2 + 1)[None, :], (streams, 1))).cuda()
-    ms_many = _time_ms(torch, lambda: vb(many), max(1, args.steps // 3), warmup=1)
-    kern = _profile(N, lambda: vb(many), 1)
-    audio_s = streams * 600.0
-    v = audio_s / (ms_many / 1e3)
-    alg = 32125.0 * audio_s
-    line = {"metric": METRIC, "value": v, "unit": UNIT, "n_gpus": 1, "steps": max(1, args.steps // 3), "warmup": 1, "ms_per_step": ms_many,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"BASELINE configs[1]: Silero-shaped VAD 512-sample scoring + segmenting, {streams} streams x 600 s (seeded random-init weights)",
-                       "single_stream_1h": {"ms": ms_one, "x_realtime": 3600.0 / (ms_one / 1e3), "windows": 112500}},
-            "roofline": {"bound": "hbm", "achieved": alg / (ms_many / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
-                         "frac": alg / (ms_many / 1e3) / 1e9 / peak, "traffic": None, "peak_source": src,
-                         "note": "compute + serial-latency bound by arithmetic (SURVEY 8(d)); HBM fraction reported for completeness",
-                         "kernels_ms_per_step": dict(sorted(kern.items(), key=lambda kv: -kv[1]))}}
-    print(json.dumps(line), flush=True)
+    vb = VadBatch(_vad_session())
+    reps = max(1, int(round(seconds / 600.0)))
+    base = torch.from_numpy(synth.clip_pcm16(min(seconds, 600.0), seed=synth.SEED_C2 + 1 + ctx.rank)).cuda()
+    many = base.repeat(reps).unsqueeze(0).repeat(streams, 1).contiguous()   # device-side tiling: plumbing, not the path
+    ms_many = ctx.timed(lambda: vb(many), steps, warmup=2)
+    kern = ctx.profile(lambda: vb(many), 1)
+    audio_s = streams * many.shape[1] / SR
+    del many
+    torch.cuda.empty_cache()
+    one = torch.from_numpy(synth.clip_pcm16(600.0, seed=synth.SEED_C2)).cuda().repeat(6).unsqueeze(0).contiguous()  # 1 h = 57.6 M samples
+    ms_one = ctx.timed(lambda: vb(one), max(1, steps // 2), warmup=1)
+    alg = VAD_ALG_BYTES_PER_AUDIO_S * audio_s
+    front = sum(v["ms"] for k, v in kern.items() if "gemm" in k or "front" in k)
+    recur = sum(v["ms"] for k, v in kern.items() if "recur" in k)
+    return {"workload": f"BASELINE configs[1]: Silero-shaped VAD 512-sample scoring + segmenting, {streams} streams x {audio_s / streams:.0f} s per GPU "
+                        "(seeded random-init weights: silero-vad is not installed)",
+            "value": ctx.world * audio_s / (ms_many / 1e3), "unit": UNIT, "ms_per_step": ms_many, "steps": steps,
+            "front_ms": front, "recurrence_ms": recur,
+            "single_stream_1h": {"ms": ms_one, "x_realtime": 3600.0 / (ms_one / 1e3), "windows": 112500},
+            "roofline_frac": alg / (ms_many / 1e3) / 1e9 / ctx.peak,
+            "roofline_note": "compute + serial-latency bound by arithmetic (SURVEY 8(d)); the HBM fraction is reported for completeness",
+            "kernels_ms_per_step": {k: round(v["ms"], 4) for k, v in sorted(kern.items(), key=lambda kv: -kv[1]["ms"])}}
 
 
-def run_realtime(args):
-    """BASELINE configs[2]: 1024 concurrent G.711 mu-law 8 kHz streams, 20 ms chunks -> pcm16 -> 16 kHz (+VAD): p50/p99 chunk latency.
+# ----------------------------------------------------------------------------- BASELINE configs[2]: realtime ticks
+def realtime_run(ctx: Ctx, S: int, ticks: int) -> dict:
+    """1024 concurrent G.711 mu-law 8 kHz streams: host wire bytes in -> host pcm16 + speech events out, per tick.
 
-    Reference-exact semantics: a 320-sample chunk holds no full 512-sample VAD window, so the reference's VAD returns
-    0.0 without running; variant B feeds 40 ms chunks (640 samples = 1 window) so that the VAD runs.
+    A  reference-exact: 20 ms chunks = 320 samples < 512, the reference's VAD scores nothing and returns 0.0
+    B  40 ms chunks (640 samples = one VAD window), the network runs every tick
+    P  the polyphase door of north_star: audioop.ulaw2lin -> resample_pcm16(8000 -> 16000), 40 ms chunks, network runs
     """
-    torch, N = _gpu_setup()
+    torch = ctx.torch
     from open_speech_b200 import synth
-    from open_speech_b200.batch import RealtimeTick, VadBatch
+    from open_speech_b200.realtime.gate import RealtimeGate
 
-    S, ticks = args.clips or 1024, 1000
+    sess = _vad_session()
     data = synth.ulaw_streams(S, 64)                     # [64, S, 160], cycled
-    host_in = torch.from_numpy(data).pin_memory()
-    host_out = torch.empty((S, 320), dtype=torch.int16).pin_memory()
-    dev_in = torch.empty((S, 160), dtype=torch.uint8, device="cuda")
-    dev_out = torch.empty((S, 320), dtype=torch.int16, device="cuda")
-    tick = RealtimeTick(S)
+    res = {}
+    for tag, chunk, poly, n_ticks in (("A_20ms_reference_exact", 160, False, ticks), ("B_40ms_vad_scored", 320, False, ticks // 2),
+                                      ("P_40ms_polyphase_vad_scored", 320, True, ticks // 2)):
+        per = chunk // 160
+        src = np.ascontiguousarray(data.reshape(64 // per, per, S, 160).transpose(0, 2, 1, 3).reshape(64 // per, S, chunk))
+        host_in = torch.from_numpy(src).pin_memory()
+        g = RealtimeGate(S, chunk, fmt="g711_ulaw", session=sess, threshold=0.5, silence_duration_ms=500, poly=poly)
+        dev_in = torch.empty((S, chunk), dtype=torch.uint8, device="cuda")
+        host_pcm = torch.empty((S, g.n_out), dtype=torch.int16).pin_memory()
+        n_ev = 0
 
-    def one(i):
-        dev_in.copy_(host_in[i % 64], non_blocking=True)
-        tick(dev_in, dev_out)
-        host_out.copy_(dev_out, non_blocking=True)
-        torch.cuda.synchronize()
+        def one(i):
+            nonlocal n_ev
+            dev_in.copy_(host_in[i % host_in.shape[0]], non_blocking=True)
+            g.tick(dev_in)
+            host_pcm.copy_(g.pcm, non_blocking=True)
+            n_ev += len(g.read_events())  # D2H of the compact list + stream synchronize
 
-    for i in range(20):
-        one(i)
-    lat = []
-    for i in range(ticks):
-        t0 = time.perf_counter()
-        one(i)
-        lat.append((time.perf_counter() - t0) * 1e3)
-    lat = np.array(lat)
-    # variant B: 40 ms chunks with the VAD (state carried per stream on the device)
-    vb = VadBatch()
-    dev_in2 = torch.empty((S, 320), dtype=torch.uint8, device="cuda")
-    dev_pcm2 = torch.empty((S, 640), dtype=torch.int16, device="cuda")
-    tick2 = RealtimeTick(S, chunk=320)
-    state = torch.zeros((S, 2, 128), dtype=torch.float32, device="cuda")
-    host_in2 = torch.from_numpy(np.ascontiguousarray(data.reshape(32, 2, S, 160).transpose(0, 2, 1, 3).reshape(32, S, 320))).pin_memory()
-    host_prob = torch.empty((S, 1), dtype=torch.float32).pin_memory()
-
-    def two(i):
-        nonlocal state
-        dev_in2.copy_(host_in2[i % 32], non_blocking=True)
-        tick2(dev_in2, dev_pcm2)
-        probs, state = vb.score(dev_pcm2, state)
-        host_prob.copy_(probs, non_blocking=True)
-        torch.cuda.synchronize()
-
-    for i in range(10):
-        two(i)
-    lat2 = []
-    for i in range(300):
-        t0 = time.perf_counter()
-        two(i)
-        lat2.append((time.perf_counter() - t0) * 1e3)
-    lat2 = np.array(lat2)
-    # CUDA-graph variant: the tick's bytes are copied into a pinned slot (host memcpy included), one graph launch, sync
-    from open_speech_b200.batch import RealtimeTickGraph
-
-    rg = RealtimeTickGraph(S)
-    for i in range(20):
-        rg.host_in.copy_(host_in[i % 64])
-        rg.run()
-    lat3 = []
-    for i in range(ticks):
-        t0 = time.perf_counter()
-        rg.host_in.copy_(host_in[i % 64])
-        rg.run()
-        lat3.append((time.perf_counter() - t0) * 1e3)
-    lat3 = np.array(lat3)
-    graph_ok = bool(torch.equal(rg.host_out, host_out)) if (ticks - 1) % 64 == (ticks - 1) % 64 else True
-    ms_dev = _time_ms(torch, lambda: tick(dev_in, dev_out), 200)
-    peak, src = load_peaks()
-    alg = 800.0 * S
-    v = S * 0.020 / (np.median(lat) / 1e3)
-    line = {"metric": METRIC, "value": v, "unit": UNIT, "n_gpus": 1, "steps": ticks, "warmup": 20, "ms_per_step": float(np.median(lat)),
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/f64", "data": "synthetic",
-            "config": {"workload": f"BASELINE configs[2]: {S} G.711 mu-law 8 kHz streams, 20 ms chunks -> pcm16 16 kHz (host bytes in -> host bytes out per tick)",
-                       "latency_ms": {"p50": float(np.percentile(lat, 50)), "p99": float(np.percentile(lat, 99)), "max": float(lat.max())},
-                       "cuda_graph_latency_ms": {"p50": float(np.percentile(lat3, 50)), "p99": float(np.percentile(lat3, 99)), "matches_stream_path": graph_ok},
-                       "variant_B_40ms_with_vad_latency_ms": {"p50": float(np.percentile(lat2, 50)), "p99": float(np.percentile(lat2, 99))},
-                       "vad_semantics": "A: reference-exact (320 samples < 512 -> VAD scores nothing, prob 0.0); B: 40 ms chunks, 1 window scored"},
-            "roofline": {"bound": "hbm", "achieved": alg / (ms_dev / 1e3) / 1e9, "peak": peak, "unit": "GB/s", "frac": alg / (ms_dev / 1e3) / 1e9 / peak,
-                         "traffic": None, "peak_source": src, "ms_per_launch": ms_dev,
-                         "note": "a tick is 0.8 MB: launch-latency bound, latency is the headline (SURVEY 8(d))"}}
-    print(json.dumps(line), flush=True)
+        for i in range(20):
+            one(i)
+        n_ev = 0
+        ctx.barrier()
+        lat = np.empty(n_ticks)
+        for i in range(n_ticks):
+            t0 = time.perf_counter()
+            one(i)
+            lat[i] = (time.perf_counter() - t0) * 1e3
+        p50, p99 = ctx.max_over_ranks(float(np.percentile(lat, 50))), ctx.max_over_ranks(float(np.percentile(lat, 99)))
+        res[tag] = {"p50_ms": p50, "p99_ms": p99, "ticks": n_ticks, "events": n_ev, "chunk_ms": chunk / 8.0,
+                    "x_realtime_p50": ctx.world * S * (chunk / 8000.0) / (p50 / 1e3)}
+    a = res["A_20ms_reference_exact"]
+    return {"workload": f"BASELINE configs[2]: {S} G.711 mu-law 8 kHz streams per GPU, per tick: host bytes in -> decode -> 16 kHz -> buffer + VAD gate -> "
+                        "host pcm16 + compact speech events out (device-resident per-stream state)",
+            "value": a["x_realtime_p50"], "unit": UNIT, "ms_per_step": a["p50_ms"], "steps": ticks, "variants": res,
+            "vad_semantics": "A: reference-exact (no full window in 20 ms: probability 0.0, no events possible); B / P: one window per 40 ms chunk is scored"}
 
 
-def run_tts(args):
-    """BASELINE configs[4]: 4096 Kokoro-shaped 24 kHz utterances: trim + peak normalise + effects chain + int16, and voice blends."""
-    torch, N = _gpu_setup()
+# ----------------------------------------------------------------------------- BASELINE configs[4]: TTS post-processing
+def tts_run(ctx: Ctx, B: int, steps: int) -> dict:
+    torch, N = ctx.torch, ctx.N
     from open_speech_b200 import synth
     from open_speech_b200.batch import TtsPost
 
-    B = args.clips or 4096
     fx = [{"type": "normalize", "target_lufs": -16}, {"type": "reverb", "room": "medium"}, {"type": "podcast_eq"}, {"type": "robot"}]
-    utts = synth.tts_batch(B, seed=synth.SEED_C5, distinct=32)
+    utts = synth.tts_batch(B, seed=synth.SEED_C5 + ctx.rank, distinct=32)
     post = TtsPost(24000, fx)
     flat, offsets, lens = post.pack(utts)
     audio_s = float(lens.sum()) / 24000.0
     d_flat, d_off, d_len = torch.from_numpy(flat).cuda(), torch.from_numpy(offsets).cuda(), torch.from_numpy(lens).cuda()
     out = torch.empty(flat.size, dtype=torch.int16, device="cuda")
     mx = int(lens.max())
-    ms = _time_ms(torch, lambda: post(d_flat, d_off, d_len, mx, out), args.steps)
-    kern = _profile(N, lambda: post(d_flat, d_off, d_len, mx, out), 2)
-    # voice blends: B blends of 2-3 packs out of 3
+    ms = ctx.timed(lambda: post(d_flat, d_off, d_len, mx, out), steps)
+    kern = ctx.profile(lambda: post(d_flat, d_off, d_len, mx, out), 1)
+    # voice blends: B blends of 2-3 packs out of 3 resident packs
     packs = torch.from_numpy(np.stack([p.reshape(-1) for p in synth.voice_packs(3)])).cuda()
     n = packs.shape[1]
     idx = torch.tensor([[0, 1, -1], [0, 1, -1], [0, 1, 2]] * (B // 3 + 1), dtype=torch.int32)[:B].contiguous().cuda()
     w = torch.tensor([[2 / 3, 1 / 3, 0], [0.5, 0.5, 0], [0.5, 1 / 3, 1 / 6]] * (B // 3 + 1), dtype=torch.float32)[:B].contiguous().cuda()
     bout = torch.empty((B, n), dtype=torch.float32, device="cuda")
     st = torch.cuda.current_stream().cuda_stream
-    ms_blend = _time_ms(torch, lambda: N.call("osb_voice_blend_dev", packs.data_ptr(), n, idx.data_ptr(), w.data_ptr(), 3, B, bout.data_ptr(), st), args.steps)
-    peak, src = load_peaks()
-    alg = 192000.0 * audio_s
-    blend_bytes = float((idx >= 0).sum().item() + B) * n * 4
-    line = {"metric": METRIC, "value": audio_s / (ms / 1e3), "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": 3, "ms_per_step": ms,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32/f64", "data": "synthetic",
-            "config": {"workload": f"BASELINE configs[4]: {B} Kokoro-shaped 24 kHz utterances ({audio_s:.0f} audio-s): trim + peak normalise + "
-                                   "[normalize, reverb medium, podcast_eq, robot] + int16; plus voice-style blends",
-                       "voice_blend": {"blends_per_s": B / (ms_blend / 1e3), "GBps": blend_bytes / (ms_blend / 1e3) / 1e9, "frac_of_hbm": blend_bytes / (ms_blend / 1e3) / 1e9 / peak}},
-            "roofline": {"bound": "hbm", "achieved": alg / (ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s", "frac": alg / (ms / 1e3) / 1e9 / peak,
-                         "traffic": None, "peak_source": src, "kernels_ms_per_step": dict(sorted(kern.items(), key=lambda kv: -kv[1]))}}
+    ms_blend = ctx.timed(lambda: N.call("osb_voice_blend_dev", packs.data_ptr(), n, idx.data_ptr(), w.data_ptr(), 3, B, bout.data_ptr(), st), steps)
+    alg = TTS_ALG_BYTES_PER_AUDIO_S * audio_s
+    # the three packs (1.5 MB) stay in L2: the HBM bytes of a blend batch are its OUTPUT only; the survey's (K+1) x 522,240 B per
+    # blend counts reads that never reach HBM here, so it is reported separately and not against the HBM peak
+    out_bytes = float(B) * n * 4
+    return {"workload": f"BASELINE configs[4]: {B} Kokoro-shaped 24 kHz utterances per GPU ({audio_s:.0f} audio-s): trim + peak normalise + "
+                        "[normalize, reverb medium, podcast_eq, robot] + int16; plus voice-style blends",
+            "value": ctx.world * audio_s / (ms / 1e3), "unit": UNIT, "ms_per_step": ms, "steps": steps,
+            "roofline_frac": alg / (ms / 1e3) / 1e9 / ctx.peak,
+            "voice_blend": {"blends_per_s": ctx.world * B / (ms_blend / 1e3), "hbm_GBps_output_only": out_bytes / (ms_blend / 1e3) / 1e9,
+                            "frac_of_hbm": out_bytes / (ms_blend / 1e3) / 1e9 / ctx.peak,
+                            "survey_bytes_GBps_incl_L2_resident_reads": float((idx >= 0).sum().item() + B) * n * 4 / (ms_blend / 1e3) / 1e9},
+            "kernels_ms_per_step": {k: round(v["ms"], 4) for k, v in sorted(kern.items(), key=lambda kv: -kv[1]["ms"])}}
+
+
+def print_sub(ctx: Ctx, args, res: dict, dtype: str) -> None:
+    if ctx.rank != 0:
+        return
+    line = {"metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": ctx.world, "steps": res.get("steps", args.steps), "warmup": 3,
+            "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": dtype, "data": "synthetic",
+            "config": {"workload": res.pop("workload")}, "roofline": {"bound": "hbm", "frac": res.get("roofline_frac"), "peak": ctx.peak, "unit": "GB/s",
+                                                                       "peak_source": ctx.peak_src, "traffic": None}, "detail": res}
     print(json.dumps(line), flush=True)
 
-
-EXTRA = {"vad": run_vad, "realtime": run_realtime, "tts": run_tts}
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--workload", default="stt_batch", choices=sorted(WORKLOADS) + ["vad", "realtime", "tts"])
+    ap.add_argument("--workload", default="default", choices=["default"] + sorted(STT) + ["vad", "realtime", "tts"])
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--clips", type=int, default=0, help="clips per GPU (default: the config's 256)")
+    ap.add_argument("--clips", type=int, default=0, help="clips / streams / utterances per GPU (default: the config's)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-extra", action="store_true", help="default workload only: skip the compact results of the other configs")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -561,10 +680,32 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
                "--master-port", "29517", os.path.abspath(__file__)] + sys.argv[1:]
         sys.exit(subprocess.call(cmd))
-    if args.workload in EXTRA:
-        EXTRA[args.workload](args)
-        return
-    run_gpu(args)
+    ctx = Ctx()
+    try:
+        if args.workload == "vad":
+            print_sub(ctx, args, vad_run(ctx, args.clips or 256, 3600.0, max(1, args.steps // 3)), "f32 (bf16x3 tensor-core front)")
+        elif args.workload == "realtime":
+            print_sub(ctx, args, realtime_run(ctx, args.clips or 1024, 3000), "u8/f64")
+        elif args.workload == "tts":
+            print_sub(ctx, args, tts_run(ctx, args.clips or 4096, args.steps), "f32/f64")
+        elif args.workload in STT:
+            bench_stt(ctx, args, args.workload, None)
+        else:
+            extra = None
+            if not args.no_extra:
+                torch = ctx.torch
+                extra = {}
+                for name, fn in (("stt_full", lambda: compact_stt(ctx, "stt_full", 5)), ("c1", lambda: compact_stt(ctx, "c1", 10)),
+                                 ("vad", lambda: vad_run(ctx, 256, 3600.0, 2)), ("realtime", lambda: realtime_run(ctx, 1024, 3000)),
+                                 ("tts", lambda: tts_run(ctx, 4096, 5))):
+                    t0 = time.perf_counter()
+                    extra[name] = fn()
+                    extra[name]["bench_wall_s"] = round(time.perf_counter() - t0, 1)
+                    torch.cuda.synchronize()
+                    torch.cuda.empty_cache()
+            bench_stt(ctx, args, "stt_batch", extra)
+    finally:
+        ctx.close()
 
 
 if __name__ == "__main__":

@@ -158,6 +158,8 @@ int osb_stt_frontend_dev(const int16_t* d_pcm, int64_t n, int64_t batch, int64_t
                          int normalize, int n_mels, float* d_mel, void* stream);
 int osb_stt_frontend_host(const int16_t* pcm, int64_t n, int64_t batch, int64_t stride, int sample_rate, int noise_reduce,
                           int normalize, int n_mels, float* mel);
+/* measurement aid: the H2D / D2H schedule of the *_host batch entries with no kernels in between (the floor of an end-to-end step) */
+int osb_copy_floor_host(const void* in, int64_t in_bytes_per_unit, void* out, int64_t out_bytes_per_unit, int64_t batch);
 
 /* osb_stt_full_*: the north_star chain as ONE call, no host hop between stages -- wire audio [batch][n_in] (PCM16 | ULAW | ALAW at
  * from_rate) -> decode_audio_to_pcm16 / resample_pcm16 to 16 kHz -> { SileroVAD.get_speech_segments | preprocess_stt_audio -> log-mel }.

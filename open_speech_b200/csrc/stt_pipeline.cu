@@ -281,6 +281,31 @@ int osb_stt_frontend_host(const int16_t* pcm, int64_t n, int64_t batch, int64_t 
     return gp.close(rc);
 }
 
+// Measurement aid (bench.py "e2e.copy_floor"): the copy schedule of the *_host batch entries with NO kernels in between -- H2D of every
+// group on the input stream, D2H of the same group on the output stream as soon as its H2D has landed.  What this takes is the floor of
+// any host-buffers-in / host-buffers-out step on this box; nothing is computed and `out` receives whatever the device buffer held.
+int osb_copy_floor_host(const void* in, int64_t in_bytes_per_unit, void* out, int64_t out_bytes_per_unit, int64_t batch) {
+    HostWs& ws = host_ws();
+    int rc = ws.prepare();
+    if (rc) return rc;
+    OSB_REQUIRE(in && out && in_bytes_per_unit > 0 && out_bytes_per_unit > 0 && batch > 0, "bad arguments");
+    void *di, *dout;
+    if ((rc = ws.dev_buf(0, (size_t)(batch * in_bytes_per_unit), &di)) || (rc = ws.dev_buf(1, (size_t)(batch * out_bytes_per_unit), &dout))) return rc;
+    GroupPipe gp(ws);
+    if ((rc = gp.open(batch))) return rc;
+    for (int g = 0; g < gp.groups && rc == OSB_OK; ++g) {
+        const int64_t c0 = gp.bounds[g], nb = gp.bounds[g + 1] - c0;
+        cudaError_t e = cudaMemcpyAsync((uint8_t*)di + c0 * in_bytes_per_unit, (const uint8_t*)in + c0 * in_bytes_per_unit, (size_t)(nb * in_bytes_per_unit),
+                                        cudaMemcpyHostToDevice, gp.s_in);
+        if (e == cudaSuccess) e = cudaEventRecord(gp.ev_in[g], gp.s_in);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(gp.s_out, gp.ev_in[g], 0);
+        if (e == cudaSuccess) e = cudaMemcpyAsync((uint8_t*)out + c0 * out_bytes_per_unit, (uint8_t*)dout + c0 * out_bytes_per_unit, (size_t)(nb * out_bytes_per_unit),
+                                                  cudaMemcpyDeviceToHost, gp.s_out);
+        if (e != cudaSuccess) rc = cuda_fail(e, "copy floor", __FILE__, __LINE__);
+    }
+    return gp.close(rc);
+}
+
 int osb_preprocess_stt_host(const int16_t* in, int64_t n, int channels, int sample_rate, int noise_reduce, int normalize,
                             float target_dbfs, int16_t* out) {
     HostWs& ws = host_ws();
