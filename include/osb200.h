@@ -111,7 +111,8 @@ int osb_normalize_gain_f32_host(const float* in, void* out, int out_pcm16, int64
  * weights_host: flat f32 blob in the order of open_speech_b200/vad/silero.py WEIGHT_LAYOUT. */
 int osb_vad_create(const float* weights_host, size_t n_floats, void** handle);
 int osb_vad_destroy(void* handle);
-/* front-end GEMM engine: 1 = tcgen05 split-bf16 tensor-core kernel (default), 0 = FP32 FFMA kernel (cross-check) */
+/* front-end engine: 2 = fused persistent tcgen05 kernel, samples -> gate pre-activations on chip (default); 1 = one tcgen05 split-bf16
+ * GEMM per layer; 0 = FP32 FFMA GEMMs (cross-check) */
 int osb_vad_set_gemm(void* handle, int use_tcgen05);
 /* batch streams, n samples each (floor(n/512) windows); d_state [batch][2][128] in/out;
  * d_probs [batch][probs_stride] out (one probability per window). */

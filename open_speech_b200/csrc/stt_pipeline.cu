@@ -198,11 +198,14 @@ int osb_stt_full_host(void* vad, const void* in, int in_fmt, int from_rate, int6
     const long long n16 = full_samples(n_in, from_rate, linear_chunk), n_win = n16 / 512;
     const size_t per_mel = (size_t)n_mels * osb_logmel_frames(n16);
     const size_t per_vad = vad ? ((size_t)n_win * 4 + (size_t)max_seg * 8 + 4 + 15) / 16 * 16 : 0;  // probs | segments | count, per clip
-    void *di, *dmel, *dvad;
+    void *di, *dmel, *dvad, *dpcm = nullptr;
     if ((rc = ws.dev_buf(0, (size_t)batch * n_in * es + 16, &di)) || (rc = ws.dev_buf(1, (size_t)batch * per_mel * 4, &dmel)) ||
         (rc = ws.dev_buf(2, (size_t)batch * (per_vad ? per_vad : 16) + 16, &dvad))) return rc;
-    // VAD results of the whole batch, planar on the device: probs [batch][n_win] | segments [batch][max_seg][2] | counts [batch]
-    float* d_probs = (float*)dvad;
+    // the VAD branch is a serial chain per stream whose cost does not shrink with the group (1,875 dependent steps per 60 s, whatever the
+    // number of streams): it runs ONCE over the whole batch behind the last group, on the resampled pcm16 that every group leaves in d_pcm,
+    // while the features of the last groups are still on their way out
+    if (vad && (rc = ws.dev_buf(3, (size_t)batch * n16 * 2 + 16, &dpcm))) return rc;
+    float* d_probs = (float*)dvad;  // planar: probs [batch][n_win] | segments [batch][max_seg][2] | counts [batch]
     int32_t* d_segs = (int32_t*)(d_probs + (size_t)batch * n_win);
     int32_t* d_cnt = d_segs + (size_t)batch * max_seg * 2;
     GroupPipe gp(ws);
@@ -216,21 +219,23 @@ int osb_stt_full_host(void* vad, const void* in, int in_fmt, int from_rate, int6
         if (e == cudaSuccess) e = cudaEventRecord(gp.ev_in[g], gp.s_in);
         if (e == cudaSuccess) e = cudaStreamWaitEvent(ws.stream, gp.ev_in[g], 0);
         if (e != cudaSuccess) { rc = cuda_fail(e, "h2d group", __FILE__, __LINE__); break; }
-        rc = osb_stt_full_dev(vad, din, in_fmt, from_rate, n_in, nb, n_in, linear_chunk, noise_reduce, normalize, n_mels, vad_threshold, min_speech_ms,
-                              silence_ms, nullptr, vad ? d_probs + c0 * n_win : nullptr, vad ? d_segs + c0 * max_seg * 2 : nullptr,
-                              vad ? d_cnt + c0 : nullptr, max_seg, dm, ws.stream);
+        rc = osb_stt_full_dev(nullptr, din, in_fmt, from_rate, n_in, nb, n_in, linear_chunk, noise_reduce, normalize, n_mels, vad_threshold, min_speech_ms,
+                              silence_ms, dpcm ? (int16_t*)dpcm + c0 * n16 : nullptr, nullptr, nullptr, nullptr, 0, dm, ws.stream);
         if (rc) break;
         e = cudaEventRecord(gp.ev_done[g], ws.stream);
         if (e == cudaSuccess) e = cudaStreamWaitEvent(gp.s_out, gp.ev_done[g], 0);
         if (e == cudaSuccess) e = cudaMemcpyAsync(mel + c0 * per_mel, dm, (size_t)nb * per_mel * 4, cudaMemcpyDeviceToHost, gp.s_out);
         if (e != cudaSuccess) { rc = cuda_fail(e, "d2h group", __FILE__, __LINE__); break; }
     }
-    if (rc == OSB_OK && vad) {  // the VAD results are small: three copies for the whole batch behind the last group
-        cudaError_t e = cudaStreamWaitEvent(gp.s_out, gp.ev_done[gp.groups - 1], 0);
-        if (e == cudaSuccess && n_win > 0) e = cudaMemcpyAsync(probs, d_probs, (size_t)batch * n_win * 4, cudaMemcpyDeviceToHost, gp.s_out);
-        if (e == cudaSuccess && max_seg > 0) e = cudaMemcpyAsync(segments, d_segs, (size_t)batch * max_seg * 8, cudaMemcpyDeviceToHost, gp.s_out);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(counts, d_cnt, (size_t)batch * 4, cudaMemcpyDeviceToHost, gp.s_out);
-        if (e != cudaSuccess) rc = cuda_fail(e, "d2h vad", __FILE__, __LINE__);
+    if (rc == OSB_OK && vad) {
+        rc = osb_stt_full_dev(vad, dpcm, OSB_FMT_PCM16, 16000, n16, batch, n16, 0, 0, 0, n_mels, vad_threshold, min_speech_ms, silence_ms, nullptr, d_probs,
+                              d_segs, d_cnt, max_seg, nullptr, ws.stream);
+        // three small copies behind the VAD kernels, on the compute stream: the output stream is still busy with features
+        cudaError_t e = cudaSuccess;
+        if (rc == OSB_OK && n_win > 0) e = cudaMemcpyAsync(probs, d_probs, (size_t)batch * n_win * 4, cudaMemcpyDeviceToHost, ws.stream);
+        if (rc == OSB_OK && e == cudaSuccess && max_seg > 0) e = cudaMemcpyAsync(segments, d_segs, (size_t)batch * max_seg * 8, cudaMemcpyDeviceToHost, ws.stream);
+        if (rc == OSB_OK && e == cudaSuccess) e = cudaMemcpyAsync(counts, d_cnt, (size_t)batch * 4, cudaMemcpyDeviceToHost, ws.stream);
+        if (rc == OSB_OK && e != cudaSuccess) rc = cuda_fail(e, "d2h vad", __FILE__, __LINE__);
     }
     return gp.close(rc);
 }

@@ -17,6 +17,7 @@
 #include <cuda_bf16.h>
 
 #include "common.cuh"
+#include "vad_front.cuh"
 
 namespace osb {
 
@@ -50,7 +51,8 @@ struct VadModel {
     // tcgen05 path: per layer, B as split-bf16 (hi, lo) tiles pre-arranged in the 128B-swizzled K-major
     // shared-memory image, [n_tile][k_chunk][plane][NT*64]
     struct Tc { uint16_t* img; int NT, n_tiles, k_chunks; } tc[6];
-    int use_tc;
+    VadFront* fused;   // weight image of the fused persistent front kernel (vad_front.cu)
+    int use_tc;        // 2: fused tcgen05 kernel (default) | 1: one tcgen05 GEMM per layer | 0: FP32 FFMA GEMMs (cross-check)
 };
 
 // ------------------------------------------------------------------ batched front GEMM
@@ -902,23 +904,27 @@ static int vad_score(VadModel* m, const void* d_audio, int fmt, int64_t n, int64
     // chunk the window axis: windows per chunk ~ 4 x 148 SMs x 128 rows, so the three GEMM shapes (3W, 2W, W rows) run
     // 12 / 8 / 4 whole waves per launch.  Larger chunks amortise the launches and the recurrence prologue (measured: x4 is
     // 9 % faster on the front than one wave) at ~0.7 GB of activations per chunk, part of which leaves L2.
-    long long T = ((long long)OSB_NUM_SMS * 128 * 4 + batch - 1) / batch;
+    // (the fused front keeps nothing but the pre-activations in HBM: 16 waves of 128-window tiles per launch, 0.6 GB)
+    long long T = ((long long)OSB_NUM_SMS * 128 * (m->use_tc == 2 ? 16 : 4) + batch - 1) / batch;
     if (T < 1) T = 1;
     if (T > n_win) T = n_win;
     const long long W = batch * T;  // windows per chunk
     Scratch scr(st);
-    float *mag, *h1, *h2, *h3, *h4, *pre;
-    OSB_CUDA(scr.alloc(&mag, (size_t)W * 5 * kMagC + 128));
-    OSB_CUDA(scr.alloc(&h1, (size_t)W * 5 * 128 + 64));
-    OSB_CUDA(scr.alloc(&h2, (size_t)W * 4 * 64 + 64));
-    OSB_CUDA(scr.alloc(&h3, (size_t)W * 3 * 64 + 64));
-    OSB_CUDA(scr.alloc(&h4, (size_t)W * 128 + 64));
+    const bool fused = m->use_tc == 2;
+    float *mag = nullptr, *h1 = nullptr, *h2 = nullptr, *h3 = nullptr, *h4 = nullptr, *pre;
     OSB_CUDA(scr.alloc(&pre, (size_t)W * kGates + 64));
-    // zero once: the padding rows/channels are never written by the GEMMs
-    OSB_CUDA(cudaMemsetAsync(mag, 0, ((size_t)W * 5 * kMagC + 128) * 4, st));
-    OSB_CUDA(cudaMemsetAsync(h1, 0, ((size_t)W * 5 * 128 + 64) * 4, st));
-    OSB_CUDA(cudaMemsetAsync(h2, 0, ((size_t)W * 4 * 64 + 64) * 4, st));
-    OSB_CUDA(cudaMemsetAsync(h3, 0, ((size_t)W * 3 * 64 + 64) * 4, st));
+    if (!fused) {
+        OSB_CUDA(scr.alloc(&mag, (size_t)W * 5 * kMagC + 128));
+        OSB_CUDA(scr.alloc(&h1, (size_t)W * 5 * 128 + 64));
+        OSB_CUDA(scr.alloc(&h2, (size_t)W * 4 * 64 + 64));
+        OSB_CUDA(scr.alloc(&h3, (size_t)W * 3 * 64 + 64));
+        OSB_CUDA(scr.alloc(&h4, (size_t)W * 128 + 64));
+        // zero once: the padding rows/channels are never written by the GEMMs
+        OSB_CUDA(cudaMemsetAsync(mag, 0, ((size_t)W * 5 * kMagC + 128) * 4, st));
+        OSB_CUDA(cudaMemsetAsync(h1, 0, ((size_t)W * 5 * 128 + 64) * 4, st));
+        OSB_CUDA(cudaMemsetAsync(h2, 0, ((size_t)W * 4 * 64 + 64) * 4, st));
+        OSB_CUDA(cudaMemsetAsync(h3, 0, ((size_t)W * 3 * 64 + 64) * 4, st));
+    }
     static PerDeviceOnce once;
     OSB_CUDA(once.run([&] {
         cudaError_t e = cudaFuncSetAttribute(k_vad_recur<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, RecurCfg<1>::smem);
@@ -933,6 +939,9 @@ static int vad_score(VadModel* m, const void* d_audio, int fmt, int64_t n, int64
         const int t = (int)((n_win - w0) < T ? (n_win - w0) : T);
         const int Wc = (int)(batch * t);
         GemmDesc d{};
+        if (fused) {
+            if ((rc = launch_vad_front_fused(m->fused, d_audio, fmt, stride, t, w0, (long long)batch * t, m->e1b, m->e2b, m->e3b, m->e4b, m->bsum, pre, st))) return rc;
+        } else {
         // L0: DFT conv + magnitude -> mag[w][1+f][0..128]
         d.A = d_audio; d.audio_stride = stride; d.wins_per_stream = t; d.win0 = w0;
         d.B = m->basis; d.bias = nullptr; d.C = mag; d.c_outer = 5 * kMagC; d.c_icount = 3; d.c_istride = kMagC; d.c_offset = kMagC;
@@ -970,6 +979,7 @@ static int vad_score(VadModel* m, const void* d_audio, int fmt, int64_t n, int64
         d.B = m->wih; d.bias = m->bsum; d.C = pre; d.c_outer = kGates; d.c_icount = 1; d.c_istride = 0; d.c_offset = 0;
         d.M = Wc; d.N = kGates; d.K = 128; d.relu = 0;
         if ((rc = m->use_tc ? launch_gemm_tc<0, 0>(d, m->tc[5], st) : launch_gemm<0, 0>(d, st))) return rc;
+        }
         // recurrence over the chunk's t windows, one CTA per stream
         const unsigned rg = (unsigned)((batch + rs - 1) / rs);
         if (rs == 1) OSB_LAUNCH(k_vad_recur<1>, rg, 512, RecurCfg<1>::smem, st, pre, (long long)t * kGates, t, (const float4*)m->whh_perm, m->dw, m->db,
@@ -1066,8 +1076,15 @@ int osb_vad_create(const float* weights_host, size_t n_floats, void** handle) {
             return rc;
         }
     }
-    const char* env = getenv("OSB_VAD_GEMM");
-    m->use_tc = !(env && strcmp(env, "ffma") == 0);
+    {
+        VadFrontLayout L{oBasis, oE1w, oE2w, oE3w, oE4w, oWih};
+        if ((rc = vad_front_create(w, L, &m->fused))) {
+            delete m;
+            return rc;
+        }
+    }
+    const char* env = getenv("OSB_VAD_GEMM");  // "ffma" | "layers" | (default) fused
+    m->use_tc = (env && strcmp(env, "ffma") == 0) ? 0 : ((env && strcmp(env, "layers") == 0) ? 1 : 2);
     *handle = m;
     return OSB_OK;
 }
@@ -1078,13 +1095,15 @@ int osb_vad_destroy(void* handle) {
     float* ptrs[] = {m->basis, m->e1w, m->e1b, m->e2w, m->e2b, m->e3w, m->e3b, m->e4w, m->e4b, m->wih, m->bsum, m->whh, m->whh_perm, m->dw};
     for (float* p : ptrs) cudaFree(p);
     for (auto& t : m->tc) cudaFree(t.img);
+    vad_front_destroy(m->fused);
     delete m;
     return OSB_OK;
 }
 
 int osb_vad_set_gemm(void* handle, int use_tcgen05) {
     OSB_REQUIRE(handle, "null VAD handle");
-    reinterpret_cast<VadModel*>(handle)->use_tc = use_tcgen05 ? 1 : 0;
+    OSB_REQUIRE(use_tcgen05 >= 0 && use_tcgen05 <= 2, "mode must be 0 (FFMA), 1 (tcgen05 per layer) or 2 (fused tcgen05)");
+    reinterpret_cast<VadModel*>(handle)->use_tc = use_tcgen05;
     return OSB_OK;
 }
 

@@ -1,0 +1,23 @@
+// Fused Silero-VAD front end (csrc/vad_front.cu): one persistent tcgen05 kernel from samples to LSTM gate pre-activations.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+
+namespace osb {
+
+struct VadFront;  // device-resident weight image in the kernel's consumption order
+
+// float offsets of the tensors inside the flat host weight blob (vad/silero.py WEIGHT_LAYOUT)
+struct VadFrontLayout {
+    size_t basis, e1w, e2w, e3w, e4w, wih;
+};
+
+int vad_front_create(const float* weights_host, const VadFrontLayout& layout, VadFront** out);
+void vad_front_destroy(VadFront* f);
+// windows are rows (stream, t): window w of the launch = stream w / wins_per_stream, window win0 + w % wins_per_stream of that stream;
+// d_pre [total_windows][512] receives W_ih.x + b_ih + b_hh
+int launch_vad_front_fused(const VadFront* f, const void* d_audio, int fmt, long long audio_stride, int wins_per_stream, long long win0,
+                           long long total_windows, const float* e1b, const float* e2b, const float* e3b, const float* e4b, const float* bsum,
+                           float* d_pre, cudaStream_t st);
+
+}  // namespace osb

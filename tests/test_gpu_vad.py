@@ -155,19 +155,51 @@ def test_many_streams_share_recurrence_ctas(gpu, session, batch):
     assert np.abs(got[0] - o2).max() <= PROB_TOL
 
 
-def test_tcgen05_front_matches_ffma_and_oracle(gpu, session):
-    """The tensor-core (tcgen05, split-bf16) front-end GEMM against the FP32 FFMA kernel and the oracle."""
+def test_tcgen05_fronts_match_ffma_and_oracle(gpu, session):
+    """The fused persistent tcgen05 front (mode 2, the default) and the per-layer tcgen05 GEMMs (mode 1), both split-bf16, against
+    the FP32 FFMA kernels (mode 0) and the oracle."""
     from open_speech_b200.vad.silero import SileroVAD
 
     pcm = _audio(20.0, 321)
     ref, _ = ovad.SileroNet().score_stream(pcm.astype(np.float32) / 32768.0)
     out = {}
     try:
-        for mode in (1, 0):
+        for mode in (2, 1, 0):
             gpu.call("osb_vad_set_gemm", session.handle, mode)
             out[mode] = SileroVAD(session)._score(pcm.tobytes(), gpu.FMT_PCM16, len(pcm))
     finally:
-        gpu.call("osb_vad_set_gemm", session.handle, 1)
-    assert np.abs(out[0] - ref).max() <= PROB_TOL
-    assert np.abs(out[1] - ref).max() <= PROB_TOL, float(np.abs(out[1] - ref).max())
+        gpu.call("osb_vad_set_gemm", session.handle, 2)
+    for mode in (0, 1, 2):
+        assert np.abs(out[mode] - ref).max() <= PROB_TOL, (mode, float(np.abs(out[mode] - ref).max()))
     assert np.abs(out[1] - out[0]).max() <= 2e-4, float(np.abs(out[1] - out[0]).max())
+    assert np.abs(out[2] - out[0]).max() <= 2e-4, float(np.abs(out[2] - out[0]).max())
+
+
+def test_fused_front_tiles_streams_and_float_input(gpu, session):
+    """Tile edges of the fused front: window counts that are not multiples of 128, tiles that span several streams, more tiles than
+    SMs (a CTA walks several tiles: every barrier phase wraps), float32 input, odd strides (unaligned rows)."""
+    import torch
+
+    net = ovad.SileroNet()
+    for batch, secs, pad in ((3, 1.7, 0), (37, 2.1, 3), (300, 3.0, 8), (2, 700.0, 0)):
+        base = [_audio(secs, 500 + i) for i in range(min(batch, 4))]
+        n = len(base[0])
+        pcm = np.zeros((batch, n + pad), np.int16)
+        for i in range(batch):
+            pcm[i, :n] = base[i % len(base)]
+        n_win = n // 512
+        for as_float in (False, True):
+            x = torch.from_numpy(pcm.astype(np.float32) / 32768.0 if as_float else pcm).cuda()
+            state = torch.zeros((batch, 2, 128), dtype=torch.float32, device="cuda")
+            probs = torch.empty((batch, n_win), dtype=torch.float32, device="cuda")
+            gpu.call("osb_vad_score_dev", session.handle, x.data_ptr(), gpu.FMT_F32 if as_float else gpu.FMT_PCM16, n, batch, n + pad,
+                     state.data_ptr(), probs.data_ptr(), n_win, torch.cuda.current_stream().cuda_stream)
+            torch.cuda.synchronize()
+            got = probs.cpu().numpy()
+            for i in range(len(base)):
+                ref, _ = net.score_stream(base[i].astype(np.float32) / 32768.0)
+                assert np.abs(got[i] - ref).max() <= PROB_TOL, (batch, as_float, i, float(np.abs(got[i] - ref).max()))
+            for i in range(len(base), batch):
+                assert np.array_equal(got[i], got[i % len(base)]), (batch, i)  # the tile a window lands in is invisible
+            if secs > 100:
+                break  # the long case once
