@@ -477,6 +477,13 @@ __device__ __forceinline__ float tanhf_fast(float x) {
     return copysignf(__fmul_rn(__fsub_rn(1.0f, t), __frcp_rn(__fadd_rn(1.0f, t))), x);
 }
 
+// Gate pre-activation of window w (flattened (stream, t) index of the launch), gate row `own`.  Linear: [w][512].  Tiled (what the
+// fused front writes, vad_front.cu): [w / 128][own / 4][w % 128][own % 4] -- a warp of the front stores 32 rows x 16 B as one contiguous
+// 512-byte run, and the 32-byte sector this kernel touches for window w also holds window w +- 1 of the same stream, its next step.
+__device__ __forceinline__ long long pre_at(long long w, int own, bool tiled) {
+    return tiled ? (w >> 7) * 65536 + (long long)(own >> 2) * 512 + (w & 127) * 4 + (own & 3) : w * kGates + own;
+}
+
 constexpr int kHq = 36;  // floats between the four 32-float quarters of h in shared memory: the quarters sit in different banks
 template <int S>
 struct RecurCfg {
@@ -496,7 +503,7 @@ template <int S>
 __global__ void __launch_bounds__(512, 1) k_vad_recur(const float* __restrict__ pre, long long pre_stream_stride, int n_steps,
                                                       const float4* __restrict__ whh_perm, const float* __restrict__ dw, float db,
                                                       float* __restrict__ state, float* __restrict__ probs, long long probs_stride,
-                                                      long long win0, int batch) {
+                                                      long long win0, int batch, const float* __restrict__ pre_bias) {
     constexpr int RKG = RecurCfg<S>::RKG, SKG = RecurCfg<S>::SKG;
     extern __shared__ __align__(16) float sm[];
     float4* w_sm = reinterpret_cast<float4*>(sm);                 // [4][SKG][512] float4
@@ -525,23 +532,29 @@ __global__ void __launch_bounds__(512, 1) k_vad_recur(const float* __restrict__ 
         c[s] = s < ns ? st[kHid + unit] : 0.f;
         if (q == 0) h_sm[s * 4 * kHq + upos] = s < ns ? st[unit] : 0.f;
     }
-    const float* p[S];
+    long long w0s[S];  // first window of the stream in the launch's flattened (stream, t) order
     float pre_v[S];
+    // The fused front (pre_bias != null) leaves W_ih.x without b_ih + b_hh and in its own tiled layout (pre_at): the row's bias is
+    // added here with the rounding the GEMM epilogue of the other engines applies, fl(acc + b), off the serial chain.
+    const bool tiled = pre_bias != nullptr;
+    const float pb = tiled ? pre_bias[own] : 0.f;
 #pragma unroll
     for (int s = 0; s < S; ++s) {
-        p[s] = pre + (long long)(b0 + (s < ns ? s : 0)) * pre_stream_stride + own;
-        pre_v[s] = n_steps > 0 ? p[s][0] : 0.f;
+        w0s[s] = (long long)(b0 + (s < ns ? s : 0)) * (pre_stream_stride / kGates);
+        pre_v[s] = n_steps > 0 ? pre[pre_at(w0s[s], own, tiled)] : 0.f;
     }
     __syncthreads();
     for (int t = 0; t < n_steps; ++t) {
         const float* hr = h_sm + (t & 1) * (S * 4 * kHq);          // h of the previous step
         float* hw = h_sm + ((t + 1) & 1) * (S * 4 * kHq);          // h of this step
         float* pw = part_sm + (t & 63) * (S * 17);
-        float pre_next[S];
+        float pre_next[S], pre_b[S];
+#pragma unroll
+        for (int s = 0; s < S; ++s) pre_b[s] = __fadd_rn(pre_v[s], pb);  // loaded a step ago: ready long before the matvec ends
         float2 a[4][S];
 #pragma unroll
         for (int s = 0; s < S; ++s) {
-            pre_next[s] = (t + 1 < n_steps) ? p[s][(long long)(t + 1) * kGates] : 0.f;  // prefetch
+            pre_next[s] = (t + 1 < n_steps) ? pre[pre_at(w0s[s] + t + 1, own, tiled)] : 0.f;  // prefetch (consumed one step later)
 #pragma unroll
             for (int i = 0; i < 4; ++i) a[i][s] = make_float2(0.f, 0.f);
         }
@@ -571,7 +584,7 @@ __global__ void __launch_bounds__(512, 1) k_vad_recur(const float* __restrict__ 
             const float v0 = (hi ? p2 : p0) + __shfl_xor_sync(0xffffffffu, hi ? p0 : p2, 8);
             const float v1 = (hi ? p3 : p1) + __shfl_xor_sync(0xffffffffu, hi ? p1 : p3, 8);
             const bool hi2 = q & 2;
-            x[s] = ((hi2 ? v1 : v0) + __shfl_xor_sync(0xffffffffu, hi2 ? v0 : v1, 16)) + pre_v[s];
+            x[s] = ((hi2 ? v1 : v0) + __shfl_xor_sync(0xffffffffu, hi2 ? v0 : v1, 16)) + pre_b[s];
         }
 #pragma unroll
         for (int s = 0; s < S; ++s) {
@@ -648,7 +661,7 @@ template <int S>
 __global__ void __launch_bounds__(512, 1) k_vad_recur_mb(const float* __restrict__ pre, long long pre_stream_stride, int n_steps,
                                                       const float4* __restrict__ whh_perm, const float* __restrict__ dw, float db,
                                                       float* __restrict__ state, float* __restrict__ probs, long long probs_stride,
-                                                      long long win0, int batch) {
+                                                      long long win0, int batch, const float* __restrict__ pre_bias) {
     constexpr int RKG = RecurMbCfg<S>::RKG, SKG = RecurMbCfg<S>::SKG;
     extern __shared__ __align__(16) float sm[];
     float4* w_sm = reinterpret_cast<float4*>(sm);                 // [4][SKG][512] float4
@@ -676,21 +689,27 @@ __global__ void __launch_bounds__(512, 1) k_vad_recur_mb(const float* __restrict
     if (tid < S * kHid) h_sm[hpos] = cell ? st[cu] : 0.f;
     if (cell) c = st[kHid + cu];
     if (tid < kHid) dw_sm[tid] = dw[tid];
-    const float* p[S];
+    long long w0s[S];  // first window of the stream in the launch's flattened (stream, t) order
     float pre_v[S];
+    // The fused front (pre_bias != null) leaves W_ih.x without b_ih + b_hh and in its own tiled layout (pre_at): the row's bias is
+    // added here with the rounding the GEMM epilogue of the other engines applies, fl(acc + b), off the serial chain.
+    const bool tiled = pre_bias != nullptr;
+    const float pb = tiled ? pre_bias[own] : 0.f;
 #pragma unroll
     for (int s = 0; s < S; ++s) {
-        p[s] = pre + (long long)(b0 + (s < ns ? s : 0)) * pre_stream_stride + own;
-        pre_v[s] = n_steps > 0 ? p[s][0] : 0.f;
+        w0s[s] = (long long)(b0 + (s < ns ? s : 0)) * (pre_stream_stride / kGates);
+        pre_v[s] = n_steps > 0 ? pre[pre_at(w0s[s], own, tiled)] : 0.f;
     }
     float* pr = probs + (long long)(b0 + (cell ? cs : 0)) * probs_stride + win0;
     __syncthreads();
     for (int t = 0; t < n_steps; ++t) {
-        float pre_next[S];
+        float pre_next[S], pre_b[S];
+#pragma unroll
+        for (int s = 0; s < S; ++s) pre_b[s] = __fadd_rn(pre_v[s], pb);  // loaded a step ago: ready long before the matvec ends
         float2 a[4][S];
 #pragma unroll
         for (int s = 0; s < S; ++s) {
-            pre_next[s] = (t + 1 < n_steps) ? p[s][(long long)(t + 1) * kGates] : 0.f;  // prefetch
+            pre_next[s] = (t + 1 < n_steps) ? pre[pre_at(w0s[s] + t + 1, own, tiled)] : 0.f;  // prefetch (consumed one step later)
 #pragma unroll
             for (int i = 0; i < 4; ++i) a[i][s] = make_float2(0.f, 0.f);
         }
@@ -718,7 +737,7 @@ __global__ void __launch_bounds__(512, 1) k_vad_recur_mb(const float* __restrict
             const float v1 = (hi ? p3 : p1) + __shfl_xor_sync(0xffffffffu, hi ? p1 : p3, 8);
             const bool hi2 = q & 2;
             const float r = (hi2 ? v1 : v0) + __shfl_xor_sync(0xffffffffu, hi2 ? v0 : v1, 16);
-            g_sm[s * kGates + own] = r + pre_v[s];
+            g_sm[s * kGates + own] = r + pre_b[s];
         }
         __syncthreads();
         if (tid < S * kHid) {
@@ -912,7 +931,7 @@ static int vad_score(VadModel* m, const void* d_audio, int fmt, int64_t n, int64
     Scratch scr(st);
     const bool fused = m->use_tc == 2;
     float *mag = nullptr, *h1 = nullptr, *h2 = nullptr, *h3 = nullptr, *h4 = nullptr, *pre;
-    OSB_CUDA(scr.alloc(&pre, (size_t)W * kGates + 64));
+    OSB_CUDA(scr.alloc(&pre, (size_t)((W + 127) / 128) * 128 * kGates + 64));  // whole 128-window tiles (the fused front's tiled layout)
     if (!fused) {
         OSB_CUDA(scr.alloc(&mag, (size_t)W * 5 * kMagC + 128));
         OSB_CUDA(scr.alloc(&h1, (size_t)W * 5 * 128 + 64));
@@ -940,7 +959,7 @@ static int vad_score(VadModel* m, const void* d_audio, int fmt, int64_t n, int64
         const int Wc = (int)(batch * t);
         GemmDesc d{};
         if (fused) {
-            if ((rc = launch_vad_front_fused(m->fused, d_audio, fmt, stride, t, w0, (long long)batch * t, m->e1b, m->e2b, m->e3b, m->e4b, m->bsum, pre, st))) return rc;
+            if ((rc = launch_vad_front_fused(m->fused, d_audio, fmt, stride, t, w0, (long long)batch * t, pre, st))) return rc;
         } else {
         // L0: DFT conv + magnitude -> mag[w][1+f][0..128]
         d.A = d_audio; d.audio_stride = stride; d.wins_per_stream = t; d.win0 = w0;
@@ -982,12 +1001,13 @@ static int vad_score(VadModel* m, const void* d_audio, int fmt, int64_t n, int64
         }
         // recurrence over the chunk's t windows, one CTA per stream
         const unsigned rg = (unsigned)((batch + rs - 1) / rs);
+        const float* rbias = fused ? m->bsum : nullptr;
         if (rs == 1) OSB_LAUNCH(k_vad_recur<1>, rg, 512, RecurCfg<1>::smem, st, pre, (long long)t * kGates, t, (const float4*)m->whh_perm, m->dw, m->db,
-                                d_state, d_probs, (long long)probs_stride, w0, (int)batch);
+                                d_state, d_probs, (long long)probs_stride, w0, (int)batch, rbias);
         else if (rs == 2) OSB_LAUNCH(k_vad_recur_mb<2>, rg, 512, RecurMbCfg<2>::smem, st, pre, (long long)t * kGates, t, (const float4*)m->whh_perm, m->dw, m->db,
-                                     d_state, d_probs, (long long)probs_stride, w0, (int)batch);
+                                     d_state, d_probs, (long long)probs_stride, w0, (int)batch, rbias);
         else OSB_LAUNCH(k_vad_recur_mb<4>, rg, 512, RecurMbCfg<4>::smem, st, pre, (long long)t * kGates, t, (const float4*)m->whh_perm, m->dw, m->db,
-                        d_state, d_probs, (long long)probs_stride, w0, (int)batch);
+                        d_state, d_probs, (long long)probs_stride, w0, (int)batch, rbias);
         OSB_CHECK_LAUNCH();
     }
     return OSB_OK;
@@ -1077,7 +1097,7 @@ int osb_vad_create(const float* weights_host, size_t n_floats, void** handle) {
         }
     }
     {
-        VadFrontLayout L{oBasis, oE1w, oE2w, oE3w, oE4w, oWih};
+        VadFrontLayout L{oBasis, oE1w, oE1b, oE2w, oE2b, oE3w, oE3b, oE4w, oE4b, oWih};
         if ((rc = vad_front_create(w, L, &m->fused))) {
             delete m;
             return rc;

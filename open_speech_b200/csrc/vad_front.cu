@@ -15,14 +15,13 @@
 // The 129th |STFT| channel (Nyquist) does not fit the 128-wide K tiling: it takes the imaginary-DC column of the DFT GEMM
 // (identically zero) and enters enc1 as a rank-1 FP32 update in the epilogue.
 //
-// Warp roles (448 threads, one CTA per SM, persistent over tiles):
+// Warp roles (576 threads, one CTA per SM, persistent over tiles):
 //   warps 0-7   epilogue: TMEM -> registers -> bias / ReLU / |re,im| -> bf16 hi+lo -> swizzled smem operand (or global store)
-//   warps 8-11  staging: pcm16 / f32 samples -> bf16 hi+lo -> swizzled smem operand (two 64-sample chunk buffers in flight)
-//   warp 12     one lane issues every tcgen05.mma and the commits that release buffers / publish accumulators
-//   warp 13     one lane keeps the weight ring full (cp.async.bulk, 32 KB slots)
-// (14 warps: at most 4 per scheduler partition, so every thread may use 128 registers)
-// Per tile the schedule is static (57 weight slots, 119 MMA groups of K = 64); every shared resource (4 operand buffers, 4
-// TMEM slots of 128 columns) alternates strictly full -> free, each transition on its own mbarrier.
+//   warps 8-15  staging: pcm16 / f32 samples -> bf16 hi+lo -> swizzled smem operand (two 64-sample chunk buffers in flight)
+//   warp 16     one lane issues every tcgen05.mma and the commits that release buffers / publish accumulators
+//   warp 17     one lane keeps the weight ring full (cp.async.bulk, 32 KB slots)
+// Per tile the schedule is static: 57 MMA groups of K = 64 (12 tcgen05.mma each), one weight slot per group; every shared resource
+// (4 operand buffers, 4 TMEM slots of 128 columns) alternates strictly full -> free, each transition on its own mbarrier.
 #include <cstdlib>
 #include <vector>
 
@@ -41,7 +40,7 @@ constexpr int kPlane = kRows * kKc * 2;         // 16 KB
 constexpr int kBuf = 2 * kPlane;                // hi + lo: 32 KB
 constexpr int kRing = 3;                        // weight ring depth
 constexpr int kSlotsPerTile = 57;
-constexpr int kEpiThreads = 256, kStageThreads = 128;
+constexpr int kEpiThreads = 256, kStageThreads = 256;
 constexpr int kThreads = kEpiThreads + kStageThreads + 64;
 // dynamic shared memory: [4 operand buffers][kRing weight slots][side |re128| 3 x 128 f32][barriers][tmem ptr]
 constexpr int kOffRing = 4 * kBuf;
@@ -55,6 +54,11 @@ constexpr int kSmem = kOffTmem + 16 + 1024;          // + slack to align the bas
 // A1: 12 audio chunks + h1_0[64:128] + h1_2[64:128] = 14; M0 / M1: |STFT| chunks of three units + h1_1 half + h2_q + h4 half = 6 each.
 enum { A0 = 0, A1 = 1, M0 = 2, M1 = 3 };
 
+struct Consts {
+    float e1b[128], e2b[64], e3b[64], e4b[128];
+    float w1side[3][128];       // enc1 weights of input channel 128 (the Nyquist bin), per tap
+};
+
 struct Params {
     const void* audio;          // pcm16 or f32
     int fmt;                    // OSB_FMT_PCM16 | OSB_FMT_F32
@@ -65,10 +69,22 @@ struct Params {
     int n_tiles;
     const uint8_t* wimg;        // weight image
     const uint2* slots;         // [57] (byte offset, bytes) in consumption order
-    const float* e1b; const float* e2b; const float* e3b; const float* e4b; const float* bsum;
-    const float* w1side;        // [3 taps][128 oc]: enc1 weights of input channel 128
-    float* pre;                 // [total][512]
+    float* pre;                 // [tiles][128 column groups][128 rows][4]: W_ih.x, tiled (vad.cu pre_at); b_ih + b_hh is added by the recurrence
+    // per-channel vectors the epilogue needs, in the kernel's constant bank: every lane of a warp reads the same element (a warp holds
+    // 32 rows of the same columns), which the constant cache serves as a broadcast; with 227 KB of shared memory carved out there is
+    // no L1 left for them and the L2 round trip (~700 cycles per dependent load) was the epilogue's whole cost
+    Consts c;
+    unsigned long long* trace;  // debug: clock stamps of CTA 0 (OSB_VF_TRACE), or null
 };
+
+// debug trace: role r (0 MMA, 1 epilogue, 2 staging, 3 producer), tile iteration it (< 4), event e (< 64) of CTA 0
+__device__ __forceinline__ void stamp(const Params& p, int r, int it, int e) {
+    if (p.trace && blockIdx.x == 0 && it < 4 && e < 64) p.trace[(r * 4 + it) * 64 + e] = clock64();
+}
+
+__device__ __forceinline__ void stamp_val(const Params& p, int r, int it, int e, unsigned long long v) {
+    if (p.trace && blockIdx.x == 0 && it < 4 && e < 64) p.trace[(r * 4 + it) * 64 + e] = v;
+}
 
 __device__ __forceinline__ uint64_t desc_sw128(uint32_t saddr) {
     const uint32_t lo = ((saddr >> 4) & 0x3FFFu) | (1u << 16);
@@ -86,6 +102,12 @@ __device__ __forceinline__ void commit(uint64_t* bar) {
 __device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void arrive(uint64_t* bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory"); }
+// sqrt.approx (2 ulp): the magnitude is split into bf16 hi + lo (2^-16) right after, an IEEE square root would cost ~25 instructions more
+__device__ __forceinline__ float sqrt_approx(float x) {
+    float y;
+    asm("sqrt.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
     const __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
     hi = *reinterpret_cast<const uint32_t*>(&h2);
@@ -135,18 +157,25 @@ struct MmaRole {
     const Sm sm;
     Book bk;
     uint32_t slot = 0;    // weight slots consumed so far (ring position = slot % kRing)
-    __device__ __forceinline__ MmaRole(const Sm& s, const Book& b) : sm(s), bk(b) {}
+    const Params& p;
+    int it = 0;
+    __device__ __forceinline__ MmaRole(const Sm& s, const Book& b, const Params& pp) : sm(s), bk(b), p(pp) {}
+    long long cyc_p = 0, cyc_b = 0, cyc_t = 0;  // debug: cycles spent waiting for operands / weights / TMEM
     __device__ __forceinline__ void wait_full(int buf) {
+        const long long c0 = p.trace ? clock64() : 0;
         mbar_wait(&sm.pfull[buf], (bk.ph >> buf) & 1u);
         bk.ph ^= 1u << buf;
         fence_after();
+        if (p.trace) cyc_p += clock64() - c0;
     }
     __device__ __forceinline__ void release(int buf) { commit(&sm.pfree[buf]); }
     __device__ __forceinline__ void acc_begin(int t) {  // before the first MMA of a new accumulation into TMEM slot t
         if ((bk.tany >> t) & 1u) {
+            const long long c0 = p.trace ? clock64() : 0;
             mbar_wait(&sm.tfree[t], (bk.ph >> (4 + t)) & 1u);
             bk.ph ^= 1u << (4 + t);
             fence_after();
+            if (p.trace) cyc_t += clock64() - c0;
         }
         bk.tany |= 1u << t;
     }
@@ -154,8 +183,10 @@ struct MmaRole {
     // one group: A = operand buffer `buf` (K = 64), B = next weight slot (rows = N), D = TMEM column `col`, N columns
     __device__ __forceinline__ void group(int buf, uint32_t col, int N, bool accumulate) {
         const uint32_t rs = slot % kRing;
+        const long long c0 = p.trace ? clock64() : 0;
         mbar_wait(&sm.bfull[rs], (slot / kRing) & 1u);
         fence_after();
+        if (p.trace) cyc_b += clock64() - c0;
         const uint32_t a_hi = smem_u32(sm.buf(buf)), a_lo = a_hi + kPlane;
         const uint32_t b_hi = smem_u32(sm.ring + (size_t)rs * kBuf), b_lo = b_hi + (uint32_t)N * 128u;
         const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(kRows >> 4) << 24);
@@ -171,9 +202,11 @@ struct MmaRole {
         ++slot;
     }
     __device__ __forceinline__ void run_tile() {
+        stamp(p, 0, it, 0);
         // ---- DFT conv + enc1, interleaved: unit u = (frame f, bin half h)
 #pragma unroll 1
         for (int u = 0; u < 7; ++u) {
+            stamp(p, 0, it, 1 + 2 * u);
             if (u < 6) {
                 acc_begin(0);
 #pragma unroll 1
@@ -185,6 +218,7 @@ struct MmaRole {
                 }
                 acc_done(0);
             }
+            stamp(p, 0, it, 2 + 2 * u);
             if (u >= 1) {  // enc1 contributions of |STFT| chunk (f, h) of unit u-1: positions p = f-1, f, f+1
                 const int v = u - 1, f = v >> 1, h = v & 1, buf = M0 + (v & 1);
                 wait_full(buf);
@@ -200,6 +234,7 @@ struct MmaRole {
             }
         }
         // ---- enc2 (stride 2): q0 <- h1_0 tap1, h1_1 tap2 ; q1 <- h1_1 tap0, h1_2 tap1.  ACC2 = TMEM slot 0, 64 + 64 columns
+        stamp(p, 0, it, 15);
         acc_begin(0);
         wait_full(A0); wait_full(A1);
         group(A0, 0, 64, false); group(A1, 0, 64, true);
@@ -213,19 +248,23 @@ struct MmaRole {
         release(A0); release(A1);
         acc_done(0);
         // ---- enc3 (stride 2): out <- h2_0 tap1, h2_1 tap2.  ACC3 = slot 1, 64 columns
+        stamp(p, 0, it, 16);
         acc_begin(1);
         wait_full(M0); wait_full(M1);
         group(M0, 128, 64, false); group(M1, 128, 64, true);
         release(M0); release(M1);
         acc_done(1);
         // ---- enc4: out <- h3 tap1.  ACC4 = slot 2
+        stamp(p, 0, it, 17);
         acc_begin(2);
         wait_full(A0);
         group(A0, 256, 128, false);
         release(A0);
         acc_done(2);
         // ---- W_ih: four 128-wide gate blocks, K = 128
+        stamp(p, 0, it, 18);
         wait_full(M0); wait_full(M1);
+        stamp(p, 0, it, 19);
 #pragma unroll 1
         for (int j = 0; j < 4; ++j) {
             acc_begin(j);
@@ -234,6 +273,10 @@ struct MmaRole {
             acc_done(j);
         }
         release(M0); release(M1);
+        stamp(p, 0, it, 20);
+        stamp_val(p, 0, it, 40, (unsigned long long)cyc_p); stamp_val(p, 0, it, 41, (unsigned long long)cyc_b); stamp_val(p, 0, it, 42, (unsigned long long)cyc_t);
+        cyc_p = cyc_b = cyc_t = 0;
+        ++it;
     }
 };
 
@@ -264,72 +307,140 @@ __device__ __forceinline__ void writer_publish(const Sm& sm, int buf) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(&sm.pfull[buf])), "n"(COUNT) : "memory");
 }
 
-// ------------------------------------------------------------------ role: audio staging (128 threads)
+// ------------------------------------------------------------------ role: audio staging (256 threads)
 struct StageRole {
     const Sm sm;
     Book bk;
     const Params& p;
-    int t;  // 0..127
+    int t;  // 0..255
+    int it = 0;
     __device__ __forceinline__ StageRole(const Sm& s, const Book& b, const Params& pp, int tid) : sm(s), bk(b), p(pp), t(tid) {}
-    __device__ __forceinline__ void chunk(long long tile, int f, int kc, int buf) {
-        const int row = t;  // one row per thread: 64 samples = one 128-byte operand row per plane
-        const long long wi = tile * kRows + row;
-        uint8_t* hi = sm.buf(buf);
-        uint8_t* lo = hi + kPlane;
-        long long base = 0;
-        const bool live = wi < p.total;
-        if (live) {
-            const long long sidx = wi / p.wins_per_stream;
-            base = sidx * p.audio_stride + (p.win0 + (wi - sidx * p.wins_per_stream)) * 512 + 128 * f + 64 * kc;
-        }
-        const int16_t* s16 = reinterpret_cast<const int16_t*>(p.audio) + base;
-        const float* sf = reinterpret_cast<const float*>(p.audio) + base;
-        const bool vec = p.fmt == OSB_FMT_PCM16 && (((uintptr_t)s16) & 15) == 0;
+    // One 64-sample chunk = 128 rows x 8 operand units (8 samples = 16 bytes of pcm16 each).  Thread t takes the four units
+    // q = t + 256 k (row q / 8, unit q % 8): the eight lanes of a quarter-warp read one row's 128 contiguous bytes, a warp-wide load
+    // touches 4 lines instead of 32 (one line per lane cost 32 L1 wavefronts per load and made this role the kernel's bottleneck),
+    // and the matching 16-byte shared-memory stores of a quarter-warp fall into eight different bank groups (XOR swizzle).
+    // The pcm16 loads of chunk c+1 are issued BEFORE chunk c is converted (two register sets); float32 input loads inside the conversion.
+    // int16 -> float without the quarter-rate I2F: as_float(0x4B400000 + v) = 12582912 + v exactly, and one FFMA rescales it to v / 32768.
+    long long cyc_acq = 0, cyc_cvt = 0, cyc_u0 = 0, cyc_pub = 0;
+    long long rbase[4];  // per tile: sample offset of window row (t / 8 + 32 k) in the audio buffer, -1 past the end
+    __device__ __forceinline__ void tile_rows(long long tile) {
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {  // 8 samples -> one 16-byte unit per plane
-            float v[8];
-            if (!live) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] = 0.f;
-            } else if (vec) {
-                const uint4 w = ld_stream_u4(s16 + 8 * u);
-                const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    v[2 * i] = (float)(int16_t)(ws[i] & 0xFFFF) * 3.0517578125e-05f;
-                    v[2 * i + 1] = (float)(int16_t)(ws[i] >> 16) * 3.0517578125e-05f;
-                }
-            } else if (p.fmt == OSB_FMT_PCM16) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] = (float)__ldg(s16 + 8 * u + i) * 3.0517578125e-05f;
-            } else {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] = __ldg(sf + 8 * u + i);
-            }
-            uint32_t h[4], l[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) split2(v[2 * j], v[2 * j + 1], h[j], l[j]);
-            const uint32_t off = unit_off(row, u);
-            *reinterpret_cast<uint4*>(hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
-            *reinterpret_cast<uint4*>(lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
+        for (int k = 0; k < 4; ++k) {
+            const long long wi = tile * kRows + (t >> 3) + 32 * k;
+            if (wi < p.total) {
+                const long long sidx = wi / p.wins_per_stream;
+                rbase[k] = sidx * p.audio_stride + (p.win0 + (wi - sidx * p.wins_per_stream)) * 512 + 8 * (t & 7);
+            } else rbase[k] = -1;
         }
     }
-    __device__ __forceinline__ void run_tile(long long tile) {
-#pragma unroll 1
-        for (int u = 0; u < 6; ++u)
-#pragma unroll 1
-            for (int kc = 0; kc < 4; ++kc) {
-                const int buf = kc & 1;
-                writer_acquire(sm, bk, buf, true);
-                chunk(tile, u >> 1, kc, buf);
-                writer_publish<2>(sm, buf);  // 128 staging threads stand in for the 256 arrivals the barrier expects
+    __device__ __forceinline__ static int chunk_off(int c) { return 128 * (c >> 3) + 64 * (c & 3); }  // c = 4 u + kc, u = 2 f + h
+    __device__ __forceinline__ void load_pcm(int c, uint4 (&w)[4]) const {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (rbase[k] < 0) { w[k] = make_uint4(0u, 0u, 0u, 0u); continue; }
+            const int16_t* s16 = reinterpret_cast<const int16_t*>(p.audio) + rbase[k] + chunk_off(c);
+            if ((((uintptr_t)s16) & 15) == 0) w[k] = ld_stream_u4(s16);
+            else {
+                uint32_t q[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) q[i] = (uint32_t)(uint16_t)__ldg(s16 + 2 * i) | ((uint32_t)(uint16_t)__ldg(s16 + 2 * i + 1) << 16);
+                w[k] = make_uint4(q[0], q[1], q[2], q[3]);
             }
-        // The epilogue's writes of these two buffers (h1_0, h1_2, h3) come next.  A parity wait can only tell "the phase I mean" from
-        // "the one before it", so this role must not run more than one phase ahead: it waits through the release of every one of those
-        // writes, in schedule order, before it may ask for the buffers again (next tile).  Pure waits: nothing is written or published.
-        writer_acquire(sm, bk, A0, true); writer_acquire(sm, bk, A1, true);   // h1_0
-        writer_acquire(sm, bk, A0, true); writer_acquire(sm, bk, A1, true);   // h1_2
-        writer_acquire(sm, bk, A0, true);                                     // h3
+        }
+    }
+    __device__ __forceinline__ void put_unit(int buf, int k, const float (&v)[8]) {
+        uint32_t h[4], l[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) split2(v[2 * j], v[2 * j + 1], h[j], l[j]);
+        uint8_t* hi = sm.buf(buf) + unit_off((t >> 3) + 32 * k, t & 7);
+        *reinterpret_cast<uint4*>(hi) = make_uint4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<uint4*>(hi + kPlane) = make_uint4(l[0], l[1], l[2], l[3]);
+    }
+    __device__ __forceinline__ void acquire(int buf, int c) {
+        const long long c0 = p.trace ? clock64() : 0;
+        writer_acquire(sm, bk, buf, true);
+        if (p.trace) cyc_acq += clock64() - c0;
+        if (t == 0) stamp(p, 2, it, 2 * c);
+    }
+    __device__ __forceinline__ void publish(int buf, int c) {
+        writer_publish(sm, buf);
+        if (t == 0) stamp(p, 2, it, 2 * c + 1);
+    }
+    __device__ __forceinline__ void convert_pcm(int buf, int c, const uint4 (&w)[4]) {
+        acquire(buf, c);
+        const long long c1 = p.trace ? clock64() : 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t ws[4] = {w[k].x, w[k].y, w[k].z, w[k].w};
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int s0 = (int)(short)(ws[i] & 0xFFFFu), s1 = (int)ws[i] >> 16;
+                v[2 * i] = fmaf(__int_as_float(0x4B400000 + s0), 3.0517578125e-05f, -384.0f);      // (12582912 + s) / 32768 - 384
+                v[2 * i + 1] = fmaf(__int_as_float(0x4B400000 + s1), 3.0517578125e-05f, -384.0f);
+            }
+            put_unit(buf, k, v);
+            if (p.trace && k == 0) cyc_u0 += clock64() - c1;
+        }
+        if (p.trace) cyc_cvt += clock64() - c1;
+        const long long c2 = p.trace ? clock64() : 0;
+        publish(buf, c);
+        if (p.trace) cyc_pub += clock64() - c2;
+    }
+    __device__ __forceinline__ void convert_f32(int buf, int c) {
+        float4 g[8];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (rbase[k] < 0) { g[2 * k] = g[2 * k + 1] = make_float4(0.f, 0.f, 0.f, 0.f); continue; }
+            const float* sf = reinterpret_cast<const float*>(p.audio) + rbase[k] + chunk_off(c);
+            if ((((uintptr_t)sf) & 15) == 0) {
+                g[2 * k] = ld_stream_f4(sf);
+                g[2 * k + 1] = ld_stream_f4(sf + 4);
+            } else {
+                g[2 * k] = make_float4(__ldg(sf), __ldg(sf + 1), __ldg(sf + 2), __ldg(sf + 3));
+                g[2 * k + 1] = make_float4(__ldg(sf + 4), __ldg(sf + 5), __ldg(sf + 6), __ldg(sf + 7));
+            }
+        }
+        acquire(buf, c);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float v[8] = {g[2 * k].x, g[2 * k].y, g[2 * k].z, g[2 * k].w, g[2 * k + 1].x, g[2 * k + 1].y, g[2 * k + 1].z, g[2 * k + 1].w};
+            put_unit(buf, k, v);
+        }
+        publish(buf, c);
+    }
+    // all tiles of this CTA: 24 chunks per tile, chunk c -> buffer A(c & 1)
+    __device__ __forceinline__ void run(int n_my) {
+        const bool pcm = p.fmt == OSB_FMT_PCM16;
+        uint4 wa[4], wb[4];
+        if (n_my > 0) tile_rows((long long)blockIdx.x);
+        if (pcm && n_my > 0) load_pcm(0, wa);
+        for (int i = 0; i < n_my; ++i) {
+            const long long tile = (long long)blockIdx.x + (long long)i * gridDim.x;
+            if (pcm) {
+#pragma unroll 1
+                for (int c = 0; c < 24; c += 2) {
+                    load_pcm(c + 1, wb);
+                    convert_pcm(A0, c, wa);
+                    if (c + 2 < 24) load_pcm(c + 2, wa);
+                    else if (i + 1 < n_my) { tile_rows(tile + gridDim.x); load_pcm(0, wa); }
+                    convert_pcm(A1, c + 1, wb);
+                }
+            } else {
+#pragma unroll 1
+                for (int c = 0; c < 24; ++c) convert_f32(c & 1, c);
+                if (i + 1 < n_my) tile_rows(tile + gridDim.x);
+            }
+            // The epilogue's writes of these two buffers (h1_0, h1_2, h3) come next.  A parity wait can only tell "the phase I mean" from
+            // "the one before it", so this role must not run more than one phase ahead: it waits through the release of every one of those
+            // writes, in schedule order, before it may ask for the buffers again (next tile).  Pure waits: nothing is written or published.
+            writer_acquire(sm, bk, A0, true); writer_acquire(sm, bk, A1, true);   // h1_0
+            writer_acquire(sm, bk, A0, true); writer_acquire(sm, bk, A1, true);   // h1_2
+            writer_acquire(sm, bk, A0, true);                                     // h3
+            if (t == 0) { stamp(p, 2, it, 48); stamp_val(p, 2, it, 50, (unsigned long long)cyc_acq); stamp_val(p, 2, it, 51, (unsigned long long)cyc_cvt); stamp_val(p, 2, it, 52, (unsigned long long)cyc_u0); stamp_val(p, 2, it, 53, (unsigned long long)cyc_pub); }
+            cyc_acq = cyc_cvt = cyc_u0 = cyc_pub = 0;
+            ++it;
+        }
     }
 };
 
@@ -346,10 +457,13 @@ struct EpiRole {
         half = warp >> 2;
         lane_base = (uint32_t)((warp & 3) * 32) << 16;
     }
+    int it = 0, ev = 0;
     __device__ __forceinline__ void wait_acc(int t) {
+        if (row == 0 && half == 0) stamp(p, 1, it, ev++);
         mbar_wait(&sm.tfull[t], (bk.ph >> t) & 1u);
         bk.ph ^= 1u << t;
         fence_after();
+        if (row == 0 && half == 0) stamp(p, 1, it, ev++);
     }
     __device__ __forceinline__ void free_acc(int t) {
         fence_before();
@@ -378,7 +492,7 @@ struct EpiRole {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const float re = __uint_as_float(v[2 * i]), im = __uint_as_float(v[2 * i + 1]);
-                m[i] = sqrtf(re * re + im * im);
+                m[i] = sqrt_approx(re * re + im * im);
             }
             if (u == 0 && h == 0 && half == 0) {  // columns 0, 1 of the first half are (re 0, re 128): two real bins, not a pair
                 sm.side[f * kRows + row] = fabsf(__uint_as_float(v[1]));
@@ -412,22 +526,11 @@ struct EpiRole {
             const int oc = 64 * half + 8 * u;
             float x[8];
 #pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + oc) + q);
-                x[4 * q] = __uint_as_float(v[4 * q]) + bb.x; x[4 * q + 1] = __uint_as_float(v[4 * q + 1]) + bb.y;
-                x[4 * q + 2] = __uint_as_float(v[4 * q + 2]) + bb.z; x[4 * q + 3] = __uint_as_float(v[4 * q + 3]) + bb.w;
-                if (SIDE) {
-                    const float4 w0 = __ldg(reinterpret_cast<const float4*>(p.w1side + oc) + q);
-                    const float4 w1 = __ldg(reinterpret_cast<const float4*>(p.w1side + 128 + oc) + q);
-                    const float4 w2 = __ldg(reinterpret_cast<const float4*>(p.w1side + 256 + oc) + q);
-                    x[4 * q] = fmaf(s0, w0.x, fmaf(s1, w1.x, fmaf(s2, w2.x, x[4 * q])));
-                    x[4 * q + 1] = fmaf(s0, w0.y, fmaf(s1, w1.y, fmaf(s2, w2.y, x[4 * q + 1])));
-                    x[4 * q + 2] = fmaf(s0, w0.z, fmaf(s1, w1.z, fmaf(s2, w2.z, x[4 * q + 2])));
-                    x[4 * q + 3] = fmaf(s0, w0.w, fmaf(s1, w1.w, fmaf(s2, w2.w, x[4 * q + 3])));
-                }
+            for (int i = 0; i < 8; ++i) {
+                float a = __uint_as_float(v[i]) + bias[oc + i];  // constant bank, warp-uniform index
+                if (SIDE) a = fmaf(s0, p.c.w1side[0][oc + i], fmaf(s1, p.c.w1side[1][oc + i], fmaf(s2, p.c.w1side[2][oc + i], a)));
+                x[i] = fmaxf(a, 0.f);
             }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) x[i] = fmaxf(x[i], 0.f);
             put8(buf, u, x);
         }
         writer_publish(sm, b_lo);  // every epilogue thread arrives on both barriers (count = 256 each); each wrote one of the buffers
@@ -443,11 +546,7 @@ struct EpiRole {
             if (u == 3 && last_reader) free_acc(t);
             float x[8];
 #pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + 32 * half + 8 * u) + q);
-                x[4 * q] = fmaxf(__uint_as_float(v[4 * q]) + bb.x, 0.f); x[4 * q + 1] = fmaxf(__uint_as_float(v[4 * q + 1]) + bb.y, 0.f);
-                x[4 * q + 2] = fmaxf(__uint_as_float(v[4 * q + 2]) + bb.z, 0.f); x[4 * q + 3] = fmaxf(__uint_as_float(v[4 * q + 3]) + bb.w, 0.f);
-            }
+            for (int i = 0; i < 8; ++i) x[i] = fmaxf(__uint_as_float(v[i]) + bias[32 * half + 8 * u + i], 0.f);
             put8(buf, 4 * half + u, x);
         }
         writer_publish(sm, buf);
@@ -456,20 +555,17 @@ struct EpiRole {
         wait_acc(j);
         const uint32_t ta = sm.tmem + lane_base + (uint32_t)(128 * j + 64 * half);
         const long long wi = tile * kRows + row;
-        float* out = p.pre + wi * 512 + 128 * j + 64 * half;
-        const float* b = p.bsum + 128 * j + 64 * half;
-#pragma unroll 1
-        for (int u = 0; u < 8; ++u) {  // this thread's 256 contiguous bytes of its row, 32 bytes (one sector) per step
-            uint32_t v[8];
-            tmem_ld8(ta + 8 * u, v);
-            if (u == 7) free_acc(j);
+        // tiled layout [tile][column / 4][row][column % 4] (vad.cu pre_at): lane = row, so one store instruction of a warp is one contiguous
+        // 512-byte run -- with the linear [window][512] layout it was 32 half-sectors 2 KB apart and this loop cost 9,000 cycles per block
+        float* out = p.pre + tile * 65536 + (long long)(32 * j + 16 * half) * 512 + row * 4;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            uint32_t v[16];
+            tmem_ld16(ta + 16 * u, v);
+            if (u == 3) free_acc(j);
             if (wi < p.total) {
 #pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                    const float4 bb = __ldg(reinterpret_cast<const float4*>(b + 8 * u) + q);
-                    *reinterpret_cast<float4*>(out + 8 * u + 4 * q) = make_float4(__uint_as_float(v[4 * q]) + bb.x, __uint_as_float(v[4 * q + 1]) + bb.y,
-                                                                                 __uint_as_float(v[4 * q + 2]) + bb.z, __uint_as_float(v[4 * q + 3]) + bb.w);
-                }
+                for (int q = 0; q < 4; ++q) *reinterpret_cast<uint4*>(out + (4 * u + q) * 512) = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
             }
         }
     }
@@ -481,18 +577,21 @@ struct EpiRole {
 #pragma unroll 1
         for (int u = 0; u < 6; ++u) mags(u >> 1, u & 1, M0 + (u & 1));
         epi_sync();                          // side[] of all three positions is written
-        act128<true>(1, p.e1b, A0, A1, 0);   // h1_0
-        act128<true>(2, p.e1b, M0, M1, 1);   // h1_1
-        act128<true>(3, p.e1b, A0, A1, 2);   // h1_2
+        act128<true>(1, p.c.e1b, A0, A1, 0); // h1_0
+        act128<true>(2, p.c.e1b, M0, M1, 1); // h1_1
+        act128<true>(3, p.c.e1b, A0, A1, 2); // h1_2
         wait_acc(0);                         // enc2: q0 = columns 0-63 -> M0, q1 = columns 64-127 -> M1
-        act64(0, 0, p.e2b, M0, false);
-        act64(0, 64, p.e2b, M1, true);
+        act64(0, 0, p.c.e2b, M0, false);
+        act64(0, 64, p.c.e2b, M1, true);
         wait_acc(1);                         // enc3 -> A0
-        act64(1, 0, p.e3b, A0, true);
-        act128<false>(2, p.e4b, M0, M1, 0);  // enc4 -> h4
+        act64(1, 0, p.c.e3b, A0, true);
+        act128<false>(2, p.c.e4b, M0, M1, 0);  // enc4 -> h4
 #pragma unroll 1
         for (int j = 0; j < 4; ++j) store_pre(j, tile);
         epi_sync();                          // side[] is rewritten by the next tile's mags
+        if (row == 0 && half == 0) stamp(p, 1, it, ev++);
+        ++it;
+        ev = 0;
     }
 };
 
@@ -532,9 +631,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_vad_front_fused(Params p) {
         for (int i = 0; i < n_my; ++i) r.run_tile((long long)blockIdx.x + (long long)i * gridDim.x);
     } else if (warp < (kEpiThreads + kStageThreads) / 32) {
         StageRole r(sm, bk, p, tid - kEpiThreads);
-        for (int i = 0; i < n_my; ++i) r.run_tile((long long)blockIdx.x + (long long)i * gridDim.x);
+        r.run(n_my);
     } else if (tid == kEpiThreads + kStageThreads) {
-        MmaRole r(sm, bk);
+        MmaRole r(sm, bk, p);
         for (int i = 0; i < n_my; ++i) r.run_tile();
     } else if (tid == kEpiThreads + kStageThreads + 32) {
         producer_loop(sm, p, n_my);
@@ -550,7 +649,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_vad_front_fused(Params p) {
 struct VadFront {
     uint8_t* wimg = nullptr;
     uint2* slots = nullptr;
-    float* w1side = nullptr;
+    vf::Consts consts;  // host copy: travels to the device as part of the kernel parameters
 };
 
 static uint16_t f2bf(float f) {
@@ -626,16 +725,17 @@ int vad_front_create(const float* w, const VadFrontLayout& L, VadFront** out) {
     push(o_e4, 128);
     for (int j = 0; j < 4; ++j) { push(o_ih[j][0], 128); push(o_ih[j][1], 128); }
     if ((int)slots.size() != vf::kSlotsPerTile) { set_error("internal: VAD front slot table has %zu entries", slots.size()); return OSB_ERR_CUDA; }
-    std::vector<float> side(3 * 128);
-    for (int tap = 0; tap < 3; ++tap)
-        for (int oc = 0; oc < 128; ++oc) side[tap * 128 + oc] = w[L.e1w + ((size_t)oc * 129 + 128) * 3 + tap];
     VadFront* f = new VadFront();
+    memcpy(f->consts.e1b, w + L.e1b, sizeof(f->consts.e1b));
+    memcpy(f->consts.e2b, w + L.e2b, sizeof(f->consts.e2b));
+    memcpy(f->consts.e3b, w + L.e3b, sizeof(f->consts.e3b));
+    memcpy(f->consts.e4b, w + L.e4b, sizeof(f->consts.e4b));
+    for (int tap = 0; tap < 3; ++tap)
+        for (int oc = 0; oc < 128; ++oc) f->consts.w1side[tap][oc] = w[L.e1w + ((size_t)oc * 129 + 128) * 3 + tap];
     cudaError_t e = cudaMalloc(&f->wimg, img.size());
     if (e == cudaSuccess) e = cudaMemcpy(f->wimg, img.data(), img.size(), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMalloc(&f->slots, slots.size() * sizeof(uint2));
     if (e == cudaSuccess) e = cudaMemcpy(f->slots, slots.data(), slots.size() * sizeof(uint2), cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMalloc(&f->w1side, side.size() * 4);
-    if (e == cudaSuccess) e = cudaMemcpy(f->w1side, side.data(), side.size() * 4, cudaMemcpyHostToDevice);
     if (e != cudaSuccess) {
         vad_front_destroy(f);
         return cuda_fail(e, "VAD front weight image", __FILE__, __LINE__);
@@ -648,23 +748,48 @@ void vad_front_destroy(VadFront* f) {
     if (!f) return;
     cudaFree(f->wimg);
     cudaFree(f->slots);
-    cudaFree(f->w1side);
     delete f;
 }
 
 int launch_vad_front_fused(const VadFront* f, const void* d_audio, int fmt, long long audio_stride, int wins_per_stream, long long win0,
-                           long long total_windows, const float* e1b, const float* e2b, const float* e3b, const float* e4b, const float* bsum,
-                           float* d_pre, cudaStream_t st) {
+                           long long total_windows, float* d_pre, cudaStream_t st) {
     static PerDeviceOnce once;
     OSB_CUDA(once.run([&] { return cudaFuncSetAttribute(vf::k_vad_front_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, vf::kSmem); }));
     vf::Params p;
     p.audio = d_audio; p.fmt = fmt; p.audio_stride = audio_stride; p.wins_per_stream = wins_per_stream; p.win0 = win0; p.total = total_windows;
     p.n_tiles = (int)((total_windows + vf::kRows - 1) / vf::kRows);
-    p.wimg = f->wimg; p.slots = f->slots; p.e1b = e1b; p.e2b = e2b; p.e3b = e3b; p.e4b = e4b; p.bsum = bsum; p.w1side = f->w1side; p.pre = d_pre;
+    p.wimg = f->wimg; p.slots = f->slots; p.pre = d_pre; p.c = f->consts;
     const int grid = p.n_tiles < num_sms() ? p.n_tiles : num_sms();
     if (grid <= 0) return OSB_OK;
+    p.trace = nullptr;
+    const char* tpath = getenv("OSB_VF_TRACE");  // debug: clock stamps of CTA 0's first four tiles, written as text after a device sync
+    if (tpath) {
+        OSB_CUDA(cudaMalloc(&p.trace, 16 * 64 * 8));
+        OSB_CUDA(cudaMemset(p.trace, 0, 16 * 64 * 8));
+    }
     OSB_LAUNCH(vf::k_vad_front_fused, grid, vf::kThreads, vf::kSmem, st, p);
     OSB_CHECK_LAUNCH();
+    if (tpath) {
+        std::vector<unsigned long long> h(16 * 64);
+        OSB_CUDA(cudaDeviceSynchronize());
+        OSB_CUDA(cudaMemcpy(h.data(), p.trace, h.size() * 8, cudaMemcpyDeviceToHost));
+        cudaFree(p.trace);
+        if (FILE* f = fopen(tpath, "w")) {
+            unsigned long long t0 = ~0ull;
+            for (size_t i = 0; i < h.size(); ++i) if ((i % 64) < 40 && h[i] && h[i] < t0) t0 = h[i];
+            static const char* names[4] = {"mma", "epi", "stage", "prod"};
+            for (int r = 0; r < 4; ++r)
+                for (int it = 0; it < 4; ++it) {
+                    fprintf(f, "%s tile%d:", names[r], it);
+                    for (int e = 0; e < 64; ++e) {
+                        const unsigned long long v = h[(r * 4 + it) * 64 + e];
+                        if (v) fprintf(f, " %d=%llu", e, e < 40 ? v - t0 : v);
+                    }
+                    fprintf(f, "\n");
+                }
+            fclose(f);
+        }
+    }
     return OSB_OK;
 }
 
