@@ -8,6 +8,11 @@
 // divergent constant-cache or shared-memory bank traffic), grid = multiple of 148 CTAs.
 // The interpolation is IEEE f64 with explicit _rn intrinsics so that nvcc cannot contract
 // mul+add into an FMA: numpy's arr_interp computes slope*(x-xp[i]) + fp[i] as two roundings.
+#include <cstdlib>
+#include <map>
+#include <mutex>
+#include <vector>
+
 #include "common.cuh"
 
 namespace osb {
@@ -101,6 +106,10 @@ struct LinArgs {
     void* out;
     long long n_in, n_out, batch, in_stride, out_stride;
     double step_o, step_n;  // 1/(n_in-1), 1/(n_out-1) formed in f64 on the host like np.linspace
+    int exact_int;          // 1: the integer fast path below is provably bit-identical for these sizes
+    const unsigned* tab;    // exact_int: per output j, (floor(p) << 16) | (1 << 15 if interior coincidence) | remainder r
+    unsigned long long magic;  // ceil(2^shift / (m-1))
+    int shift;                 // 32 + ceil(log2(m-1))
 };
 
 template <int IN_FMT>
@@ -140,6 +149,33 @@ __device__ __forceinline__ int interp_one(const void* in, long long j, const Lin
     return __double2int_rz(y);  // astype(int16): truncation toward zero (|y| <= 32768)
 }
 
+// Integer fast path.  In exact arithmetic output j sits at p = j (n-1) / (m-1) = i + r / (m-1) and is y = f0 + (f1 - f0) r / (m-1), a rational
+// with denominator m-1.  numpy's float64 evaluation differs from it by < 3e-11 (n-1) (two roundings on each grid point, a division, a
+// multiply and an add on |values| <= 65535), so whenever y is NOT an integer -- at least 1 / (m-1) away from one -- truncating the
+// exact value gives numpy's int16 bit for bit; the host enables this path only for m <= 32768 and (n-1)(m-1) <= 1e8, a margin of > 100x.
+// The same margin makes the float64 bucket search land on i = floor(p) whenever r != 0.  Left to the float64 path (returns false):
+// interior grid coincidences (r == 0, flagged in the table) and exactly integral interpolants with f1 != f0 (~1 % of the outputs for
+// 160 -> 320), where the sign of a 1e-12 rounding error decides the truncation.  The two ends are exact in numpy as well (xn == xo).
+// Per output: one table word (i, r: the same for every chunk), two samples, one multiply-shift division by the invariant m-1.
+template <int IN_FMT>
+__device__ __forceinline__ bool interp_int(const void* in, long long j, const LinArgs& a, int& y) {
+    const unsigned e = __ldg(a.tab + j);
+    const unsigned i = e >> 16, r = e & 0x7FFFu;
+    if (e & 0x8000u) return false;                 // interior coincidence of the two grids
+    const int f0 = load_in<IN_FMT>(in, i);
+    if (r == 0) { y = f0; return true; }           // j = 0 or j = m-1
+    const int f1 = load_in<IN_FMT>(in, i + 1);
+    const unsigned den = (unsigned)(a.n_out - 1);
+    // U = (y + 32768) (m-1) >= 0 and < 2^31; q = floor(U / den) by multiply-shift (Granlund-Montgomery, exact for 32-bit dividends)
+    const unsigned U = (unsigned)(f0 + 32768) * den + (unsigned)((f1 - f0) * (int)r);
+    const unsigned q = (unsigned)(((unsigned long long)U * a.magic) >> a.shift);
+    const unsigned rem = U - q * den;
+    if (rem == 0 && f1 != f0) return false;        // exactly integral: float64's rounding error decides
+    const int yf = (int)q - 32768;                 // floor of the exact value
+    y = (yf >= 0 || rem == 0) ? yf : yf + 1;       // astype(int16) truncates toward zero
+    return true;
+}
+
 template <int IN_FMT, int OUT_FMT>
 __global__ void __launch_bounds__(256) k_resample_linear(LinArgs a, int vec_ok) {
     const long long groups = (a.n_out + 7) / 8;
@@ -150,8 +186,28 @@ __global__ void __launch_bounds__(256) k_resample_linear(LinArgs a, int vec_ok) 
         const long long c = g / groups, j0 = (g - c * groups) * 8;
         const void* in = reinterpret_cast<const char*>(a.in) + c * a.in_stride * in_es;
         int v[8];
+        if (a.exact_int) {
+            unsigned slow = 0;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) v[k] = (j0 + k < a.n_out) ? interp_one<IN_FMT>(in, j0 + k, a) : 0;
+            for (int k = 0; k < 8; ++k) {
+                v[k] = 0;
+                if (j0 + k < a.n_out && !interp_int<IN_FMT>(in, j0 + k, a, v[k])) slow |= 1u << k;
+            }
+            // the rare float64 evaluations: every pass, each lane that still has one takes its lowest; ~1 pass per warp iteration
+            while (__any_sync(0xffffffffu, slow != 0)) {
+                if (slow) {
+                    const int k = __ffs(slow) - 1;
+                    slow &= slow - 1;
+                    const int y = interp_one<IN_FMT>(in, j0 + k, a);
+#pragma unroll
+                    for (int kk = 0; kk < 8; ++kk)
+                        if (kk == k) v[kk] = y;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = (j0 + k < a.n_out) ? interp_one<IN_FMT>(in, j0 + k, a) : 0;
+        }
         if (OUT_FMT == OSB_FMT_PCM16) {
             int16_t* o = reinterpret_cast<int16_t*>(a.out) + c * a.out_stride + j0;
             if (vec_ok && j0 + 8 <= a.n_out) {
@@ -184,6 +240,33 @@ static int launch_linear_out(const LinArgs& a, int out_fmt, int vec_ok, int grid
         default: set_error("invalid argument: out_fmt %d", out_fmt); return OSB_ERR_INVALID_ARG;
     }
     OSB_CHECK_LAUNCH();
+    return OSB_OK;
+}
+
+// (i, r) table of the integer fast path, per (device, n_in, n_out); built once, a few hundred words for the realtime sizes
+struct LinTab { unsigned* d = nullptr; };
+static std::mutex g_lin_mu;
+static std::map<unsigned long long, LinTab> g_lin_tabs;
+
+static int linear_table(long long n, long long m, const unsigned** out) {
+    int dev = 0;
+    OSB_CUDA(cudaGetDevice(&dev));
+    const unsigned long long key = ((unsigned long long)dev << 56) ^ ((unsigned long long)n << 24) ^ (unsigned long long)m;
+    std::lock_guard<std::mutex> lk(g_lin_mu);
+    auto it = g_lin_tabs.find(key);
+    if (it == g_lin_tabs.end()) {
+        std::vector<unsigned> h((size_t)m);
+        for (long long j = 0; j < m; ++j) {
+            const long long num = j * (n - 1), i = num / (m - 1), r = num - i * (m - 1);
+            const bool interior = (r == 0) && j != 0 && j != m - 1;
+            h[(size_t)j] = ((unsigned)i << 16) | (interior ? 0x8000u : 0u) | (unsigned)r;
+        }
+        LinTab t;
+        OSB_CUDA(cudaMalloc(&t.d, h.size() * sizeof(unsigned)));
+        OSB_CUDA(cudaMemcpy(t.d, h.data(), h.size() * sizeof(unsigned), cudaMemcpyHostToDevice));
+        it = g_lin_tabs.emplace(key, t).first;
+    }
+    *out = it->second.d;
     return OSB_OK;
 }
 
@@ -236,6 +319,16 @@ int osb_resample_linear_dev(const void* d_in, int in_fmt, void* d_out, int out_f
     a.in_stride = in_stride; a.out_stride = out_stride;
     a.step_o = n_in > 1 ? 1.0 / (double)(n_in - 1) : 0.0;
     a.step_n = n_out > 1 ? 1.0 / (double)(n_out - 1) : 0.0;
+    a.exact_int = (n_in > 1 && n_in <= 65536 && n_out > 1 && n_out <= 32768 && (double)(n_in - 1) * (double)(n_out - 1) <= 1.0e8) ? 1 : 0;
+    if (const char* e = getenv("OSB_LINEAR_F64")) a.exact_int = (e[0] == '1') ? 0 : a.exact_int;  // cross-check switch
+    a.tab = nullptr; a.magic = 0; a.shift = 0;
+    if (a.exact_int) {
+        if ((rc = linear_table(n_in, n_out, &a.tab))) return rc;
+        int l = 0;
+        while ((1ll << l) < n_out - 1) ++l;
+        a.shift = 32 + l;
+        a.magic = (unsigned long long)((((unsigned __int128)1 << a.shift) + (unsigned)(n_out - 2)) / (unsigned)(n_out - 1));
+    }
     int vec_ok = (out_fmt == OSB_FMT_PCM16) && (((uintptr_t)d_out & 15) == 0) && (out_stride % 8 == 0);
     long long groups = (n_out + 7) / 8 * batch;
     int grid = grid_for((size_t)groups, 256);

@@ -477,11 +477,12 @@ __device__ __forceinline__ float tanhf_fast(float x) {
     return copysignf(__fmul_rn(__fsub_rn(1.0f, t), __frcp_rn(__fadd_rn(1.0f, t))), x);
 }
 
-// Gate pre-activation of window w (flattened (stream, t) index of the launch), gate row `own`.  Linear: [w][512].  Tiled (what the
-// fused front writes, vad_front.cu): [w / 128][own / 4][w % 128][own % 4] -- a warp of the front stores 32 rows x 16 B as one contiguous
-// 512-byte run, and the 32-byte sector this kernel touches for window w also holds window w +- 1 of the same stream, its next step.
+// Gate pre-activation of window w (flattened (stream, t) index of the launch), gate row `own`.  Linear: [w][512].  Interleaved (what the
+// fused front writes, vad_front.cu): [w / 8][own / 8][w % 8][own % 8] -- eight lanes (rows) of the front's epilogue fill 256 contiguous
+// bytes with two store instructions, the eight gate rows a quarter-warp of this kernel reads are one 32-byte sector (as in the linear
+// layout), and the eight windows a stream consumes over eight steps sit in one contiguous 16 KB block.
 __device__ __forceinline__ long long pre_at(long long w, int own, bool tiled) {
-    return tiled ? (w >> 7) * 65536 + (long long)(own >> 2) * 512 + (w & 127) * 4 + (own & 3) : w * kGates + own;
+    return tiled ? (w >> 3) * 4096 + (long long)((own >> 3) * 64 + (own & 7)) + (w & 7) * 8 : w * kGates + own;
 }
 
 constexpr int kHq = 36;  // floats between the four 32-float quarters of h in shared memory: the quarters sit in different banks
@@ -499,11 +500,11 @@ struct RecurCfg {
 __host__ __device__ inline int recur_row(int warp, int r) { return 128 * (r & 3) + 8 * warp + (r >> 2); }
 
 // whh_perm: float4 chunk c = i*8 + kg of thread tid at [(c*512 + tid)*4], i = row of the block, kg = column group
-template <int S>
+template <int S, bool ILV>  // ILV: the pre-activations come in the fused front's interleaved layout (pre_at)
 __global__ void __launch_bounds__(512, 1) k_vad_recur(const float* __restrict__ pre, long long pre_stream_stride, int n_steps,
                                                       const float4* __restrict__ whh_perm, const float* __restrict__ dw, float db,
                                                       float* __restrict__ state, float* __restrict__ probs, long long probs_stride,
-                                                      long long win0, int batch, const float* __restrict__ pre_bias) {
+                                                      long long win0, int batch) {
     constexpr int RKG = RecurCfg<S>::RKG, SKG = RecurCfg<S>::SKG;
     extern __shared__ __align__(16) float sm[];
     float4* w_sm = reinterpret_cast<float4*>(sm);                 // [4][SKG][512] float4
@@ -532,29 +533,33 @@ __global__ void __launch_bounds__(512, 1) k_vad_recur(const float* __restrict__ 
         c[s] = s < ns ? st[kHid + unit] : 0.f;
         if (q == 0) h_sm[s * 4 * kHq + upos] = s < ns ? st[unit] : 0.f;
     }
-    long long w0s[S];  // first window of the stream in the launch's flattened (stream, t) order
+    const float* p[S];  // this thread's gate row of the NEXT window to load, per stream
+    int ph[S];          // ILV: that window's index mod 8 inside its 16 KB block
     float pre_v[S];
-    // The fused front (pre_bias != null) leaves W_ih.x without b_ih + b_hh and in its own tiled layout (pre_at): the row's bias is
-    // added here with the rounding the GEMM epilogue of the other engines applies, fl(acc + b), off the serial chain.
-    const bool tiled = pre_bias != nullptr;
-    const float pb = tiled ? pre_bias[own] : 0.f;
 #pragma unroll
     for (int s = 0; s < S; ++s) {
-        w0s[s] = (long long)(b0 + (s < ns ? s : 0)) * (pre_stream_stride / kGates);
-        pre_v[s] = n_steps > 0 ? pre[pre_at(w0s[s], own, tiled)] : 0.f;
+        const long long w0 = (long long)(b0 + (s < ns ? s : 0)) * (pre_stream_stride / kGates);  // first window of the stream in the launch
+        p[s] = pre + pre_at(w0, own, ILV);
+        ph[s] = (int)(w0 & 7);
+        pre_v[s] = n_steps > 0 ? *p[s] : 0.f;
     }
+    auto advance = [&](int s) {  // p[s] -> the same gate row of the next window
+        if (ILV) {
+            ph[s] = (ph[s] + 1) & 7;
+            p[s] += ph[s] ? 8 : 4096 - 56;
+        } else p[s] += kGates;
+    };
     __syncthreads();
     for (int t = 0; t < n_steps; ++t) {
         const float* hr = h_sm + (t & 1) * (S * 4 * kHq);          // h of the previous step
         float* hw = h_sm + ((t + 1) & 1) * (S * 4 * kHq);          // h of this step
         float* pw = part_sm + (t & 63) * (S * 17);
-        float pre_next[S], pre_b[S];
-#pragma unroll
-        for (int s = 0; s < S; ++s) pre_b[s] = __fadd_rn(pre_v[s], pb);  // loaded a step ago: ready long before the matvec ends
+        float pre_next[S];
         float2 a[4][S];
 #pragma unroll
         for (int s = 0; s < S; ++s) {
-            pre_next[s] = (t + 1 < n_steps) ? pre[pre_at(w0s[s] + t + 1, own, tiled)] : 0.f;  // prefetch (consumed one step later)
+            advance(s);
+            pre_next[s] = (t + 1 < n_steps) ? *p[s] : 0.f;  // prefetch (consumed one step later)
 #pragma unroll
             for (int i = 0; i < 4; ++i) a[i][s] = make_float2(0.f, 0.f);
         }
@@ -584,7 +589,7 @@ __global__ void __launch_bounds__(512, 1) k_vad_recur(const float* __restrict__ 
             const float v0 = (hi ? p2 : p0) + __shfl_xor_sync(0xffffffffu, hi ? p0 : p2, 8);
             const float v1 = (hi ? p3 : p1) + __shfl_xor_sync(0xffffffffu, hi ? p1 : p3, 8);
             const bool hi2 = q & 2;
-            x[s] = ((hi2 ? v1 : v0) + __shfl_xor_sync(0xffffffffu, hi2 ? v0 : v1, 16)) + pre_b[s];
+            x[s] = ((hi2 ? v1 : v0) + __shfl_xor_sync(0xffffffffu, hi2 ? v0 : v1, 16)) + pre_v[s];
         }
 #pragma unroll
         for (int s = 0; s < S; ++s) {
@@ -657,11 +662,11 @@ struct RecurMbCfg {
 // The same recurrence for S >= 2 streams per CTA: there the in-warp cell update of k_vad_recur costs more than it saves (every
 // lane repeats the cell arithmetic of its unit: measured 33.7 ms against 30.5 ms on 256 streams), so the gates go through shared
 // memory to 128 S cell threads and the step takes two barriers.  Same row dealing, same whh_perm, same arithmetic.
-template <int S>
+template <int S, bool ILV>
 __global__ void __launch_bounds__(512, 1) k_vad_recur_mb(const float* __restrict__ pre, long long pre_stream_stride, int n_steps,
                                                       const float4* __restrict__ whh_perm, const float* __restrict__ dw, float db,
                                                       float* __restrict__ state, float* __restrict__ probs, long long probs_stride,
-                                                      long long win0, int batch, const float* __restrict__ pre_bias) {
+                                                      long long win0, int batch) {
     constexpr int RKG = RecurMbCfg<S>::RKG, SKG = RecurMbCfg<S>::SKG;
     extern __shared__ __align__(16) float sm[];
     float4* w_sm = reinterpret_cast<float4*>(sm);                 // [4][SKG][512] float4
@@ -689,27 +694,31 @@ __global__ void __launch_bounds__(512, 1) k_vad_recur_mb(const float* __restrict
     if (tid < S * kHid) h_sm[hpos] = cell ? st[cu] : 0.f;
     if (cell) c = st[kHid + cu];
     if (tid < kHid) dw_sm[tid] = dw[tid];
-    long long w0s[S];  // first window of the stream in the launch's flattened (stream, t) order
+    const float* p[S];  // this thread's gate row of the NEXT window to load, per stream
+    int ph[S];          // ILV: that window's index mod 8 inside its 16 KB block
     float pre_v[S];
-    // The fused front (pre_bias != null) leaves W_ih.x without b_ih + b_hh and in its own tiled layout (pre_at): the row's bias is
-    // added here with the rounding the GEMM epilogue of the other engines applies, fl(acc + b), off the serial chain.
-    const bool tiled = pre_bias != nullptr;
-    const float pb = tiled ? pre_bias[own] : 0.f;
 #pragma unroll
     for (int s = 0; s < S; ++s) {
-        w0s[s] = (long long)(b0 + (s < ns ? s : 0)) * (pre_stream_stride / kGates);
-        pre_v[s] = n_steps > 0 ? pre[pre_at(w0s[s], own, tiled)] : 0.f;
+        const long long w0 = (long long)(b0 + (s < ns ? s : 0)) * (pre_stream_stride / kGates);  // first window of the stream in the launch
+        p[s] = pre + pre_at(w0, own, ILV);
+        ph[s] = (int)(w0 & 7);
+        pre_v[s] = n_steps > 0 ? *p[s] : 0.f;
     }
+    auto advance = [&](int s) {  // p[s] -> the same gate row of the next window
+        if (ILV) {
+            ph[s] = (ph[s] + 1) & 7;
+            p[s] += ph[s] ? 8 : 4096 - 56;
+        } else p[s] += kGates;
+    };
     float* pr = probs + (long long)(b0 + (cell ? cs : 0)) * probs_stride + win0;
     __syncthreads();
     for (int t = 0; t < n_steps; ++t) {
-        float pre_next[S], pre_b[S];
-#pragma unroll
-        for (int s = 0; s < S; ++s) pre_b[s] = __fadd_rn(pre_v[s], pb);  // loaded a step ago: ready long before the matvec ends
+        float pre_next[S];
         float2 a[4][S];
 #pragma unroll
         for (int s = 0; s < S; ++s) {
-            pre_next[s] = (t + 1 < n_steps) ? pre[pre_at(w0s[s] + t + 1, own, tiled)] : 0.f;  // prefetch (consumed one step later)
+            advance(s);
+            pre_next[s] = (t + 1 < n_steps) ? *p[s] : 0.f;  // prefetch (consumed one step later)
 #pragma unroll
             for (int i = 0; i < 4; ++i) a[i][s] = make_float2(0.f, 0.f);
         }
@@ -737,7 +746,7 @@ __global__ void __launch_bounds__(512, 1) k_vad_recur_mb(const float* __restrict
             const float v1 = (hi ? p3 : p1) + __shfl_xor_sync(0xffffffffu, hi ? p1 : p3, 8);
             const bool hi2 = q & 2;
             const float r = (hi2 ? v1 : v0) + __shfl_xor_sync(0xffffffffu, hi2 ? v0 : v1, 16);
-            g_sm[s * kGates + own] = r + pre_b[s];
+            g_sm[s * kGates + own] = r + pre_v[s];
         }
         __syncthreads();
         if (tid < S * kHid) {
@@ -924,7 +933,9 @@ static int vad_score(VadModel* m, const void* d_audio, int fmt, int64_t n, int64
     // 12 / 8 / 4 whole waves per launch.  Larger chunks amortise the launches and the recurrence prologue (measured: x4 is
     // 9 % faster on the front than one wave) at ~0.7 GB of activations per chunk, part of which leaves L2.
     // (the fused front keeps nothing but the pre-activations in HBM: 16 waves of 128-window tiles per launch, 0.6 GB)
-    long long T = ((long long)OSB_NUM_SMS * 128 * (m->use_tc == 2 ? 16 : 4) + batch - 1) / batch;
+    int waves = m->use_tc == 2 ? 16 : 4;
+    if (const char* e = getenv("OSB_VAD_CHUNK_WAVES")) { const int v = atoi(e); if (v >= 1 && v <= 256) waves = v; }
+    long long T = ((long long)OSB_NUM_SMS * 128 * waves + batch - 1) / batch;
     if (T < 1) T = 1;
     if (T > n_win) T = n_win;
     const long long W = batch * T;  // windows per chunk
@@ -946,9 +957,12 @@ static int vad_score(VadModel* m, const void* d_audio, int fmt, int64_t n, int64
     }
     static PerDeviceOnce once;
     OSB_CUDA(once.run([&] {
-        cudaError_t e = cudaFuncSetAttribute(k_vad_recur<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, RecurCfg<1>::smem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_vad_recur_mb<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, RecurMbCfg<2>::smem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_vad_recur_mb<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, RecurMbCfg<4>::smem);
+        cudaError_t e = cudaFuncSetAttribute(k_vad_recur<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, RecurCfg<1>::smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_vad_recur<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, RecurCfg<1>::smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_vad_recur_mb<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, RecurMbCfg<2>::smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_vad_recur_mb<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, RecurMbCfg<2>::smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_vad_recur_mb<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, RecurMbCfg<4>::smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_vad_recur_mb<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, RecurMbCfg<4>::smem);
         return e;
     }));
     // streams per recurrence CTA: as few as keep the grid within one wave of SMs
@@ -1001,13 +1015,12 @@ static int vad_score(VadModel* m, const void* d_audio, int fmt, int64_t n, int64
         }
         // recurrence over the chunk's t windows, one CTA per stream
         const unsigned rg = (unsigned)((batch + rs - 1) / rs);
-        const float* rbias = fused ? m->bsum : nullptr;
-        if (rs == 1) OSB_LAUNCH(k_vad_recur<1>, rg, 512, RecurCfg<1>::smem, st, pre, (long long)t * kGates, t, (const float4*)m->whh_perm, m->dw, m->db,
-                                d_state, d_probs, (long long)probs_stride, w0, (int)batch, rbias);
-        else if (rs == 2) OSB_LAUNCH(k_vad_recur_mb<2>, rg, 512, RecurMbCfg<2>::smem, st, pre, (long long)t * kGates, t, (const float4*)m->whh_perm, m->dw, m->db,
-                                     d_state, d_probs, (long long)probs_stride, w0, (int)batch, rbias);
-        else OSB_LAUNCH(k_vad_recur_mb<4>, rg, 512, RecurMbCfg<4>::smem, st, pre, (long long)t * kGates, t, (const float4*)m->whh_perm, m->dw, m->db,
-                        d_state, d_probs, (long long)probs_stride, w0, (int)batch, rbias);
+#define OSB_RECUR(KERN, SMEM) OSB_LAUNCH(KERN, rg, 512, SMEM, st, pre, (long long)t * kGates, t, (const float4*)m->whh_perm, m->dw, m->db, d_state, d_probs, \
+                                         (long long)probs_stride, w0, (int)batch)
+        if (rs == 1) { if (fused) OSB_RECUR((k_vad_recur<1, true>), RecurCfg<1>::smem); else OSB_RECUR((k_vad_recur<1, false>), RecurCfg<1>::smem); }
+        else if (rs == 2) { if (fused) OSB_RECUR((k_vad_recur_mb<2, true>), RecurMbCfg<2>::smem); else OSB_RECUR((k_vad_recur_mb<2, false>), RecurMbCfg<2>::smem); }
+        else { if (fused) OSB_RECUR((k_vad_recur_mb<4, true>), RecurMbCfg<4>::smem); else OSB_RECUR((k_vad_recur_mb<4, false>), RecurMbCfg<4>::smem); }
+#undef OSB_RECUR
         OSB_CHECK_LAUNCH();
     }
     return OSB_OK;
@@ -1097,7 +1110,7 @@ int osb_vad_create(const float* weights_host, size_t n_floats, void** handle) {
         }
     }
     {
-        VadFrontLayout L{oBasis, oE1w, oE1b, oE2w, oE2b, oE3w, oE3b, oE4w, oE4b, oWih};
+        VadFrontLayout L{oBasis, oE1w, oE1b, oE2w, oE2b, oE3w, oE3b, oE4w, oE4b, oWih, oBih, oBhh};
         if ((rc = vad_front_create(w, L, &m->fused))) {
             delete m;
             return rc;

@@ -56,6 +56,7 @@ enum { A0 = 0, A1 = 1, M0 = 2, M1 = 3 };
 
 struct Consts {
     float e1b[128], e2b[64], e3b[64], e4b[128];
+    float bsum[512];            // b_ih + b_hh
     float w1side[3][128];       // enc1 weights of input channel 128 (the Nyquist bin), per tap
 };
 
@@ -69,7 +70,7 @@ struct Params {
     int n_tiles;
     const uint8_t* wimg;        // weight image
     const uint2* slots;         // [57] (byte offset, bytes) in consumption order
-    float* pre;                 // [tiles][128 column groups][128 rows][4]: W_ih.x, tiled (vad.cu pre_at); b_ih + b_hh is added by the recurrence
+    float* pre;                 // [windows / 8][64 column groups][8][8]: W_ih.x + b_ih + b_hh, interleaved (vad.cu pre_at)
     // per-channel vectors the epilogue needs, in the kernel's constant bank: every lane of a warp reads the same element (a warp holds
     // 32 rows of the same columns), which the constant cache serves as a broadcast; with 227 KB of shared memory carved out there is
     // no L1 left for them and the L2 round trip (~700 cycles per dependent load) was the epilogue's whole cost
@@ -555,9 +556,10 @@ struct EpiRole {
         wait_acc(j);
         const uint32_t ta = sm.tmem + lane_base + (uint32_t)(128 * j + 64 * half);
         const long long wi = tile * kRows + row;
-        // tiled layout [tile][column / 4][row][column % 4] (vad.cu pre_at): lane = row, so one store instruction of a warp is one contiguous
-        // 512-byte run -- with the linear [window][512] layout it was 32 half-sectors 2 KB apart and this loop cost 9,000 cycles per block
-        float* out = p.pre + tile * 65536 + (long long)(32 * j + 16 * half) * 512 + row * 4;
+        // interleaved layout [window / 8][column / 8][window % 8][column % 8] (vad.cu pre_at): lane = row, so eight lanes fill 256
+        // contiguous bytes with two store instructions -- with the linear [window][512] layout an instruction wrote 32 half-sectors
+        // 2 KB apart and this loop cost 9,000 cycles per block
+        float* out = p.pre + (wi >> 3) * 4096 + (long long)(16 * j + 8 * half) * 64 + (wi & 7) * 8;
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             uint32_t v[16];
@@ -565,7 +567,12 @@ struct EpiRole {
             if (u == 3) free_acc(j);
             if (wi < p.total) {
 #pragma unroll
-                for (int q = 0; q < 4; ++q) *reinterpret_cast<uint4*>(out + (4 * u + q) * 512) = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                for (int q = 0; q < 4; ++q) {
+                    const int col = 128 * j + 64 * half + 16 * u + 4 * q;  // constant bank, warp-uniform
+                    *reinterpret_cast<float4*>(out + (2 * u + (q >> 1)) * 64 + 4 * (q & 1)) =
+                        make_float4(__uint_as_float(v[4 * q]) + p.c.bsum[col], __uint_as_float(v[4 * q + 1]) + p.c.bsum[col + 1],
+                                    __uint_as_float(v[4 * q + 2]) + p.c.bsum[col + 2], __uint_as_float(v[4 * q + 3]) + p.c.bsum[col + 3]);
+                }
             }
         }
     }
@@ -730,6 +737,7 @@ int vad_front_create(const float* w, const VadFrontLayout& L, VadFront** out) {
     memcpy(f->consts.e2b, w + L.e2b, sizeof(f->consts.e2b));
     memcpy(f->consts.e3b, w + L.e3b, sizeof(f->consts.e3b));
     memcpy(f->consts.e4b, w + L.e4b, sizeof(f->consts.e4b));
+    for (int i = 0; i < 512; ++i) f->consts.bsum[i] = w[L.bih + i] + w[L.bhh + i];
     for (int tap = 0; tap < 3; ++tap)
         for (int oc = 0; oc < 128; ++oc) f->consts.w1side[tap][oc] = w[L.e1w + ((size_t)oc * 129 + 128) * 3 + tap];
     cudaError_t e = cudaMalloc(&f->wimg, img.size());

@@ -9,14 +9,13 @@ struct VadFront;  // device-resident weight image in the kernel's consumption or
 
 // float offsets of the tensors inside the flat host weight blob (vad/silero.py WEIGHT_LAYOUT)
 struct VadFrontLayout {
-    size_t basis, e1w, e1b, e2w, e2b, e3w, e3b, e4w, e4b, wih;
+    size_t basis, e1w, e1b, e2w, e2b, e3w, e3b, e4w, e4b, wih, bih, bhh;
 };
 
 int vad_front_create(const float* weights_host, const VadFrontLayout& layout, VadFront** out);
 void vad_front_destroy(VadFront* f);
 // windows are rows (stream, t): window w of the launch = stream w / wins_per_stream, window win0 + w % wins_per_stream of that stream;
-// d_pre (ceil(total_windows / 128) * 65536 floats) receives W_ih.x in the tiled layout of vad.cu's pre_at(), WITHOUT b_ih + b_hh (the
-// recurrence kernel adds the bias of its gate row)
+// d_pre (ceil(total_windows / 128) * 65536 floats) receives W_ih.x + b_ih + b_hh in the interleaved layout of vad.cu's pre_at()
 int launch_vad_front_fused(const VadFront* f, const void* d_audio, int fmt, long long audio_stride, int wins_per_stream, long long win0,
                            long long total_windows, float* d_pre, cudaStream_t st);
 

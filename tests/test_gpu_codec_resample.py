@@ -51,6 +51,27 @@ def test_linear_resample_bit_exact(gpu, ab, n, fr, to):
     assert ab._resample_linear(x.tobytes(), fr, to) == codec.resample_linear(x.tobytes(), fr, to)
 
 
+@pytest.mark.parametrize("n,m", [(160, 320), (480, 320), (2400, 1600), (320, 160), (441, 160), (161, 321), (7, 13), (1000, 3000), (2, 5)])
+def test_linear_resample_integer_fast_path_adversarial(gpu, n, m):
+    """The integer fast path of k_resample_linear against np.interp on inputs built to hit its hand-over cases: interpolants that are
+    exactly integral (sample differences that are multiples of m-1), grids with common factors (interior coincidences), flat segments,
+    full-scale steps, many independent chunks per launch.  Every output must equal numpy's float64 result bit for bit."""
+    rng = np.random.default_rng(n * 1000 + m)
+    batch = 257
+    x = rng.integers(-32768, 32768, (batch, n)).astype(np.int64)
+    x[0::5] = (x[0::5] // (m - 1)) * (m - 1)                 # differences divisible by m-1: exactly integral interpolants
+    x[1::7] = x[1::7, :1]                                    # flat
+    x[2::11] = np.where(rng.integers(0, 2, (len(x[2::11]), n)) > 0, 32767, -32768)  # full-scale steps
+    x[3::13] = np.cumsum(rng.integers(-3, 4, (len(x[3::13]), n)), axis=1) * (m - 1) // 2  # half-integral slopes
+    x = np.clip(x, -32768, 32767).astype(np.int16)
+    out = np.empty((batch, m), np.int16)
+    gpu.call("osb_resample_linear_host", gpu.ptr(x), gpu.FMT_PCM16, gpu.ptr(out), gpu.FMT_PCM16, n, m, batch, n, m)
+    xo, xn = np.linspace(0, 1, n), np.linspace(0, 1, m)
+    for b in range(batch):
+        want = np.interp(xn, xo, x[b].astype(np.float32)).astype(np.int16)   # audio_buffer.py:28-33
+        assert np.array_equal(out[b], want), (b, np.nonzero(out[b] != want)[0][:5])
+
+
 def test_linear_resample_edges(gpu, ab):
     assert ab._resample_linear(b"", 8000, 16000) == b""
     assert ab.decode_audio_to_pcm16(b"", "g711_ulaw", 16000) == b""
