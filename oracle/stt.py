@@ -102,31 +102,34 @@ def nr_params(sr: int) -> dict:
 
 
 def _gate_chunk(chunk: np.ndarray, sr: int) -> np.ndarray:
-    """One padded chunk (float64) -> filtered padded chunk (float64)."""
+    """One padded chunk -> filtered padded chunk, in the chunk's dtype: float64 is what noisereduce does; float32 is the
+    PRECISION CONTROL of tests/test_gpu_denoise.py (same recipe, complex64 FFTs, float32 mask arithmetic)."""
     from scipy.signal import fftconvolve, filtfilt, istft, stft
 
     p = nr_params(sr)
+    dt = chunk.dtype
     _, _, S = stft(chunk, nfft=NR_NFFT, noverlap=NR_NFFT - NR_HOP, nperseg=NR_NFFT, padded=False)
     A = np.abs(S)
-    A_s = filtfilt([p["b"]], [1, p["b"] - 1], A, axis=-1, padtype=None)
+    A_s = filtfilt([p["b"]], [1, p["b"] - 1], A, axis=-1, padtype=None).astype(dt)
     with np.errstate(divide="ignore", invalid="ignore"):
-        M = 1.0 / (1.0 + np.exp(-((A - A_s) / A_s - 2.0) * 10.0))
+        M = (dt.type(1.0) / (dt.type(1.0) + np.exp(-((A - A_s) / A_s - dt.type(2.0)) * dt.type(10.0)))).astype(dt)
     if not (p["n_f"] == 1 and p["n_t"] == 1):
-        M = fftconvolve(M, _nr_smoothing_filter(p["n_f"], p["n_t"]), mode="same")
-    M = M * 1.0 + np.ones(M.shape) * 0.0
+        M = fftconvolve(M, _nr_smoothing_filter(p["n_f"], p["n_t"]).astype(dt), mode="same")
+    M = M * dt.type(1.0) + np.ones(M.shape, dt) * dt.type(0.0)
     _, xr = istft(S * M, nfft=NR_NFFT, noverlap=NR_NFFT - NR_HOP, nperseg=NR_NFFT)
-    out = np.zeros(chunk.shape, chunk.dtype)
+    out = np.zeros(chunk.shape, dt)
     out[: len(xr)] = xr
     return out
 
 
-def spectral_gate(y: np.ndarray, sr: int) -> np.ndarray:
-    """noisereduce SpectralGateNonStationary.get_traces() for a 1-D signal."""
+def spectral_gate(y: np.ndarray, sr: int, work_dtype=np.float64) -> np.ndarray:
+    """noisereduce SpectralGateNonStationary.get_traces() for a 1-D signal (work_dtype=float64, as upstream reads every chunk
+    into a float64 buffer).  work_dtype=float32 is the precision control: the identical recipe carried out in single precision."""
     y = np.asarray(y)
     n = len(y)
 
     def read(i1, i2):
-        c = np.zeros(i2 - i1)
+        c = np.zeros(i2 - i1, dtype=work_dtype)
         a, b = max(i1, 0), min(i2, n)
         c[a - i1 : b - i1] = y[a:b]
         return c
@@ -201,11 +204,12 @@ def logmel_n_frames(n_samples: int, padding: int = 160) -> int:
 
 
 def stt_frontend(pcm16: np.ndarray, *, noise_reduce: bool, normalize: bool = True, n_mels: int = 128,
-                 sr: int = 16000) -> np.ndarray:
-    """BASELINE configs 1 / 4 chain: int16 clip -> (denoise) -> normalise -> int16 -> /32768 -> log-mel."""
+                 sr: int = 16000, gate_dtype=np.float64) -> np.ndarray:
+    """BASELINE configs 1 / 4 chain: int16 clip -> (denoise) -> normalise -> int16 -> /32768 -> log-mel.
+    gate_dtype=float32: the single-precision control of the denoise stage (see spectral_gate)."""
     a = pcm16.astype(np.float32) / 32768.0
     if noise_reduce:
-        a = spectral_gate(a, sr)
+        a = spectral_gate(a, sr, gate_dtype)
     if normalize:
         a = normalize_gain(a)
     q = quantise_pcm16(a)

@@ -7,12 +7,16 @@ then the per-stage tolerances of test_gpu_logmel for what follows.
 import io
 import wave
 
+import json
+import os
+
 import numpy as np
 import pytest
 
 from oracle import stt
 
 pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 TOL = 1e-4
 
 
@@ -116,6 +120,7 @@ def test_stt_frontend_config4_chain(gpu):
     out = torch.empty((3, 128, nf), dtype=torch.float32, device="cuda")
     gpu.call("osb_stt_frontend_dev", x.data_ptr(), n, 3, n, 16000, 1, 1, 128, out.data_ptr(), torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
+    records = []
     for i in range(3):
         # stage-wise: (1) the GPU's denoised+normalised int16 is within 1e-4 of full scale (3 LSB) of the oracle's,
         q = np.empty(n, np.int16)
@@ -127,13 +132,37 @@ def test_stt_frontend_config4_chain(gpu):
         got = out[i].cpu().numpy()
         ref_stage = stt.logmel(q.astype(np.float32) / 32768.0, 128)
         assert (np.abs(got - ref_stage) / np.maximum(1.0, np.abs(ref_stage))).max() <= TOL
-        # (3) end to end.  The denoised audio itself is within ~5e-7 of the f64 oracle (tools/nr_err.py), but the chain
-        # requantises to int16 in between: < 0.1 % of samples round to the neighbouring LSB, and in gated (near-silent)
-        # stretches, where the signal is a few LSB, one flipped sample moves every mel cell of the frames that contain it
-        # by more than 1e-4.  (1) and (2) pin the stages; here only the bulk and the worst cell are bounded.
+        # (3) end to end.  The chain requantises to int16 between the denoiser and the log-mel (src/audio/preprocessing.py:23-25 truncates
+        # x * 32767): a float32 denoiser lands on the other side of an integer boundary for a few samples in 10,000, and in gated
+        # (near-silent) stretches, where the signal is a few LSB, one flipped sample moves every mel cell of the frames that contain it
+        # by more than 1e-4.  This is MEASURED, not assumed: the same metric is taken for a CPU control -- the oracle's own recipe
+        # carried out in float32 (complex64 scipy FFTs, oracle/stt.py spectral_gate(work_dtype=float32)) against the float64 oracle.
+        # Measured on B200 (profiles/r02_parity_config4.json): GPU 1.1-1.6 % of the cells beyond 1e-4 (control 0.8-1.3 %), 0.05-0.08 % of
+        # the int16 samples one LSB off (control 0.03-0.08 %), worst cell 1.5e-3 (control 1.4e-3): the same share, so the tolerance is a
+        # property of the reference's int16 round trip, not of this implementation.  Asserted: never more than 1 LSB; per clip within 2x
+        # of the measured rates; over the three clips no more than twice the control's misses and flips.
         ref = stt.stt_frontend(pcm[i], noise_reduce=True, normalize=True)
+        ctl = stt.stt_frontend(pcm[i], noise_reduce=True, normalize=True, gate_dtype=np.float32)
+        q_ref = stt.quantise_pcm16(a)
+        q_ctl = stt.quantise_pcm16(stt.normalize_gain(stt.spectral_gate(pcm[i].astype(np.float32) / 32768.0, 16000, np.float32)))
         err = np.abs(got - ref) / np.maximum(1.0, np.abs(ref))
-        assert (err <= TOL).mean() >= 0.97 and err.max() <= 5e-3, ((err <= TOL).mean(), err.max())
+        err_c = np.abs(ctl - ref) / np.maximum(1.0, np.abs(ref))
+        rec = {"clip": i, "gpu_cells_beyond_tol": float((err > TOL).mean()), "gpu_worst_cell": float(err.max()),
+               "control_cells_beyond_tol": float((err_c > TOL).mean()), "control_worst_cell": float(err_c.max()),
+               "gpu_int16_flips": float((q != q_ref).mean()), "control_int16_flips": float((q_ctl != q_ref).mean()),
+               "gpu_max_lsb": int(dq.max()), "control_max_lsb": int(np.abs(q_ctl.astype(np.int32) - q_ref.astype(np.int32)).max())}
+        records.append(rec)
+        print("config-4 chain parity:", rec)
+        assert rec["gpu_max_lsb"] <= 1 and rec["gpu_cells_beyond_tol"] <= 0.03 and rec["gpu_worst_cell"] <= 3e-3, rec
+    # over the three clips together (per clip the flip counts are a few dozen samples: too few for a ratio)
+    agg = {k: float(np.mean([r[k] for r in records])) for k in ("gpu_cells_beyond_tol", "control_cells_beyond_tol", "gpu_int16_flips", "control_int16_flips")}
+    print("config-4 chain parity, mean of 3 clips:", agg)
+    assert agg["gpu_cells_beyond_tol"] <= 2.0 * agg["control_cells_beyond_tol"], agg
+    assert agg["gpu_int16_flips"] <= 2.0 * agg["control_int16_flips"], agg
+    records.append(agg)
+    if os.path.isdir(os.path.join(ROOT, "gpurun_out")):
+        with open(os.path.join(ROOT, "gpurun_out", "parity_config4.json"), "w") as f:
+            json.dump(records, f, indent=1)
     # host-pointer entry == device entry
     mel = np.empty((3, 128, nf), np.float32)
     gpu.call("osb_stt_frontend_host", gpu.ptr(pcm), n, 3, n, 16000, 1, 1, 128, gpu.ptr(mel))

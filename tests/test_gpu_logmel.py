@@ -99,4 +99,8 @@ def test_logmel_batch_fused_normalise(gpu):
         assert _close(got, stt.logmel(q[i].astype(np.float32) / 32768.0, 128)) <= TOL
         ref = stt.stt_frontend(pcm[i], noise_reduce=False, normalize=True)
         err = np.abs(got - ref) / np.maximum(1.0, np.abs(ref))
-        assert (err <= TOL).mean() >= 0.999 and err.max() <= 2e-3, ((err <= TOL).mean(), err.max())
+        flips = float((q[i] != ref_q).mean())
+        print(f"normalise-only chain clip {i}: int16 flips {flips:.5%}, cells beyond 1e-4 {(err > TOL).mean():.5%}, worst {err.max():.2e}")
+        # the only difference to the oracle is the gain's last float32 bit (tree reduction vs numpy's pairwise sum): a sample whose
+        # product sits within that bit of an integer lands on the neighbouring LSB.  Bounds = 2x the rates measured on B200.
+        assert flips <= 4e-4 and (err > TOL).mean() <= 1e-3 and err.max() <= 2e-3, (flips, (err > TOL).mean(), err.max())

@@ -19,11 +19,15 @@ def session(gpu):
     return VadSession(random_init_weights(1002))
 
 
-def _mel_check(got, ref, frac_min, worst):
+def _mel_check(got, ref, control):
+    """Cells beyond the 1e-4 tolerance: no more than twice what the single-precision CPU control of the same chain misses (the int16
+    requantisation between denoiser and log-mel turns float32-vs-float64 ties into LSB flips: tests/test_gpu_denoise.py), and within
+    2x of the rates measured on B200 (<= 1.6 % of the cells, worst cell 1.5e-3); per clip the control's own rate varies by 2x, hence 3x."""
     err = np.abs(got - ref) / np.maximum(1.0, np.abs(ref))
-    frac = float((err <= MEL_TOL).mean())
-    assert got.shape == ref.shape and frac >= frac_min and err.max() <= worst, (frac, float(err.max()))
-    return frac, float(err.max())
+    err_c = np.abs(control - ref) / np.maximum(1.0, np.abs(ref))
+    bad, bad_c = float((err > MEL_TOL).mean()), float((err_c > MEL_TOL).mean())
+    assert got.shape == ref.shape and bad <= max(3.0 * bad_c, 0.005) and bad <= 0.03 and err.max() <= 3e-3, (bad, bad_c, float(err.max()))
+    return bad, float(err.max())
 
 
 @pytest.mark.parametrize("mode", ["ulaw8k_linear", "ulaw8k_poly", "pcm48k_poly", "pcm16k"])
@@ -58,7 +62,7 @@ def test_stt_full_matches_oracle_chain(gpu, session, mode):
         assert got_segs == [(s.start_ms, s.end_ms) for s in ovad.segments_from_probs(gp, len(pcm))]  # machine bit-exact on its own probabilities
         if (np.abs(probs - 0.5) > PROB_TOL).all():
             assert got_segs == segs
-        _mel_check(out["mel"][i].cpu().numpy(), mel, 0.97, 5e-3)
+        _mel_check(out["mel"][i].cpu().numpy(), mel, stt.stt_frontend(pcm, noise_reduce=True, normalize=True, gate_dtype=np.float32))
 
 
 def test_stt_full_host_equals_device(gpu, session):
