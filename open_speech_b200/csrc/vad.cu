@@ -932,8 +932,8 @@ static int vad_score(VadModel* m, const void* d_audio, int fmt, int64_t n, int64
     // chunk the window axis: windows per chunk ~ 4 x 148 SMs x 128 rows, so the three GEMM shapes (3W, 2W, W rows) run
     // 12 / 8 / 4 whole waves per launch.  Larger chunks amortise the launches and the recurrence prologue (measured: x4 is
     // 9 % faster on the front than one wave) at ~0.7 GB of activations per chunk, part of which leaves L2.
-    // (the fused front keeps nothing but the pre-activations in HBM: 16 waves of 128-window tiles per launch, 0.6 GB)
-    int waves = m->use_tc == 2 ? 16 : 4;
+    // (the fused front keeps nothing but the pre-activations in HBM: 32 waves of 128-window tiles per launch, 1.2 GB: 256 x 60 s is one chunk)
+    int waves = m->use_tc == 2 ? 32 : 4;
     if (const char* e = getenv("OSB_VAD_CHUNK_WAVES")) { const int v = atoi(e); if (v >= 1 && v <= 256) waves = v; }
     long long T = ((long long)OSB_NUM_SMS * 128 * waves + batch - 1) / batch;
     if (T < 1) T = 1;
