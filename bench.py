@@ -88,8 +88,9 @@ def kernel_io_bytes_per_audio_s(name: str, seconds: float, denoised_input: bool)
         "k_vad_front_fused": 2.0 * SR + 31.25 * 2048.0,   # pcm16 in, gate pre-activations [512] f32 per window out
         "k_vad_recur": 31.25 * 2048.0 + 31.25 * 4.0,      # pre-activations in, probabilities out
     }
+    bare = name.strip("()").split("::")[-1]  # OSB_LAUNCH stringifies template kernels as "(k_x<..>)"; the fused front lives in vf::
     for k, v in table.items():
-        if name.startswith(k):
+        if bare.startswith(k):
             return v
     return None
 
@@ -459,7 +460,8 @@ def stt_roofline(ctx: Ctx, workload: str, s: dict, ms_step: float, kern: dict) -
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
-        traffic = json.load(open(tp)).get(workload, {}).get(dom_name)
+        tj = json.load(open(tp)).get(workload, {})
+        traffic = tj.get(dom_name, tj.get(dom_name.strip("()")))
     r = {"bound": "hbm", "achieved": gbs, "peak": ctx.peak, "unit": "GB/s", "frac": gbs / ctx.peak, "traffic": traffic, "peak_source": ctx.peak_src,
          "algorithmic_bytes_per_step": alg, "what": "whole step: SURVEY 8(d) algorithmic bytes of the chain / step time",
          "kernel": dom_name, "kernel_ms_per_launch": dom_ms, "kernel_share_of_step": dom["ms"] / ms_step,
