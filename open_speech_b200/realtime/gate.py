@@ -77,6 +77,14 @@ class RealtimeGate:
         k = int(self._ev_host[self.max_events, 0])
         return [(int(s), EVENT_NAMES[int(t)], int(ms)) for s, t, ms in self._ev_host[: min(k, self.max_events)].tolist()]
 
+    def capture(self) -> "GateTickGraph":
+        """The whole tick -- pinned wire slot -> H2D -> decode + resample + buffer + gate -> D2H of pcm16 and the event list -- as ONE
+        CUDA graph launch (the tick is launch-latency bound: five driver submissions become one).  Chunks shorter than a VAD window
+        only (the reference's 20 ms case): scoring allocates stream-ordered scratch, which is not captured here."""
+        if self.n_out >= 512 and self.session is not None:
+            raise RuntimeError("graph capture covers ticks without a full VAD window (chunk < 512 samples at 16 kHz)")
+        return GateTickGraph(self)
+
     def records(self) -> np.ndarray:
         return self.state.cpu().numpy().view(GATE_STATE).reshape(self.S)
 
@@ -92,6 +100,45 @@ class RealtimeGate:
         out = self.arena[stream, :n].clone()
         self.clear([stream])
         return out
+
+
+class GateTickGraph:
+    """A captured tick of a :class:`RealtimeGate`: write the tick's bytes into ``host_in`` (pinned), ``run()``, read ``host_pcm``
+    and the returned events."""
+
+    def __init__(self, gate: RealtimeGate):
+        self.gate = gate
+        self.host_in = torch.zeros((gate.S, gate.chunk), dtype=gate.in_dtype).pin_memory()
+        self.host_pcm = torch.empty((gate.S, max(gate.n_out, 1)), dtype=torch.int16).pin_memory()
+        self.dev_in = torch.empty((gate.S, gate.chunk), dtype=gate.in_dtype, device=gate.state.device)
+        self.stream = torch.cuda.Stream()
+        saved = (gate.state.clone(), gate.work.clone())
+        with torch.cuda.stream(self.stream):
+            self._body()  # warm-up outside capture (lazy initialisation inside the library, e.g. the resampler's table)
+        self.stream.synchronize()
+        gate.state.copy_(saved[0])
+        gate.work.copy_(saved[1])
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph, stream=self.stream):
+            self._body()
+
+    def _body(self):
+        g = self.gate
+        self.dev_in.copy_(self.host_in, non_blocking=True)
+        g.tick(self.dev_in)
+        self.host_pcm.copy_(g.pcm, non_blocking=True)
+        g._ev_host.copy_(g.events, non_blocking=True)
+
+    def run(self) -> list[tuple[int, str, int]]:
+        g = self.gate
+        with torch.cuda.stream(self.stream):
+            self.graph.replay()
+        self.stream.synchronize()
+        k = int(g._ev_host[g.max_events, 0])
+        if k == 0:
+            return []
+        return [(int(s), EVENT_NAMES[int(t)], int(ms)) for s, t, ms in g._ev_host[: min(k, g.max_events)].tolist()]
 
 
 class StreamGate:

@@ -168,6 +168,29 @@ def test_gate_reference_exact_20ms_is_one_gate_launch(gpu, session):
     assert np.array_equal(g.arena[3].cpu().numpy(), np.concatenate(ref))
 
 
+def test_gate_tick_cuda_graph_matches_stream_path(gpu, session):
+    """The captured tick (one graph launch: H2D, resample, gate, D2H) leaves the same pcm16, records and events as the stream path."""
+    import torch
+
+    from open_speech_b200 import synth
+    from open_speech_b200.realtime.gate import RealtimeGate
+
+    S = 64
+    data = synth.ulaw_streams(S, 12)
+    a = RealtimeGate(S, 160, fmt="g711_ulaw", session=session, arena_samples=320 * 12)
+    b = RealtimeGate(S, 160, fmt="g711_ulaw", session=session, arena_samples=320 * 12)
+    gb = b.capture()
+    for t in range(12):
+        a.tick(torch.from_numpy(data[t]).cuda())
+        ev_a = a.read_events()
+        gb.host_in.copy_(torch.from_numpy(data[t]))
+        ev_b = gb.run()
+        assert ev_a == ev_b
+        assert torch.equal(a.pcm.cpu(), gb.host_pcm)
+    assert np.array_equal(a.records(), b.records()) and torch.equal(a.arena, b.arena)
+    assert int(a.records()["total_samples"][0]) == 320 * 12
+
+
 def test_gate_buffer_errors(gpu):
     """The two BufferError cases of InputAudioBuffer.append against the arena capacity (audio_buffer.py:118-122)."""
     import torch
