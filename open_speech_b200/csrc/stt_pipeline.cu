@@ -121,7 +121,7 @@ struct GroupPipe {
     int groups = 0;
     int64_t bounds[33] = {0};
     explicit GroupPipe(HostWs& w) : ws(w) {}
-    int open(int64_t batch) {
+    int open(int64_t batch, int max_groups = 24) {
         static thread_local cudaStream_t t_in = nullptr, t_out = nullptr;
         static thread_local cudaEvent_t t_ev[64];
         static thread_local int t_dev = -1;
@@ -141,6 +141,7 @@ struct GroupPipe {
         // clip groups (OSB_STT_HOST_GROUPS=1..32 to tune): the middle of the pipeline is PCIe-bound (the float32 features leaving), so
         // more groups = shorter fill (first H2D + first kernels) and drain; measured on 256 x 60 s: 8 groups 17.0 ms, 16: 16.2, 24: 16.0
         groups = batch >= 192 ? 24 : (batch >= 64 ? 8 : (batch >= 16 ? 4 : 1));
+        if (groups > max_groups) groups = max_groups;
         if (const char* e = getenv("OSB_STT_HOST_GROUPS")) {
             const int g = atoi(e);
             if (g >= 1 && g <= 32 && g <= batch) groups = g;
@@ -208,8 +209,10 @@ int osb_stt_full_host(void* vad, const void* in, int in_fmt, int from_rate, int6
     float* d_probs = (float*)dvad;  // planar: probs [batch][n_win] | segments [batch][max_seg][2] | counts [batch]
     int32_t* d_segs = (int32_t*)(d_probs + (size_t)batch * n_win);
     int32_t* d_cnt = d_segs + (size_t)batch * max_seg * 2;
+    // the wire input is a quarter of configs[3]'s bytes (mu-law 8 kHz) and arrives early; what has to be hidden is the features' way out.
+    // Eight groups: the kernels of a group keep the SMs full (24 groups of ~10 clips cost 3 ms more compute), the fill stays ~1.5 ms
     GroupPipe gp(ws);
-    if ((rc = gp.open(batch))) return rc;
+    if ((rc = gp.open(batch, 8))) return rc;
     rc = OSB_OK;
     for (int g = 0; g < gp.groups && rc == OSB_OK; ++g) {
         const int64_t c0 = gp.bounds[g], nb = gp.bounds[g + 1] - c0;

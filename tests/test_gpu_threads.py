@@ -1,7 +1,7 @@
 """Re-entrancy: the reference calls this path from the asyncio loop thread and from 4-worker thread pools at once
 (src/streaming.py:50-52, src/realtime/server.py:33-35, src/main.py:796-813; SURVEY.md 8(b) "Threading").  Every host
 entry uses a thread-local stream and workspace, and one VAD session (weights) is shared by per-stream SileroVAD states.
-Nine threads hammer different entry points concurrently; every result must equal the single-threaded one bit for bit."""
+Twelve threads hammer different entry points concurrently; every result must equal the single-threaded one bit for bit."""
 import threading
 
 import numpy as np
@@ -28,7 +28,30 @@ def test_concurrent_host_calls_are_independent(gpu):
     fe = B200FeatureExtractor(feature_size=128)
     fx = [{"type": "normalize"}, {"type": "reverb", "room": "medium"}, {"type": "podcast_eq"}, {"type": "robot"}]
 
+    def buffer_events():
+        from open_speech_b200.realtime.audio_buffer import InputAudioBuffer
+
+        b = InputAudioBuffer(vad=SileroVAD(session), silence_duration_ms=200)
+        return repr([b.append(clip[i:i + 1600].tobytes()) for i in range(0, len(clip) - 1600, 1600)]) + repr(b._total_samples)
+
+    def session_gate():
+        from open_speech_b200.streaming import SessionGate
+
+        g = SessionGate(16000, 300, vad=SileroVAD(session))
+        return repr([g.process_chunk(clip[i:i + 1600].tobytes())[1] for i in range(0, len(clip) - 1600, 1600)])
+
+    def full_chain():
+        from open_speech_b200.batch import SttFull
+
+        out = {"probs": np.empty((2, 187), np.float32), "segments": np.empty((2, 95, 2), np.int32), "counts": np.empty(2, np.int32),
+               "mel": np.empty((2, 128, 601), np.float32)}
+        SttFull(session, fmt="pcm16", from_rate=16000).run_host(np.stack([clip, clip[::-1]]).copy(), out)
+        return out["mel"].tobytes() + out["probs"].tobytes() + out["counts"].tobytes()
+
     jobs = {
+        "buffer": buffer_events,
+        "session_gate": session_gate,
+        "full": full_chain,
         "decode": lambda: decode_audio_to_pcm16(ulaw, "g711_ulaw", 16000),
         "poly": lambda: resample_pcm16(clip.tobytes(), 16000, 8000),
         "gate": lambda: pre.reduce_noise(clip_f, 16000).tobytes(),
