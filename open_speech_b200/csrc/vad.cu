@@ -466,15 +466,22 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_vad_gemm_tc(GemmDesc d, const
 __device__ __forceinline__ float sigmoidf_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
 // cell non-linearities on the SFU (ex2 + rcp): absolute error ~1e-7, three decimal orders inside the 1e-3 probability
 // budget, and they sit on the serial chain of every step
+// 1 / x for x in [1, 2]: the bare MUFU.RCP (1 ulp).  __frcp_rn carries a slow-path branch for operands it cannot meet here, and a branch on
+// the serial chain of every step is a scheduling fence and two extra Newton steps (256 x 1 h: 196 -> 170 ms)
+__device__ __forceinline__ float rcp_1to2(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 // sigmoid with explicit roundings (both recurrence kernels must round alike): t = exp(-|x|), r = 1/(1+t); sigmoid(|x|) = r, sigmoid(-|x|) = t r
 __device__ __forceinline__ float sigmoidf_det(float x) {
     const float t = __expf(-fabsf(x));
-    const float r = __frcp_rn(__fadd_rn(1.0f, t));
+    const float r = rcp_1to2(__fadd_rn(1.0f, t));
     return x >= 0.f ? r : __fmul_rn(t, r);
 }
 __device__ __forceinline__ float tanhf_fast(float x) {
     const float t = __expf(-2.0f * fabsf(x));
-    return copysignf(__fmul_rn(__fsub_rn(1.0f, t), __frcp_rn(__fadd_rn(1.0f, t))), x);
+    return copysignf(__fmul_rn(__fsub_rn(1.0f, t), rcp_1to2(__fadd_rn(1.0f, t))), x);
 }
 
 // Gate pre-activation of window w (flattened (stream, t) index of the launch), gate row `own`.  Linear: [w][512].  Interleaved (what the
@@ -597,7 +604,7 @@ __global__ void __launch_bounds__(512, 1) k_vad_recur(const float* __restrict__ 
             // t = exp(-k|x|), r = 1/(1+t):  sigmoid(|x|) = r, sigmoid(-|x|) = t r (k = 1),  tanh(|x|) = (1-t) r (k = 2)
             const float ax = fabsf(x[s]);
             const float t = __expf(gate == 2 ? -2.0f * ax : -ax);
-            const float r = __frcp_rn(__fadd_rn(1.0f, t));
+            const float r = rcp_1to2(__fadd_rn(1.0f, t));
             // (explicit roundings: every S instantiation must round alike, the packing of streams into CTAs is invisible)
             act[s] = gate == 2 ? copysignf(__fmul_rn(__fsub_rn(1.0f, t), r), x[s]) : (x[s] >= 0.f ? r : __fmul_rn(t, r));  // sigmoid(-|x|) = t r
         }
