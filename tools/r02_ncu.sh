@@ -10,4 +10,4 @@ python tools/prof_target.py vad 1 > gpurun_out/r02_plain_vad.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:'k_vad_front_fused|k_vad_recur' -c 2 -o gpurun_out/r02_prof_vad -f python tools/prof_target.py vad 1 > gpurun_out/r02_ncu_d.log 2>&1
 python tools/prof_target.py tts 1 > gpurun_out/r02_plain_tts.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:'k_fx_reverb_eq' -c 1 -o gpurun_out/r02_prof_tts -f python tools/prof_target.py tts 1 > gpurun_out/r02_ncu_e.log 2>&1
-tail -2 gpurun_out/r02_ncu_?.log
+for f in gpurun_out/r02_ncu_?.log; do tail -n 2 $f; done
