@@ -339,6 +339,7 @@ class Ctx:
         torch = self.torch
         for _ in range(warmup):
             fn()
+            torch.cuda.synchronize()  # one call at a time while the stream-ordered pools of the side streams settle (first calls only)
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         self.barrier()
         ev0.record()
@@ -477,7 +478,7 @@ def bench_stt(ctx: Ctx, args, workload: str, extra: dict | None) -> None:
     warm = max(args.warmup, 3)
     for _ in range(warm):
         s["run"]()
-    torch.cuda.synchronize()
+        torch.cuda.synchronize()
     sampler = ClockSampler(ctx.local)
     launches0 = N.lib().osb_launch_count()
     if ctx.rank == 0:

@@ -120,8 +120,9 @@ int launch_normalize_f32(const float* d_in, void* d_out, int out_pcm16, long lon
                          float target_dbfs, cudaStream_t st);
 
 // vad.cu: batched scoring (state [batch][2][128] in/out) and the integer segmenter, for the composed paths
+// front_done (optional): recorded on st after the first chunk's front kernel(s); shared_gpu: another branch runs beside the recurrence
 int launch_vad_score(void* handle, const void* d_audio, int fmt, long long n, long long batch, long long stride, float* d_state,
-                     float* d_probs, long long probs_stride, cudaStream_t st);
+                     float* d_probs, long long probs_stride, cudaStream_t st, cudaEvent_t front_done = nullptr, bool shared_gpu = false);
 int launch_vad_segments(const float* d_probs, long long probs_stride, long long n_win, long long batch, long long n_samples, float thr,
                         int min_speech_ms, int silence_ms, int32_t* d_segs, int32_t* d_counts, int max_seg, cudaStream_t st);
 

@@ -932,8 +932,13 @@ static int launch_gemm(const GemmDesc& d, cudaStream_t st) {
     return OSB_OK;
 }
 
+static int share_width() {
+    static const int w = [] { const char* e = getenv("OSB_VAD_SHARE_WIDTH"); const int v = e ? atoi(e) : 0; return (v == 1 || v == 2 || v == 4) ? v : 4; }();
+    return w;
+}
+
 static int vad_score(VadModel* m, const void* d_audio, int fmt, int64_t n, int64_t batch, int64_t stride, float* d_state,
-                     float* d_probs, int64_t probs_stride, cudaStream_t st) {
+                     float* d_probs, int64_t probs_stride, cudaStream_t st, cudaEvent_t front_done = nullptr, bool shared_gpu = false) {
     const long long n_win = n / kWin;
     if (n_win == 0 || batch == 0) return OSB_OK;
     // chunk the window axis: windows per chunk ~ 4 x 148 SMs x 128 rows, so the three GEMM shapes (3W, 2W, W rows) run
@@ -973,7 +978,11 @@ static int vad_score(VadModel* m, const void* d_audio, int fmt, int64_t n, int64
         return e;
     }));
     // streams per recurrence CTA: as few as keep the grid within one wave of SMs
-    const int rs = batch <= OSB_NUM_SMS ? 1 : (batch <= 2 * OSB_NUM_SMS ? 2 : 4);
+    // shared_gpu (the composed chain runs its feature branch beside this one, stt_pipeline.cu): four streams per CTA from 75 streams on.
+    // A recurrence CTA owns its SM (the whole register file) and is bound by the latency of its serial chain, so a wider CTA costs the
+    // VAD branch time but hands the SMs it vacates to kernels that can fill them.
+    int rs = batch <= OSB_NUM_SMS ? 1 : (batch <= 2 * OSB_NUM_SMS ? 2 : 4);
+    if (shared_gpu && batch > OSB_NUM_SMS / 2) rs = share_width();
     int rc;
     for (long long w0 = 0; w0 < n_win; w0 += T) {
         const int t = (int)((n_win - w0) < T ? (n_win - w0) : T);
@@ -1020,6 +1029,7 @@ static int vad_score(VadModel* m, const void* d_audio, int fmt, int64_t n, int64
         d.M = Wc; d.N = kGates; d.K = 128; d.relu = 0;
         if ((rc = m->use_tc ? launch_gemm_tc<0, 0>(d, m->tc[5], st) : launch_gemm<0, 0>(d, st))) return rc;
         }
+        if (front_done && w0 == 0) OSB_CUDA(cudaEventRecord(front_done, st));  // from here on this branch leaves SMs free
         // recurrence over the chunk's t windows, one CTA per stream
         const unsigned rg = (unsigned)((batch + rs - 1) / rs);
 #define OSB_RECUR(KERN, SMEM) OSB_LAUNCH(KERN, rg, 512, SMEM, st, pre, (long long)t * kGates, t, (const float4*)m->whh_perm, m->dw, m->db, d_state, d_probs, \
@@ -1047,9 +1057,9 @@ static int vad_segments(const float* d_probs, int64_t probs_stride, int64_t n_wi
 }
 
 int launch_vad_score(void* handle, const void* d_audio, int fmt, long long n, long long batch, long long stride, float* d_state,
-                     float* d_probs, long long probs_stride, cudaStream_t st) {
+                     float* d_probs, long long probs_stride, cudaStream_t st, cudaEvent_t front_done, bool shared_gpu) {
     if (!handle) { set_error("invalid argument: null VAD handle"); return OSB_ERR_INVALID_ARG; }
-    return vad_score(reinterpret_cast<VadModel*>(handle), d_audio, fmt, n, batch, stride, d_state, d_probs, probs_stride, st);
+    return vad_score(reinterpret_cast<VadModel*>(handle), d_audio, fmt, n, batch, stride, d_state, d_probs, probs_stride, st, front_done, shared_gpu);
 }
 int launch_vad_segments(const float* d_probs, long long probs_stride, long long n_win, long long batch, long long n_samples, float thr,
                         int min_speech_ms, int silence_ms, int32_t* d_segs, int32_t* d_counts, int max_seg, cudaStream_t st) {
