@@ -9,14 +9,44 @@ namespace osb {
 
 #define OSB_HD __host__ __device__ __forceinline__
 
-struct cpx {
+// Complex values are 8-byte aligned register pairs: on sm_100a every operation below is ONE packed FP32 instruction
+// (FADD2 / FMUL2 / FFMA2).  ptxas folds the operand shapes these helpers produce -- a scalar broadcast to both halves, a swap of the
+// halves, a sign on one half -- into the instruction's operand modifiers (R.F32, .F32x2.LO_HI, .NP / .PN), so a multiplication by
+// +-i costs nothing and a radix-2 butterfly with a general twiddle is three instructions instead of six.  The host versions
+// (tests/host/fft_check.cu) compute the same expressions with scalar fmaf.
+struct __align__(8) cpx {
     float x, y;
 };
-OSB_HD cpx cmul(cpx a, cpx b) { return cpx{a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x}; }
+#if defined(__CUDA_ARCH__) && __CUDA_ARCH__ >= 1000
+#define OSB_F2(a) make_float2((a).x, (a).y)
+OSB_HD cpx osb_c(float2 v) { return cpx{v.x, v.y}; }
+OSB_HD cpx cadd(cpx a, cpx b) { return osb_c(__fadd2_rn(OSB_F2(a), OSB_F2(b))); }
+OSB_HD cpx csub(cpx a, cpx b) { return osb_c(__fadd2_rn(OSB_F2(a), make_float2(-b.x, -b.y))); }
+OSB_HD cpx cscale(cpx a, float s) { return osb_c(__fmul2_rn(OSB_F2(a), make_float2(s, s))); }
+OSB_HD cpx cfma(cpx a, float s, cpx c) { return osb_c(__ffma2_rn(OSB_F2(a), make_float2(s, s), OSB_F2(c))); }            // a s + c
+OSB_HD cpx cfma_negi(cpx q, float s, cpx c) { return osb_c(__ffma2_rn(make_float2(q.y, q.x), make_float2(s, -s), OSB_F2(c))); }  // c + s (-i q)
+OSB_HD cpx cfma_posi(cpx q, float s, cpx c) { return osb_c(__ffma2_rn(make_float2(q.y, q.x), make_float2(-s, s), OSB_F2(c))); }  // c + s (+i q)
+OSB_HD cpx cadd_negi(cpx c, cpx q) { return osb_c(__fadd2_rn(OSB_F2(c), make_float2(q.y, -q.x))); }                     // c - i q
+OSB_HD cpx cadd_posi(cpx c, cpx q) { return osb_c(__fadd2_rn(OSB_F2(c), make_float2(-q.y, q.x))); }                     // c + i q
+OSB_HD cpx cscale_negi(cpx q, float s) { return osb_c(__fmul2_rn(make_float2(q.y, q.x), make_float2(s, -s))); }          // s (-i q)
+OSB_HD cpx cmul2(cpx a, cpx b) { return osb_c(__fmul2_rn(OSB_F2(a), OSB_F2(b))); }                                       // element-wise
+#else
 OSB_HD cpx cadd(cpx a, cpx b) { return cpx{a.x + b.x, a.y + b.y}; }
 OSB_HD cpx csub(cpx a, cpx b) { return cpx{a.x - b.x, a.y - b.y}; }
-OSB_HD cpx cmul_negi(cpx a) { return cpx{a.y, -a.x}; }  // a * (-i)
+OSB_HD cpx cscale(cpx a, float s) { return cpx{a.x * s, a.y * s}; }
+OSB_HD cpx cfma(cpx a, float s, cpx c) { return cpx{fmaf(a.x, s, c.x), fmaf(a.y, s, c.y)}; }
+OSB_HD cpx cfma_negi(cpx q, float s, cpx c) { return cpx{fmaf(q.y, s, c.x), fmaf(q.x, -s, c.y)}; }
+OSB_HD cpx cfma_posi(cpx q, float s, cpx c) { return cpx{fmaf(q.y, -s, c.x), fmaf(q.x, s, c.y)}; }
+OSB_HD cpx cadd_negi(cpx c, cpx q) { return cpx{c.x + q.y, c.y - q.x}; }
+OSB_HD cpx cadd_posi(cpx c, cpx q) { return cpx{c.x - q.y, c.y + q.x}; }
+OSB_HD cpx cscale_negi(cpx q, float s) { return cpx{q.y * s, q.x * -s}; }
+OSB_HD cpx cmul2(cpx a, cpx b) { return cpx{a.x * b.x, a.y * b.y}; }
+#endif
+OSB_HD cpx cneg(cpx a) { return cpx{-a.x, -a.y}; }
 OSB_HD cpx cconj(cpx a) { return cpx{a.x, -a.y}; }
+OSB_HD cpx cmul(cpx a, cpx b) { return cfma_posi(a, b.y, cscale(a, b.x)); }       // a b        = a b.x + (i a) b.y
+OSB_HD cpx cmul_conj(cpx a, cpx w) { return cfma_negi(a, w.y, cscale(a, w.x)); }  // a conj(w)  = a w.x + (-i a) w.y
+OSB_HD cpx cmul_negi(cpx a) { return cpx{a.y, -a.x}; }                            // a * (-i)
 
 // cos/sin(2 pi k / 32), k = 0..15
 #define OSB_C32 { 1.0000000000e+00f, 9.8078528040e-01f, 9.2387953251e-01f, 8.3146961230e-01f, 7.0710678119e-01f, 5.5557023302e-01f, 3.8268343237e-01f, 1.9509032202e-01f, 6.1232339957e-17f, -1.9509032202e-01f, -3.8268343237e-01f, -5.5557023302e-01f, -7.0710678119e-01f, -8.3146961230e-01f, -9.2387953251e-01f, -9.8078528040e-01f }
@@ -70,16 +100,15 @@ OSB_HD void fft_pow2(cpx (&v)[N]) {
                 v[b + j] = cadd(a, q);
                 v[b + j + half] = csub(a, q);
             } else if (ti == 8) {  // -i (forward) / +i (inverse)
-                const cpx t = INV ? cpx{-q.y, q.x} : cpx{q.y, -q.x};
-                v[b + j] = cadd(a, t);
-                v[b + j + half] = csub(a, t);
+                v[b + j] = INV ? cadd_posi(a, q) : cadd_negi(a, q);
+                v[b + j + half] = INV ? cadd_negi(a, q) : cadd_posi(a, q);
             } else {
-                // a + w q as two FMA chains, a - w q = 2a - (a + w q): six FMA-pipe instructions with immediate
-                // twiddles instead of a complex multiply and four additions
-                const float wc = c32[ti], ws = INV ? s32[ti] : -s32[ti];
-                const cpx hi = cpx{fmaf(q.x, wc, fmaf(-q.y, ws, a.x)), fmaf(q.x, ws, fmaf(q.y, wc, a.y))};
+                // hi = a + w q with w = wc -+ i ws: two packed FMAs (the +-i q operand is a modifier); lo = a - w q = 2a - hi
+                const float wc = c32[ti], ws = s32[ti];
+                const cpx t = cfma(q, wc, a);
+                const cpx hi = INV ? cfma_posi(q, ws, t) : cfma_negi(q, ws, t);
                 v[b + j] = hi;
-                v[b + j + half] = cpx{fmaf(2.0f, a.x, -hi.x), fmaf(2.0f, a.y, -hi.y)};
+                v[b + j + half] = cfma(a, 2.0f, cneg(hi));
             }
         }
     }
@@ -91,17 +120,16 @@ OSB_HD void dft5(cpx& a0, cpx& a1, cpx& a2, cpx& a3, cpx& a4) {
     const cpx t1 = cadd(a1, a4), t2 = cadd(a2, a3), t3 = csub(a1, a4), t4 = csub(a2, a3);
     const cpx t5 = cadd(t1, t2);
     const cpx b0 = cadd(a0, t5);
-    const cpx m1 = cpx{a0.x - 0.25f * t5.x, a0.y - 0.25f * t5.y};
-    const cpx m2 = cpx{c2 * (t1.x - t2.x), c2 * (t1.y - t2.y)};
+    const cpx m1 = cfma(t5, -0.25f, a0);
+    const cpx m2 = cscale(csub(t1, t2), c2);
     const cpx r1 = cadd(m1, m2), r2 = csub(m1, m2);
-    const cpx u1 = cpx{s1 * t3.x + s2 * t4.x, s1 * t3.y + s2 * t4.y};
-    const cpx u2 = cpx{s2 * t3.x - s1 * t4.x, s2 * t3.y - s1 * t4.y};
-    const cpx n1 = cmul_negi(u1), n2 = cmul_negi(u2);
+    const cpx u1 = cfma(t4, s2, cscale(t3, s1));
+    const cpx u2 = cfma(t4, -s1, cscale(t3, s2));
     a0 = b0;
-    a1 = cadd(r1, n1);
-    a4 = csub(r1, n1);
-    a2 = cadd(r2, n2);
-    a3 = csub(r2, n2);
+    a1 = cadd_negi(r1, u1);  // r1 - i u1
+    a4 = cadd_posi(r1, u1);
+    a2 = cadd_negi(r2, u2);
+    a3 = cadd_posi(r2, u2);
 }
 
 // 25-point DFT, forward, natural in -> natural out (in place)
@@ -134,49 +162,38 @@ OSB_HD void dft25(cpx (&v)[25]) {
 
 // ---------------------------------------------------------------- 400-point complex FFT (25 x 16 four-step)
 // Two real 400-sample frames A,B are packed as z = w*(A + iB).  n = 16*n1 + n2, k = k1 + 25*k2:
-//   step1(n2): 25-point DFT over n1, times W400^(n2*k1)      -> Y[k1][n2]   (twc/tws hold W400^(n2*k1) at [k1*16 + n2])
+//   step1(n2): 25-point DFT over n1, times W400^(n2*k1)      -> Y[k1][n2]   (tw holds (cos, sin)(2 pi n2 k1 / 400) at [k1*16 + n2])
 //   step2(k1): 16-point FFT over n2                          -> Z[k1 + 25*k2] stored at [k1][k2]
-// Y/Z live in two float planes [25][17] (row padded to 17 so step-2 rows hit distinct banks).
-constexpr int kF400Stride = 17, kF400Plane = 25 * 17;
+// Y/Z are interleaved complex [25][17] (rows padded to 17 complex: the 64-bit accesses of both steps are conflict-free per half-warp).
+constexpr int kF400Stride = 17, kF400Plane = 25 * 17;  // in complex elements
 
-OSB_HD void fft400_step1(const float* xa, const float* xb, const float* win, const float* twc, const float* tws, int n2,
-                         float* Yre, float* Yim) {
+OSB_HD void fft400_step1(const float* xa, const float* xb, const float* win, const cpx* tw, int n2, cpx* Y) {
     cpx v[25];
 #pragma unroll
     for (int n1 = 0; n1 < 25; ++n1) {
         const int idx = 16 * n1 + n2;
-        const float w = win[idx];
-        v[n1] = cpx{xa[idx] * w, xb[idx] * w};
+        v[n1] = cscale(cpx{xa[idx], xb[idx]}, win[idx]);
     }
     dft25(v);
 #pragma unroll
-    for (int k1 = 0; k1 < 25; ++k1) {
-        const int t = k1 * 16 + n2;  // table laid out [k1][n2]
-        const cpx y = cmul(v[k1], cpx{twc[t], -tws[t]});
-        Yre[k1 * kF400Stride + n2] = y.x;
-        Yim[k1 * kF400Stride + n2] = y.y;
-    }
+    for (int k1 = 0; k1 < 25; ++k1) Y[k1 * kF400Stride + n2] = cmul_conj(v[k1], tw[k1 * 16 + n2]);
 }
 
-OSB_HD void fft400_step2(int k1, float* Yre, float* Yim) {
+OSB_HD void fft400_step2(int k1, cpx* Y) {
     cpx v[16];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = cpx{Yre[k1 * kF400Stride + i], Yim[k1 * kF400Stride + i]};
+    for (int i = 0; i < 16; ++i) v[i] = Y[k1 * kF400Stride + i];
     fft_pow2<16>(v);
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        Yre[k1 * kF400Stride + i] = v[i].x;
-        Yim[k1 * kF400Stride + i] = v[i].y;
-    }
+    for (int i = 0; i < 16; ++i) Y[k1 * kF400Stride + i] = v[i];
 }
 
 OSB_HD int fft400_addr(int k) { return (k % 25) * kF400Stride + (k / 25); }
 
 // power spectra of the two packed real frames at bin k (0..200):  X_A = (Z[k]+conj Z[N-k])/2, X_B = (Z[k]-conj Z[N-k])/(2i)
-OSB_HD void fft400_pair_power(const float* Zre, const float* Zim, int k, float* pa, float* pb) {
-    const int a0 = fft400_addr(k), a1 = fft400_addr(k == 0 ? 0 : 400 - k);
-    const float zr = Zre[a0], zi = Zim[a0], yr = Zre[a1], yi = Zim[a1];
-    const float ar = zr + yr, ai = zi - yi, br = zi + yi, bi = yr - zr;
+OSB_HD void fft400_pair_power(const cpx* Z, int k, float* pa, float* pb) {
+    const cpx z = Z[fft400_addr(k)], y = Z[fft400_addr(k == 0 ? 0 : 400 - k)];
+    const float ar = z.x + y.x, ai = z.y - y.y, br = z.y + y.y, bi = y.x - z.x;
     *pa = 0.25f * (ar * ar + ai * ai);
     *pb = 0.25f * (br * br + bi * bi);
 }
@@ -201,7 +218,8 @@ __device__ __forceinline__ void fft1024_warp(float* yr, float* yi, const float* 
 #pragma unroll
         for (int k1 = 0; k1 < 32; ++k1) {
             const int tw = k1 * 32 + lane;
-            const cpx y = cmul(v[k1], cpx{twc[tw], INV ? tws[tw] : -tws[tw]});
+            const cpx w = cpx{twc[tw], tws[tw]};
+            const cpx y = INV ? cmul(v[k1], w) : cmul_conj(v[k1], w);
             yr[k1 * kF1024Stride + lane] = y.x;
             yi[k1 * kF1024Stride + lane] = y.y;
         }

@@ -27,16 +27,16 @@ namespace osb {
 constexpr int kNfft = 400, kHop = 160, kBins = 201, kPad = 160;
 constexpr int MF = 32;                             // frames per CTA
 constexpr int kXs = kHop * (MF - 1) + kNfft;       // 5360 staged samples
-constexpr int kPStride = MF + 1;                   // power tile [204][33]: 201 bins + 3 rows the zero-padded mel taps may touch
+constexpr int kPStride = MF + 2;                   // power tile [204][34]: 201 bins + 3 rows the zero-padded mel taps may touch; row = 16 x (frame q, frame q + 16)
 constexpr int kPRows = kBins + 3;
 constexpr int kMelWMax = 768;                      // padded mel taps staged in shared memory (128 mels: 512, 80 mels: 480)
 
 struct MelTables {
     int n_mels = 0;
     std::vector<float> dense;   // [n_mels][201] f32 (what FeatureExtractor.mel_filters holds)
-    float* d_consts = nullptr;  // win[400], twc[400], tws[400]
+    float* d_consts = nullptr;  // win[400], tw[400] as (cos, sin) pairs
     int* d_meta = nullptr;      // [n_mels] first non-zero bin | padded tap count << 8 | offset into d_w << 16
-    float* d_w = nullptr;       // taps of every filter, each zero-padded to a multiple of 4 (kMelWMax floats in total at most)
+    float* d_w = nullptr;       // taps of every filter x 0.25 (the power tile holds 4 |X|^2: exact), each zero-padded to a multiple of 4
     int n_w = 0;
 };
 
@@ -85,8 +85,8 @@ static int get_mel(int n_mels, bool need_device, const MelTables** out) {
                 consts[i] = (float)(0.5 - 0.5 * std::cos(2.0 * pi * i / 400.0));  // np.hanning(401)[:-1] -> f32
                 // four-step twiddles W400^(n2*k1) stored as [k1][n2] (25 x 16): conflict-free per-lane reads
                 const int k1 = i / 16, n2 = i % 16;
-                consts[400 + i] = (float)std::cos(2.0 * pi * (double)(n2 * k1) / 400.0);
-                consts[800 + i] = (float)std::sin(2.0 * pi * (double)(n2 * k1) / 400.0);
+                consts[400 + 2 * i] = (float)std::cos(2.0 * pi * (double)(n2 * k1) / 400.0);
+                consts[401 + 2 * i] = (float)std::sin(2.0 * pi * (double)(n2 * k1) / 400.0);
             }
             std::vector<int> meta(n_mels);
             std::vector<float> w;
@@ -96,7 +96,7 @@ static int get_mel(int n_mels, bool need_device, const MelTables** out) {
                     if (t.dense[(size_t)m * kBins + k] != 0.f) { if (a < 0) a = k; b = k; }
                 const int start = a < 0 ? 0 : a, len = a < 0 ? 0 : b - a + 1, len4 = (len + 3) / 4 * 4;
                 meta[m] = start | (len4 << 8) | ((int)w.size() << 16);
-                for (int k = 0; k < len4; ++k) w.push_back(k < len ? t.dense[(size_t)m * kBins + start + k] : 0.f);
+                for (int k = 0; k < len4; ++k) w.push_back(k < len ? 0.25f * t.dense[(size_t)m * kBins + start + k] : 0.f);
             }
             if ((int)w.size() > kMelWMax) {
                 set_error("internal: mel filterbank has %d padded taps (> %d)", (int)w.size(), kMelWMax);
@@ -140,10 +140,10 @@ __device__ __forceinline__ float mel_sample(const MelArgs& a, int s16, float gai
 // Persistent kernel: grid = 2 CTAs per SM, each CTA walks tiles (32 frames of one clip) round-robin.  The raw
 // int16 samples of the NEXT tile are fetched by the TMA unit (cp.async.bulk -> mbarrier) while the current tile is
 // transformed, so the HBM latency of the staging step is off the critical path.
-//   smem: [xs|P (aliased)] [win twc tws] [Y] [raw int16] ; P reuses the float sample buffer once step 1 is done.
+//   smem: [xs|P (aliased)] [win tw] [Y] [raw int16] ; P reuses the float sample buffer once step 1 is done.
 constexpr int kRawBytes = kXs * 4;                                   // raw staging: 10,720 B of int16 or 21,440 B of float32
 constexpr int kXsP = (((kPRows * kPStride > kXs) ? kPRows * kPStride : kXs) + 3) / 4 * 4;  // 6,732 floats (keeps raw[] 16 B aligned)
-static_assert(((kXsP + 1200 + 16 * 2 * kF400Plane) * 4) % 16 == 0, "raw[] must be 16-byte aligned");
+static_assert(kPStride % 2 == 0 && ((kXsP + 1200 + 16 * 2 * kF400Plane) * 4) % 16 == 0, "raw[] must be 16-byte aligned");
 
 __device__ __forceinline__ bool mel_tile_interior(const MelArgs& a, int b, int t0, const int16_t** src) {
     const long long p0 = (long long)kHop * t0 - kNfft / 2;  // multiple of 8 samples
@@ -159,10 +159,9 @@ __global__ void __launch_bounds__(256, 2) k_logmel(MelArgs a, int tiles_per_clip
     float* xs = sm;                       // [kXs] float samples (step 1)  |  P [201][33] (power, later phases)
     float* P = sm;
     float* win = sm + kXsP;               // [400]
-    float* twc = win + 400;               // [400]
-    float* tws = twc + 400;               // [400]
-    float* Y = tws + 400;                 // [16][2][425]
-    int16_t* raw = reinterpret_cast<int16_t*>(Y + 16 * 2 * kF400Plane);  // [kXs] int16 or float32, TMA destination
+    cpx* tw = reinterpret_cast<cpx*>(win + 400);  // [400] (cos, sin)
+    cpx* Y = tw + 400;                    // [16][425] complex
+    int16_t* raw = reinterpret_cast<int16_t*>(Y + 16 * kF400Plane);  // [kXs] int16 or float32, TMA destination
     constexpr uint32_t raw_bytes = F32 ? kXs * 4 : kXs * 2;
     __shared__ int mel_meta[128];
     __shared__ __align__(16) float mel_wsm[kMelWMax];
@@ -248,9 +247,10 @@ __global__ void __launch_bounds__(256, 2) k_logmel(MelArgs a, int tiles_per_clip
                 bulk_g2s(raw, src, raw_bytes, &bar);
             }
         }
-        {   // four-step FFT, step 1: 16 frame pairs x 16 residues = 256 tasks
+        {   // four-step FFT, step 1: 16 frame pairs x 16 residues = 256 tasks.  Pair q = frames (q, q + 16): the mel phase below
+            // then finds the two frames of a pair side by side and still stores 64-byte runs
             const int q = tid >> 4, n2 = tid & 15;
-            fft400_step1(xs + (2 * q) * kHop, xs + (2 * q + 1) * kHop, win, twc, tws, n2, Y + q * 2 * kF400Plane, Y + q * 2 * kF400Plane + kF400Plane);
+            fft400_step1(xs + q * kHop, xs + (q + 16) * kHop, win, tw, n2, Y + q * kF400Plane);
         }
         __syncthreads();
         {   // step 2 fused with the power spectrum, one warp per frame pair (two pairs per warp): lane k1 < 25 runs the
@@ -261,53 +261,58 @@ __global__ void __launch_bounds__(256, 2) k_logmel(MelArgs a, int tiles_per_clip
 #pragma unroll 1
             for (int h = 0; h < 2; ++h) {
                 const int q = (tid >> 5) + 8 * h;
-                const float* yr = Y + q * 2 * kF400Plane;
-                const float* yi = yr + kF400Plane;
+                const cpx* y = Y + q * kF400Plane + k1 * kF400Stride;
                 cpx v[16];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] = cpx{yr[k1 * kF400Stride + i], yi[k1 * kF400Stride + i]};
+                for (int i = 0; i < 16; ++i) v[i] = y[i];
                 fft_pow2<16>(v);
 #pragma unroll
                 for (int k2 = 0; k2 <= 8; ++k2) {
                     // general lanes: partner's Z[(25-k1) + 25 (15-k2)]; lane 0: own Z[25 (16-k2)] (k2 = 0: Z[0] itself)
                     const float sr = __shfl_sync(0xffffffffu, v[k2 < 8 ? 15 - k2 : 15].x, src);
                     const float si = __shfl_sync(0xffffffffu, v[k2 < 8 ? 15 - k2 : 15].y, src);
-                    const float mr = lane == 0 ? v[(16 - k2) & 15].x : sr, mi = lane == 0 ? v[(16 - k2) & 15].y : si;
+                    const cpx mc = lane == 0 ? cconj(v[(16 - k2) & 15]) : cpx{sr, -si};  // conj Z[400 - k]
                     const int k = k1 + 25 * k2;
                     if (lane < 25 && k < kBins) {
-                        const float zr = v[k2].x, zi = v[k2].y;
-                        const float ar = zr + mr, ai = zi - mi, br = zi + mi, bi = mr - zr;
-                        P[k * kPStride + 2 * q] = 0.25f * (ar * ar + ai * ai);
-                        P[k * kPStride + 2 * q + 1] = 0.25f * (br * br + bi * bi);
+                        // 2 X_a = Z[k] + conj Z[N-k], 2i X_b = Z[k] - conj Z[N-k]: the tile holds 4 |X|^2 (the mel taps carry the 1/4)
+                        const cpx sa = cadd(v[k2], mc), sb = csub(v[k2], mc);
+                        *reinterpret_cast<float2*>(P + k * kPStride + 2 * q) = make_float2(fmaf(sa.x, sa.x, sa.y * sa.y), fmaf(sb.x, sb.x, sb.y * sb.y));
                     }
                 }
             }
         }
         __syncthreads();
-        // sparse mel contraction (each triangle touches a few bins; taps zero-padded to fours) + log10; lanes = frames
-        const int f = tid & 31;
-        const bool live = (t0 + f) < a.n_frames;
+        // sparse mel contraction (each triangle touches a few bins; taps zero-padded to fours) + log10.  A thread owns the frames
+        // (l, l + 16) of one mel row at a time: one 64-bit load and one packed FMA per tap serve both.
+        const int l16 = tid & 15;
+        const bool live0 = (t0 + l16) < a.n_frames, live1 = (t0 + 16 + l16) < a.n_frames;
         float vmax = -10.0f;
-        float* outb = a.out + (long long)b * a.n_mels * a.n_frames + t0 + f;
-        const float* Pf = P + f;
-        for (int m = tid >> 5; m < a.n_mels; m += 8) {
+        float* outb = a.out + (long long)b * a.n_mels * a.n_frames + t0 + l16;
+        const cpx* Pf = reinterpret_cast<const cpx*>(P) + l16;
+        for (int m = tid >> 4; m < a.n_mels; m += 16) {
             const int meta = mel_meta[m];
             const int len4 = (meta >> 8) & 255;
             const float* w = mel_wsm + (meta >> 16);
-            const float* pp = Pf + (meta & 255) * kPStride;
-            float acc0 = 0.f, acc1 = 0.f;
+            const cpx* pp = Pf + (meta & 255) * (kPStride / 2);
+            cpx acc0 = cpx{0.f, 0.f}, acc1 = cpx{0.f, 0.f};
             for (int i = 0; i < len4; i += 4) {
                 const float4 w4 = *reinterpret_cast<const float4*>(w + i);
-                acc0 = fmaf(w4.x, pp[i * kPStride], acc0);
-                acc1 = fmaf(w4.y, pp[(i + 1) * kPStride], acc1);
-                acc0 = fmaf(w4.z, pp[(i + 2) * kPStride], acc0);
-                acc1 = fmaf(w4.w, pp[(i + 3) * kPStride], acc1);
+                acc0 = cfma(pp[i * (kPStride / 2)], w4.x, acc0);
+                acc1 = cfma(pp[(i + 1) * (kPStride / 2)], w4.y, acc1);
+                acc0 = cfma(pp[(i + 2) * (kPStride / 2)], w4.z, acc0);
+                acc1 = cfma(pp[(i + 3) * (kPStride / 2)], w4.w, acc1);
             }
+            const cpx acc = cadd(acc0, acc1);
             // log10 via the SFU log2: |error| < 3e-6 on log10, 1e-6 on the output (tolerance 1e-4)
-            const float v = __log2f(fmaxf(acc0 + acc1, 1e-10f)) * 0.30102999566398120f;
-            if (live) {
-                outb[(long long)m * a.n_frames] = v;
-                vmax = fmaxf(vmax, v);
+            const float v0 = __log2f(fmaxf(acc.x, 1e-10f)) * 0.30102999566398120f;
+            const float v1 = __log2f(fmaxf(acc.y, 1e-10f)) * 0.30102999566398120f;
+            if (live0) {
+                outb[(long long)m * a.n_frames] = v0;
+                vmax = fmaxf(vmax, v0);
+            }
+            if (live1) {
+                outb[(long long)m * a.n_frames + 16] = v1;
+                vmax = fmaxf(vmax, v1);
             }
         }
         vmax = warp_max(vmax);
@@ -347,7 +352,7 @@ __global__ void __launch_bounds__(256) k_logmel_finalize(float* __restrict__ out
     for (long long i = nvec * 4 + tid; i < per_clip; i += nthr) o[i] = logmel_fin(o[i], thr);
 }
 
-constexpr int kLogmelSmemF32 = (kXsP + 1200 + 16 * 2 * kF400Plane) * (int)sizeof(float) + kRawBytes;
+constexpr int kLogmelSmemF32 = (kXsP + 1200 + 16 * 2 * kF400Plane) * (int)sizeof(float) + kRawBytes;  // (a complex plane = 2 x 425 floats)
 constexpr int kLogmelSmemP16 = kLogmelSmemF32 - kRawBytes / 2;
 
 // d_sumsq (pcm16 input) / d_sumsq_f (float32 input): fuse normalize_gain in front; requant: the chain's int16 round trip

@@ -33,7 +33,7 @@ namespace osb {
 
 constexpr int NF = 1024, NH = 256, NB = 513;       // n_fft, hop, one-sided bins
 constexpr long long kChunk = 600000, kCtx = 30000;
-constexpr int kYs = 33, kYPlane = 32 * 33;          // four-step planes [32][33]
+constexpr int kYs = 33, kYPlane = 32 * 33;          // four-step planes [32][33]: a frame pair owns one COMPLEX plane (= two float planes)
 
 struct NrGeom {
     long long n;       // samples per clip
@@ -46,7 +46,7 @@ struct NrGeom {
 };
 
 struct NrTables {
-    float* d = nullptr;  // win[1024], cos[1024], sin[1024], ola_scale[256]
+    float* d = nullptr;  // win[1024], (cos, sin)[1024], ola_scale[256]
 };
 static std::mutex g_nr_mu;
 static std::map<int, NrTables> g_nr;
@@ -65,8 +65,8 @@ static int get_nr_tables(const float** out) {
             h[i] = (float)w[i];
             // four-step twiddles W1024^(n2*k1) stored as [k1][n2]: a warp (n2 = lane) reads 32 consecutive words
             const int k1 = i >> 5, n2 = i & 31;
-            h[NF + i] = (float)std::cos(2.0 * pi * (double)(n2 * k1) / NF);
-            h[2 * NF + i] = (float)std::sin(2.0 * pi * (double)(n2 * k1) / NF);
+            h[NF + 2 * i] = (float)std::cos(2.0 * pi * (double)(n2 * k1) / NF);
+            h[NF + 2 * i + 1] = (float)std::sin(2.0 * pi * (double)(n2 * k1) / NF);
         }
         for (int r = 0; r < NH; ++r) {
             // istft: x *= win.sum() (=512); x /= sum_t win^2 ; our inverse FFT is unnormalised (x 1/1024)
@@ -98,6 +98,18 @@ __device__ __forceinline__ int nr_tlim(const NrGeom& g, int chunk) {
     if (p_hi > g.Lc) p_hi = g.Lc;
     const long long t = (p_hi + NF / 2 + NH - 1) / NH;        // frame t covers [256 t - 512, 256 t + 512)
     return t < g.F ? (int)t : g.F;
+}
+
+// loads that keep their program order (asm volatile): see the load schedule of k_nr_istft
+__device__ __forceinline__ float ldg_f32_ordered(const float* p) {
+    float v;
+    asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float2 ldg_f2_ordered(const float2* p) {
+    float2 v;
+    asm volatile("ld.global.nc.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+    return v;
 }
 
 // |z| through the SFU reciprocal square root (2 ulp); |S| only feeds the smoothed-threshold mask
@@ -132,9 +144,8 @@ __global__ void __launch_bounds__(256, 2) k_nr_stft(const void* __restrict__ aud
     extern __shared__ __align__(16) float sm[];
     float* xs = sm;                 // [4864]
     float* win = xs + kStftXs;      // [1024]
-    float* twc = win + NF;          // [1024]
-    float* tws = twc + NF;          // [1024]
-    float* Y = tws + NF;            // [8][2][32*33]; at the end plane k holds the 513 magnitudes of frame t0 + k
+    const cpx* tw = reinterpret_cast<const cpx*>(win + NF);  // [1024] (cos, sin)
+    float* Y = win + 3 * NF;        // [8] complex planes [32*33]; at the end float plane k holds the 513 magnitudes of frame t0 + k
     int16_t* raw = reinterpret_cast<int16_t*>(Y + 8 * 2 * kYPlane);  // [4864] int16, TMA destination
     __shared__ __align__(8) uint64_t bar;
     const int tid = threadIdx.x;
@@ -222,6 +233,7 @@ __global__ void __launch_bounds__(256, 2) k_nr_stft(const void* __restrict__ aud
     const int q = tid >> 5, lane = tid & 31;
     float* yr = Y + q * 2 * kYPlane;
     float* yi = yr + kYPlane;
+    cpx* yc = reinterpret_cast<cpx*>(yr);
     {   // step 1: 32 residues of the pair.  n = 32*n1 + n2, n2 = lane
         const float* xa = xs + (2 * q) * NH;
         const float* xb = xa + NH;
@@ -229,17 +241,11 @@ __global__ void __launch_bounds__(256, 2) k_nr_stft(const void* __restrict__ aud
 #pragma unroll
         for (int n1 = 0; n1 < 32; ++n1) {
             const int idx = 32 * n1 + lane;
-            const float w = win[idx];
-            v[n1] = cpx{xa[idx] * w, xb[idx] * w};
+            v[n1] = cscale(cpx{xa[idx], xb[idx]}, win[idx]);
         }
         fft_pow2<32>(v);
 #pragma unroll
-        for (int k1 = 0; k1 < 32; ++k1) {
-            const int tw = k1 * 32 + lane;
-            const cpx y = cmul(v[k1], cpx{twc[tw], -tws[tw]});
-            yr[k1 * kYs + lane] = y.x;
-            yi[k1 * kYs + lane] = y.y;
-        }
+        for (int k1 = 0; k1 < 32; ++k1) yc[k1 * kYs + lane] = cmul_conj(v[k1], tw[k1 * 32 + lane]);
     }
     __syncwarp();
     const long long row0 = ((long long)clip * g.n_chunks + chunk) * g.F;
@@ -250,7 +256,7 @@ __global__ void __launch_bounds__(256, 2) k_nr_stft(const void* __restrict__ aud
         // shared memory; the planes receive the magnitudes instead (row 2q at yr[0..513), row 2q+1 at yi[0..513)).
         cpx v[32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = cpx{yr[lane * kYs + i], yi[lane * kYs + i]};
+        for (int i = 0; i < 32; ++i) v[i] = yc[lane * kYs + i];
         fft_pow2<32>(v);
         __syncwarp();  // every lane has read its row
         const float sc = 0.5f / 512.0f;  // spectrum scaling 1/sum(win) = 1/512, and the 1/2 of the split
@@ -263,18 +269,18 @@ __global__ void __launch_bounds__(256, 2) k_nr_stft(const void* __restrict__ aud
         for (int k2 = 0; k2 <= 16; ++k2) {
             const float sr = __shfl_sync(0xffffffffu, v[k2 < 16 ? 31 - k2 : 31].x, src);
             const float si = __shfl_sync(0xffffffffu, v[k2 < 16 ? 31 - k2 : 31].y, src);
-            const float wr = lane == 0 ? v[(32 - k2) & 31].x : sr, wi = lane == 0 ? v[(32 - k2) & 31].y : si;
+            const cpx wc = lane == 0 ? cconj(v[(32 - k2) & 31]) : cpx{sr, -si};  // conj Z[1024 - k]
             const int f = lane + 32 * k2;
             if (has_a && f < NB) {
-                const float zr = v[k2 & 31].x, zi = v[k2 & 31].y;
-                const float ar = (zr + wr) * sc, ai = (zi - wi) * sc, br = (zi + wi) * sc, bi = (wr - zr) * sc;
-                const float ma = fast_mag(ar, ai), mb = fast_mag(br, bi);
-                Sa[f] = make_float2(ar, ai);
+                const cpx z = v[k2 & 31];
+                const cpx xa2 = cscale(cadd(z, wc), sc), xb2 = cscale_negi(csub(z, wc), sc);  // X_a, X_b = -i (Z - conj Z')/2
+                const float ma = fast_mag(xa2.x, xa2.y), mb = fast_mag(xb2.x, xb2.y);
+                Sa[f] = make_float2(xa2.x, xa2.y);
                 Aa[f] = ma;
                 yr[f] = ma;
                 yi[f] = mb;
                 if (has_b) {
-                    Sa[NB + f] = make_float2(br, bi);
+                    Sa[NB + f] = make_float2(xb2.x, xb2.y);
                     Aa[NB + f] = mb;
                 }
             }
@@ -608,10 +614,9 @@ __global__ void __launch_bounds__(256, 2) k_nr_istft(const float2* __restrict__ 
     // persistent: 2 CTAs per SM walk the (clip, chunk, tile) list, so the 13 KB of tables are fetched once per CTA
     extern __shared__ __align__(16) float sm[];
     float* win = sm;               // [1024]
-    float* twc = win + NF;
-    float* tws = twc + NF;
-    float* osc = tws + NF;         // [256] overlap-add scale
-    float* Y = osc + NH;           // [8][2][32*33]
+    const cpx* tw = reinterpret_cast<const cpx*>(win + NF);  // [1024] (cos, sin)
+    float* osc = win + 3 * NF;     // [256] overlap-add scale
+    float* Y = osc + NH;           // [8] complex planes [32*33]
     float* acc = Y + 8 * 2 * kYPlane;  // [7424]
     const int tid = threadIdx.x, q = tid >> 5, lane = tid & 31;
     for (int i = tid; i < 3 * NF + NH; i += 256) win[i] = tabs[i];
@@ -619,8 +624,7 @@ __global__ void __launch_bounds__(256, 2) k_nr_istft(const float2* __restrict__ 
     float wreg[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) wreg[j] = win[tid + 256 * j];
-    float* yr = Y + q * 2 * kYPlane;
-    float* yi = yr + kYPlane;
+    cpx* yc = reinterpret_cast<cpx*>(Y + q * 2 * kYPlane);
     const float oscv = osc[tid];
     for (int i = tid; i < kOlaOut; i += 256) acc[i] = 0.f;
     const long long total_tiles = (long long)tiles_per_chunk * g.n_chunks * g.batch;
@@ -650,26 +654,32 @@ __global__ void __launch_bounds__(256, 2) k_nr_istft(const float2* __restrict__ 
             const float2* Sa = S + (row0 + ta) * NB;
             const float* Ma = Msm + (row0 + ta) * NB;
             cpx v[32], mir[16];
+            // Load schedule (ncu: a burst of 64 loads per thread filled the LSU queue -- lg_throttle / mio_throttle stalls, during
+            // which a warp cannot issue its arithmetic either): all mask values first (32-bit), then the spectrum four cells at a
+            // time, each batch consumed before the next is requested.  The volatile asm keeps ptxas from re-merging the batches.
+            float ma[16], mb[16];
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+                ma[c] = va ? ldg_f32_ordered(Ma + lane + 32 * c) : 0.f;
+                mb[c] = vb ? ldg_f32_ordered(Ma + NB + lane + 32 * c) : 0.f;
+            }
 #pragma unroll
             for (int ib = 0; ib < 16; ib += 4) {
                 float2 sa[4], sb[4];
-                float ma[4], mb[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     const int f = lane + 32 * (ib + u);
-                    sa[u] = va ? Sa[f] : make_float2(0.f, 0.f);
-                    ma[u] = va ? Ma[f] : 0.f;
-                    sb[u] = vb ? Sa[NB + f] : make_float2(0.f, 0.f);
-                    mb[u] = vb ? Ma[NB + f] : 0.f;
+                    sa[u] = va ? ldg_f2_ordered(Sa + f) : make_float2(0.f, 0.f);
+                    sb[u] = vb ? ldg_f2_ordered(Sa + NB + f) : make_float2(0.f, 0.f);
                 }
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    const float ar = sa[u].x * ma[u], br = sb[u].x * mb[u];
-                    float ai = sa[u].y * ma[u], bi = sb[u].y * mb[u];
-                    if (ib + u == 0 && lane == 0) { ai = 0.f; bi = 0.f; }  // irfft ignores the imaginary part of DC
-                    v[ib + u] = cpx{ar - bi, ai + br};
-                    mir[ib + u] = cpx{ar + bi, br - ai};
+                    cpx xa2 = cscale(cpx{sa[u].x, sa[u].y}, ma[ib + u]), xb2 = cscale(cpx{sb[u].x, sb[u].y}, mb[ib + u]);
+                    if (ib + u == 0 && lane == 0) { xa2.y = 0.f; xb2.y = 0.f; }  // irfft ignores the imaginary part of DC
+                    v[ib + u] = cadd_posi(xa2, xb2);            // Xa + i Xb
+                    mir[ib + u] = cconj(cadd_negi(xa2, xb2));   // conj(Xa) + i conj(Xb) = conj(Xa - i Xb)
                 }
+                if (g.F == -1 - ib) asm volatile("trap;");  // never taken: a basic-block boundary ptxas does not hoist the next batch's loads across
             }
             // Nyquist (lane 0 only): real parts
             const float nyr = (lane == 0 && va) ? Sa[512].x * Ma[512] : 0.f, nyi = (lane == 0 && vb) ? Sa[NB + 512].x * Ma[NB + 512] : 0.f;
@@ -683,41 +693,44 @@ __global__ void __launch_bounds__(256, 2) k_nr_istft(const float2* __restrict__ 
             }
             fft_pow2<32, true>(v);
 #pragma unroll
-            for (int c = 0; c < 32; ++c) {
-                const int tw = c * 32 + lane;
-                const cpx y = cmul(v[c], cpx{twc[tw], tws[tw]});
-                yr[c * kYs + lane] = y.x;
-                yi[c * kYs + lane] = y.y;
-            }
+            for (int c = 0; c < 32; ++c) yc[c * kYs + lane] = cmul(v[c], tw[c * 32 + lane]);
         }
         __syncwarp();
         {
             cpx v[32];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = cpx{yr[lane * kYs + i], yi[lane * kYs + i]};
+            for (int i = 0; i < 32; ++i) v[i] = yc[lane * kYs + i];
             fft_pow2<32, true>(v);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {  // z[n = c + 32 d] at [c][d]
-                yr[lane * kYs + i] = v[i].x;
-                yi[lane * kYs + i] = v[i].y;
-            }
+            for (int i = 0; i < 32; ++i) yc[lane * kYs + i] = v[i];  // z[n = c + 32 d] at [c][d]: frame 2q in .x, frame 2q + 1 in .y
         }
         __syncthreads();
         // overlap-add the 16 frames of this pass.  Sample n = tid + 256 j of frame lt lands on hop block
         // m = lt + j + 16 pass - 3 at offset tid: each thread sums the (up to four) frames meeting in a block in
         // registers and touches acc[256 m + tid] once.
         {
-            const float* pb = Y + lane * kYs + q;  // element n = tid + 256 j of a plane sits at pb[8 j]
+            // element n = tid + 256 j of pair p sits at pb[p * kYPlane + 8 j]; one 64-bit load serves frames 2p and 2p + 1.
+            // Per hop block the frames are added in the same order as before (j = 0 first), so the sums keep their roundings.
+            const cpx* pb = reinterpret_cast<const cpx*>(Y) + lane * kYs + q;
+            float sacc[19];
 #pragma unroll
-            for (int mm = 0; mm < 19; ++mm) {
-                float sacc = 0.f;
+            for (int mm = 0; mm < 19; ++mm) sacc[mm] = 0.f;
+#pragma unroll
+            for (int d = 0; d < 11; ++d) {  // d = p + j: pair p's frames land on blocks 2p + j and 2p + 1 + j
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const int lt = mm - j;
-                    if (lt >= 0 && lt < 16) sacc = fmaf(pb[lt * kYPlane + 8 * j], wreg[j], sacc);
+                    const int pp = d - j;
+                    if (pp >= 0 && pp < 8) {
+                        const cpx z = pb[pp * kYPlane + 8 * j];
+                        sacc[2 * pp + j] = fmaf(z.x, wreg[j], sacc[2 * pp + j]);
+                        sacc[2 * pp + 1 + j] = fmaf(z.y, wreg[j], sacc[2 * pp + 1 + j]);
+                    }
                 }
+            }
+#pragma unroll
+            for (int mm = 0; mm < 19; ++mm) {
                 const int m = mm + 16 * pass - 3;
-                if (m >= 0 && m < kOlaBlocks) acc[256 * m + tid] += sacc;
+                if (m >= 0 && m < kOlaBlocks) acc[256 * m + tid] += sacc[mm];
             }
         }
         __syncthreads();

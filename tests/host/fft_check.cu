@@ -35,14 +35,15 @@ int main() {
 }
 // (appended) four-step 400-point check
 static int check400() {
-    static float xa[400], xb[400], win[400], twc[400], tws[400], Yre[kF400Plane], Yim[kF400Plane];
+    static float xa[400], xb[400], win[400];
+    static cpx tw[400], Y[kF400Plane];
     for (int i = 0; i < 400; ++i) {
         xa[i] = rand() / (float)RAND_MAX - 0.5f; xb[i] = rand() / (float)RAND_MAX - 0.5f;
         win[i] = (float)(0.5 - 0.5 * cos(2 * M_PI * i / 400));
-        twc[i] = (float)cos(2 * M_PI * ((i % 16) * (i / 16)) / 400); tws[i] = (float)sin(2 * M_PI * ((i % 16) * (i / 16)) / 400);
+        tw[i] = cpx{(float)cos(2 * M_PI * ((i % 16) * (i / 16)) / 400), (float)sin(2 * M_PI * ((i % 16) * (i / 16)) / 400)};
     }
-    for (int n2 = 0; n2 < 16; ++n2) fft400_step1(xa, xb, win, twc, tws, n2, Yre, Yim);
-    for (int k1 = 0; k1 < 25; ++k1) fft400_step2(k1, Yre, Yim);
+    for (int n2 = 0; n2 < 16; ++n2) fft400_step1(xa, xb, win, tw, n2, Y);
+    for (int k1 = 0; k1 < 25; ++k1) fft400_step2(k1, Y);
     double err = 0, mx = 0;
     for (int k = 0; k <= 200; ++k) {
         double ar = 0, ai = 0, br = 0, bi = 0;
@@ -52,7 +53,7 @@ static int check400() {
             br += (double)xb[n] * win[n] * cos(a); bi += (double)xb[n] * win[n] * sin(a);
         }
         float pa, pb;
-        fft400_pair_power(Yre, Yim, k, &pa, &pb);
+        fft400_pair_power(Y, k, &pa, &pb);
         double ra = ar * ar + ai * ai, rb = br * br + bi * bi;
         mx = fmax(mx, fmax(ra, rb));
         err = fmax(err, fmax(fabs(pa - ra), fabs(pb - rb)));
