@@ -120,8 +120,7 @@ struct MelArgs {
     int fmt, n_frames, n_mels;
     float* out;                            // [batch][n_mels][n_frames] raw log10 values
     unsigned int* gmax;                    // [batch] bits of (max log10 + 10) >= 0
-    const unsigned long long* sumsq;       // fused normalise of pcm16 input: per-clip sum of squared int16 samples, else null
-    const double* sumsq_f;                 // fused normalise of float32 input: per-clip sum of squares, else null
+    const float* gain;                     // fused normalise: per-clip gain from k_mel_gain (negative: silent clip, passed through), else null
     int requant;                           // clip / x32767 / truncate / (/32768) while staging (the chain's WAV round trip)
     float target_dbfs;
     const float* consts;
@@ -130,8 +129,10 @@ struct MelArgs {
     int n_w;
 };
 
-__device__ __forceinline__ float mel_requant(const MelArgs& a, float x, float gain, bool silent) {
-    return a.requant ? (float)quant_pcm16(apply_gain(x, gain, silent)) * 3.0517578125e-05f : x;
+// normalize_gain (clip of x * gain; a silent clip passes through unclipped) followed by the WAV round trip (clip, x 32767, truncate, / 32768):
+// the second clip makes the first one redundant, and a silent clip is the gain 1.0f (x * 1.0f is x), so one multiply and one clip serve both
+__device__ __forceinline__ float mel_requant(const MelArgs& a, float x, float gain, bool /*silent: folded into gain by the caller*/) {
+    return a.requant ? (float)__float2int_rz(__fmul_rn(fminf(fmaxf(__fmul_rn(x, gain), -1.0f), 1.0f), 32767.0f)) * 3.0517578125e-05f : x;
 }
 __device__ __forceinline__ float mel_sample(const MelArgs& a, int s16, float gain, bool silent) {
     return mel_requant(a, (float)s16 * 3.0517578125e-05f, gain, silent);  // /32768, exact
@@ -192,8 +193,11 @@ __global__ void __launch_bounds__(256, 2) k_logmel(MelArgs a, int tiles_per_clip
             // stage the tile's samples: reflect pad 200 around [x, 160 zeros]; fused normalise + requantise
             bool silent = true;
             float gain = 1.0f;
-            if (a.sumsq) gain = gain_from_meansq((double)a.sumsq[b] / 1073741824.0 / (double)a.n, a.target_dbfs, &silent);
-            else if (a.sumsq_f) gain = gain_from_meansq(a.sumsq_f[b] / (double)a.n, a.target_dbfs, &silent);
+            if (a.gain) {
+                gain = a.gain[b];
+                silent = gain < 0.f;
+                if (silent) gain = 1.0f;
+            }
             const int16_t* src;
             if (mel_tile_interior(a, b, t0, &src)) {
                 mbar_wait(&bar, parity);
@@ -321,6 +325,17 @@ __global__ void __launch_bounds__(256, 2) k_logmel(MelArgs a, int tiles_per_clip
     }
 }
 
+// per-clip gain of the fused normalise, once per clip instead of once per thread and tile (log10f + powf + a double division)
+__global__ void k_mel_gain(const unsigned long long* __restrict__ sumsq, const double* __restrict__ sumsq_f, long long n, float target_dbfs,
+                           float* __restrict__ gain, int batch) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= batch) return;
+    bool silent = true;
+    const float g = sumsq ? gain_from_meansq((double)sumsq[b] / 1073741824.0 / (double)n, target_dbfs, &silent)
+                          : gain_from_meansq(sumsq_f[b] / (double)n, target_dbfs, &silent);
+    gain[b] = silent ? -1.0f : g;  // a real gain is 10^x > 0
+}
+
 // log_spec = maximum(log_spec, log_spec.max() - 8.0); (log_spec + 4.0) / 4.0
 // (x / 4.0 is written as x * 0.25: the same value for every float, without the division's slow path)
 __device__ __forceinline__ float logmel_fin(float x, float thr) { return __fmul_rn(__fadd_rn(fmaxf(x, thr), 4.0f), 0.25f); }
@@ -374,8 +389,15 @@ int launch_logmel(const void* d_audio, int fmt, long long n, long long batch, lo
     OSB_CUDA(cudaMemsetAsync(gmax, 0, sizeof(unsigned int) * batch, st));
     MelArgs a;
     a.audio = d_audio; a.n = n; a.stride = stride; a.fmt = fmt; a.n_frames = n_frames; a.n_mels = n_mels;
-    a.out = d_out; a.gmax = gmax; a.sumsq = d_sumsq; a.target_dbfs = target_dbfs;
-    a.sumsq_f = d_sumsq_f; a.requant = (d_sumsq || d_sumsq_f || requant) ? 1 : 0;
+    a.out = d_out; a.gmax = gmax; a.target_dbfs = target_dbfs; a.gain = nullptr;
+    if (d_sumsq || d_sumsq_f) {
+        float* gain;
+        OSB_CUDA(scr.alloc(&gain, (size_t)batch));
+        OSB_LAUNCH(k_mel_gain, (unsigned)((batch + 127) / 128), 128, 0, st, d_sumsq, d_sumsq_f, n, target_dbfs, gain, (int)batch);
+        OSB_CHECK_LAUNCH();
+        a.gain = gain;
+    }
+    a.requant = (d_sumsq || d_sumsq_f || requant) ? 1 : 0;
     a.consts = t->d_consts; a.mel_meta = t->d_meta; a.mel_w = t->d_w; a.n_w = t->n_w;
     const int tiles_per_clip = (n_frames + MF - 1) / MF;
     const long long total_tiles_ll = (long long)tiles_per_clip * batch;
