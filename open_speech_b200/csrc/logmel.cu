@@ -325,6 +325,193 @@ __global__ void __launch_bounds__(256, 2) k_logmel(MelArgs a, int tiles_per_clip
     }
 }
 
+// ---------------------------------------------------------------- integer-staged variant: three CTAs per SM
+// Whenever the samples entering the transform are 16-bit integers / 32768 -- pcm16 input, or any input that goes through the chain's
+// WAV round trip (requant) -- the staged tile is kept as biased uint16 (10.7 KB instead of 21.4 KB), the power tile overwrites the
+// transform planes of its own frame pair (no separate P), and the next tile's samples wait in REGISTERS (loaded while step 2 and the mel
+// phase run) instead of a TMA buffer: 69.9 KB of shared memory and 80 registers, i.e. 24 warps per SM instead of 16.
+//   smem: [Y / P: 16 x 425 complex] [win * 2^-15 | tw] [xs16: 5360 x uint16 = sample + 32768]
+// Step 1 rebuilds the float from the uint16 with one byte permute (0x4B00'xxxx = 2^23 + u) and one packed subtract: no I2F.
+constexpr int kLm16Smem = 16 * kF400Plane * 8 + 1200 * 4 + kXs * 2;  // 69,920 B
+static_assert((16 * kF400Plane * 8 + 1200 * 4) % 16 == 0, "xs16 must be 16-byte aligned");
+
+template <bool F32>
+__device__ __forceinline__ bool lm16_interior(const MelArgs& a, int b, int t0, const char** src) {
+    const long long p0 = (long long)kHop * t0 - kNfft / 2;  // multiple of 8 samples
+    const char* s = reinterpret_cast<const char*>(a.audio) + ((long long)b * a.stride + p0) * (F32 ? 4 : 2);
+    *src = s;
+    return p0 >= 0 && p0 + kXs <= a.n && (((uintptr_t)s) & 15) == 0;
+}
+// sample -> biased uint16 of what the reference's int16 round trip leaves (or of the pcm16 sample itself)
+__device__ __forceinline__ uint32_t lm16_q(const MelArgs& a, float x, float gain) {
+    return (uint32_t)(__float2int_rz(__fmul_rn(fminf(fmaxf(__fmul_rn(x, gain), -1.0f), 1.0f), 32767.0f)) + 32768);
+}
+__device__ __forceinline__ uint32_t lm16_q16(const MelArgs& a, int s16, float gain) {
+    return a.requant ? lm16_q(a, (float)s16 * 3.0517578125e-05f, gain) : (uint32_t)(s16 + 32768);
+}
+
+template <bool F32>
+__global__ void __launch_bounds__(256, 3) k_logmel16(MelArgs a, int tiles_per_clip, int total_tiles) {
+    extern __shared__ __align__(16) float sm[];
+    cpx* Y = reinterpret_cast<cpx*>(sm);                              // [16][425] complex; pair q's power tile later sits at Y_q as [204] x (frame q, frame q + 16)
+    float* win = sm + 16 * kF400Plane * 2;                            // [400] Hann * 2^-15
+    const cpx* tw = reinterpret_cast<const cpx*>(win + 400);          // [400] (cos, sin)
+    uint16_t* xs16 = reinterpret_cast<uint16_t*>(win + 1200);         // [kXs]
+    __shared__ int mel_meta[128];
+    __shared__ __align__(16) float mel_wsm[kMelWMax];
+    const int tid = threadIdx.x;
+    constexpr int NV = F32 ? 6 : 3;              // 16-byte vectors per thread: 1,340 float4 or 670 uint4 per tile
+    constexpr int kVecs = F32 ? kXs / 4 : kXs / 8;
+
+    for (int i = tid; i < 400; i += 256) win[i] = a.consts[i] * 3.0517578125e-05f;  // exact: the staged samples are integers
+    for (int i = tid; i < 800; i += 256) win[400 + i] = a.consts[400 + i];
+    for (int m = tid; m < a.n_mels; m += 256) mel_meta[m] = a.mel_meta[m];
+    for (int i = tid; i < a.n_w; i += 256) mel_wsm[i] = a.mel_w[i];
+
+    uint4 pre[NV];
+    bool pre_ok = false;
+    auto prefetch = [&](int tile) {
+        const char* src;
+        pre_ok = tile < total_tiles && lm16_interior<F32>(a, tile / tiles_per_clip, (tile % tiles_per_clip) * MF, &src);
+        if (pre_ok) {
+#pragma unroll
+            for (int r = 0; r < NV; ++r) {
+                const int i = tid + 256 * r;
+                if (i < kVecs) pre[r] = ld_stream_u4(reinterpret_cast<const uint4*>(src) + i);
+            }
+        }
+    };
+    prefetch(blockIdx.x);
+
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int b = tile / tiles_per_clip, t0 = (tile - b * tiles_per_clip) * MF;
+        {
+            float gain = 1.0f;
+            if (a.gain) {
+                gain = a.gain[b];
+                if (gain < 0.f) gain = 1.0f;  // silent clip: passed through (x * 1.0f is x; the WAV round trip clips it all the same)
+            }
+            if (pre_ok) {
+#pragma unroll
+                for (int r = 0; r < NV; ++r) {
+                    const int i = tid + 256 * r;
+                    if (i < kVecs) {
+                        const uint32_t w[4] = {pre[r].x, pre[r].y, pre[r].z, pre[r].w};
+                        if (F32) {
+                            uint32_t o[4];
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) o[k] = lm16_q(a, __uint_as_float(w[k]), gain);
+                            *reinterpret_cast<uint2*>(xs16 + 4 * i) = make_uint2(o[0] | (o[1] << 16), o[2] | (o[3] << 16));
+                        } else {
+                            uint32_t o[4];
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                o[k] = lm16_q16(a, (int)(int16_t)(w[k] & 0xFFFF), gain) | (lm16_q16(a, (int)(int16_t)(w[k] >> 16), gain) << 16);
+                            *reinterpret_cast<uint4*>(xs16 + 8 * i) = make_uint4(o[0], o[1], o[2], o[3]);
+                        }
+                    }
+                }
+            } else {
+                // clip edges: reflect pad 200 around [x, 160 zeros]
+                const long long L = a.n + kPad;
+                const long long p0 = (long long)kHop * t0 - kNfft / 2;
+                for (int i = tid; i < kXs; i += 256) {
+                    long long p = p0 + i;
+                    while (p < 0 || p >= L) p = p < 0 ? -p : 2 * (L - 1) - p;
+                    uint32_t v = 32768u;
+                    if (p < a.n) {
+                        if (F32) v = lm16_q(a, reinterpret_cast<const float*>(a.audio)[(long long)b * a.stride + p], gain);
+                        else v = lm16_q16(a, (int)reinterpret_cast<const int16_t*>(a.audio)[(long long)b * a.stride + p], gain);
+                    }
+                    xs16[i] = (uint16_t)v;
+                }
+            }
+        }
+        __syncthreads();  // xs16 complete (and every thread is past the previous tile's mel phase: Y is free)
+        {   // four-step FFT, step 1: 16 frame pairs x 16 residues = 256 tasks; pair q = frames (q, q + 16)
+            const int q = tid >> 4, n2 = tid & 15;
+            const uint16_t* xa = xs16 + q * kHop + n2;
+            cpx v[25];
+#pragma unroll
+            for (int n1 = 0; n1 < 25; ++n1) {
+                const int idx = 16 * n1;
+                // 0x4B00'0000 | u is the float 2^23 + u: subtracting 2^23 + 2^15 leaves the signed sample, exactly
+                const cpx raw2 = cpx{__uint_as_float(__byte_perm((uint32_t)xa[idx], 0x4B00u, 0x5410)),
+                                     __uint_as_float(__byte_perm((uint32_t)xa[idx + 16 * kHop], 0x4B00u, 0x5410))};
+                v[n1] = cscale(cadd(raw2, cpx{-8421376.0f, -8421376.0f}), win[idx + n2]);
+            }
+            dft25(v);
+            cpx* y = Y + q * kF400Plane + n2;
+#pragma unroll
+            for (int k1 = 0; k1 < 25; ++k1) y[k1 * kF400Stride] = cmul_conj(v[k1], tw[k1 * 16 + n2]);
+        }
+        __syncthreads();
+        if (!F32) prefetch(tile + gridDim.x);  // the next tile's samples travel while step 2 and the mel phase run
+        {   // step 2 fused with the power spectrum (see k_logmel); the powers of pair q overwrite its own planes
+            const int lane = tid & 31, k1 = lane < 25 ? lane : 0, src = lane == 0 ? 0 : (lane < 25 ? 25 - lane : 0);
+#pragma unroll 1
+            for (int h = 0; h < 2; ++h) {
+                const int q = (tid >> 5) + 8 * h;
+                cpx* yq = Y + q * kF400Plane;
+                cpx v[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = yq[k1 * kF400Stride + i];
+                __syncwarp();  // every lane holds its row: the planes of this pair may be overwritten
+                fft_pow2<16>(v);
+                float2* Pq = reinterpret_cast<float2*>(yq);
+                if (lane >= 25 && lane < 28) Pq[kBins + lane - 25] = make_float2(0.f, 0.f);  // rows the zero-padded mel taps may touch
+#pragma unroll
+                for (int k2 = 0; k2 <= 8; ++k2) {
+                    const float sr = __shfl_sync(0xffffffffu, v[k2 < 8 ? 15 - k2 : 15].x, src);
+                    const float si = __shfl_sync(0xffffffffu, v[k2 < 8 ? 15 - k2 : 15].y, src);
+                    const cpx mc = lane == 0 ? cconj(v[(16 - k2) & 15]) : cpx{sr, -si};  // conj Z[400 - k]
+                    const int k = k1 + 25 * k2;
+                    if (lane < 25 && k < kBins) {
+                        const cpx sa = cadd(v[k2], mc), sb = csub(v[k2], mc);
+                        Pq[k] = make_float2(fmaf(sa.x, sa.x, sa.y * sa.y), fmaf(sb.x, sb.x, sb.y * sb.y));
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        if (F32) prefetch(tile + gridDim.x);  // float32 input: 24 registers of samples, requested once step 2's 16 complex values are dead
+        // sparse mel contraction + log10: thread = (pair l16: frames l16 and l16 + 16, one mel row at a time)
+        const int l16 = tid & 15;
+        const bool live0 = (t0 + l16) < a.n_frames, live1 = (t0 + 16 + l16) < a.n_frames;
+        float vmax = -10.0f;
+        float* outb = a.out + (long long)b * a.n_mels * a.n_frames + t0 + l16;
+        const cpx* Pf = Y + l16 * kF400Plane;
+        for (int m = tid >> 4; m < a.n_mels; m += 16) {
+            const int meta = mel_meta[m];
+            const int len4 = (meta >> 8) & 255;
+            const float* w = mel_wsm + (meta >> 16);
+            const cpx* pp = Pf + (meta & 255);
+            cpx acc0 = cpx{0.f, 0.f}, acc1 = cpx{0.f, 0.f};
+            for (int i = 0; i < len4; i += 4) {
+                const float4 w4 = *reinterpret_cast<const float4*>(w + i);
+                acc0 = cfma(pp[i], w4.x, acc0);
+                acc1 = cfma(pp[i + 1], w4.y, acc1);
+                acc0 = cfma(pp[i + 2], w4.z, acc0);
+                acc1 = cfma(pp[i + 3], w4.w, acc1);
+            }
+            const cpx acc = cadd(acc0, acc1);
+            const float v0 = __log2f(fmaxf(acc.x, 1e-10f)) * 0.30102999566398120f;
+            const float v1 = __log2f(fmaxf(acc.y, 1e-10f)) * 0.30102999566398120f;
+            if (live0) {
+                outb[(long long)m * a.n_frames] = v0;
+                vmax = fmaxf(vmax, v0);
+            }
+            if (live1) {
+                outb[(long long)m * a.n_frames + 16] = v1;
+                vmax = fmaxf(vmax, v1);
+            }
+        }
+        vmax = warp_max(vmax);
+        if ((tid & 31) == 0) atomicMax(a.gmax + b, __float_as_uint(vmax + 10.0f));
+        // (no barrier here: the next tile's staging only writes xs16, and its step 1 follows a barrier)
+    }
+}
+
 // per-clip gain of the fused normalise, once per clip instead of once per thread and tile (log10f + powf + a double division)
 __global__ void k_mel_gain(const unsigned long long* __restrict__ sumsq, const double* __restrict__ sumsq_f, long long n, float target_dbfs,
                            float* __restrict__ gain, int batch) {
@@ -379,7 +566,8 @@ int launch_logmel(const void* d_audio, int fmt, long long n, long long batch, lo
     static PerDeviceOnce once;
     OSB_CUDA(once.run([&] {
         cudaError_t e = cudaFuncSetAttribute(k_logmel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLogmelSmemF32);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_logmel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLogmelSmemP16);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_logmel16<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLm16Smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_logmel16<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLm16Smem);
         return e;
     }));
     const int n_frames = (int)((n + kPad) / kHop);
@@ -406,10 +594,18 @@ int launch_logmel(const void* d_audio, int fmt, long long n, long long batch, lo
         return OSB_ERR_INVALID_ARG;
     }
     const int total_tiles = (int)total_tiles_ll;
-    const int persistent = 2 * num_sms();  // 2 resident CTAs per SM (97 KB of shared memory each)
-    const int grid = total_tiles < persistent ? total_tiles : persistent;
-    if (fmt == OSB_FMT_PCM16) OSB_LAUNCH(k_logmel<false>, grid, 256, kLogmelSmemP16, st, a, tiles_per_clip, total_tiles);
-    else OSB_LAUNCH(k_logmel<true>, grid, 256, kLogmelSmemF32, st, a, tiles_per_clip, total_tiles);
+    if (fmt == OSB_FMT_PCM16 || a.requant) {
+        // integer-staged kernel: 3 resident CTAs per SM (70 KB of shared memory, 80 registers)
+        const int persistent = 3 * num_sms();
+        const int grid = total_tiles < persistent ? total_tiles : persistent;
+        if (fmt == OSB_FMT_PCM16) OSB_LAUNCH(k_logmel16<false>, grid, 256, kLm16Smem, st, a, tiles_per_clip, total_tiles);
+        else OSB_LAUNCH(k_logmel16<true>, grid, 256, kLm16Smem, st, a, tiles_per_clip, total_tiles);
+    } else {
+        // float32 audio taken as it is: float staging, 2 resident CTAs per SM (108 KB of shared memory)
+        const int persistent = 2 * num_sms();
+        const int grid = total_tiles < persistent ? total_tiles : persistent;
+        OSB_LAUNCH(k_logmel<true>, grid, 256, kLogmelSmemF32, st, a, tiles_per_clip, total_tiles);
+    }
     OSB_CHECK_LAUNCH();
     const long long per_clip = (long long)n_mels * n_frames;
     long long fb = (per_clip / 4 + 255) / 256;
