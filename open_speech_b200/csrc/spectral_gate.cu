@@ -35,6 +35,30 @@ constexpr int NF = 1024, NH = 256, NB = 513;       // n_fft, hop, one-sided bins
 constexpr long long kChunk = 600000, kCtx = 30000;
 constexpr int kYs = 33, kYPlane = 32 * 33;          // four-step planes [32][33]: a frame pair owns one COMPLEX plane (= two float planes)
 
+// a row of 32 complex values of a plane <-> registers: 128-bit accesses when the row stride keeps rows 16-byte aligned
+__device__ __forceinline__ void nr_row_load(cpx (&v)[32], const cpx* row) {
+    if constexpr (kYs % 2 == 0) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const float4 t = reinterpret_cast<const float4*>(row)[i];
+            v[2 * i] = cpx{t.x, t.y};
+            v[2 * i + 1] = cpx{t.z, t.w};
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = row[i];
+    }
+}
+__device__ __forceinline__ void nr_row_store(cpx* row, const cpx (&v)[32]) {
+    if constexpr (kYs % 2 == 0) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) reinterpret_cast<float4*>(row)[i] = make_float4(v[2 * i].x, v[2 * i].y, v[2 * i + 1].x, v[2 * i + 1].y);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) row[i] = v[i];
+    }
+}
+
 struct NrGeom {
     long long n;       // samples per clip
     long long stride;  // samples between clips
@@ -255,8 +279,7 @@ __global__ void __launch_bounds__(256, 2) k_nr_stft(const void* __restrict__ aud
         // go straight to global memory: lanes are consecutive bins, every store is coalesced.  Z never returns to
         // shared memory; the planes receive the magnitudes instead (row 2q at yr[0..513), row 2q+1 at yi[0..513)).
         cpx v[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = yc[lane * kYs + i];
+        nr_row_load(v, yc + lane * kYs);
         fft_pow2<32>(v);
         __syncwarp();  // every lane has read its row
         const float sc = 0.5f / 512.0f;  // spectrum scaling 1/sum(win) = 1/512, and the 1/2 of the split
@@ -607,6 +630,7 @@ __global__ void __launch_bounds__(kMaskThreads, 2) k_nr_mask(const float* __rest
 // ---------------------------------------------------------------- inverse STFT + overlap-add
 // grid (tiles, n_chunks, batch): tile = 29 hop blocks [j0, j0+29) <- frames [j0-1, j0+30]
 constexpr int kOlaBlocks = 29, kOlaOut = kOlaBlocks * NH;  // 7424 samples
+constexpr int kIstftBatch = 2;  // spectrum cells per load batch of the inverse transform's first step (measured 1 / 2 / 4 / 8)
 
 __global__ void __launch_bounds__(256, 2) k_nr_istft(const float2* __restrict__ S, const float* __restrict__ Msm, NrGeom g,
                                                      const float* __restrict__ tabs, int j_first, int tiles_per_chunk, float* __restrict__ out,
@@ -664,16 +688,16 @@ __global__ void __launch_bounds__(256, 2) k_nr_istft(const float2* __restrict__ 
                 mb[c] = vb ? ldg_f32_ordered(Ma + NB + lane + 32 * c) : 0.f;
             }
 #pragma unroll
-            for (int ib = 0; ib < 16; ib += 4) {
-                float2 sa[4], sb[4];
+            for (int ib = 0; ib < 16; ib += kIstftBatch) {
+                float2 sa[kIstftBatch], sb[kIstftBatch];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < kIstftBatch; ++u) {
                     const int f = lane + 32 * (ib + u);
                     sa[u] = va ? ldg_f2_ordered(Sa + f) : make_float2(0.f, 0.f);
                     sb[u] = vb ? ldg_f2_ordered(Sa + NB + f) : make_float2(0.f, 0.f);
                 }
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < kIstftBatch; ++u) {
                     cpx xa2 = cscale(cpx{sa[u].x, sa[u].y}, ma[ib + u]), xb2 = cscale(cpx{sb[u].x, sb[u].y}, mb[ib + u]);
                     if (ib + u == 0 && lane == 0) { xa2.y = 0.f; xb2.y = 0.f; }  // irfft ignores the imaginary part of DC
                     v[ib + u] = cadd_posi(xa2, xb2);            // Xa + i Xb
@@ -698,11 +722,9 @@ __global__ void __launch_bounds__(256, 2) k_nr_istft(const float2* __restrict__ 
         __syncwarp();
         {
             cpx v[32];
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = yc[lane * kYs + i];
+            nr_row_load(v, yc + lane * kYs);
             fft_pow2<32, true>(v);
-#pragma unroll
-            for (int i = 0; i < 32; ++i) yc[lane * kYs + i] = v[i];  // z[n = c + 32 d] at [c][d]: frame 2q in .x, frame 2q + 1 in .y
+            nr_row_store(yc + lane * kYs, v);  // z[n = c + 32 d] at [c][d]: frame 2q in .x, frame 2q + 1 in .y
         }
         __syncthreads();
         // overlap-add the 16 frames of this pass.  Sample n = tid + 256 j of frame lt lands on hop block
