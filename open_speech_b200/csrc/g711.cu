@@ -108,8 +108,8 @@ struct LinArgs {
     double step_o, step_n;  // 1/(n_in-1), 1/(n_out-1) formed in f64 on the host like np.linspace
     int exact_int;          // 1: the integer fast path below is provably bit-identical for these sizes
     const unsigned* tab;    // exact_int: per output j, (floor(p) << 16) | (1 << 15 if interior coincidence) | remainder r
-    unsigned long long magic;  // ceil(2^shift / (m-1))
-    int shift;                 // 32 + ceil(log2(m-1))
+    unsigned magic;            // floor(2^(31+l) / (m-1)) + 1, l = ceil(log2(m-1)): exact floor division of any dividend < 2^31 by m-1 < 2^15
+    int shift;                 // l - 1:  U / (m-1) == __umulhi(U, magic) >> shift   (Granlund-Montgomery, N = 31)
 };
 
 template <int IN_FMT>
@@ -166,9 +166,9 @@ __device__ __forceinline__ bool interp_int(const void* in, long long j, const Li
     if (r == 0) { y = f0; return true; }           // j = 0 or j = m-1
     const int f1 = load_in<IN_FMT>(in, i + 1);
     const unsigned den = (unsigned)(a.n_out - 1);
-    // U = (y + 32768) (m-1) >= 0 and < 2^31; q = floor(U / den) by multiply-shift (Granlund-Montgomery, exact for 32-bit dividends)
+    // U = (y + 32768) (m-1) >= 0 and < 2^31; q = floor(U / den) by one high multiply and a shift
     const unsigned U = (unsigned)(f0 + 32768) * den + (unsigned)((f1 - f0) * (int)r);
-    const unsigned q = (unsigned)(((unsigned long long)U * a.magic) >> a.shift);
+    const unsigned q = __umulhi(U, a.magic) >> a.shift;
     const unsigned rem = U - q * den;
     if (rem == 0 && f1 != f0) return false;        // exactly integral: float64's rounding error decides
     const int yf = (int)q - 32768;                 // floor of the exact value
@@ -228,6 +228,118 @@ __global__ void __launch_bounds__(256) k_resample_linear(LinArgs a, int vec_ok) 
             for (int k = 0; k < 8; ++k)
                 if (j0 + k < a.n_out) o[k] = (uint8_t)compress<OUT_FMT>((int)(int16_t)v[k]);
         }
+    }
+}
+
+// Tiled variant for many short rows (the realtime door replayed over whole recordings: 768,000 chunks of 160 -> 320 per 256 x 60 s).
+// A CTA takes R dense rows at a time: the wire bytes are expanded ONCE into shared memory (the per-output kernel above expands two
+// samples per output: 4x the work for 2x upsampling), the (i, r) table is read from shared memory, the results are assembled in shared
+// memory and leave as whole 16-byte stores, and the ~1 % of outputs that need the float64 evaluation are queued and then worked off by
+// consecutive threads instead of stalling a warp per straggler.  Same arithmetic (interp_int / interp_one): bit-identical.
+constexpr int kLinTileRows = 32, kLinSlowCap = 1024;
+
+// the queue of float64 evaluations is full (adversarial input: it holds 10 % of a 160 -> 320 tile, real audio needs ~1 %): evaluate in
+// place, out of line so that the eight unrolled outputs of the main loop do not each carry a copy of the float64 path
+// (scalars by value: a reference to the kernel's argument block would force the whole block into local memory)
+template <int IN_FMT>
+__device__ __noinline__ int interp_one_overflow(const void* in, long long j, long long n_in, long long n_out, double step_o, double step_n) {
+    LinArgs a;
+    a.n_in = n_in; a.n_out = n_out; a.step_o = step_o; a.step_n = step_n;
+    return interp_one<IN_FMT>(in, j, a);
+}
+
+template <int IN_FMT>
+__global__ void __launch_bounds__(256) k_resample_linear_tiled(LinArgs a, long long n_tiles) {
+    extern __shared__ __align__(16) unsigned char lsm[];
+    const int n_in = (int)a.n_in, n_out = (int)a.n_out;
+    unsigned* tab = reinterpret_cast<unsigned*>(lsm);                                     // [n_out]
+    int16_t* outb = reinterpret_cast<int16_t*>(tab + n_out);                              // [R][n_out]   (n_out % 8 == 0: 16-byte rows)
+    int16_t* samp = outb + kLinTileRows * n_out;                                          // [R][n_in]
+    unsigned* slow = reinterpret_cast<unsigned*>(samp + ((kLinTileRows * n_in + 2) & ~1));  // [kLinSlowCap]  row << 16 | j  (one spare sample in between)
+    __shared__ int slow_n;
+    const int tid = threadIdx.x;
+    constexpr int in_es = (IN_FMT == OSB_FMT_PCM16) ? 2 : 1;
+    for (int j = tid; j < n_out; j += 256) tab[j] = a.tab[j];
+    const int gpr = n_out / 8;  // 8-output groups per row
+    const unsigned den = (unsigned)(n_out - 1), magic = a.magic;
+    const int shift = a.shift;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const long long row0 = tile * kLinTileRows;
+        const int rows = (int)((a.batch - row0) < kLinTileRows ? (a.batch - row0) : kLinTileRows);
+        const unsigned char* inb = reinterpret_cast<const unsigned char*>(a.in) + row0 * n_in * in_es;
+        if (tid == 0) slow_n = 0;
+        // expand / copy the tile's input once: 4 samples per thread and pass (rows are dense and the tile starts 4-byte aligned)
+        const int words = rows * n_in * in_es / 4;
+        for (int w = tid; w < words; w += 256) {
+            const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(inb) + w);
+            if (IN_FMT == OSB_FMT_PCM16) {
+                reinterpret_cast<uint32_t*>(samp)[w] = v;
+            } else {
+                const uint32_t lo = (uint32_t)(expand<IN_FMT>(v & 0xFFu) & 0xFFFF) | ((uint32_t)expand<IN_FMT>((v >> 8) & 0xFFu) << 16);
+                const uint32_t hi = (uint32_t)(expand<IN_FMT>((v >> 16) & 0xFFu) & 0xFFFF) | ((uint32_t)expand<IN_FMT>(v >> 24) << 16);
+                reinterpret_cast<uint2*>(samp)[w] = make_uint2(lo, hi);
+            }
+        }
+        __syncthreads();
+        const int groups = rows * gpr;
+        for (int g = tid; g < groups; g += 256) {
+            const int r = g / gpr, j0 = (g - r * gpr) * 8;
+            const int16_t* sr = samp + r * n_in;
+            const uint4 e0 = *reinterpret_cast<const uint4*>(tab + j0), e1 = *reinterpret_cast<const uint4*>(tab + j0 + 4);
+            const unsigned e[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
+            int v[8];
+            unsigned slowmask = 0;
+            // straight-line: every output loads both neighbours (samp has one spare element behind the last row) and runs the division;
+            // what the table or the remainder hands over to float64 is collected in a mask and queued after the loop
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const unsigned i = e[k] >> 16, rr = e[k] & 0x7FFFu;
+                const int f0 = sr[i], f1 = sr[i + 1];
+                const unsigned U = (unsigned)(f0 + 32768) * den + (unsigned)((f1 - f0) * (int)rr);
+                const unsigned q = __umulhi(U, magic) >> shift;
+                const unsigned rem = U - q * den;
+                const int yf = (int)q - 32768;
+                v[k] = (yf >= 0 || rem == 0) ? yf : yf + 1;  // rr == 0: U = (f0 + 32768) den, so q - 32768 = f0 exactly
+                // interior coincidence of the two grids (flag), or an exactly integral interpolant between different samples
+                const bool hand_over = (e[k] & 0x8000u) || (rr != 0 && rem == 0 && f1 != f0);
+                slowmask |= hand_over ? (1u << k) : 0u;
+            }
+            while (slowmask) {
+                const int k = __ffs(slowmask) - 1;
+                slowmask &= slowmask - 1;
+                const int pos = atomicAdd(&slow_n, 1);
+                if (pos < kLinSlowCap) {
+                    slow[pos] = ((unsigned)r << 16) | (unsigned)(j0 + k);
+                } else {
+                    const int y = interp_one_overflow<IN_FMT>(inb + (long long)r * n_in * in_es, j0 + k, a.n_in, a.n_out, a.step_o, a.step_n);
+#pragma unroll
+                    for (int kk = 0; kk < 8; ++kk)
+                        if (kk == k) v[kk] = y;
+                }
+            }
+            uint4 w;
+            w.x = (uint32_t)(v[0] & 0xFFFF) | ((uint32_t)v[1] << 16);
+            w.y = (uint32_t)(v[2] & 0xFFFF) | ((uint32_t)v[3] << 16);
+            w.z = (uint32_t)(v[4] & 0xFFFF) | ((uint32_t)v[5] << 16);
+            w.w = (uint32_t)(v[6] & 0xFFFF) | ((uint32_t)v[7] << 16);
+            *reinterpret_cast<uint4*>(outb + r * n_out + j0) = w;
+        }
+        __syncthreads();
+        {   // the float64 evaluations, one per thread
+            const int ns = slow_n < kLinSlowCap ? slow_n : kLinSlowCap;
+            for (int sidx = tid; sidx < ns; sidx += 256) {
+                const unsigned it = slow[sidx];
+                const int r = (int)(it >> 16), j = (int)(it & 0xFFFFu);
+                outb[r * n_out + j] = (int16_t)interp_one<IN_FMT>(inb + (long long)r * n_in * in_es, j, a);
+            }
+        }
+        __syncthreads();
+        {
+            uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<int16_t*>(a.out) + row0 * n_out);
+            const int vecs = rows * n_out / 8;
+            for (int w = tid; w < vecs; w += 256) st_stream_u4(o + w, reinterpret_cast<const uint4*>(outb)[w]);
+        }
+        // (the next tile's expansion writes samp and resets the queue counter; outb is rewritten only after its next barrier)
     }
 }
 
@@ -326,13 +438,42 @@ int osb_resample_linear_dev(const void* d_in, int in_fmt, void* d_out, int out_f
         if ((rc = linear_table(n_in, n_out, &a.tab))) return rc;
         int l = 0;
         while ((1ll << l) < n_out - 1) ++l;
-        a.shift = 32 + l;
-        a.magic = (unsigned long long)((((unsigned __int128)1 << a.shift) + (unsigned)(n_out - 2)) / (unsigned)(n_out - 1));
+        if (l >= 1) {  // n_out == 2 has no interior output: the division is never reached
+            a.shift = l - 1;
+            a.magic = (unsigned)((1ull << (31 + l)) / (unsigned long long)(n_out - 1) + 1ull);
+        }
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    // many short dense rows: the tiled kernel (a single tick of the realtime path keeps the per-output kernel: more CTAs, lower latency)
+    if (a.exact_int && out_fmt == OSB_FMT_PCM16 && in_stride == n_in && out_stride == n_out && n_out % 8 == 0 && n_out <= 4096 && n_in <= 4096 &&
+        (n_in * (in_fmt == OSB_FMT_PCM16 ? 2 : 1)) % 4 == 0 && ((uintptr_t)d_in & 3) == 0 && ((uintptr_t)d_out & 15) == 0 &&
+        batch >= 16384 && !getenv("OSB_LINEAR_NO_TILES")) {
+        const size_t smem = (size_t)n_out * 4 + (size_t)kLinTileRows * n_out * 2 + (size_t)((kLinTileRows * n_in + 2) & ~1ll) * 2 + kLinSlowCap * 4;
+        if (smem <= 200 * 1024) {
+            const long long n_tiles = (batch + kLinTileRows - 1) / kLinTileRows;
+            const int per_sm = (int)std::min<size_t>(8, (220 * 1024) / (smem + 1024));
+            const long long want = (long long)num_sms() * (per_sm < 1 ? 1 : per_sm);
+            const unsigned grid_t = (unsigned)(n_tiles < want ? n_tiles : want);
+            static PerDeviceOnce once;
+            OSB_CUDA(once.run([&] {
+                cudaError_t e = cudaFuncSetAttribute(k_resample_linear_tiled<OSB_FMT_PCM16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+                if (e == cudaSuccess) e = cudaFuncSetAttribute(k_resample_linear_tiled<OSB_FMT_ULAW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+                if (e == cudaSuccess) e = cudaFuncSetAttribute(k_resample_linear_tiled<OSB_FMT_ALAW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+                return e;
+            }));
+            switch (in_fmt) {
+                case OSB_FMT_PCM16: OSB_LAUNCH(k_resample_linear_tiled<OSB_FMT_PCM16>, grid_t, 256, smem, st, a, n_tiles); break;
+                case OSB_FMT_ULAW: OSB_LAUNCH(k_resample_linear_tiled<OSB_FMT_ULAW>, grid_t, 256, smem, st, a, n_tiles); break;
+                case OSB_FMT_ALAW: OSB_LAUNCH(k_resample_linear_tiled<OSB_FMT_ALAW>, grid_t, 256, smem, st, a, n_tiles); break;
+                default: set_error("invalid argument: in_fmt %d", in_fmt); return OSB_ERR_INVALID_ARG;
+            }
+            OSB_CHECK_LAUNCH();
+            return OSB_OK;
+        }
     }
     int vec_ok = (out_fmt == OSB_FMT_PCM16) && (((uintptr_t)d_out & 15) == 0) && (out_stride % 8 == 0);
     long long groups = (n_out + 7) / 8 * batch;
     int grid = grid_for((size_t)groups, 256);
-    cudaStream_t st = (cudaStream_t)stream;
     switch (in_fmt) {
         case OSB_FMT_PCM16: return launch_linear_out<OSB_FMT_PCM16>(a, out_fmt, vec_ok, grid, st);
         case OSB_FMT_ULAW: return launch_linear_out<OSB_FMT_ULAW>(a, out_fmt, vec_ok, grid, st);

@@ -72,6 +72,37 @@ def test_linear_resample_integer_fast_path_adversarial(gpu, n, m):
         assert np.array_equal(out[b], want), (b, np.nonzero(out[b] != want)[0][:5])
 
 
+@pytest.mark.parametrize("fmt,n,m", [("ulaw", 160, 320), ("alaw", 160, 320), ("pcm16", 160, 320), ("pcm16", 480, 320), ("ulaw", 400, 800), ("pcm16", 882, 320)])
+def test_linear_resample_tiled_kernel(gpu, fmt, n, m, monkeypatch):
+    """The tiled kernel (many short dense rows: the realtime door replayed over whole recordings) against the per-output kernel on the same
+    input, bit for bit, and against np.interp on a sample of rows.  The batch is not a multiple of the tile (32 rows), the rows carry the
+    adversarial patterns of the test above, and one row per tile region is all hand-over cases (exactly integral interpolants)."""
+    rng = np.random.default_rng(n + m)
+    batch = 16384 + 37
+    code = {"ulaw": gpu.FMT_ULAW, "alaw": gpu.FMT_ALAW, "pcm16": gpu.FMT_PCM16}[fmt]
+    if fmt == "pcm16":
+        x = rng.integers(-32768, 32768, (batch, n)).astype(np.int64)
+        x[0::5] = (x[0::5] // (m - 1)) * (m - 1)
+        x[1::7] = x[1::7, :1]
+        x[2::11] = np.where(rng.integers(0, 2, (len(x[2::11]), n)) > 0, 32767, -32768)
+        x = np.clip(x, -32768, 32767).astype(np.int16)
+    else:
+        x = rng.integers(0, 256, (batch, n)).astype(np.uint8)
+        x[1::7] = x[1::7, :1]
+    tiled = np.empty((batch, m), np.int16)
+    gpu.call("osb_resample_linear_host", gpu.ptr(x), code, gpu.ptr(tiled), gpu.FMT_PCM16, n, m, batch, n, m)
+    monkeypatch.setenv("OSB_LINEAR_NO_TILES", "1")
+    plain = np.empty((batch, m), np.int16)
+    gpu.call("osb_resample_linear_host", gpu.ptr(x), code, gpu.ptr(plain), gpu.FMT_PCM16, n, m, batch, n, m)
+    monkeypatch.delenv("OSB_LINEAR_NO_TILES")
+    assert np.array_equal(tiled, plain), np.argwhere(tiled != plain)[:5]
+    xo, xn = np.linspace(0, 1, n), np.linspace(0, 1, m)
+    for b in (0, 1, 2, 5, 31, 32, 16383, 16384, batch - 1):
+        lin = x[b] if fmt == "pcm16" else np.frombuffer((codec.ulaw2lin if fmt == "ulaw" else codec.alaw2lin)(x[b].tobytes()), np.int16)
+        want = np.interp(xn, xo, lin.astype(np.float32)).astype(np.int16)
+        assert np.array_equal(tiled[b], want), b
+
+
 def test_linear_resample_edges(gpu, ab):
     assert ab._resample_linear(b"", 8000, 16000) == b""
     assert ab.decode_audio_to_pcm16(b"", "g711_ulaw", 16000) == b""
