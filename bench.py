@@ -313,6 +313,8 @@ class Ctx:
         self.world = int(os.environ.get("WORLD_SIZE", "1"))
         self.rank = int(os.environ.get("RANK", "0"))
         self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if self.world > 1:  # the copy threads of the pageable-buffer staging (csrc/host_stage.cu) share the box's cores with the other ranks
+            os.environ.setdefault("OSB_COPY_THREADS", str(max(1, min(8, (os.cpu_count() or 8) // self.world))))
         N.require_gpu()  # no device: RuntimeError here, there is nothing to fall back to
         torch.cuda.set_device(self.local)
         self.numa = bind_to_gpu_numa_node(torch, self.local)

@@ -3,6 +3,7 @@
 #include <cstdlib>
 
 #include "common.cuh"
+#include "host_stage.cuh"
 
 using namespace osb;
 
@@ -171,13 +172,13 @@ static int stt_full(void* vad, const void* d_in, int in_fmt, int from_rate, long
 struct GroupPipe {
     HostWs& ws;
     cudaStream_t s_in = nullptr, s_out = nullptr;
-    cudaEvent_t ev_in[32], ev_done[32];
+    cudaEvent_t ev_in[32], ev_done[32], ev_out[32];
     int groups = 0;
     int64_t bounds[33] = {0};
     explicit GroupPipe(HostWs& w) : ws(w) {}
     int open(int64_t batch, int max_groups = 24) {
         static thread_local cudaStream_t t_in = nullptr, t_out = nullptr;
-        static thread_local cudaEvent_t t_ev[64];
+        static thread_local cudaEvent_t t_ev[96];
         static thread_local int t_dev = -1;
         if (t_dev != ws.device) {  // per-thread copy streams and events, created once per device instead of per call
             if (t_in) {
@@ -191,7 +192,7 @@ struct GroupPipe {
             t_dev = ws.device;
         }
         s_in = t_in; s_out = t_out;
-        for (int g = 0; g < 32; ++g) { ev_in[g] = t_ev[g]; ev_done[g] = t_ev[32 + g]; }
+        for (int g = 0; g < 32; ++g) { ev_in[g] = t_ev[g]; ev_done[g] = t_ev[32 + g]; ev_out[g] = t_ev[64 + g]; }
         // clip groups (OSB_STT_HOST_GROUPS=1..32 to tune): the middle of the pipeline is PCIe-bound (the float32 features leaving), so
         // more groups = shorter fill (first H2D + first kernels) and drain; measured on 256 x 60 s: 8 groups 17.0 ms, 16: 16.2, 24: 16.0
         groups = batch >= 192 ? 24 : (batch >= 64 ? 8 : (batch >= 16 ? 4 : 1));
@@ -267,12 +268,23 @@ int osb_stt_full_host(void* vad, const void* in, int in_fmt, int from_rate, int6
     // Eight groups: the kernels of a group keep the SMs full (24 groups of ~10 clips cost 3 ms more compute), the fill stays ~1.5 ms
     GroupPipe gp(ws);
     if ((rc = gp.open(batch, 8))) return rc;
+    // pageable caller buffers (numpy arrays, bytes) go through our own pinned rings and copy threads (host_stage.cu)
+    StageIn sin;
+    StageOut sout;
+    {
+        int64_t mg = 0;
+        for (int g = 0; g < gp.groups; ++g) mg = std::max<int64_t>(mg, gp.bounds[g + 1] - gp.bounds[g]);
+        if ((rc = sin.open(host_is_pageable(in), (size_t)mg * n_in * es, ws.device)) ||
+            (rc = sout.open(host_is_pageable(mel), (size_t)mg * per_mel * 4, ws.device, gp.ev_out))) return rc;
+    }
     rc = OSB_OK;
     for (int g = 0; g < gp.groups && rc == OSB_OK; ++g) {
         const int64_t c0 = gp.bounds[g], nb = gp.bounds[g + 1] - c0;
         uint8_t* din = (uint8_t*)di + (size_t)c0 * n_in * es;
         float* dm = (float*)dmel + c0 * per_mel;
-        cudaError_t e = cudaMemcpyAsync(din, (const uint8_t*)in + (size_t)c0 * n_in * es, (size_t)nb * n_in * es, cudaMemcpyHostToDevice, gp.s_in);
+        const void* hsrc;
+        if ((rc = sin.src(g, (const uint8_t*)in + (size_t)c0 * n_in * es, (size_t)nb * n_in * es, gp.ev_in, &hsrc))) break;
+        cudaError_t e = cudaMemcpyAsync(din, hsrc, (size_t)nb * n_in * es, cudaMemcpyHostToDevice, gp.s_in);
         if (e == cudaSuccess) e = cudaEventRecord(gp.ev_in[g], gp.s_in);
         if (e == cudaSuccess) e = cudaStreamWaitEvent(ws.stream, gp.ev_in[g], 0);
         if (e != cudaSuccess) { rc = cuda_fail(e, "h2d group", __FILE__, __LINE__); break; }
@@ -281,8 +293,11 @@ int osb_stt_full_host(void* vad, const void* in, int in_fmt, int from_rate, int6
         if (rc) break;
         e = cudaEventRecord(gp.ev_done[g], ws.stream);
         if (e == cudaSuccess) e = cudaStreamWaitEvent(gp.s_out, gp.ev_done[g], 0);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(mel + c0 * per_mel, dm, (size_t)nb * per_mel * 4, cudaMemcpyDeviceToHost, gp.s_out);
+        void* hdst = nullptr;
+        if (e == cudaSuccess && (rc = sout.dst(g, mel + c0 * per_mel, &hdst))) break;
+        if (e == cudaSuccess) e = cudaMemcpyAsync(hdst, dm, (size_t)nb * per_mel * 4, cudaMemcpyDeviceToHost, gp.s_out);
         if (e != cudaSuccess) { rc = cuda_fail(e, "d2h group", __FILE__, __LINE__); break; }
+        if ((rc = sout.done(g, mel + c0 * per_mel, (size_t)nb * per_mel * 4, gp.s_out))) break;
     }
     if (rc == OSB_OK && vad) {
         rc = osb_stt_full_dev(vad, dpcm, OSB_FMT_PCM16, 16000, n16, batch, n16, 0, 0, 0, n_mels, vad_threshold, min_speech_ms, silence_ms, nullptr, d_probs,
@@ -294,6 +309,7 @@ int osb_stt_full_host(void* vad, const void* in, int in_fmt, int from_rate, int6
         if (rc == OSB_OK && e == cudaSuccess) e = cudaMemcpyAsync(counts, d_cnt, (size_t)batch * 4, cudaMemcpyDeviceToHost, ws.stream);
         if (rc == OSB_OK && e != cudaSuccess) rc = cuda_fail(e, "d2h vad", __FILE__, __LINE__);
     }
+    if (rc == OSB_OK) rc = sout.finish();
     return gp.close(rc);
 }
 
@@ -322,6 +338,15 @@ int osb_stt_frontend_host(const int16_t* pcm, int64_t n, int64_t batch, int64_t 
     if ((rc = ws.dev_buf(0, (size_t)batch * stride * 2, &di)) || (rc = ws.dev_buf(1, (size_t)batch * per_mel * 4, &dout))) return rc;
     GroupPipe gp(ws);
     if ((rc = gp.open(batch))) return rc;
+    // pageable caller buffers (numpy arrays, bytes) go through our own pinned rings and copy threads (host_stage.cu)
+    StageIn sin;
+    StageOut sout;
+    {
+        int64_t mg = 0;
+        for (int g = 0; g < gp.groups; ++g) mg = std::max<int64_t>(mg, gp.bounds[g + 1] - gp.bounds[g]);
+        if ((rc = sin.open(host_is_pageable(pcm), (size_t)mg * stride * 2, ws.device)) ||
+            (rc = sout.open(host_is_pageable(mel), (size_t)mg * per_mel * 4, ws.device, gp.ev_out))) return rc;
+    }
     rc = OSB_OK;
     for (int g = 0; g < gp.groups && rc == OSB_OK; ++g) {
         const int64_t c0 = gp.bounds[g], nb = gp.bounds[g + 1] - c0;
@@ -329,7 +354,9 @@ int osb_stt_frontend_host(const int16_t* pcm, int64_t n, int64_t batch, int64_t 
         int16_t* din = (int16_t*)di + c0 * stride;
         float* dmel = (float*)dout + c0 * per_mel;
         const size_t ib = (size_t)((nb - 1) * stride + n) * 2;
-        cudaError_t e = cudaMemcpyAsync(din, hin, ib, cudaMemcpyHostToDevice, gp.s_in);
+        const void* hsrc;
+        if ((rc = sin.src(g, hin, ib, gp.ev_in, &hsrc))) break;
+        cudaError_t e = cudaMemcpyAsync(din, hsrc, ib, cudaMemcpyHostToDevice, gp.s_in);
         if (e == cudaSuccess) e = cudaEventRecord(gp.ev_in[g], gp.s_in);
         if (e == cudaSuccess) e = cudaStreamWaitEvent(ws.stream, gp.ev_in[g], 0);
         if (e != cudaSuccess) { rc = cuda_fail(e, "h2d group", __FILE__, __LINE__); break; }
@@ -337,9 +364,13 @@ int osb_stt_frontend_host(const int16_t* pcm, int64_t n, int64_t batch, int64_t 
         if (rc) break;
         e = cudaEventRecord(gp.ev_done[g], ws.stream);
         if (e == cudaSuccess) e = cudaStreamWaitEvent(gp.s_out, gp.ev_done[g], 0);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(mel + c0 * per_mel, dmel, (size_t)nb * per_mel * 4, cudaMemcpyDeviceToHost, gp.s_out);
+        void* hdst = nullptr;
+        if (e == cudaSuccess && (rc = sout.dst(g, mel + c0 * per_mel, &hdst))) break;
+        if (e == cudaSuccess) e = cudaMemcpyAsync(hdst, dmel, (size_t)nb * per_mel * 4, cudaMemcpyDeviceToHost, gp.s_out);
         if (e != cudaSuccess) { rc = cuda_fail(e, "d2h group", __FILE__, __LINE__); break; }
+        if ((rc = sout.done(g, mel + c0 * per_mel, (size_t)nb * per_mel * 4, gp.s_out))) break;
     }
+    if (rc == OSB_OK) rc = sout.finish();
     return gp.close(rc);
 }
 

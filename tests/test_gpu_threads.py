@@ -80,3 +80,51 @@ def test_concurrent_host_calls_are_independent(gpu):
     for t in threads:
         t.join()
     assert not errors, errors
+
+
+@pytest.mark.gpu
+def test_pageable_host_buffers_go_through_the_staging_rings(gpu):
+    """numpy (pageable) buffers on the batch host entries are staged through pinned rings by copy threads (csrc/host_stage.cu): enough
+    groups for both rings to wrap (four groups, two input slots, three output slots), groups big enough for the thread pool (> 4 MiB),
+    and the result must be the one pinned buffers give, bit for bit -- for both batch entries."""
+    import torch
+    from open_speech_b200 import synth
+    from open_speech_b200.batch import SttFull
+    from open_speech_b200.vad.silero import VadSession
+
+    batch, seconds = 20, 60.0
+    pcm = synth.clip_batch_pcm16(batch, seconds, seed=77, distinct=4)
+    n = pcm.shape[1]
+    nf = gpu.lib().osb_logmel_frames(n)
+    page_out = np.full((batch, 128, nf), np.nan, np.float32)
+    gpu.call("osb_stt_frontend_host", gpu.ptr(pcm), n, batch, n, 16000, 0, 1, 128, gpu.ptr(page_out))
+    pin_in = torch.from_numpy(pcm).pin_memory()
+    pin_out = torch.empty((batch, 128, nf), dtype=torch.float32).pin_memory()
+    gpu.call("osb_stt_frontend_host", pin_in.data_ptr(), n, batch, n, 16000, 0, 1, 128, pin_out.data_ptr())
+    assert np.array_equal(page_out, pin_out.numpy())
+    # mixed: pinned in, pageable out and the other way round
+    mixed = np.full((batch, 128, nf), np.nan, np.float32)
+    gpu.call("osb_stt_frontend_host", pin_in.data_ptr(), n, batch, n, 16000, 0, 1, 128, gpu.ptr(mixed))
+    assert np.array_equal(mixed, page_out)
+    pin_out.zero_()
+    gpu.call("osb_stt_frontend_host", gpu.ptr(pcm), n, batch, n, 16000, 0, 1, 128, pin_out.data_ptr())
+    assert np.array_equal(pin_out.numpy(), page_out)
+
+    # composed chain: mu-law wire bytes in pageable memory, every result in pageable memory
+    from oracle import codec
+    wire = np.stack([np.frombuffer(codec.lin2ulaw(synth.clip_pcm16(30.0, sr=8000, seed=80 + i).tobytes()), np.uint8) for i in range(4)])
+    wire = np.tile(wire, (5, 1)).copy()
+    full = SttFull(VadSession(), fmt="g711_ulaw", from_rate=8000, linear_chunk=160)
+    n16 = 2 * wire.shape[1]
+    nf2 = gpu.lib().osb_logmel_frames(n16)
+
+    def outs(pinned):
+        mk = (lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory()) if pinned else (lambda shape, dt: np.empty(shape, {torch.float32: np.float32, torch.int32: np.int32}[dt]))
+        return {"probs": mk((20, n16 // 512), torch.float32), "segments": mk((20, n16 // 512 // 2 + 2, 2), torch.int32),
+                "counts": mk((20,), torch.int32), "mel": mk((20, 128, nf2), torch.float32)}
+
+    a, b = outs(False), outs(True)
+    full.run_host(wire, a)
+    full.run_host(torch.from_numpy(wire).pin_memory(), b)
+    for k in ("probs", "counts", "mel"):
+        assert np.array_equal(np.asarray(a[k]), b[k].numpy()), k
