@@ -134,6 +134,11 @@ struct MelArgs {
 __device__ __forceinline__ float mel_requant(const MelArgs& a, float x, float gain, bool /*silent: folded into gain by the caller*/) {
     return a.requant ? (float)__float2int_rz(__fmul_rn(fminf(fmaxf(__fmul_rn(x, gain), -1.0f), 1.0f), 32767.0f)) * 3.0517578125e-05f : x;
 }
+// (log_spec + 4.0) / 4.0, applied by the transform kernels themselves (x / 4.0 written as x * 0.25: the same value for every float).  The
+// clamp log_spec = maximum(log_spec, max - 8.0) comes BEFORE it in the reference; the two commute exactly because rounding is monotonic:
+// (max(x, t) + 4) / 4 == max((x + 4) / 4, (t + 4) / 4) for all floats, so the clamp pass only rewrites the cells it changes.
+__device__ __forceinline__ float logmel_affine(float x) { return __fmul_rn(__fadd_rn(x, 4.0f), 0.25f); }
+
 __device__ __forceinline__ float mel_sample(const MelArgs& a, int s16, float gain, bool silent) {
     return mel_requant(a, (float)s16 * 3.0517578125e-05f, gain, silent);  // /32768, exact
 }
@@ -311,11 +316,11 @@ __global__ void __launch_bounds__(256, 2) k_logmel(MelArgs a, int tiles_per_clip
             const float v0 = __log2f(fmaxf(acc.x, 1e-10f)) * 0.30102999566398120f;
             const float v1 = __log2f(fmaxf(acc.y, 1e-10f)) * 0.30102999566398120f;
             if (live0) {
-                outb[(long long)m * a.n_frames] = v0;
+                outb[(long long)m * a.n_frames] = logmel_affine(v0);
                 vmax = fmaxf(vmax, v0);
             }
             if (live1) {
-                outb[(long long)m * a.n_frames + 16] = v1;
+                outb[(long long)m * a.n_frames + 16] = logmel_affine(v1);
                 vmax = fmaxf(vmax, v1);
             }
         }
@@ -528,11 +533,11 @@ __global__ void __launch_bounds__(256, 3) k_logmel16(MelArgs a, int tiles_per_cl
             const float v0 = lg2_bare(fmaxf(acc.x, 1e-10f)) * 0.30102999566398120f;
             const float v1 = lg2_bare(fmaxf(acc.y, 1e-10f)) * 0.30102999566398120f;
             if (live0) {
-                outp[0] = v0;
+                outp[0] = logmel_affine(v0);
                 vmax = fmaxf(vmax, v0);
             }
             if (live1) {
-                outp[16] = v1;
+                outp[16] = logmel_affine(v1);
                 vmax = fmaxf(vmax, v1);
             }
         }
@@ -553,12 +558,17 @@ __global__ void k_mel_gain(const unsigned long long* __restrict__ sumsq, const d
     gain[b] = silent ? -1.0f : g;  // a real gain is 10^x > 0
 }
 
-// log_spec = maximum(log_spec, log_spec.max() - 8.0); (log_spec + 4.0) / 4.0
-// (x / 4.0 is written as x * 0.25: the same value for every float, without the division's slow path)
-__device__ __forceinline__ float logmel_fin(float x, float thr) { return __fmul_rn(__fadd_rn(fmaxf(x, thr), 4.0f), 0.25f); }
+// log_spec = maximum(log_spec, log_spec.max() - 8.0) on the already affine-mapped features: reads every cell, writes the 16-byte groups the
+// clamp changes (normalise-only clips: a few per cent; denoised clips: most -- gated cells are far below the threshold)
+__device__ __forceinline__ bool logmel_clamp4(float4& x, float ty) {
+    const float4 m = make_float4(fmaxf(x.x, ty), fmaxf(x.y, ty), fmaxf(x.z, ty), fmaxf(x.w, ty));
+    const bool changed = m.x != x.x || m.y != x.y || m.z != x.z || m.w != x.w;
+    x = m;
+    return changed;
+}
 
 __global__ void __launch_bounds__(256) k_logmel_finalize(float* __restrict__ out, long long per_clip, const unsigned int* __restrict__ gmax) {
-    const float thr = (__uint_as_float(gmax[blockIdx.y]) - 10.0f) - 8.0f;
+    const float ty = logmel_affine((__uint_as_float(gmax[blockIdx.y]) - 10.0f) - 8.0f);
     float* o = out + (long long)blockIdx.y * per_clip;
     const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nthr = (long long)gridDim.x * blockDim.x;
     const bool aligned = (((uintptr_t)o) & 15) == 0;
@@ -570,18 +580,14 @@ __global__ void __launch_bounds__(256) k_logmel_finalize(float* __restrict__ out
 #pragma unroll
         for (int j = 0; j < 4; ++j) x[j] = o4[v + j * nthr];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            x[j].x = logmel_fin(x[j].x, thr); x[j].y = logmel_fin(x[j].y, thr);
-            x[j].z = logmel_fin(x[j].z, thr); x[j].w = logmel_fin(x[j].w, thr);
-            o4[v + j * nthr] = x[j];
-        }
+        for (int j = 0; j < 4; ++j)
+            if (logmel_clamp4(x[j], ty)) o4[v + j * nthr] = x[j];
     }
     for (; v < nvec; v += nthr) {
         float4 x = o4[v];
-        x.x = logmel_fin(x.x, thr); x.y = logmel_fin(x.y, thr); x.z = logmel_fin(x.z, thr); x.w = logmel_fin(x.w, thr);
-        o4[v] = x;
+        if (logmel_clamp4(x, ty)) o4[v] = x;
     }
-    for (long long i = nvec * 4 + tid; i < per_clip; i += nthr) o[i] = logmel_fin(o[i], thr);
+    for (long long i = nvec * 4 + tid; i < per_clip; i += nthr) o[i] = fmaxf(o[i], ty);
 }
 
 constexpr int kLogmelSmemF32 = (kXsP + 1200 + 16 * 2 * kF400Plane) * (int)sizeof(float) + kRawBytes;  // (a complex plane = 2 x 425 floats)
