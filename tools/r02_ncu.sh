@@ -5,7 +5,9 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
 python tools/prof_target.py full 2 > gpurun_out/r02_plain_full.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/r02_launches_stt_full.csv python tools/prof_target.py full 2 > gpurun_out/r02_ncu_b.log 2>&1
 python tools/prof_target.py stt 1 > gpurun_out/r02_plain_stt.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:'k_nr_|k_logmel' -c 6 -o gpurun_out/r02_prof_stt -f python tools/prof_target.py stt 1 > gpurun_out/r02_ncu_c.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:'k_nr_|k_logmel|k_mel_gain' -c 7 -o gpurun_out/r02_prof_stt -f python tools/prof_target.py stt 1 > gpurun_out/r02_ncu_c.log 2>&1
+python tools/prof_target.py full 1 > gpurun_out/r02_plain_full1.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:'k_resample_linear_tiled' -c 1 -o gpurun_out/r02_prof_resample -f python tools/prof_target.py full 1 > gpurun_out/r02_ncu_f.log 2>&1
 python tools/prof_target.py vad 1 > gpurun_out/r02_plain_vad.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:'k_vad_front_fused|k_vad_recur' -c 2 -o gpurun_out/r02_prof_vad -f python tools/prof_target.py vad 1 > gpurun_out/r02_ncu_d.log 2>&1
 python tools/prof_target.py tts 1 > gpurun_out/r02_plain_tts.log 2>&1 &&
