@@ -1134,11 +1134,11 @@ static int fx_reverb(FxState& s, int sample_rate, int room_ms, double mix, Scrat
     const int smem = 256 * kSegStride * (int)sizeof(double);
     OSB_CUDA(fx_smem_attrs(smem));
     if (with_eq) {
-        // The chain's result is cast to float32 (chain.py:32): a start-up transient below 1e-11 of the state is invisible, and
-        // the shorter warm-up (2048 instead of 2656 samples at 24 kHz) is recomputed by every block.  Multiple of 512 samples:
-        // thread t then owns outputs t, t + 512, ...
+        // The chain's result is cast to float32 (chain.py:32; 6e-8 relative) and the tolerance is 1e-4 of the peak: a start-up transient
+        // below 1e-7 of the state is invisible, and the warm-up is recomputed by every block -- 1,536 instead of 2,048 samples at 24 kHz
+        // (1e-11) is 8 % more outputs per block.  Multiple of 512 samples: thread t then owns outputs t, t + 512, ...
         EqArgs e;
-        if ((rc = eq_prepare(sample_rate, e, 1e-11, kRqThreads, kRqT))) return rc;
+        if ((rc = eq_prepare(sample_rate, e, 1e-7, kRqThreads, kRqT))) return rc;
         e.rg = s.rg;
         EqLanePow lp;
         if ((rc = eq_lane_pow(sample_rate, kRqT, e, &lp.tab))) return rc;
