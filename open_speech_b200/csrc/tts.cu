@@ -597,12 +597,16 @@ struct RqShared {
     double red[16];
     double rsum[16];
     St4 wsum[16];
+    double carry[2][5];  // chained blocks: reverb state and biquad state at the end of the previous block (double-buffered by block parity)
 };
+// A CTA walks kRqRun consecutive blocks of one utterance.  Only the first starts from rest behind a warm-up; the others take the exact
+// states their predecessor ended in (no warm-up: 8,192 outputs instead of 8,192 - warm, and no FIR carry-in sum for the reverb).
+constexpr int kRqRun = 4;
 
 template <typename T, bool INTERIOR, int FINISH>
 __device__ __forceinline__ void rveq_block(const T* __restrict__ p, const ReverbArgs& ra, const EqArgs& a, const EqLanePow& lp, const FxPre& pre,
                                            const FxPost& post, double* __restrict__ y, double* smd, RqShared& sh, int b, long long n,
-                                           long long n0) {
+                                           long long n0, bool chained, int parity) {
     T* xs = reinterpret_cast<T*>(smd);          // [512][17] pre-processed input
     float* os = reinterpret_cast<float*>(smd);  // later: finished samples (FINISH != 0)
     double* tabs = reinterpret_cast<double*>(xs + kRqThreads * kRqStride);  // [32][17] Phi^lane
@@ -612,8 +616,9 @@ __device__ __forceinline__ void rveq_block(const T* __restrict__ p, const Reverb
     double* rsum = sh.rsum;
     St4* wsum = sh.wsum;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int kEqWarm = a.warm;
+    const int kEqWarm = chained ? 0 : a.warm;
     const long long base = n0 - kEqWarm;
+    const double* carry_in = sh.carry[parity ^ 1];  // written by the previous block of this CTA (behind a block barrier)
     const PreOps po = fx_pre_ops(pre, b, n);
     const int cidx = (tid >> 4) * kRqStride + (tid & 15);
     tabs[(tid >> 4) * kRqStride + (tid & 15)] = lp.tab[tid];
@@ -636,7 +641,7 @@ __device__ __forceinline__ void rveq_block(const T* __restrict__ p, const Reverb
     }
     // carry-in wet[base-1] = sum_k ir[k] x[base-1-k]: eight taps' loads in flight per thread
     double part = 0.0;
-    if (base > 0) {
+    if (base > 0 && !chained) {
 #pragma unroll 1
         for (int k0 = tid; k0 < ra.L; k0 += kRqThreads * 8) {
             T xv[8];
@@ -662,6 +667,7 @@ __device__ __forceinline__ void rveq_block(const T* __restrict__ p, const Reverb
 #pragma unroll
         for (int w = 0; w < 8; ++w) r8[w] = red[2 * w] + red[2 * w + 1];
         carry0 = ((r8[0] + r8[1]) + (r8[2] + r8[3])) + ((r8[4] + r8[5]) + (r8[6] + r8[7]));
+        if (chained) carry0 = carry_in[0];
     }
     // ---- segment mapping: thread = samples [16 tid, 16 tid + 16) of the block, in registers from here on
     const int i0 = kRqT * tid;
@@ -728,6 +734,7 @@ __device__ __forceinline__ void rveq_block(const T* __restrict__ p, const Reverb
                 if (g < 0 || g >= n) uu[i] = 0.0;
             }
         }
+        if (tid == kRqThreads - 1) sh.carry[parity][0] = s;  // reverb state behind the block's last sample
     }
     // ---- biquads from rest over the block: zero-state end state of the segment (impulse-to-state table), warp scan
     St4 e{{0, 0, 0, 0}};
@@ -748,7 +755,20 @@ __device__ __forceinline__ void rveq_block(const T* __restrict__ p, const Reverb
             for (int i = 0; i < 4; ++i) v.z[i] += t.z[i];
         }
     }
-    if (lane == 31) wsum[wid] = v;
+    St4 x0{{0, 0, 0, 0}};  // biquad state entering the block: rest (behind a warm-up), or what the previous block ended in
+    if (chained) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) x0.z[i] = carry_in[1 + i];
+    }
+    if (lane == 31) {
+        St4 tot = v;
+        if (chained && wid == 0) {  // the warp totals are scanned from rest: the entering state rides along as Phi^512 x0 on the first one
+            const St4 t = mat4(a.Qp[0], x0);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) tot.z[i] += t.z[i];
+        }
+        wsum[wid] = tot;
+    }
     __syncthreads();  // also: every thread has read its xs[] values
     if (i0 >= kEqWarm) {  // warm-up segments are done: their outputs are discarded (warp-uniform: the warm-up is a multiple of 512)
         // state entering this warp's first segment: every warp scans the 16 warp totals itself (lane w holds warp w; four
@@ -770,7 +790,7 @@ __device__ __forceinline__ void rveq_block(const T* __restrict__ p, const Reverb
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const double c = __shfl_sync(0xffffffffu, t.z[i], (wid + 15) & 15);  // inclusive total of warps 0..wid-1
-                cw.z[i] = wid == 0 ? 0.0 : c;
+                cw.z[i] = wid == 0 ? x0.z[i] : c;
             }
         }
         St4 s;            // state entering this segment = zero-carry prefix of the previous lanes + Phi^lane (warp carry)
@@ -808,6 +828,10 @@ __device__ __forceinline__ void rveq_block(const T* __restrict__ p, const Reverb
                 os[tid * kRqStride + i] = (float)o;
             }
         }
+        if (tid == kRqThreads - 1) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) sh.carry[parity][1 + i] = s.z[i];
+        }
     }
     if (FINISH == 0) return;
     __syncthreads();
@@ -830,12 +854,18 @@ __global__ void __launch_bounds__(kRqThreads, 2) k_fx_reverb_eq(const T* __restr
     __shared__ RqShared sh;
     const int b = blockIdx.y;
     const long long n = a.rg.lens[b];
-    const long long n0 = (long long)blockIdx.x * (kEqBlock - a.warm);
-    if (n0 >= n) return;
-    const long long base = n0 - a.warm;
+    const int kEqOut = kEqBlock - a.warm;
+    long long n0 = (long long)blockIdx.x * (kEqOut + (long long)(kRqRun - 1) * kEqBlock);
     const T* p = x + a.rg.offsets[b];
-    if (base - ra.L >= 0 && base + kEqBlock <= n) rveq_block<T, true, FINISH>(p, ra, a, lp, pre, post, y, smd, sh, b, n, n0);
-    else rveq_block<T, false, FINISH>(p, ra, a, lp, pre, post, y, smd, sh, b, n, n0);
+    for (int r = 0; r < kRqRun; ++r) {
+        if (n0 >= n) return;
+        if (r) __syncthreads();  // the previous block's staging buffer and carried states
+        const bool chained = r > 0;
+        const long long base = chained ? n0 : n0 - a.warm;
+        if (base - ra.L >= 0 && base + kEqBlock <= n) rveq_block<T, true, FINISH>(p, ra, a, lp, pre, post, y, smd, sh, b, n, n0, chained, r & 1);
+        else rveq_block<T, false, FINISH>(p, ra, a, lp, pre, post, y, smd, sh, b, n, n0, chained, r & 1);
+        n0 += chained ? kEqBlock : kEqOut;
+    }
 }
 
 template <typename T>
@@ -1143,8 +1173,8 @@ static int fx_reverb(FxState& s, int sample_rate, int room_ms, double mix, Scrat
         EqLanePow lp;
         if ((rc = eq_lane_pow(sample_rate, kRqT, e, &lp.tab))) return rc;
         a.rT = std::pow(a.r, (double)kRqT);
-        const int kEqOut = kEqBlock - e.warm;
-        const dim3 ge((unsigned)((s.max_len + kEqOut - 1) / kEqOut), (unsigned)s.batch);
+        const long long run_out = (kEqBlock - e.warm) + (long long)(kRqRun - 1) * kEqBlock;  // outputs of one CTA: kRqRun chained blocks
+        const dim3 ge((unsigned)((s.max_len + run_out - 1) / run_out), (unsigned)s.batch);
         if (!s.f64) rc = launch_reverb_eq<float>(ge, s.st, (const float*)s.cur, a, e, lp, s.pre, s.post, dst);
         else rc = launch_reverb_eq<double>(ge, s.st, (const double*)s.cur, a, e, lp, s.pre, s.post, dst);
         if (rc) return rc;
