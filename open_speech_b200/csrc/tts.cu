@@ -601,7 +601,7 @@ struct RqShared {
 };
 // A CTA walks kRqRun consecutive blocks of one utterance.  Only the first starts from rest behind a warm-up; the others take the exact
 // states their predecessor ended in (no warm-up: 8,192 outputs instead of 8,192 - warm, and no FIR carry-in sum for the reverb).
-constexpr int kRqRun = 4;
+constexpr int kRqRun = 8;
 
 template <typename T, bool INTERIOR, int FINISH>
 __device__ __forceinline__ void rveq_block(const T* __restrict__ p, const ReverbArgs& ra, const EqArgs& a, const EqLanePow& lp, const FxPre& pre,
