@@ -34,6 +34,7 @@ struct TtsStats {
     int first, last;      // first / last index with |x| > threshold (first = INT_MAX when none)
     unsigned int maxbits; // bits of max |x| (non-negative float -> ordered as uint)
     int pad;
+    double sumsq;         // k_tts_stats<true>: sum of the float32 squares of ALL samples of the utterance, summed wide
 };
 
 // Utterances start anywhere in the flat buffer: a scalar head up to the first 16-byte boundary, a float4 body, a scalar tail.
@@ -46,15 +47,20 @@ __device__ __forceinline__ Span4 span4(const float* p, long long n) {
     return Span4{head, (n - head) >> 2};
 }
 
+// SUMSQ: also the utterance's sum of squares, so that an RMS normalise at the head of the effects chain needs no pass of its own
+// (k_fx_sumsq_from_stats takes the trimmed edges off and applies the peak gain)
+template <bool SUMSQ>
 __global__ void __launch_bounds__(256) k_tts_stats(const float* __restrict__ x, Ragged rg, float thr, TtsStats* __restrict__ st) {
     const int b = blockIdx.y;
     const long long n = rg.lens[b];
     const float* p = x + rg.offsets[b];
     int first = 0x7fffffff, last = -1;
     float mx = 0.f;
+    double acc = 0.0;
     auto see = [&](float v, long long i) {
         const float a = fabsf(v);
         mx = fmaxf(mx, a);
+        if (SUMSQ) acc += (double)__fmul_rn(v, v);
         if (a > thr) {
             first = min(first, (int)i);
             last = max(last, (int)i);
@@ -91,11 +97,15 @@ __global__ void __launch_bounds__(256) k_tts_stats(const float* __restrict__ x, 
         }
         atomicMax(&st[b].maxbits, __float_as_uint(mx));
     }
+    if (SUMSQ) {
+        acc = warp_sum(acc);
+        if ((threadIdx.x & 31) == 0) atomicAdd(&st[b].sumsq, acc);
+    }
 }
 
 __global__ void k_tts_stats_init(TtsStats* st, int batch) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < batch) st[i] = TtsStats{0x7fffffff, -1, 0u, 0};
+    if (i < batch) st[i] = TtsStats{0x7fffffff, -1, 0u, 0, 0.0};
 }
 
 // sumsq (optional): per-utterance sum of squares of the samples written (float32 squares summed wide, as k_fx_sumsq
@@ -183,6 +193,32 @@ __global__ void __launch_bounds__(256) k_fx_sumsq_post(const float* __restrict__
     for (long long i = sp.head + 4 * sp.nvec + tid; i < n; i += nthr) add(p[i]);
     acc = warp_sum(acc);
     if ((threadIdx.x & 31) == 0) atomicAdd(&sumsq[b], acc);
+}
+
+// The same quantity from the statistics pass (k_tts_stats<true>): sum of squares of the whole utterance, minus the two trimmed edges (at
+// most a few hundred milliseconds each: this kernel reads only those), times the square of the peak gain.  Against squaring the gained
+// samples one by one this moves the sum by ~1e-7 relative (float32 roundings of x * gain), four decimal orders inside the tolerance, and
+// saves a full pass over the input.  One CTA per utterance.
+__global__ void __launch_bounds__(256) k_fx_sumsq_from_stats(const float* __restrict__ x, const long long* __restrict__ offsets,
+                                                             const long long* __restrict__ lens, const long long* __restrict__ offs2,
+                                                             const long long* __restrict__ lens2, const TtsStats* __restrict__ st,
+                                                             const float* __restrict__ pscale, double* __restrict__ sumsq) {
+    const int b = blockIdx.x;
+    const float* p = x + offsets[b];
+    const long long n = lens[b], head = offs2[b] - offsets[b], tail0 = head + lens2[b];
+    double acc = 0.0;
+    for (long long i = threadIdx.x; i < head; i += 256) acc += (double)__fmul_rn(p[i], p[i]);
+    for (long long i = tail0 + threadIdx.x; i < n; i += 256) acc += (double)__fmul_rn(p[i], p[i]);
+    __shared__ double part[8];
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double edges = 0.0;
+        for (int w = 0; w < 8; ++w) edges += part[w];
+        const double kept = fmax(st[b].sumsq - edges, 0.0), sc = (double)pscale[b];
+        sumsq[b] = kept * sc * sc;
+    }
 }
 
 // ---------------------------------------------------------------- effects: normalise (RMS), robot, cast
@@ -1084,7 +1120,9 @@ struct TtsPlan {
     const long long* lens2;        // its length
     const float* pscale;           // peak gain
     const int* pon;                // ... applied (with clip) where non-zero
-    const long long* out_offsets;  // where the result of utterance b goes
+    const long long* out_offsets;  // where the result of utterance b goes (= the utterance's offset in the untouched input)
+    const long long* lens;         // untrimmed lengths
+    const TtsStats* stats;         // with the utterances' sums of squares (k_tts_stats<true>)
 };
 
 // OSB_FX_UNFUSED=1 keeps reverb and podcast_eq in separate kernels (tests compare the two paths)
@@ -1120,7 +1158,9 @@ static int fx_normalize(FxState& s, double target_lufs, Scratch& scr, bool defer
     const double target_rms = std::pow(10.0, target_lufs / 20.0);
     if (!s.f64) {
         if (!have_sumsq) {
-            if (plan) OSB_LAUNCH(k_fx_sumsq_post, g, 256, 0, s.st, (const float*)s.cur, s.rg, plan->pscale, plan->pon, sumsq);
+            if (plan && plan->stats) OSB_LAUNCH(k_fx_sumsq_from_stats, (unsigned)s.batch, 256, 0, s.st, (const float*)s.cur, plan->out_offsets, plan->lens, plan->offs2,
+                                                plan->lens2, plan->stats, plan->pscale, sumsq);
+            else if (plan) OSB_LAUNCH(k_fx_sumsq_post, g, 256, 0, s.st, (const float*)s.cur, s.rg, plan->pscale, plan->pon, sumsq);
             else OSB_LAUNCH(k_fx_sumsq<float>, g, 256, 0, s.st, (const float*)s.cur, s.rg, sumsq);
             OSB_CHECK_LAUNCH();
         }
@@ -1294,7 +1334,7 @@ static int tts_post_impl(const float* d_in, const int64_t* d_offsets, const int6
     OSB_LAUNCH(k_tts_stats_init, (unsigned)((batch + 255) / 256), 256, 0, st, stats, (int)batch);
     OSB_CHECK_LAUNCH();
     const dim3 g = ragged_grid(max_len > 0 ? max_len : 1, batch);
-    OSB_LAUNCH(k_tts_stats, g, 256, 0, st, d_in, rg, threshold, stats);
+    OSB_LAUNCH(k_tts_stats<false>, g, 256, 0, st, d_in, rg, threshold, stats);
     OSB_CHECK_LAUNCH();
     OSB_LAUNCH(k_tts_apply, g, 256, 0, st, d_in, rg, stats, trim, normalize, peak, d_out, (long long*)d_out_lens, d_sumsq);
     OSB_CHECK_LAUNCH();
@@ -1410,12 +1450,12 @@ int osb_tts_post_fx_dev(const float* d_in, const int64_t* d_offsets, const int64
         Ragged rg{(const long long*)d_offsets, (const long long*)d_lens};
         OSB_LAUNCH(k_tts_stats_init, (unsigned)((batch + 255) / 256), 256, 0, st, stats, (int)batch);
         OSB_CHECK_LAUNCH();
-        OSB_LAUNCH(k_tts_stats, ragged_grid(max_len > 0 ? max_len : 1, batch), 256, 0, st, d_in, rg, threshold, stats);
+        OSB_LAUNCH(k_tts_stats<true>, ragged_grid(max_len > 0 ? max_len : 1, batch), 256, 0, st, d_in, rg, threshold, stats);
         OSB_CHECK_LAUNCH();
         OSB_LAUNCH(k_tts_plan, (unsigned)((batch + 255) / 256), 256, 0, st, rg, stats, (int)batch, trim, normalize, peak, offs2,
                    (long long*)d_out_lens, pscale, pon);
         OSB_CHECK_LAUNCH();
-        const TtsPlan plan{offs2, (const long long*)d_out_lens, pscale, pon, (const long long*)d_offsets};
+        const TtsPlan plan{offs2, (const long long*)d_out_lens, pscale, pon, (const long long*)d_offsets, (const long long*)d_lens, stats};
         return fx_chain_impl(d_in, d_offsets, d_out_lens, batch, max_len, total, sample_rate, fx_types, fx_p0, fx_p1, n_fx, d_out, out_pcm16,
                              nullptr, stream, &plan);
     }
