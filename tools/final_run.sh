@@ -14,3 +14,12 @@ print("$f", d.get("value"), d.get("ms_per_step"), (d.get("e2e") or {}).get("valu
 if "configs" in d: print({k: (round(v.get("value", 0)), v.get("ms_per_step")) for k, v in d["configs"].items()})
 PY
 done
+python bench.py --workload tts --steps 5 --warmup 3 2>/dev/null | tail -1 > gpurun_out/r02f_bench_tts.json
+python bench.py --workload vad --steps 3 --warmup 1 2>/dev/null | tail -1 > gpurun_out/r02f_bench_vad.json
+python bench.py --workload realtime 2>/dev/null | tail -1 > gpurun_out/r02f_bench_realtime.json
+for f in tts vad realtime; do python - <<PY
+import json
+d=json.load(open("gpurun_out/r02f_bench_$f.json"))
+print("$f", d.get("value"), d.get("ms_per_step"))
+PY
+done
