@@ -191,6 +191,59 @@ def test_gate_tick_cuda_graph_matches_stream_path(gpu, session):
     assert int(a.records()["total_samples"][0]) == 320 * 12
 
 
+def test_gate_host_io_matches_stream_path(gpu, session):
+    """A host_io gate (wire bytes read from, pcm16 + events written to pinned host memory by the kernels themselves: no copies) leaves
+    the same pcm16, records, arena and events as the device-buffer gate -- scripted probabilities, then the real network at 40 ms."""
+    import torch
+
+    from open_speech_b200 import synth
+    from open_speech_b200.realtime.gate import RealtimeGate
+
+    S, T = 96, 40
+    data = synth.ulaw_streams(S, T)
+    rng = np.random.default_rng(7)
+    probs = (rng.random((T, S)) < 0.3).astype(np.float32) * 0.9
+    a = RealtimeGate(S, 160, fmt="g711_ulaw", session=None, silence_duration_ms=60, arena_samples=320 * T)
+    b = RealtimeGate(S, 160, fmt="g711_ulaw", session=None, silence_duration_ms=60, arena_samples=320 * T, host_io=True)
+    assert b.pcm.is_pinned() and b.events.is_pinned() and not b.pcm.is_cuda
+    n_ev = 0
+    for t in range(T):
+        p = torch.from_numpy(probs[t]).cuda()
+        a.tick(torch.from_numpy(data[t]).cuda(), p)
+        ev_a = a.read_events()
+        l0 = gpu.lib().osb_launch_count()
+        ev_b = b.tick_host(torch.from_numpy(data[t]).pin_memory(), p)
+        assert gpu.lib().osb_launch_count() - l0 == 2
+        assert ev_a == ev_b
+        n_ev += len(ev_b)
+        assert torch.equal(a.pcm.cpu(), b.pcm)
+        assert np.array_equal(b.pcm[5].numpy(), np.frombuffer(codec.decode_audio_to_pcm16(data[t, 5].tobytes(), "g711_ulaw", 16000), np.int16))
+    assert n_ev > S
+    assert np.array_equal(a.records(), b.records()) and torch.equal(a.arena, b.arena)
+    with pytest.raises(RuntimeError):
+        a.tick_host(torch.from_numpy(data[0]).pin_memory())
+    with pytest.raises(RuntimeError):
+        b.capture()
+    with pytest.raises(ValueError):
+        a.tick(torch.from_numpy(data[0]).pin_memory())          # a device-buffer gate takes device tensors only
+    # the network in the loop: one VAD window per 40 ms chunk, scored from the pinned pcm16
+    S2, chunk, T2 = 4, 320, 60
+    x8 = [synth.clip_pcm16(chunk * T2 / 8000.0, sr=8000, seed=90 + s) for s in range(S2)]
+    ul = np.stack([np.frombuffer(codec.lin2ulaw(x.tobytes()), np.uint8) for x in x8])
+    c = RealtimeGate(S2, chunk, fmt="g711_ulaw", session=session, silence_duration_ms=200)
+    d = RealtimeGate(S2, chunk, fmt="g711_ulaw", session=session, silence_duration_ms=200, host_io=True)
+    seen = 0
+    for t in range(T2):
+        w = np.ascontiguousarray(ul[:, t * chunk:(t + 1) * chunk])
+        c.tick(torch.from_numpy(w).cuda())
+        ev_c = c.read_events()
+        ev_d = d.tick_host(torch.from_numpy(w).pin_memory())
+        assert ev_c == ev_d
+        seen += len(ev_d)
+        assert torch.equal(c.pcm.cpu(), d.pcm)
+    assert seen > 0 and np.array_equal(c.records(), d.records())
+
+
 def test_gate_buffer_errors(gpu):
     """The two BufferError cases of InputAudioBuffer.append against the arena capacity (audio_buffer.py:118-122)."""
     import torch
