@@ -224,14 +224,105 @@ def cpu_baseline(workload: str, cores: int, n_clips: int, seconds: float) -> dic
                       f"numpy/scipy around those packages), {dt:.2f} s of wall time"}
 
 
+TTS_FX = [{"type": "normalize", "target_lufs": -16}, {"type": "reverb", "room": "medium"}, {"type": "podcast_eq"}, {"type": "robot"}]
+OTHER_CPU = {
+    # workload: (jobs for one host thread on the default line, audio-seconds per job, what one job is)
+    "vad": (4, 60.0, "60 s streams: Silero-shaped network restated in numpy (front batched over the windows, LSTM cell per window; the reference "
+                     "calls onnxruntime once per window, src/vad/silero.py:63-91) + get_speech_segments"),
+    "realtime": (256, 64 * 0.020, "streams x 64 ticks of 20 ms: per tick decode_audio_to_pcm16(g711_ulaw -> 16 kHz) + buffer append + gate machine "
+                                  "(src/realtime/server.py:127-170, audio_buffer.py:37-58, :111-154; no full VAD window in 20 ms, as in the reference)"),
+    "tts": (16, None, "utterances of the same synthetic batch: process_tts_chunks(trim, normalize) + apply_chain([normalize, reverb medium, podcast_eq, "
+                      "robot]) + float32_to_int16 (src/audio/postprocessing.py, src/effects/chain.py, src/tts/pipeline.py)"),
+}
+
+
+def _cpu_other_one(args):
+    """One job of the oracle port of configs[1] / [2] / [4]; returns its wall time."""
+    import warnings
+
+    warnings.filterwarnings("ignore")
+    kind, data = args
+    t = time.perf_counter()
+    if kind == "vad":
+        from oracle import vad as ovad
+
+        if not hasattr(_cpu_other_one, "net"):
+            _cpu_other_one.net = ovad.SileroNet()  # weights made once per process (the reference loads its model once, too)
+        probs, _ = _cpu_other_one.net.score_stream(data.astype(np.float32) / 32768.0)
+        ovad.segments_from_probs(probs, len(data))
+    elif kind == "realtime":
+        from oracle import codec
+        from oracle import vad as ovad
+
+        buf = bytearray()
+        for k in range(data.shape[0]):
+            buf.extend(codec.decode_audio_to_pcm16(data[k].tobytes(), "g711_ulaw", 16000))
+        ovad.input_buffer_events([0.0] * data.shape[0], [2 * data.shape[1]] * data.shape[0], 0.5, 500)
+    else:
+        from oracle import tts as otts
+
+        otts.tts_chain([data], TTS_FX)
+    return time.perf_counter() - t
+
+
+def cpu_baseline_other(workload: str, cores: int, n_jobs: int = 0) -> dict:
+    """Oracle port of configs[1] (vad), [2] (realtime) or [4] (tts) on `cores` host processes, bounded sample of the same synthetic workload."""
+    from open_speech_b200 import synth
+
+    dflt, job_s, what = OTHER_CPU[workload]
+    n_jobs = n_jobs or dflt
+    if workload == "vad":
+        base = [synth.clip_pcm16(job_s, seed=synth.SEED_C2 + 1 + i) for i in range(min(n_jobs, DISTINCT))]
+        jobs = [("vad", base[i % len(base)]) for i in range(n_jobs)]
+        warm, audio_s = ("vad", base[0][: SR * 2]), n_jobs * job_s
+    elif workload == "realtime":
+        data = synth.ulaw_streams(min(n_jobs, 16), 64)                       # [64 ticks, streams, 160 bytes]
+        jobs = [("realtime", np.ascontiguousarray(data[:, i % data.shape[1]])) for i in range(n_jobs)]
+        warm, audio_s = ("realtime", jobs[0][1][:4]), n_jobs * job_s
+    else:
+        utts = synth.tts_batch(n_jobs, seed=synth.SEED_C5, distinct=32)
+        jobs = [("tts", u) for u in utts]
+        warm, audio_s = ("tts", utts[0][:24000]), sum(len(u) for u in utts) / 24000.0
+    if cores <= 1:
+        _cpu_other_one(warm)
+        t0 = time.perf_counter()
+        for j in jobs:
+            _cpu_other_one(j)
+        dt = time.perf_counter() - t0
+    else:
+        import multiprocessing as mp
+
+        with mp.get_context("fork").Pool(cores) as pool:
+            pool.map(_cpu_other_one, [warm] * cores)
+            t0 = time.perf_counter()
+            pool.map(_cpu_other_one, jobs, chunksize=max(1, len(jobs) // (4 * cores)))
+            dt = time.perf_counter() - t0
+    return {"value": audio_s / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{n_jobs} {what}; numpy/scipy oracle port, {audio_s:.0f} audio-s in {dt:.2f} s of wall time"}
+
+
 def run_reference(args) -> None:
     """--impl reference: the reference's CPU path (oracle port) on all host cores; rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    cores = os.cpu_count() or 1
+    if args.workload in OTHER_CPU:
+        per_core = {"vad": 2, "realtime": 256, "tts": 8}[args.workload]
+        vals, base = [], None
+        for i in range(args.warmup + args.steps):
+            base = cpu_baseline_other(args.workload, cores, per_core * cores)
+            if i >= args.warmup:
+                vals.append(base["value"])
+        v = float(np.mean(vals))
+        base["value"] = v
+        print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                          "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64/f32", "data": "synthetic",
+                          "config": {"workload": f"BASELINE {args.workload} config, bounded sample: " + OTHER_CPU[args.workload][2], "host_cores": cores},
+                          "cpu_baseline": base, "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}), flush=True)
+        return
     wl = args.workload if args.workload in STT else "stt_batch"
     desc, clips_per_gpu, seconds, nr, norm, n_mels, _full = STT[wl]
-    cores = os.cpu_count() or 1
     n_clips = max(cores, 8)
     sample_s = 60.0 if seconds >= 60.0 else seconds
     vals = []
@@ -705,10 +796,13 @@ def tts_run(ctx: Ctx, B: int, steps: int) -> dict:
 def print_sub(ctx: Ctx, args, res: dict, dtype: str) -> None:
     if ctx.rank != 0:
         return
+    if ctx.world == 1 and not args.no_cpu and args.workload in OTHER_CPU:  # a larger sample than the default line's compact leg
+        res["cpu_baseline"] = cpu_baseline_other(args.workload, 1, 3 * OTHER_CPU[args.workload][0])
     line = {"metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": ctx.world, "steps": res.get("steps", args.steps), "warmup": 3,
             "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": dtype, "data": "synthetic",
             "config": {"workload": res.pop("workload")}, "roofline": {"bound": "hbm", "frac": res.get("roofline_frac"), "peak": ctx.peak, "unit": "GB/s",
-                                                                       "peak_source": ctx.peak_src, "traffic": None}, "detail": res}
+                                                                       "peak_source": ctx.peak_src, "traffic": None},
+            "cpu_baseline": res.pop("cpu_baseline", None), "detail": res}
     print(json.dumps(line), flush=True)
 
 
@@ -753,6 +847,9 @@ def main():
                     t0 = time.perf_counter()
                     extra[name] = fn()
                     extra[name]["bench_wall_s"] = round(time.perf_counter() - t0, 1)
+                    if ctx.rank == 0 and ctx.world == 1 and not args.no_cpu:  # the CPU path of every named shape beside it, one host thread
+                        extra[name]["cpu_baseline"] = (cpu_baseline_other(name, 1) if name in OTHER_CPU
+                                                       else cpu_baseline(name, 1, 4 if name == "stt_full" else 24, STT[name][2]))
                     torch.cuda.synchronize()
                     torch.cuda.empty_cache()
             bench_stt(ctx, args, "stt_batch", extra)

@@ -30,6 +30,30 @@ def test_reference_arm_json_line():
     assert line["e2e"] == {"value": line["value"], "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 
+@pytest.mark.parametrize("workload", ["vad", "realtime", "tts"])
+def test_reference_arm_other_configs(workload):
+    """configs[1] / [2] / [4] have a CPU arm of their own (north_star: every named shape next to the CPU path)."""
+    r = _run("--impl", "reference", "--workload", workload, "--steps", "1", "--warmup", "0")
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "audio-s/s" and line["value"] > 0 and line["gpu_launches"] == 0
+    assert workload in line["config"]["workload"]
+    cb = line["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == line["value"] and "audio-s in" in cb["sample"]
+
+
+def test_cpu_legs_of_the_other_configs_are_bounded():
+    import time
+
+    sys.path.insert(0, ROOT)
+    import bench
+
+    for w in bench.OTHER_CPU:
+        t0 = time.perf_counter()
+        cb = bench.cpu_baseline_other(w, 1)
+        assert cb["value"] > 0 and cb["cores"] == 1 and time.perf_counter() - t0 < 60.0
+
+
 def test_reference_arm_other_ranks_exit_quietly():
     env = dict(os.environ, PYTHONPATH=ROOT, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"],
