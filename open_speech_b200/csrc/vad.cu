@@ -495,7 +495,7 @@ __device__ __forceinline__ long long pre_at(long long w, int own, bool tiled) {
 constexpr int kHq = 36;  // floats between the four 32-float quarters of h in shared memory: the quarters sit in different banks
 template <int S>
 struct RecurCfg {
-    static constexpr int RKG = S == 1 ? 6 : (S == 2 ? 5 : 3);  // of the 8 four-column groups of a thread's block, those kept in registers
+    static constexpr int RKG = S == 1 ? 6 : (S == 2 ? 5 : (S == 3 ? 4 : 3));  // of the 8 four-column groups of a thread's block, those kept in registers
     static constexpr int SKG = 8 - RKG;
     // W slice | h, double-buffered | per-warp partials of the head: a ring of 64 steps (row of 16 padded to 17)
     static constexpr int smem = (SKG * 4 * 4 * kGates + 2 * S * 4 * kHq + 64 * S * 17) * (int)sizeof(float);
@@ -662,7 +662,7 @@ __global__ void __launch_bounds__(512, 1) k_vad_recur(const float* __restrict__ 
 
 template <int S>
 struct RecurMbCfg {
-    static constexpr int RKG = S == 1 ? 6 : (S == 2 ? 5 : 3);  // of the 8 four-column groups of a thread's block, those kept in registers
+    static constexpr int RKG = S == 1 ? 6 : (S == 2 ? 5 : (S == 3 ? 4 : 3));  // of the 8 four-column groups of a thread's block, those kept in registers
     static constexpr int SKG = 8 - RKG;
     static constexpr int smem = (SKG * 4 * 4 * kGates + S * (4 * kHq + kGates) + kHid + 64 * S * 17) * (int)sizeof(float);
 };
@@ -933,8 +933,38 @@ static int launch_gemm(const GemmDesc& d, cudaStream_t st) {
 }
 
 static int share_width() {
-    static const int w = [] { const char* e = getenv("OSB_VAD_SHARE_WIDTH"); const int v = e ? atoi(e) : 0; return (v == 1 || v == 2 || v == 4) ? v : 4; }();
+    static const int w = [] { const char* e = getenv("OSB_VAD_SHARE_WIDTH"); const int v = e ? atoi(e) : 0; return (v >= 1 && v <= 4) ? v : 4; }();
     return w;
+}
+
+static bool pipeline_enabled() {  // read per call: a test (and the bench's A/B leg) switches it inside one process
+    const char* e = getenv("OSB_VAD_PIPELINE");
+    return !(e && atoi(e) == 0);
+}
+
+// per-thread side stream + events of the pipelined chunks (created once per device)
+struct FrontSide {
+    cudaStream_t front = nullptr;
+    cudaEvent_t start = nullptr, front_done[2] = {nullptr, nullptr}, recur_done[2] = {nullptr, nullptr};
+    int device = -1;
+};
+static int front_side(FrontSide** out) {
+    static thread_local FrontSide s;
+    int dev = 0;
+    OSB_CUDA(cudaGetDevice(&dev));
+    if (s.device != dev) {
+        if (s.front) {
+            cudaStreamDestroy(s.front);
+            for (cudaEvent_t e : {s.start, s.front_done[0], s.front_done[1], s.recur_done[0], s.recur_done[1]}) cudaEventDestroy(e);
+            s = FrontSide{};
+        }
+        OSB_CUDA(cudaStreamCreateWithFlags(&s.front, cudaStreamNonBlocking));
+        for (cudaEvent_t* e : {&s.start, &s.front_done[0], &s.front_done[1], &s.recur_done[0], &s.recur_done[1]})
+            OSB_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+        s.device = dev;
+    }
+    *out = &s;
+    return OSB_OK;
 }
 
 static int vad_score(VadModel* m, const void* d_audio, int fmt, int64_t n, int64_t batch, int64_t stride, float* d_state,
@@ -954,7 +984,6 @@ static int vad_score(VadModel* m, const void* d_audio, int fmt, int64_t n, int64
     Scratch scr(st);
     const bool fused = m->use_tc == 2;
     float *mag = nullptr, *h1 = nullptr, *h2 = nullptr, *h3 = nullptr, *h4 = nullptr, *pre;
-    OSB_CUDA(scr.alloc(&pre, (size_t)((W + 127) / 128) * 128 * kGates + 64));  // whole 128-window tiles (the fused front's tiled layout)
     if (!fused) {
         OSB_CUDA(scr.alloc(&mag, (size_t)W * 5 * kMagC + 128));
         OSB_CUDA(scr.alloc(&h1, (size_t)W * 5 * 128 + 64));
@@ -973,6 +1002,8 @@ static int vad_score(VadModel* m, const void* d_audio, int fmt, int64_t n, int64
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_vad_recur<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, RecurCfg<1>::smem);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_vad_recur_mb<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, RecurMbCfg<2>::smem);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_vad_recur_mb<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, RecurMbCfg<2>::smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_vad_recur_mb<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, RecurMbCfg<3>::smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_vad_recur_mb<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, RecurMbCfg<3>::smem);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_vad_recur_mb<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, RecurMbCfg<4>::smem);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_vad_recur_mb<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, RecurMbCfg<4>::smem);
         return e;
@@ -983,12 +1014,44 @@ static int vad_score(VadModel* m, const void* d_audio, int fmt, int64_t n, int64
     // VAD branch time but hands the SMs it vacates to kernels that can fill them.
     int rs = batch <= OSB_NUM_SMS ? 1 : (batch <= 2 * OSB_NUM_SMS ? 2 : 4);
     if (shared_gpu && batch > OSB_NUM_SMS / 2) rs = share_width();
+    // Pipelined chunks (fused front, more than one chunk, the GPU to ourselves): the front of chunk i + 1 runs on a side stream BESIDE the
+    // recurrence of chunk i, on the SMs the recurrence leaves free (neither kernel shares an SM: 227 KB of shared memory each), into the
+    // other half of a double-buffered `pre`.  The recurrence is the serial chain, so it gets as few SMs as keep it in one wave with at
+    // least kFrontMinSms left over: 256 streams -> four per CTA on 64 SMs, front on 84.
+    constexpr int kFrontMinSms = 48;
+    bool pipelined = false;
+    if (fused && !shared_gpu && n_win > T && pipeline_enabled()) {
+        int prs = rs;
+        if (const char* e = getenv("OSB_VAD_PIPE_WIDTH")) { const int v = atoi(e); if (v >= 1 && v <= 4) prs = v > rs ? v : rs; }  // experiments
+        while (prs < 4 && OSB_NUM_SMS - (int)((batch + prs - 1) / prs) < kFrontMinSms) ++prs;
+        if (OSB_NUM_SMS - (int)((batch + prs - 1) / prs) >= kFrontMinSms) { pipelined = true; rs = prs; }
+    }
+    const size_t pre_floats = (size_t)((W + 127) / 128) * 128 * kGates + 64;  // whole 128-window tiles (the fused front's tiled layout)
+    OSB_CUDA(scr.alloc(&pre, pre_floats * (pipelined ? 2 : 1)));
+    FrontSide* fs = nullptr;
     int rc;
-    for (long long w0 = 0; w0 < n_win; w0 += T) {
+    if (pipelined) {
+        if ((rc = front_side(&fs))) return rc;
+        OSB_CUDA(cudaEventRecord(fs->start, st));  // the audio and `pre` exist on st from here on
+        OSB_CUDA(cudaStreamWaitEvent(fs->front, fs->start, 0));
+    }
+    const int front_ctas = OSB_NUM_SMS - (int)((batch + rs - 1) / rs);
+    long long chunk = 0;
+    float* const pre0 = pre;
+    for (long long w0 = 0; w0 < n_win; w0 += T, ++chunk) {
         const int t = (int)((n_win - w0) < T ? (n_win - w0) : T);
         const int Wc = (int)(batch * t);
         GemmDesc d{};
-        if (fused) {
+        if (pipelined) {
+            const int b = (int)(chunk & 1);
+            pre = pre0 + (size_t)b * pre_floats;
+            if (chunk >= 2) OSB_CUDA(cudaStreamWaitEvent(fs->front, fs->recur_done[b], 0));  // the recurrence of chunk - 2 has read this half
+            // chunk 0 has the whole GPU; later fronts start while a recurrence holds its SMs
+            if ((rc = launch_vad_front_fused(m->fused, d_audio, fmt, stride, t, w0, (long long)batch * t, pre, fs->front, 0, -1, chunk ? front_ctas : 0)))
+                return rc;
+            OSB_CUDA(cudaEventRecord(fs->front_done[b], fs->front));
+            OSB_CUDA(cudaStreamWaitEvent(st, fs->front_done[b], 0));
+        } else if (fused) {
             if ((rc = launch_vad_front_fused(m->fused, d_audio, fmt, stride, t, w0, (long long)batch * t, pre, st))) return rc;
         } else {
         // L0: DFT conv + magnitude -> mag[w][1+f][0..128]
@@ -1036,9 +1099,11 @@ static int vad_score(VadModel* m, const void* d_audio, int fmt, int64_t n, int64
                                          (long long)probs_stride, w0, (int)batch)
         if (rs == 1) { if (fused) OSB_RECUR((k_vad_recur<1, true>), RecurCfg<1>::smem); else OSB_RECUR((k_vad_recur<1, false>), RecurCfg<1>::smem); }
         else if (rs == 2) { if (fused) OSB_RECUR((k_vad_recur_mb<2, true>), RecurMbCfg<2>::smem); else OSB_RECUR((k_vad_recur_mb<2, false>), RecurMbCfg<2>::smem); }
+        else if (rs == 3) { if (fused) OSB_RECUR((k_vad_recur_mb<3, true>), RecurMbCfg<3>::smem); else OSB_RECUR((k_vad_recur_mb<3, false>), RecurMbCfg<3>::smem); }
         else { if (fused) OSB_RECUR((k_vad_recur_mb<4, true>), RecurMbCfg<4>::smem); else OSB_RECUR((k_vad_recur_mb<4, false>), RecurMbCfg<4>::smem); }
 #undef OSB_RECUR
         OSB_CHECK_LAUNCH();
+        if (pipelined) OSB_CUDA(cudaEventRecord(fs->recur_done[chunk & 1], st));
     }
     return OSB_OK;
 }

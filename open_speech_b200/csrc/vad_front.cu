@@ -67,7 +67,8 @@ struct Params {
     int wins_per_stream;        // windows of this chunk per stream (T)
     long long win0;             // first window of the chunk
     long long total;            // windows in this launch = streams * T
-    int n_tiles;
+    int n_tiles;                // end of the tile range of this launch
+    int tile0;                  // first tile of this launch (the chunk's tiles may be split over two launches, vad.cu)
     const uint8_t* wimg;        // weight image
     const uint2* slots;         // [57] (byte offset, bytes) in consumption order
     float* pre;                 // [windows / 8][64 column groups][8][8]: W_ih.x + b_ih + b_hh, interleaved (vad.cu pre_at)
@@ -414,10 +415,10 @@ struct StageRole {
     __device__ __forceinline__ void run(int n_my) {
         const bool pcm = p.fmt == OSB_FMT_PCM16;
         uint4 wa[4], wb[4];
-        if (n_my > 0) tile_rows((long long)blockIdx.x);
+        if (n_my > 0) tile_rows((long long)p.tile0 + blockIdx.x);
         if (pcm && n_my > 0) load_pcm(0, wa);
         for (int i = 0; i < n_my; ++i) {
-            const long long tile = (long long)blockIdx.x + (long long)i * gridDim.x;
+            const long long tile = (long long)p.tile0 + blockIdx.x + (long long)i * gridDim.x;
             if (pcm) {
 #pragma unroll 1
                 for (int c = 0; c < 24; c += 2) {
@@ -630,12 +631,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_vad_front_fused(Params p) {
     __syncthreads();
     fence_after();
     sm.tmem = *tmem_ptr;
-    const int n_my = (p.n_tiles > (int)blockIdx.x) ? (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    const int n_my = (p.n_tiles - p.tile0 > (int)blockIdx.x) ? (p.n_tiles - p.tile0 - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
     Book bk;
     bk.wpar = bk.wany = bk.ph = bk.tany = 0;
     if (warp < 8) {
         EpiRole r(sm, bk, p, tid);
-        for (int i = 0; i < n_my; ++i) r.run_tile((long long)blockIdx.x + (long long)i * gridDim.x);
+        for (int i = 0; i < n_my; ++i) r.run_tile((long long)p.tile0 + blockIdx.x + (long long)i * gridDim.x);
     } else if (warp < (kEpiThreads + kStageThreads) / 32) {
         StageRole r(sm, bk, p, tid - kEpiThreads);
         r.run(n_my);
@@ -759,15 +760,20 @@ void vad_front_destroy(VadFront* f) {
     delete f;
 }
 
+int vad_front_tiles(long long total_windows) { return (int)((total_windows + vf::kRows - 1) / vf::kRows); }
+
 int launch_vad_front_fused(const VadFront* f, const void* d_audio, int fmt, long long audio_stride, int wins_per_stream, long long win0,
-                           long long total_windows, float* d_pre, cudaStream_t st) {
+                           long long total_windows, float* d_pre, cudaStream_t st, int tile_begin, int tile_end, int max_ctas) {
     static PerDeviceOnce once;
     OSB_CUDA(once.run([&] { return cudaFuncSetAttribute(vf::k_vad_front_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, vf::kSmem); }));
     vf::Params p;
     p.audio = d_audio; p.fmt = fmt; p.audio_stride = audio_stride; p.wins_per_stream = wins_per_stream; p.win0 = win0; p.total = total_windows;
-    p.n_tiles = (int)((total_windows + vf::kRows - 1) / vf::kRows);
+    p.n_tiles = vad_front_tiles(total_windows);
+    if (tile_end >= 0 && tile_end < p.n_tiles) p.n_tiles = tile_end;
+    p.tile0 = tile_begin > 0 ? tile_begin : 0;
     p.wimg = f->wimg; p.slots = f->slots; p.pre = d_pre; p.c = f->consts;
-    const int grid = p.n_tiles < num_sms() ? p.n_tiles : num_sms();
+    const int ctas = (max_ctas > 0 && max_ctas < num_sms()) ? max_ctas : num_sms();
+    const int grid = (p.n_tiles - p.tile0) < ctas ? (p.n_tiles - p.tile0) : ctas;
     if (grid <= 0) return OSB_OK;
     p.trace = nullptr;
     const char* tpath = getenv("OSB_VF_TRACE");  // debug: clock stamps of CTA 0's first four tiles, written as text after a device sync

@@ -15,8 +15,11 @@ struct VadFrontLayout {
 int vad_front_create(const float* weights_host, const VadFrontLayout& layout, VadFront** out);
 void vad_front_destroy(VadFront* f);
 // windows are rows (stream, t): window w of the launch = stream w / wins_per_stream, window win0 + w % wins_per_stream of that stream;
-// d_pre (ceil(total_windows / 128) * 65536 floats) receives W_ih.x + b_ih + b_hh in the interleaved layout of vad.cu's pre_at()
+// d_pre (ceil(total_windows / 128) * 65536 floats) receives W_ih.x + b_ih + b_hh in the interleaved layout of vad.cu's pre_at().
+// tile_begin / tile_end (-1: to the last tile) restrict the launch to a range of the chunk's 128-window tiles; max_ctas (0: one per SM)
+// caps the grid, so that the launch fits on the SMs a concurrently running recurrence leaves free (vad.cu, pipelined chunks)
+int vad_front_tiles(long long total_windows);
 int launch_vad_front_fused(const VadFront* f, const void* d_audio, int fmt, long long audio_stride, int wins_per_stream, long long win0,
-                           long long total_windows, float* d_pre, cudaStream_t st);
+                           long long total_windows, float* d_pre, cudaStream_t st, int tile_begin = 0, int tile_end = -1, int max_ctas = 0);
 
 }  // namespace osb

@@ -155,6 +155,38 @@ def test_many_streams_share_recurrence_ctas(gpu, session, batch):
     assert np.abs(got[0] - o2).max() <= PROB_TOL
 
 
+@pytest.mark.parametrize("batch", [40, 131, 256])
+def test_pipelined_chunks_match_serial(gpu, session, batch, monkeypatch):
+    """More than one chunk of windows: the fused front of chunk i + 1 runs on a side stream beside the recurrence of chunk i (double-
+    buffered pre-activations, front grid capped to the SMs the recurrence leaves free; 256 streams -> four streams per recurrence CTA
+    instead of two).  Same probabilities and carried state, bit for bit, as the serial schedule; ragged last chunk; two calls."""
+    import torch
+
+    monkeypatch.setenv("OSB_VAD_CHUNK_WAVES", "1")  # 148 x 128 windows per chunk
+    secs = {40: 50.0, 131: 16.0, 256: 9.0}[batch]  # 4-5 chunks each, the last one short
+    base = [_audio(secs, 700 + i) for i in range(5)]
+    pcm = np.stack([base[i % 5] for i in range(batch)])
+    n = pcm.shape[1]
+    n_win = n // 512
+    assert n_win * batch > 3 * 148 * 128
+    x = torch.from_numpy(pcm).cuda()
+    res = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("OSB_VAD_PIPELINE", mode)
+        state = torch.zeros((batch, 2, 128), dtype=torch.float32, device="cuda")
+        probs = torch.full((batch, n_win), -1.0, dtype=torch.float32, device="cuda")
+        for _ in range(2):
+            gpu.call("osb_vad_score_dev", session.handle, x.data_ptr(), gpu.FMT_PCM16, n, batch, n, state.data_ptr(), probs.data_ptr(), n_win,
+                     torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        res[mode] = (probs.cpu().numpy(), state.cpu().numpy())
+    assert np.array_equal(res["0"][0], res["1"][0]) and np.array_equal(res["0"][1], res["1"][1])
+    net = ovad.SileroNet()
+    o1, s1 = net.score_stream(base[1].astype(np.float32) / 32768.0)
+    o2, _ = net.score_stream(base[1].astype(np.float32) / 32768.0, s1)
+    assert np.abs(res["1"][0][1] - o2).max() <= PROB_TOL
+
+
 def test_tcgen05_fronts_match_ffma_and_oracle(gpu, session):
     """The fused persistent tcgen05 front (mode 2, the default) and the per-layer tcgen05 GEMMs (mode 1), both split-bf16, against
     the FP32 FFMA kernels (mode 0) and the oracle."""
