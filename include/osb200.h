@@ -114,6 +114,9 @@ int osb_vad_destroy(void* handle);
 /* front-end engine: 2 = fused persistent tcgen05 kernel, samples -> gate pre-activations on chip (default); 1 = one tcgen05 split-bf16
  * GEMM per layer; 0 = FP32 FFMA GEMMs (cross-check) */
 int osb_vad_set_gemm(void* handle, int use_tcgen05);
+/* recurrence engine: 1 = tensor-pipe kernel (W_hh as fp16 mma fragments in registers, h as fp16 hi + lo planes, eight streams per CTA;
+ * default); 0 = the FP32 FFMA lock-step kernels (cross-check).  Both replace the LSTM cell inside session.run (:86). */
+int osb_vad_set_recurrence(void* handle, int tensor_pipe);
 /* batch streams, n samples each (floor(n/512) windows); d_state [batch][2][128] in/out;
  * d_probs [batch][probs_stride] out (one probability per window). */
 int osb_vad_score_dev(void* handle, const void* d_audio, int fmt, int64_t n, int64_t batch, int64_t stride, float* d_state,

@@ -15,6 +15,7 @@
 #include <vector>
 
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 #include "vad_front.cuh"
@@ -46,6 +47,8 @@ struct VadModel {
     float *wih, *bsum; // [512][128], b_ih + b_hh
     float *whh;        // [512][128]
     float *whh_perm;   // the same weights in the per-thread block order of k_vad_recur
+    uint32_t *whh_tc;  // the same weights as fp16 mma.sync A fragments in the register order of k_vad_recur_tc
+    int recur_tc;      // 1: tensor-pipe recurrence, eight streams per CTA (default) | 0: FP32 FFMA lock-step kernels (cross-check)
     float *dw;         // [128]
     float db;
     // tcgen05 path: per layer, B as split-bf16 (hi, lo) tiles pre-arranged in the 128B-swizzled K-major
@@ -790,6 +793,151 @@ __global__ void __launch_bounds__(512, 1) k_vad_recur_mb(const float* __restrict
     }
 }
 
+// ------------------------------------------------------------------ recurrence on the tensor pipe, eight streams per CTA
+// The FFMA kernels above spend ~1,400 SM-cycles per stream and step on a 512 x 128 matrix-vector product whose FP32 floor alone is 512.
+// Batched over EIGHT streams the product is a [512 x 128] x [128 x 8] matrix product per step, and the warp-level mma.sync is the tensor
+// instruction whose shape (m16n8k16) and latency (tens of cycles, operands and result in registers, no descriptor, no TMEM round trip,
+// no commit/wait) fit a chain that is a few hundred cycles long and strictly serial: tcgen05.mma needs N >= 16 at M = 128 and an
+// asynchronous commit -> tcgen05.ld -> fence hand-over per step, which is most of such a step.
+//   * W_hh lives in REGISTERS as fp16 A fragments for the whole launch (64 registers per thread: warp w owns the four gates of units
+//     8w .. 8w+7 = two 16-row tiles x eight k tiles), h as two fp16 planes (hi + lo) in shared memory, double-buffered: two MMAs per
+//     tile and k step (W.h_hi + W.h_lo), FP32 accumulate.  Probability error of this operand scheme through the recurrence, simulated
+//     on 120 s clips (tools/vad_precision_sim.py recur): 1.1e-4 (budget 1e-3; W rounded to fp16 is the whole of it).
+//   * Row r of tile mt: gate r / 4, unit 8w + 2 (r % 4) + mt, so a lane's accumulators hold two gates of one unit for two streams; the
+//     partner lane (lane ^ 16) holds the other two gates: two shuffles, then every lane owns ONE stream's cell for two adjacent units
+//     (c in registers, h written as one packed fp16 pair per plane).
+//   * k slot (kt, s) of the fragments = unit (kt / 2) * 32 + ((s % 8) / 2) * 8 + (kt % 2) * 4 + (s / 8) * 2 + s % 2: with that order a
+//     lane's B fragments of all eight k tiles are four 16-byte chunks of the stream's row, 64 bytes apart, bank-conflict free at a row
+//     stride of 320 bytes.
+//   * one barrier per step; the head's partial sums go through a 64-step ring as in the FFMA kernels.
+// Which CTA column a stream sits in is invisible (every output element of an MMA is the same dot product whatever its neighbours hold).
+constexpr int kTcStreams = 8;
+constexpr int kTcRow = 320;  // bytes between the streams' rows of an h plane
+__device__ __forceinline__ void mma_f16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__host__ __device__ inline int recur_tc_kslot_unit(int kt, int s) { return (kt >> 1) * 32 + ((s & 7) >> 1) * 8 + (kt & 1) * 4 + (s >> 3) * 2 + (s & 1); }
+
+template <bool ILV, int TERMS>  // TERMS 2: W.h_hi + W.h_lo | 1: W.h_hi only (h rounded to fp16)
+__global__ void __launch_bounds__(512, 1) k_vad_recur_tc(const float* __restrict__ pre, long long pre_stream_stride, int n_steps,
+                                                      const uint32_t* __restrict__ wimg, const float* __restrict__ dw, float db,
+                                                      float* __restrict__ state, float* __restrict__ probs, long long probs_stride,
+                                                      long long win0, int batch) {
+    __shared__ __align__(16) unsigned char h_sm[2][2][kTcStreams * kTcRow];  // [buffer][plane hi | lo][stream][128 fp16 (+ pad)]
+    __shared__ float part_sm[64][kTcStreams][17];                            // [step ring][stream][warp]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, tig = lane & 3, b0 = blockIdx.x * kTcStreams;
+    const int ns = min(kTcStreams, batch - b0);  // live streams of this CTA
+    uint32_t wa[2][8][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int kt = 0; kt < 8; ++kt)
+#pragma unroll
+            for (int r = 0; r < 4; ++r) wa[mt][kt][r] = wimg[((((warp * 2 + mt) * 8 + kt) * 4 + r) << 5) + lane];
+    // this lane's cell: stream cs, units u0 and u0 + 1
+    const bool is_a = g < 4;
+    const int cs = 2 * tig + (g >> 2), u0 = 8 * warp + 2 * (g & 3);
+    const bool live = cs < ns;
+    const int srd = live ? cs : 0;  // dead columns read stream 0's inputs and store nothing
+    float* st = state + (long long)(b0 + srd) * 2 * kHid;
+    float2 h = live ? *reinterpret_cast<const float2*>(st + u0) : make_float2(0.f, 0.f);
+    float2 c = live ? *reinterpret_cast<const float2*>(st + kHid + u0) : make_float2(0.f, 0.f);
+    const float2 dwv = *reinterpret_cast<const float2*>(dw + u0);
+    auto store_h = [&](unsigned char* buf) {  // h as fp16 hi + lo, one packed pair per plane
+        const __half2 hi = __floats2half2_rn(h.x, h.y);
+        const float2 hf = __half22float2(hi);
+        *reinterpret_cast<__half2*>(buf + cs * kTcRow + u0 * 2) = hi;
+        if (TERMS == 2) {
+            const __half2 lo = __floats2half2_rn(__fsub_rn(h.x, hf.x), __fsub_rn(h.y, hf.y));
+            *reinterpret_cast<__half2*>(buf + kTcStreams * kTcRow + cs * kTcRow + u0 * 2) = lo;
+        }
+    };
+    store_h(&h_sm[0][0][0]);
+    // gate pre-activations of the lane's cell: four float2 (gates i, f, g, o of units u0, u0 + 1) per window
+    const long long w_first = (long long)(b0 + srd) * (pre_stream_stride / kGates);
+    const float* p = pre + pre_at(w_first, u0, ILV);  // gate G at p + G * (ILV ? 1024 : 128)
+    constexpr int kGateStep = ILV ? 16 * 64 : kHid;
+    int ph = (int)(w_first & 7);
+    float2 pv[4];
+#pragma unroll
+    for (int G = 0; G < 4; ++G) pv[G] = n_steps > 0 ? *reinterpret_cast<const float2*>(p + G * kGateStep) : make_float2(0.f, 0.f);
+    const unsigned char* my_b = &h_sm[0][0][0] + g * kTcRow + tig * 16;
+    __syncthreads();
+    for (int t = 0; t < n_steps; ++t) {
+        const unsigned char* hr = my_b + (t & 1) * (2 * kTcStreams * kTcRow);
+        float ahi[2][4], alo[2][4];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) ahi[mt][k] = alo[mt][k] = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint4 bh = *reinterpret_cast<const uint4*>(hr + j * 64);
+            if (TERMS == 2) {
+                const uint4 bl = *reinterpret_cast<const uint4*>(hr + kTcStreams * kTcRow + j * 64);
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt) {
+                    mma_f16(ahi[mt], wa[mt][2 * j], bh.x, bh.y);
+                    mma_f16(alo[mt], wa[mt][2 * j], bl.x, bl.y);
+                    mma_f16(ahi[mt], wa[mt][2 * j + 1], bh.z, bh.w);
+                    mma_f16(alo[mt], wa[mt][2 * j + 1], bl.z, bl.w);
+                }
+            } else {  // even and odd k tiles on separate accumulators: four chains of four instead of two of eight
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt) {
+                    mma_f16(ahi[mt], wa[mt][2 * j], bh.x, bh.y);
+                    mma_f16(alo[mt], wa[mt][2 * j + 1], bh.z, bh.w);
+                }
+            }
+        }
+        float hn[2];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+            const float d0 = __fadd_rn(ahi[mt][0], alo[mt][0]), d1 = __fadd_rn(ahi[mt][1], alo[mt][1]);
+            const float d2 = __fadd_rn(ahi[mt][2], alo[mt][2]), d3 = __fadd_rn(ahi[mt][3], alo[mt][3]);
+            const float x = __shfl_xor_sync(0xffffffffu, is_a ? d1 : d0, 16), y = __shfl_xor_sync(0xffffffffu, is_a ? d3 : d2, 16);
+            const float gi = __fadd_rn(is_a ? d0 : x, mt ? pv[0].y : pv[0].x), gf = __fadd_rn(is_a ? x : d1, mt ? pv[1].y : pv[1].x);
+            const float gg = __fadd_rn(is_a ? d2 : y, mt ? pv[2].y : pv[2].x), go = __fadd_rn(is_a ? y : d3, mt ? pv[3].y : pv[3].x);
+            float& cc = mt ? c.y : c.x;
+            cc = __fmaf_rn(sigmoidf_det(gf), cc, __fmul_rn(sigmoidf_det(gi), tanhf_fast(gg)));
+            hn[mt] = __fmul_rn(sigmoidf_det(go), tanhf_fast(cc));
+        }
+        h = make_float2(hn[0], hn[1]);
+        // the next window's pre-activations: issued here, consumed a step later
+        if (ILV) {
+            ph = (ph + 1) & 7;
+            p += ph ? 8 : 4096 - 56;
+        } else p += kGates;
+        if (t + 1 < n_steps) {
+#pragma unroll
+            for (int G = 0; G < 4; ++G) pv[G] = *reinterpret_cast<const float2*>(p + G * kGateStep);
+        }
+        store_h(&h_sm[(t + 1) & 1][0][0]);
+        // head: relu(h) . w_dec over the warp's eight units of this stream
+        float part = __fmaf_rn(fmaxf(h.y, 0.f), dwv.y, __fmul_rn(fmaxf(h.x, 0.f), dwv.x));
+        part += __shfl_xor_sync(0xffffffffu, part, 4);
+        part += __shfl_xor_sync(0xffffffffu, part, 8);
+        if ((g & 3) == 0) part_sm[t & 63][cs][warp] = part;
+        __syncthreads();
+        if (((t & 31) == 31 || t == n_steps - 1) && tid < 32 * kTcStreams) {  // 32 probabilities per stream every 32 steps
+            const int tb = t & ~31;
+            if (tb + lane <= t && warp < ns) {
+                const float* ps = part_sm[(tb + lane) & 63][warp];
+                float sum = 0.f;
+#pragma unroll
+                for (int k = 0; k < 16; k += 4) sum += (ps[k] + ps[k + 1]) + (ps[k + 2] + ps[k + 3]);
+                probs[(long long)(b0 + warp) * probs_stride + win0 + tb + lane] = sigmoidf_acc(sum + db);
+            }
+        }
+    }
+    if (live) {
+        *reinterpret_cast<float2*>(st + u0) = h;
+        *reinterpret_cast<float2*>(st + kHid + u0) = c;
+    }
+}
+
 // ------------------------------------------------------------------ segmenter (bit-exact integer machine)
 // one warp per stream: 32 probabilities per coalesced load -> ballot -> lane 0 walks the bits.
 __global__ void __launch_bounds__(32) k_vad_segment(const float* __restrict__ probs, long long probs_stride, long long n_win,
@@ -865,6 +1013,12 @@ __global__ void __launch_bounds__(256) k_vad_gather(const int16_t* __restrict__ 
 static int upload(float** dst, const std::vector<float>& v) {
     OSB_CUDA(cudaMalloc(dst, v.size() * sizeof(float)));
     OSB_CUDA(cudaMemcpy(*dst, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice));
+    return OSB_OK;
+}
+
+static int upload_words(uint32_t** dst, const std::vector<uint32_t>& v) {
+    OSB_CUDA(cudaMalloc(dst, v.size() * sizeof(uint32_t)));
+    OSB_CUDA(cudaMemcpy(*dst, v.data(), v.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
     return OSB_OK;
 }
 
@@ -1014,6 +1168,8 @@ static int vad_score(VadModel* m, const void* d_audio, int fmt, int64_t n, int64
     // VAD branch time but hands the SMs it vacates to kernels that can fill them.
     int rs = batch <= OSB_NUM_SMS ? 1 : (batch <= 2 * OSB_NUM_SMS ? 2 : 4);
     if (shared_gpu && batch > OSB_NUM_SMS / 2) rs = share_width();
+    const bool rtc = m->recur_tc != 0;
+    if (rtc) rs = kTcStreams;  // the tensor-pipe kernel: always eight streams per CTA
     // Pipelined chunks (fused front, more than one chunk, the GPU to ourselves): the front of chunk i + 1 runs on a side stream BESIDE the
     // recurrence of chunk i, on the SMs the recurrence leaves free (neither kernel shares an SM: 227 KB of shared memory each), into the
     // other half of a double-buffered `pre`.  The recurrence is the serial chain, so it gets as few SMs as keep it in one wave with at
@@ -1022,8 +1178,10 @@ static int vad_score(VadModel* m, const void* d_audio, int fmt, int64_t n, int64
     bool pipelined = false;
     if (fused && !shared_gpu && n_win > T && pipeline_enabled()) {
         int prs = rs;
-        if (const char* e = getenv("OSB_VAD_PIPE_WIDTH")) { const int v = atoi(e); if (v >= 1 && v <= 4) prs = v > rs ? v : rs; }  // experiments
-        while (prs < 4 && OSB_NUM_SMS - (int)((batch + prs - 1) / prs) < kFrontMinSms) ++prs;
+        if (!rtc) {
+            if (const char* e = getenv("OSB_VAD_PIPE_WIDTH")) { const int v = atoi(e); if (v >= 1 && v <= 4) prs = v > rs ? v : rs; }  // experiments
+            while (prs < 4 && OSB_NUM_SMS - (int)((batch + prs - 1) / prs) < kFrontMinSms) ++prs;
+        }
         if (OSB_NUM_SMS - (int)((batch + prs - 1) / prs) >= kFrontMinSms) { pipelined = true; rs = prs; }
     }
     const size_t pre_floats = (size_t)((W + 127) / 128) * 128 * kGates + 64;  // whole 128-window tiles (the fused front's tiled layout)
@@ -1097,11 +1255,17 @@ static int vad_score(VadModel* m, const void* d_audio, int fmt, int64_t n, int64
         const unsigned rg = (unsigned)((batch + rs - 1) / rs);
 #define OSB_RECUR(KERN, SMEM) OSB_LAUNCH(KERN, rg, 512, SMEM, st, pre, (long long)t * kGates, t, (const float4*)m->whh_perm, m->dw, m->db, d_state, d_probs, \
                                          (long long)probs_stride, w0, (int)batch)
-        if (rs == 1) { if (fused) OSB_RECUR((k_vad_recur<1, true>), RecurCfg<1>::smem); else OSB_RECUR((k_vad_recur<1, false>), RecurCfg<1>::smem); }
+#define OSB_RECUR_TC(ILV, TERMS) OSB_LAUNCH((k_vad_recur_tc<ILV, TERMS>), rg, 512, 0, st, pre, (long long)t * kGates, t, (const uint32_t*)m->whh_tc, m->dw, m->db, \
+                                            d_state, d_probs, (long long)probs_stride, w0, (int)batch)
+        if (rtc) {
+            if (m->recur_tc == 2) { if (fused) OSB_RECUR_TC(true, 1); else OSB_RECUR_TC(false, 1); }
+            else { if (fused) OSB_RECUR_TC(true, 2); else OSB_RECUR_TC(false, 2); }
+        } else if (rs == 1) { if (fused) OSB_RECUR((k_vad_recur<1, true>), RecurCfg<1>::smem); else OSB_RECUR((k_vad_recur<1, false>), RecurCfg<1>::smem); }
         else if (rs == 2) { if (fused) OSB_RECUR((k_vad_recur_mb<2, true>), RecurMbCfg<2>::smem); else OSB_RECUR((k_vad_recur_mb<2, false>), RecurMbCfg<2>::smem); }
         else if (rs == 3) { if (fused) OSB_RECUR((k_vad_recur_mb<3, true>), RecurMbCfg<3>::smem); else OSB_RECUR((k_vad_recur_mb<3, false>), RecurMbCfg<3>::smem); }
         else { if (fused) OSB_RECUR((k_vad_recur_mb<4, true>), RecurMbCfg<4>::smem); else OSB_RECUR((k_vad_recur_mb<4, false>), RecurMbCfg<4>::smem); }
 #undef OSB_RECUR
+#undef OSB_RECUR_TC
         OSB_CHECK_LAUNCH();
         if (pipelined) OSB_CUDA(cudaEventRecord(fs->recur_done[chunk & 1], st));
     }
@@ -1179,6 +1343,30 @@ int osb_vad_create(const float* weights_host, size_t n_floats, void** handle) {
             return rc;
         }
     }
+    {   // W_hh as fp16 A fragments of mma.m16n8k16 (k_vad_recur_tc): word [((warp * 2 + mt) * 8 + kt) * 4 + r][lane]
+        std::vector<uint32_t> img((size_t)16 * 2 * 8 * 4 * 32);
+        for (int warp = 0; warp < 16; ++warp)
+            for (int mt = 0; mt < 2; ++mt)
+                for (int kt = 0; kt < 8; ++kt)
+                    for (int r = 0; r < 4; ++r)
+                        for (int lane = 0; lane < 32; ++lane) {
+                            const int g = lane >> 2, tig = lane & 3, rr = g + 8 * (r & 1);                 // row of the 16-row tile
+                            const int row = (rr >> 2) * kHid + 8 * warp + 2 * (rr & 3) + mt;               // gate rr / 4 of that unit
+                            uint32_t word = 0;
+                            for (int e = 0; e < 2; ++e) {
+                                const int col = recur_tc_kslot_unit(kt, 2 * tig + 8 * (r >> 1) + e);
+                                const __half hv = __float2half_rn(w[oWhh + (size_t)row * kHid + col]);
+                                unsigned short bits;
+                                memcpy(&bits, &hv, 2);
+                                word |= (uint32_t)bits << (16 * e);
+                            }
+                            img[((size_t)(((warp * 2 + mt) * 8 + kt) * 4 + r) << 5) + lane] = word;
+                        }
+        if ((rc = upload_words(&m->whh_tc, img))) {
+            delete m;
+            return rc;
+        }
+    }
     m->db = w[oDb];
     {   // tcgen05 operand images
         std::vector<float> e1 = relay_conv(w + oE1w, 128, 129, kMagC, 448);
@@ -1200,6 +1388,8 @@ int osb_vad_create(const float* weights_host, size_t n_floats, void** handle) {
     }
     const char* env = getenv("OSB_VAD_GEMM");  // "ffma" | "layers" | (default) fused
     m->use_tc = (env && strcmp(env, "ffma") == 0) ? 0 : ((env && strcmp(env, "layers") == 0) ? 1 : 2);
+    const char* renv = getenv("OSB_VAD_RECUR");  // "ffma" | (default) tensor pipe
+    m->recur_tc = (renv && strcmp(renv, "ffma") == 0) ? 0 : ((renv && strcmp(renv, "fp16x1") == 0) ? 2 : 1);
     *handle = m;
     return OSB_OK;
 }
@@ -1210,6 +1400,7 @@ int osb_vad_destroy(void* handle) {
     float* ptrs[] = {m->basis, m->e1w, m->e1b, m->e2w, m->e2b, m->e3w, m->e3b, m->e4w, m->e4b, m->wih, m->bsum, m->whh, m->whh_perm, m->dw};
     for (float* p : ptrs) cudaFree(p);
     for (auto& t : m->tc) cudaFree(t.img);
+    cudaFree(m->whh_tc);
     vad_front_destroy(m->fused);
     delete m;
     return OSB_OK;
@@ -1219,6 +1410,13 @@ int osb_vad_set_gemm(void* handle, int use_tcgen05) {
     OSB_REQUIRE(handle, "null VAD handle");
     OSB_REQUIRE(use_tcgen05 >= 0 && use_tcgen05 <= 2, "mode must be 0 (FFMA), 1 (tcgen05 per layer) or 2 (fused tcgen05)");
     reinterpret_cast<VadModel*>(handle)->use_tc = use_tcgen05;
+    return OSB_OK;
+}
+
+int osb_vad_set_recurrence(void* handle, int tensor_pipe) {
+    OSB_REQUIRE(handle, "null VAD handle");
+    OSB_REQUIRE(tensor_pipe >= 0 && tensor_pipe <= 2, "mode must be 0 (FP32 FFMA kernels), 1 (tensor pipe, h as fp16 hi + lo) or 2 (tensor pipe, h as one fp16 plane)");
+    reinterpret_cast<VadModel*>(handle)->recur_tc = tensor_pipe;
     return OSB_OK;
 }
 

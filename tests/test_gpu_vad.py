@@ -187,6 +187,43 @@ def test_pipelined_chunks_match_serial(gpu, session, batch, monkeypatch):
     assert np.abs(res["1"][0][1] - o2).max() <= PROB_TOL
 
 
+@pytest.mark.parametrize("batch", [1, 8, 11])
+def test_tensor_pipe_recurrence_matches_ffma_and_oracle(gpu, session, batch):
+    """The shipped recurrence (mma.sync, W_hh as fp16 fragments in registers, h as fp16 hi + lo planes, eight streams per CTA) against the
+    FP32 FFMA recurrence kernels and the oracle: 60 s per stream, state carried over a second call, partly filled CTAs."""
+    import torch
+
+    pcm = np.stack([_audio(60.0, 900 + i) for i in range(min(batch, 3))])
+    pcm = np.stack([pcm[i % len(pcm)] for i in range(batch)])
+    n = pcm.shape[1]
+    n_win = n // 512
+    x = torch.from_numpy(pcm).cuda()
+    res = {}
+    try:
+        for mode in (0, 1, 2):
+            gpu.call("osb_vad_set_recurrence", session.handle, mode)
+            state = torch.zeros((batch, 2, 128), dtype=torch.float32, device="cuda")
+            probs = torch.full((2, batch, n_win), -1.0, dtype=torch.float32, device="cuda")
+            for k in range(2):
+                gpu.call("osb_vad_score_dev", session.handle, x.data_ptr(), gpu.FMT_PCM16, n, batch, n, state.data_ptr(), probs[k].data_ptr(), n_win,
+                         torch.cuda.current_stream().cuda_stream)
+            torch.cuda.synchronize()
+            res[mode] = (probs.cpu().numpy(), state.cpu().numpy())
+    finally:
+        gpu.call("osb_vad_set_recurrence", session.handle, 1)
+    for mode in (1, 2):  # 1: h as fp16 hi + lo (default), 2: h as one fp16 plane
+        d = float(np.abs(res[0][0] - res[mode][0]).max())
+        print(f"tensor-pipe (mode {mode}) vs FFMA recurrence, batch {batch}: max |dp| = {d:.2e}, max |dstate| = {float(np.abs(res[0][1] - res[mode][1]).max()):.2e}")
+        assert d <= 5e-4
+    net = ovad.SileroNet()
+    a = pcm[0].astype(np.float32) / 32768.0
+    o1, s1 = net.score_stream(a)
+    o2, _ = net.score_stream(a, s1)
+    assert np.abs(res[1][0][0][0] - o1).max() <= PROB_TOL and np.abs(res[1][0][1][0] - o2).max() <= PROB_TOL
+    for i in range(batch):  # the column a stream sits in is invisible
+        assert np.array_equal(res[1][0][:, i], res[1][0][:, i % 3 if batch >= 3 else 0])
+
+
 def test_tcgen05_fronts_match_ffma_and_oracle(gpu, session):
     """The fused persistent tcgen05 front (mode 2, the default) and the per-layer tcgen05 GEMMs (mode 1), both split-bf16, against
     the FP32 FFMA kernels (mode 0) and the oracle."""
