@@ -829,7 +829,7 @@ def main():
     ctx = Ctx()
     try:
         if args.workload == "vad":
-            print_sub(ctx, args, vad_run(ctx, args.clips or 256, 3600.0, max(1, args.steps // 3)), "f32 (bf16x3 tensor-core front)")
+            print_sub(ctx, args, vad_run(ctx, args.clips or 256, 3600.0, max(1, args.steps // 3)), "f32 (bf16x3 tcgen05 front; recurrence: fp16 W_hh x fp16 hi+lo h on mma.sync, f32 accumulate and cell)")
         elif args.workload == "realtime":
             print_sub(ctx, args, realtime_run(ctx, args.clips or 1024, 3000), "u8/f64")
         elif args.workload == "tts":

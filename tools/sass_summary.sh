@@ -3,7 +3,7 @@
 # usage: tools/sass_summary.sh > profiles/r02_sass_summary.txt
 LIB=open_speech_b200/libosb200.so
 echo "# cuobjdump -sass $LIB (sm_100a).  tcgen05.mma = UTCHMMA, tcgen05.ld = LDTM, tcgen05.commit = UTCBAR, cp.async.bulk (TMA unit) = UBLKCP,"
-echo "# mbarrier = SYNCS, packed FP32 (F32x2 column) = FFMA2 + FADD2 + FMUL2, FP64 = DFMA/DADD/DMUL, legacy tensor path = HMMA (must be 0 everywhere)"
+echo "# mbarrier = SYNCS, packed FP32 (F32x2 column) = FFMA2 + FADD2 + FMUL2, FP64 = DFMA/DADD/DMUL, warp-level MMA = HMMA (only k_vad_recur_tc, the eight-stream LSTM recurrence: DESIGN 4.5)"
 printf "%-58s %8s %6s %7s %7s %6s %6s %7s %6s %5s\n" kernel UTCHMMA LDTM UTCBAR UBLKCP SYNCS F32x2 FFMA F64 HMMA
 cuobjdump -sass $LIB | awk '
 /Function :/ { if (name != "") out(); name=$3; u=l=b=k=s=f2=f=d=h=0; next }
