@@ -6,6 +6,8 @@ speech-like audio with the oracle network (oracle/vad.py) and with each operand 
 and prints the largest probability error: the number the 1e-3 budget of BASELINE.json's north_star applies to.
 
     python tools/vad_precision_sim.py [seconds]
+    python tools/vad_precision_sim.py recur [seconds]     operand schemes of the tensor-pipe RECURRENCE (k_vad_recur_tc):
+                                                          the front stays float32, W_hh . h goes through rounded planes
 """
 import sys
 
@@ -75,7 +77,50 @@ MODES = {
 }
 
 
+RECUR_MODES = {  # (dtype, terms (W plane, h plane))
+    "f32": None,
+    "bf16 3-term (W_hi.h_hi + W_hi.h_lo + W_lo.h_hi)": (BF, ((0, 0), (0, 1), (1, 0))),
+    "fp16 3-term": (FP, ((0, 0), (0, 1), (1, 0))),
+    "fp16 W 1 plane, h 2 planes (2 MMAs)  [shipped]": (FP, ((0, 0), (0, 1))),
+    "fp16 W 2 planes, h 1 plane (2 MMAs)": (FP, ((0, 0), (1, 0))),
+    "bf16 W 1 plane, h 2 planes (2 MMAs)": (BF, ((0, 0), (0, 1))),
+    "fp16 1 plane each (1 MMA)  [OSB_VAD_RECUR=fp16x1]": (FP, ((0, 0),)),
+}
+
+
+def recur_main(secs):
+    net = ovad.SileroNet()
+    w = net.w
+    sig = ovad._sigmoid
+    worst = {k: 0.0 for k in RECUR_MODES}
+    for seed in (3, 11, 21):
+        a = synth.clip_pcm16(secs, seed=seed).astype(np.float32) / 32768.0
+        n_win = len(a) // 512
+        pre = net.front(a[: n_win * 512].reshape(n_win, 512))
+        ref = None
+        for name, m in RECUR_MODES.items():
+            h, c, p = np.zeros(128, np.float32), np.zeros(128, np.float32), np.zeros(n_win, np.float32)
+            wp = planes(w["lstm.weight_hh"], m[0], 2) if m else None
+            for t in range(n_win):
+                if m is None:
+                    g = pre[t] + w["lstm.weight_hh"] @ h
+                else:
+                    hp, acc = planes(h, m[0], 2), np.zeros(512, np.float32)
+                    for (i, j) in m[1]:
+                        acc += (wp[i] @ hp[j]).astype(np.float32)
+                    g = pre[t] + acc
+                c = (sig(g[128:256]) * c + sig(g[:128]) * np.tanh(g[256:384])).astype(np.float32)
+                h = (sig(g[384:]) * np.tanh(c)).astype(np.float32)
+                p[t] = sig(np.float32(np.dot(np.maximum(h, 0.0), w["dec.weight"]) + w["dec.bias"][0]))
+            ref = p if ref is None else ref
+            worst[name] = max(worst[name], float(np.abs(p - ref).max()))
+    for name in RECUR_MODES:
+        print(f"{name:52s} max |dprob| = {worst[name]:.2e}")
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "recur":
+        return recur_main(float(sys.argv[2]) if len(sys.argv) > 2 else 120.0)
     secs = float(sys.argv[1]) if len(sys.argv) > 1 else 120.0
     net = ovad.SileroNet()
     worst = {k: 0.0 for k in MODES}
