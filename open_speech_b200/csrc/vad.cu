@@ -1162,7 +1162,7 @@ static int vad_score(VadModel* m, const void* d_audio, int fmt, int64_t n, int64
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_vad_recur_mb<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, RecurMbCfg<4>::smem);
         return e;
     }));
-    // streams per recurrence CTA: as few as keep the grid within one wave of SMs
+    // FP32 kernels (cross-check mode), streams per recurrence CTA: as few as keep the grid within one wave of SMs
     // shared_gpu (the composed chain runs its feature branch beside this one, stt_pipeline.cu): four streams per CTA from 75 streams on.
     // A recurrence CTA owns its SM (the whole register file) and is bound by the latency of its serial chain, so a wider CTA costs the
     // VAD branch time but hands the SMs it vacates to kernels that can fill them.
@@ -1172,8 +1172,9 @@ static int vad_score(VadModel* m, const void* d_audio, int fmt, int64_t n, int64
     if (rtc) rs = kTcStreams;  // the tensor-pipe kernel: always eight streams per CTA
     // Pipelined chunks (fused front, more than one chunk, the GPU to ourselves): the front of chunk i + 1 runs on a side stream BESIDE the
     // recurrence of chunk i, on the SMs the recurrence leaves free (neither kernel shares an SM: 227 KB of shared memory each), into the
-    // other half of a double-buffered `pre`.  The recurrence is the serial chain, so it gets as few SMs as keep it in one wave with at
-    // least kFrontMinSms left over: 256 streams -> four per CTA on 64 SMs, front on 84.
+    // other half of a double-buffered `pre`.  The tensor-pipe recurrence takes one SM per eight streams (256 streams: 32 SMs, the
+    // front on the other 116: 139 ms per 256 x 1 h instead of 223 in series); the FP32 kernels get as few SMs as keep them in one
+    // wave with at least kFrontMinSms left over (256 streams: three per CTA on 86 SMs, front on 62).
     constexpr int kFrontMinSms = 48;
     bool pipelined = false;
     if (fused && !shared_gpu && n_win > T && pipeline_enabled()) {
