@@ -948,12 +948,19 @@ __global__ void __launch_bounds__(32) k_vad_segment(const float* __restrict__ pr
     int* out = segs + (long long)b * max_seg * 2;
     bool in_speech = false;
     int speech_start = 0, silence_count = 0, speech_windows = 0, nseg = 0;
+    float v = lane < n_win ? p[lane] : 0.f;
     for (long long base = 0; base < n_win; base += 32) {
         const long long k = base + lane;
-        const bool sp = (k < n_win) && (p[k] >= thr);
+        const bool sp = (k < n_win) && (v >= thr);
+        v = (k + 32 < n_win) ? p[k + 32] : 0.f;  // the next word's probabilities are in flight while lane 0 walks this one
         const unsigned mask = __ballot_sync(0xffffffffu, sp);
         if (lane == 0) {
             const int lim = (int)((n_win - base) < 32 ? (n_win - base) : 32);
+            const unsigned full = lim == 32 ? 0xffffffffu : ((1u << lim) - 1u);
+            // whole-word fast paths (the machine's state after the word is the same as after walking its bits): silence outside
+            // speech changes nothing, speech inside speech only counts
+            if (mask == 0u && !in_speech) continue;
+            if (mask == full && in_speech) { silence_count = 0; speech_windows += lim; continue; }
             for (int i = 0; i < lim; ++i) {
                 const int cur_ms = (int)(((base + i) * kWin * 1000) / 16000);
                 if ((mask >> i) & 1u) {
