@@ -1106,8 +1106,17 @@ static bool pipeline_enabled() {  // read per call: a test (and the bench's A/B 
 // per-thread side stream + events of the pipelined chunks (created once per device)
 struct FrontSide {
     cudaStream_t front = nullptr;
-    cudaEvent_t start = nullptr, front_done[2] = {nullptr, nullptr}, recur_done[2] = {nullptr, nullptr};
+    cudaEvent_t start = nullptr, joined = nullptr, front_done[2] = {nullptr, nullptr}, recur_done[2] = {nullptr, nullptr};
     int device = -1;
+};
+// Joins the side stream into the caller's stream when vad_score leaves, on the error paths too: declared behind the Scratch, so it runs
+// before the scratch buffers are handed back on the caller's stream and nothing on the side stream can outlive them.
+struct FrontJoin {
+    FrontSide* fs = nullptr;
+    cudaStream_t st = nullptr;
+    ~FrontJoin() {
+        if (fs && cudaEventRecord(fs->joined, fs->front) == cudaSuccess) cudaStreamWaitEvent(st, fs->joined, 0);
+    }
 };
 static int front_side(FrontSide** out) {
     static thread_local FrontSide s;
@@ -1116,11 +1125,11 @@ static int front_side(FrontSide** out) {
     if (s.device != dev) {
         if (s.front) {
             cudaStreamDestroy(s.front);
-            for (cudaEvent_t e : {s.start, s.front_done[0], s.front_done[1], s.recur_done[0], s.recur_done[1]}) cudaEventDestroy(e);
+            for (cudaEvent_t e : {s.start, s.joined, s.front_done[0], s.front_done[1], s.recur_done[0], s.recur_done[1]}) cudaEventDestroy(e);
             s = FrontSide{};
         }
         OSB_CUDA(cudaStreamCreateWithFlags(&s.front, cudaStreamNonBlocking));
-        for (cudaEvent_t* e : {&s.start, &s.front_done[0], &s.front_done[1], &s.recur_done[0], &s.recur_done[1]})
+        for (cudaEvent_t* e : {&s.start, &s.joined, &s.front_done[0], &s.front_done[1], &s.recur_done[0], &s.recur_done[1]})
             OSB_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
         s.device = dev;
     }
@@ -1195,9 +1204,12 @@ static int vad_score(VadModel* m, const void* d_audio, int fmt, int64_t n, int64
     const size_t pre_floats = (size_t)((W + 127) / 128) * 128 * kGates + 64;  // whole 128-window tiles (the fused front's tiled layout)
     OSB_CUDA(scr.alloc(&pre, pre_floats * (pipelined ? 2 : 1)));
     FrontSide* fs = nullptr;
+    FrontJoin join;
     int rc;
     if (pipelined) {
         if ((rc = front_side(&fs))) return rc;
+        join.fs = fs;
+        join.st = st;
         OSB_CUDA(cudaEventRecord(fs->start, st));  // the audio and `pre` exist on st from here on
         OSB_CUDA(cudaStreamWaitEvent(fs->front, fs->start, 0));
     }
