@@ -17,6 +17,11 @@ void set_error(const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 int ensure_init();          // lazy osb_init(current device)
 int num_sms();              // queried once; 148 on B200
+// One-shot hint of the calling thread for the NEXT persistent launches that ask: "only this many SMs are free for your first wave" (a
+// concurrently running kernel holds the others).  A persistent kernel whose CTAs take a static share of the tiles must not launch more
+// CTAs than can be resident at once: the ones that wait start when the first ones END, and the kernel takes up to twice as long.
+void set_sm_budget(int sms, int launches = 1);  // the hint holds for the next `launches` persistent launches that ask; 0 clears
+int take_sm_budget();                           // the hint (one use taken), or num_sms() when none is set
 void count_launch();        // osb_launch_count bookkeeping
 bool prof_on();             // osb_profile_enable: per-kernel CUDA-event timing on the launching stream
 void prof_begin(const char* name, cudaStream_t st);
@@ -121,6 +126,7 @@ int launch_normalize_f32(const float* d_in, void* d_out, int out_pcm16, long lon
 
 // vad.cu: batched scoring (state [batch][2][128] in/out) and the integer segmenter, for the composed paths
 // front_done (optional): recorded on st after the first chunk's front kernel(s); shared_gpu: another branch runs beside the recurrence
+int vad_recurrence_sms(void* handle, long long batch);
 int launch_vad_score(void* handle, const void* d_audio, int fmt, long long n, long long batch, long long stride, float* d_state,
                      float* d_probs, long long probs_stride, cudaStream_t st, cudaEvent_t front_done = nullptr, bool shared_gpu = false);
 int launch_vad_segments(const float* d_probs, long long probs_stride, long long n_win, long long batch, long long n_samples, float thr,

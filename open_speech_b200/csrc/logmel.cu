@@ -632,13 +632,13 @@ int launch_logmel(const void* d_audio, int fmt, long long n, long long batch, lo
     const int total_tiles = (int)total_tiles_ll;
     if (fmt == OSB_FMT_PCM16 || a.requant) {
         // integer-staged kernel: 3 resident CTAs per SM (70 KB of shared memory, 80 registers)
-        const int persistent = 3 * num_sms();
+        const int persistent = 3 * take_sm_budget();
         const int grid = total_tiles < persistent ? total_tiles : persistent;
         if (fmt == OSB_FMT_PCM16) OSB_LAUNCH(k_logmel16<false>, grid, 256, kLm16Smem, st, a, tiles_per_clip, total_tiles);
         else OSB_LAUNCH(k_logmel16<true>, grid, 256, kLm16Smem, st, a, tiles_per_clip, total_tiles);
     } else {
         // float32 audio taken as it is: float staging, 2 resident CTAs per SM (108 KB of shared memory)
-        const int persistent = 2 * num_sms();
+        const int persistent = 2 * take_sm_budget();
         const int grid = total_tiles < persistent ? total_tiles : persistent;
         OSB_LAUNCH(k_logmel<true>, grid, 256, kLogmelSmemF32, st, a, tiles_per_clip, total_tiles);
     }

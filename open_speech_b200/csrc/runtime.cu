@@ -72,6 +72,17 @@ int num_sms() {
     return v > 0 ? v : OSB_NUM_SMS;
 }
 
+static thread_local int t_sm_budget = 0, t_sm_budget_uses = 0;
+void set_sm_budget(int sms, int launches) {
+    t_sm_budget = (sms > 0 && launches > 0) ? sms : 0;
+    t_sm_budget_uses = t_sm_budget ? launches : 0;
+}
+int take_sm_budget() {
+    const int n = num_sms(), b = t_sm_budget;
+    if (t_sm_budget_uses > 0 && --t_sm_budget_uses == 0) t_sm_budget = 0;
+    return (b > 0 && b < n) ? b : n;
+}
+
 int ensure_init() {
     if (t_device >= 0) return OSB_OK;
     int dev = 0;

@@ -862,7 +862,7 @@ int launch_spectral_gate(const void* d_audio, int fmt, long long n, long long ba
         const long long n_rows = (long long)gb * g.n_chunks;
         {
             const long long total_tiles = (long long)NT * g.n_chunks * gb;
-            const long long persistent = 2ll * num_sms();  // 2 resident CTAs per SM (109 KB of shared memory each)
+            const long long persistent = 2ll * take_sm_budget();  // 2 resident CTAs per SM (109 KB of shared memory each) on the SMs that are free
             NrAgg ag;
             for (int k = 0; k < kStftFrames; ++k) ag.bb[k] = b * b * std::pow(1.0 - b, (double)k);
             OSB_LAUNCH(k_nr_stft, (unsigned)(total_tiles < persistent ? total_tiles : persistent), 256, kStftSmem, st, (const void*)in, g, tabs,
@@ -877,7 +877,7 @@ int launch_spectral_gate(const void* d_audio, int fmt, long long n, long long ba
         OSB_CHECK_LAUNCH();
         {
             const long long total_tiles = (long long)tiles * g.n_chunks * gb;
-            const long long persistent = 2ll * num_sms();  // 2 resident CTAs per SM (110 KB of shared memory each)
+            const long long persistent = 2ll * take_sm_budget();  // 2 resident CTAs per SM (110 KB of shared memory each) on the SMs that are free
             OSB_LAUNCH(k_nr_istft, (unsigned)(total_tiles < persistent ? total_tiles : persistent), 256, kIstftSmem, st, S, Msm, g, tabs, j_first,
                        tiles, outp, d_sumsq ? d_sumsq + c0 : (double*)nullptr);
         }

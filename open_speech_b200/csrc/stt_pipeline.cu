@@ -150,7 +150,14 @@ static int stt_full(void* vad, const void* d_in, int in_fmt, int from_rate, long
             // (on failure `forked` may not have been recorded: the feature branch is then simply not started)
             if (!rc) {
                 OSB_CUDA(cudaStreamWaitEvent(sd->feat, sd->forked, 0));
+                // the recurrence holds its SMs for about as long as the branch's first persistent kernel runs: that kernel is sized for
+                // the others (256 x 60 s: the STFT beside the recurrence 2.93 -> 2.3 ms; it takes 1.77 ms with the GPU to itself)
+                static const bool budget_ok = [] { const char* e = getenv("OSB_STT_FULL_BUDGET"); return !(e && e[0] == '0'); }();
+                // (both scale with the clip length; with fewer clips the recurrence outlasts the inverse STFT's and the log-mel kernel's
+                // start as well: measured shares of the chain at 256 clips -- the launch order is STFT, inverse STFT, log-mel)
+                if (budget_ok) set_sm_budget(num_sms() - vad_recurrence_sms(vad, batch), noise_reduce ? 1 + (batch < 146) + (batch < 90) : 1);
                 rc = stt_frontend(pcm, n16, batch, stride16, 16000, noise_reduce, normalize, n_mels, d_mel, sd->feat);
+                set_sm_budget(0);
                 cudaEventRecord(sd->feat_done, sd->feat);  // join even when a launch failed: st must not run ahead of the side streams
                 cudaStreamWaitEvent(st, sd->feat_done, 0);
             }

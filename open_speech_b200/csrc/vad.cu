@@ -1310,6 +1310,18 @@ int launch_vad_score(void* handle, const void* d_audio, int fmt, long long n, lo
     if (!handle) { set_error("invalid argument: null VAD handle"); return OSB_ERR_INVALID_ARG; }
     return vad_score(reinterpret_cast<VadModel*>(handle), d_audio, fmt, n, batch, stride, d_state, d_probs, probs_stride, st, front_done, shared_gpu);
 }
+// SMs the recurrence of `batch` streams holds while it runs beside other kernels (stt_pipeline.cu sizes the first feature kernel by it)
+int vad_recurrence_sms(void* handle, long long batch) {
+    if (!handle || batch <= 0) return 0;
+    const VadModel* m = reinterpret_cast<const VadModel*>(handle);
+    int rs = kTcStreams;
+    if (!m->recur_tc) {
+        rs = batch <= OSB_NUM_SMS ? 1 : (batch <= 2 * OSB_NUM_SMS ? 2 : 4);
+        if (batch > OSB_NUM_SMS / 2) rs = share_width();
+    }
+    const long long ctas = (batch + rs - 1) / rs;
+    return (int)(ctas < OSB_NUM_SMS ? ctas : OSB_NUM_SMS);
+}
 int launch_vad_segments(const float* d_probs, long long probs_stride, long long n_win, long long batch, long long n_samples, float thr,
                         int min_speech_ms, int silence_ms, int32_t* d_segs, int32_t* d_counts, int max_seg, cudaStream_t st) {
     return vad_segments(d_probs, probs_stride, n_win, batch, n_samples, thr, min_speech_ms, silence_ms, d_segs, d_counts, max_seg, st);
